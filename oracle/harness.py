@@ -1,0 +1,109 @@
+"""TEST INFRASTRUCTURE (CPU oracle) -- never imported by the product.
+
+Drives envs built with the reference plugin API (real reference or phantom_oracle) under
+the counter-based RNG contract and records tensor traces in the layout the C-ABI uses
+([env, strategic_agent, ...]), so that tests can compare them with the CUDA path.
+"""
+from __future__ import annotations
+
+import contextlib
+from typing import Any, Callable, Dict, List, Optional, Sequence
+
+import numpy as np
+
+from . import rng
+
+
+class EpisodeClock:
+    """Keeps the (episode, step) coordinates of every RNG stream of one env in sync with
+    the env's own clock."""
+
+    def __init__(self, streams: Sequence[rng.StepStream]):
+        self.streams = list(streams)
+        self.episode = -1
+
+    def on_reset(self) -> None:
+        self.episode += 1
+        for s in self.streams:
+            s.begin(self.episode, 0)
+
+    def on_step(self, env) -> None:
+        for s in self.streams:
+            s.begin(self.episode, env.current_step + 1)
+
+
+@contextlib.contextmanager
+def patched_np_randint(stream: rng.StepStream):
+    """Route `np.random.randint(n)` (the reference example's call site,
+    supply_chain.py:64) to the contract stream while the block runs."""
+    orig = np.random.randint
+    np.random.randint = lambda n, *a, **k: stream.randint(n)
+    try:
+        yield
+    finally:
+        np.random.randint = orig
+
+
+def tracked_to_rows(tracked, slot_of: Dict[Any, int], type_of: Callable[[Any], int],
+                    value_of: Callable[[Any], Sequence[float]]) -> np.ndarray:
+    """Flatten Resolver.tracked_messages to rows (sender_slot, recv_slot, type, v0, v1)."""
+    rows = []
+    for m in tracked:
+        v = list(value_of(m.payload)) + [0.0, 0.0]
+        rows.append((slot_of[m.sender_id], slot_of[m.receiver_id], type_of(m.payload), v[0], v[1]))
+    return np.asarray(rows, dtype=np.float64).reshape(-1, 5)
+
+
+def run_supply_chain(env, clock: EpisodeClock, actions: np.ndarray,
+                     action_mask: Optional[np.ndarray] = None,
+                     stream_ctx=contextlib.nullcontext, track: bool = False) -> Dict[str, np.ndarray]:
+    """Run `actions.shape[0]` episodes of `actions.shape[1]` steps on one supply-chain env.
+
+    actions: f32 [n_ep, T, 1]; action_mask: u8 [n_ep, T] (0 => SHOP absent from `actions`,
+    which makes env.py:330-333 fall back to generate_messages()).
+    """
+    from .workloads import supply_chain as wl
+
+    n_ep, T = actions.shape[:2]
+    out = {
+        "reset_obs": np.zeros((n_ep, 3), np.float32),
+        "obs": np.zeros((n_ep, T, 3), np.float32),
+        "reward": np.zeros((n_ep, T), np.float64),
+        "term": np.zeros((n_ep, T), np.uint8),
+        "trunc": np.zeros((n_ep, T), np.uint8),
+        "all_term": np.zeros((n_ep, T), np.uint8),
+        "all_trunc": np.zeros((n_ep, T), np.uint8),
+        "state": np.zeros((n_ep, T, 4), np.int64),
+    }
+    msgs: List[np.ndarray] = []
+    slot_of = {aid: i for i, aid in enumerate(env.agent_ids)}
+    with stream_ctx():
+        for ep in range(n_ep):
+            clock.on_reset()
+            obs, _ = env.reset()
+            out["reset_obs"][ep] = obs["SHOP"]
+            for t in range(T):
+                clock.on_step(env)
+                acts = {}
+                if action_mask is None or action_mask[ep, t]:
+                    acts["SHOP"] = actions[ep, t]
+                if track:
+                    env.network.resolver.clear_tracked_messages()
+                step = env.step(acts)
+                out["obs"][ep, t] = step.observations["SHOP"]
+                out["reward"][ep, t] = step.rewards["SHOP"]
+                out["term"][ep, t] = step.terminations["SHOP"]
+                out["trunc"][ep, t] = step.truncations["SHOP"]
+                out["all_term"][ep, t] = step.terminations["__all__"]
+                out["all_trunc"][ep, t] = step.truncations["__all__"]
+                out["state"][ep, t] = wl.shop_state(env)
+                if track:
+                    rows = tracked_to_rows(
+                        env.network.resolver.tracked_messages, slot_of,
+                        lambda p: wl.PAYLOAD_TYPE_IDS[type(p).__name__],
+                        lambda p: (p.size,))
+                    hdr = np.tile(np.array([[ep, t]], np.float64), (len(rows), 1))
+                    msgs.append(np.concatenate([hdr, rows], axis=1))
+    if track:
+        out["messages"] = np.concatenate(msgs, axis=0) if msgs else np.zeros((0, 7))
+    return out

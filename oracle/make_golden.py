@@ -1,0 +1,79 @@
+"""TEST INFRASTRUCTURE.  Generates tests/golden/*.npz from the UNMODIFIED reference.
+
+Only runs in the build container (needs /root/reference, imported through
+oracle/ref_shim.py).  The committed fixtures are what the oracle restatement and the CUDA
+path are compared against where the reference is not available (GPU box).
+
+    python -m oracle.make_golden
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+
+from . import harness, ref_shim, rng
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(REPO, "tests", "golden")
+
+
+def supply_chain_actions(n_env: int, n_ep: int, T: int, seed: int = 123):
+    """Actions covering the quirks of SURVEY.md 7.2-H6: in-range uniforms, exact
+    integers, exact halves (round-half-even), values above max stock, negatives,
+    tiny values, and steps where the shop supplies no action at all."""
+    r = np.random.RandomState(seed)
+    a = r.uniform(0, 100, size=(n_env, n_ep, T, 1)).astype(np.float32)
+    mask = np.ones((n_env, n_ep, T), np.uint8)
+    kinds = r.randint(0, 12, size=(n_env, n_ep, T))
+    a[kinds == 0] = np.floor(a[kinds == 0])                      # exact integers
+    a[kinds == 1] = np.floor(a[kinds == 1]) + np.float32(0.5)    # ties -> even
+    a[kinds == 2] = a[kinds == 2] * np.float32(3.0)              # above max stock
+    if n_env > 4:
+        a[4:][kinds[4:] == 3] *= np.float32(-0.25)               # negative requests
+        mask[5:][kinds[5:] == 4] = 0                             # action missing
+    a[kinds == 5] *= np.float32(1e-3)
+    return a, mask
+
+
+def gen_supply_chain_reference() -> None:
+    """The reference's own example file, RNG call site patched to the contract."""
+    sc = ref_shim.import_reference_supply_chain()
+    seed, n_env, n_ep, T = 20261017, 12, 2, 100
+    actions, mask = supply_chain_actions(n_env, n_ep, T)
+    keys = None
+    per_env = []
+    for e in range(n_env):
+        stream = rng.StepStream(seed, e, 0)
+        env = sc.SupplyChainEnv()
+        env.network.resolver.enable_tracking = e < 3
+        clock = harness.EpisodeClock([stream])
+        tr = harness.run_supply_chain(
+            env, clock, actions[e], mask[e],
+            stream_ctx=lambda s=stream: harness.patched_np_randint(s), track=e < 3)
+        per_env.append(tr)
+        keys = keys or [k for k in tr if k != "messages"]
+    out = {k: np.stack([t[k] for t in per_env]) for k in keys}
+    rows = []
+    for e in range(3):
+        m = per_env[e]["messages"]
+        rows.append(np.concatenate([np.full((len(m), 1), e, np.float64), m], axis=1))
+    out["messages"] = np.concatenate(rows)  # (env, ep, t, sender, recv, type, v0, v1)
+    out["actions"], out["action_mask"] = actions, mask
+    out["seed"] = np.int64(seed)
+    np.savez_compressed(os.path.join(GOLDEN, "supply_chain_reference.npz"), **out)
+    print("supply_chain_reference.npz:", {k: v.shape for k, v in out.items()})
+
+
+def main() -> int:
+    if not ref_shim.reference_available():
+        print("reference not available")
+        return 2
+    os.makedirs(GOLDEN, exist_ok=True)
+    gen_supply_chain_reference()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,149 @@
+"""TEST INFRASTRUCTURE (CPU oracle) -- never imported by the product.
+
+The counter-based RNG contract shared by the oracle and the CUDA kernels
+(device twin: phantom_b200/csrc/phx_rng.cuh).
+
+The reference draws from process-global generators (`np.random.randint` at
+examples/environments/supply_chain/supply_chain.py:64, `np.random.shuffle` at
+phantom/resolvers.py:151, ...), which cannot be reproduced across 65 536
+concurrently stepped envs.  "Identical seeds" therefore means: both sides consume the
+same stateless stream
+
+    u32(seed, env, episode, step, stream, idx) =
+        Philox4x32-10( key = (seed & 0xffffffff, seed >> 32),
+                       ctr = (env, episode, step, (stream << 16) | (idx >> 2)) )[idx & 3]
+
+  env     global env index (independent of how envs are sharded over GPUs)
+  episode number of resets this env has seen minus one (0 for the first episode)
+  step    PhantomEnv.current_step *after* the increment at the top of step()
+          (env.py:252), i.e. 1..num_steps; 0 is used for draws made during reset()
+  stream  draw-site id chosen by the workload (one per distinct RNG call site)
+  idx     index of the draw within that site and step (e.g. the customer index)
+
+Derived distributions:
+  randint(n)  := (u32 * n) >> 32          (multiply-shift; replaces np.random.randint(n))
+  uniform01() := (u32 >> 8) * 2**-24      (float32-exact, in [0, 1))
+
+Philox4x32-10 is Salmon et al., "Parallel random numbers: as easy as 1, 2, 3" (SC'11),
+with the standard Random123 constants; checked below against the Random123 known-answer
+vectors.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+M0 = 0xD2511F53
+M1 = 0xCD9E8D57
+W0 = 0x9E3779B9
+W1 = 0xBB67AE85
+MASK = 0xFFFFFFFF
+
+
+def philox4x32(ctr, key, rounds: int = 10):
+    """Scalar Philox4x32 on Python ints. ctr = 4 x u32, key = 2 x u32."""
+    c0, c1, c2, c3 = (int(c) & MASK for c in ctr)
+    k0, k1 = (int(k) & MASK for k in key)
+    for _ in range(rounds):
+        p0 = M0 * c0
+        p1 = M1 * c2
+        c0, c1, c2, c3 = (
+            ((p1 >> 32) ^ c1 ^ k0) & MASK,
+            p1 & MASK,
+            ((p0 >> 32) ^ c3 ^ k1) & MASK,
+            p0 & MASK,
+        )
+        k0 = (k0 + W0) & MASK
+        k1 = (k1 + W1) & MASK
+    return c0, c1, c2, c3
+
+
+def philox4x32_np(c0, c1, c2, c3, k0, k1, rounds: int = 10):
+    """Vectorised Philox4x32 over numpy uint32 arrays (broadcasting)."""
+    c0, c1, c2, c3, k0, k1 = (
+        np.asarray(x).astype(np.uint64) & MASK for x in (c0, c1, c2, c3, k0, k1)
+    )
+    c0, c1, c2, c3, k0, k1 = np.broadcast_arrays(c0, c1, c2, c3, k0, k1)
+    for _ in range(rounds):
+        p0 = np.uint64(M0) * c0
+        p1 = np.uint64(M1) * c2
+        c0, c1, c2, c3 = (
+            ((p1 >> np.uint64(32)) ^ c1 ^ k0) & np.uint64(MASK),
+            p1 & np.uint64(MASK),
+            ((p0 >> np.uint64(32)) ^ c3 ^ k1) & np.uint64(MASK),
+            p0 & np.uint64(MASK),
+        )
+        k0 = (k0 + np.uint64(W0)) & np.uint64(MASK)
+        k1 = (k1 + np.uint64(W1)) & np.uint64(MASK)
+    return tuple(x.astype(np.uint32) for x in (c0, c1, c2, c3))
+
+
+# ------------------------------------------------------------------ the contract proper
+def u32(seed: int, env: int, episode: int, step: int, stream: int, idx: int) -> int:
+    words = philox4x32(
+        (env, episode, step, ((stream & 0xFFFF) << 16) | ((idx >> 2) & 0xFFFF)),
+        (seed & MASK, (seed >> 32) & MASK),
+    )
+    return words[idx & 3]
+
+
+def u32_np(seed: int, env, episode, step, stream: int, idx):
+    """Vectorised contract draw; env/episode/step/idx broadcast against each other."""
+    idx = np.asarray(idx, dtype=np.int64)
+    c3 = ((stream & 0xFFFF) << 16) | ((idx >> 2) & 0xFFFF)
+    w = philox4x32_np(env, episode, step, c3, seed & MASK, (seed >> 32) & MASK)
+    sel = np.broadcast_to(idx & 3, w[0].shape)
+    return np.choose(sel, w).astype(np.uint32)
+
+
+def randint(n: int, word: int) -> int:
+    return (int(word) * int(n)) >> 32
+
+
+def randint_np(n: int, words) -> np.ndarray:
+    return ((np.asarray(words).astype(np.uint64) * np.uint64(n)) >> np.uint64(32)).astype(np.int32)
+
+
+def uniform01(word: int) -> float:
+    return float(np.float32(int(word) >> 8) * np.float32(2.0**-24))
+
+
+def uniform01_np(words) -> np.ndarray:
+    return (np.asarray(words, dtype=np.uint32) >> np.uint32(8)).astype(np.float32) * np.float32(2.0**-24)
+
+
+# Random123 known-answer vectors for philox4x32-10 (kat_vectors in the Random123
+# distribution): (counter, key) -> output.
+KAT = [
+    ((0x00000000,) * 4, (0x00000000,) * 2,
+     (0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8)),
+    ((0xFFFFFFFF,) * 4, (0xFFFFFFFF,) * 2,
+     (0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD)),
+    ((0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344), (0xA4093822, 0x299F31D0),
+     (0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1)),
+]
+
+
+class StepStream:
+    """Sequential view of one (env, episode, step, stream): the k-th call gets idx=k.
+
+    Used to patch the reference's global RNG call sites: within one env step the
+    reference consumes its generator sequentially, so "k-th call at this site during
+    this step" is well defined (for supply chain, k == customer index because customers
+    draw in agent order, env.py:324 / supply_chain.py:64)."""
+
+    def __init__(self, seed: int, env: int, stream: int):
+        self.seed, self.env, self.stream = seed, env, stream
+        self.episode = 0
+        self.step = 0
+        self.k = 0
+
+    def begin(self, episode: int, step: int) -> None:
+        self.episode, self.step, self.k = episode, step, 0
+
+    def next_u32(self) -> int:
+        w = u32(self.seed, self.env, self.episode, self.step, self.stream, self.k)
+        self.k += 1
+        return w
+
+    def randint(self, n: int) -> int:
+        return randint(n, self.next_u32())

@@ -1,0 +1,111 @@
+"""Oracle vs fixtures generated from the UNMODIFIED reference (oracle/make_golden.py).
+
+CPU only.  These are what make the oracle trustworthy as the checker of the CUDA path."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle.phantom_oracle as po
+from oracle import harness, rng, vectorised
+from oracle.workloads import supply_chain as wl
+
+STEP_KEYS = ["obs", "reward", "term", "trunc", "all_term", "all_trunc", "state"]
+
+
+@pytest.fixture(scope="module")
+def sc_golden(golden_dir):
+    return np.load(os.path.join(golden_dir, "supply_chain_reference.npz"))
+
+
+def test_philox_known_answers():
+    # Random123 kat_vectors, philox4x32-10
+    for ctr, key, want in rng.KAT:
+        assert rng.philox4x32(ctr, key) == want
+        got = rng.philox4x32_np(*[np.array([c]) for c in ctr], *[np.array([k]) for k in key])
+        assert tuple(int(x[0]) for x in got) == want
+
+
+def test_contract_scalar_equals_vectorised():
+    env = np.arange(50)
+    for idx in (0, 3, 4, 9):
+        v = rng.u32_np(77, env, 2, 13, 1, idx)
+        s = [rng.u32(77, int(e), 2, 13, 1, idx) for e in env]
+        assert v.tolist() == s
+    assert all(0 <= rng.randint(5, w) < 5 for w in (0, 1, 2**31, 2**32 - 1))
+
+
+def test_survey_probe_trace():
+    """SURVEY.md 3.6 / 8c probe: np.random.seed(0) orders (4,0,3,3,3 then ...) are not
+    reproducible under the contract stream, but the dynamics are: feed the same orders."""
+
+    class Fixed:
+        def __init__(self, seq):
+            self.seq = list(seq)
+
+        def randint(self, n):
+            return self.seq.pop(0)
+
+    # orders drawn by the reference with np.random.seed(0): 4,0,3,3,3 | 1,3,2,4,0 | 0,4,2,1,0
+    st = Fixed([4, 0, 3, 3, 3, 1, 3, 2, 4, 0, 0, 4, 2, 1, 0])
+    env = wl.build(po, st)
+    env.reset()
+    s = env.step({"SHOP": np.array([69.64692], np.float32)})
+    assert s.observations["SHOP"].tolist() == np.array([0.70, 0.0, 0.52], np.float32).tolist()
+    assert s.rewards["SHOP"] == -7.0
+    s = env.step({"SHOP": np.array([28.613934], np.float32)})
+    assert s.observations["SHOP"].tolist() == np.array([0.89, 0.40, 0.0], np.float32).tolist()
+    assert s.rewards["SHOP"] == 1.0999999999999996
+    s = env.step({"SHOP": np.array([22.685144], np.float32)})
+    assert s.observations["SHOP"].tolist() == np.array([0.93, 0.28, 0.0], np.float32).tolist()
+    assert s.rewards["SHOP"] == -2.3000000000000007
+
+
+def test_object_oracle_matches_reference_golden(sc_golden):
+    g = sc_golden
+    seed, A, M = int(g["seed"]), g["actions"], g["action_mask"]
+    for e in range(A.shape[0]):
+        st = rng.StepStream(seed, e, wl.STREAM_CUSTOMER_ORDER)
+        env = wl.build(po, st, enable_tracking=e < 3)
+        tr = harness.run_supply_chain(env, harness.EpisodeClock([st]), A[e], M[e], track=e < 3)
+        for k in ["reset_obs"] + STEP_KEYS:
+            assert np.array_equal(tr[k], g[k][e]), (e, k)
+        if e < 3:  # exact global message order == Resolver.tracked_messages of the reference
+            gm = g["messages"]
+            assert np.array_equal(tr["messages"], gm[gm[:, 0] == e][:, 1:])
+
+
+def test_vectorised_oracle_matches_reference_golden(sc_golden):
+    g = sc_golden
+    seed, A, M = int(g["seed"]), g["actions"], g["action_mask"]
+    v = vectorised.SupplyChainVec(A.shape[0], seed)
+    for ep in range(A.shape[1]):
+        assert np.array_equal(v.reset(), g["reset_obs"][:, ep])
+        for t in range(A.shape[2]):
+            s = v.step(A[:, ep, t], M[:, ep, t])
+            for k in STEP_KEYS:
+                assert np.array_equal(s[k], g[k][:, ep, t]), (ep, t, k)
+
+
+def test_golden_covers_quirks(sc_golden):
+    g = sc_golden
+    assert (g["state"][..., 0] < 0).any(), "negative stock (no lower clamp) not exercised"
+    assert (g["action_mask"] == 0).any(), "missing-action fallback not exercised"
+    a = g["actions"][..., 0]
+    assert ((a - np.floor(a)) == 0.5).any(), "round-half-even not exercised"
+    assert (g["reset_obs"][:, 1, 1:] != 0).any(), "sales/missed carry-over across reset not exercised"
+    assert g["all_trunc"][:, :, -1].all() and not g["all_trunc"][:, :, :-1].any()
+
+
+def test_pinned_record(golden_dir):
+    """oracle/pin_against_reference.py ran the reference's own hot-path tests against the
+    reference (through the shim) and against the oracle; both must have been green, and
+    the oracle must not have changed since."""
+    from oracle import pin_against_reference as pin
+
+    rec = json.load(open(os.path.join(golden_dir, "PINNED.json")))
+    assert rec["reference"]["returncode"] == 0 and rec["oracle"]["returncode"] == 0
+    assert rec["oracle"]["counts"]["passed"] == rec["reference"]["counts"]["passed"] >= 64
+    assert rec["oracle_sha256"] == pin.oracle_fingerprint(), (
+        "oracle/phantom_oracle changed: re-run `python -m oracle.pin_against_reference`")
