@@ -1,0 +1,243 @@
+/* phx.h -- C ABI of libphx: the B200-native batched env-step engine.
+ *
+ * This is the drop-in boundary for the data-parallel hot path of jpmorganchase/Phantom
+ * (reference @ 9ce42f2, v2.2.0).  The reference has no FFI: its boundary is the Python
+ * plugin API, and one call of `PhantomEnv.step` advances ONE env object
+ * (phantom/env.py:239-303).  Each entry point below replaces that call (and the Python
+ * list-of-envs loops around it, phantom/utils/rllib/rollout.py:289-363) for a whole batch
+ * of independent env instances whose state lives in HBM.
+ *
+ * Conventions
+ *   - plain C, no torch types; every buffer is a raw pointer + an implied shape.
+ *   - "device pointer" = CUDA device memory on the handle's device, contiguous, aligned to
+ *     16 bytes; the caller owns every I/O buffer (a torch tensor's data_ptr()).
+ *   - E = num_envs of the handle, S = spec.n_strategic, A = spec.act_dim, O = spec.obs_dim.
+ *   - all work is ordered on `stream` (a cudaStream_t passed as void*); no entry point
+ *     synchronises the host except the *_host variants, phx_get_field, phx_poll_errors,
+ *     phx_get_trace and phx_destroy.
+ *   - every int-returning function returns PHX_OK (0) or a negative phx_status; the
+ *     message for the last failure on the calling thread is phx_last_error().
+ *   - device-side faults (the reference's exceptions raised from inside step()) never abort
+ *     a kernel: they are recorded in a sticky per-env error word (first code wins) and
+ *     collected with phx_poll_errors().
+ *   - a handle is not thread-safe; one handle per device.
+ */
+#ifndef PHX_H_
+#define PHX_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PHX_ABI_VERSION 1
+
+#define PHX_MAX_AGENTS 128  /* agent slots per env                                   */
+#define PHX_MAX_TYPES 16    /* payload types per env class                           */
+#define PHX_MAX_STAGES 8    /* FSM stages                                            */
+#define PHX_MASK_WORDS 4    /* PHX_MAX_AGENTS / 32                                   */
+#define PHX_MAX_PARAMS 16
+#define PHX_TRACE_WORDS 4   /* one traced message = 4 x int32 (see phx_get_trace)    */
+
+typedef enum phx_status {
+  PHX_OK = 0,
+  PHX_ERR_INVALID = -1,      /* bad argument / spec rejected by the family lowering   */
+  PHX_ERR_CUDA = -2,         /* a CUDA runtime call failed                            */
+  PHX_ERR_UNSUPPORTED = -3,  /* valid in the reference, no device program for it      */
+  PHX_ERR_NO_DEVICE = -4
+} phx_status;
+
+/* Device fault codes; each mirrors the exception the reference raises from step(). */
+typedef enum phx_fault {
+  PHX_FAULT_NONE = 0,
+  PHX_FAULT_NO_EDGE = 1,          /* NetworkError, phantom/network.py:246-249          */
+  PHX_FAULT_BAD_PAYLOAD_TYPE = 2, /* NetworkError, phantom/network.py:315-331          */
+  PHX_FAULT_UNKNOWN_MSG_TYPE = 3, /* ValueError,   phantom/agents.py:140-143           */
+  PHX_FAULT_ROUND_LIMIT = 4,      /* RuntimeError, phantom/resolvers.py:160-163        */
+  PHX_FAULT_BAD_TRANSITION = 5,   /* FSMRuntimeError, phantom/fsm.py:304-307           */
+  PHX_FAULT_QUEUE_OVERFLOW = 6,   /* engine capacity exceeded (no reference analogue)  */
+  PHX_FAULT_INVALID_ACTION = 7    /* non-finite / out-of-contract action value
+                                     (ValueError/OverflowError from int(round(a)))     */
+} phx_fault;
+
+/* Which step loop drives the env (phantom/env.py, fsm.py, stackelberg.py). */
+typedef enum phx_env_kind {
+  PHX_ENV_BASE = 0,
+  PHX_ENV_FSM = 1,
+  PHX_ENV_STACKELBERG = 2
+} phx_env_kind;
+
+/* Device program families (one fused step kernel each). */
+typedef enum phx_family {
+  PHX_FAMILY_SUPPLY_CHAIN = 1, /* examples/environments/supply_chain/supply_chain.py  */
+  PHX_FAMILY_MOCK = 2,         /* the agents of the reference's own step-loop KATs
+                                  (tests/__init__.py:28-69)                           */
+  PHX_FAMILY_MARKET = 3,       /* 3-stage FSM market (BASELINE config C3)             */
+  PHX_FAMILY_STACKELBERG = 4,  /* leader/follower pricing game (BASELINE config C4)   */
+  PHX_FAMILY_DENSE = 5         /* dense-graph broadcast + batch aggregation (C5)      */
+} phx_family;
+
+typedef enum phx_exec_mode {
+  PHX_EXEC_AUTO = 0,   /* fastest kernel that is valid for the spec                   */
+  PHX_EXEC_QUEUE = 1,  /* force the generic message-queue engine (any topology)       */
+  PHX_EXEC_FAST = 2    /* force the schedule-specialised kernel; create fails if the
+                          spec is outside its domain                                  */
+} phx_exec_mode;
+
+enum {
+  PHX_FLAG_IGNORE_CONNECTION_ERRORS = 1 << 0, /* Network(ignore_connection_errors=True)   */
+  PHX_FLAG_NO_PAYLOAD_CHECKS = 1 << 1,        /* Network(enforce_msg_payload_checks=False)*/
+  PHX_FLAG_TRACK_MESSAGES = 1 << 2,           /* BatchResolver(enable_tracking=True)      */
+  PHX_FLAG_AUTO_RESET = 1 << 3                /* reset an env in the step that ends its
+                                                 episode; obs then holds the reset obs   */
+};
+
+typedef struct phx_stage {
+  uint32_t acting[PHX_MASK_WORDS];   /* FSMStage.acting_agents as a slot bitmask         */
+  uint32_t rewarded[PHX_MASK_WORDS]; /* FSMStage.rewarded_agents                         */
+  int32_t rewarded_is_none;          /* rewarded_agents is None (phantom/fsm.py:315-317) */
+  int32_t next_stage;                /* the single next stage of a handler-less stage    */
+} phx_stage;
+
+/* Flat description of one env class, lowered from the Python objects
+ * (PhantomEnv / Network / Agent / FSMStage ...) by phantom_b200/lowering.py. */
+typedef struct phx_spec {
+  uint32_t struct_size; /* sizeof(phx_spec), ABI guard */
+  int32_t family;       /* phx_family       */
+  int32_t env_kind;     /* phx_env_kind     */
+  int32_t exec_mode;    /* phx_exec_mode    */
+  uint32_t flags;       /* PHX_FLAG_*       */
+  int32_t num_steps;    /* PhantomEnv.num_steps */
+  int32_t round_limit;  /* BatchResolver.round_limit, -1 = None */
+  int32_t trace_capacity; /* max traced messages per env per step (tracking only) */
+
+  int32_t n_agents;                       /* agent slots, in Network.agents order      */
+  int32_t n_strategic;                    /* number of StrategicAgent slots            */
+  int32_t agent_kind[PHX_MAX_AGENTS];     /* family-specific device-program id per slot*/
+  int32_t strategic_index[PHX_MAX_AGENTS];/* slot -> index among strategic agents, -1  */
+  uint32_t adjacency[PHX_MAX_AGENTS][PHX_MASK_WORDS]; /* bit r of row s: edge s -> r   */
+
+  int32_t n_payload_types;
+  uint32_t type_sender_ok[PHX_MAX_TYPES][PHX_MASK_WORDS];   /* slots allowed to send   */
+  uint32_t type_receiver_ok[PHX_MAX_TYPES][PHX_MASK_WORDS]; /* slots allowed to receive*/
+
+  int32_t n_stages;      /* PHX_ENV_FSM */
+  int32_t initial_stage;
+  phx_stage stages[PHX_MAX_STAGES];
+
+  uint32_t leaders[PHX_MASK_WORDS];   /* PHX_ENV_STACKELBERG */
+  uint32_t followers[PHX_MASK_WORDS];
+
+  int32_t obs_dim; /* floats per strategic agent in the obs tensors (family maximum) */
+  int32_t act_dim; /* floats per strategic agent in the action tensors               */
+
+  int32_t iparams[PHX_MAX_PARAMS]; /* family parameters (see the family header)      */
+  double fparams[PHX_MAX_PARAMS];
+  int32_t agent_iparam[PHX_MAX_AGENTS][4]; /* per-slot family parameters, e.g. the slot
+                                              of the peer an agent addresses           */
+  double agent_fparam[PHX_MAX_AGENTS][2];
+} phx_spec;
+
+typedef struct phx_env phx_env; /* opaque */
+
+/* State columns readable through phx_get_field / writable through phx_set_field.
+ * Generic ids below; family columns start at PHX_FIELD_FAMILY (see family headers). */
+typedef enum phx_field {
+  PHX_FIELD_STEP = 0,       /* int32 [E]   PhantomEnv.current_step                   */
+  PHX_FIELD_EPISODE = 1,    /* int32 [E]   resets seen - 1 (RNG contract coordinate) */
+  PHX_FIELD_STAGE = 2,      /* int32 [E]   FSM current stage index                   */
+  PHX_FIELD_TERMINATED = 3, /* uint32[E,W] PhantomEnv._terminations as bitmask over
+                               strategic index, W = ceil(S/32)                       */
+  PHX_FIELD_TRUNCATED = 4,  /* uint32[E,W]                                           */
+  PHX_FIELD_ERROR = 5,      /* uint32[E]   sticky fault word                         */
+  PHX_FIELD_FAMILY = 16
+} phx_field;
+
+int32_t phx_abi_version(void);
+uint32_t phx_sizeof_spec(void); /* sizeof(phx_spec) as compiled: binding self-check */
+const char* phx_last_error(void);
+int32_t phx_device_count(void);
+
+/* Create the device-resident batch.  Replaces `env_class(**env_config)` executed once per
+ * env replica (phantom/utils/rllib/train.py:185-187, rollout.py:289-291).
+ *   seed       base seed of the RNG contract (oracle/rng.py)
+ *   env_offset global index of this handle's env 0 (multi-GPU sharding: results do not
+ *              depend on how envs are split over handles)                             */
+int32_t phx_create(const phx_spec* spec, int32_t num_envs, int32_t device, uint64_t seed,
+                   int64_t env_offset, phx_env** out);
+void phx_destroy(phx_env* env);
+
+int32_t phx_num_envs(const phx_env* env);
+/* name of the kernel variant chosen by phx_create ("fast" / "queue<G>") */
+const char* phx_exec_name(const phx_env* env);
+
+/* PhantomEnv.reset (phantom/env.py:185-237; fsm.py:195-251; stackelberg.py:53-109) for
+ * every env (env_mask == NULL) or for the envs whose mask byte is non-zero.
+ *   env_mask  device uint8 [E] or NULL
+ *   obs       device float [E,S,O]   initial observations (rows of unmasked envs untouched)
+ *   obs_mask  device uint8 [E,S]     1 where the reference's reset() returned an obs    */
+int32_t phx_reset(phx_env* env, const uint8_t* env_mask, float* obs, uint8_t* obs_mask,
+                  void* stream);
+
+/* PhantomEnv.step / FiniteStateMachineEnv.step / StackelbergEnv.step for every env.
+ *   actions     device float [E,S,A]
+ *   action_mask device uint8 [E,S] or NULL (= all present); 0 means the agent is absent
+ *               from the `actions` mapping and falls back to generate_messages()
+ *               (phantom/env.py:330-333)
+ *   obs         device float [E,S,O]; rows with obs_mask == 0 are left untouched
+ *   obs_mask    device uint8 [E,S]   agent is a key of Step.observations
+ *   reward      device float [E,S]   float32(Step.rewards[aid])
+ *   reward_mask device uint8 [E,S]   0 = not a key of Step.rewards, 1 = value present,
+ *                                    2 = key present with value None (phantom/fsm.py:378)
+ *   term, trunc device uint8 [E,S]   Step.terminations / truncations; 255 = key absent
+ *                                    (agent was already done)
+ *   all_done    device uint8 [E,2]   terminations["__all__"], truncations["__all__"]    */
+int32_t phx_step(phx_env* env, const float* actions, const uint8_t* action_mask, float* obs,
+                 uint8_t* obs_mask, float* reward, uint8_t* reward_mask, uint8_t* term,
+                 uint8_t* trunc, uint8_t* all_done, void* stream);
+
+/* T consecutive steps in ONE launch; env state stays on chip between steps.  All arrays
+ * get a leading T: actions [T,E,S,A], obs [T,E,S,O], ...  Replaces the inner loop of
+ * phantom/utils/rllib/rollout.py:321-363 when actions are known up front (open-loop
+ * evaluation, replay) and is what bench.py times as the fused step kernel.              */
+int32_t phx_rollout(phx_env* env, int32_t num_steps_T, const float* actions,
+                    const uint8_t* action_mask, float* obs, uint8_t* obs_mask, float* reward,
+                    uint8_t* reward_mask, uint8_t* term, uint8_t* trunc, uint8_t* all_done,
+                    void* stream);
+
+/* Same as phx_rollout but every buffer is HOST memory (ideally from phx_host_alloc, i.e.
+ * pinned): copies the actions to the device, runs, copies all outputs back, and
+ * synchronises.  This is the end-to-end call bench.py reports as `e2e`.                 */
+int32_t phx_rollout_host(phx_env* env, int32_t num_steps_T, const float* actions,
+                         const uint8_t* action_mask, float* obs, uint8_t* obs_mask,
+                         float* reward, uint8_t* reward_mask, uint8_t* term, uint8_t* trunc,
+                         uint8_t* all_done);
+
+void* phx_host_alloc(uint64_t bytes); /* pinned host memory (cudaMallocHost) */
+void phx_host_free(void* p);
+
+/* Copy one state column to / from HOST memory (metrics, parity tests; replaces reading
+ * live Python agent attributes, phantom/metrics.py:230-231).  `index` selects the agent
+ * instance for per-agent family columns.  Synchronises.                                 */
+int32_t phx_get_field(phx_env* env, int32_t field, int32_t index, void* host_out,
+                      uint64_t out_bytes);
+int32_t phx_set_field(phx_env* env, int32_t field, int32_t index, const void* host_in,
+                      uint64_t in_bytes);
+
+/* Resolver.tracked_messages (phantom/resolvers.py:41-60) of the LAST phx_step, for envs
+ * [env_begin, env_end): host_counts int32 [n] messages recorded per env, host_msgs
+ * int32 [n, trace_capacity, PHX_TRACE_WORDS] rows (sender_slot | recv_slot << 8 |
+ * type << 16, payload0, payload1, round).  Needs PHX_FLAG_TRACK_MESSAGES.  Synchronises. */
+int32_t phx_get_trace(phx_env* env, int32_t env_begin, int32_t env_end, int32_t* host_counts,
+                      int32_t* host_msgs);
+
+/* Collect device faults.  n_bad = envs whose error word is set, first_env / code = the
+ * lowest such env and its phx_fault.  clear != 0 zeroes the words.  Synchronises.       */
+int32_t phx_poll_errors(phx_env* env, int32_t* n_bad, int32_t* first_env, int32_t* code,
+                        int32_t clear);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PHX_H_ */

@@ -1,0 +1,428 @@
+// fam_supply_chain.cu -- device program family PHX_FAMILY_SUPPLY_CHAIN.
+//
+// Replaces, for a batch of E env instances, one PhantomEnv.step of
+// /root/reference/examples/environments/supply_chain/supply_chain.py:
+//   ShopAgent      :70-150  (decode_action :136-142, handle_order_request :104-122,
+//                            handle_stock_response :98-102, pre_message_resolution :93-96,
+//                            encode_observation :124-134, compute_reward :144-147, reset :149)
+//   FactoryAgent   :36-45   (echo StockRequest -> StockResponse)
+//   CustomerAgent  :48-67   (generate_messages: OrderRequest(randint(max_order)))
+//   SupplyChainEnv :153-175 (agents [SHOP, WAREHOUSE, CUST1..N], star on SHOP)
+// driven by phantom/env.py:239-303 and phantom/resolvers.py:128-163.
+//
+// Agent kinds (phx_spec.agent_kind):  0 = ShopAgent, 1 = FactoryAgent, 2 = CustomerAgent
+// Payload types:                      0 = OrderRequest, 1 = OrderResponse,
+//                                     2 = StockRequest, 3 = StockResponse
+// Family parameters:                  iparams[0] = CUSTOMER_MAX_ORDER_SIZE (5)
+//                                     iparams[1] = SHOP_MAX_STOCK (100)
+// Family fields (phx_get_field):      PHX_FIELD_FAMILY + 0 = shop state int32 [E,4]
+//                                     (stock, sales, missed_sales, delivered_stock)
+//
+// HBM layout: env header int4 [E] (step, episode, -, -), shop state int4 [E].  Messages,
+// contexts and views never touch HBM (unless message tracking is on).
+//
+// Two kernels:
+//  * sc_fast_kernel  -- one THREAD per env.  On the canonical topology the message graph of
+//    a step is data independent, so the routing rules are evaluated once per
+//    handle on the host (make_plan) into a static schedule, and the kernel executes the
+//    handler bodies in that order with the whole env state in registers.
+//  * (queue engine, fam_supply_chain_queue) -- any agent order / topology, messages routed
+//    dynamically through the shared-memory queue of phx_queue.cuh.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <string>
+
+#include "phx_family.h"
+#include "phx_rng.cuh"
+
+namespace phx {
+namespace {
+
+enum { SC_SHOP = 0, SC_FACTORY = 1, SC_CUSTOMER = 2 };
+enum { SC_ORDER_REQUEST = 0, SC_ORDER_RESPONSE = 1, SC_STOCK_REQUEST = 2, SC_STOCK_RESPONSE = 3 };
+constexpr int SC_STREAM_ORDER = 0;       // RNG stream of supply_chain.py:64
+constexpr int SC_MAX_CUSTOMERS = 30;
+constexpr float SC_MAX_ABS_ACTION = 1048576.0f;  // action contract: finite, |a| <= 2^20
+
+// Static schedule of one step on the canonical topology (see make_plan).
+struct ScPlan {
+  int32_t E, num_steps, nc, max_order, max_stock;
+  uint32_t flags;
+  uint32_t fault[2];     // [shop supplied an action?] -> first fault in event order, 0 = none
+  uint32_t deliver_ord;  // bit i: CUSTi's OrderRequest reaches the shop's handler
+  uint32_t delivery_ok;  // StockRequest reaches the factory AND StockResponse reaches the shop
+  uint32_t push_req, push_resp;  // tracking: message is pushed (passes the send checks)
+  uint32_t push_ord, push_ordresp;
+  uint64_t seed;
+  uint32_t env_offset;
+};
+
+struct ScArgs {
+  ScPlan p;
+  int32_t T;
+  int4* hdr;
+  int4* shop;
+  StepIO io;
+  FaultSink faults;
+  TraceSink trace;
+};
+
+__device__ __forceinline__ float sc_ratio(int num, float den) {
+  // reference: float32(int / int) computed in float64 then cast.  RN32(RN64(n/d)) equals the
+  // correctly rounded float32 quotient here: |n| < 2^24 and d <= 2^12 are exact in float32,
+  // and n/d with d | 4*25 has a binary expansion of period <= 20 < 29, so the float64
+  // rounding can never land on a float32 tie (DESIGN.md "float parity").
+  return __fdiv_rn((float)num, den);
+}
+
+// One thread per env; T steps per launch with the env state in registers.
+template <int NC, bool TRACK>
+__global__ void __launch_bounds__(128) sc_fast_kernel(const ScArgs a) {
+  __shared__ __align__(16) float obs_stage[4][96];
+
+  const ScPlan& p = a.p;
+  const int e = blockIdx.x * 128 + threadIdx.x;
+  const bool live = e < p.E;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nc = NC > 0 ? NC : p.nc;
+  const uint32_t env_id = p.env_offset + (uint32_t)e;
+  const float cap_f = (float)(nc * p.max_order);
+  const float max_stock_f = (float)p.max_stock;
+  // vector path for obs needs a full warp and 16-byte aligned rows
+  const bool warp_full = (blockIdx.x * 128 + warp * 32 + 32) <= p.E;
+  const bool vec_obs = warp_full && ((p.E & 3) == 0) && a.io.obs != nullptr;
+
+  int2 h = make_int2(0, 0);
+  int4 s = make_int4(0, 0, 0, 0);
+  if (live) {
+    h = *reinterpret_cast<const int2*>(a.hdr + e);
+    s = a.shop[e];
+  }
+  uint32_t fault = 0;
+
+  for (int t = 0; t < a.T; ++t) {
+    const size_t row = (size_t)t * p.E + e;
+    float act = 0.f;
+    bool has = true;
+    if (live) {
+      if (a.io.action_mask) has = a.io.action_mask[row] != 0;
+      act = ld_stream(a.io.actions + row);
+    }
+    h.x += 1;  // env.py:252
+
+    // ---- acting phase (env.py:320-336), agent order SHOP, WAREHOUSE, CUST1..N
+    // ShopAgent.decode_action: min(int(round(a)), max_stock - stock); python round() of a
+    // float32 is round-half-even == cvt.rni
+    const int ask = min(__float2int_rn(act), p.max_stock - s.x);
+    if (has && !(fabsf(act) <= SC_MAX_ABS_ACTION)) fault = fault ? fault : PHX_FAULT_INVALID_ACTION;
+    if (fault == 0) fault = p.fault[has ? 1 : 0];
+
+    int cnt = 0;
+    int4* trow = nullptr;
+    if (TRACK && live) {
+      trow = a.trace.rows + (size_t)e * a.trace.cap;
+      if (has && p.push_req) trow[cnt++] = trace_row(0, 1, SC_STOCK_REQUEST, ask, 0, 0);
+    }
+
+    // ---- pre_message_resolution (supply_chain.py:93-96)
+    s.y = 0;
+    s.z = 0;
+
+    // ---- round 0, receiver SHOP: orders are filled serially in push (= customer) order
+    // from the stock held BEFORE this step's delivery (delivery arrives in round 1).
+    int sold_each[NC > 0 ? NC : 1];
+    int order_each[NC > 0 ? NC : 1];
+#pragma unroll
+    for (int b = 0; b < (NC > 0 ? (NC + 3) / 4 : 8); ++b) {
+      if (NC == 0 && b * 4 >= nc) break;
+      const Philox4 blk = rng_block(p.seed, env_id, (uint32_t)h.y, (uint32_t)h.x, SC_STREAM_ORDER, b);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int i = b * 4 + k;
+        if (i >= nc) break;
+        const int want = rng_randint(blk.w[k], (uint32_t)p.max_order);  // supply_chain.py:64
+        if (TRACK && live && ((p.push_ord >> i) & 1u))
+          trow[cnt++] = trace_row(2 + i, 0, SC_ORDER_REQUEST, want, 0, 0);
+        int sold = 0;
+        if ((p.deliver_ord >> i) & 1u) {  // handle_order_request, supply_chain.py:104-122
+          if (want > s.x) {
+            s.z += want - s.x;
+            sold = s.x;
+            s.x = 0;
+          } else {
+            sold = want;
+            s.x -= want;
+          }
+          s.y += sold;
+        }
+        if (NC > 0) { sold_each[i] = sold; order_each[i] = want; }
+      }
+    }
+    (void)order_each;
+    if (TRACK && live) {
+      // responses generated in round 0, in receiver first-arrival order: WAREHOUSE, SHOP
+      if (has && p.push_resp) trow[cnt++] = trace_row(1, 0, SC_STOCK_RESPONSE, ask, 0, 1);
+      if (NC > 0) {
+#pragma unroll
+        for (int i = 0; i < (NC > 0 ? NC : 1); ++i)
+          if ((p.push_ordresp >> i) & 1u)
+            trow[cnt++] = trace_row(0, 2 + i, SC_ORDER_RESPONSE, sold_each[i], 0, 1);
+      }
+      a.trace.cnt[e] = cnt;
+    }
+
+    // ---- round 1, receiver SHOP: handle_stock_response (supply_chain.py:98-102)
+    if (has && p.delivery_ok) {
+      s.w = ask;
+      s.x = min(s.x + ask, p.max_stock);
+    }
+
+    // ---- outputs (env.py:273-303).  The shop never terminates (agents.py:307,323).
+    const double reward64 = __dsub_rn((double)s.y, __dmul_rn(0.1, (double)s.x));
+    const bool at_max = h.x == p.num_steps;  // env.py:312-318
+
+    if ((p.flags & PHX_FLAG_AUTO_RESET) && at_max) {
+      // Network.reset -> ShopAgent.reset: only the stock is cleared (supply_chain.py:149)
+      s.x = 0;
+      h.x = 0;
+      h.y += 1;
+    }
+    const float o0 = sc_ratio(s.x, max_stock_f);
+    const float o1 = sc_ratio(s.y, cap_f);
+    const float o2 = sc_ratio(s.z, cap_f);
+
+    if (vec_obs) {
+      float* st = obs_stage[warp];
+      st[lane * 3 + 0] = o0;
+      st[lane * 3 + 1] = o1;
+      st[lane * 3 + 2] = o2;
+      __syncwarp();
+      if (lane < 24) {
+        const float4 v = reinterpret_cast<const float4*>(st)[lane];
+        float4* dst = reinterpret_cast<float4*>(a.io.obs + ((size_t)t * p.E + (e - lane)) * 3);
+        st_stream(dst + lane, v);
+      }
+      __syncwarp();
+    } else if (live && a.io.obs) {
+      float* o = a.io.obs + row * 3;
+      o[0] = o0; o[1] = o1; o[2] = o2;
+    }
+    if (live) {
+      if (a.io.reward) st_stream(a.io.reward + row, (float)reward64);
+      if (a.io.obs_mask) a.io.obs_mask[row] = 1;
+      if (a.io.reward_mask) a.io.reward_mask[row] = 1;
+      if (a.io.term) a.io.term[row] = 0;
+      if (a.io.trunc) a.io.trunc[row] = 0;
+      if (a.io.all_done)
+        reinterpret_cast<uchar2*>(a.io.all_done)[row] = make_uchar2(0, at_max ? 1 : 0);
+    }
+  }
+
+  if (live) {
+    *reinterpret_cast<int2*>(a.hdr + e) = h;
+    a.shop[e] = s;
+    if (fault) raise_fault(a.faults, e, fault);
+  }
+}
+
+// PhantomEnv.reset (env.py:185-237) for the masked envs.
+__global__ void sc_reset_kernel(ScPlan p, int4* hdr, int4* shop, uint32_t* term, uint32_t* trunc,
+                                const uint8_t* env_mask, float* obs, uint8_t* obs_mask) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= p.E) return;
+  if (env_mask && env_mask[e] == 0) return;
+  int4 h = hdr[e];
+  int4 s = shop[e];
+  h.x = 0;
+  h.y += 1;
+  s.x = 0;  // sales / missed_sales survive the reset (supply_chain.py:149-150)
+  hdr[e] = h;
+  shop[e] = s;
+  term[e] = 0;
+  trunc[e] = 0;
+  if (obs) {
+    const float cap_f = (float)(p.nc * p.max_order);
+    obs[e * 3 + 0] = sc_ratio(s.x, (float)p.max_stock);
+    obs[e * 3 + 1] = sc_ratio(s.y, cap_f);
+    obs[e * 3 + 2] = sc_ratio(s.z, cap_f);
+  }
+  if (obs_mask) obs_mask[e] = 1;
+}
+
+__global__ void sc_init_kernel(int E, int4* hdr, int4* shop) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  hdr[e] = make_int4(0, -1, 0, 0);  // episode becomes 0 on the first reset
+  shop[e] = make_int4(0, 0, 0, 0);
+}
+
+class SupplyChainFamily final : public Family {
+ public:
+  ~SupplyChainFamily() override { cudaFree(d_shop); }
+
+  int32_t init(const phx_spec& s) override {
+    PHX_REQUIRE(s.env_kind == PHX_ENV_BASE, PHX_ERR_UNSUPPORTED,
+                "supply-chain family runs under PhantomEnv (PHX_ENV_BASE) only");
+    PHX_REQUIRE(s.n_payload_types == 4, PHX_ERR_INVALID,
+                "supply-chain family expects 4 payload types "
+                "(OrderRequest, OrderResponse, StockRequest, StockResponse)");
+    PHX_REQUIRE(s.obs_dim == 3 && s.act_dim == 1, PHX_ERR_INVALID,
+                "supply-chain family: obs_dim must be 3 and act_dim 1");
+    PHX_REQUIRE(s.iparams[0] >= 1 && s.iparams[0] <= 4096 && s.iparams[1] >= 0 &&
+                    s.iparams[1] <= (1 << 20),
+                PHX_ERR_INVALID, "supply-chain family: max_order / max_stock out of range");
+    const bool canonical = is_canonical(s);
+    PHX_REQUIRE(s.exec_mode != PHX_EXEC_FAST || canonical, PHX_ERR_UNSUPPORTED,
+                "PHX_EXEC_FAST needs the canonical supply-chain layout "
+                "[ShopAgent, FactoryAgent, CustomerAgent x N]");
+    PHX_REQUIRE(canonical && s.exec_mode != PHX_EXEC_QUEUE, PHX_ERR_UNSUPPORTED,
+                "supply-chain queue engine not built yet");
+    PHX_CUDA(cudaMalloc(&d_shop, sizeof(int4) * (size_t)E));
+    sc_init_kernel<<<(E + 255) / 256, 256>>>(E, d_hdr, d_shop);
+    PHX_CUDA(cudaGetLastError());
+    PHX_CUDA(cudaDeviceSynchronize());
+    return make_plan(s);
+  }
+
+  static bool is_canonical(const phx_spec& s) {
+    if (s.n_agents < 3 || s.n_agents > 2 + SC_MAX_CUSTOMERS) return false;
+    if (s.agent_kind[0] != SC_SHOP || s.agent_kind[1] != SC_FACTORY) return false;
+    for (int i = 2; i < s.n_agents; ++i)
+      if (s.agent_kind[i] != SC_CUSTOMER) return false;
+    return s.n_strategic == 1 && s.strategic_index[0] == 0;
+  }
+
+  // network.py:246-254 evaluated on the static graph: 0 = pushed, else the fault raised.
+  uint32_t send_check(const phx_spec& s, int from, int to, int type) const {
+    const bool edge = mask_bit(s.adjacency[from], to);
+    if (!(s.flags & PHX_FLAG_IGNORE_CONNECTION_ERRORS) && !edge) return PHX_FAULT_NO_EDGE;
+    if (!(s.flags & PHX_FLAG_NO_PAYLOAD_CHECKS)) {
+      if (!mask_bit(s.type_sender_ok[type], from) || !mask_bit(s.type_receiver_ok[type], to))
+        return PHX_FAULT_BAD_PAYLOAD_TYPE;
+    }
+    return 0;
+  }
+
+  // Walks one step's event order (SURVEY.md A.1 rules 2-7) on the static graph and records
+  // which messages are pushed / delivered and the first fault, once with and once without a
+  // shop action.  The two walks must agree on the customer side (they do: it does not depend
+  // on the shop's action), which is what makes a single static schedule valid.
+  int32_t make_plan(const phx_spec& s) {
+    ScPlan& p = plan;
+    std::memset(&p, 0, sizeof(p));
+    p.E = E;
+    p.num_steps = s.num_steps;
+    p.nc = s.n_agents - 2;
+    p.max_order = s.iparams[0];
+    p.max_stock = s.iparams[1];
+    p.flags = s.flags;
+    p.seed = seed;
+    p.env_offset = (uint32_t)env_offset;
+    for (int has = 0; has < 2; ++has) {
+      uint32_t fault = 0;
+      bool push_req = false, deliver_req = false;
+      uint32_t push_ord = 0, deliver_ord = 0;
+      // acting phase
+      if (has) {
+        fault = send_check(s, 0, 1, SC_STOCK_REQUEST);
+        if (!fault) { push_req = true; deliver_req = mask_bit(s.adjacency[0], 1); }
+      }
+      for (int i = 0; i < p.nc && !fault; ++i) {
+        fault = send_check(s, 2 + i, 0, SC_ORDER_REQUEST);
+        if (!fault) {
+          push_ord |= 1u << i;
+          if (mask_bit(s.adjacency[2 + i], 0)) deliver_ord |= 1u << i;
+        }
+      }
+      const bool any0 = push_req || push_ord;
+      bool push_resp = false, deliver_resp = false;
+      uint32_t push_ordresp = 0;
+      if (!fault && any0 && s.round_limit == 0) fault = PHX_FAULT_ROUND_LIMIT;
+      if (!fault && any0) {
+        // round 0: receivers in first-arrival order = WAREHOUSE (if asked), SHOP
+        if (deliver_req) {
+          fault = send_check(s, 1, 0, SC_STOCK_RESPONSE);
+          if (!fault) { push_resp = true; deliver_resp = mask_bit(s.adjacency[1], 0); }
+        }
+        for (int i = 0; i < p.nc && !fault; ++i) {
+          if (!((deliver_ord >> i) & 1u)) continue;
+          fault = send_check(s, 0, 2 + i, SC_ORDER_RESPONSE);
+          if (!fault) push_ordresp |= 1u << i;
+        }
+        const bool any1 = push_resp || push_ordresp;
+        if (!fault && any1 && s.round_limit == 1) fault = PHX_FAULT_ROUND_LIMIT;
+        // round 1 produces no further messages (both handlers return nothing)
+      }
+      p.fault[has] = fault;
+      if (has) {
+        p.push_req = push_req;
+        p.push_resp = push_resp;
+        p.delivery_ok = (deliver_req && deliver_resp) ? 1u : 0u;
+      }
+      p.push_ord = push_ord;
+      p.deliver_ord = deliver_ord;
+      p.push_ordresp = push_ordresp;
+    }
+    if (tracking())
+      PHX_REQUIRE(s.trace_capacity >= 2 * (1 + p.nc), PHX_ERR_INVALID,
+                  "trace_capacity must be >= 2 * (1 + n_customers) for the supply chain");
+    return PHX_OK;
+  }
+
+  int32_t reset(const uint8_t* env_mask, float* obs, uint8_t* obs_mask,
+                cudaStream_t stream) override {
+    sc_reset_kernel<<<(E + 255) / 256, 256, 0, stream>>>(plan, d_hdr, d_shop, d_term, d_trunc,
+                                                        env_mask, obs, obs_mask);
+    PHX_CUDA(cudaGetLastError());
+    return PHX_OK;
+  }
+
+  int32_t rollout(int32_t T, const StepIO& io, cudaStream_t stream) override {
+    ScArgs a;
+    a.p = plan;
+    a.T = T;
+    a.hdr = d_hdr;
+    a.shop = d_shop;
+    a.io = io;
+    a.faults = fault_sink();
+    a.trace = trace_sink();
+    const int grid = (E + 127) / 128;
+    const bool track = tracking();
+    PHX_REQUIRE(!track || T == 1, PHX_ERR_INVALID,
+                "message tracking records one step: use phx_step (T == 1)");
+    if (plan.nc == 5) {
+      if (track) sc_fast_kernel<5, true><<<grid, 128, 0, stream>>>(a);
+      else sc_fast_kernel<5, false><<<grid, 128, 0, stream>>>(a);
+    } else {
+      PHX_REQUIRE(!track, PHX_ERR_UNSUPPORTED,
+                  "message tracking on the fast path is built for 5 customers; "
+                  "use PHX_EXEC_QUEUE");
+      sc_fast_kernel<0, false><<<grid, 128, 0, stream>>>(a);
+    }
+    PHX_CUDA(cudaGetLastError());
+    return PHX_OK;
+  }
+
+  int32_t family_field(int32_t field, int32_t, void** p, size_t* bytes) override {
+    if (field == PHX_FIELD_FAMILY + 0) {
+      *p = d_shop;
+      *bytes = sizeof(int4) * (size_t)E;
+      return PHX_OK;
+    }
+    set_error("supply-chain family: unknown field " + std::to_string(field));
+    return PHX_ERR_INVALID;
+  }
+
+  const char* exec_name() const override { return "fast(thread-per-env)"; }
+
+ private:
+  ScPlan plan{};
+  int4* d_shop = nullptr;
+};
+
+}  // namespace
+
+Family* make_supply_chain_family() { return new SupplyChainFamily(); }
+
+}  // namespace phx

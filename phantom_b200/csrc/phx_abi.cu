@@ -1,0 +1,375 @@
+// phx_abi.cu -- the C ABI of libphx (include/phx.h): handle management, argument checks,
+// dispatch to the device program families, host-buffer variants, field/trace/fault access.
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "phx_family.h"
+
+namespace phx {
+
+static thread_local std::string g_last_error;
+void set_error(const std::string& msg) { g_last_error = msg; }
+
+Family::~Family() {
+  cudaSetDevice(device);
+  cudaFree(d_hdr);
+  cudaFree(d_term);
+  cudaFree(d_trunc);
+  cudaFree(d_err);
+  cudaFree(d_nfaults);
+  cudaFree(d_trace);
+  cudaFree(d_trace_cnt);
+  cudaFree(d_stage);
+  if (own_stream) cudaStreamDestroy(own_stream);
+}
+
+int32_t Family::base_init(const phx_spec& s, int32_t num_envs, int32_t dev, uint64_t sd,
+                          int64_t off) {
+  spec = s;
+  E = num_envs;
+  device = dev;
+  seed = sd;
+  env_offset = off;
+  mask_words = (s.n_strategic + 31) / 32;
+  if (mask_words < 1) mask_words = 1;
+  PHX_CUDA(cudaSetDevice(device));
+  PHX_CUDA(cudaMalloc(&d_hdr, sizeof(int4) * (size_t)E));
+  PHX_CUDA(cudaMalloc(&d_term, sizeof(uint32_t) * (size_t)E * mask_words));
+  PHX_CUDA(cudaMalloc(&d_trunc, sizeof(uint32_t) * (size_t)E * mask_words));
+  PHX_CUDA(cudaMalloc(&d_err, sizeof(uint32_t) * (size_t)E));
+  PHX_CUDA(cudaMalloc(&d_nfaults, sizeof(uint32_t)));
+  PHX_CUDA(cudaMemset(d_hdr, 0, sizeof(int4) * (size_t)E));
+  PHX_CUDA(cudaMemset(d_term, 0, sizeof(uint32_t) * (size_t)E * mask_words));
+  PHX_CUDA(cudaMemset(d_trunc, 0, sizeof(uint32_t) * (size_t)E * mask_words));
+  PHX_CUDA(cudaMemset(d_err, 0, sizeof(uint32_t) * (size_t)E));
+  PHX_CUDA(cudaMemset(d_nfaults, 0, sizeof(uint32_t)));
+  if (tracking()) {
+    PHX_REQUIRE(spec.trace_capacity > 0, PHX_ERR_INVALID,
+                "PHX_FLAG_TRACK_MESSAGES needs trace_capacity > 0");
+    PHX_CUDA(cudaMalloc(&d_trace, sizeof(int4) * (size_t)E * spec.trace_capacity));
+    PHX_CUDA(cudaMalloc(&d_trace_cnt, sizeof(int32_t) * (size_t)E));
+    PHX_CUDA(cudaMemset(d_trace_cnt, 0, sizeof(int32_t) * (size_t)E));
+  }
+  PHX_CUDA(cudaStreamCreateWithFlags(&own_stream, cudaStreamNonBlocking));
+  return PHX_OK;
+}
+
+int32_t Family::field_ptr(int32_t field, int32_t index, void** p, size_t* bytes) {
+  switch (field) {
+    case PHX_FIELD_TERMINATED:
+      *p = d_term; *bytes = sizeof(uint32_t) * (size_t)E * mask_words; return PHX_OK;
+    case PHX_FIELD_TRUNCATED:
+      *p = d_trunc; *bytes = sizeof(uint32_t) * (size_t)E * mask_words; return PHX_OK;
+    case PHX_FIELD_ERROR:
+      *p = d_err; *bytes = sizeof(uint32_t) * (size_t)E; return PHX_OK;
+    default:
+      break;
+  }
+  if (field >= PHX_FIELD_FAMILY) return family_field(field, index, p, bytes);
+  set_error("unknown field id " + std::to_string(field));
+  return PHX_ERR_INVALID;
+}
+
+}  // namespace phx
+
+using phx::Family;
+using phx::set_error;
+
+struct phx_env {
+  Family* fam;
+};
+
+static int32_t check_spec(const phx_spec* s) {
+  PHX_REQUIRE(s != nullptr, PHX_ERR_INVALID, "spec is NULL");
+  PHX_REQUIRE(s->struct_size == sizeof(phx_spec), PHX_ERR_INVALID,
+              "phx_spec.struct_size mismatch (ABI skew): got " + std::to_string(s->struct_size) +
+                  ", library has " + std::to_string(sizeof(phx_spec)));
+  PHX_REQUIRE(s->n_agents >= 1 && s->n_agents <= PHX_MAX_AGENTS, PHX_ERR_INVALID,
+              "n_agents out of range");
+  PHX_REQUIRE(s->n_strategic >= 0 && s->n_strategic <= s->n_agents, PHX_ERR_INVALID,
+              "n_strategic out of range");
+  PHX_REQUIRE(s->n_payload_types >= 0 && s->n_payload_types <= PHX_MAX_TYPES, PHX_ERR_INVALID,
+              "n_payload_types out of range");
+  PHX_REQUIRE(s->num_steps >= 1, PHX_ERR_INVALID, "num_steps must be >= 1");
+  PHX_REQUIRE(s->round_limit >= -1, PHX_ERR_INVALID, "round_limit must be >= -1");
+  int n_strat = 0;
+  for (int i = 0; i < s->n_agents; ++i) {
+    if (s->strategic_index[i] >= 0) {
+      PHX_REQUIRE(s->strategic_index[i] == n_strat, PHX_ERR_INVALID,
+                  "strategic_index must number strategic slots 0..S-1 in slot order");
+      ++n_strat;
+    }
+  }
+  PHX_REQUIRE(n_strat == s->n_strategic, PHX_ERR_INVALID, "n_strategic != #strategic slots");
+  if (s->env_kind == PHX_ENV_FSM) {
+    PHX_REQUIRE(s->n_stages >= 1 && s->n_stages <= PHX_MAX_STAGES, PHX_ERR_INVALID,
+                "n_stages out of range");
+    PHX_REQUIRE(s->initial_stage >= 0 && s->initial_stage < s->n_stages, PHX_ERR_INVALID,
+                "initial_stage out of range");
+  }
+  return PHX_OK;
+}
+
+extern "C" {
+
+int32_t phx_abi_version(void) { return PHX_ABI_VERSION; }
+
+uint32_t phx_sizeof_spec(void) { return (uint32_t)sizeof(phx_spec); }
+
+const char* phx_last_error(void) { return phx::g_last_error.c_str(); }
+
+int32_t phx_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int32_t phx_create(const phx_spec* spec, int32_t num_envs, int32_t device, uint64_t seed,
+                   int64_t env_offset, phx_env** out) {
+  PHX_REQUIRE(out != nullptr, PHX_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  int32_t rc = check_spec(spec);
+  if (rc != PHX_OK) return rc;
+  PHX_REQUIRE(num_envs >= 1, PHX_ERR_INVALID, "num_envs must be >= 1");
+  PHX_REQUIRE(env_offset >= 0 && env_offset + num_envs <= 0xFFFFFFFFll, PHX_ERR_INVALID,
+              "env_offset + num_envs must fit the 32-bit env coordinate of the RNG contract");
+  int ndev = phx_device_count();
+  PHX_REQUIRE(ndev > 0, PHX_ERR_NO_DEVICE,
+              "no CUDA device visible: libphx has no CPU fallback by design");
+  PHX_REQUIRE(device >= 0 && device < ndev, PHX_ERR_INVALID, "device index out of range");
+
+  Family* fam = nullptr;
+  switch (spec->family) {
+    case PHX_FAMILY_SUPPLY_CHAIN:
+      fam = phx::make_supply_chain_family();
+      break;
+    default:
+      set_error("no device program for family " + std::to_string(spec->family));
+      return PHX_ERR_UNSUPPORTED;
+  }
+  rc = fam->base_init(*spec, num_envs, device, seed, env_offset);
+  if (rc == PHX_OK) rc = fam->init(*spec);
+  if (rc != PHX_OK) {
+    delete fam;
+    return rc;
+  }
+  *out = new (std::nothrow) phx_env{fam};
+  return PHX_OK;
+}
+
+void phx_destroy(phx_env* env) {
+  if (!env) return;
+  cudaSetDevice(env->fam->device);
+  cudaDeviceSynchronize();
+  delete env->fam;
+  delete env;
+}
+
+int32_t phx_num_envs(const phx_env* env) { return env ? env->fam->E : 0; }
+
+const char* phx_exec_name(const phx_env* env) { return env ? env->fam->exec_name() : ""; }
+
+int32_t phx_reset(phx_env* env, const uint8_t* env_mask, float* obs, uint8_t* obs_mask,
+                  void* stream) {
+  PHX_REQUIRE(env != nullptr, PHX_ERR_INVALID, "env is NULL");
+  PHX_CUDA(cudaSetDevice(env->fam->device));
+  return env->fam->reset(env_mask, obs, obs_mask, (cudaStream_t)stream);
+}
+
+int32_t phx_rollout(phx_env* env, int32_t T, const float* actions, const uint8_t* action_mask,
+                    float* obs, uint8_t* obs_mask, float* reward, uint8_t* reward_mask,
+                    uint8_t* term, uint8_t* trunc, uint8_t* all_done, void* stream) {
+  PHX_REQUIRE(env != nullptr, PHX_ERR_INVALID, "env is NULL");
+  PHX_REQUIRE(T >= 1, PHX_ERR_INVALID, "T must be >= 1");
+  PHX_REQUIRE(actions != nullptr || env->fam->spec.n_strategic == 0 || action_mask != nullptr,
+              PHX_ERR_INVALID, "actions is NULL");
+  PHX_CUDA(cudaSetDevice(env->fam->device));
+  phx::StepIO io{actions, action_mask, obs, obs_mask, reward, reward_mask, term, trunc, all_done};
+  return env->fam->rollout(T, io, (cudaStream_t)stream);
+}
+
+int32_t phx_step(phx_env* env, const float* actions, const uint8_t* action_mask, float* obs,
+                 uint8_t* obs_mask, float* reward, uint8_t* reward_mask, uint8_t* term,
+                 uint8_t* trunc, uint8_t* all_done, void* stream) {
+  return phx_rollout(env, 1, actions, action_mask, obs, obs_mask, reward, reward_mask, term,
+                     trunc, all_done, stream);
+}
+
+void* phx_host_alloc(uint64_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+
+void phx_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+int32_t phx_rollout_host(phx_env* env, int32_t T, const float* actions,
+                         const uint8_t* action_mask, float* obs, uint8_t* obs_mask,
+                         float* reward, uint8_t* reward_mask, uint8_t* term, uint8_t* trunc,
+                         uint8_t* all_done) {
+  PHX_REQUIRE(env != nullptr, PHX_ERR_INVALID, "env is NULL");
+  PHX_REQUIRE(T >= 1, PHX_ERR_INVALID, "T must be >= 1");
+  Family* f = env->fam;
+  PHX_CUDA(cudaSetDevice(f->device));
+  const size_t n = (size_t)T * f->E * (size_t)(f->spec.n_strategic > 0 ? f->spec.n_strategic : 1);
+  const size_t S = f->spec.n_strategic;
+  const size_t TE = (size_t)T * f->E;
+  auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+  // carve one staging block: actions | action_mask | obs | obs_mask | reward | reward_mask |
+  // term | trunc | all_done
+  const size_t b_act = up(TE * S * f->spec.act_dim * sizeof(float));
+  const size_t b_am = up(TE * S);
+  const size_t b_obs = up(TE * S * f->spec.obs_dim * sizeof(float));
+  const size_t b_u8 = up(TE * S);
+  const size_t b_rew = up(TE * S * sizeof(float));
+  const size_t b_all = up(TE * 2);
+  const size_t total = b_act + b_am + b_obs + 4 * b_u8 + b_rew + b_all;
+  (void)n;
+  if (total > f->stage_bytes) {
+    PHX_CUDA(cudaStreamSynchronize(f->own_stream));
+    if (f->d_stage) PHX_CUDA(cudaFree(f->d_stage));
+    f->d_stage = nullptr;
+    f->stage_bytes = 0;
+    PHX_CUDA(cudaMalloc(&f->d_stage, total));
+    f->stage_bytes = total;
+  }
+  uint8_t* p = (uint8_t*)f->d_stage;
+  float* d_act = (float*)p; p += b_act;
+  uint8_t* d_am = p; p += b_am;
+  float* d_obs = (float*)p; p += b_obs;
+  uint8_t* d_om = p; p += b_u8;
+  float* d_rew = (float*)p; p += b_rew;
+  uint8_t* d_rm = p; p += b_u8;
+  uint8_t* d_term = p; p += b_u8;
+  uint8_t* d_trunc = p; p += b_u8;
+  uint8_t* d_all = p;
+  cudaStream_t st = f->own_stream;
+  if (actions)
+    PHX_CUDA(cudaMemcpyAsync(d_act, actions, TE * S * f->spec.act_dim * sizeof(float),
+                             cudaMemcpyHostToDevice, st));
+  if (action_mask)
+    PHX_CUDA(cudaMemcpyAsync(d_am, action_mask, TE * S, cudaMemcpyHostToDevice, st));
+  phx::StepIO io{d_act,
+                 action_mask ? d_am : nullptr,
+                 obs ? d_obs : nullptr,
+                 obs_mask ? d_om : nullptr,
+                 reward ? d_rew : nullptr,
+                 reward_mask ? d_rm : nullptr,
+                 term ? d_term : nullptr,
+                 trunc ? d_trunc : nullptr,
+                 all_done ? d_all : nullptr};
+  int32_t rc = f->rollout(T, io, st);
+  if (rc != PHX_OK) return rc;
+  if (obs)
+    PHX_CUDA(cudaMemcpyAsync(obs, d_obs, TE * S * f->spec.obs_dim * sizeof(float),
+                             cudaMemcpyDeviceToHost, st));
+  if (obs_mask) PHX_CUDA(cudaMemcpyAsync(obs_mask, d_om, TE * S, cudaMemcpyDeviceToHost, st));
+  if (reward)
+    PHX_CUDA(cudaMemcpyAsync(reward, d_rew, TE * S * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (reward_mask)
+    PHX_CUDA(cudaMemcpyAsync(reward_mask, d_rm, TE * S, cudaMemcpyDeviceToHost, st));
+  if (term) PHX_CUDA(cudaMemcpyAsync(term, d_term, TE * S, cudaMemcpyDeviceToHost, st));
+  if (trunc) PHX_CUDA(cudaMemcpyAsync(trunc, d_trunc, TE * S, cudaMemcpyDeviceToHost, st));
+  if (all_done) PHX_CUDA(cudaMemcpyAsync(all_done, d_all, TE * 2, cudaMemcpyDeviceToHost, st));
+  PHX_CUDA(cudaStreamSynchronize(st));
+  return PHX_OK;
+}
+
+static int32_t field_copy(phx_env* env, int32_t field, int32_t index, void* host, uint64_t bytes,
+                          bool set) {
+  PHX_REQUIRE(env != nullptr && host != nullptr, PHX_ERR_INVALID, "NULL argument");
+  Family* f = env->fam;
+  PHX_CUDA(cudaSetDevice(f->device));
+  PHX_CUDA(cudaDeviceSynchronize());
+  if (field == PHX_FIELD_STEP || field == PHX_FIELD_EPISODE || field == PHX_FIELD_STAGE) {
+    PHX_REQUIRE(bytes == sizeof(int32_t) * (uint64_t)f->E, PHX_ERR_INVALID,
+                "buffer must hold int32 [E]");
+    std::vector<int4> h((size_t)f->E);
+    PHX_CUDA(cudaMemcpy(h.data(), f->d_hdr, sizeof(int4) * (size_t)f->E, cudaMemcpyDeviceToHost));
+    int32_t* io = (int32_t*)host;
+    for (int e = 0; e < f->E; ++e) {
+      int32_t* w = field == PHX_FIELD_STEP ? &h[e].x : field == PHX_FIELD_EPISODE ? &h[e].y : &h[e].z;
+      if (set) *w = io[e]; else io[e] = *w;
+    }
+    if (set)
+      PHX_CUDA(cudaMemcpy(f->d_hdr, h.data(), sizeof(int4) * (size_t)f->E, cudaMemcpyHostToDevice));
+    return PHX_OK;
+  }
+  void* d = nullptr;
+  size_t n = 0;
+  int32_t rc = f->field_ptr(field, index, &d, &n);
+  if (rc != PHX_OK) return rc;
+  PHX_REQUIRE(bytes == n, PHX_ERR_INVALID,
+              "field size mismatch: column has " + std::to_string(n) + " bytes, buffer " +
+                  std::to_string(bytes));
+  if (set) PHX_CUDA(cudaMemcpy(d, host, n, cudaMemcpyHostToDevice));
+  else PHX_CUDA(cudaMemcpy(host, d, n, cudaMemcpyDeviceToHost));
+  return PHX_OK;
+}
+
+int32_t phx_get_field(phx_env* env, int32_t field, int32_t index, void* host_out,
+                      uint64_t out_bytes) {
+  return field_copy(env, field, index, host_out, out_bytes, false);
+}
+
+int32_t phx_set_field(phx_env* env, int32_t field, int32_t index, const void* host_in,
+                      uint64_t in_bytes) {
+  return field_copy(env, field, index, const_cast<void*>(host_in), in_bytes, true);
+}
+
+int32_t phx_get_trace(phx_env* env, int32_t env_begin, int32_t env_end, int32_t* host_counts,
+                      int32_t* host_msgs) {
+  PHX_REQUIRE(env != nullptr && host_counts != nullptr && host_msgs != nullptr, PHX_ERR_INVALID,
+              "NULL argument");
+  Family* f = env->fam;
+  PHX_REQUIRE(f->tracking(), PHX_ERR_INVALID, "handle was created without PHX_FLAG_TRACK_MESSAGES");
+  PHX_REQUIRE(0 <= env_begin && env_begin <= env_end && env_end <= f->E, PHX_ERR_INVALID,
+              "env range out of bounds");
+  PHX_CUDA(cudaSetDevice(f->device));
+  PHX_CUDA(cudaDeviceSynchronize());
+  const size_t n = (size_t)(env_end - env_begin);
+  PHX_CUDA(cudaMemcpy(host_counts, f->d_trace_cnt + env_begin, sizeof(int32_t) * n,
+                      cudaMemcpyDeviceToHost));
+  PHX_CUDA(cudaMemcpy(host_msgs, f->d_trace + (size_t)env_begin * f->spec.trace_capacity,
+                      sizeof(int4) * n * f->spec.trace_capacity, cudaMemcpyDeviceToHost));
+  return PHX_OK;
+}
+
+int32_t phx_poll_errors(phx_env* env, int32_t* n_bad, int32_t* first_env, int32_t* code,
+                        int32_t clear) {
+  PHX_REQUIRE(env != nullptr, PHX_ERR_INVALID, "env is NULL");
+  Family* f = env->fam;
+  PHX_CUDA(cudaSetDevice(f->device));
+  PHX_CUDA(cudaDeviceSynchronize());
+  uint32_t n = 0;
+  PHX_CUDA(cudaMemcpy(&n, f->d_nfaults, sizeof(n), cudaMemcpyDeviceToHost));
+  int32_t first = -1, c = 0;
+  if (n != 0) {
+    std::vector<uint32_t> h((size_t)f->E);
+    PHX_CUDA(cudaMemcpy(h.data(), f->d_err, sizeof(uint32_t) * (size_t)f->E,
+                        cudaMemcpyDeviceToHost));
+    for (int e = 0; e < f->E; ++e)
+      if (h[e] != 0) { first = e; c = (int32_t)h[e]; break; }
+    if (clear) {
+      PHX_CUDA(cudaMemset(f->d_err, 0, sizeof(uint32_t) * (size_t)f->E));
+      PHX_CUDA(cudaMemset(f->d_nfaults, 0, sizeof(uint32_t)));
+    }
+  }
+  if (n_bad) *n_bad = (int32_t)n;
+  if (first_env) *first_env = first;
+  if (code) *code = c;
+  return PHX_OK;
+}
+
+}  // extern "C"

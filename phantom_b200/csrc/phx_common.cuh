@@ -1,0 +1,113 @@
+// phx_common.cuh -- shared host/device plumbing of libphx.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/phx.h"
+
+namespace phx {
+
+// ------------------------------------------------------------------ host error plumbing
+void set_error(const std::string& msg);  // thread-local, read by phx_last_error()
+
+#define PHX_CUDA(call)                                                              \
+  do {                                                                              \
+    cudaError_t err__ = (call);                                                     \
+    if (err__ != cudaSuccess) {                                                     \
+      ::phx::set_error(std::string(#call) + ": " + cudaGetErrorString(err__));      \
+      return PHX_ERR_CUDA;                                                          \
+    }                                                                               \
+  } while (0)
+
+#define PHX_REQUIRE(cond, code, msg)   \
+  do {                                 \
+    if (!(cond)) {                     \
+      ::phx::set_error(msg);           \
+      return (code);                   \
+    }                                  \
+  } while (0)
+
+inline bool mask_bit(const uint32_t* m, int i) { return (m[i >> 5] >> (i & 31)) & 1u; }
+
+// --------------------------------------------------------------------- per-env bookkeeping
+// Env header, one int4 per env:  x = PhantomEnv.current_step (phantom/env.py:252)
+//                                y = episode (RNG contract coordinate)
+//                                z = FSM stage index (phantom/fsm.py:171)
+//                                w = reserved
+// PhantomEnv._terminations / _truncations (phantom/env.py:71-72) are bitmasks over the
+// strategic index, stored as uint32 [W][E].
+
+struct StepIO {
+  // inputs
+  const float* actions;        // [T,E,S,A]
+  const uint8_t* action_mask;  // [T,E,S] or null
+  // outputs (any may be null = not wanted)
+  float* obs;            // [T,E,S,O]
+  uint8_t* obs_mask;     // [T,E,S]
+  float* reward;         // [T,E,S]
+  uint8_t* reward_mask;  // [T,E,S]
+  uint8_t* term;         // [T,E,S]
+  uint8_t* trunc;        // [T,E,S]
+  uint8_t* all_done;     // [T,E,2]
+};
+
+// Faults: sticky per-env error word, first code wins; a global counter lets
+// phx_poll_errors skip the scan when nothing happened.
+struct FaultSink {
+  uint32_t* err;       // [E]
+  uint32_t* n_faults;  // [1]
+};
+
+__device__ __forceinline__ void raise_fault(const FaultSink& f, int env, uint32_t code) {
+  if (code != 0u && f.err[env] == 0u) {  // env is owned by exactly one tile: no race
+    f.err[env] = code;
+    atomicAdd(f.n_faults, 1u);
+  }
+}
+
+// Message trace (Resolver.tracked_messages, phantom/resolvers.py:41-60): rows of the last
+// step, [E, cap] int4 = (sender | recv << 8 | type << 16, payload0, payload1, round).
+struct TraceSink {
+  int4* rows;    // [E, cap]
+  int32_t* cnt;  // [E]
+  int32_t cap;
+};
+
+__device__ __forceinline__ int4 trace_row(int sender, int recv, int type, int p0, int p1,
+                                          int round) {
+  return make_int4(sender | (recv << 8) | (type << 16), p0, p1, round);
+}
+
+// ------------------------------------------------------------------------ memory helpers
+__device__ __forceinline__ float ld_stream(const float* p) { return __ldcs(p); }
+__device__ __forceinline__ void st_stream(float* p, float v) { __stcs(p, v); }
+__device__ __forceinline__ void st_stream(float4* p, float4 v) { __stcs(p, v); }
+
+// cp.async.bulk shared::cta -> global (TMA bulk store, SASS UBLKCP).  `bytes` % 16 == 0,
+// both addresses 16-byte aligned.  Issued by ONE thread after the writers of `smem_src`
+// have fenced (fence.proxy.async) and synchronised.
+__device__ __forceinline__ void bulk_store(void* gmem_dst, const void* smem_src,
+                                           uint32_t bytes) {
+  const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem_src);
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gmem_dst),
+               "r"(s), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() {
+  asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {  // smem source reusable
+  asm volatile("cp.async.bulk.wait_group.read %0;\n" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait() {  // writes complete
+  asm volatile("cp.async.bulk.wait_group %0;\n" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+}
+
+}  // namespace phx

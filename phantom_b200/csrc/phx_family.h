@@ -1,0 +1,58 @@
+// phx_family.h -- host-side base class of a device program family.
+//
+// A family owns the HBM-resident state of E env instances of one env class and launches
+// the fused reset / step kernels for it.  The generic per-env bookkeeping (clock, episode,
+// stage, done sets, fault words, message trace) lives here; the agent state columns and the
+// kernels live in fam_<name>.cu.
+#pragma once
+#include <vector>
+
+#include "phx_common.cuh"
+
+namespace phx {
+
+class Family {
+ public:
+  virtual ~Family();
+
+  // Validates the spec against the family's domain and allocates state.
+  virtual int32_t init(const phx_spec& spec) = 0;
+  virtual int32_t reset(const uint8_t* env_mask, float* obs, uint8_t* obs_mask,
+                        cudaStream_t stream) = 0;
+  virtual int32_t rollout(int32_t T, const StepIO& io, cudaStream_t stream) = 0;
+  // Family state columns (field >= PHX_FIELD_FAMILY); returns PHX_ERR_INVALID if unknown.
+  virtual int32_t family_field(int32_t field, int32_t index, void** dev_ptr, size_t* bytes) = 0;
+  virtual const char* exec_name() const = 0;
+
+  int32_t base_init(const phx_spec& spec, int32_t num_envs, int32_t device, uint64_t seed,
+                    int64_t env_offset);
+  int32_t field_ptr(int32_t field, int32_t index, void** dev_ptr, size_t* bytes);
+
+  phx_spec spec{};
+  int32_t E = 0;
+  int32_t device = 0;
+  uint64_t seed = 0;
+  int64_t env_offset = 0;
+  int32_t mask_words = 1;  // W = ceil(S / 32)
+
+  int4* d_hdr = nullptr;       // [E]
+  uint32_t* d_term = nullptr;  // [W][E]
+  uint32_t* d_trunc = nullptr; // [W][E]
+  uint32_t* d_err = nullptr;   // [E]
+  uint32_t* d_nfaults = nullptr;  // [1]
+  int4* d_trace = nullptr;     // [E, cap]
+  int32_t* d_trace_cnt = nullptr;  // [E]
+
+  // staging for the *_host entry points
+  void* d_stage = nullptr;
+  size_t stage_bytes = 0;
+  cudaStream_t own_stream = nullptr;
+
+  FaultSink fault_sink() const { return FaultSink{d_err, d_nfaults}; }
+  TraceSink trace_sink() const { return TraceSink{d_trace, d_trace_cnt, spec.trace_capacity}; }
+  bool tracking() const { return (spec.flags & PHX_FLAG_TRACK_MESSAGES) != 0; }
+};
+
+Family* make_supply_chain_family();
+
+}  // namespace phx

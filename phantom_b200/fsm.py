@@ -1,0 +1,88 @@
+"""FiniteStateMachineEnv (reference: phantom/fsm.py:12-380).
+
+Host side: stage registration and the reference's validation errors.  The stage-gated step
+loop, the reward / observation caches and the transition run on the device
+(PHX_ENV_FSM); only handler-less (deterministic) stages lower.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, Mapping, Optional, Sequence
+
+from .env import PhantomEnv
+from .network import Network
+from .types import AgentID, StageID
+
+
+class FSMValidationError(Exception):
+    pass
+
+
+class FSMRuntimeError(Exception):
+    pass
+
+
+class FSMStage:
+    def __init__(self, stage_id: StageID, acting_agents: Sequence[AgentID],
+                 rewarded_agents: Optional[Sequence[AgentID]] = None,
+                 next_stages: Optional[Sequence[StageID]] = None,
+                 handler: Optional[Callable[[], StageID]] = None) -> None:
+        self.id = stage_id
+        self.acting_agents = acting_agents
+        self.rewarded_agents = rewarded_agents
+        self.next_stages = next_stages or []
+        self.handler = handler
+
+    def __call__(self, handler_fn):
+        handler_fn._decorator = self
+        self.handler = handler_fn
+        return handler_fn
+
+
+class FiniteStateMachineEnv(PhantomEnv):
+    def __init__(self, num_steps: int, network: Network, initial_stage: StageID,
+                 env_supertype=None, agent_supertypes=None,
+                 stages: Optional[Sequence[FSMStage]] = None, **batch_kwargs) -> None:
+        super().__init__(num_steps, network, env_supertype, agent_supertypes, **batch_kwargs)
+        self._initial_stage = initial_stage
+        self._stages: Dict[StageID, FSMStage] = {}
+        self.previous_stage: Optional[StageID] = None
+        for st in stages or []:
+            self._stages.setdefault(st.id, st)
+        for name in dir(type(self)):
+            attr = getattr(type(self), name, None)
+            if callable(attr) and hasattr(attr, "_decorator"):
+                if attr._decorator.id in self._stages:
+                    raise FSMValidationError(f"Found multiple stages with ID '{attr._decorator.id}'")
+                self._stages[attr._decorator.id] = attr._decorator
+        if not self._stages:
+            raise FSMValidationError("No registered stages.")
+        if initial_stage not in self._stages:
+            raise FSMValidationError(f"Initial stage '{initial_stage}' is not a valid stage")
+        for st in self._stages.values():
+            for nxt in st.next_stages:
+                if nxt not in self._stages:
+                    raise FSMValidationError(
+                        f"Next stage '{nxt}' given in stage '{st.id}' is not a valid stage")
+        for st in self._stages.values():
+            if len(st.next_stages) != 1 and st.handler is None:
+                raise FSMValidationError(
+                    f"Stage '{st.id}' without handler must have exactly one next stage "
+                    f"(got {len(st.next_stages)})")
+
+    @property
+    def initial_stage(self) -> StageID:
+        return self._initial_stage
+
+    @property
+    def current_stage(self):
+        from . import _lib as L
+        import numpy as np
+
+        ids = list(self._stages)
+        if not self.is_live:
+            return self._initial_stage
+        col = self.field(L.FIELD_STAGE, np.int32)
+        return ids[int(col[0])] if self.num_envs == 1 else col
+
+    def is_fsm_deterministic(self) -> bool:
+        return all(len(s.next_stages) == 1 for s in self._stages.values())

@@ -1,0 +1,158 @@
+"""Lowering: Python env objects -> flat `phx_spec` (include/phx.h).
+
+Walks exactly the objects the reference's step loop consults:
+  agent order            Network.agents insertion order   (phantom/network.py:96, env.py:142)
+  strategic agents       isinstance(a, StrategicAgent)    (phantom/env.py:147-159)
+  edges                  the directed graph               (phantom/network.py:122-123,224-231)
+  payload whitelists     _sender_types / _receiver_types matched against the agent's exact
+                         class name                       (phantom/network.py:315-331)
+  resolver options       round_limit, enable_tracking     (phantom/resolvers.py:109-120)
+  network options        ignore_connection_errors, enforce_msg_payload_checks
+  FSM stages             acting / rewarded / next         (phantom/fsm.py:45-63)
+  Stackelberg groups     leader_agents / follower_agents  (phantom/stackelberg.py:47-48)
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List
+
+from . import _lib as L
+from . import families
+from .agents import Agent, StrategicAgent
+from .errors import NotLowerableError
+from .resolvers import BatchResolver
+
+_DEVICE_ONLY_METHODS = (
+    "handle_batch", "handle_message", "generate_messages", "pre_message_resolution",
+    "post_message_resolution", "encode_observation", "decode_action", "compute_reward",
+    "is_terminated", "is_truncated",
+)
+
+
+def _check_no_python_logic(agent: Agent) -> None:
+    """A user subclass of a device agent class must not (re)define per-message logic in
+    Python: it would be silently ignored by the kernel."""
+    for klass in type(agent).__mro__:
+        if klass.__dict__.get("__phx_device_class__", False):
+            return
+        if klass in (Agent, StrategicAgent, object):
+            break
+        for name, attr in klass.__dict__.items():
+            if name in _DEVICE_ONLY_METHODS or hasattr(attr, "_message_type"):
+                raise NotLowerableError(
+                    f"agent class '{klass.__name__}' defines '{name}' in Python but the step "
+                    "loop runs on the GPU; only registered device programs can supply "
+                    "per-message logic (phantom_b200 has no CPU fallback)")
+    raise NotLowerableError(
+        f"agent '{agent.id}' of class '{type(agent).__name__}' has no device program "
+        "(__phx_family__ / __phx_kind__); phantom_b200 has no CPU fallback")
+
+
+def lower(env, exec_mode: str = "auto", auto_reset: bool = False) -> L.PhxSpec:
+    from .fsm import FiniteStateMachineEnv
+    from .stackelberg import StackelbergEnv
+
+    net = env.network
+    agents: List[Agent] = list(net.agents.values())
+    if not agents:
+        raise NotLowerableError("env has no agents")
+    if len(agents) > L.PHX_MAX_AGENTS:
+        raise NotLowerableError(f"more than {L.PHX_MAX_AGENTS} agents per env")
+    for a in agents:
+        _check_no_python_logic(a)
+    fam_names = {type(a).__phx_family__ for a in agents}
+    if len(fam_names) != 1 or None in fam_names:
+        raise NotLowerableError(f"agents belong to different device families: {fam_names}")
+    info = families.get(fam_names.pop())
+
+    spec = L.PhxSpec()
+    spec.struct_size = C.sizeof(L.PhxSpec)
+    spec.family = info.family_id
+    spec.exec_mode = L.EXEC_MODES[exec_mode]
+    spec.num_steps = int(env.num_steps)
+    spec.n_agents = len(agents)
+    spec.obs_dim, spec.act_dim = info.obs_dim, info.act_dim
+
+    slot = {a.id: i for i, a in enumerate(agents)}
+    n_strat = 0
+    for i, a in enumerate(agents):
+        spec.agent_kind[i] = int(type(a).__phx_kind__)
+        if isinstance(a, StrategicAgent):
+            spec.strategic_index[i] = n_strat
+            n_strat += 1
+        else:
+            spec.strategic_index[i] = -1
+        a._phx_slot = i
+        for nb in net.neighbours(a.id):
+            L.set_mask(spec.adjacency[i], slot[nb])
+    spec.n_strategic = n_strat
+
+    # payload whitelists -> per-slot bitmasks
+    if len(info.payload_types) > L.PHX_MAX_TYPES:
+        raise NotLowerableError("too many payload types")
+    spec.n_payload_types = len(info.payload_types)
+    for t, cls in enumerate(info.payload_types):
+        if not hasattr(cls, "_sender_types") or not hasattr(cls, "_receiver_types"):
+            raise NotLowerableError(
+                f"payload class {cls.__name__} must use the msg_payload decorator")
+        for i, a in enumerate(agents):
+            name = type(a).__name__
+            if cls._sender_types is None or name in cls._sender_types:
+                L.set_mask(spec.type_sender_ok[t], i)
+            if cls._receiver_types is None or name in cls._receiver_types:
+                L.set_mask(spec.type_receiver_ok[t], i)
+
+    # resolver / network options
+    res = net.resolver
+    if not isinstance(res, BatchResolver):
+        raise NotLowerableError(
+            f"resolver {type(res).__name__}: only BatchResolver has a device implementation")
+    spec.round_limit = -1 if res.round_limit is None else int(res.round_limit)
+    flags = 0
+    if net.ignore_connection_errors:
+        flags |= L.FLAG_IGNORE_CONNECTION_ERRORS
+    if not net.enforce_msg_payload_checks:
+        flags |= L.FLAG_NO_PAYLOAD_CHECKS
+    if res.enable_tracking:
+        flags |= L.FLAG_TRACK_MESSAGES
+        spec.trace_capacity = int(info.trace_capacity(env, agents))
+    if auto_reset:
+        flags |= L.FLAG_AUTO_RESET
+    spec.flags = flags
+
+    # step-loop kind
+    if isinstance(env, FiniteStateMachineEnv):
+        spec.env_kind = L.ENV_FSM
+        stage_ids = list(env._stages)
+        if len(stage_ids) > L.PHX_MAX_STAGES:
+            raise NotLowerableError(f"more than {L.PHX_MAX_STAGES} FSM stages")
+        spec.n_stages = len(stage_ids)
+        spec.initial_stage = stage_ids.index(env.initial_stage)
+        for k, sid in enumerate(stage_ids):
+            st = env._stages[sid]
+            if st.handler is not None:
+                raise NotLowerableError(
+                    f"FSM stage '{sid}' has a Python handler; only handler-less "
+                    "(deterministic) stages lower to the device (SURVEY.md 8f row 4)")
+            for aid in st.acting_agents:
+                L.set_mask(spec.stages[k].acting, slot[aid])
+            if st.rewarded_agents is None:
+                spec.stages[k].rewarded_is_none = 1
+            else:
+                for aid in st.rewarded_agents:
+                    L.set_mask(spec.stages[k].rewarded, slot[aid])
+            spec.stages[k].next_stage = stage_ids.index(st.next_stages[0])
+    elif isinstance(env, StackelbergEnv):
+        spec.env_kind = L.ENV_STACKELBERG
+        for aid in env.leader_agents:
+            L.set_mask(spec.leaders, slot[aid])
+        for aid in env.follower_agents:
+            L.set_mask(spec.followers, slot[aid])
+    else:
+        spec.env_kind = L.ENV_BASE
+    if spec.env_kind not in info.env_kinds:
+        raise NotLowerableError(
+            f"family '{info.name}' has no kernel for env kind {spec.env_kind}")
+
+    info.collect(env, agents, spec)
+    return spec
