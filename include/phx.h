@@ -237,6 +237,12 @@ int32_t phx_get_trace(phx_env* env, int32_t env_begin, int32_t env_end, int32_t*
 int32_t phx_poll_errors(phx_env* env, int32_t* n_bad, int32_t* first_env, int32_t* code,
                         int32_t clear);
 
+/* Self-test hook: evaluates the kernels' float32(n / den) routine (observation encoding,
+ * supply_chain.py:124-134) for n = lo .. lo+count-1 on `device` into host_out float[count].
+ * Lets tests compare the device arithmetic exhaustively against numpy's float32(n / den). */
+int32_t phx_selftest_ratio(int32_t device, int32_t den, int32_t lo, int32_t count,
+                           float* host_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -104,6 +104,7 @@ SYMBOLS = {
     "phx_get_trace": (C.c_int32, [_P, C.c_int32, C.c_int32, _P, _P]),
     "phx_poll_errors": (C.c_int32, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                     C.POINTER(C.c_int32), C.c_int32]),
+    "phx_selftest_ratio": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
 }
 
 

@@ -56,6 +56,7 @@ struct ScPlan {
   uint32_t push_ord, push_ordresp;
   uint64_t seed;
   uint32_t env_offset;
+  float max_stock_f, rcp_stock, cap_f, rcp_cap;  // obs denominators and RN(1/d)
 };
 
 struct ScArgs {
@@ -68,30 +69,45 @@ struct ScArgs {
   TraceSink trace;
 };
 
-__device__ __forceinline__ float sc_ratio(int num, float den) {
-  // reference: float32(int / int) computed in float64 then cast.  RN32(RN64(n/d)) equals the
-  // correctly rounded float32 quotient here: |n| < 2^24 and d <= 2^12 are exact in float32,
-  // and n/d with d | 4*25 has a binary expansion of period <= 20 < 29, so the float64
-  // rounding can never land on a float32 tie (DESIGN.md "float parity").
-  return __fdiv_rn((float)num, den);
+// float32(n / d) exactly as the reference computes it (float64 division, then cast):
+// Markstein's FMA sequence with the correctly rounded reciprocal rcp = RN(1/d) yields the
+// correctly rounded float32 quotient, and RN32(RN64(n/d)) == RN32(n/d) here because |n| < 2^24
+// and d < 2^24 are exact in float32 and n/d with d | 100 has a binary expansion of period
+// <= 20 < 29 bits, so the float64 rounding can never land on a float32 tie.  Checked
+// exhaustively on the device by tests/test_gpu_supply_chain.py::test_ratio_exhaustive.
+__device__ __forceinline__ float sc_ratio(int num, float den, float rcp) {
+  const float x = (float)num;
+  const float q = __fmul_rn(x, rcp);
+  const float r = __fmaf_rn(-den, q, x);
+  return __fmaf_rn(r, rcp, q);
 }
 
+constexpr int SC_BLOCK = 64;
+
 // One thread per env; T steps per launch with the env state in registers.
-template <int NC, bool TRACK>
-__global__ void __launch_bounds__(128) sc_fast_kernel(const ScArgs a) {
-  __shared__ __align__(16) float obs_stage[4][96];
+//   NC        number of customers if known at compile time (0 = runtime, up to 30)
+//   TRACK     record Resolver.tracked_messages rows (T == 1)
+//   HAS_MASK  an action_mask plane is supplied
+//   FULL_IO   all seven output planes are written; otherwise only obs, reward and all_done
+//             (the four per-agent mask planes are constant for this env class)
+template <int NC, bool TRACK, bool HAS_MASK, bool FULL_IO>
+__global__ void __launch_bounds__(SC_BLOCK) sc_fast_kernel(const ScArgs a) {
+  __shared__ __align__(16) float obs_stage[SC_BLOCK / 32][96];
 
   const ScPlan& p = a.p;
-  const int e = blockIdx.x * 128 + threadIdx.x;
+  const int e = blockIdx.x * SC_BLOCK + threadIdx.x;
   const bool live = e < p.E;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nc = NC > 0 ? NC : p.nc;
   const uint32_t env_id = p.env_offset + (uint32_t)e;
-  const float cap_f = (float)(nc * p.max_order);
-  const float max_stock_f = (float)p.max_stock;
+  const float cap_f = p.cap_f, rcp_cap = p.rcp_cap;
+  const float max_stock_f = p.max_stock_f, rcp_stock = p.rcp_stock;
+  const uint32_t all_customers = nc >= 32 ? 0xFFFFFFFFu : ((1u << nc) - 1u);
+  const bool all_delivered = p.deliver_ord == all_customers;
   // vector path for obs needs a full warp and 16-byte aligned rows
-  const bool warp_full = (blockIdx.x * 128 + warp * 32 + 32) <= p.E;
-  const bool vec_obs = warp_full && ((p.E & 3) == 0) && a.io.obs != nullptr;
+  const bool warp_full = (blockIdx.x * SC_BLOCK + warp * 32 + 32) <= p.E;
+  const bool vec_obs = warp_full && ((p.E & 3) == 0);
+  const uint32_t E = (uint32_t)p.E;
 
   int2 h = make_int2(0, 0);
   int4 s = make_int4(0, 0, 0, 0);
@@ -99,24 +115,35 @@ __global__ void __launch_bounds__(128) sc_fast_kernel(const ScArgs a) {
     h = *reinterpret_cast<const int2*>(a.hdr + e);
     s = a.shop[e];
   }
-  uint32_t fault = 0;
+  // bit 0: a step ran without a shop action, bit 1: with one (selects p.fault[] afterwards);
+  // bit 2: an action outside the contract was seen
+  uint32_t seen = 0;
+
+  // row = t * E + e indexes every [T,E,...] plane (the host guarantees T * E * 3 < 2^32)
+  uint32_t row = (uint32_t)e;
+
+  // actions are prefetched two steps ahead: the load latency (DRAM, ~1 us) is hidden behind
+  // two steps of arithmetic instead of being exposed once per step
+  float a_cur = 0.f, a_nxt = 0.f;
+  if (live) {
+    a_cur = ld_stream(a.io.actions + row);
+    if (a.T > 1) a_nxt = ld_stream(a.io.actions + row + E);
+  }
 
   for (int t = 0; t < a.T; ++t) {
-    const size_t row = (size_t)t * p.E + e;
-    float act = 0.f;
+    float a_nn = 0.f;
+    if (live && t + 2 < a.T) a_nn = ld_stream(a.io.actions + row + 2 * E);
+    const float act = a_cur;
     bool has = true;
-    if (live) {
-      if (a.io.action_mask) has = a.io.action_mask[row] != 0;
-      act = ld_stream(a.io.actions + row);
-    }
+    if (HAS_MASK) has = live ? (a.io.action_mask[row] != 0) : false;
     h.x += 1;  // env.py:252
 
     // ---- acting phase (env.py:320-336), agent order SHOP, WAREHOUSE, CUST1..N
     // ShopAgent.decode_action: min(int(round(a)), max_stock - stock); python round() of a
     // float32 is round-half-even == cvt.rni
     const int ask = min(__float2int_rn(act), p.max_stock - s.x);
-    if (has && !(fabsf(act) <= SC_MAX_ABS_ACTION)) fault = fault ? fault : PHX_FAULT_INVALID_ACTION;
-    if (fault == 0) fault = p.fault[has ? 1 : 0];
+    if (HAS_MASK) seen |= has ? 2u : 1u;
+    if (has && !(fabsf(act) <= SC_MAX_ABS_ACTION)) seen |= 4u;
 
     int cnt = 0;
     int4* trow = nullptr;
@@ -125,50 +152,71 @@ __global__ void __launch_bounds__(128) sc_fast_kernel(const ScArgs a) {
       if (has && p.push_req) trow[cnt++] = trace_row(0, 1, SC_STOCK_REQUEST, ask, 0, 0);
     }
 
-    // ---- pre_message_resolution (supply_chain.py:93-96)
-    s.y = 0;
-    s.z = 0;
-
-    // ---- round 0, receiver SHOP: orders are filled serially in push (= customer) order
-    // from the stock held BEFORE this step's delivery (delivery arrives in round 1).
+    // ---- customers' OrderRequest sizes (supply_chain.py:64), RNG stream 0, idx = customer
+    // ---- pre_message_resolution (supply_chain.py:93-96): sales = missed_sales = 0
+    // ---- round 0, receiver SHOP: handle_order_request (supply_chain.py:104-122), serially in
+    // push (= customer) order, from the stock held BEFORE this step's delivery.  One order:
+    //   sold = min(want, stock); missed += want - sold; stock -= sold; sales += sold
+    // (covers both branches of the reference, including negative stock: want >= 0 > stock
+    // sells `stock` and leaves 0).  sales telescopes to stock_before - stock_after.
+    const int stock_before = s.x;
+    int wanted_total = 0;
+    int want[NC > 0 ? NC : 1];
     int sold_each[NC > 0 ? NC : 1];
-    int order_each[NC > 0 ? NC : 1];
+    (void)sold_each;
 #pragma unroll
-    for (int b = 0; b < (NC > 0 ? (NC + 3) / 4 : 8); ++b) {
+    for (int b = 0; b < (NC > 0 ? (NC + 3) / 4 : (SC_MAX_CUSTOMERS + 3) / 4); ++b) {
       if (NC == 0 && b * 4 >= nc) break;
-      const Philox4 blk = rng_block(p.seed, env_id, (uint32_t)h.y, (uint32_t)h.x, SC_STREAM_ORDER, b);
+      const Philox4 blk =
+          rng_block(p.seed, env_id, (uint32_t)h.y, (uint32_t)h.x, SC_STREAM_ORDER, b);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int i = b * 4 + k;
-        if (i >= nc) break;
-        const int want = rng_randint(blk.w[k], (uint32_t)p.max_order);  // supply_chain.py:64
-        if (TRACK && live && ((p.push_ord >> i) & 1u))
-          trow[cnt++] = trace_row(2 + i, 0, SC_ORDER_REQUEST, want, 0, 0);
-        int sold = 0;
-        if ((p.deliver_ord >> i) & 1u) {  // handle_order_request, supply_chain.py:104-122
-          if (want > s.x) {
-            s.z += want - s.x;
-            sold = s.x;
-            s.x = 0;
-          } else {
-            sold = want;
-            s.x -= want;
-          }
-          s.y += sold;
+        const int w = rng_randint(blk.w[k], (uint32_t)p.max_order);
+        if (NC > 0) {
+          if (i < NC) want[i < NC ? i : 0] = w;
+        } else if (i < nc && ((p.deliver_ord >> i) & 1u)) {  // runtime-N path: fill in place
+          const int sold = min(w, s.x);
+          s.x -= sold;
+          wanted_total += w;
         }
-        if (NC > 0) { sold_each[i] = sold; order_each[i] = want; }
       }
     }
-    (void)order_each;
-    if (TRACK && live) {
+    if (NC > 0) {
+      if (all_delivered) {
+#pragma unroll
+        for (int i = 0; i < (NC > 0 ? NC : 1); ++i) {
+          const int sold = min(want[i], s.x);
+          s.x -= sold;
+          wanted_total += want[i];
+          if (TRACK) sold_each[i] = sold;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < (NC > 0 ? NC : 1); ++i) {
+          int sold = 0;
+          if ((p.deliver_ord >> i) & 1u) {
+            sold = min(want[i], s.x);
+            s.x -= sold;
+            wanted_total += want[i];
+          }
+          if (TRACK) sold_each[i] = sold;
+        }
+      }
+    }
+    s.y = stock_before - s.x;
+    s.z = wanted_total - s.y;
+
+    if (TRACK && NC > 0 && live) {
+#pragma unroll
+      for (int i = 0; i < (NC > 0 ? NC : 1); ++i)
+        if ((p.push_ord >> i) & 1u) trow[cnt++] = trace_row(2 + i, 0, SC_ORDER_REQUEST, want[i], 0, 0);
       // responses generated in round 0, in receiver first-arrival order: WAREHOUSE, SHOP
       if (has && p.push_resp) trow[cnt++] = trace_row(1, 0, SC_STOCK_RESPONSE, ask, 0, 1);
-      if (NC > 0) {
 #pragma unroll
-        for (int i = 0; i < (NC > 0 ? NC : 1); ++i)
-          if ((p.push_ordresp >> i) & 1u)
-            trow[cnt++] = trace_row(0, 2 + i, SC_ORDER_RESPONSE, sold_each[i], 0, 1);
-      }
+      for (int i = 0; i < (NC > 0 ? NC : 1); ++i)
+        if ((p.push_ordresp >> i) & 1u)
+          trow[cnt++] = trace_row(0, 2 + i, SC_ORDER_RESPONSE, sold_each[i], 0, 1);
       a.trace.cnt[e] = cnt;
     }
 
@@ -179,7 +227,8 @@ __global__ void __launch_bounds__(128) sc_fast_kernel(const ScArgs a) {
     }
 
     // ---- outputs (env.py:273-303).  The shop never terminates (agents.py:307,323).
-    const double reward64 = __dsub_rn((double)s.y, __dmul_rn(0.1, (double)s.x));
+    // compute_reward: sales - 0.1 * stock in float64, no FMA contraction (two roundings)
+    const float reward = (float)__dsub_rn((double)s.y, __dmul_rn(0.1, (double)s.x));
     const bool at_max = h.x == p.num_steps;  // env.py:312-318
 
     if ((p.flags & PHX_FLAG_AUTO_RESET) && at_max) {
@@ -188,11 +237,12 @@ __global__ void __launch_bounds__(128) sc_fast_kernel(const ScArgs a) {
       h.x = 0;
       h.y += 1;
     }
-    const float o0 = sc_ratio(s.x, max_stock_f);
-    const float o1 = sc_ratio(s.y, cap_f);
-    const float o2 = sc_ratio(s.z, cap_f);
+    const float o0 = sc_ratio(s.x, max_stock_f, rcp_stock);
+    const float o1 = sc_ratio(s.y, cap_f, rcp_cap);
+    const float o2 = sc_ratio(s.z, cap_f, rcp_cap);
 
     if (vec_obs) {
+      // [32 envs x 3 floats] transposed through shared memory -> 24 coalesced 16-byte stores
       float* st = obs_stage[warp];
       st[lane * 3 + 0] = o0;
       st[lane * 3 + 1] = o1;
@@ -200,30 +250,46 @@ __global__ void __launch_bounds__(128) sc_fast_kernel(const ScArgs a) {
       __syncwarp();
       if (lane < 24) {
         const float4 v = reinterpret_cast<const float4*>(st)[lane];
-        float4* dst = reinterpret_cast<float4*>(a.io.obs + ((size_t)t * p.E + (e - lane)) * 3);
-        st_stream(dst + lane, v);
+        st_stream(reinterpret_cast<float4*>(a.io.obs + (size_t)(row - lane) * 3) + lane, v);
       }
       __syncwarp();
-    } else if (live && a.io.obs) {
-      float* o = a.io.obs + row * 3;
+    } else if (live) {
+      float* o = a.io.obs + (size_t)row * 3;
       o[0] = o0; o[1] = o1; o[2] = o2;
     }
     if (live) {
-      if (a.io.reward) st_stream(a.io.reward + row, (float)reward64);
-      if (a.io.obs_mask) a.io.obs_mask[row] = 1;
-      if (a.io.reward_mask) a.io.reward_mask[row] = 1;
-      if (a.io.term) a.io.term[row] = 0;
-      if (a.io.trunc) a.io.trunc[row] = 0;
-      if (a.io.all_done)
-        reinterpret_cast<uchar2*>(a.io.all_done)[row] = make_uchar2(0, at_max ? 1 : 0);
+      st_stream(a.io.reward + row, reward);
+      reinterpret_cast<uchar2*>(a.io.all_done)[row] = make_uchar2(0, at_max ? 1 : 0);
+      if (FULL_IO) {
+        a.io.obs_mask[row] = 1;
+        a.io.reward_mask[row] = 1;
+        a.io.term[row] = 0;
+        a.io.trunc[row] = 0;
+      }
     }
+
+    a_cur = a_nxt;
+    a_nxt = a_nn;
+    row += E;
   }
 
   if (live) {
     *reinterpret_cast<int2*>(a.hdr + e) = h;
     a.shop[e] = s;
+    uint32_t fault = 0;
+    if (!HAS_MASK) seen |= 2u;
+    // first fault in event order: a bad action is detected in decode_action, before any send
+    if (seen & 4u) fault = PHX_FAULT_INVALID_ACTION;
+    else if ((seen & 2u) && p.fault[1]) fault = p.fault[1];
+    else if ((seen & 1u) && p.fault[0]) fault = p.fault[0];
     if (fault) raise_fault(a.faults, e, fault);
   }
+}
+
+// float32(n / den) through the kernel's own routine, for the exhaustive parity test.
+__global__ void sc_ratio_selftest_kernel(int lo, int n, float den, float rcp, float* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = sc_ratio(lo + i, den, rcp);
 }
 
 // PhantomEnv.reset (env.py:185-237) for the masked envs.
@@ -242,10 +308,9 @@ __global__ void sc_reset_kernel(ScPlan p, int4* hdr, int4* shop, uint32_t* term,
   term[e] = 0;
   trunc[e] = 0;
   if (obs) {
-    const float cap_f = (float)(p.nc * p.max_order);
-    obs[e * 3 + 0] = sc_ratio(s.x, (float)p.max_stock);
-    obs[e * 3 + 1] = sc_ratio(s.y, cap_f);
-    obs[e * 3 + 2] = sc_ratio(s.z, cap_f);
+    obs[e * 3 + 0] = sc_ratio(s.x, p.max_stock_f, p.rcp_stock);
+    obs[e * 3 + 1] = sc_ratio(s.y, p.cap_f, p.rcp_cap);
+    obs[e * 3 + 2] = sc_ratio(s.z, p.cap_f, p.rcp_cap);
   }
   if (obs_mask) obs_mask[e] = 1;
 }
@@ -259,7 +324,10 @@ __global__ void sc_init_kernel(int E, int4* hdr, int4* shop) {
 
 class SupplyChainFamily final : public Family {
  public:
-  ~SupplyChainFamily() override { cudaFree(d_shop); }
+  ~SupplyChainFamily() override {
+    cudaFree(d_shop);
+    cudaFree(d_scratch);
+  }
 
   int32_t init(const phx_spec& s) override {
     PHX_REQUIRE(s.env_kind == PHX_ENV_BASE, PHX_ERR_UNSUPPORTED,
@@ -319,6 +387,10 @@ class SupplyChainFamily final : public Family {
     p.flags = s.flags;
     p.seed = seed;
     p.env_offset = (uint32_t)env_offset;
+    p.max_stock_f = (float)p.max_stock;
+    p.rcp_stock = 1.0f / p.max_stock_f;  // IEEE division: correctly rounded
+    p.cap_f = (float)(p.nc * p.max_order);
+    p.rcp_cap = 1.0f / p.cap_f;
     for (int has = 0; has < 2; ++has) {
       uint32_t fault = 0;
       bool push_req = false, deliver_req = false;
@@ -387,19 +459,60 @@ class SupplyChainFamily final : public Family {
     a.io = io;
     a.faults = fault_sink();
     a.trace = trace_sink();
-    const int grid = (E + 127) / 128;
+    const int grid = (E + SC_BLOCK - 1) / SC_BLOCK;
     const bool track = tracking();
     PHX_REQUIRE(!track || T == 1, PHX_ERR_INVALID,
                 "message tracking records one step: use phx_step (T == 1)");
+    PHX_REQUIRE((uint64_t)T * (uint64_t)E * 3ull < (1ull << 32), PHX_ERR_INVALID,
+                "T * num_envs too large for one launch (row index is 32-bit): split the rollout");
+    // Two output layouts are compiled: "lean" = obs + reward + all_done, "full" = all seven
+    // planes.  Any other combination of NULLs runs "full" into scratch planes.
+    const bool lean = a.io.obs && a.io.reward && a.io.all_done && !a.io.obs_mask &&
+                      !a.io.reward_mask && !a.io.term && !a.io.trunc;
+    if (!lean) {
+      const size_t n = (size_t)T * E;
+      const size_t need = n * 12 + n * 4 + n * 6;
+      if (need > scratch_bytes) {
+        PHX_CUDA(cudaStreamSynchronize(stream));
+        if (d_scratch) PHX_CUDA(cudaFree(d_scratch));
+        d_scratch = nullptr;
+        scratch_bytes = 0;
+        PHX_CUDA(cudaMalloc(&d_scratch, need));
+        scratch_bytes = need;
+      }
+      uint8_t* q = (uint8_t*)d_scratch;
+      if (!a.io.obs) a.io.obs = (float*)q;
+      q += n * 12;
+      if (!a.io.reward) a.io.reward = (float*)q;
+      q += n * 4;
+      if (!a.io.obs_mask) a.io.obs_mask = q;
+      q += n;
+      if (!a.io.reward_mask) a.io.reward_mask = q;
+      q += n;
+      if (!a.io.term) a.io.term = q;
+      q += n;
+      if (!a.io.trunc) a.io.trunc = q;
+      q += n;
+      if (!a.io.all_done) a.io.all_done = q;
+    }
+    const bool mask = a.io.action_mask != nullptr;
+#define SC_LAUNCH(NC_, TRACK_)                                                              \
+  do {                                                                                      \
+    if (mask && !lean) sc_fast_kernel<NC_, TRACK_, true, true><<<grid, SC_BLOCK, 0, stream>>>(a);  \
+    else if (mask) sc_fast_kernel<NC_, TRACK_, true, false><<<grid, SC_BLOCK, 0, stream>>>(a);     \
+    else if (!lean) sc_fast_kernel<NC_, TRACK_, false, true><<<grid, SC_BLOCK, 0, stream>>>(a);    \
+    else sc_fast_kernel<NC_, TRACK_, false, false><<<grid, SC_BLOCK, 0, stream>>>(a);              \
+  } while (0)
     if (plan.nc == 5) {
-      if (track) sc_fast_kernel<5, true><<<grid, 128, 0, stream>>>(a);
-      else sc_fast_kernel<5, false><<<grid, 128, 0, stream>>>(a);
+      if (track) SC_LAUNCH(5, true);
+      else SC_LAUNCH(5, false);
     } else {
       PHX_REQUIRE(!track, PHX_ERR_UNSUPPORTED,
                   "message tracking on the fast path is built for 5 customers; "
                   "use PHX_EXEC_QUEUE");
-      sc_fast_kernel<0, false><<<grid, 128, 0, stream>>>(a);
+      SC_LAUNCH(0, false);
     }
+#undef SC_LAUNCH
     PHX_CUDA(cudaGetLastError());
     return PHX_OK;
   }
@@ -419,10 +532,25 @@ class SupplyChainFamily final : public Family {
  private:
   ScPlan plan{};
   int4* d_shop = nullptr;
+  void* d_scratch = nullptr;  // planes the caller did not ask for (non-lean layouts)
+  size_t scratch_bytes = 0;
 };
 
 }  // namespace
 
 Family* make_supply_chain_family() { return new SupplyChainFamily(); }
+
+int32_t selftest_ratio(int32_t device, int32_t den, int32_t lo, int32_t count, float* host_out) {
+  PHX_REQUIRE(den > 0 && count > 0 && host_out != nullptr, PHX_ERR_INVALID, "bad arguments");
+  PHX_CUDA(cudaSetDevice(device));
+  float* d = nullptr;
+  PHX_CUDA(cudaMalloc(&d, sizeof(float) * (size_t)count));
+  const float den_f = (float)den;
+  sc_ratio_selftest_kernel<<<(count + 255) / 256, 256>>>(lo, count, den_f, 1.0f / den_f, d);
+  cudaError_t err = cudaMemcpy(host_out, d, sizeof(float) * (size_t)count, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  PHX_CUDA(err);
+  return PHX_OK;
+}
 
 }  // namespace phx

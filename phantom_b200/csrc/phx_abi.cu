@@ -372,4 +372,9 @@ int32_t phx_poll_errors(phx_env* env, int32_t* n_bad, int32_t* first_env, int32_
   return PHX_OK;
 }
 
+int32_t phx_selftest_ratio(int32_t device, int32_t den, int32_t lo, int32_t count,
+                           float* host_out) {
+  return phx::selftest_ratio(device, den, lo, count, host_out);
+}
+
 }  // extern "C"

@@ -54,5 +54,6 @@ class Family {
 };
 
 Family* make_supply_chain_family();
+int32_t selftest_ratio(int32_t device, int32_t den, int32_t lo, int32_t count, float* host_out);
 
 }  // namespace phx

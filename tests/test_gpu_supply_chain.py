@@ -342,3 +342,19 @@ def test_nondefault_customer_count(sc):
             ref = v.step(A[t, :, 0, 0])
             assert np.array_equal(obs[t], ref["obs"]), (n, t)
         env.close()
+
+
+def test_ratio_exhaustive():
+    """Observation arithmetic: the kernel's float32(n / d) (Markstein FMA sequence with the
+    correctly rounded reciprocal) equals numpy's float32(float64(n) / d) -- the reference's
+    `np.array([n / d], dtype=np.float32)` -- for EVERY n the action contract allows
+    (|n| <= 2^21) and the denominators of the shipped configs."""
+    from phantom_b200 import _lib as L
+
+    for den in (100, 25, 5, 40, 65):
+        lo, count = -(1 << 21), (1 << 22) + 1
+        out = np.empty(count, np.float32)
+        L.check(L.lib.phx_selftest_ratio(0, den, lo, count, out.ctypes.data))
+        n = np.arange(lo, lo + count, dtype=np.float64)
+        want = (n / den).astype(np.float32)
+        assert np.array_equal(out, want), den
