@@ -7,11 +7,17 @@ The reference draws from process-global generators (`np.random.randint` at
 examples/environments/supply_chain/supply_chain.py:64, `np.random.shuffle` at
 phantom/resolvers.py:151, ...), which cannot be reproduced across 65 536
 concurrently stepped envs.  "Identical seeds" therefore means: both sides consume the
-same stateless stream
+same stateless stream of 24-bit draws
 
-    u32(seed, env, episode, step, stream, idx) =
+    d24(seed, env, episode, step, stream, idx) = slot (idx % 5) of
         Philox4x32-10( key = (seed & 0xffffffff, seed >> 32),
-                       ctr = (env, episode, step, (stream << 16) | (idx >> 2)) )[idx & 3]
+                       ctr = (env, episode, step, (stream << 16) | (idx // 5)) )
+
+  one 128-bit Philox block (w0..w3) yields FIVE 24-bit draws:
+      slot k < 4 :  w_k >> 8
+      slot 4     :  (w0 & 0xff) << 16 | (w1 & 0xff) << 8 | (w2 & 0xff)
+  (24 bits = a float32 mantissa, so uniform01 is exact; 5 draws per block instead of 4
+  32-bit words is what lets one block serve the five customers of the supply chain)
 
   env     global env index (independent of how envs are sharded over GPUs)
   episode number of resets this env has seen minus one (0 for the first episode)
@@ -21,8 +27,9 @@ same stateless stream
   idx     index of the draw within that site and step (e.g. the customer index)
 
 Derived distributions:
-  randint(n)  := (u32 * n) >> 32          (multiply-shift; replaces np.random.randint(n))
-  uniform01() := (u32 >> 8) * 2**-24      (float32-exact, in [0, 1))
+  randint(n)  := (d24 * n) >> 24          (multiply-shift; replaces np.random.randint(n);
+                                           bias <= n / 2^24)
+  uniform01() := d24 * 2**-24             (float32-exact, in [0, 1))
 
 Philox4x32-10 is Salmon et al., "Parallel random numbers: as easy as 1, 2, 3" (SC'11),
 with the standard Random123 constants; checked below against the Random123 known-answer
@@ -78,37 +85,44 @@ def philox4x32_np(c0, c1, c2, c3, k0, k1, rounds: int = 10):
 
 
 # ------------------------------------------------------------------ the contract proper
-def u32(seed: int, env: int, episode: int, step: int, stream: int, idx: int) -> int:
+def _slots(w):
+    """The five 24-bit draws of one block (works on ints and on numpy arrays)."""
+    return (w[0] >> 8, w[1] >> 8, w[2] >> 8, w[3] >> 8,
+            ((w[0] & 0xFF) << 16) | ((w[1] & 0xFF) << 8) | (w[2] & 0xFF))
+
+
+def d24(seed: int, env: int, episode: int, step: int, stream: int, idx: int) -> int:
     words = philox4x32(
-        (env, episode, step, ((stream & 0xFFFF) << 16) | ((idx >> 2) & 0xFFFF)),
+        (env, episode, step, ((stream & 0xFFFF) << 16) | ((idx // 5) & 0xFFFF)),
         (seed & MASK, (seed >> 32) & MASK),
     )
-    return words[idx & 3]
+    return _slots(words)[idx % 5]
 
 
-def u32_np(seed: int, env, episode, step, stream: int, idx):
+def d24_np(seed: int, env, episode, step, stream: int, idx):
     """Vectorised contract draw; env/episode/step/idx broadcast against each other."""
     idx = np.asarray(idx, dtype=np.int64)
-    c3 = ((stream & 0xFFFF) << 16) | ((idx >> 2) & 0xFFFF)
+    c3 = ((stream & 0xFFFF) << 16) | ((idx // 5) & 0xFFFF)
     w = philox4x32_np(env, episode, step, c3, seed & MASK, (seed >> 32) & MASK)
-    sel = np.broadcast_to(idx & 3, w[0].shape)
-    return np.choose(sel, w).astype(np.uint32)
+    slots = _slots(w)
+    sel = np.broadcast_to(idx % 5, w[0].shape)
+    return np.choose(sel, slots).astype(np.uint32)
 
 
-def randint(n: int, word: int) -> int:
-    return (int(word) * int(n)) >> 32
+def randint(n: int, draw: int) -> int:
+    return (int(draw) * int(n)) >> 24
 
 
-def randint_np(n: int, words) -> np.ndarray:
-    return ((np.asarray(words).astype(np.uint64) * np.uint64(n)) >> np.uint64(32)).astype(np.int32)
+def randint_np(n: int, draws) -> np.ndarray:
+    return ((np.asarray(draws).astype(np.uint64) * np.uint64(n)) >> np.uint64(24)).astype(np.int32)
 
 
-def uniform01(word: int) -> float:
-    return float(np.float32(int(word) >> 8) * np.float32(2.0**-24))
+def uniform01(draw: int) -> float:
+    return float(np.float32(int(draw)) * np.float32(2.0**-24))
 
 
-def uniform01_np(words) -> np.ndarray:
-    return (np.asarray(words, dtype=np.uint32) >> np.uint32(8)).astype(np.float32) * np.float32(2.0**-24)
+def uniform01_np(draws) -> np.ndarray:
+    return np.asarray(draws, dtype=np.uint32).astype(np.float32) * np.float32(2.0**-24)
 
 
 # Random123 known-answer vectors for philox4x32-10 (kat_vectors in the Random123
@@ -140,10 +154,13 @@ class StepStream:
     def begin(self, episode: int, step: int) -> None:
         self.episode, self.step, self.k = episode, step, 0
 
-    def next_u32(self) -> int:
-        w = u32(self.seed, self.env, self.episode, self.step, self.stream, self.k)
+    def next_d24(self) -> int:
+        d = d24(self.seed, self.env, self.episode, self.step, self.stream, self.k)
         self.k += 1
-        return w
+        return d
 
     def randint(self, n: int) -> int:
-        return randint(n, self.next_u32())
+        return randint(n, self.next_d24())
+
+    def uniform01(self) -> float:
+        return uniform01(self.next_d24())

@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libphx.so")
+# PHX_LIB overrides the library path (A/B builds of the same sources; tools/ab_variants.sh)
+LIB_PATH = os.environ.get("PHX_LIB") or os.path.join(_HERE, "libphx.so")
 
 PHX_MAX_AGENTS = 128
 PHX_MAX_TYPES = 16

@@ -82,7 +82,38 @@ __device__ __forceinline__ float sc_ratio(int num, float den, float rcp) {
   return __fmaf_rn(r, rcp, q);
 }
 
-constexpr int SC_BLOCK = 64;
+// Tuning knobs (defaults = the measured best, see profiles/README.md; override with -D for A/B)
+#ifndef SC_BLOCK_THREADS
+#define SC_BLOCK_THREADS 64
+#endif
+#ifndef SC_OVERLAP_RNG
+#define SC_OVERLAP_RNG 0  // 1: draw step t+1's orders during step t
+#endif
+#ifndef SC_VEC_OBS
+#define SC_VEC_OBS 0      // 1: obs rows transposed through smem into 16-byte stores
+#endif
+#ifndef SC_REWARD_F64
+#define SC_REWARD_F64 0   // 1: reference-literal float64 reward arithmetic
+#endif
+#ifndef SC_RING_DEPTH
+#define SC_RING_DEPTH 8   // action prefetch ring (steps in flight + 1)
+#endif
+constexpr int SC_BLOCK = SC_BLOCK_THREADS;
+constexpr int SC_RING = SC_RING_DEPTH;
+
+// The NC order sizes of one (episode, step): rng stream SC_STREAM_ORDER, idx = customer.
+template <int NC>
+__device__ __forceinline__ void sc_draw_orders(const ScPlan& p, uint32_t env_id, uint32_t episode,
+                                               uint32_t step, int (&want)[NC > 0 ? NC : 1]) {
+#pragma unroll
+  for (int b = 0; b < (NC + 4) / 5; ++b) {
+    const Philox4 blk = rng_block(p.seed, env_id, episode, step, SC_STREAM_ORDER, b);
+#pragma unroll
+    for (int k = 0; k < 5; ++k)
+      if (b * 5 + k < NC)
+        want[b * 5 + k] = rng_randint(rng_slot_hi(blk, k), (uint32_t)p.max_order);
+  }
+}
 
 // One thread per env; T steps per launch with the env state in registers.
 //   NC        number of customers if known at compile time (0 = runtime, up to 30)
@@ -95,8 +126,12 @@ __global__ void __launch_bounds__(SC_BLOCK) sc_fast_kernel(const ScArgs a) {
   __shared__ __align__(16) float obs_stage[SC_BLOCK / 32][96];
 
   const ScPlan& p = a.p;
-  const int e = blockIdx.x * SC_BLOCK + threadIdx.x;
-  const bool live = e < p.E;
+  // Threads past the last env re-run env E-1: they compute and store bit-identical values
+  // (a benign duplicate), which keeps every `live` test out of the step loop.
+  const int e_raw = blockIdx.x * SC_BLOCK + threadIdx.x;
+  const bool real = e_raw < p.E;
+  const int e = real ? e_raw : p.E - 1;
+  constexpr bool live = true;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nc = NC > 0 ? NC : p.nc;
   const uint32_t env_id = p.env_offset + (uint32_t)e;
@@ -105,8 +140,8 @@ __global__ void __launch_bounds__(SC_BLOCK) sc_fast_kernel(const ScArgs a) {
   const uint32_t all_customers = nc >= 32 ? 0xFFFFFFFFu : ((1u << nc) - 1u);
   const bool all_delivered = p.deliver_ord == all_customers;
   // vector path for obs needs a full warp and 16-byte aligned rows
-  const bool warp_full = (blockIdx.x * SC_BLOCK + warp * 32 + 32) <= p.E;
-  const bool vec_obs = warp_full && ((p.E & 3) == 0);
+  const bool warp_full = (blockIdx.x * SC_BLOCK + warp * 32 + 32) <= (uint32_t)p.E;
+  const bool vec_obs = SC_VEC_OBS && warp_full && ((p.E & 3) == 0);
   const uint32_t E = (uint32_t)p.E;
 
   int2 h = make_int2(0, 0);
@@ -122,21 +157,49 @@ __global__ void __launch_bounds__(SC_BLOCK) sc_fast_kernel(const ScArgs a) {
   // row = t * E + e indexes every [T,E,...] plane (the host guarantees T * E * 3 < 2^32)
   uint32_t row = (uint32_t)e;
 
-  // actions are prefetched two steps ahead: the load latency (DRAM, ~1 us) is hidden behind
-  // two steps of arithmetic instead of being exposed once per step
-  float a_cur = 0.f, a_nxt = 0.f;
-  if (live) {
-    a_cur = ld_stream(a.io.actions + row);
-    if (a.T > 1) a_nxt = ld_stream(a.io.actions + row + E);
+  // Actions are prefetched SC_RING-1 steps ahead with cp.async (LDGSTS) into a per-thread
+  // shared-memory ring.  HBM latency is ~0.6 us = more than one whole step of this kernel
+  // (measured: a register prefetch one step ahead still stalled 31% of all warp samples on
+  // its scoreboard); the async copy has no register to wait on and the ring gives it
+  // SC_RING-1 steps to land.
+  __shared__ float act_ring[SC_RING][SC_BLOCK];
+#pragma unroll
+  for (int k = 0; k < SC_RING - 1; ++k) {
+    if (k < a.T) cp_async4(&act_ring[k][threadIdx.x], a.io.actions + row + (uint32_t)k * E);
+    cp_async_commit();
   }
 
+  // customers' OrderRequest sizes (supply_chain.py:64): RNG stream 0, idx = customer.  The
+  // draws of step t+1 depend only on the (episode, step) coordinates, so they are computed
+  // during step t: the two independent Philox chains then overlap the serial order fill.
+  int want_nxt[NC > 0 ? NC : 1];
+  if (NC > 0 && SC_OVERLAP_RNG)
+    sc_draw_orders<NC>(p, env_id, (uint32_t)h.y, (uint32_t)(h.x + 1), want_nxt);
+
   for (int t = 0; t < a.T; ++t) {
-    float a_nn = 0.f;
-    if (live && t + 2 < a.T) a_nn = ld_stream(a.io.actions + row + 2 * E);
-    const float act = a_cur;
+    if (t + SC_RING - 1 < a.T)
+      cp_async4(&act_ring[(t + SC_RING - 1) % SC_RING][threadIdx.x],
+                a.io.actions + row + (uint32_t)(SC_RING - 1) * E);
+    cp_async_commit();
+    cp_async_wait<SC_RING - 1>();  // this step's copy (issued SC_RING-1 steps ago) has landed
+    const float act = act_ring[t % SC_RING][threadIdx.x];
     bool has = true;
     if (HAS_MASK) has = live ? (a.io.action_mask[row] != 0) : false;
     h.x += 1;  // env.py:252
+    const bool at_max = h.x == p.num_steps;  // env.py:312-318
+    const bool wrap = (p.flags & PHX_FLAG_AUTO_RESET) && at_max;
+
+    int want[NC > 0 ? NC : 1];
+    if (NC > 0 && !SC_OVERLAP_RNG) {
+      sc_draw_orders<NC>(p, env_id, (uint32_t)h.y, (uint32_t)h.x, want);
+    } else if (NC > 0) {
+#pragma unroll
+      for (int i = 0; i < (NC > 0 ? NC : 1); ++i) want[i] = want_nxt[i];
+      // unconditional (one wasted draw on the last step) so that it shares a basic block
+      // with the fill below and the scheduler can interleave the two
+      sc_draw_orders<NC>(p, env_id, (uint32_t)(wrap ? h.y + 1 : h.y),
+                         (uint32_t)(wrap ? 1 : h.x + 1), want_nxt);
+    }
 
     // ---- acting phase (env.py:320-336), agent order SHOP, WAREHOUSE, CUST1..N
     // ShopAgent.decode_action: min(int(round(a)), max_stock - stock); python round() of a
@@ -147,12 +210,11 @@ __global__ void __launch_bounds__(SC_BLOCK) sc_fast_kernel(const ScArgs a) {
 
     int cnt = 0;
     int4* trow = nullptr;
-    if (TRACK && live) {
+    if (TRACK && real) {
       trow = a.trace.rows + (size_t)e * a.trace.cap;
       if (has && p.push_req) trow[cnt++] = trace_row(0, 1, SC_STOCK_REQUEST, ask, 0, 0);
     }
 
-    // ---- customers' OrderRequest sizes (supply_chain.py:64), RNG stream 0, idx = customer
     // ---- pre_message_resolution (supply_chain.py:93-96): sales = missed_sales = 0
     // ---- round 0, receiver SHOP: handle_order_request (supply_chain.py:104-122), serially in
     // push (= customer) order, from the stock held BEFORE this step's delivery.  One order:
@@ -161,24 +223,21 @@ __global__ void __launch_bounds__(SC_BLOCK) sc_fast_kernel(const ScArgs a) {
     // sells `stock` and leaves 0).  sales telescopes to stock_before - stock_after.
     const int stock_before = s.x;
     int wanted_total = 0;
-    int want[NC > 0 ? NC : 1];
     int sold_each[NC > 0 ? NC : 1];
     (void)sold_each;
+    if (NC == 0) {  // runtime-N path: draw and fill in place
+      for (int b = 0; b * 5 < nc; ++b) {
+        const Philox4 blk =
+            rng_block(p.seed, env_id, (uint32_t)h.y, (uint32_t)h.x, SC_STREAM_ORDER, b);
 #pragma unroll
-    for (int b = 0; b < (NC > 0 ? (NC + 3) / 4 : (SC_MAX_CUSTOMERS + 3) / 4); ++b) {
-      if (NC == 0 && b * 4 >= nc) break;
-      const Philox4 blk =
-          rng_block(p.seed, env_id, (uint32_t)h.y, (uint32_t)h.x, SC_STREAM_ORDER, b);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int i = b * 4 + k;
-        const int w = rng_randint(blk.w[k], (uint32_t)p.max_order);
-        if (NC > 0) {
-          if (i < NC) want[i < NC ? i : 0] = w;
-        } else if (i < nc && ((p.deliver_ord >> i) & 1u)) {  // runtime-N path: fill in place
-          const int sold = min(w, s.x);
-          s.x -= sold;
-          wanted_total += w;
+        for (int k = 0; k < 5; ++k) {
+          const int i = b * 5 + k;
+          const int w = rng_randint(rng_slot_hi(blk, k), (uint32_t)p.max_order);
+          if (i < nc && ((p.deliver_ord >> i) & 1u)) {
+            const int sold = min(w, s.x);
+            s.x -= sold;
+            wanted_total += w;
+          }
         }
       }
     }
@@ -207,7 +266,7 @@ __global__ void __launch_bounds__(SC_BLOCK) sc_fast_kernel(const ScArgs a) {
     s.y = stock_before - s.x;
     s.z = wanted_total - s.y;
 
-    if (TRACK && NC > 0 && live) {
+    if (TRACK && NC > 0 && real) {
 #pragma unroll
       for (int i = 0; i < (NC > 0 ? NC : 1); ++i)
         if ((p.push_ord >> i) & 1u) trow[cnt++] = trace_row(2 + i, 0, SC_ORDER_REQUEST, want[i], 0, 0);
@@ -227,11 +286,20 @@ __global__ void __launch_bounds__(SC_BLOCK) sc_fast_kernel(const ScArgs a) {
     }
 
     // ---- outputs (env.py:273-303).  The shop never terminates (agents.py:307,323).
-    // compute_reward: sales - 0.1 * stock in float64, no FMA contraction (two roundings)
+    // compute_reward (supply_chain.py:144-147): float32(sales - 0.1 * stock), the product and
+    // the difference rounded in float64 by the reference.  With k = 10*sales - stock the exact
+    // value is k/10; |k| < 2^24, and k/10 is either exactly representable or at least
+    // 2^-24/10 (relative) away from every float32 rounding boundary, far more than the
+    // float64 path's error of a few 2^-53 -- so the reference's result equals the correctly
+    // rounded float32 quotient k/10 (sc_ratio).  Pinned by test_reward_identity (CPU,
+    // exhaustive over k) and the golden / full-size parity tests.
+#if SC_REWARD_F64
     const float reward = (float)__dsub_rn((double)s.y, __dmul_rn(0.1, (double)s.x));
-    const bool at_max = h.x == p.num_steps;  // env.py:312-318
+#else
+    const float reward = sc_ratio(10 * s.y - s.x, 10.0f, 0.1f);
+#endif
 
-    if ((p.flags & PHX_FLAG_AUTO_RESET) && at_max) {
+    if (wrap) {
       // Network.reset -> ShopAgent.reset: only the stock is cleared (supply_chain.py:149)
       s.x = 0;
       h.x = 0;
@@ -268,12 +336,10 @@ __global__ void __launch_bounds__(SC_BLOCK) sc_fast_kernel(const ScArgs a) {
       }
     }
 
-    a_cur = a_nxt;
-    a_nxt = a_nn;
     row += E;
   }
 
-  if (live) {
+  if (real) {
     *reinterpret_cast<int2*>(a.hdr + e) = h;
     a.shop[e] = s;
     uint32_t fault = 0;
@@ -337,7 +403,7 @@ class SupplyChainFamily final : public Family {
                 "(OrderRequest, OrderResponse, StockRequest, StockResponse)");
     PHX_REQUIRE(s.obs_dim == 3 && s.act_dim == 1, PHX_ERR_INVALID,
                 "supply-chain family: obs_dim must be 3 and act_dim 1");
-    PHX_REQUIRE(s.iparams[0] >= 1 && s.iparams[0] <= 4096 && s.iparams[1] >= 0 &&
+    PHX_REQUIRE(s.iparams[0] >= 1 && s.iparams[0] <= 255 && s.iparams[1] >= 0 &&
                     s.iparams[1] <= (1 << 20),
                 PHX_ERR_INVALID, "supply-chain family: max_order / max_stock out of range");
     const bool canonical = is_canonical(s);

@@ -85,6 +85,20 @@ __device__ __forceinline__ float ld_stream(const float* p) { return __ldcs(p); }
 __device__ __forceinline__ void st_stream(float* p, float v) { __stcs(p, v); }
 __device__ __forceinline__ void st_stream(float4* p, float4 v) { __stcs(p, v); }
 
+// cp.async (SASS LDGSTS): 4-byte global -> shared copy that bypasses the register file, so a
+// prefetch has no register scoreboard to trip over; completion is tracked per commit group.
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
+  const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() {
+  asm volatile("cp.async.commit_group;\n" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
 // cp.async.bulk shared::cta -> global (TMA bulk store, SASS UBLKCP).  `bytes` % 16 == 0,
 // both addresses 16-byte aligned.  Issued by ONE thread after the writers of `smem_src`
 // have fenced (fence.proxy.async) and synchronised.

@@ -2,13 +2,15 @@
 //
 // Replaces the reference's process-global draw sites (np.random.randint at
 // examples/environments/supply_chain/supply_chain.py:64, np.random.shuffle at
-// phantom/resolvers.py:151, ...) with a stateless stream:
+// phantom/resolvers.py:151, ...) with a stateless stream of 24-bit draws:
 //
-//   u32(seed, env, episode, step, stream, idx) =
+//   d24(seed, env, episode, step, stream, idx) = slot (idx % 5) of
 //       Philox4x32-10(key = (seed_lo, seed_hi),
-//                     ctr = (env, episode, step, (stream << 16) | (idx >> 2)))[idx & 3]
+//                     ctr = (env, episode, step, (stream << 16) | (idx / 5)))
 //
-// One Philox block therefore serves four consecutive idx of a stream.
+// One 128-bit block (w0..w3) yields FIVE draws: slots 0..3 = w_k >> 8, slot 4 = the low
+// bytes of w0, w1, w2.  24 bits = a float32 mantissa (uniform01 is exact), and five draws
+// per block is what lets ONE Philox block serve the five customers of the supply chain.
 #pragma once
 #include <stdint.h>
 
@@ -39,27 +41,41 @@ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint3
   return out;
 }
 
-// The block holding idx = 4*block .. 4*block+3 of `stream`.
+// The block holding draws idx = 5*block .. 5*block+4 of `stream`.
 __device__ __forceinline__ Philox4 rng_block(uint64_t seed, uint32_t env, uint32_t episode,
                                              uint32_t step, uint32_t stream, uint32_t block) {
   return philox4x32_10(env, episode, step, (stream << 16) | (block & 0xFFFFu),
                        (uint32_t)seed, (uint32_t)(seed >> 32));
 }
 
-__device__ __forceinline__ uint32_t rng_u32(uint64_t seed, uint32_t env, uint32_t episode,
-                                            uint32_t step, uint32_t stream, uint32_t idx) {
-  const Philox4 b = rng_block(seed, env, episode, step, stream, idx >> 2);
-  return b.w[idx & 3];
+// Draw `slot` (0..4) of a block, LEFT-ALIGNED in 32 bits (d24 << 8): with the draw in the
+// top 24 bits, randint is a single multiply-high.
+__device__ __forceinline__ uint32_t rng_slot_hi(const Philox4& b, int slot) {
+  if (slot < 4) return b.w[slot] & 0xFFFFFF00u;
+  // ((w0 & 0xff) << 16 | (w1 & 0xff) << 8 | (w2 & 0xff)) << 8: two byte-permutes + mask
+  const uint32_t t = __byte_perm(b.w[2], b.w[1], 0x7407);  // bytes [x, w2.b0, w1.b0, x]
+  return __byte_perm(t, b.w[0], 0x4210) & 0xFFFFFF00u;      // bytes [0, w2.b0, w1.b0, w0.b0]
 }
 
-// randint(n) := (u32 * n) >> 32   (replaces np.random.randint(n))
-__device__ __forceinline__ int rng_randint(uint32_t word, uint32_t n) {
-  return (int)__umulhi(word, n);
+__device__ __forceinline__ uint32_t rng_d24_hi(uint64_t seed, uint32_t env, uint32_t episode,
+                                               uint32_t step, uint32_t stream, uint32_t idx) {
+  const Philox4 b = rng_block(seed, env, episode, step, stream, idx / 5u);
+  const uint32_t slot = idx % 5u;
+  uint32_t r = rng_slot_hi(b, 4);
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (slot == (uint32_t)k) r = rng_slot_hi(b, k);
+  return r;
 }
 
-// uniform01() := (u32 >> 8) * 2^-24, float32-exact, in [0, 1)
-__device__ __forceinline__ float rng_uniform01(uint32_t word) {
-  return (float)(word >> 8) * 5.9604644775390625e-8f;
+// randint(n) := (d24 * n) >> 24 == umulhi(d24 << 8, n)   (replaces np.random.randint(n))
+__device__ __forceinline__ int rng_randint(uint32_t d24_hi, uint32_t n) {
+  return (int)__umulhi(d24_hi, n);
+}
+
+// uniform01() := d24 * 2^-24, float32-exact, in [0, 1)
+__device__ __forceinline__ float rng_uniform01(uint32_t d24_hi) {
+  return (float)(d24_hi >> 8) * 5.9604644775390625e-8f;
 }
 
 }  // namespace phx

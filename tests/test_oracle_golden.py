@@ -29,11 +29,17 @@ def test_philox_known_answers():
 
 def test_contract_scalar_equals_vectorised():
     env = np.arange(50)
-    for idx in (0, 3, 4, 9):
-        v = rng.u32_np(77, env, 2, 13, 1, idx)
-        s = [rng.u32(77, int(e), 2, 13, 1, idx) for e in env]
-        assert v.tolist() == s
-    assert all(0 <= rng.randint(5, w) < 5 for w in (0, 1, 2**31, 2**32 - 1))
+    for idx in (0, 3, 4, 5, 9, 14):
+        v = rng.d24_np(77, env, 2, 13, 1, idx)
+        s = [rng.d24(77, int(e), 2, 13, 1, idx) for e in env]
+        assert v.tolist() == s and max(s) < 2**24
+    assert all(0 <= rng.randint(5, d) < 5 for d in (0, 1, 2**23, 2**24 - 1))
+    # the five draws of a block: four high 24-bit fields + the three low bytes of w0..w2
+    w = rng.philox4x32((3, 0, 1, 0), (9, 0))
+    assert [rng.d24(9, 3, 0, 1, 0, k) for k in range(5)] == [
+        w[0] >> 8, w[1] >> 8, w[2] >> 8, w[3] >> 8,
+        ((w[0] & 255) << 16) | ((w[1] & 255) << 8) | (w[2] & 255)]
+    assert rng.d24(9, 3, 0, 1, 0, 5) == rng.philox4x32((3, 0, 1, 1), (9, 0))[0] >> 8
 
 
 def test_survey_probe_trace():
