@@ -34,10 +34,10 @@ def msg_handler(message_type):
 
 
 class _DeviceColumn:
-    """Descriptor: agent attribute backed by a state column in HBM."""
+    """Descriptor: agent attribute backed by a state word in HBM (int32 or float32)."""
 
-    def __init__(self, field: int, word: int, default=0):
-        self.field, self.word, self.default = field, word, default
+    def __init__(self, word: int, dtype="int32", default=0):
+        self.word, self.dtype, self.default = word, dtype, default
 
     def __set_name__(self, owner, name):
         self.name = name
@@ -48,7 +48,7 @@ class _DeviceColumn:
         env = getattr(agent, "_phx_env", None)
         if env is None or not env.is_live:
             return agent.__dict__.get("_col_" + self.name, self.default)
-        col = env.agent_column(agent, self.field, self.word)
+        col = env.agent_column(agent, self.word, self.dtype)
         return col.item() if col.size == 1 else col
 
     def __set__(self, agent, value):
@@ -56,11 +56,14 @@ class _DeviceColumn:
         if env is None or not env.is_live:
             agent.__dict__["_col_" + self.name] = value
         else:
-            env.set_agent_column(agent, self.field, self.word, value)
+            import numpy as np
+
+            v = np.asarray(value, dtype=self.dtype)
+            env.set_agent_column(agent, self.word, v.view(np.int32) if v.dtype != np.int32 else v)
 
 
-def device_column(field: int, word: int, default=0) -> _DeviceColumn:
-    return _DeviceColumn(field, word, default)
+def device_column(word: int, dtype="int32", default=0) -> _DeviceColumn:
+    return _DeviceColumn(word, dtype, default)
 
 
 class Agent:

@@ -33,6 +33,7 @@
 #include <cstring>
 #include <string>
 
+#include "phx_engine_host.cuh"
 #include "phx_family.h"
 #include "phx_rng.cuh"
 
@@ -388,9 +389,9 @@ __global__ void sc_init_kernel(int E, int4* hdr, int4* shop) {
   shop[e] = make_int4(0, 0, 0, 0);
 }
 
-class SupplyChainFamily final : public Family {
+class SupplyChainFast final : public Family {
  public:
-  ~SupplyChainFamily() override {
+  ~SupplyChainFast() override {
     cudaFree(d_shop);
     cudaFree(d_scratch);
   }
@@ -406,12 +407,9 @@ class SupplyChainFamily final : public Family {
     PHX_REQUIRE(s.iparams[0] >= 1 && s.iparams[0] <= 255 && s.iparams[1] >= 0 &&
                     s.iparams[1] <= (1 << 20),
                 PHX_ERR_INVALID, "supply-chain family: max_order / max_stock out of range");
-    const bool canonical = is_canonical(s);
-    PHX_REQUIRE(s.exec_mode != PHX_EXEC_FAST || canonical, PHX_ERR_UNSUPPORTED,
+    PHX_REQUIRE(is_canonical(s), PHX_ERR_UNSUPPORTED,
                 "PHX_EXEC_FAST needs the canonical supply-chain layout "
-                "[ShopAgent, FactoryAgent, CustomerAgent x N]");
-    PHX_REQUIRE(canonical && s.exec_mode != PHX_EXEC_QUEUE, PHX_ERR_UNSUPPORTED,
-                "supply-chain queue engine not built yet");
+                "[ShopAgent, FactoryAgent, CustomerAgent x N] with N <= 30");
     PHX_CUDA(cudaMalloc(&d_shop, sizeof(int4) * (size_t)E));
     sc_init_kernel<<<(E + 255) / 256, 256>>>(E, d_hdr, d_shop);
     PHX_CUDA(cudaGetLastError());
@@ -602,9 +600,133 @@ class SupplyChainFamily final : public Family {
   size_t scratch_bytes = 0;
 };
 
+
+// ---------------------------------------------------------------------------------------
+// The same agents as a device program of the generic queue engine (phx_engine.cuh): any agent
+// order and topology (one shop and one factory per env), messages routed dynamically.
+//   state words (per slot; only the shop uses them): stock, sales, missed_sales, delivered
+//   agent_iparam[slot][0] = slot of the peer the agent addresses (customer -> its shop,
+//                           shop -> its factory);  [slot][1] = customer ordinal (RNG idx)
+template <int SEGCAP_>
+struct ScProgram {
+  static constexpr int PW = 1, NWORDS = 4, VW = 0, SEGCAP = SEGCAP_, OBS_DIM = 3;
+  static constexpr bool BATCHED = false;
+
+  static int32_t validate(const phx_spec& s) {
+    PHX_REQUIRE(s.env_kind == PHX_ENV_BASE, PHX_ERR_UNSUPPORTED,
+                "supply-chain family runs under PhantomEnv (PHX_ENV_BASE) only");
+    int shops = 0, customers = 0;
+    for (int i = 0; i < s.n_agents; ++i) {
+      shops += s.agent_kind[i] == SC_SHOP;
+      customers += s.agent_kind[i] == SC_CUSTOMER;
+      PHX_REQUIRE(s.agent_kind[i] >= SC_SHOP && s.agent_kind[i] <= SC_CUSTOMER, PHX_ERR_INVALID,
+                  "unknown supply-chain agent kind");
+    }
+    PHX_REQUIRE(shops == 1, PHX_ERR_UNSUPPORTED, "exactly one ShopAgent per env");
+    PHX_REQUIRE(customers + 1 <= SEGCAP, PHX_ERR_UNSUPPORTED, "too many customers for this queue");
+    return PHX_OK;
+  }
+
+  template <class E>
+  __device__ static void act(const Ctx& c, int* st, bool has_action, const float* action, E& out) {
+    const EngineSpec& sp = *c.spec;
+    if (c.kind == SC_SHOP) {
+      if (!has_action) return;  // Agent.generate_messages default: [] (agents.py:157-158)
+      const float a0 = action[0];
+      if (!(fabsf(a0) <= SC_MAX_ABS_ACTION)) {
+        out.fault = PHX_FAULT_INVALID_ACTION;
+        return;
+      }
+      const int ask = min(__float2int_rn(a0), sp.iparams[1] - st[0]);  // supply_chain.py:136-142
+      out.send(sp.agent_iparam[c.slot][0], SC_STOCK_REQUEST, ask);
+    } else if (c.kind == SC_CUSTOMER) {  // supply_chain.py:61-67
+      const int want = rng_randint(c.rand24_hi(SC_STREAM_ORDER, (uint32_t)sp.agent_iparam[c.slot][1]),
+                                   (uint32_t)sp.iparams[0]);
+      out.send(sp.agent_iparam[c.slot][0], SC_ORDER_REQUEST, want);
+    }
+  }
+
+  __device__ static void view(const Ctx&, const int*, int*) {}
+
+  __device__ static void pre(const Ctx& c, int* st) {
+    if (c.kind == SC_SHOP) st[1] = st[2] = 0;  // supply_chain.py:93-96
+  }
+  __device__ static void post(const Ctx&, int*) {}
+
+  template <class E>
+  __device__ static bool handle(const Ctx& c, int* st, const Msg& m, E& out) {
+    if (c.kind == SC_SHOP) {
+      if (m.type == SC_STOCK_RESPONSE) {  // supply_chain.py:98-102
+        st[3] = m.p[0];
+        st[0] = min(st[0] + m.p[0], c.spec->iparams[1]);
+        return true;
+      }
+      if (m.type == SC_ORDER_REQUEST) {  // supply_chain.py:104-122
+        const int sold = min(m.p[0], st[0]);
+        st[2] += m.p[0] - sold;
+        st[0] -= sold;
+        st[1] += sold;
+        out.send(m.sender, SC_ORDER_RESPONSE, sold);
+        return true;
+      }
+      return false;
+    }
+    if (c.kind == SC_FACTORY) {  // supply_chain.py:40-45
+      if (m.type != SC_STOCK_REQUEST) return false;
+      out.send(m.sender, SC_STOCK_RESPONSE, m.p[0]);
+      return true;
+    }
+    return m.type == SC_ORDER_RESPONSE;  // CustomerAgent.handle_order_response: no-op
+  }
+
+  __device__ static bool encode(const Ctx& c, const int* st, float* obs) {
+    const EngineSpec& sp = *c.spec;
+    obs[0] = sc_ratio(st[0], sp.fparams[0], sp.fparams[1]);
+    obs[1] = sc_ratio(st[1], sp.fparams[2], sp.fparams[3]);
+    obs[2] = sc_ratio(st[2], sp.fparams[2], sp.fparams[3]);
+    return true;
+  }
+  __device__ static float reward(const Ctx&, const int* st) {
+    return sc_ratio(10 * st[1] - st[0], 10.0f, 0.1f);
+  }
+  __device__ static bool terminated(const Ctx&, const int*) { return false; }
+  __device__ static bool truncated(const Ctx&, const int*) { return false; }
+  __device__ static void reset_agent(const Ctx& c, int* st) {
+    if (c.kind == SC_SHOP) st[0] = 0;  // supply_chain.py:149-150
+  }
+};
+
+template <int SEGCAP_>
+class SupplyChainQueue final : public EngineFamily<ScProgram<SEGCAP_>> {
+ public:
+  int32_t init(const phx_spec& s) override {
+    int customers = 0;
+    for (int i = 0; i < s.n_agents; ++i) customers += s.agent_kind[i] == SC_CUSTOMER;
+    PHX_REQUIRE(s.obs_dim == 3 && s.act_dim == 1 && s.n_payload_types == 4, PHX_ERR_INVALID,
+                "supply-chain family: obs_dim 3, act_dim 1, 4 payload types");
+    PHX_REQUIRE(s.iparams[0] >= 1 && s.iparams[0] <= 255 && s.iparams[1] >= 1 &&
+                    s.iparams[1] <= (1 << 20) && customers >= 1,
+                PHX_ERR_INVALID, "supply-chain family: parameters out of range");
+    phx_spec t = s;  // obs denominators and their correctly rounded reciprocals
+    t.fparams[0] = (double)s.iparams[1];
+    t.fparams[1] = (double)(1.0f / (float)s.iparams[1]);
+    t.fparams[2] = (double)(customers * s.iparams[0]);
+    t.fparams[3] = (double)(1.0f / (float)(customers * s.iparams[0]));
+    return EngineFamily<ScProgram<SEGCAP_>>::init(t);
+  }
+};
+
 }  // namespace
 
-Family* make_supply_chain_family() { return new SupplyChainFamily(); }
+Family* make_supply_chain_family(const phx_spec& s) {
+  const bool canonical = SupplyChainFast::is_canonical(s);
+  if (s.exec_mode == PHX_EXEC_FAST || (s.exec_mode == PHX_EXEC_AUTO && canonical))
+    return new SupplyChainFast();
+  int customers = 0;
+  for (int i = 0; i < s.n_agents; ++i) customers += s.agent_kind[i] == SC_CUSTOMER;
+  if (customers + 1 <= 8) return new SupplyChainQueue<8>();
+  return new SupplyChainQueue<32>();
+}
 
 int32_t selftest_ratio(int32_t device, int32_t den, int32_t lo, int32_t count, float* host_out) {
   PHX_REQUIRE(den > 0 && count > 0 && host_out != nullptr, PHX_ERR_INVALID, "bad arguments");

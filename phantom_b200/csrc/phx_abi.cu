@@ -147,7 +147,7 @@ int32_t phx_create(const phx_spec* spec, int32_t num_envs, int32_t device, uint6
   Family* fam = nullptr;
   switch (spec->family) {
     case PHX_FAMILY_SUPPLY_CHAIN:
-      fam = phx::make_supply_chain_family();
+      fam = phx::make_supply_chain_family(*spec);
       break;
     default:
       set_error("no device program for family " + std::to_string(spec->family));

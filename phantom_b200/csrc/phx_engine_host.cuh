@@ -1,0 +1,216 @@
+// phx_engine_host.cuh -- host side of the generic queue engine: a Family implementation that
+// owns the state of E envs of a device program P and launches engine_step_kernel<P, G>.
+#pragma once
+#include <cstring>
+#include <string>
+
+#include "phx_engine.cuh"
+#include "phx_family.h"
+
+namespace phx {
+
+inline uint32_t low_mask(const uint32_t* words) { return words[0]; }
+
+// Lowers the generic part of phx_spec into the engine's kernel-parameter form.
+inline int32_t make_engine_spec(const phx_spec& s, int32_t E, uint64_t seed, int64_t env_offset,
+                                EngineSpec* out) {
+  PHX_REQUIRE(s.n_agents <= ENGINE_MAX_AGENTS, PHX_ERR_UNSUPPORTED,
+              "queue engine (tile variant) supports up to 32 agents per env");
+  EngineSpec& d = *out;
+  std::memset(&d, 0, sizeof(d));
+  d.E = E;
+  d.n_agents = s.n_agents;
+  d.n_strategic = s.n_strategic;
+  d.num_steps = s.num_steps;
+  d.round_limit = s.round_limit;
+  d.env_kind = s.env_kind;
+  d.flags = s.flags;
+  d.obs_dim = s.obs_dim;
+  d.act_dim = s.act_dim;
+  for (int i = 0; i < s.n_agents; ++i) {
+    d.kind[i] = (int8_t)s.agent_kind[i];
+    d.sidx[i] = (int8_t)s.strategic_index[i];
+    d.adj[i] = s.adjacency[i][0];
+    if (s.strategic_index[i] >= 0) d.strategic_mask |= 1u << i;
+    for (int k = 0; k < 4; ++k) d.agent_iparam[i][k] = s.agent_iparam[i][k];
+  }
+  for (int t = 0; t < s.n_payload_types; ++t) {
+    d.sender_ok[t] = s.type_sender_ok[t][0];
+    d.receiver_ok[t] = s.type_receiver_ok[t][0];
+  }
+  d.n_stages = s.n_stages;
+  d.initial_stage = s.env_kind == PHX_ENV_FSM ? s.initial_stage : 0;
+  for (int k = 0; k < s.n_stages && k < PHX_MAX_STAGES; ++k) {
+    d.stage_acting[k] = s.stages[k].acting[0];
+    d.stage_rewarded[k] = s.stages[k].rewarded[0];
+    d.stage_rewarded_none[k] = (uint8_t)(s.stages[k].rewarded_is_none != 0);
+    PHX_REQUIRE(s.stages[k].next_stage >= 0 && s.stages[k].next_stage < s.n_stages,
+                PHX_ERR_INVALID, "FSM stage has an invalid next_stage");
+    d.stage_next[k] = (int8_t)s.stages[k].next_stage;
+  }
+  d.leaders = s.leaders[0];
+  d.followers = s.followers[0];
+  d.seed = seed;
+  d.env_offset = (uint32_t)env_offset;
+  for (int k = 0; k < PHX_MAX_PARAMS; ++k) {
+    d.iparams[k] = s.iparams[k];
+    d.fparams[k] = (float)s.fparams[k];
+  }
+  return PHX_OK;
+}
+
+template <class P>
+__global__ void engine_init_kernel(int E, int G, int4* hdr, int32_t* state, int nwords) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < E) hdr[i] = make_int4(0, -1, 0, 0);  // episode becomes 0 on the first reset
+  (void)state; (void)nwords; (void)G;
+}
+
+// Family backed by the queue engine.  `Field` mapping: PHX_FIELD_FAMILY + w = state word w,
+// int32 [E, G] (slot-major inside an env).
+template <class P>
+class EngineFamily : public Family {
+ public:
+  ~EngineFamily() override {
+    cudaFree(d_state);
+    cudaFree(d_rcache);
+    cudaFree(d_rnone);
+    cudaFree(d_ocache);
+    cudaFree(d_ocached);
+  }
+
+  int32_t init(const phx_spec& s) override {
+    int32_t rc = make_engine_spec(s, E, seed, env_offset, &espec);
+    if (rc != PHX_OK) return rc;
+    rc = P::validate(s);
+    if (rc != PHX_OK) return rc;
+    G = s.n_agents <= 8 ? 8 : (s.n_agents <= 16 ? 16 : 32);
+    PHX_REQUIRE(s.obs_dim <= P::OBS_DIM, PHX_ERR_INVALID, "obs_dim exceeds the family's OBS_DIM");
+    const size_t n = (size_t)E * G;
+    PHX_CUDA(cudaMalloc(&d_state, sizeof(int32_t) * n * (P::NWORDS > 0 ? P::NWORDS : 1)));
+    PHX_CUDA(cudaMemset(d_state, 0, sizeof(int32_t) * n * (P::NWORDS > 0 ? P::NWORDS : 1)));
+    if (s.env_kind != PHX_ENV_BASE) {
+      PHX_CUDA(cudaMalloc(&d_rcache, sizeof(float) * n));
+      PHX_CUDA(cudaMemset(d_rcache, 0, sizeof(float) * n));
+      PHX_CUDA(cudaMalloc(&d_rnone, sizeof(uint32_t) * (size_t)E));
+      PHX_CUDA(cudaMemset(d_rnone, 0, sizeof(uint32_t) * (size_t)E));
+      if (s.env_kind == PHX_ENV_FSM) {
+        PHX_CUDA(cudaMalloc(&d_ocache, sizeof(float) * n * s.obs_dim));
+        PHX_CUDA(cudaMemset(d_ocache, 0, sizeof(float) * n * s.obs_dim));
+        PHX_CUDA(cudaMalloc(&d_ocached, sizeof(uint32_t) * (size_t)E));
+        PHX_CUDA(cudaMemset(d_ocached, 0, sizeof(uint32_t) * (size_t)E));
+      }
+    }
+    engine_init_kernel<P><<<(E + 255) / 256, 256>>>(E, G, d_hdr, d_state, P::NWORDS);
+    PHX_CUDA(cudaGetLastError());
+    // constructor-time agent state (PhantomEnv.__init__ ends with agent.reset(), env.py:122-124)
+    rc = launch_reset(nullptr, nullptr, nullptr, 0, /*count_episode=*/false);
+    if (rc != PHX_OK) return rc;
+    PHX_CUDA(cudaDeviceSynchronize());
+    name = std::string("queue(G=") + std::to_string(G) + ")";
+    return PHX_OK;
+  }
+
+  EngineArgs<P> make_args(int32_t T, const StepIO& io) const {
+    EngineArgs<P> a;
+    a.spec = espec;
+    a.T = T;
+    a.hdr = d_hdr;
+    a.term = d_term;
+    a.trunc = d_trunc;
+    a.state = d_state;
+    a.reward_cache = d_rcache;
+    a.reward_none = d_rnone;
+    a.obs_cache = d_ocache;
+    a.obs_cached = d_ocached;
+    a.io = io;
+    a.faults = fault_sink();
+    a.trace = trace_sink();
+    return a;
+  }
+
+  template <int GG>
+  int32_t launch_step(const EngineArgs<P>& a, cudaStream_t stream) {
+    constexpr int TPB = ENGINE_BLOCK / GG;
+    const size_t smem = sizeof(TileSmem<P, GG>) * TPB;
+    const int grid = (E + TPB - 1) / TPB;
+    if (tracking()) {
+      PHX_CUDA(cudaFuncSetAttribute(engine_step_kernel<P, GG, true>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      engine_step_kernel<P, GG, true><<<grid, ENGINE_BLOCK, smem, stream>>>(a);
+    } else {
+      PHX_CUDA(cudaFuncSetAttribute(engine_step_kernel<P, GG, false>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      engine_step_kernel<P, GG, false><<<grid, ENGINE_BLOCK, smem, stream>>>(a);
+    }
+    PHX_CUDA(cudaGetLastError());
+    return PHX_OK;
+  }
+
+  template <int GG>
+  int32_t launch_reset_g(const EngineArgs<P>& a, const uint8_t* env_mask, float* obs,
+                         uint8_t* obs_mask, cudaStream_t stream) {
+    constexpr int TPB = ENGINE_BLOCK / GG;
+    const size_t smem = sizeof(TileSmem<P, GG>) * TPB;
+    PHX_CUDA(cudaFuncSetAttribute(engine_reset_kernel<P, GG>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    engine_reset_kernel<P, GG><<<(E + TPB - 1) / TPB, ENGINE_BLOCK, smem, stream>>>(a, env_mask, obs,
+                                                                                    obs_mask);
+    PHX_CUDA(cudaGetLastError());
+    return PHX_OK;
+  }
+
+  int32_t launch_reset(const uint8_t* env_mask, float* obs, uint8_t* obs_mask, cudaStream_t stream,
+                       bool count_episode) {
+    StepIO io{};
+    EngineArgs<P> a = make_args(1, io);
+    int32_t rc = G == 8 ? launch_reset_g<8>(a, env_mask, obs, obs_mask, stream)
+                 : G == 16 ? launch_reset_g<16>(a, env_mask, obs, obs_mask, stream)
+                           : launch_reset_g<32>(a, env_mask, obs, obs_mask, stream);
+    if (rc != PHX_OK) return rc;
+    if (!count_episode) {  // undo the episode increment of the constructor-time reset
+      PHX_CUDA(cudaStreamSynchronize(stream));
+      engine_init_kernel<P><<<(E + 255) / 256, 256, 0, stream>>>(E, G, d_hdr, d_state, P::NWORDS);
+      PHX_CUDA(cudaGetLastError());
+    }
+    return PHX_OK;
+  }
+
+  int32_t reset(const uint8_t* env_mask, float* obs, uint8_t* obs_mask,
+                cudaStream_t stream) override {
+    return launch_reset(env_mask, obs, obs_mask, stream, true);
+  }
+
+  int32_t rollout(int32_t T, const StepIO& io, cudaStream_t stream) override {
+    PHX_REQUIRE(!tracking() || T == 1, PHX_ERR_INVALID,
+                "message tracking records one step: use phx_step (T == 1)");
+    EngineArgs<P> a = make_args(T, io);
+    return G == 8 ? launch_step<8>(a, stream)
+           : G == 16 ? launch_step<16>(a, stream)
+                     : launch_step<32>(a, stream);
+  }
+
+  int32_t family_field(int32_t field, int32_t, void** p, size_t* bytes) override {
+    const int w = field - PHX_FIELD_FAMILY;
+    if (w >= 0 && w < P::NWORDS) {
+      *p = d_state + (size_t)w * E * G;
+      *bytes = sizeof(int32_t) * (size_t)E * G;
+      return PHX_OK;
+    }
+    set_error("unknown family field " + std::to_string(field));
+    return PHX_ERR_INVALID;
+  }
+
+  const char* exec_name() const override { return name.c_str(); }
+
+  EngineSpec espec{};
+  int G = 8;
+  int32_t* d_state = nullptr;
+  float* d_rcache = nullptr;
+  uint32_t* d_rnone = nullptr;
+  float* d_ocache = nullptr;
+  uint32_t* d_ocached = nullptr;
+  std::string name;
+};
+
+}  // namespace phx

@@ -53,7 +53,7 @@ class Family {
   bool tracking() const { return (spec.flags & PHX_FLAG_TRACK_MESSAGES) != 0; }
 };
 
-Family* make_supply_chain_family();
+Family* make_supply_chain_family(const phx_spec& spec);
 int32_t selftest_ratio(int32_t device, int32_t den, int32_t lo, int32_t count, float* host_out);
 
 }  // namespace phx

@@ -310,19 +310,34 @@ class PhantomEnv:
         L.check(L.lib.phx_set_field(self._handle, field, index, values.ctypes.data, values.nbytes))
 
     # agent attribute <-> state column plumbing (used by agents.device_column)
-    def agent_column(self, agent: Agent, field: int, word: int) -> np.ndarray:
-        width = getattr(type(agent), "__phx_field_width__", 1)
-        col = self.field(field, np.int32, index=agent._phx_slot, width=width)
-        return col[:, word] if width > 1 else col
+    @property
+    def family(self):
+        from . import families
 
-    def set_agent_column(self, agent: Agent, field: int, word: int, value) -> None:
-        width = getattr(type(agent), "__phx_field_width__", 1)
-        col = self.field(field, np.int32, index=agent._phx_slot, width=width)
-        if width > 1:
-            col[:, word] = value
-        else:
-            col[:] = value
-        self.set_field(field, col, index=agent._phx_slot)
+        return families.get(type(next(iter(self.agents.values()))).__phx_family__)
+
+    @property
+    def tile_width(self) -> int:
+        """Lanes per env of the queue engine (state columns are [E, G], slot-major)."""
+        name = self.exec_name
+        return int(name.split("G=")[1].rstrip(")")) if "G=" in name else 0
+
+    def agent_column(self, agent: Agent, word: int, dtype=np.int32) -> np.ndarray:
+        """State word `word` of `agent` for every env: array [E]."""
+        info = self.family
+        if info.fast_column is not None and not self.exec_name.startswith("queue"):
+            return info.fast_column(self, agent, word)
+        col = self.field(L.FIELD_FAMILY + word, np.int32, width=self.tile_width)
+        return col[:, agent._phx_slot].view(dtype)
+
+    def set_agent_column(self, agent: Agent, word: int, value) -> None:
+        info = self.family
+        if info.fast_column is not None and not self.exec_name.startswith("queue"):
+            info.fast_column(self, agent, word, value)
+            return
+        col = self.field(L.FIELD_FAMILY + word, np.int32, width=self.tile_width)
+        col[:, agent._phx_slot] = np.asarray(value).astype(col.dtype)
+        self.set_field(L.FIELD_FAMILY + word, col)
 
     def tracked_messages_batch(self, env_begin: int = 0, env_end: Optional[int] = None):
         """phx_get_trace: (counts [n], rows [n, cap, 4]) of the last step."""
@@ -402,9 +417,7 @@ class PhantomEnv:
         return self.Step(observations, rewards, terminations, truncations, infos)
 
     def _decode_trace(self) -> List[Message]:
-        from . import families
-
-        info = families.get(type(next(iter(self.agents.values()))).__phx_family__)
+        info = self.family
         counts, rows = self.tracked_messages_batch(0, 1)
         ids = self.agent_ids
         msgs = []

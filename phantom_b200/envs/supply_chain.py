@@ -74,12 +74,11 @@ class ShopAgent(ph.StrategicAgent):
     __phx_family__ = "supply_chain"
     __phx_kind__ = KIND_SHOP
     __phx_device_class__ = True
-    __phx_field_width__ = 4
 
-    stock = device_column(FIELD_SHOP_STATE, 0)
-    sales = device_column(FIELD_SHOP_STATE, 1)
-    missed_sales = device_column(FIELD_SHOP_STATE, 2)
-    delivered_stock = device_column(FIELD_SHOP_STATE, 3)
+    stock = device_column(0)
+    sales = device_column(1)
+    missed_sales = device_column(2)
+    delivered_stock = device_column(3)
 
     def __init__(self, agent_id: str, factory_id: str):
         super().__init__(agent_id)
@@ -102,11 +101,25 @@ def _collect(env, agents, spec) -> None:
             raise NotLowerableError(f"CustomerAgent '{a.id}' addresses unknown shop '{a.shop_id}'")
     spec.iparams[0] = int(getattr(env, "max_order", CUSTOMER_MAX_ORDER_SIZE))
     spec.iparams[1] = int(getattr(env, "max_stock", SHOP_MAX_STOCK))
+    ordinal = 0
     for i, a in enumerate(agents):
         if isinstance(a, CustomerAgent):
             spec.agent_iparam[i][0] = shop._phx_slot
+            spec.agent_iparam[i][1] = ordinal  # RNG idx: k-th customer in agent order
+            ordinal += 1
         elif isinstance(a, ShopAgent):
             spec.agent_iparam[i][0] = factory._phx_slot
+
+
+def _fast_column(env, agent, word, value=None):
+    """Shop state of the thread-per-env kernel: one int4 per env."""
+    import numpy as np
+
+    col = env.field(FIELD_SHOP_STATE, np.int32, width=4)
+    if value is None:
+        return col[:, word]
+    col[:, word] = value
+    env.set_field(FIELD_SHOP_STATE, col)
 
 
 FAMILY = register(FamilyInfo(
@@ -118,6 +131,7 @@ FAMILY = register(FamilyInfo(
     env_kinds=(L.ENV_BASE,),
     collect=_collect,
     trace_capacity=lambda env, agents: 2 * len(agents),
+    fast_column=_fast_column,
 ))
 
 

@@ -21,8 +21,8 @@ class FamilyInfo:
     env_kinds: Tuple[int, ...]               # phx_env_kind values the kernels implement
     collect: Callable                        # (env, agents, spec) -> None; fills params, validates
     trace_capacity: Callable                 # (env, agents) -> int
-    # agent class name -> {attribute: (field id, word index)} for device-backed attributes
-    payload_fields: Dict[str, Sequence[str]] = dataclasses.field(default_factory=dict)
+    # (env, agent, word[, value]) -> column: state access for a family's non-engine kernel
+    fast_column: Optional[Callable] = None
 
 
 REGISTRY: Dict[str, FamilyInfo] = {}

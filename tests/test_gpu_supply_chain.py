@@ -36,9 +36,8 @@ def golden(golden_dir):
 
 
 def shop_state(env):
-    from phantom_b200.envs.supply_chain import FIELD_SHOP_STATE
-
-    return env.field(FIELD_SHOP_STATE, np.int32, width=4)
+    shop = env.agents["SHOP"]
+    return np.stack([np.atleast_1d(env.agent_column(shop, w)) for w in range(4)], axis=1)
 
 
 def assert_step_equal(out, ref, ctx=""):
@@ -62,7 +61,7 @@ def test_native_library_is_loaded(ph):
     assert os.path.basename(_lib.LIB_PATH) == "libphx.so"
 
 
-@pytest.mark.parametrize("exec_mode", ["fast"])
+@pytest.mark.parametrize("exec_mode", ["fast", "queue"])
 def test_single_step_api_matches_reference_golden(sc, golden, exec_mode):
     g = golden
     seed, A, M = int(g["seed"]), g["actions"], g["action_mask"]
@@ -81,14 +80,15 @@ def test_single_step_api_matches_reference_golden(sc, golden, exec_mode):
     env.close()
 
 
-def test_message_trace_matches_reference_tracked_messages(sc, golden):
+@pytest.mark.parametrize("exec_mode", ["fast", "queue"])
+def test_message_trace_matches_reference_tracked_messages(sc, golden, exec_mode):
     """Bit-exact routing: the device trace equals Resolver.tracked_messages of the reference
     (global push order over both rounds) for every step of 3 envs x 2 episodes."""
     g = golden
     seed, A, M = int(g["seed"]), g["actions"], g["action_mask"]
     gm = g["messages"]  # (env, ep, t, sender, recv, type, v0, v1)
     n_env = 3
-    env = sc.SupplyChainEnv(num_envs=n_env, seed=seed, enable_tracking=True)
+    env = sc.SupplyChainEnv(num_envs=n_env, seed=seed, enable_tracking=True, exec_mode=exec_mode)
     for ep in range(A.shape[1]):
         env.reset_batch()
         for t in range(A.shape[2]):
@@ -102,12 +102,13 @@ def test_message_trace_matches_reference_tracked_messages(sc, golden):
     env.close()
 
 
-def test_rollout_equals_single_steps(sc):
+@pytest.mark.parametrize("exec_mode", ["fast", "queue"])
+def test_rollout_equals_single_steps(sc, exec_mode):
     E, T, seed = 1000, 37, 5
     r = np.random.RandomState(0)
     A = r.uniform(-20, 150, size=(T, E, 1, 1)).astype(np.float32)
-    a = sc.SupplyChainEnv(num_envs=E, seed=seed)
-    b = sc.SupplyChainEnv(num_envs=E, seed=seed)
+    a = sc.SupplyChainEnv(num_envs=E, seed=seed, exec_mode=exec_mode)
+    b = sc.SupplyChainEnv(num_envs=E, seed=seed, exec_mode=exec_mode)
     a.reset_batch(); b.reset_batch()
     ro = b.rollout_batch(A)
     for t in range(T):
@@ -328,12 +329,14 @@ def test_rollout_host_roundtrip(sc):
     a.close(); b.close()
 
 
-def test_nondefault_customer_count(sc):
-    """Runtime-N path of the fast kernel (N != 5) against the vectorised oracle."""
+@pytest.mark.parametrize("exec_mode", ["fast", "queue"])
+def test_nondefault_customer_count(sc, exec_mode):
+    """Runtime-N path of the fast kernel (N != 5) and the wider queue tiles (G = 16, 32)
+    against the vectorised oracle."""
     for n in (1, 3, 8, 13):
         E, T, seed = 257, 25, 12
         A = np.random.RandomState(n).uniform(0, 100, size=(T, E, 1, 1)).astype(np.float32)
-        env = sc.SupplyChainEnv(n, num_envs=E, seed=seed)
+        env = sc.SupplyChainEnv(n, num_envs=E, seed=seed, exec_mode=exec_mode)
         v = vectorised.SupplyChainVec(E, seed, n_customers=n)
         env.reset_batch(); v.reset()
         ro = env.rollout_batch(A)
@@ -358,3 +361,66 @@ def test_ratio_exhaustive():
         n = np.arange(lo, lo + count, dtype=np.float64)
         want = (n / den).astype(np.float32)
         assert np.array_equal(out, want), den
+
+
+def test_queue_engine_equals_fast_kernel_full_episode(sc):
+    """Invariance under the kernel variant: schedule-specialised kernel == dynamic queue."""
+    E, T, seed = 4096, 100, 77
+    A = np.random.RandomState(5).uniform(-10, 130, size=(T, E, 1, 1)).astype(np.float32)
+    M = (np.random.RandomState(6).uniform(size=(T, E, 1)) > 0.1).astype(np.uint8)
+    f = sc.SupplyChainEnv(num_envs=E, seed=seed, exec_mode="fast")
+    q = sc.SupplyChainEnv(num_envs=E, seed=seed, exec_mode="queue")
+    assert f.exec_name.startswith("fast") and q.exec_name.startswith("queue")
+    f.reset_batch(); q.reset_batch()
+    a, b = f.rollout_batch(A, M), q.rollout_batch(A, M)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+    assert np.array_equal(shop_state(f), shop_state(q))
+    f.close(); q.close()
+
+
+def test_queue_engine_any_agent_order(sc, ph):
+    """The queue engine is not tied to the example's agent order: customers first, shop
+    last.  Routing (receiver first-arrival order!) changes; compare with the object-level
+    oracle running the same permuted env, including the tracked message order."""
+    seed = 19
+
+    def build(api, mods, stream=None):
+        # agents in the order: CUST1, CUST2, WAREHOUSE, CUST3, SHOP
+        if api is ph:
+            agents = [mods.CustomerAgent("CUST1", "SHOP"), mods.CustomerAgent("CUST2", "SHOP"),
+                      mods.FactoryAgent("WAREHOUSE"), mods.CustomerAgent("CUST3", "SHOP"),
+                      mods.ShopAgent("SHOP", "WAREHOUSE")]
+            net = ph.Network(agents, ph.resolvers.BatchResolver(enable_tracking=True))
+            net.add_connection("SHOP", "WAREHOUSE")
+            net.add_connections_between(["SHOP"], ["CUST1", "CUST2", "CUST3"])
+            env = ph.PhantomEnv(num_steps=20, network=net, seed=seed)
+            env.max_order, env.max_stock = 5, 100
+            return env
+        return None
+
+    env = build(ph, sc)
+    assert env.exec_name.startswith("queue")
+    # oracle twin with the same order
+    st = rng.StepStream(seed, 0, 0)
+    ref_full = wl.build(po, st, n_customers=3, num_steps=20, enable_tracking=True)
+    order = ["CUST1", "CUST2", "WAREHOUSE", "CUST3", "SHOP"]
+    ref_full.network.agents = {k: ref_full.network.agents[k] for k in order}
+    clock = harness.EpisodeClock([st])
+    clock.on_reset(); ref_full.reset(); env.reset()
+    slot = {aid: i for i, aid in enumerate(order)}
+    r = np.random.RandomState(1)
+    for t in range(20):
+        a = {"SHOP": r.uniform(0, 60, size=(1,)).astype(np.float32)}
+        clock.on_step(ref_full)
+        ref_full.network.resolver.clear_tracked_messages()
+        env.network.resolver.clear_tracked_messages()
+        s_ref, s = ref_full.step(a), env.step(a)
+        assert np.array_equal(s.observations["SHOP"], s_ref.observations["SHOP"]), t
+        assert s.truncations == s_ref.truncations
+        got = [(m.sender_id, m.receiver_id, type(m.payload).__name__, m.payload.size)
+               for m in env.network.resolver.tracked_messages]
+        want = [(m.sender_id, m.receiver_id, type(m.payload).__name__, m.payload.size)
+                for m in ref_full.network.resolver.tracked_messages]
+        assert got == want, t
+    env.close()
