@@ -679,14 +679,14 @@ struct ScProgram {
     return m.type == SC_ORDER_RESPONSE;  // CustomerAgent.handle_order_response: no-op
   }
 
-  __device__ static bool encode(const Ctx& c, const int* st, float* obs) {
+  __device__ static bool encode(const Ctx& c, int* st, float* obs) {
     const EngineSpec& sp = *c.spec;
     obs[0] = sc_ratio(st[0], sp.fparams[0], sp.fparams[1]);
     obs[1] = sc_ratio(st[1], sp.fparams[2], sp.fparams[3]);
     obs[2] = sc_ratio(st[2], sp.fparams[2], sp.fparams[3]);
     return true;
   }
-  __device__ static float reward(const Ctx&, const int* st) {
+  __device__ static float reward(const Ctx&, int* st) {
     return sc_ratio(10 * st[1] - st[0], 10.0f, 0.1f);
   }
   __device__ static bool terminated(const Ctx&, const int*) { return false; }

@@ -168,7 +168,8 @@ struct TileSmem {
 
 // The fused step kernel.  P is the device program of a family (see fam_*.cu for the
 // interface: view / act / pre / handle / post / encode / reward / terminated / truncated /
-// reset_agent).
+// reset_agent).  encode and reward receive the mutable agent state: the reference's
+// callbacks may have side effects (the KAT agents count their calls).
 template <class P, int G, bool TRACK>
 __global__ void __launch_bounds__(ENGINE_BLOCK) engine_step_kernel(const EngineArgs<P> a) {
   constexpr int TPB = ENGINE_BLOCK / G;  // env tiles per block
@@ -510,7 +511,8 @@ __global__ void __launch_bounds__(ENGINE_BLOCK) engine_step_kernel(const EngineA
 // PhantomEnv.reset / FiniteStateMachineEnv.reset / StackelbergEnv.reset for masked envs.
 template <class P, int G>
 __global__ void __launch_bounds__(ENGINE_BLOCK)
-engine_reset_kernel(const EngineArgs<P> a, const uint8_t* env_mask, float* obs, uint8_t* obs_mask) {
+engine_reset_kernel(const EngineArgs<P> a, const uint8_t* env_mask, float* obs, uint8_t* obs_mask,
+                    bool agents_only) {
   constexpr int TPB = ENGINE_BLOCK / G;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   TileSmem<P, G>* tiles = reinterpret_cast<TileSmem<P, G>*>(smem_raw);
@@ -540,6 +542,13 @@ engine_reset_kernel(const EngineArgs<P> a, const uint8_t* env_mask, float* obs, 
   ctx.views = &ts.views[0][0];
   ctx.view_stride = P::VW > 0 ? P::VW : 1;
   if (is_agent) P::reset_agent(ctx, st);  // Network.reset -> agent.reset() (network.py:179-184)
+  if (agents_only) {  // PhantomEnv.__init__ ends with agent.reset() only (env.py:122-124)
+    if (env_live) {
+#pragma unroll
+      for (int w = 0; w < P::NWORDS; ++w) a.state[((size_t)w * sp.E + e) * G + slot] = st[w];
+    }
+    return;
+  }
   if (P::VW > 0) {
     if (is_agent) P::view(ctx, st, &ts.views[slot][0]);
     __syncwarp(tmask);

@@ -149,13 +149,13 @@ class EngineFamily : public Family {
 
   template <int GG>
   int32_t launch_reset_g(const EngineArgs<P>& a, const uint8_t* env_mask, float* obs,
-                         uint8_t* obs_mask, cudaStream_t stream) {
+                         uint8_t* obs_mask, cudaStream_t stream, bool agents_only) {
     constexpr int TPB = ENGINE_BLOCK / GG;
     const size_t smem = sizeof(TileSmem<P, GG>) * TPB;
     PHX_CUDA(cudaFuncSetAttribute(engine_reset_kernel<P, GG>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    engine_reset_kernel<P, GG><<<(E + TPB - 1) / TPB, ENGINE_BLOCK, smem, stream>>>(a, env_mask, obs,
-                                                                                    obs_mask);
+    engine_reset_kernel<P, GG><<<(E + TPB - 1) / TPB, ENGINE_BLOCK, smem, stream>>>(
+        a, env_mask, obs, obs_mask, agents_only);
     PHX_CUDA(cudaGetLastError());
     return PHX_OK;
   }
@@ -164,16 +164,10 @@ class EngineFamily : public Family {
                        bool count_episode) {
     StepIO io{};
     EngineArgs<P> a = make_args(1, io);
-    int32_t rc = G == 8 ? launch_reset_g<8>(a, env_mask, obs, obs_mask, stream)
-                 : G == 16 ? launch_reset_g<16>(a, env_mask, obs, obs_mask, stream)
-                           : launch_reset_g<32>(a, env_mask, obs, obs_mask, stream);
-    if (rc != PHX_OK) return rc;
-    if (!count_episode) {  // undo the episode increment of the constructor-time reset
-      PHX_CUDA(cudaStreamSynchronize(stream));
-      engine_init_kernel<P><<<(E + 255) / 256, 256, 0, stream>>>(E, G, d_hdr, d_state, P::NWORDS);
-      PHX_CUDA(cudaGetLastError());
-    }
-    return PHX_OK;
+    const bool ao = !count_episode;
+    return G == 8 ? launch_reset_g<8>(a, env_mask, obs, obs_mask, stream, ao)
+           : G == 16 ? launch_reset_g<16>(a, env_mask, obs, obs_mask, stream, ao)
+                     : launch_reset_g<32>(a, env_mask, obs, obs_mask, stream, ao);
   }
 
   int32_t reset(const uint8_t* env_mask, float* obs, uint8_t* obs_mask,

@@ -1,0 +1,383 @@
+"""The reference's own step-loop / routing known-answer tests, restated once and run twice:
+on the CPU against the oracle (tests/test_oracle_kats.py) and on the B200 against the CUDA
+engine through phantom_b200 (tests/test_gpu_kats.py).
+
+Every scenario cites the reference test it restates; the expected literals are the
+reference's.  `K` is a namespace with the API module (`ph`), the mock agent classes and
+`finish_network` (see oracle/workloads/mock.py, phantom_b200/envs/mock.py).
+"""
+import numpy as np
+import pytest
+
+
+def approx_obs(got, want):
+    """Observations: the reference returns float64 arrays, the device float32 (spec tolerance
+    1e-5 relative)."""
+    assert set(got) == set(want), (got, want)
+    for k in want:
+        np.testing.assert_allclose(np.asarray(got[k], np.float64), np.asarray(want[k], np.float64),
+                                   rtol=1e-5, atol=1e-7)
+
+
+def counts(agent):
+    return (int(agent.compute_reward_count), int(agent.encode_obs_count),
+            int(agent.decode_action_count))
+
+
+def scenario_env_step_with_done_dropout(K):
+    """/root/reference/tests/test_env.py:9-21,71-107"""
+    ph = K.ph
+    env = ph.PhantomEnv(
+        num_steps=2,
+        network=K.finish_network(ph.Network([
+            K.MockStrategicAgent("A", num_steps=1), K.MockStrategicAgent("B"), K.MockAgent("C")])),
+    )
+    assert env.n_agents == 3
+    assert env.agent_ids == ["A", "B", "C"]
+    assert env.strategic_agent_ids == ["A", "B"]
+    assert env.non_strategic_agent_ids == ["C"]
+    assert env.strategic_agents == [env.agents["A"], env.agents["B"]]
+    assert env.non_strategic_agents == [env.agents["C"]]
+    assert env["A"].id == "A"
+
+    obs, infos = env.reset()
+    assert env.current_step == 0
+    assert list(obs.keys()) == ["A", "B"]
+    assert infos == {}
+
+    step = env.step({"A": 0, "B": 0})
+    assert env.current_step == 1
+    assert list(step.observations.keys()) == ["A", "B"]
+    assert list(step.rewards.keys()) == ["A", "B"]
+    assert list(step.infos.keys()) == ["A", "B"]
+    assert step.terminations == {"A": True, "B": False, "__all__": False}
+    assert step.truncations == {"A": True, "B": False, "__all__": False}
+
+    step = env.step({"A": 0, "B": 0})
+    assert env.current_step == 2
+    assert list(step.observations.keys()) == ["B"]
+    assert list(step.rewards.keys()) == ["B"]
+    assert list(step.infos.keys()) == ["B"]
+    assert step.terminations == {"B": False, "__all__": False}
+    assert step.truncations == {"B": False, "__all__": True}
+    return env
+
+
+def scenario_is_terminated_truncated(K):
+    """/root/reference/tests/test_env.py:44-68, driven through real steps instead of poking
+    the private sets: all strategic agents done => __all__ terminated and truncated."""
+    ph = K.ph
+    env = ph.PhantomEnv(
+        num_steps=5,
+        network=K.finish_network(ph.Network([
+            K.MockStrategicAgent("A", num_steps=1), K.MockStrategicAgent("B", num_steps=2),
+            K.MockAgent("C")])),
+    )
+    env.reset()
+    s = env.step({"A": 0, "B": 0})
+    assert s.terminations == {"A": True, "B": False, "__all__": False}
+    s = env.step({"B": 0})
+    assert s.terminations == {"B": True, "__all__": True}
+    assert s.truncations == {"B": True, "__all__": True}
+    return env
+
+
+def _fsm_one_agent(K):
+    ph = K.ph
+    network = K.finish_network(ph.Network([K.MockStrategicAgent("agent")]))
+    return ph.FiniteStateMachineEnv(
+        num_steps=3, network=network, initial_stage="ODD",
+        stages=[
+            ph.FSMStage(stage_id="ODD", acting_agents=["agent"], next_stages=["EVEN"]),
+            ph.FSMStage(stage_id="EVEN", acting_agents=["agent"], next_stages=["ODD"]),
+        ])
+
+
+def scenario_fsm_odd_even_one_agent(K):
+    """/root/reference/tests/fsm/test_odd_even_one_agent.py:40-61"""
+    env = _fsm_one_agent(K)
+    obs, info = env.reset()
+    approx_obs(obs, {"agent": np.array([0])})
+    assert info == {}
+    assert env.current_stage == "ODD"
+    assert counts(env.agents["agent"]) == (0, 1, 0)
+
+    step = env.step({"agent": np.array([0])})
+    assert env.current_stage == "EVEN"
+    approx_obs(step.observations, {"agent": np.array([1.0 / 3.0])})
+    assert step.rewards == {"agent": 0.0}
+    assert step.terminations == {"agent": False, "__all__": False}
+    assert step.truncations == {"agent": False, "__all__": False}
+    assert step.infos == {"agent": {}}
+    assert counts(env.agents["agent"]) == (1, 2, 1)
+    return env
+
+
+def scenario_fsm_odd_even_two_agents(K):
+    """/root/reference/tests/fsm/test_odd_even_two_agents.py:42-104 (incl. the `None` reward of
+    an agent that observes before it was ever rewarded)"""
+    ph = K.ph
+    network = K.finish_network(ph.Network(
+        [K.MockStrategicAgent("odd_agent"), K.MockStrategicAgent("even_agent")]))
+    env = ph.FiniteStateMachineEnv(
+        num_steps=3, network=network, initial_stage="ODD",
+        stages=[
+            ph.FSMStage(stage_id="ODD", next_stages=["EVEN"], acting_agents=["odd_agent"],
+                        rewarded_agents=["odd_agent"]),
+            ph.FSMStage(stage_id="EVEN", next_stages=["ODD"], acting_agents=["even_agent"],
+                        rewarded_agents=["even_agent"]),
+        ])
+    obs, info = env.reset()
+    approx_obs(obs, {"odd_agent": np.array([0])})
+    assert env.current_stage == "ODD"
+    assert counts(env.agents["odd_agent"]) == (0, 1, 0)
+    assert counts(env.agents["even_agent"]) == (0, 0, 0)
+
+    step = env.step({"odd_agent": np.array([1])})
+    assert env.current_stage == "EVEN"
+    approx_obs(step.observations, {"even_agent": np.array([1.0 / 3.0])})
+    assert step.rewards == {"even_agent": None}
+    assert step.terminations == {"even_agent": False, "odd_agent": False, "__all__": False}
+    assert step.truncations == {"even_agent": False, "odd_agent": False, "__all__": False}
+    assert step.infos == {"even_agent": {}}
+    assert counts(env.agents["odd_agent"]) == (1, 1, 1)
+    assert counts(env.agents["even_agent"]) == (0, 1, 0)
+
+    step = env.step({"even_agent": np.array([0])})
+    assert env.current_stage == "ODD"
+    approx_obs(step.observations, {"odd_agent": np.array([2.0 / 3.0])})
+    assert step.rewards == {"odd_agent": 0.0}
+    assert step.terminations == {"even_agent": False, "odd_agent": False, "__all__": False}
+    assert step.truncations == {"even_agent": False, "odd_agent": False, "__all__": False}
+    assert step.infos == {"odd_agent": {}}
+    assert counts(env.agents["odd_agent"]) == (1, 2, 1)
+    assert counts(env.agents["even_agent"]) == (1, 1, 1)
+
+    # not in the reference test: the terminal step flushes the caches (fsm.py:360-375)
+    step = env.step({"odd_agent": np.array([1])})
+    assert step.truncations["__all__"] is True
+    approx_obs(step.observations, {"odd_agent": np.array([2.0 / 3.0]), "even_agent": np.array([1.0])})
+    assert step.rewards == {"odd_agent": 0.0, "even_agent": 0.0}
+    return env
+
+
+def scenario_fsm_one_state(K):
+    """/root/reference/tests/fsm/test_one_state.py:88-147 (handler-less variant, self-loop)"""
+    ph = K.ph
+    network = K.finish_network(ph.Network([K.MockStrategicAgent("agent")]))
+    network.add_connection("agent", "agent")
+    env = ph.FiniteStateMachineEnv(
+        num_steps=2, network=network, initial_stage="UNIT",
+        stages=[ph.FSMStage(stage_id="UNIT", acting_agents=["agent"], next_stages=["UNIT"],
+                            handler=None)])
+    obs, info = env.reset()
+    approx_obs(obs, {"agent": np.array([0.0])})
+    assert env.current_stage == "UNIT"
+    assert counts(env.agents["agent"]) == (0, 1, 0)
+
+    step = env.step({"agent": np.array([0])})
+    assert env.current_stage == "UNIT"
+    assert counts(env.agents["agent"]) == (1, 2, 1)
+    approx_obs(step.observations, {"agent": np.array([0.5])})
+    assert step.rewards == {"agent": 0}
+    assert step.terminations == {"agent": False, "__all__": False}
+    assert step.truncations == {"agent": False, "__all__": False}
+    assert step.infos == {"agent": {}}
+
+    step = env.step({"agent": np.array([0])})
+    assert env.current_stage == "UNIT"
+    assert counts(env.agents["agent"]) == (2, 3, 2)
+    approx_obs(step.observations, {"agent": np.array([1.0])})
+    assert step.rewards == {"agent": 0}
+    assert step.terminations == {"agent": False, "__all__": False}
+    assert step.truncations == {"agent": False, "__all__": True}
+    assert step.infos == {"agent": {}}
+    return env
+
+
+def scenario_fsm_validation(K):
+    """/root/reference/tests/fsm/test_fsm_validation.py:7-174 and
+    tests/fsm/test_is_fsm_deterministic.py:4-47 (the list-registration cases)"""
+    ph = K.ph
+    net = lambda: K.finish_network(ph.Network([]))
+    with pytest.raises(ph.fsm.FSMValidationError):  # no stages
+        ph.FiniteStateMachineEnv(num_steps=1, network=net(), initial_stage="A")
+    with pytest.raises(ph.fsm.FSMValidationError):  # bad initial stage
+        ph.FiniteStateMachineEnv(
+            num_steps=1, network=net(), initial_stage="X",
+            stages=[ph.FSMStage(stage_id="A", acting_agents=[], next_stages=["A"])])
+    with pytest.raises(ph.fsm.FSMValidationError):  # bad next stage
+        ph.FiniteStateMachineEnv(
+            num_steps=1, network=net(), initial_stage="A",
+            stages=[ph.FSMStage(stage_id="A", acting_agents=[], next_stages=["B"])])
+    with pytest.raises(ph.fsm.FSMValidationError):  # handler-less stage needs exactly one next
+        ph.FiniteStateMachineEnv(
+            num_steps=1, network=net(), initial_stage="A",
+            stages=[ph.FSMStage(stage_id="A", acting_agents=[], next_stages=[])])
+    env = ph.FiniteStateMachineEnv(
+        num_steps=1, network=net(), initial_stage="A",
+        stages=[ph.FSMStage(stage_id="A", acting_agents=[], next_stages=["B"]),
+                ph.FSMStage(stage_id="B", acting_agents=[], next_stages=["C"]),
+                ph.FSMStage(stage_id="C", acting_agents=[], next_stages=["A"])])
+    assert env.is_fsm_deterministic()
+
+
+def scenario_stackelberg(K):
+    """/root/reference/tests/test_stackelberg.py:10-74"""
+    ph = K.ph
+    network = K.finish_network(ph.Network(
+        [K.MockStrategicAgent("leader"), K.MockStrategicAgent("follower")]))
+    env = ph.StackelbergEnv(3, network, ["leader"], ["follower"])
+    obs, info = env.reset()
+    approx_obs(obs, {"leader": np.array([0])})
+    assert info == {}
+    assert counts(env.agents["leader"]) == (0, 1, 0)
+    assert counts(env.agents["follower"]) == (0, 0, 0)
+
+    step = env.step({"leader": np.array([0])})
+    approx_obs(step.observations, {"follower": np.array([1 / 3])})
+    assert step.rewards == {}
+    assert step.terminations == {"leader": False, "follower": False, "__all__": False}
+    assert step.truncations == {"leader": False, "follower": False, "__all__": False}
+    assert step.infos == {"follower": {}}
+    assert counts(env.agents["leader"]) == (1, 1, 1)
+    assert counts(env.agents["follower"]) == (0, 1, 0)
+
+    step = env.step({"follower": np.array([0])})
+    approx_obs(step.observations, {"leader": np.array([2 / 3])})
+    assert step.rewards == {"leader": 0.0}
+    assert step.terminations == {"leader": False, "follower": False, "__all__": False}
+    assert step.truncations == {"leader": False, "follower": False, "__all__": False}
+    assert step.infos == {"leader": {}}
+    assert counts(env.agents["leader"]) == (1, 2, 1)
+    assert counts(env.agents["follower"]) == (1, 1, 1)
+
+    step = env.step({"leader": np.array([0])})
+    approx_obs(step.observations, {"follower": np.array([1])})
+    assert step.rewards == {"leader": 0.0, "follower": 0.0}
+    assert step.terminations == {"leader": False, "follower": False, "__all__": False}
+    assert step.truncations == {"leader": False, "follower": False, "__all__": True}
+    assert step.infos == {"follower": {}}
+    assert counts(env.agents["leader"]) == (2, 2, 2)
+    assert counts(env.agents["follower"]) == (1, 2, 1)
+    return env
+
+
+def _msgs(env):
+    out = []
+    for m in env.network.resolver.tracked_messages:
+        p = m.payload
+        out.append((m.sender_id, m.receiver_id, type(p).__name__,
+                    getattr(p, "value", getattr(p, "cash", None))))
+    return out
+
+
+def scenario_tracking_golden_vector(K):
+    """/root/reference/tests/network/test_tracking.py:29-57 -- THE routing golden vector: exact
+    global message order over three rounds.  The test's two hand-made sends become A's
+    generate_messages()."""
+    ph = K.ph
+    resolver = ph.resolvers.BatchResolver(enable_tracking=True)
+    n = ph.Network([K.EchoAgent("A", seed_value=4), K.EchoAgent("B"), K.EchoAgent("C")], resolver)
+    n.add_connection("A", "B")
+    n.add_connection("A", "C")
+    env = ph.PhantomEnv(num_steps=3, network=K.finish_network(n))
+    env.reset()
+    env.step({})
+    assert _msgs(env) == [
+        ("A", "B", "TestMessage", 4),
+        ("A", "C", "TestMessage", 4),
+        ("B", "A", "TestMessage", 2),
+        ("C", "A", "TestMessage", 2),
+        ("A", "B", "TestMessage", 1),
+        ("A", "C", "TestMessage", 1),
+    ]
+    env.network.resolver.clear_tracked_messages()
+    assert env.network.resolver.tracked_messages == []
+    return env
+
+
+def scenario_resolver_round_ordering(K):
+    """/root/reference/tests/network/test_resolver.py:48-70: requests A->B, A->C, B->C; round 0
+    receivers are visited B then C (first arrival), C answering A before B; in round 1 the
+    responses are delivered B->A, C->A, C->B -- receivers A then B."""
+    ph = K.ph
+    n = ph.Network(
+        [K.EchoAgent("A", seed_value=100, request_response=True),
+         K.EchoAgent("B", seed_value=100, request_response=True), K.EchoAgent("C")],
+        ph.resolvers.BatchResolver(enable_tracking=True))
+    n.add_connection("A", "B")
+    n.add_connection("A", "C")
+    n.add_connection("B", "C")
+    env = ph.PhantomEnv(num_steps=3, network=K.finish_network(n))
+    env.reset()
+    env.step({})
+    assert _msgs(env) == [
+        ("A", "B", "Request", 100), ("A", "C", "Request", 100), ("B", "C", "Request", 100),
+        ("B", "A", "Response", 50), ("C", "A", "Response", 50), ("C", "B", "Response", 50),
+    ]
+    assert int(env.agents["A"].handled_count) == 2 and int(env.agents["C"].handled_count) == 2
+    assert int(env.agents["B"].handled_total) == 150
+    return env
+
+
+def scenario_round_limit(K):
+    """/root/reference/tests/network/test_resolver.py:73-86: round_limit=0 with a queued
+    message raises (RuntimeError, resolvers.py:160-163)."""
+    ph = K.ph
+    n = ph.Network([K.EchoAgent("A", seed_value=1), K.EchoAgent("B")],
+                   ph.resolvers.BatchResolver(round_limit=0))
+    n.add_connection("A", "B")
+    env = ph.PhantomEnv(num_steps=3, network=K.finish_network(n))
+    env.reset()
+    with pytest.raises(RuntimeError):
+        env.step({})
+
+
+def scenario_unknown_message_type(K):
+    """/root/reference/tests/test_agent.py:55-68: a message for an agent without a handler for
+    its payload type raises ValueError (agents.py:140-143)."""
+    ph = K.ph
+    n = ph.Network([K.EchoAgent("A", seed_value=3), K.MockAgent("B")])
+    n.add_connection("A", "B")
+    env = ph.PhantomEnv(num_steps=3, network=K.finish_network(n))
+    env.reset()
+    with pytest.raises(ValueError):
+        env.step({})
+
+
+def scenario_done_agent_mail_is_dropped(K):
+    """resolvers.py:143-144 (SURVEY.md A.1 rule 5): mail for an agent without a context (done)
+    is dropped silently -- no handler call, no error.  S has no handler for TestMessage, so a
+    DELIVERED message would raise ValueError; S finishes in step 1, A only acts from step 2."""
+    ph = K.ph
+    n = ph.Network([K.EchoAgent("A", seed_value=6), K.MockStrategicAgent("S", num_steps=1)],
+                   ph.resolvers.BatchResolver(enable_tracking=True))
+    n.add_connection("A", "S")
+    env = ph.FiniteStateMachineEnv(
+        num_steps=4, network=K.finish_network(n), initial_stage="ONE",
+        stages=[ph.FSMStage(stage_id="ONE", acting_agents=["S"], next_stages=["TWO"]),
+                ph.FSMStage(stage_id="TWO", acting_agents=["A"], next_stages=["TWO"])])
+    env.reset()
+    s = env.step({"S": 0})
+    assert s.terminations["S"] is True and _msgs(env) == []
+    s = env.step({})
+    assert _msgs(env) == [("A", "S", "TestMessage", 6)]
+    assert "S" not in s.terminations
+    return env
+
+
+ALL = [
+    scenario_env_step_with_done_dropout,
+    scenario_is_terminated_truncated,
+    scenario_fsm_odd_even_one_agent,
+    scenario_fsm_odd_even_two_agents,
+    scenario_fsm_one_state,
+    scenario_fsm_validation,
+    scenario_stackelberg,
+    scenario_tracking_golden_vector,
+    scenario_resolver_round_ordering,
+    scenario_round_limit,
+    scenario_unknown_message_type,
+    scenario_done_agent_mail_is_dropped,
+]
