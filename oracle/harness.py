@@ -107,3 +107,81 @@ def run_supply_chain(env, clock: EpisodeClock, actions: np.ndarray,
     if track:
         out["messages"] = np.concatenate(msgs, axis=0) if msgs else np.zeros((0, 7))
     return out
+
+
+def run_generic(env, clock: EpisodeClock, actions: np.ndarray, action_mask: np.ndarray,
+                obs_dim: int, track: bool = False, state_fn=None) -> Dict[str, np.ndarray]:
+    """Run actions.shape[0] episodes x actions.shape[1] steps of ANY env built with the
+    plugin API and record the tensors of the C-ABI layout.
+
+    actions f32 [n_ep, T, S, A]; action_mask u8 [n_ep, T, S] (0 => agent absent from the
+    `actions` mapping).  Discrete action spaces receive int(round(a[0])).
+    Outputs (S = strategic agents in env order):
+      obs f32 [n_ep,T,S,O] (zero padded), obs_mask u8, reward f64, reward_mask u8 (0 absent,
+      1 value, 2 None), term/trunc u8 (255 = key absent), all_done u8 [..,2];
+      reset_obs / reset_mask for every episode; optional state [n_ep,T,...] via state_fn(env).
+    """
+    n_ep, T, S, A = actions.shape
+    ids = env.strategic_agent_ids
+    assert len(ids) == S
+    discrete = [hasattr(getattr(env.agents[a], "action_space", None), "n") for a in ids]
+    out = {
+        "reset_obs": np.zeros((n_ep, S, obs_dim), np.float32),
+        "reset_mask": np.zeros((n_ep, S), np.uint8),
+        "obs": np.zeros((n_ep, T, S, obs_dim), np.float32),
+        "obs_mask": np.zeros((n_ep, T, S), np.uint8),
+        "reward": np.zeros((n_ep, T, S), np.float64),
+        "reward_mask": np.zeros((n_ep, T, S), np.uint8),
+        "term": np.full((n_ep, T, S), 255, np.uint8),
+        "trunc": np.full((n_ep, T, S), 255, np.uint8),
+        "all_done": np.zeros((n_ep, T, 2), np.uint8),
+    }
+    states, msgs = [], []
+    slot_of = {aid: i for i, aid in enumerate(env.agent_ids)}
+
+    def put_obs(dst, dmask, obs):
+        for s, aid in enumerate(ids):
+            if aid in obs:
+                v = np.asarray(obs[aid], np.float32).reshape(-1)
+                dst[s, : v.size] = v
+                dmask[s] = 1
+
+    for ep in range(n_ep):
+        clock.on_reset()
+        obs, _ = env.reset()
+        put_obs(out["reset_obs"][ep], out["reset_mask"][ep], obs)
+        ep_states = []
+        for t in range(T):
+            clock.on_step(env)
+            acts = {}
+            for s, aid in enumerate(ids):
+                if action_mask[ep, t, s]:
+                    a = actions[ep, t, s]
+                    acts[aid] = int(round(float(a[0]))) if discrete[s] else a
+            if track:
+                env.network.resolver.clear_tracked_messages()
+            step = env.step(acts)
+            put_obs(out["obs"][ep, t], out["obs_mask"][ep, t], step.observations)
+            for s, aid in enumerate(ids):
+                if aid in step.rewards:
+                    r = step.rewards[aid]
+                    out["reward_mask"][ep, t, s] = 2 if r is None else 1
+                    out["reward"][ep, t, s] = 0.0 if r is None else r
+                if aid in step.terminations:
+                    out["term"][ep, t, s] = step.terminations[aid]
+                    out["trunc"][ep, t, s] = step.truncations[aid]
+            out["all_done"][ep, t] = (step.terminations["__all__"], step.truncations["__all__"])
+            if state_fn is not None:
+                ep_states.append(state_fn(env))
+            if track:
+                for k, m in enumerate(env.network.resolver.tracked_messages):
+                    vals = [int(v) for v in m.payload.__dict__.values()][:2] + [0, 0]
+                    msgs.append((ep, t, slot_of[m.sender_id], slot_of[m.receiver_id],
+                                 type(m.payload).__name__, vals[0], vals[1]))
+        if state_fn is not None:
+            states.append(np.stack(ep_states))
+    if state_fn is not None:
+        out["state"] = np.stack(states)
+    if track:
+        out["messages"] = msgs
+    return out

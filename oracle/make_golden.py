@@ -66,12 +66,69 @@ def gen_supply_chain_reference() -> None:
     print("supply_chain_reference.npz:", {k: v.shape for k, v in out.items()})
 
 
+def generic_actions(n_env, n_ep, T, S, discrete_from=None, seed=11, p_missing=0.05):
+    r = np.random.RandomState(seed)
+    a = r.uniform(0, 1, size=(n_env, n_ep, T, S, 1)).astype(np.float32)
+    if discrete_from is not None:
+        a[:, :, :, discrete_from:, :] = (a[:, :, :, discrete_from:, :] > 0.3)
+    m = (r.uniform(size=(n_env, n_ep, T, S)) > p_missing).astype(np.uint8)
+    return a, m
+
+
+MESSAGE_TYPE_IDS = {"Quote": 0, "Order": 1, "Fill": 2}
+
+
+def pack_generic(per_env, actions, mask, seed, msg_envs, type_ids):
+    keys = [k for k in per_env[0] if k != "messages"]
+    out = {k: np.stack([t[k] for t in per_env]) for k in keys}
+    rows = []
+    for e in range(msg_envs):
+        for (ep, t, s, r, name, v0, v1) in per_env[e]["messages"]:
+            rows.append((e, ep, t, s, r, type_ids[name], v0, v1))
+    out["messages"] = np.asarray(rows, np.int64).reshape(-1, 8)
+    out["actions"], out["action_mask"], out["seed"] = actions, mask, np.int64(seed)
+    return out
+
+
+def market_state(env):
+    rows = []
+    for a in env.agents.values():
+        n = type(a).__name__
+        if n == "MakerAgent":
+            rows.append([a.inventory, a.cash, a.last_price, a.last_notional, 0])
+        elif n == "TakerAgent":
+            rows.append([a.value, a.best_price, a.best_maker, a.holdings, a.last_surplus])
+    return np.array(rows, np.int64)
+
+
+def gen_market_reference() -> None:
+    """oracle/workloads/market.py (C3) executed by the UNMODIFIED reference."""
+    from .workloads import market
+
+    ref = ref_shim.import_reference()
+    seed, n_env, n_ep, T, S = 20261018, 6, 2, 99, market.N_MAKERS + market.N_TAKERS
+    actions, mask = generic_actions(n_env, n_ep, T, S, discrete_from=market.N_MAKERS)
+    per_env = []
+    for e in range(n_env):
+        st = rng.StepStream(seed, e, market.STREAM_TAKER_VALUE)
+        env = market.build(ref, st, enable_tracking=e < 1)
+        per_env.append(harness.run_generic(env, harness.EpisodeClock([st]), actions[e], mask[e], 3,
+                                           track=e < 1, state_fn=market_state))
+        if e >= 1:
+            per_env[-1]["messages"] = []
+    out = pack_generic(per_env, actions, mask, seed, 1, MESSAGE_TYPE_IDS)
+    np.savez_compressed(os.path.join(GOLDEN, "market_reference.npz"), **out)
+    print("market_reference.npz:", {k: v.shape for k, v in out.items()},
+          "terminated:", int((out["term"] == 1).sum()))
+
+
 def main() -> int:
     if not ref_shim.reference_available():
         print("reference not available")
         return 2
     os.makedirs(GOLDEN, exist_ok=True)
     gen_supply_chain_reference()
+    gen_market_reference()
     return 0
 
 

@@ -115,3 +115,24 @@ def test_pinned_record(golden_dir):
     assert rec["oracle"]["counts"]["passed"] == rec["reference"]["counts"]["passed"] >= 64
     assert rec["oracle_sha256"] == pin.oracle_fingerprint(), (
         "oracle/phantom_oracle changed: re-run `python -m oracle.pin_against_reference`")
+
+
+def test_object_oracle_matches_market_golden(golden_dir):
+    """C3 workload: oracle restatement == the reference running the same env definition."""
+    from oracle import make_golden
+    from oracle.workloads import market
+
+    from .generic_parity import assert_oracle_trace_equal
+
+    g = np.load(os.path.join(golden_dir, "market_reference.npz"))
+    seed, A, M = int(g["seed"]), g["actions"], g["action_mask"]
+    for e in range(2):
+        st = rng.StepStream(seed, e, market.STREAM_TAKER_VALUE)
+        env = market.build(po, st, enable_tracking=e < 1)
+        tr = harness.run_generic(env, harness.EpisodeClock([st]), A[e], M[e], 3, track=e < 1,
+                                 state_fn=make_golden.market_state)
+        assert_oracle_trace_equal(tr, g, e)
+        if e < 1:
+            rows = [(0, ep, t, s, r, make_golden.MESSAGE_TYPE_IDS[n], v0, v1)
+                    for (ep, t, s, r, n, v0, v1) in tr["messages"]]
+            assert np.array_equal(np.asarray(rows, np.int64), g["messages"])
