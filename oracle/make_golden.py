@@ -122,6 +122,26 @@ def gen_market_reference() -> None:
           "terminated:", int((out["term"] == 1).sum()))
 
 
+def gen_stackelberg_reference() -> None:
+    """oracle/workloads/stackelberg.py (C4) executed by the UNMODIFIED reference."""
+    from .workloads import stackelberg as wl
+
+    ref = ref_shim.import_reference()
+    seed, n_env, n_ep, T, S = 20261019, 16, 2, 100, 1 + wl.N_FOLLOWERS
+    actions, mask = generic_actions(n_env, n_ep, T, S, seed=13, p_missing=0.1)
+    per_env = []
+    for e in range(n_env):
+        st = rng.StepStream(seed, e, wl.STREAM_FOLLOWER_VALUE)
+        env = wl.build(ref, st, enable_tracking=e < 4)
+        per_env.append(harness.run_generic(env, harness.EpisodeClock([st]), actions[e], mask[e], 2,
+                                           track=e < 4, state_fn=wl.state))
+        if e >= 4:
+            per_env[-1]["messages"] = []
+    out = pack_generic(per_env, actions, mask, seed, 4, wl.MESSAGE_TYPE_IDS)
+    np.savez_compressed(os.path.join(GOLDEN, "stackelberg_reference.npz"), **out)
+    print("stackelberg_reference.npz:", {k: v.shape for k, v in out.items()})
+
+
 def main() -> int:
     if not ref_shim.reference_available():
         print("reference not available")
@@ -129,6 +149,7 @@ def main() -> int:
     os.makedirs(GOLDEN, exist_ok=True)
     gen_supply_chain_reference()
     gen_market_reference()
+    gen_stackelberg_reference()
     return 0
 
 

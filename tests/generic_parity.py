@@ -48,3 +48,38 @@ def assert_batchsteps_equal(a, b, ctx=""):
     assert torch.equal(a.observations[sel], b.observations[sel]), f"observations {ctx}"
     sel = a.reward_mask == 1
     assert torch.equal(a.rewards[sel], b.rewards[sel]), f"rewards {ctx}"
+
+
+def run_device_vs_golden(make_env, g, state_fn=None, state_every=1):
+    """Step a device env (one handle holding every env of the golden) through the golden's
+    action tape and compare every step."""
+    seed, A, M = int(g["seed"]), g["actions"], g["action_mask"]
+    n_env, n_ep, T = A.shape[:3]
+    env = make_env(num_envs=n_env, seed=seed)
+    for ep in range(n_ep):
+        obs, mask = env.reset_batch()
+        assert np.array_equal(mask.cpu().numpy(), g["reset_mask"][:, ep]), f"reset mask ep {ep}"
+        sel = g["reset_mask"][:, ep].astype(bool)
+        assert np.array_equal(obs.cpu().numpy()[sel], g["reset_obs"][:, ep][sel]), f"reset obs {ep}"
+        for t in range(T):
+            out = env.step_batch(A[:, ep, t], M[:, ep, t])
+            assert_device_step_equal(out, g, ep, t, f"ep {ep} t {t}")
+            if state_fn is not None and (t % state_every == 0 or t == T - 1):
+                assert np.array_equal(state_fn(env), g["state"][:, ep, t]), (ep, t)
+    env.check_errors()
+    return env
+
+
+def run_device_trace_vs_golden(make_env, g, n_env):
+    """Device message trace == the reference's Resolver.tracked_messages, env by env."""
+    seed, A, M = int(g["seed"]), g["actions"], g["action_mask"]
+    gm = g["messages"]  # (env, ep, t, sender, recv, type, v0, v1)
+    env = make_env(num_envs=n_env, seed=seed, enable_tracking=True)
+    for ep in range(A.shape[1]):
+        env.reset_batch()
+        for t in range(A.shape[2]):
+            env.step_batch(A[:n_env, ep, t], M[:n_env, ep, t])
+            for e in range(n_env):
+                want = gm[(gm[:, 0] == e) & (gm[:, 1] == ep) & (gm[:, 2] == t)][:, 3:8]
+                assert np.array_equal(device_trace_rows(env, e), want), (e, ep, t)
+    env.close()

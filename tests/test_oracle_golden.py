@@ -136,3 +136,24 @@ def test_object_oracle_matches_market_golden(golden_dir):
             rows = [(0, ep, t, s, r, make_golden.MESSAGE_TYPE_IDS[n], v0, v1)
                     for (ep, t, s, r, n, v0, v1) in tr["messages"]]
             assert np.array_equal(np.asarray(rows, np.int64), g["messages"])
+
+
+def test_object_oracle_matches_stackelberg_golden(golden_dir):
+    """C4 workload: oracle restatement == the reference running the same env definition."""
+    from oracle.workloads import stackelberg as wl
+
+    from .generic_parity import assert_oracle_trace_equal
+
+    g = np.load(os.path.join(golden_dir, "stackelberg_reference.npz"))
+    seed, A, M = int(g["seed"]), g["actions"], g["action_mask"]
+    rows = []
+    for e in range(6):
+        st = rng.StepStream(seed, e, wl.STREAM_FOLLOWER_VALUE)
+        env = wl.build(po, st, enable_tracking=e < 4)
+        tr = harness.run_generic(env, harness.EpisodeClock([st]), A[e], M[e], 2, track=e < 4,
+                                 state_fn=wl.state)
+        assert_oracle_trace_equal(tr, g, e)
+        if e < 4:
+            rows += [(e, ep, t, s, r, wl.MESSAGE_TYPE_IDS[n], v0, v1)
+                     for (ep, t, s, r, n, v0, v1) in tr["messages"]]
+    assert np.array_equal(np.asarray(rows, np.int64), g["messages"])
