@@ -142,6 +142,32 @@ def gen_stackelberg_reference() -> None:
     print("stackelberg_reference.npz:", {k: v.shape for k, v in out.items()})
 
 
+def gen_dense_reference() -> None:
+    """oracle/workloads/dense.py (C5) executed by the UNMODIFIED reference: the full 128-agent
+    complete graph (no message list: 16 256 per step) and a sparse 12-agent graph with the
+    tracked message order."""
+    from .workloads import dense as wl
+
+    ref = ref_shim.import_reference()
+    for name, n, adj, n_env, T, msg_envs in (
+            ("dense128_reference.npz", 128, None, 2, 8, 0),
+            ("dense12_reference.npz", 12, wl.random_adjacency(12, 0.6, 1), 6, 8, 6)):
+        seed, n_ep = 20261020, 2
+        actions, mask = generic_actions(n_env, n_ep, T, n, seed=17, p_missing=0.12)
+        per_env = []
+        for e in range(n_env):
+            env = wl.build(ref, n_agents=n, adjacency=adj, num_steps=T, enable_tracking=msg_envs > 0)
+            per_env.append(harness.run_generic(env, harness.EpisodeClock([]), actions[e], mask[e], 3,
+                                               track=msg_envs > 0, state_fn=wl.state))
+            if msg_envs == 0:
+                per_env[-1]["messages"] = []
+        out = pack_generic(per_env, actions, mask, seed, msg_envs, wl.MESSAGE_TYPE_IDS)
+        if adj is not None:
+            out["adjacency"] = adj
+        np.savez_compressed(os.path.join(GOLDEN, name), **out)
+        print(name, {k: v.shape for k, v in out.items()})
+
+
 def main() -> int:
     if not ref_shim.reference_available():
         print("reference not available")
@@ -150,6 +176,7 @@ def main() -> int:
     gen_supply_chain_reference()
     gen_market_reference()
     gen_stackelberg_reference()
+    gen_dense_reference()
     return 0
 
 

@@ -1,0 +1,415 @@
+// fam_dense.cu -- device program family PHX_FAMILY_DENSE (BASELINE config C5): the dense-graph
+// broadcast / batch-aggregation env of oracle/workloads/dense.py.
+//
+// Replaces, for up to 128 agents per env, the message-queue stress path of the reference:
+//   env.py:320-336         acting phase: every agent sends to every neighbour (N (N-1) sends)
+//   network.py:233-254     Network.send checks
+//   resolvers.py:128-163   BatchResolver.resolve with round_limit = 2
+//   agents.py:96-120       Agent.handle_batch, OVERRIDDEN by the agents to aggregate the batch
+//                          (sum, max, first arg-max; cf. the auction of
+//                          examples/environments/digital_ads_market/digital_ads_market.py:429-510)
+//
+// Mapping: ONE THREAD BLOCK PER ENV, thread == agent slot (the north star's layout; it pays
+// here because an env has 128 agents and 16 256 messages per step).  The per-env message
+// queue is a MAILBOX in shared memory, mb[receiver][sender] (66 KB, row stride 129 words so
+// that both the senders' column writes and the receivers' row reads are bank-conflict free).
+// The reference's batch order for a receiver (global push order = sender slot order) is the
+// mailbox row order; the receivers' first-arrival order only matters for the order in which
+// the Acks are pushed, i.e. for the message trace, and is reconstructed there.
+// Outputs of a step are staged in shared memory and written with TMA bulk stores
+// (cp.async.bulk.global.shared::cta, SASS UBLKCP): one env's rows are contiguous in every
+// [T,E,S,...] plane.
+//
+// Agent kind 0 = DenseAgent (strategic).  Payload types: 0 Signal(value), 1 Ack(value).
+// State words per agent: 0 signal, 1 total, 2 best, 3 best_sender, 4 acks, 5 ack_total.
+#include <cstring>
+#include <string>
+
+#include "phx_family.h"
+
+namespace phx {
+namespace {
+
+constexpr int DN_MAX = 128;       // agents per env == threads per block
+constexpr int DN_STRIDE = 129;    // mailbox row stride (words)
+constexpr int DN_WORDS = 6;
+enum { DN_SIGNAL = 0, DN_ACK = 1 };
+
+struct DenseSpec {
+  int32_t E, n, num_steps, round_limit;
+  uint32_t flags;
+  uint32_t sender_ok[2][4], receiver_ok[2][4];
+};
+
+struct DenseArgs {
+  DenseSpec sp;
+  int32_t T;
+  int4* hdr;
+  int32_t* state;        // [DN_WORDS][E][128]
+  const uint32_t* adj;   // [128][4] adjacency rows (bit r of row s: edge s -> r)
+  StepIO io;
+  FaultSink faults;
+  TraceSink trace;
+};
+
+struct alignas(16) DenseStage {  // one step's output rows of one env, 16-byte aligned planes
+  float obs[DN_MAX * 3];
+  float reward[DN_MAX];
+  uint8_t obs_mask[DN_MAX], reward_mask[DN_MAX], term[DN_MAX], trunc[DN_MAX];
+};
+
+struct DenseSmem {
+  int32_t mb[DN_MAX * DN_STRIDE];  // mailbox, round 0
+  int32_t ack_to[DN_MAX];          // round 1: Ack receiver of every agent (-1 = none)
+  int32_t ack_val[DN_MAX];
+  int32_t order_key[DN_MAX];       // trace only: first-arrival keys
+  uint32_t sent[4];
+  uint32_t any_ack;
+  DenseStage stage[2];
+};
+
+__device__ __forceinline__ int dn_tailored(int value, int s, int r) {
+  return value + (7 * s + 3 * r) % 5;
+}
+
+template <bool TRACK>
+__global__ void __launch_bounds__(DN_MAX) dense_step_kernel(const DenseArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  DenseSmem& sm = *reinterpret_cast<DenseSmem*>(smem_raw);
+  const DenseSpec& sp = a.sp;
+  const int e = blockIdx.x;
+  const int slot = threadIdx.x;
+  const int lane = slot & 31, warp = slot >> 5;
+  const int n = sp.n;
+  const bool is_agent = slot < n;
+
+  uint32_t adj[4];
+#pragma unroll
+  for (int w = 0; w < 4; ++w) adj[w] = is_agent ? a.adj[slot * 4 + w] : 0u;
+  int4 h = a.hdr[e];
+  int st[DN_WORDS];
+#pragma unroll
+  for (int w = 0; w < DN_WORDS; ++w) st[w] = a.state[((size_t)w * sp.E + e) * DN_MAX + slot];
+  uint32_t fault = 0;
+  const bool bulk = (n % 16) == 0;  // plane sizes multiples of 16 bytes
+  const bool ok_send_signal = ((sp.sender_ok[DN_SIGNAL][slot >> 5] >> (slot & 31)) & 1u) ||
+                              (sp.flags & PHX_FLAG_NO_PAYLOAD_CHECKS);
+  const bool ok_send_ack = ((sp.sender_ok[DN_ACK][slot >> 5] >> (slot & 31)) & 1u) ||
+                           (sp.flags & PHX_FLAG_NO_PAYLOAD_CHECKS);
+
+  for (int t = 0; t < a.T; ++t) {
+    const size_t row = (size_t)t * sp.E + e;
+    DenseStage& sg = sm.stage[t & 1];
+    h.x += 1;  // env.py:252
+
+    // ---- acting phase: decode_action -> Signal to every neighbour, in slot order
+    bool has = false;
+    float act = 0.f;
+    if (is_agent) {
+      has = a.io.action_mask ? a.io.action_mask[row * n + slot] != 0 : true;
+      act = a.io.actions[row * n + slot];
+    }
+    bool sends = false;
+    if (has) {
+      if (!(fabsf(act) <= 1048576.0f)) fault = fault ? fault : PHX_FAULT_INVALID_ACTION;
+      st[0] = max(0, min(1000, __float2int_rn(__fmul_rn(act, 1000.0f))));
+      sends = (adj[0] | adj[1] | adj[2] | adj[3]) != 0u;
+      if (sends && !ok_send_signal) fault = fault ? fault : PHX_FAULT_BAD_PAYLOAD_TYPE;
+    }
+    const uint32_t sent_w = __ballot_sync(0xFFFFFFFFu, sends);
+    if (lane == 0) sm.sent[warp] = sent_w;
+    if (sends) {
+      // column write: mb[r][slot] for every neighbour r (lanes hit consecutive words)
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        uint32_t m = adj[w];
+        while (m) {
+          const int r = w * 32 + __ffs(m) - 1;
+          m &= m - 1;
+          if (!((sp.receiver_ok[DN_SIGNAL][r >> 5] >> (r & 31)) & 1u) &&
+              !(sp.flags & PHX_FLAG_NO_PAYLOAD_CHECKS))
+            fault = fault ? fault : PHX_FAULT_BAD_PAYLOAD_TYPE;
+          sm.mb[r * DN_STRIDE + slot] = dn_tailored(st[0], slot, r);
+        }
+      }
+    }
+    // ---- pre_message_resolution
+    st[1] = 0; st[2] = 0; st[3] = -1; st[4] = 0; st[5] = 0;
+    __syncthreads();
+
+    // ---- round 0: handle_batch over this receiver's mailbox row (batch order = sender order)
+    const uint32_t any_sent = sm.sent[0] | sm.sent[1] | sm.sent[2] | sm.sent[3];
+    if (any_sent && sp.round_limit == 0) fault = fault ? fault : PHX_FAULT_ROUND_LIMIT;
+    int ack_recv = -1;
+    int first_sender = -1;
+    if (is_agent && sp.round_limit != 0) {
+      int total = 0, best = 0, best_s = -1;
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        uint32_t m = adj[w] & sm.sent[w];  // symmetric graph: senders with an edge to me
+        while (m) {
+          const int s = w * 32 + __ffs(m) - 1;
+          m &= m - 1;
+          if (first_sender < 0) first_sender = s;
+          const int v = sm.mb[slot * DN_STRIDE + s];
+          total += v;
+          if (best_s < 0 || v > best) {  // strict: the FIRST sender attaining the max wins
+            best = v;
+            best_s = s;
+          }
+        }
+      }
+      if (best_s >= 0) {
+        st[1] = total;
+        st[2] = best;
+        st[3] = best_s;
+        ack_recv = best_s;
+        if (!ok_send_ack || (!((sp.receiver_ok[DN_ACK][best_s >> 5] >> (best_s & 31)) & 1u) &&
+                             !(sp.flags & PHX_FLAG_NO_PAYLOAD_CHECKS)))
+          fault = fault ? fault : PHX_FAULT_BAD_PAYLOAD_TYPE;
+      }
+    }
+    sm.ack_to[slot] = ack_recv;
+    sm.ack_val[slot] = st[2];
+    if (TRACK) sm.order_key[slot] = first_sender < 0 ? 0x7FFFFFFF : first_sender * DN_MAX + slot;
+    const uint32_t acks_w = __ballot_sync(0xFFFFFFFFu, ack_recv >= 0);
+    if (slot == 0) sm.any_ack = 0;
+    __syncthreads();
+    if (lane == 0 && acks_w) atomicOr(&sm.any_ack, 1u);
+    __syncthreads();
+    if (sm.any_ack && sp.round_limit == 1) fault = fault ? fault : PHX_FAULT_ROUND_LIMIT;
+
+    // ---- round 1: the Acks (same handle_batch override): count and sum
+    if (is_agent && sp.round_limit != 1 && sp.round_limit != 0) {
+      int acks = 0, ack_total = 0;
+      for (int r = 0; r < n; ++r) {  // broadcast reads
+        if (sm.ack_to[r] == slot) {
+          acks += 1;
+          ack_total += sm.ack_val[r];
+        }
+      }
+      st[4] = acks;
+      st[5] = ack_total;
+    }
+
+    if (TRACK && slot == 0) {  // Resolver.tracked_messages of this step, global push order
+      int cnt = 0;
+      int4* rows = a.trace.rows + (size_t)e * a.trace.cap;
+      for (int s = 0; s < n; ++s) {
+        if (!((sm.sent[s >> 5] >> (s & 31)) & 1u)) continue;
+        for (int r = 0; r < n; ++r)
+          if ((a.adj[s * 4 + (r >> 5)] >> (r & 31)) & 1u) {
+            if (cnt < a.trace.cap)
+              rows[cnt] = trace_row(s, r, DN_SIGNAL, sm.mb[r * DN_STRIDE + s], 0, 0);
+            ++cnt;
+          }
+      }
+      // Acks are pushed in the receivers' first-arrival order: (first sender, slot)
+      int last = -1;
+      for (;;) {
+        int best_r = -1, best_k = 0x7FFFFFFF;
+        for (int r = 0; r < n; ++r) {
+          const int k = sm.order_key[r];
+          if (k > last && k < best_k) { best_k = k; best_r = r; }
+        }
+        if (best_r < 0) break;
+        last = best_k;
+        if (sm.ack_to[best_r] >= 0) {
+          if (cnt < a.trace.cap)
+            rows[cnt] = trace_row(best_r, sm.ack_to[best_r], DN_ACK, sm.ack_val[best_r], 0, 1);
+          ++cnt;
+        }
+      }
+      a.trace.cnt[e] = cnt;
+    }
+
+    // ---- outputs (env.py:273-303): every agent observes and is rewarded; nobody terminates
+    const bool at_max = h.x == sp.num_steps;
+    if ((sp.flags & PHX_FLAG_AUTO_RESET) && at_max) {
+      h.x = 0;
+      h.y += 1;
+#pragma unroll
+      for (int w = 0; w < DN_WORDS; ++w) st[w] = 0;
+      st[3] = -1;
+    }
+    const float o0 = (float)st[1] * (1.0f / 131072.0f);  // powers of two: exact
+    const float o1 = (float)st[2] * (1.0f / 1024.0f);
+    const float o2 = (float)st[4] * (1.0f / 128.0f);
+    const float rew = (float)st[5] * (1.0f / 1024.0f);
+    if (bulk) {
+      // the previous use of this stage buffer (step t-2) must have been read out
+      if (slot == 0) bulk_wait_read<1>();
+      __syncthreads();
+      sg.obs[slot * 3 + 0] = o0;
+      sg.obs[slot * 3 + 1] = o1;
+      sg.obs[slot * 3 + 2] = o2;
+      sg.reward[slot] = rew;
+      sg.obs_mask[slot] = 1;
+      sg.reward_mask[slot] = 1;
+      sg.term[slot] = 0;
+      sg.trunc[slot] = 0;
+      fence_async_smem();
+      __syncthreads();
+      if (slot == 0) {
+        const size_t base = row * n;
+        if (a.io.obs) bulk_store(a.io.obs + base * 3, sg.obs, (uint32_t)n * 12u);
+        if (a.io.reward) bulk_store(a.io.reward + base, sg.reward, (uint32_t)n * 4u);
+        if (a.io.obs_mask) bulk_store(a.io.obs_mask + base, sg.obs_mask, (uint32_t)n);
+        if (a.io.reward_mask) bulk_store(a.io.reward_mask + base, sg.reward_mask, (uint32_t)n);
+        if (a.io.term) bulk_store(a.io.term + base, sg.term, (uint32_t)n);
+        if (a.io.trunc) bulk_store(a.io.trunc + base, sg.trunc, (uint32_t)n);
+        bulk_commit();
+      }
+    } else if (is_agent) {
+      const size_t o = row * n + slot;
+      if (a.io.obs) {
+        a.io.obs[o * 3 + 0] = o0; a.io.obs[o * 3 + 1] = o1; a.io.obs[o * 3 + 2] = o2;
+      }
+      if (a.io.reward) a.io.reward[o] = rew;
+      if (a.io.obs_mask) a.io.obs_mask[o] = 1;
+      if (a.io.reward_mask) a.io.reward_mask[o] = 1;
+      if (a.io.term) a.io.term[o] = 0;
+      if (a.io.trunc) a.io.trunc[o] = 0;
+    }
+    if (!bulk) __syncthreads();  // mailbox / ack arrays are rewritten by the next step
+    if (slot == 0 && a.io.all_done)
+      reinterpret_cast<uchar2*>(a.io.all_done)[row] = make_uchar2(n == 0, at_max ? 1 : 0);
+  }
+  if (slot == 0) {
+    bulk_wait<0>();
+    a.hdr[e] = h;
+  }
+#pragma unroll
+  for (int w = 0; w < DN_WORDS; ++w) a.state[((size_t)w * sp.E + e) * DN_MAX + slot] = st[w];
+  // first fault of the env (lowest slot)
+  const uint32_t fw = __ballot_sync(0xFFFFFFFFu, fault != 0);
+  __shared__ uint32_t fault_slot;
+  if (slot == 0) fault_slot = 0xFFFFFFFFu;
+  __syncthreads();
+  if (fw && lane == (__ffs(fw) - 1)) atomicMin(&fault_slot, (uint32_t)slot);
+  __syncthreads();
+  if (fault && fault_slot == (uint32_t)slot) raise_fault(a.faults, e, fault);
+}
+
+__global__ void dense_reset_kernel(DenseSpec sp, int4* hdr, int32_t* state, const uint8_t* env_mask,
+                                   float* obs, uint8_t* obs_mask, bool init_only) {
+  const int e = blockIdx.x, slot = threadIdx.x;
+  if (env_mask && env_mask[e] == 0) return;
+  if (init_only) {
+    if (slot == 0) hdr[e] = make_int4(0, -1, 0, 0);
+  } else if (slot == 0) {
+    int4 h = hdr[e];
+    h.x = 0;
+    h.y += 1;
+    hdr[e] = h;
+  }
+  for (int w = 0; w < DN_WORDS; ++w)
+    state[((size_t)w * sp.E + e) * DN_MAX + slot] = w == 3 ? -1 : 0;  // DenseAgent.reset
+  if (!init_only && slot < sp.n) {
+    const size_t o = (size_t)e * sp.n + slot;
+    if (obs) { obs[o * 3] = 0.f; obs[o * 3 + 1] = 0.f; obs[o * 3 + 2] = 0.f; }
+    if (obs_mask) obs_mask[o] = 1;
+  }
+}
+
+class DenseFamily final : public Family {
+ public:
+  ~DenseFamily() override {
+    cudaFree(d_state);
+    cudaFree(d_adj);
+  }
+
+  int32_t init(const phx_spec& s) override {
+    PHX_REQUIRE(s.env_kind == PHX_ENV_BASE, PHX_ERR_UNSUPPORTED,
+                "dense family runs under PhantomEnv (PHX_ENV_BASE) only");
+    PHX_REQUIRE(s.n_agents <= DN_MAX && s.n_strategic == s.n_agents, PHX_ERR_UNSUPPORTED,
+                "dense family: up to 128 agents, all strategic DenseAgents");
+    PHX_REQUIRE(s.obs_dim == 3 && s.act_dim == 1 && s.n_payload_types == 2, PHX_ERR_INVALID,
+                "dense family: obs_dim 3, act_dim 1, 2 payload types");
+    PHX_REQUIRE(!(s.flags & PHX_FLAG_IGNORE_CONNECTION_ERRORS), PHX_ERR_UNSUPPORTED,
+                "dense family: ignore_connection_errors has no effect (agents only address "
+                "neighbours) and is not accepted");
+    std::memset(&dsp, 0, sizeof(dsp));
+    dsp.E = E;
+    dsp.n = s.n_agents;
+    dsp.num_steps = s.num_steps;
+    dsp.round_limit = s.round_limit;
+    dsp.flags = s.flags;
+    for (int t = 0; t < 2; ++t)
+      for (int w = 0; w < 4; ++w) {
+        dsp.sender_ok[t][w] = s.type_sender_ok[t][w];
+        dsp.receiver_ok[t][w] = s.type_receiver_ok[t][w];
+      }
+    uint32_t h_adj[DN_MAX * 4];
+    std::memset(h_adj, 0, sizeof(h_adj));
+    for (int i = 0; i < s.n_agents; ++i) {
+      for (int w = 0; w < 4; ++w) h_adj[i * 4 + w] = s.adjacency[i][w];
+      for (int j = 0; j < s.n_agents; ++j)
+        PHX_REQUIRE(mask_bit(s.adjacency[i], j) == mask_bit(s.adjacency[j], i), PHX_ERR_INVALID,
+                    "dense family needs a symmetric graph (Network.add_connection always is)");
+    }
+    PHX_CUDA(cudaMalloc(&d_adj, sizeof(h_adj)));
+    PHX_CUDA(cudaMemcpy(d_adj, h_adj, sizeof(h_adj), cudaMemcpyHostToDevice));
+    PHX_CUDA(cudaMalloc(&d_state, sizeof(int32_t) * DN_WORDS * (size_t)E * DN_MAX));
+    dense_reset_kernel<<<E, DN_MAX>>>(dsp, d_hdr, d_state, nullptr, nullptr, nullptr, true);
+    PHX_CUDA(cudaGetLastError());
+    PHX_CUDA(cudaDeviceSynchronize());
+    if (tracking())
+      PHX_REQUIRE(s.trace_capacity >= s.n_agents * s.n_agents, PHX_ERR_INVALID,
+                  "trace_capacity must be >= n_agents^2 for the dense family");
+    PHX_CUDA(cudaFuncSetAttribute(dense_step_kernel<false>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DenseSmem)));
+    PHX_CUDA(cudaFuncSetAttribute(dense_step_kernel<true>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DenseSmem)));
+    return PHX_OK;
+  }
+
+  int32_t reset(const uint8_t* env_mask, float* obs, uint8_t* obs_mask,
+                cudaStream_t stream) override {
+    dense_reset_kernel<<<E, DN_MAX, 0, stream>>>(dsp, d_hdr, d_state, env_mask, obs, obs_mask, false);
+    PHX_CUDA(cudaGetLastError());
+    return PHX_OK;
+  }
+
+  int32_t rollout(int32_t T, const StepIO& io, cudaStream_t stream) override {
+    PHX_REQUIRE(!tracking() || T == 1, PHX_ERR_INVALID,
+                "message tracking records one step: use phx_step (T == 1)");
+    DenseArgs a;
+    a.sp = dsp;
+    a.T = T;
+    a.hdr = d_hdr;
+    a.state = d_state;
+    a.adj = d_adj;
+    a.io = io;
+    a.faults = fault_sink();
+    a.trace = trace_sink();
+    if (tracking()) dense_step_kernel<true><<<E, DN_MAX, sizeof(DenseSmem), stream>>>(a);
+    else dense_step_kernel<false><<<E, DN_MAX, sizeof(DenseSmem), stream>>>(a);
+    PHX_CUDA(cudaGetLastError());
+    return PHX_OK;
+  }
+
+  int32_t family_field(int32_t field, int32_t, void** p, size_t* bytes) override {
+    const int w = field - PHX_FIELD_FAMILY;
+    if (w >= 0 && w < DN_WORDS) {
+      *p = d_state + (size_t)w * E * DN_MAX;
+      *bytes = sizeof(int32_t) * (size_t)E * DN_MAX;
+      return PHX_OK;
+    }
+    set_error("dense family: unknown field " + std::to_string(field));
+    return PHX_ERR_INVALID;
+  }
+
+  const char* exec_name() const override { return "queue(block-per-env,G=128)"; }
+
+ private:
+  DenseSpec dsp{};
+  int32_t* d_state = nullptr;
+  uint32_t* d_adj = nullptr;
+};
+
+}  // namespace
+
+Family* make_dense_family(const phx_spec&) { return new DenseFamily(); }
+
+}  // namespace phx

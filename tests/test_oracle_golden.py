@@ -157,3 +157,30 @@ def test_object_oracle_matches_stackelberg_golden(golden_dir):
             rows += [(e, ep, t, s, r, wl.MESSAGE_TYPE_IDS[n], v0, v1)
                      for (ep, t, s, r, n, v0, v1) in tr["messages"]]
     assert np.array_equal(np.asarray(rows, np.int64), g["messages"])
+
+
+def test_object_oracle_matches_dense_goldens(golden_dir):
+    """C5 workload: oracle restatement == the reference running the same env definition (the
+    sparse 12-agent fixture incl. message order; one env of the 128-agent fixture)."""
+    from oracle.workloads import dense as wl
+
+    from .generic_parity import assert_oracle_trace_equal
+
+    g = np.load(os.path.join(golden_dir, "dense12_reference.npz"))
+    A, M = g["actions"], g["action_mask"]
+    rows = []
+    for e in range(3):
+        env = wl.build(po, n_agents=12, adjacency=g["adjacency"], enable_tracking=True)
+        tr = harness.run_generic(env, harness.EpisodeClock([]), A[e], M[e], 3, track=True,
+                                 state_fn=wl.state)
+        assert_oracle_trace_equal(tr, g, e)
+        rows += [(e, ep, t, s, r, wl.MESSAGE_TYPE_IDS[n], v0, v1)
+                 for (ep, t, s, r, n, v0, v1) in tr["messages"]]
+    gm = g["messages"]
+    assert np.array_equal(np.asarray(rows, np.int64), gm[gm[:, 0] < 3])
+    g = np.load(os.path.join(golden_dir, "dense128_reference.npz"))
+    env = wl.build(po, n_agents=128)
+    tr = harness.run_generic(env, harness.EpisodeClock([]), g["actions"][0, :1], g["action_mask"][0, :1],
+                             3, state_fn=wl.state)
+    for k in ["obs", "reward", "state", "obs_mask", "reward_mask", "all_done"]:
+        assert np.array_equal(tr[k][0], g[k][0, 0]), k
