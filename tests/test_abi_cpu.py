@@ -1,0 +1,135 @@
+"""CPU-only checks of the drop-in boundary: the C-ABI library loads, exports every symbol
+include/phx.h declares, the ctypes mirror of phx_spec matches the compiled layout, lowering
+produces the expected flat tables, and the product refuses to run without a GPU (no CPU
+fallback).  No compute calls."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import phantom_b200 as ph
+from phantom_b200 import _lib as L
+
+
+def header_functions():
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(here, "include", "phx.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(phx_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    declared = header_functions()
+    assert len(declared) >= 19
+    lib = C.CDLL(L.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/phx.h but not exported"
+    assert sorted(L.SYMBOLS) == declared, "ctypes binding and header disagree"
+
+
+def test_spec_layout_matches_compiled_struct():
+    assert L.lib.phx_sizeof_spec() == C.sizeof(L.PhxSpec)
+    assert L.lib.phx_abi_version() == 1
+
+
+def test_no_cpu_fallback():
+    from phantom_b200.envs.supply_chain import SupplyChainEnv
+
+    if L.lib.phx_device_count() > 0:
+        pytest.skip("a GPU is present")
+    env = SupplyChainEnv(num_envs=4)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        env.reset_batch()
+    # and the raw ABI refuses too
+    h = C.c_void_p()
+    spec = env.spec
+    rc = L.lib.phx_create(C.byref(spec), 4, 0, 0, 0, C.byref(h))
+    assert rc == L.PHX_ERR_NO_DEVICE and b"no CPU fallback" in L.lib.phx_last_error()
+
+
+def test_bad_spec_is_rejected_before_touching_the_device():
+    spec = L.PhxSpec()
+    h = C.c_void_p()
+    assert L.lib.phx_create(C.byref(spec), 4, 0, 0, 0, C.byref(h)) == L.PHX_ERR_INVALID
+    assert b"struct_size" in L.lib.phx_last_error()
+    assert L.lib.phx_create(None, 4, 0, 0, 0, C.byref(h)) == L.PHX_ERR_INVALID
+
+
+def test_lowering_supply_chain_tables():
+    from phantom_b200.envs.supply_chain import SupplyChainEnv
+
+    env = SupplyChainEnv()
+    s = env.spec
+    assert (s.family, s.env_kind, s.n_agents, s.n_strategic) == (L.FAMILY_SUPPLY_CHAIN, L.ENV_BASE, 7, 1)
+    assert list(s.agent_kind[:7]) == [0, 1, 2, 2, 2, 2, 2]
+    assert list(s.strategic_index[:7]) == [0, -1, -1, -1, -1, -1, -1]
+    # star on SHOP, every connection in both directions (network.py:122-123)
+    assert s.adjacency[0][0] == 0b1111110 and all(s.adjacency[i][0] == 1 for i in range(1, 7))
+    # OrderRequest: CustomerAgent -> ShopAgent (exact class-name whitelists, network.py:315-331)
+    assert s.type_sender_ok[0][0] == 0b1111100 and s.type_receiver_ok[0][0] == 0b1
+    assert s.round_limit == -1 and s.num_steps == 100 and (s.obs_dim, s.act_dim) == (3, 1)
+    assert (s.iparams[0], s.iparams[1]) == (5, 100)
+
+
+def test_lowering_fsm_and_stackelberg_tables():
+    from phantom_b200.envs.market import MarketEnv
+    from phantom_b200.envs.stackelberg_game import StackelbergGameEnv
+
+    s = MarketEnv().spec
+    assert (s.env_kind, s.n_stages, s.initial_stage, s.n_agents, s.n_strategic) == (L.ENV_FSM, 3, 0, 32, 31)
+    assert s.stages[0].acting[0] == 0x7F and s.stages[1].acting[0] == 0x7FFFFF80
+    assert s.stages[2].acting[0] == 1 << 31 and s.stages[2].rewarded[0] == 0x7FFFFFFF
+    assert [s.stages[k].next_stage for k in range(3)] == [1, 2, 0]
+    assert [s.stages[k].rewarded_is_none for k in range(3)] == [0, 0, 0]
+    s = StackelbergGameEnv().spec
+    assert (s.env_kind, s.leaders[0], s.followers[0]) == (L.ENV_STACKELBERG, 0b0001, 0b1110)
+
+
+def test_python_logic_is_never_silently_ignored():
+    """An agent class that (re)defines per-message logic in Python cannot be lowered -- the
+    product never runs Python handlers on the CPU instead."""
+    from phantom_b200.envs.supply_chain import ShopAgent, SupplyChainEnv
+
+    class GreedyShop(ShopAgent):
+        def compute_reward(self, ctx):
+            return 1.0
+
+    env = SupplyChainEnv()
+    env.network.agents["SHOP"].__class__ = GreedyShop
+    with pytest.raises(ph.NotLowerableError, match="compute_reward"):
+        env.spec
+
+    class Plain(ph.Agent):
+        pass
+
+    env = ph.PhantomEnv(num_steps=3, network=ph.Network([Plain("x")]))
+    with pytest.raises(ph.NotLowerableError, match="no device program"):
+        env.spec
+    with pytest.raises(ph.DeviceOnlyError):
+        ph.Network([Plain("x")]).send("x", "x", None)
+    with pytest.raises(ph.NotLowerableError):
+        ph.resolvers.BatchResolver(shuffle_batches=True)
+
+
+def test_network_construction_api_and_errors():
+    """Network builders and their validation errors (network.py:87-177)."""
+    from phantom_b200.envs.mock import MockAgent
+
+    with pytest.raises(ValueError):
+        ph.Network([MockAgent("a1"), MockAgent("a1")])
+    with pytest.raises(ValueError):
+        ph.Network([MockAgent("a1")], connections=[("a1", "a2")])
+    net = ph.Network([MockAgent("mm"), MockAgent("inv"), MockAgent("inv2")])
+    net.add_connection("mm", "inv")
+    assert net.has_edge("mm", "inv") and net.has_edge("inv", "mm") and not net.has_edge("mm", "inv2")
+    assert len(net) == 3 and net["mm"].id == "mm"
+    assert list(net.get_agents_where(lambda a: a.id == "mm")) == ["mm"]
+    assert net.get_agents_with_type(ph.Agent) == net.agents and net.get_agents_without_type(ph.Agent) == {}
+    ctx = net.context_for("mm", ph.EnvView(0, 0.0))
+    assert ctx.neighbour_ids == ["inv"] and "inv" in ctx and "inv2" not in ctx
+    sub = net.subnet_for("mm")
+    assert list(sub.agents) == ["mm", "inv"]
+    with pytest.raises(ValueError, match="square"):
+        net.add_connections_with_adjmat(["mm", "inv"], np.zeros((2, 3)))
