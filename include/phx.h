@@ -39,6 +39,7 @@ extern "C" {
 #define PHX_MASK_WORDS 4    /* PHX_MAX_AGENTS / 32                                   */
 #define PHX_MAX_PARAMS 16
 #define PHX_TRACE_WORDS 4   /* one traced message = 4 x int32 (see phx_get_trace)    */
+#define PHX_MAX_CODEC_OPS 6 /* encoder ops per agent (Chained/Dict encoder composition)*/
 
 typedef enum phx_status {
   PHX_OK = 0,
@@ -137,6 +138,11 @@ typedef struct phx_spec {
   int32_t agent_iparam[PHX_MAX_AGENTS][4]; /* per-slot family parameters, e.g. the slot
                                               of the peer an agent addresses           */
   double agent_fparam[PHX_MAX_AGENTS][2];
+  /* Encoder composition (phantom/encoders.py:64-131) lowered to a per-agent op list:
+   * op = opcode | length << 8 (opcode 0 constant, 1 proportion_time_elapsed, 2 current_step),
+   * evaluated in order into the agent's obs row; 0 terminates the list. */
+  int32_t agent_codec_op[PHX_MAX_AGENTS][PHX_MAX_CODEC_OPS];
+  float agent_codec_val[PHX_MAX_AGENTS][PHX_MAX_CODEC_OPS];
 } phx_spec;
 
 typedef struct phx_env phx_env; /* opaque */

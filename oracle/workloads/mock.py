@@ -97,6 +97,27 @@ def build_classes(ph):
             self.handled_total += message.payload.cash
             return []
 
+    Box = __import__("oracle.phantom_oracle.spaces", fromlist=["Box"]).Box
+
+    class ElapsedTime(ph.encoders.Encoder):
+        @property
+        def observation_space(self):
+            return Box(0.0, 1.0, (1,))
+
+        def encode(self, ctx):
+            return np.array([ctx.env_view.proportion_time_elapsed])
+
+    class CurrentStep(ph.encoders.Encoder):
+        @property
+        def observation_space(self):
+            return Box(0.0, np.inf, (1,))
+
+        def encode(self, ctx):
+            return np.array([float(ctx.env_view.current_step)])
+
+    class CodecAgent(ph.StrategicAgent):
+        """Pure composition: everything comes from the encoder / decoder / reward objects."""
+
     class NS:
         pass
 
@@ -105,6 +126,7 @@ def build_classes(ph):
     ns.TestMessage, ns.Request, ns.Response = TestMessage, Request, Response
     ns.MockAgent, ns.MockStrategicAgent, ns.EchoAgent = MockAgent, MockStrategicAgent, EchoAgent
     ns.NetworkError = ph.network.NetworkError
+    ns.CodecAgent, ns.ElapsedTime, ns.CurrentStep = CodecAgent, ElapsedTime, CurrentStep
 
     def finish_network(network):
         slots = {aid: i for i, aid in enumerate(network.agent_ids)}

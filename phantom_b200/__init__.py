@@ -9,14 +9,18 @@ built library raises ImportError.
 __version__ = "0.1.0"
 
 from . import _lib  # noqa: F401  (fails loudly if libphx.so is missing)
-from . import agents, context, errors, fsm, message, network, resolvers, spaces, views
+from . import (agents, context, decoders, encoders, errors, fsm, message, network, resolvers,
+               reward_functions, spaces, views)
 from .agents import Agent, StrategicAgent
 from .context import Context
+from .decoders import Decoder
+from .encoders import Encoder
 from .env import BatchStep, PhantomEnv
 from .errors import DeviceOnlyError, NotLowerableError
 from .fsm import FiniteStateMachineEnv, FSMStage
 from .message import Message, MsgPayload, msg_payload
 from .network import Network, NetworkError
+from .reward_functions import RewardFunction
 from .stackelberg import StackelbergEnv
 from .types import AgentID, PolicyID, StageID
 from .views import AgentView, EnvView, View

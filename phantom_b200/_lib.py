@@ -19,6 +19,7 @@ PHX_MAX_STAGES = 8
 PHX_MASK_WORDS = 4
 PHX_MAX_PARAMS = 16
 PHX_TRACE_WORDS = 4
+PHX_MAX_CODEC_OPS = 6
 
 # phx_status
 PHX_OK, PHX_ERR_INVALID, PHX_ERR_CUDA, PHX_ERR_UNSUPPORTED, PHX_ERR_NO_DEVICE = 0, -1, -2, -3, -4
@@ -79,6 +80,8 @@ class PhxSpec(C.Structure):
         ("fparams", C.c_double * PHX_MAX_PARAMS),
         ("agent_iparam", (C.c_int32 * 4) * PHX_MAX_AGENTS),
         ("agent_fparam", (C.c_double * 2) * PHX_MAX_AGENTS),
+        ("agent_codec_op", (C.c_int32 * PHX_MAX_CODEC_OPS) * PHX_MAX_AGENTS),
+        ("agent_codec_val", (C.c_float * PHX_MAX_CODEC_OPS) * PHX_MAX_AGENTS),
     ]
 
 

@@ -11,6 +11,11 @@
 //             tests/network/test_resolver.py:24-45  (request -> response(cash / 2))
 //           generate_messages: sends TestMessage(seed) to every neighbour with a HIGHER slot
 //           (in slot order) when seed > 0 -- this replaces the tests' hand-made n.send() calls
+//   kind 3  CodecAgent           a StrategicAgent assembled from Encoder / Decoder /
+//             RewardFunction objects (agents.py:199-290): obs = the agent's encoder op list
+//             (ChainedEncoder / DictEncoder / EmptyEncoder / Constant, encoders.py:53-131),
+//             decode = EmptyDecoder compositions (decoders.py:54-124: no messages),
+//             reward = reward_functions.Constant (reward_functions.py:26-38)
 // Payload types: 0 = TestMessage(value), 1 = Request(cash), 2 = Response(cash) (int payloads).
 // State words:   0 encode_obs_count, 1 decode_action_count, 2 compute_reward_count,
 //                3 messages handled, 4 sum of handled payload values
@@ -20,26 +25,31 @@
 namespace phx {
 namespace {
 
-enum { MK_AGENT = 0, MK_STRATEGIC = 1, MK_ECHO = 2 };
+enum { MK_AGENT = 0, MK_STRATEGIC = 1, MK_ECHO = 2, MK_CODEC = 3 };
 enum { MK_TEST_MESSAGE = 0, MK_REQUEST = 1, MK_RESPONSE = 2 };
 
 struct MockProgram {
-  static constexpr int PW = 1, NWORDS = 5, VW = 0, SEGCAP = 32, OBS_DIM = 1;
+  static constexpr int PW = 1, NWORDS = 5, VW = 0, SEGCAP = 32, OBS_DIM = 8;
   static constexpr bool BATCHED = false;
 
   static int32_t validate(const phx_spec& s) {
     for (int i = 0; i < s.n_agents; ++i)
-      PHX_REQUIRE(s.agent_kind[i] >= MK_AGENT && s.agent_kind[i] <= MK_ECHO, PHX_ERR_INVALID,
+      PHX_REQUIRE(s.agent_kind[i] >= MK_AGENT && s.agent_kind[i] <= MK_CODEC, PHX_ERR_INVALID,
                   "unknown mock agent kind");
-    PHX_REQUIRE(s.obs_dim == 1 && s.act_dim == 1, PHX_ERR_INVALID, "mock family: obs/act dim 1");
+    PHX_REQUIRE(s.obs_dim == 8 && s.act_dim == 1, PHX_ERR_INVALID, "mock family: obs 8, act 1");
+    for (int i = 0; i < s.n_agents; ++i) {
+      int total = 0;
+      for (int k = 0; k < PHX_MAX_CODEC_OPS; ++k) total += (s.agent_codec_op[i][k] >> 8) & 0xFF;
+      PHX_REQUIRE(total <= 8, PHX_ERR_UNSUPPORTED, "encoder composition wider than 8 floats");
+    }
     return PHX_OK;
   }
 
   template <class E>
   __device__ static void act(const Ctx& c, int* st, bool has_action, const float*, E& out) {
     const EngineSpec& sp = *c.spec;
-    if (c.kind == MK_STRATEGIC) {
-      if (has_action) st[1] += 1;  // decode_action_count; returns []
+    if (c.kind == MK_STRATEGIC || c.kind == MK_CODEC) {
+      if (has_action) st[1] += 1;  // decode_action_count; EmptyDecoder compositions return []
       return;
     }
     if (c.kind == MK_ECHO) {
@@ -71,14 +81,28 @@ struct MockProgram {
   }
 
   __device__ static bool encode(const Ctx& c, int* st, float* obs) {
-    if (c.kind != MK_STRATEGIC) return false;
+    if (c.kind == MK_STRATEGIC) {
+      st[0] += 1;
+      obs[0] = c.proportion_time_elapsed();
+      return true;
+    }
+    if (c.kind != MK_CODEC) return false;
     st[0] += 1;
-    obs[0] = c.proportion_time_elapsed();
+    int at = 0;
+    for (int k = 0; k < PHX_MAX_CODEC_OPS; ++k) {  // ChainedEncoder / DictEncoder: in order
+      const int op = c.spec->codec_op[c.slot][k];
+      const int len = (op >> 8) & 0xFF;
+      if (len == 0) break;
+      float v = c.spec->codec_val[c.slot][k];                        // Constant / EmptyEncoder
+      if ((op & 0xFF) == 1) v = c.proportion_time_elapsed();         // ElapsedTime
+      if ((op & 0xFF) == 2) v = (float)c.step;                       // CurrentStep
+      for (int j = 0; j < len && at < OBS_DIM; ++j) obs[at++] = v;
+    }
     return true;
   }
-  __device__ static float reward(const Ctx&, int* st) {
+  __device__ static float reward(const Ctx& c, int* st) {
     st[2] += 1;
-    return 0.0f;
+    return c.kind == MK_CODEC ? c.spec->agent_fparam[c.slot][0] : 0.0f;  // Constant(value)
   }
   __device__ static bool terminated(const Ctx& c, const int*) {
     return c.step == c.spec->agent_iparam[c.slot][0];

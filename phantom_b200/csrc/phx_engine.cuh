@@ -59,6 +59,9 @@ struct EngineSpec {
   int32_t iparams[PHX_MAX_PARAMS];
   float fparams[PHX_MAX_PARAMS];
   int32_t agent_iparam[ENGINE_MAX_AGENTS][4];
+  float agent_fparam[ENGINE_MAX_AGENTS][2];
+  int32_t codec_op[ENGINE_MAX_AGENTS][PHX_MAX_CODEC_OPS];  // opcode | length << 8
+  float codec_val[ENGINE_MAX_AGENTS][PHX_MAX_CODEC_OPS];
 };
 
 struct Msg {
@@ -362,7 +365,7 @@ __global__ void __launch_bounds__(ENGINE_BLOCK) engine_step_kernel(const EngineA
     // ---- outputs for strategic agents (env.py:273-303; fsm.py:322-378;
     // stackelberg.py:149-194)
     bool obs_now = false, rew_now = false;
-    float obs_val[P::OBS_DIM];
+    float obs_val[P::OBS_DIM] = {};
     float rew_val = 0.f;
     bool t_flag = false, u_flag = false;
     if (strategic && has_ctx) {
@@ -561,7 +564,7 @@ engine_reset_kernel(const EngineArgs<P> a, const uint8_t* env_mask, float* obs, 
   if (sp.env_kind == PHX_ENV_STACKELBERG) first_obs &= sp.leaders;
   if (env_live) {
     if (sidx >= 0) {
-      float obs_val[P::OBS_DIM];
+      float obs_val[P::OBS_DIM] = {};
       bool got = false;
       if ((first_obs >> slot) & 1u) got = P::encode(ctx, st, obs_val);
       const size_t orow = (size_t)e * sp.n_strategic + sidx;

@@ -33,6 +33,11 @@ inline int32_t make_engine_spec(const phx_spec& s, int32_t E, uint64_t seed, int
     d.adj[i] = s.adjacency[i][0];
     if (s.strategic_index[i] >= 0) d.strategic_mask |= 1u << i;
     for (int k = 0; k < 4; ++k) d.agent_iparam[i][k] = s.agent_iparam[i][k];
+    for (int k = 0; k < 2; ++k) d.agent_fparam[i][k] = (float)s.agent_fparam[i][k];
+    for (int k = 0; k < PHX_MAX_CODEC_OPS; ++k) {
+      d.codec_op[i][k] = s.agent_codec_op[i][k];
+      d.codec_val[i][k] = s.agent_codec_val[i][k];
+    }
   }
   for (int t = 0; t < s.n_payload_types; ++t) {
     d.sender_ok[t] = s.type_sender_ok[t][0];

@@ -361,8 +361,12 @@ class PhantomEnv:
         out = {}
         for s, agent in enumerate(self.strategic_agents):
             if obs_mask[s]:
-                n = self._agent_obs_dim(agent)
-                out[agent.id] = np.array(obs[s, :n], dtype=np.float32)
+                enc = getattr(agent, "observation_encoder", None)
+                if enc is not None:  # Chained / Dict encoders: rebuild the tuple / dict
+                    out[agent.id] = enc.unflatten(np.array(obs[s], dtype=np.float32))
+                else:
+                    n = self._agent_obs_dim(agent)
+                    out[agent.id] = np.array(obs[s, :n], dtype=np.float32)
         return out
 
     def _agent_obs_dim(self, agent) -> int:

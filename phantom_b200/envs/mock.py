@@ -16,7 +16,7 @@ from phantom_b200.agents import device_column
 from phantom_b200.families import FamilyInfo, register
 from phantom_b200.spaces import Box
 
-KIND_AGENT, KIND_STRATEGIC, KIND_ECHO = 0, 1, 2
+KIND_AGENT, KIND_STRATEGIC, KIND_ECHO, KIND_CODEC = 0, 1, 2, 3
 
 
 @ph.msg_payload()
@@ -61,6 +61,24 @@ class MockStrategicAgent(ph.StrategicAgent):
         self.num_steps = num_steps
 
 
+class CodecAgent(ph.StrategicAgent):
+    """A StrategicAgent assembled from Encoder / Decoder / RewardFunction objects, with no
+    behaviour of its own (reference: agents.py:199-290 -- the encoder / decoder / reward
+    function are consulted by the default encode_observation / decode_action /
+    compute_reward).  All three must be device-lowerable."""
+
+    __phx_family__ = "mock"
+    __phx_kind__ = KIND_CODEC
+    __phx_device_class__ = True
+
+    encode_obs_count = device_column(0)
+    decode_action_count = device_column(1)
+    compute_reward_count = device_column(2)
+
+    def __init__(self, agent_id, observation_encoder, action_decoder, reward_function):
+        super().__init__(agent_id, observation_encoder, action_decoder, reward_function)
+
+
 class EchoAgent(ph.Agent):
     """seed_value > 0: every step, sends TestMessage / Request(seed_value) to each neighbour
     with a higher slot.  Handles TestMessage(v) by replying v // 2 while v > 1, Request(c) by
@@ -80,6 +98,24 @@ class EchoAgent(ph.Agent):
 
 
 def _collect(env, agents, spec) -> None:
+    from phantom_b200.errors import NotLowerableError
+
+    for i, a in enumerate(agents):
+        if isinstance(a, CodecAgent):
+            for name in ("observation_encoder", "action_decoder", "reward_function"):
+                if getattr(a, name) is None:  # agents.py:240-243,265-268,285-288
+                    raise NotImplementedError(
+                        f"Agent '{a.id}' does not have a {name} instance set")
+            ops = a.observation_encoder.device_ops()
+            if len(ops) > L.PHX_MAX_CODEC_OPS or sum(n for _, n, _ in ops) > 8:
+                raise NotLowerableError(f"encoder of agent '{a.id}' is too large for the device")
+            for k, (code, n, value) in enumerate(ops):
+                spec.agent_codec_op[i][k] = code | (n << 8)
+                spec.agent_codec_val[i][k] = value
+            if a.action_decoder.flat_dim() > 1:
+                pass  # wider Tuple / Dict action rows: only the declared width matters here
+            a.action_decoder.device_ops()  # raises NotLowerableError for non-device decoders
+            spec.agent_fparam[i][0] = a.reward_function.device_op()[1]
     for i, a in enumerate(agents):
         ns = getattr(a, "num_steps", None)
         spec.agent_iparam[i][0] = -1 if ns is None else int(ns)
@@ -91,7 +127,7 @@ FAMILY = register(FamilyInfo(
     name="mock",
     family_id=L.FAMILY_MOCK,
     payload_types=(TestMessage, Request, Response),
-    obs_dim=1,
+    obs_dim=8,
     act_dim=1,
     env_kinds=(L.ENV_BASE, L.ENV_FSM, L.ENV_STACKELBERG),
     collect=_collect,

@@ -367,6 +367,47 @@ def scenario_done_agent_mail_is_dropped(K):
     return env
 
 
+def scenario_codec_composition(K):
+    """Encoder / decoder / reward-function composition on the step path
+    (encoders.py:64-131, decoders.py:54-124, reward_functions.py:26-38; composition semantics
+    pinned by /root/reference/tests/encoders/test_chained.py:23-43, test_dict.py:23-50,
+    tests/decoders/test_chained.py:25-51, test_dict.py:27-54): sub-encoders are evaluated in
+    list / dict order, Empty decoders produce no messages, Constant rewards."""
+    ph = K.ph
+    enc, dec, rf = ph.encoders, ph.decoders, ph.reward_functions
+    a = K.CodecAgent(
+        "A", enc.ChainedEncoder([enc.Constant((2,), 0.5), K.ElapsedTime()]).chain([enc.EmptyEncoder()]),
+        dec.EmptyDecoder(), rf.Constant(1.5))
+    b = K.CodecAgent(
+        "B", enc.DictEncoder({"t": K.CurrentStep(), "z": enc.EmptyEncoder(), "c": enc.Constant((1,), -3.0)}),
+        dec.ChainedDecoder([dec.EmptyDecoder(), dec.EmptyDecoder()]), rf.Constant(-2.0))
+    assert len(a.observation_space.spaces) == 3 and set(b.observation_space.spaces) == {"t", "z", "c"}
+    env = ph.PhantomEnv(num_steps=4, network=K.finish_network(ph.Network([a, b])))
+    obs, _ = env.reset()
+
+    def check(obs, step):
+        assert isinstance(obs["A"], tuple) and len(obs["A"]) == 3
+        np.testing.assert_allclose(obs["A"][0], [0.5, 0.5])
+        np.testing.assert_allclose(obs["A"][1], [step / 4], rtol=1e-6)
+        np.testing.assert_allclose(obs["A"][2], [0.0])
+        assert list(obs["B"]) == ["t", "z", "c"]
+        np.testing.assert_allclose(obs["B"]["t"], [float(step)])
+        np.testing.assert_allclose(obs["B"]["z"], [0.0])
+        np.testing.assert_allclose(obs["B"]["c"], [-3.0])
+
+    check(obs, 0)
+    for t in (1, 2, 3, 4):
+        s = env.step({"A": np.array([0.0]), "B": (np.array([0.0]), np.array([0.0]))})
+        check(s.observations, t)
+        assert s.rewards == {"A": 1.5, "B": -2.0}
+        assert s.truncations["__all__"] is (t == 4)
+    # composition bookkeeping of the reference: chain() flattens, reset() propagates
+    ce = enc.ChainedEncoder([enc.EmptyEncoder(), [enc.EmptyEncoder(), enc.EmptyEncoder()]])
+    assert len(ce.encoders) == 3
+    ce.reset()
+    return env
+
+
 ALL = [
     scenario_env_step_with_done_dropout,
     scenario_is_terminated_truncated,
@@ -380,4 +421,5 @@ ALL = [
     scenario_round_limit,
     scenario_unknown_message_type,
     scenario_done_agent_mail_is_dropped,
+    scenario_codec_composition,
 ]

@@ -19,6 +19,8 @@ def K():
     ns.ph = ph
     ns.MockAgent, ns.MockStrategicAgent, ns.EchoAgent = mock.MockAgent, mock.MockStrategicAgent, mock.EchoAgent
     ns.finish_network = lambda network: network
+    ns.CodecAgent = mock.CodecAgent
+    ns.ElapsedTime, ns.CurrentStep = ph.encoders.ElapsedTime, ph.encoders.CurrentStep
     return ns
 
 
