@@ -153,8 +153,8 @@ typedef enum phx_field {
   PHX_FIELD_STEP = 0,       /* int32 [E]   PhantomEnv.current_step                   */
   PHX_FIELD_EPISODE = 1,    /* int32 [E]   resets seen - 1 (RNG contract coordinate) */
   PHX_FIELD_STAGE = 2,      /* int32 [E]   FSM current stage index                   */
-  PHX_FIELD_TERMINATED = 3, /* uint32[E,W] PhantomEnv._terminations as bitmask over
-                               strategic index, W = ceil(S/32)                       */
+  PHX_FIELD_TERMINATED = 3, /* uint32[E,W] PhantomEnv._terminations as a bitmask over agent
+                               slots (only strategic slots are ever set), W words   */
   PHX_FIELD_TRUNCATED = 4,  /* uint32[E,W]                                           */
   PHX_FIELD_ERROR = 5,      /* uint32[E]   sticky fault word                         */
   PHX_FIELD_FAMILY = 16

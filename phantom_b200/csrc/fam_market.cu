@@ -24,7 +24,10 @@ constexpr int MKT_NO_QUOTE = 1 << 20;
 constexpr int MKT_STREAM_VALUE = 1;
 
 struct MarketProgram {
-  static constexpr int PW = 2, NWORDS = 8, VW = 1, SEGCAP = 32, OBS_DIM = 3;
+  // a maker quotes up to 24 takers and the clearing agent settles with 31 agents in the acting
+  // phase; no handler of this market ever answers a message
+  static constexpr int PW = 2, NWORDS = 8, VW = 1, ACTCAP = 32, RESPCAP = 1, OBS_DIM = 3,
+                       ACT_DIM = 1;
   static constexpr bool BATCHED = false;
 
   static int32_t validate(const phx_spec& s) {
@@ -56,20 +59,21 @@ struct MarketProgram {
         return;
       }
       st[2] = max(0, min(100, __float2int_rn(__fmul_rn(a0, 100.0f))));
-      for (int r = 0; r < sp.n_agents; ++r)  // taker_ids in agent order
-        if (sp.kind[r] == MKT_TAKER && c.has_neighbour(r)) out.send(r, MKT_QUOTE, st[2]);
+      for (uint32_t m = c.neighbours_of_kind(MKT_TAKER); m; m &= m - 1)  // taker_ids, agent order
+        out.send(__ffs(m) - 1, MKT_QUOTE, st[2]);
     } else if (c.kind == MKT_TAKER) {
       if (has_action && __float2int_rn(action[0]) == 1 && st[2] >= 0)
         out.send(sp.iparams[6], MKT_ORDER, st[2], st[1]);
     } else if (c.stage == sp.iparams[5]) {  // ClearingAgent.generate_messages, CLEARING stage
-      for (int r = 0; r < sp.n_agents; ++r)
-        if (sp.kind[r] == MKT_MAKER && c.has_neighbour(r)) {
-          const int w = st[sp.agent_iparam[r][0]];
-          out.send(r, MKT_FILL, w & 0xFF, w >> 8);
-        }
-      for (int r = 0; r < sp.n_agents; ++r)
-        if (sp.kind[r] == MKT_TAKER && c.has_neighbour(r))
-          out.send(r, MKT_FILL, (st[7] >> sp.agent_iparam[r][0]) & 1, 0);
+      for (uint32_t m = c.neighbours_of_kind(MKT_MAKER); m; m &= m - 1) {
+        const int r = __ffs(m) - 1;
+        const int w = st[c.iparam0_of(r)];
+        out.send(r, MKT_FILL, w & 0xFF, w >> 8);
+      }
+      for (uint32_t m = c.neighbours_of_kind(MKT_TAKER); m; m &= m - 1) {
+        const int r = __ffs(m) - 1;
+        out.send(r, MKT_FILL, (st[7] >> c.iparam0_of(r)) & 1, 0);
+      }
     }
   }
 
@@ -100,7 +104,7 @@ struct MarketProgram {
         if (c.view_of(m.sender)[0] <= 0) return true;  // maker had no inventory at step start
         if (m.p[0] < st[1]) {
           st[1] = m.p[0];
-          st[2] = sp.agent_iparam[m.sender][0];
+          st[2] = c.iparam0_of(m.sender);
         }
         return true;
       }
@@ -117,7 +121,7 @@ struct MarketProgram {
     const int mk = m.p[0];
     if ((st[mk] & 0xFF) < sp.iparams[3]) {  // first come, first served
       st[mk] += 1 + (m.p[1] << 8);
-      st[7] |= 1 << sp.agent_iparam[m.sender][0];
+      st[7] |= 1 << c.iparam0_of(m.sender);
     }
     return true;
   }

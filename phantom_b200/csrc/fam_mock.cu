@@ -29,7 +29,8 @@ enum { MK_AGENT = 0, MK_STRATEGIC = 1, MK_ECHO = 2, MK_CODEC = 3 };
 enum { MK_TEST_MESSAGE = 0, MK_REQUEST = 1, MK_RESPONSE = 2 };
 
 struct MockProgram {
-  static constexpr int PW = 1, NWORDS = 5, VW = 0, SEGCAP = 32, OBS_DIM = 8;
+  static constexpr int PW = 1, NWORDS = 5, VW = 0, ACTCAP = 32, RESPCAP = 32, OBS_DIM = 8,
+                       ACT_DIM = 1;
   static constexpr bool BATCHED = false;
 
   static int32_t validate(const phx_spec& s) {
@@ -56,8 +57,8 @@ struct MockProgram {
       const int seed = sp.agent_iparam[c.slot][1];
       if (seed <= 0) return;
       const int type = sp.agent_iparam[c.slot][2] ? MK_REQUEST : MK_TEST_MESSAGE;
-      for (int r = c.slot + 1; r < sp.n_agents; ++r)
-        if (c.has_neighbour(r)) out.send(r, type, seed);
+      for (uint32_t m = c.out_mask & ~((2u << c.slot) - 1u); m; m &= m - 1)
+        out.send(__ffs(m) - 1, type, seed);
     }
   }
   __device__ static void view(const Ctx&, const int*, int*) {}

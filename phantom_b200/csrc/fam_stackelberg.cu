@@ -18,7 +18,8 @@ enum { SK_PRICE = 0, SK_DEMAND = 1, SK_ACK = 2 };
 constexpr int SK_STREAM_VALUE = 2;
 
 struct StackelbergProgram {
-  static constexpr int PW = 1, NWORDS = 4, VW = 0, SEGCAP = 8, OBS_DIM = 2;
+  static constexpr int PW = 1, NWORDS = 4, VW = 0, ACTCAP = 8, RESPCAP = 8, OBS_DIM = 2,
+                       ACT_DIM = 1;
   static constexpr bool BATCHED = false;
 
   static int32_t validate(const phx_spec& s) {
@@ -44,8 +45,8 @@ struct StackelbergProgram {
     }
     if (c.kind == SK_LEADER) {
       st[0] = max(0, min(100, __float2int_rn(__fmul_rn(a0, 100.0f))));
-      for (int r = 0; r < sp.n_agents; ++r)
-        if (sp.kind[r] == SK_FOLLOWER && c.has_neighbour(r)) out.send(r, SK_PRICE, st[0]);
+      for (uint32_t m = c.neighbours_of_kind(SK_FOLLOWER); m; m &= m - 1)
+        out.send(__ffs(m) - 1, SK_PRICE, st[0]);
     } else {
       const int qty = max(0, min(10, __float2int_rn(__fmul_rn(a0, 10.0f))));
       out.send(sp.agent_iparam[c.slot][1], SK_DEMAND, qty);

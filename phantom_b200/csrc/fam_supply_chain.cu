@@ -609,7 +609,10 @@ class SupplyChainFast final : public Family {
 //                           shop -> its factory);  [slot][1] = customer ordinal (RNG idx)
 template <int SEGCAP_>
 struct ScProgram {
-  static constexpr int PW = 1, NWORDS = 4, VW = 0, SEGCAP = SEGCAP_, OBS_DIM = 3;
+  // every agent sends at most one message in the acting phase; the shop answers every order
+  static constexpr int PW = 1, NWORDS = 4, VW = 0, ACTCAP = 1, RESPCAP = SEGCAP_, OBS_DIM = 3,
+                       ACT_DIM = 1;
+  static constexpr int SEGCAP = SEGCAP_;
   static constexpr bool BATCHED = false;
 
   static int32_t validate(const phx_spec& s) {

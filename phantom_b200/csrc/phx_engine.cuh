@@ -48,6 +48,7 @@ struct EngineSpec {
   uint32_t sender_ok[PHX_MAX_TYPES];   // bit s: slot s may send this payload type
   uint32_t receiver_ok[PHX_MAX_TYPES];
   uint32_t strategic_mask;             // over slots
+  uint32_t kind_mask[8];               // slots of each agent kind
   int32_t n_stages, initial_stage;
   uint32_t stage_acting[PHX_MAX_STAGES];
   uint32_t stage_rewarded[PHX_MAX_STAGES];
@@ -78,8 +79,12 @@ struct Ctx {
   int stage;        // FSMEnvView.stage index
   uint32_t env_id;  // global env index (RNG contract)
   uint32_t episode;
-  const int* views; // start-of-step snapshot, [slot][VW] (this env's tile)
+  uint32_t out_mask;   // adjacency row of this agent: bit r = edge slot -> r
+  uint32_t in_mask;    // adjacency column: bit s = edge s -> slot
+  const int* views;    // start-of-step snapshot, [slot][VW] (this env's tile, shared memory)
   int view_stride;
+  const int8_t* kind_tab;   // per-slot tables staged in shared memory (dynamic lookups by
+  const int32_t* ip0_tab;   // sender / receiver slot would serialise on the constant bank)
   __device__ __forceinline__ float proportion_time_elapsed() const {
     // EnvView.proportion_time_elapsed = current_step / num_steps in float64 (env.py:166-168)
     return (float)((double)step / (double)spec->num_steps);
@@ -88,8 +93,14 @@ struct Ctx {
     return views + other_slot * view_stride;
   }
   __device__ __forceinline__ bool has_neighbour(int other_slot) const {
-    return (spec->adj[slot] >> other_slot) & 1u;
+    return (out_mask >> other_slot) & 1u;
   }
+  // neighbours of a given agent kind, as a slot bitmask (iterate with __ffs)
+  __device__ __forceinline__ uint32_t neighbours_of_kind(int k) const {
+    return out_mask & spec->kind_mask[k];
+  }
+  __device__ __forceinline__ int kind_of(int other_slot) const { return kind_tab[other_slot]; }
+  __device__ __forceinline__ int iparam0_of(int other_slot) const { return ip0_tab[other_slot]; }
   __device__ __forceinline__ uint32_t rand24_hi(uint32_t stream, uint32_t idx) const {
     return rng_d24_hi(spec->seed, env_id, episode, (uint32_t)step, stream, idx);
   }
@@ -100,6 +111,7 @@ struct Ctx {
 // different banks.
 template <int G, int SEGCAP, int PW>
 struct TileQueue {
+  static constexpr int CAP = SEGCAP;
   uint32_t head[SEGCAP][G];   // sender | recv << 8 | type << 16
   int32_t pay[PW][SEGCAP][G];
   uint8_t cnt[G];             // entries per segment
@@ -109,17 +121,17 @@ struct TileQueue {
 
 // Emission cursor of one lane: appends to the lane's own segment after the reference's send
 // checks (network.py:246-254).
-template <int G, int SEGCAP, int PW>
+template <class Q>
 struct Emit {
-  TileQueue<G, SEGCAP, PW>* q;
+  Q* q;
   const EngineSpec* spec;
   int slot;
+  uint32_t out_mask;
   int n;
   uint32_t fault;
   __device__ __forceinline__ void send(int recv, int type, int p0, int p1 = 0) {
     if (fault) return;
-    const bool edge = (spec->adj[slot] >> recv) & 1u;
-    if (!(spec->flags & PHX_FLAG_IGNORE_CONNECTION_ERRORS) && !edge) {
+    if (!(spec->flags & PHX_FLAG_IGNORE_CONNECTION_ERRORS) && !((out_mask >> recv) & 1u)) {
       fault = PHX_FAULT_NO_EDGE;
       return;
     }
@@ -129,13 +141,13 @@ struct Emit {
         return;
       }
     }
-    if (n >= SEGCAP) {
+    if (n >= Q::CAP) {
       fault = PHX_FAULT_QUEUE_OVERFLOW;
       return;
     }
     q->head[n][slot] = (uint32_t)slot | ((uint32_t)recv << 8) | ((uint32_t)type << 16);
     q->pay[0][n][slot] = p0;
-    if (PW > 1) q->pay[PW > 1 ? 1 : 0][n][slot] = p1;
+    if (sizeof(q->pay) / sizeof(q->pay[0]) > 1) q->pay[sizeof(q->pay) / sizeof(q->pay[0]) > 1 ? 1 : 0][n][slot] = p1;
     ++n;
   }
 };
@@ -145,7 +157,7 @@ struct EngineArgs {
   EngineSpec spec;
   int32_t T;
   int4* hdr;            // [E] step, episode, stage, -
-  uint32_t* term;       // [E] bitmask over strategic index
+  uint32_t* term;       // [E] PhantomEnv._terminations as a bitmask over agent slots
   uint32_t* trunc;      // [E]
   int32_t* state;       // [NWORDS][E][G]
   float* reward_cache;  // [E][G]   FSM / Stackelberg `_rewards` (by slot)
@@ -161,13 +173,98 @@ __device__ __forceinline__ uint32_t tile_mask(int G) {
   return G >= 32 ? 0xFFFFFFFFu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
 }
 
-// Shared-memory footprint of one env tile.
+// Shared-memory footprint of one env tile.  The acting phase and the response rounds have
+// different fan-outs (a maker quotes 24 takers, but nobody answers a quote), so they get
+// separately sized queues: `qa` holds the acting-phase sends (ACTCAP per agent), `qr[2]`
+// alternate between the response rounds (RESPCAP per agent).
 template <class P, int G>
 struct TileSmem {
-  TileQueue<G, P::SEGCAP, P::PW> q[2];
+  TileQueue<G, P::ACTCAP, P::PW> qa;
+  TileQueue<G, P::RESPCAP, P::PW> qr[2];
   int32_t views[G][P::VW > 0 ? P::VW : 1];
   int32_t first_idx[G];
 };
+
+template <class P, int G>
+struct BlockSmem {
+  int8_t kind_tab[ENGINE_MAX_AGENTS];
+  int32_t ip0_tab[ENGINE_MAX_AGENTS];
+  TileSmem<P, G> tiles[ENGINE_BLOCK / G];
+};
+
+// One resolver round (resolvers.py:137-158): every receiver lane scans the current queue in
+// global push order, handles its batch, appends its responses to its segment of `qn`, and the
+// tile computes `qn`'s segment order = receivers by first-arrival position.  Returns the number
+// of responses pushed (tile-uniform).
+template <class P, int G, bool TRACK, class QC, class QN>
+__device__ __forceinline__ int engine_round(const EngineArgs<P>& a, const Ctx& ctx, int* st,
+                                            bool has_ctx, QC& qc, QN& qn, int32_t* first_idx,
+                                            int round, uint32_t tmask, uint32_t& fault_key,
+                                            int& traced, int e, bool trace_lane) {
+  constexpr int INF = 0x7FFFFFFF;
+  const int slot = ctx.slot;
+  Emit<QN> resp{&qn, ctx.spec, slot, ctx.out_mask, 0, 0u};
+  int first = INF, pos = 0;
+  bool bad_type = false;
+  if constexpr (P::BATCHED) {
+    if (has_ctx) P::batch_begin(ctx, st);
+  }
+  const int nseg = qc.nseg;
+  for (int si = 0; si < nseg; ++si) {
+    const int seg = qc.order[si];
+    const int c = qc.cnt[seg];
+    for (int k = 0; k < c; ++k, ++pos) {
+      const uint32_t hd = qc.head[k][seg];
+      if ((int)((hd >> 8) & 0xFFu) != slot) continue;
+      if (first == INF) first = pos;  // first-arrival position of this receiver
+      if (!has_ctx) continue;         // done agent: mail dropped (resolvers.py:143-144)
+      const int sender = (int)(hd & 0xFFu);
+      if (!((ctx.in_mask >> sender) & 1u)) continue;  // delivery-time edge filter (:146-148)
+      Msg m;
+      m.sender = sender;
+      m.type = (int)((hd >> 16) & 0xFFu);
+      m.p[0] = qc.pay[0][k][seg];
+      m.p[1] = P::PW > 1 ? qc.pay[P::PW > 1 ? 1 : 0][k][seg] : 0;
+      if (!P::handle(ctx, st, m, resp)) bad_type = true;  // agents.py:140-143
+    }
+  }
+  if constexpr (P::BATCHED) {
+    if (has_ctx && first != INF) P::batch_end(ctx, st, resp);
+  }
+  if (bad_type)
+    fault_key = min(fault_key, ((uint32_t)(round + 1) << 16) | ((uint32_t)slot << 8) |
+                                   PHX_FAULT_UNKNOWN_MSG_TYPE);
+  if (resp.fault)
+    fault_key = min(fault_key, ((uint32_t)(round + 1) << 16) | ((uint32_t)slot << 8) | resp.fault);
+  qn.cnt[slot] = (uint8_t)resp.n;
+  first_idx[slot] = first;
+  const int total_next = __reduce_add_sync(tmask, resp.n);  // also orders the smem writes
+  __syncwarp(tmask);
+  // next queue's segment order = receivers by first-arrival position
+  int rank = 0, nrecv = 0;
+#pragma unroll
+  for (int j = 0; j < G; ++j) {
+    const int fj = first_idx[j];
+    nrecv += fj != INF;
+    rank += fj < first;
+  }
+  if (first != INF) qn.order[rank] = (uint8_t)slot;
+  if (slot == 0) qn.nseg = nrecv;
+  __syncwarp(tmask);
+  if (TRACK && trace_lane) {
+    for (int si = 0; si < nrecv; ++si) {
+      const int seg = qn.order[si];
+      for (int k = 0; k < qn.cnt[seg]; ++k) {
+        if (traced < a.trace.cap)
+          a.trace.rows[(size_t)e * a.trace.cap + traced] =
+              make_int4((int)qn.head[k][seg], qn.pay[0][k][seg],
+                        P::PW > 1 ? qn.pay[P::PW > 1 ? 1 : 0][k][seg] : 0, round + 1);
+        ++traced;
+      }
+    }
+  }
+  return total_next;
+}
 
 // The fused step kernel.  P is the device program of a family (see fam_*.cu for the
 // interface: view / act / pre / handle / post / encode / reward / terminated / truncated /
@@ -176,9 +273,8 @@ struct TileSmem {
 template <class P, int G, bool TRACK>
 __global__ void __launch_bounds__(ENGINE_BLOCK) engine_step_kernel(const EngineArgs<P> a) {
   constexpr int TPB = ENGINE_BLOCK / G;  // env tiles per block
-  constexpr int INF = 0x7FFFFFFF;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  TileSmem<P, G>* tiles = reinterpret_cast<TileSmem<P, G>*>(smem_raw);
+  BlockSmem<P, G>& bs = *reinterpret_cast<BlockSmem<P, G>*>(smem_raw);
 
   const EngineSpec& sp = a.spec;
   const int tb = threadIdx.x / G;
@@ -187,13 +283,21 @@ __global__ void __launch_bounds__(ENGINE_BLOCK) engine_step_kernel(const EngineA
   const bool env_live = env < sp.E;
   const bool is_agent = env_live && slot < sp.n_agents;
   const uint32_t tmask = tile_mask(G);
-  TileSmem<P, G>& ts = tiles[tb];
+  const int tile_shift = G >= 32 ? 0 : ((threadIdx.x & 31) / G * G);
+  TileSmem<P, G>& ts = bs.tiles[tb];
   const int e = env_live ? env : sp.E - 1;
+
+  if (threadIdx.x < ENGINE_MAX_AGENTS) {
+    bs.kind_tab[threadIdx.x] = sp.kind[threadIdx.x];
+    bs.ip0_tab[threadIdx.x] = sp.agent_iparam[threadIdx.x][0];
+  }
+  __syncthreads();
 
   const int kind = slot < sp.n_agents ? sp.kind[slot] : -1;
   const int sidx = slot < sp.n_agents ? sp.sidx[slot] : -1;
   const bool strategic = sidx >= 0;
-  const int S = sp.n_strategic, O = sp.obs_dim, A = sp.act_dim;
+  const uint32_t slot_bit = 1u << slot;
+  const int S = sp.n_strategic, O = sp.obs_dim;
 
   // ---- load env header, done sets, agent state, caches (once per launch)
   int4 h = a.hdr[e];
@@ -218,15 +322,45 @@ __global__ void __launch_bounds__(ENGINE_BLOCK) engine_step_kernel(const EngineA
   ctx.env_id = sp.env_offset + (uint32_t)e;
   ctx.views = &ts.views[0][0];
   ctx.view_stride = P::VW > 0 ? P::VW : 1;
+  ctx.kind_tab = bs.kind_tab;
+  ctx.ip0_tab = bs.ip0_tab;
+  ctx.out_mask = slot < sp.n_agents ? sp.adj[slot] : 0u;
+  {
+    uint32_t in = 0;
+    for (int s = 0; s < sp.n_agents; ++s) in |= ((sp.adj[s] >> slot) & 1u) << s;
+    ctx.in_mask = in;
+  }
+
+  // actions are prefetched one step ahead (a step of this kernel is far longer than the HBM
+  // latency), so the acting phase never waits on the load
+  float act_next[P::ACT_DIM];
+  uint8_t has_next = 1;
+#pragma unroll
+  for (int j = 0; j < P::ACT_DIM; ++j) act_next[j] = 0.f;
+  if (strategic && env_live) {
+    const size_t arow = (size_t)e * S + sidx;
+#pragma unroll
+    for (int j = 0; j < P::ACT_DIM; ++j) act_next[j] = a.io.actions[arow * P::ACT_DIM + j];
+    if (a.io.action_mask) has_next = a.io.action_mask[arow];
+  }
 
   for (int t = 0; t < a.T; ++t) {
     const size_t row = (size_t)t * sp.E + e;  // [T,E] row of this env
+    float act[P::ACT_DIM];
+#pragma unroll
+    for (int j = 0; j < P::ACT_DIM; ++j) act[j] = act_next[j];
+    const bool has_action_now = has_next != 0;
+    if (strategic && env_live && t + 1 < a.T) {
+      const size_t arow = (row + sp.E) * S + sidx;
+#pragma unroll
+      for (int j = 0; j < P::ACT_DIM; ++j) act_next[j] = a.io.actions[arow * P::ACT_DIM + j];
+      if (a.io.action_mask) has_next = a.io.action_mask[arow];
+    }
     h.x += 1;                                 // env.py:252
     ctx.step = h.x;
     ctx.episode = (uint32_t)h.y;
     ctx.stage = h.z;
-    const uint32_t done_bits = term | trunc;
-    const bool was_done = strategic && ((done_bits >> sidx) & 1u);
+    const bool was_done = ((term | trunc) & slot_bit) != 0;
     const bool has_ctx = is_agent && !was_done;  // env.py:344-348: no context for done agents
 
     // ---- start-of-step snapshot of every agent's public state (network.py:208-222)
@@ -251,32 +385,24 @@ __global__ void __launch_bounds__(ENGINE_BLOCK) engine_step_kernel(const EngineA
       observing = leaders_turn ? sp.followers : sp.leaders;
       rewarded = acting;
     }
-    int cur = 0;
-    Emit<G, P::SEGCAP, P::PW> out{&ts.q[cur], &sp, slot, 0, 0u};
-    if (has_ctx && ((acting >> slot) & 1u)) {
-      bool has_action = false;
-      const float* act = nullptr;
-      if (strategic) {
-        has_action = a.io.action_mask ? a.io.action_mask[row * S + sidx] != 0 : true;
-        act = a.io.actions + (row * S + sidx) * A;
-      }
-      P::act(ctx, st, has_action, act, out);
-    }
-    ts.q[cur].cnt[slot] = (uint8_t)out.n;
-    ts.q[cur].order[slot] = (uint8_t)slot;
-    if (slot == 0) ts.q[cur].nseg = sp.n_agents;
+    Emit<decltype(ts.qa)> out{&ts.qa, &sp, slot, ctx.out_mask, 0, 0u};
+    if (has_ctx && (acting & slot_bit)) P::act(ctx, st, strategic && has_action_now, act, out);
+    ts.qa.cnt[slot] = (uint8_t)out.n;
+    ts.qa.order[slot] = (uint8_t)slot;
+    if (slot == 0) ts.qa.nseg = sp.n_agents;
     if (out.fault) fault_key = min(fault_key, (0u << 16) | ((uint32_t)slot << 8) | out.fault);
+    int pending = __reduce_add_sync(tmask, out.n);
     __syncwarp(tmask);
 
     int traced = 0;
-    if (TRACK && env_live && slot == 0) {  // pushes of the acting phase, in global push order
+    const bool trace_lane = TRACK && env_live && slot == 0;
+    if (trace_lane) {  // pushes of the acting phase, in global push order
       for (int si = 0; si < sp.n_agents; ++si)
-        for (int k = 0; k < ts.q[cur].cnt[si]; ++k) {
-          const uint32_t hd = ts.q[cur].head[k][si];
+        for (int k = 0; k < ts.qa.cnt[si]; ++k) {
           if (traced < a.trace.cap)
             a.trace.rows[(size_t)e * a.trace.cap + traced] =
-                make_int4((int)hd, ts.q[cur].pay[0][k][si],
-                          P::PW > 1 ? ts.q[cur].pay[P::PW > 1 ? 1 : 0][k][si] : 0, 0);
+                make_int4((int)ts.qa.head[k][si], ts.qa.pay[0][k][si],
+                          P::PW > 1 ? ts.qa.pay[P::PW > 1 ? 1 : 0][k][si] : 0, 0);
           ++traced;
         }
     }
@@ -286,78 +412,20 @@ __global__ void __launch_bounds__(ENGINE_BLOCK) engine_step_kernel(const EngineA
     if (has_ctx) P::pre(ctx, st);
 
     // ---- BatchResolver.resolve (resolvers.py:128-163)
-    for (int round = 0;; ++round) {
-      TileQueue<G, P::SEGCAP, P::PW>& qc = ts.q[cur];
-      TileQueue<G, P::SEGCAP, P::PW>& qn = ts.q[cur ^ 1];
-      int total = 0;
-      const int nseg = qc.nseg;
-      for (int si = 0; si < nseg; ++si) total += qc.cnt[qc.order[si]];
-      if (total == 0) break;
+    for (int round = 0; pending > 0; ++round) {
       if (sp.round_limit >= 0 && round >= sp.round_limit) {  // resolvers.py:160-163
         fault_key = min(fault_key, ((uint32_t)(round + 1) << 16) | (0xFFu << 8) | PHX_FAULT_ROUND_LIMIT);
         break;
       }
-      Emit<G, P::SEGCAP, P::PW> resp{&qn, &sp, slot, 0, 0u};
-      int first = INF, pos = 0;
-      bool bad_type = false;
-      if constexpr (P::BATCHED) {
-        if (has_ctx) P::batch_begin(ctx, st);
-      }
-      for (int si = 0; si < nseg; ++si) {
-        const int seg = qc.order[si];
-        const int c = qc.cnt[seg];
-        for (int k = 0; k < c; ++k, ++pos) {
-          const uint32_t hd = qc.head[k][seg];
-          if ((int)((hd >> 8) & 0xFFu) != slot) continue;
-          if (first == INF) first = pos;  // first-arrival position of this receiver
-          if (!has_ctx) continue;         // done agent: mail dropped (resolvers.py:143-144)
-          const int sender = (int)(hd & 0xFFu);
-          // delivery-time edge filter (resolvers.py:146-148)
-          if (!((sp.adj[sender] >> slot) & 1u)) continue;
-          Msg m;
-          m.sender = sender;
-          m.type = (int)((hd >> 16) & 0xFFu);
-          m.p[0] = qc.pay[0][k][seg];
-          m.p[1] = P::PW > 1 ? qc.pay[P::PW > 1 ? 1 : 0][k][seg] : 0;
-          if (!P::handle(ctx, st, m, resp)) bad_type = true;  // agents.py:140-143
-        }
-      }
-      if constexpr (P::BATCHED) {
-        if (has_ctx && first != INF) P::batch_end(ctx, st, resp);
-      }
-      if (bad_type)
-        fault_key = min(fault_key, ((uint32_t)(round + 1) << 16) | ((uint32_t)slot << 8) |
-                                       PHX_FAULT_UNKNOWN_MSG_TYPE);
-      if (resp.fault)
-        fault_key = min(fault_key, ((uint32_t)(round + 1) << 16) | ((uint32_t)slot << 8) | resp.fault);
-      qn.cnt[slot] = (uint8_t)resp.n;
-      ts.first_idx[slot] = first;
-      __syncwarp(tmask);
-      // next queue's segment order = receivers by first-arrival position
-      int rank = 0, nrecv = 0;
-      for (int j = 0; j < G; ++j) {
-        const int fj = ts.first_idx[j];
-        nrecv += fj != INF;
-        rank += fj < first;
-      }
-      if (first != INF) qn.order[rank] = (uint8_t)slot;
-      if (slot == 0) qn.nseg = nrecv;
-      __syncwarp(tmask);
-      if (TRACK && env_live && slot == 0) {
-        for (int si = 0; si < nrecv; ++si) {
-          const int seg = qn.order[si];
-          for (int k = 0; k < qn.cnt[seg]; ++k) {
-            if (traced < a.trace.cap)
-              a.trace.rows[(size_t)e * a.trace.cap + traced] =
-                  make_int4((int)qn.head[k][seg], qn.pay[0][k][seg],
-                            P::PW > 1 ? qn.pay[P::PW > 1 ? 1 : 0][k][seg] : 0, round + 1);
-            ++traced;
-          }
-        }
-      }
-      cur ^= 1;
+      if (round == 0)
+        pending = engine_round<P, G, TRACK>(a, ctx, st, has_ctx, ts.qa, ts.qr[0], ts.first_idx,
+                                            round, tmask, fault_key, traced, e, trace_lane);
+      else
+        pending = engine_round<P, G, TRACK>(a, ctx, st, has_ctx, ts.qr[(round - 1) & 1],
+                                            ts.qr[round & 1], ts.first_idx, round, tmask,
+                                            fault_key, traced, e, trace_lane);
     }
-    if (TRACK && env_live && slot == 0) a.trace.cnt[e] = traced;
+    if (trace_lane) a.trace.cnt[e] = traced;
 
     // ---- post_message_resolution (env.py:175-178)
     if (has_ctx) P::post(ctx, st);
@@ -369,13 +437,13 @@ __global__ void __launch_bounds__(ENGINE_BLOCK) engine_step_kernel(const EngineA
     float rew_val = 0.f;
     bool t_flag = false, u_flag = false;
     if (strategic && has_ctx) {
-      if ((observing >> slot) & 1u) obs_now = P::encode(ctx, st, obs_val);  // None -> false
+      if (observing & slot_bit) obs_now = P::encode(ctx, st, obs_val);  // None -> false
       if (sp.env_kind == PHX_ENV_BASE) {
         if (obs_now) {  // env.py:281-284: reward only travels with an observation
           rew_val = P::reward(ctx, st);
           rew_now = true;
         }
-      } else if ((rewarded >> slot) & 1u) {
+      } else if (rewarded & slot_bit) {
         rew_val = P::reward(ctx, st);
         rew_now = true;
         rcache = rew_val;
@@ -383,33 +451,31 @@ __global__ void __launch_bounds__(ENGINE_BLOCK) engine_step_kernel(const EngineA
       t_flag = P::terminated(ctx, st);
       u_flag = P::truncated(ctx, st);
     }
-    const uint32_t lane_bit = strategic ? (1u << sidx) : 0u;
-    // tile-wide: newly done agents, cache bookkeeping
-    const uint32_t t_ballot = __ballot_sync(tmask, t_flag);
-    const uint32_t u_ballot = __ballot_sync(tmask, u_flag);
-    const uint32_t o_ballot = __ballot_sync(tmask, obs_now);
-    const uint32_t r_ballot = __ballot_sync(tmask, rew_now);
-    const int tile_shift = G >= 32 ? 0 : ((threadIdx.x & 31) / G * G);
-    // ballots are over lanes (= slots); convert the done ballots to strategic-index masks
-    uint32_t t_new = 0, u_new = 0;
-    {
-      const uint32_t tb_ = (t_ballot >> tile_shift), ub_ = (u_ballot >> tile_shift);
-      for (int j = 0; j < sp.n_agents; ++j) {
-        const int sj = sp.sidx[j];
-        if (sj >= 0) {
-          t_new |= ((tb_ >> j) & 1u) << sj;
-          u_new |= ((ub_ >> j) & 1u) << sj;
-        }
+    // tile-wide masks over slots: newly done agents, who observed, who was rewarded
+    uint32_t t_slots, u_slots, obs_slots, rew_slots;
+    if (G <= 8) {  // one packed reduction instead of four ballots
+      const uint32_t packed = ((uint32_t)t_flag | ((uint32_t)u_flag << 8) | ((uint32_t)obs_now << 16) |
+                               ((uint32_t)rew_now << 24)) << slot;
+      const uint32_t all = __reduce_or_sync(tmask, packed);
+      t_slots = all & 0xFFu; u_slots = (all >> 8) & 0xFFu;
+      obs_slots = (all >> 16) & 0xFFu; rew_slots = all >> 24;
+    } else {
+      t_slots = __ballot_sync(tmask, t_flag) >> tile_shift;
+      u_slots = __ballot_sync(tmask, u_flag) >> tile_shift;
+      obs_slots = __ballot_sync(tmask, obs_now) >> tile_shift;
+      rew_slots = __ballot_sync(tmask, rew_now) >> tile_shift;
+      if (G < 32) {
+        const uint32_t m = (1u << G) - 1u;
+        t_slots &= m; u_slots &= m; obs_slots &= m; rew_slots &= m;
       }
     }
-    term |= t_new;
-    trunc |= u_new;
-    const uint32_t obs_slots = (o_ballot >> tile_shift), rew_slots = (r_ballot >> tile_shift);
+    term |= t_slots;
+    trunc |= u_slots;
     if (cached_env) {
       rnone &= ~rew_slots;  // _rewards.update(rewards)
       if (sp.env_kind == PHX_ENV_FSM) ocached |= obs_slots;
     }
-    const bool all_term = __popc(term) == S;                           // env.py:308-310
+    const bool all_term = __popc(term) == S;                             // env.py:308-310
     const bool all_trunc = (h.x == sp.num_steps) || __popc(trunc) == S;  // env.py:312-318
     const bool terminal = all_term || all_trunc;
     if (sp.env_kind == PHX_ENV_FSM) h.z = next_stage;  // fsm.py:355
@@ -424,12 +490,19 @@ __global__ void __launch_bounds__(ENGINE_BLOCK) engine_step_kernel(const EngineA
         rm = rew_now;
         r_out = rew_val;
       } else if (sp.env_kind == PHX_ENV_FSM) {
-        if (obs_now && a.obs_cache)
-          for (int j = 0; j < O; ++j) a.obs_cache[((size_t)e * G + slot) * O + j] = obs_val[j < P::OBS_DIM ? j : 0];
+        float* oc = a.obs_cache + ((size_t)e * G + slot) * O;
+        if (obs_now) {
+#pragma unroll
+          for (int j = 0; j < P::OBS_DIM; ++j)
+            if (j < O) oc[j] = obs_val[j];
+        }
         if (terminal) {  // fsm.py:360-375: flush the caches
           om = (ocached >> slot) & 1u;
-          if (om && !obs_now)
-            for (int j = 0; j < O; ++j) obs_val[j < P::OBS_DIM ? j : 0] = a.obs_cache[((size_t)e * G + slot) * O + j];
+          if (om && !obs_now) {
+#pragma unroll
+            for (int j = 0; j < P::OBS_DIM; ++j)
+              if (j < O) obs_val[j] = oc[j];
+          }
           rm = ((rnone >> slot) & 1u) ? 2 : 1;
           r_out = rcache;
         } else {  // fsm.py:378: last computed reward of every agent observing now
@@ -449,8 +522,11 @@ __global__ void __launch_bounds__(ENGINE_BLOCK) engine_step_kernel(const EngineA
           r_out = rcache;
         }
       }
-      if (a.io.obs && om)
-        for (int j = 0; j < O; ++j) a.io.obs[orow * O + j] = obs_val[j < P::OBS_DIM ? j : 0];
+      if (a.io.obs && om) {
+#pragma unroll
+        for (int j = 0; j < P::OBS_DIM; ++j)
+          if (j < O) a.io.obs[orow * O + j] = obs_val[j];
+      }
       if (a.io.obs_mask) a.io.obs_mask[orow] = om;
       if (a.io.reward) a.io.reward[orow] = rm == 1 ? r_out : 0.f;
       if (a.io.reward_mask) a.io.reward_mask[orow] = rm;
@@ -459,7 +535,6 @@ __global__ void __launch_bounds__(ENGINE_BLOCK) engine_step_kernel(const EngineA
     }
     if (env_live && slot == 0 && a.io.all_done)
       reinterpret_cast<uchar2*>(a.io.all_done)[row] = make_uchar2(all_term, all_trunc);
-    (void)lane_bit;
 
     // ---- PHX_FLAG_AUTO_RESET: the step that ends the episode also resets the env
     if ((sp.flags & PHX_FLAG_AUTO_RESET) && terminal) {
@@ -467,11 +542,11 @@ __global__ void __launch_bounds__(ENGINE_BLOCK) engine_step_kernel(const EngineA
       h.y += 1;
       h.z = sp.initial_stage;
       term = trunc = 0;
-      if (is_agent) P::reset_agent(ctx, st);
-      rnone = cached_env ? sp.strategic_mask : 0u;
       ctx.step = 0;
       ctx.episode = (uint32_t)h.y;
       ctx.stage = h.z;
+      if (is_agent) P::reset_agent(ctx, st);
+      rnone = cached_env ? sp.strategic_mask : 0u;
       if (P::VW > 0) {
         if (is_agent) P::view(ctx, st, &ts.views[slot][0]);
         __syncwarp(tmask);
@@ -482,9 +557,12 @@ __global__ void __launch_bounds__(ENGINE_BLOCK) engine_step_kernel(const EngineA
       if (strategic && env_live) {
         const size_t orow = row * S + sidx;
         bool got = false;
-        if ((first_obs >> slot) & 1u) got = P::encode(ctx, st, obs_val);
-        if (a.io.obs && got)
-          for (int j = 0; j < O; ++j) a.io.obs[orow * O + j] = obs_val[j < P::OBS_DIM ? j : 0];
+        if (first_obs & slot_bit) got = P::encode(ctx, st, obs_val);
+        if (a.io.obs && got) {
+#pragma unroll
+          for (int j = 0; j < P::OBS_DIM; ++j)
+            if (j < O) a.io.obs[orow * O + j] = obs_val[j];
+        }
         if (a.io.obs_mask) a.io.obs_mask[orow] = got;
       }
     }
@@ -506,8 +584,7 @@ __global__ void __launch_bounds__(ENGINE_BLOCK) engine_step_kernel(const EngineA
     if (cached_env) a.reward_cache[(size_t)e * G + slot] = rcache;
   }
   // first fault of the env in event order (phase, then agent order)
-  uint32_t fk = fault_key;
-  for (int off = G / 2; off > 0; off >>= 1) fk = min(fk, __shfl_xor_sync(tmask, fk, off, G));
+  const uint32_t fk = __reduce_min_sync(tmask, fault_key);
   if (env_live && slot == 0 && fk != 0xFFFFFFFFu) raise_fault(a.faults, e, fk & 0xFFu);
 }
 
@@ -518,7 +595,7 @@ engine_reset_kernel(const EngineArgs<P> a, const uint8_t* env_mask, float* obs, 
                     bool agents_only) {
   constexpr int TPB = ENGINE_BLOCK / G;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  TileSmem<P, G>* tiles = reinterpret_cast<TileSmem<P, G>*>(smem_raw);
+  BlockSmem<P, G>& bs = *reinterpret_cast<BlockSmem<P, G>*>(smem_raw);
   const EngineSpec& sp = a.spec;
   const int tb = threadIdx.x / G, slot = threadIdx.x % G;
   const int env = blockIdx.x * TPB + tb;
@@ -526,7 +603,12 @@ engine_reset_kernel(const EngineArgs<P> a, const uint8_t* env_mask, float* obs, 
   const bool env_live = env < sp.E && (env_mask == nullptr || env_mask[env < sp.E ? env : 0] != 0);
   const int e = env < sp.E ? env : sp.E - 1;
   const bool is_agent = slot < sp.n_agents;
-  TileSmem<P, G>& ts = tiles[tb];
+  TileSmem<P, G>& ts = bs.tiles[tb];
+  if (threadIdx.x < ENGINE_MAX_AGENTS) {
+    bs.kind_tab[threadIdx.x] = sp.kind[threadIdx.x];
+    bs.ip0_tab[threadIdx.x] = sp.agent_iparam[threadIdx.x][0];
+  }
+  __syncthreads();
   int4 h = a.hdr[e];
   int st[P::NWORDS > 0 ? P::NWORDS : 1];
 #pragma unroll
@@ -544,6 +626,10 @@ engine_reset_kernel(const EngineArgs<P> a, const uint8_t* env_mask, float* obs, 
   ctx.episode = (uint32_t)h.y;
   ctx.views = &ts.views[0][0];
   ctx.view_stride = P::VW > 0 ? P::VW : 1;
+  ctx.kind_tab = bs.kind_tab;
+  ctx.ip0_tab = bs.ip0_tab;
+  ctx.out_mask = is_agent ? sp.adj[slot] : 0u;
+  ctx.in_mask = 0;
   if (is_agent) P::reset_agent(ctx, st);  // Network.reset -> agent.reset() (network.py:179-184)
   if (agents_only) {  // PhantomEnv.__init__ ends with agent.reset() only (env.py:122-124)
     if (env_live) {
@@ -568,8 +654,11 @@ engine_reset_kernel(const EngineArgs<P> a, const uint8_t* env_mask, float* obs, 
       bool got = false;
       if ((first_obs >> slot) & 1u) got = P::encode(ctx, st, obs_val);
       const size_t orow = (size_t)e * sp.n_strategic + sidx;
-      if (obs && got)
-        for (int j = 0; j < sp.obs_dim; ++j) obs[orow * sp.obs_dim + j] = obs_val[j < P::OBS_DIM ? j : 0];
+      if (obs && got) {
+#pragma unroll
+        for (int j = 0; j < P::OBS_DIM; ++j)
+          if (j < sp.obs_dim) obs[orow * sp.obs_dim + j] = obs_val[j];
+      }
       if (obs_mask) obs_mask[orow] = got;
     }
     if (slot == 0) {

@@ -32,6 +32,7 @@ inline int32_t make_engine_spec(const phx_spec& s, int32_t E, uint64_t seed, int
     d.sidx[i] = (int8_t)s.strategic_index[i];
     d.adj[i] = s.adjacency[i][0];
     if (s.strategic_index[i] >= 0) d.strategic_mask |= 1u << i;
+    if (s.agent_kind[i] >= 0 && s.agent_kind[i] < 8) d.kind_mask[s.agent_kind[i]] |= 1u << i;
     for (int k = 0; k < 4; ++k) d.agent_iparam[i][k] = s.agent_iparam[i][k];
     for (int k = 0; k < 2; ++k) d.agent_fparam[i][k] = (float)s.agent_fparam[i][k];
     for (int k = 0; k < PHX_MAX_CODEC_OPS; ++k) {
@@ -137,7 +138,7 @@ class EngineFamily : public Family {
   template <int GG>
   int32_t launch_step(const EngineArgs<P>& a, cudaStream_t stream) {
     constexpr int TPB = ENGINE_BLOCK / GG;
-    const size_t smem = sizeof(TileSmem<P, GG>) * TPB;
+    const size_t smem = sizeof(BlockSmem<P, GG>);
     const int grid = (E + TPB - 1) / TPB;
     if (tracking()) {
       PHX_CUDA(cudaFuncSetAttribute(engine_step_kernel<P, GG, true>,
@@ -156,7 +157,7 @@ class EngineFamily : public Family {
   int32_t launch_reset_g(const EngineArgs<P>& a, const uint8_t* env_mask, float* obs,
                          uint8_t* obs_mask, cudaStream_t stream, bool agents_only) {
     constexpr int TPB = ENGINE_BLOCK / GG;
-    const size_t smem = sizeof(TileSmem<P, GG>) * TPB;
+    const size_t smem = sizeof(BlockSmem<P, GG>);
     PHX_CUDA(cudaFuncSetAttribute(engine_reset_kernel<P, GG>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     engine_reset_kernel<P, GG><<<(E + TPB - 1) / TPB, ENGINE_BLOCK, smem, stream>>>(
