@@ -81,9 +81,10 @@ typedef enum phx_family {
 
 typedef enum phx_exec_mode {
   PHX_EXEC_AUTO = 0,   /* fastest kernel that is valid for the spec                   */
-  PHX_EXEC_QUEUE = 1,  /* force the generic message-queue engine (any topology)       */
-  PHX_EXEC_FAST = 2    /* force the schedule-specialised kernel; create fails if the
+  PHX_EXEC_QUEUE = 1,  /* force the generic engine with a tile of lanes per env       */
+  PHX_EXEC_FAST = 2,   /* force the schedule-specialised kernel; create fails if the
                           spec is outside its domain                                  */
+  PHX_EXEC_THREAD = 3  /* force the generic engine with one thread per env (<= 8 agents) */
 } phx_exec_mode;
 
 enum {

@@ -31,8 +31,8 @@ ENV_BASE, ENV_FSM, ENV_STACKELBERG = 0, 1, 2
 # phx_family
 FAMILY_SUPPLY_CHAIN, FAMILY_MOCK, FAMILY_MARKET, FAMILY_STACKELBERG, FAMILY_DENSE = 1, 2, 3, 4, 5
 # phx_exec_mode
-EXEC_AUTO, EXEC_QUEUE, EXEC_FAST = 0, 1, 2
-EXEC_MODES = {"auto": EXEC_AUTO, "queue": EXEC_QUEUE, "fast": EXEC_FAST}
+EXEC_AUTO, EXEC_QUEUE, EXEC_FAST, EXEC_THREAD = 0, 1, 2, 3
+EXEC_MODES = {"auto": EXEC_AUTO, "queue": EXEC_QUEUE, "fast": EXEC_FAST, "thread": EXEC_THREAD}
 # flags
 FLAG_IGNORE_CONNECTION_ERRORS, FLAG_NO_PAYLOAD_CHECKS, FLAG_TRACK_MESSAGES, FLAG_AUTO_RESET = 1, 2, 4, 8
 # phx_field

@@ -27,7 +27,7 @@ struct MarketProgram {
   // a maker quotes up to 24 takers and the clearing agent settles with 31 agents in the acting
   // phase; no handler of this market ever answers a message
   static constexpr int PW = 2, NWORDS = 8, VW = 1, ACTCAP = 32, RESPCAP = 1, OBS_DIM = 3,
-                       ACT_DIM = 1;
+                       ACT_DIM = 1, Q1CAP = 0;  // 32 agents: tile engine only
   static constexpr bool BATCHED = false;
 
   static int32_t validate(const phx_spec& s) {

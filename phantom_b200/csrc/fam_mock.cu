@@ -30,7 +30,7 @@ enum { MK_TEST_MESSAGE = 0, MK_REQUEST = 1, MK_RESPONSE = 2 };
 
 struct MockProgram {
   static constexpr int PW = 1, NWORDS = 5, VW = 0, ACTCAP = 32, RESPCAP = 32, OBS_DIM = 8,
-                       ACT_DIM = 1;
+                       ACT_DIM = 1, Q1CAP = 32;
   static constexpr bool BATCHED = false;
 
   static int32_t validate(const phx_spec& s) {

@@ -19,7 +19,7 @@ constexpr int SK_STREAM_VALUE = 2;
 
 struct StackelbergProgram {
   static constexpr int PW = 1, NWORDS = 4, VW = 0, ACTCAP = 8, RESPCAP = 8, OBS_DIM = 2,
-                       ACT_DIM = 1;
+                       ACT_DIM = 1, Q1CAP = 8;
   static constexpr bool BATCHED = false;
 
   static int32_t validate(const phx_spec& s) {

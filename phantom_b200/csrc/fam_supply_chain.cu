@@ -613,6 +613,7 @@ struct ScProgram {
   static constexpr int PW = 1, NWORDS = 4, VW = 0, ACTCAP = 1, RESPCAP = SEGCAP_, OBS_DIM = 3,
                        ACT_DIM = 1;
   static constexpr int SEGCAP = SEGCAP_;
+  static constexpr int Q1CAP = SEGCAP_;  // thread-per-env engine: messages in flight per round
   static constexpr bool BATCHED = false;
 
   static int32_t validate(const phx_spec& s) {

@@ -5,6 +5,7 @@
 #include <string>
 
 #include "phx_engine.cuh"
+#include "phx_engine1.cuh"
 #include "phx_family.h"
 
 namespace phx {
@@ -91,6 +92,12 @@ class EngineFamily : public Family {
     rc = P::validate(s);
     if (rc != PHX_OK) return rc;
     G = s.n_agents <= 8 ? 8 : (s.n_agents <= 16 ? 16 : 32);
+    // thread-per-env variant: <= 8 agents and a program that declares its queue bound
+    const bool eligible = P::Q1CAP > 0 && P::VW <= 1 && s.n_agents <= ENGINE1_SLOTS;
+    PHX_REQUIRE(s.exec_mode != PHX_EXEC_THREAD || eligible, PHX_ERR_UNSUPPORTED,
+                "PHX_EXEC_THREAD needs an env class with at most 8 agents whose device program "
+                "supports the thread-per-env engine");
+    thread_per_env = s.exec_mode == PHX_EXEC_THREAD || (s.exec_mode == PHX_EXEC_AUTO && eligible);
     PHX_REQUIRE(s.obs_dim <= P::OBS_DIM, PHX_ERR_INVALID, "obs_dim exceeds the family's OBS_DIM");
     const size_t n = (size_t)E * G;
     PHX_CUDA(cudaMalloc(&d_state, sizeof(int32_t) * n * (P::NWORDS > 0 ? P::NWORDS : 1)));
@@ -113,7 +120,8 @@ class EngineFamily : public Family {
     rc = launch_reset(nullptr, nullptr, nullptr, 0, /*count_episode=*/false);
     if (rc != PHX_OK) return rc;
     PHX_CUDA(cudaDeviceSynchronize());
-    name = std::string("queue(G=") + std::to_string(G) + ")";
+    name = thread_per_env ? std::string("thread-per-env(G=8)")
+                          : std::string("queue(G=") + std::to_string(G) + ")";
     return PHX_OK;
   }
 
@@ -185,6 +193,23 @@ class EngineFamily : public Family {
     PHX_REQUIRE(!tracking() || T == 1, PHX_ERR_INVALID,
                 "message tracking records one step: use phx_step (T == 1)");
     EngineArgs<P> a = make_args(T, io);
+    if constexpr (P::Q1CAP > 0 && P::VW <= 1) {
+      if (thread_per_env) {
+        const size_t smem = sizeof(Engine1Smem<P>);
+        const int grid = (E + ENGINE1_BLOCK - 1) / ENGINE1_BLOCK;
+        if (tracking()) {
+          PHX_CUDA(cudaFuncSetAttribute(engine1_step_kernel<P, true>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          engine1_step_kernel<P, true><<<grid, ENGINE1_BLOCK, smem, stream>>>(a);
+        } else {
+          PHX_CUDA(cudaFuncSetAttribute(engine1_step_kernel<P, false>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          engine1_step_kernel<P, false><<<grid, ENGINE1_BLOCK, smem, stream>>>(a);
+        }
+        PHX_CUDA(cudaGetLastError());
+        return PHX_OK;
+      }
+    }
     return G == 8 ? launch_step<8>(a, stream)
            : G == 16 ? launch_step<16>(a, stream)
                      : launch_step<32>(a, stream);
@@ -205,6 +230,7 @@ class EngineFamily : public Family {
 
   EngineSpec espec{};
   int G = 8;
+  bool thread_per_env = false;
   int32_t* d_state = nullptr;
   float* d_rcache = nullptr;
   uint32_t* d_rnone = nullptr;

@@ -61,6 +61,10 @@ def _fault_exception(code: int, env_index: int) -> Exception:
 
 
 class PhantomEnv:
+    # kernel variant used when an env does not ask for one: "auto" (fastest valid), "fast",
+    # "thread" (generic engine, thread per env), "queue" (generic engine, tile per env)
+    default_exec_mode = "auto"
+
     class Step(NamedTuple):
         observations: Dict[AgentID, Any]
         rewards: Dict[AgentID, float]
@@ -71,7 +75,7 @@ class PhantomEnv:
     def __init__(self, num_steps: int, network: Optional[Network] = None,
                  env_supertype=None, agent_supertypes=None, *, num_envs: int = 1,
                  device: int = 0, seed: int = 0, env_offset: int = 0,
-                 exec_mode: str = "auto", auto_reset: bool = False) -> None:
+                 exec_mode: Optional[str] = None, auto_reset: bool = False) -> None:
         if env_supertype is not None or agent_supertypes is not None:
             raise NotLowerableError(
                 "Supertype / Sampler per-env parameterisation is not lowered to the device "
@@ -84,7 +88,7 @@ class PhantomEnv:
         self.device = int(device)
         self.seed = int(seed)
         self.env_offset = int(env_offset)
-        self.exec_mode = exec_mode
+        self.exec_mode = exec_mode or PhantomEnv.default_exec_mode
         self.auto_reset = bool(auto_reset)
         self._handle: Optional[C.c_void_p] = None
         self._spec: Optional[L.PhxSpec] = None
@@ -325,14 +329,14 @@ class PhantomEnv:
     def agent_column(self, agent: Agent, word: int, dtype=np.int32) -> np.ndarray:
         """State word `word` of `agent` for every env: array [E]."""
         info = self.family
-        if info.fast_column is not None and not self.exec_name.startswith("queue"):
+        if info.fast_column is not None and self.exec_name.startswith("fast"):
             return info.fast_column(self, agent, word)
         col = self.field(L.FIELD_FAMILY + word, np.int32, width=self.tile_width)
         return col[:, agent._phx_slot].view(dtype)
 
     def set_agent_column(self, agent: Agent, word: int, value) -> None:
         info = self.family
-        if info.fast_column is not None and not self.exec_name.startswith("queue"):
+        if info.fast_column is not None and self.exec_name.startswith("fast"):
             info.fast_column(self, agent, word, value)
             return
         col = self.field(L.FIELD_FAMILY + word, np.int32, width=self.tile_width)

@@ -24,11 +24,15 @@ def K():
     return ns
 
 
+@pytest.mark.parametrize("exec_mode", ["thread", "queue"])
 @pytest.mark.parametrize("scenario", kats.ALL, ids=lambda f: f.__name__)
-def test_kat_on_device(K, scenario):
+def test_kat_on_device(K, scenario, exec_mode, monkeypatch):
+    """Every KAT on both variants of the generic engine: one thread per env, and a tile of
+    lanes per env."""
+    monkeypatch.setattr(K.ph.PhantomEnv, "default_exec_mode", exec_mode)
     env = scenario(K)
     if env is not None:
-        assert env.exec_name.startswith("queue")
+        assert env.exec_name.startswith("thread-per-env" if exec_mode == "thread" else "queue(G=")
         env.close()
 
 

@@ -61,7 +61,7 @@ def test_native_library_is_loaded(ph):
     assert os.path.basename(_lib.LIB_PATH) == "libphx.so"
 
 
-@pytest.mark.parametrize("exec_mode", ["fast", "queue"])
+@pytest.mark.parametrize("exec_mode", ["fast", "thread", "queue"])
 def test_single_step_api_matches_reference_golden(sc, golden, exec_mode):
     g = golden
     seed, A, M = int(g["seed"]), g["actions"], g["action_mask"]
@@ -80,7 +80,7 @@ def test_single_step_api_matches_reference_golden(sc, golden, exec_mode):
     env.close()
 
 
-@pytest.mark.parametrize("exec_mode", ["fast", "queue"])
+@pytest.mark.parametrize("exec_mode", ["fast", "thread", "queue"])
 def test_message_trace_matches_reference_tracked_messages(sc, golden, exec_mode):
     """Bit-exact routing: the device trace equals Resolver.tracked_messages of the reference
     (global push order over both rounds) for every step of 3 envs x 2 episodes."""
@@ -102,7 +102,7 @@ def test_message_trace_matches_reference_tracked_messages(sc, golden, exec_mode)
     env.close()
 
 
-@pytest.mark.parametrize("exec_mode", ["fast", "queue"])
+@pytest.mark.parametrize("exec_mode", ["fast", "thread", "queue"])
 def test_rollout_equals_single_steps(sc, exec_mode):
     E, T, seed = 1000, 37, 5
     r = np.random.RandomState(0)
@@ -370,13 +370,16 @@ def test_queue_engine_equals_fast_kernel_full_episode(sc):
     M = (np.random.RandomState(6).uniform(size=(T, E, 1)) > 0.1).astype(np.uint8)
     f = sc.SupplyChainEnv(num_envs=E, seed=seed, exec_mode="fast")
     q = sc.SupplyChainEnv(num_envs=E, seed=seed, exec_mode="queue")
-    assert f.exec_name.startswith("fast") and q.exec_name.startswith("queue")
-    f.reset_batch(); q.reset_batch()
-    a, b = f.rollout_batch(A, M), q.rollout_batch(A, M)
-    for x, y in zip(a, b):
-        assert torch.equal(x, y)
+    th = sc.SupplyChainEnv(num_envs=E, seed=seed, exec_mode="thread")
+    assert f.exec_name.startswith("fast") and q.exec_name.startswith("queue(G=8")
+    assert th.exec_name.startswith("thread-per-env")
+    f.reset_batch(); q.reset_batch(); th.reset_batch()
+    a, b, c = f.rollout_batch(A, M), q.rollout_batch(A, M), th.rollout_batch(A, M)
+    for x, y, z in zip(a, b, c):
+        assert torch.equal(x, y) and torch.equal(x, z)
     assert np.array_equal(shop_state(f), shop_state(q))
-    f.close(); q.close()
+    assert np.array_equal(shop_state(f), shop_state(th))
+    f.close(); q.close(); th.close()
 
 
 def test_queue_engine_any_agent_order(sc, ph):
@@ -400,7 +403,7 @@ def test_queue_engine_any_agent_order(sc, ph):
         return None
 
     env = build(ph, sc)
-    assert env.exec_name.startswith("queue")
+    assert env.exec_name.startswith("thread-per-env")
     # oracle twin with the same order
     st = rng.StepStream(seed, 0, 0)
     ref_full = wl.build(po, st, n_customers=3, num_steps=20, enable_tracking=True)
