@@ -20,8 +20,9 @@ constexpr int SK_STREAM_VALUE = 2;
 struct StackelbergProgram {
   static constexpr int PW = 1, NWORDS = 4, VW = 0, ACTCAP = 8, RESPCAP = 8, OBS_DIM = 2,
                        ACT_DIM = 1, Q1CAP = 8;
-  static constexpr bool BATCHED = false;
+  static constexpr bool BATCHED = false, HAS_PRE = true, HAS_POST = false;
 
+  static int q1_cap(const phx_spec& s) { return s.n_agents - 1; }  // one message per follower
   static int32_t validate(const phx_spec& s) {
     PHX_REQUIRE(s.env_kind == PHX_ENV_STACKELBERG, PHX_ERR_UNSUPPORTED,
                 "stackelberg family runs under StackelbergEnv only");

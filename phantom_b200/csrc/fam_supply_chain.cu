@@ -614,8 +614,9 @@ struct ScProgram {
                        ACT_DIM = 1;
   static constexpr int SEGCAP = SEGCAP_;
   static constexpr int Q1CAP = SEGCAP_;  // thread-per-env engine: messages in flight per round
-  static constexpr bool BATCHED = false;
+  static constexpr bool BATCHED = false, HAS_PRE = true, HAS_POST = false;
 
+  static int q1_cap(const phx_spec& s) { return s.n_agents; }  // <= one message per agent and round
   static int32_t validate(const phx_spec& s) {
     PHX_REQUIRE(s.env_kind == PHX_ENV_BASE, PHX_ERR_UNSUPPORTED,
                 "supply-chain family runs under PhantomEnv (PHX_ENV_BASE) only");

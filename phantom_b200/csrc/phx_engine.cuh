@@ -156,6 +156,7 @@ template <class P>
 struct EngineArgs {
   EngineSpec spec;
   int32_t T;
+  int32_t qcap;         // thread-per-env engine: queue bound of this env class
   int4* hdr;            // [E] step, episode, stage, -
   uint32_t* term;       // [E] PhantomEnv._terminations as a bitmask over agent slots
   uint32_t* trunc;      // [E]

@@ -10,8 +10,9 @@
 // and each handles its batch in push order -- so no ordering machinery is needed at all.
 //
 // Per-thread working set in shared memory (word-major, thread-minor: conflict free):
-//   agent state   [NWORDS][8][threads]      views [VW][8][threads]
-//   two queues    [Q1CAP][1 + PW][threads]  (current round / next round)
+//   agent state [NWORDS][n][threads], views [n][threads], reward cache [n][threads],
+//   action ring [2][S][A][threads] (cp.async, one step ahead), two queues [qcap][1+PW][threads]
+// sized at launch from the env class actually lowered (Engine1Layout).
 #pragma once
 #include "phx_engine.cuh"
 
@@ -20,26 +21,48 @@ namespace phx {
 constexpr int ENGINE1_BLOCK = 128;
 constexpr int ENGINE1_SLOTS = 8;  // == the G of the HBM state layout [NWORDS][E][8]
 
-template <class P>
-struct Engine1Smem {
-  int32_t state[P::NWORDS > 0 ? P::NWORDS : 1][ENGINE1_SLOTS][ENGINE1_BLOCK];
-  int32_t views[P::VW > 0 ? P::VW : 1][ENGINE1_SLOTS][ENGINE1_BLOCK];
-  uint32_t qhead[2][P::Q1CAP][ENGINE1_BLOCK];
-  int32_t qpay[2][P::Q1CAP][P::PW][ENGINE1_BLOCK];
-  int8_t kind_tab[ENGINE_MAX_AGENTS];
-  int32_t ip0_tab[ENGINE_MAX_AGENTS];
+// Runtime-sized shared-memory layout (word index = (row * ENGINE1_BLOCK + tid)): sized by the
+// env class actually lowered (n agents, S strategic, queue bound), not by the family maximum,
+// so that small env classes keep enough blocks resident to run in a single wave.
+struct Engine1Layout {
+  int n, S, qcap;
+  int off_state, off_views, off_rcache, off_act, off_qhead, off_qpay, off_tables, words;
 };
+
+template <class P>
+__host__ __device__ inline Engine1Layout engine1_layout(int n_agents, int n_strategic, int qcap,
+                                                        bool cached_env) {
+  Engine1Layout L;
+  L.n = n_agents; L.S = n_strategic > 0 ? n_strategic : 1; L.qcap = qcap;
+  int rows = 0;
+  L.off_state = rows; rows += P::NWORDS * n_agents;
+  L.off_views = rows; rows += P::VW > 0 ? n_agents : 0;
+  L.off_rcache = rows; rows += cached_env ? n_agents : 0;
+  L.off_act = rows; rows += 2 * L.S * P::ACT_DIM;
+  L.off_qhead = rows; rows += 2 * qcap;
+  L.off_qpay = rows; rows += 2 * qcap * P::PW;
+  L.off_tables = rows * ENGINE1_BLOCK;           // kind_tab / ip0_tab / in_tab, 32 words each
+  L.words = L.off_tables + 3 * ENGINE_MAX_AGENTS;
+  return L;
+}
 
 // Emission cursor of one env: appends to the queue in program order (== global push order).
 template <class P>
 struct Emit1 {
-  Engine1Smem<P>* sm;
+  int32_t* sm;
   const EngineSpec* spec;
+  Engine1Layout L;
   int which, tid;
   int slot;
   uint32_t out_mask;
   int n;
   uint32_t fault;
+  __device__ __forceinline__ int32_t& head(int w, int i) const {
+    return sm[(L.off_qhead + w * L.qcap + i) * ENGINE1_BLOCK + tid];
+  }
+  __device__ __forceinline__ int32_t& pay(int w, int i, int k) const {
+    return sm[(L.off_qpay + (w * L.qcap + i) * P::PW + k) * ENGINE1_BLOCK + tid];
+  }
   __device__ __forceinline__ void send(int recv, int type, int p0, int p1 = 0) {
     if (fault) return;
     if (!(spec->flags & PHX_FLAG_IGNORE_CONNECTION_ERRORS) && !((out_mask >> recv) & 1u)) {
@@ -52,13 +75,13 @@ struct Emit1 {
         return;
       }
     }
-    if (n >= P::Q1CAP) {
+    if (n >= L.qcap) {
       fault = PHX_FAULT_QUEUE_OVERFLOW;
       return;
     }
-    sm->qhead[which][n][tid] = (uint32_t)slot | ((uint32_t)recv << 8) | ((uint32_t)type << 16);
-    sm->qpay[which][n][0][tid] = p0;
-    if (P::PW > 1) sm->qpay[which][n][P::PW > 1 ? 1 : 0][tid] = p1;
+    head(which, n) = (int32_t)((uint32_t)slot | ((uint32_t)recv << 8) | ((uint32_t)type << 16));
+    pay(which, n, 0) = p0;
+    if (P::PW > 1) pay(which, n, P::PW > 1 ? 1 : 0) = p1;
     ++n;
   }
 };
@@ -67,17 +90,37 @@ template <class P, bool TRACK>
 __global__ void __launch_bounds__(ENGINE1_BLOCK) engine1_step_kernel(const EngineArgs<P> a) {
   static_assert(P::VW <= 1, "thread-per-env engine: views of at most one word per agent");
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  Engine1Smem<P>& sm = *reinterpret_cast<Engine1Smem<P>*>(smem_raw);
+  int32_t* sm = reinterpret_cast<int32_t*>(smem_raw);
   const EngineSpec& sp = a.spec;
   const int tid = threadIdx.x;
+  const Engine1Layout L = engine1_layout<P>(sp.n_agents, sp.n_strategic, a.qcap,
+                                            sp.env_kind != PHX_ENV_BASE);
+  int8_t* kind_tab = reinterpret_cast<int8_t*>(sm + L.off_tables);
+  int32_t* ip0_tab = sm + L.off_tables + ENGINE_MAX_AGENTS;
+  uint32_t* in_tab = reinterpret_cast<uint32_t*>(sm + L.off_tables + 2 * ENGINE_MAX_AGENTS);
+  auto ST = [&](int w, int slot) -> int32_t& { return sm[(L.off_state + w * L.n + slot) * ENGINE1_BLOCK + tid]; };
+  auto VIEW = [&](int slot) -> int32_t& { return sm[(L.off_views + slot) * ENGINE1_BLOCK + tid]; };
+  auto RC = [&](int slot) -> float& {
+    return reinterpret_cast<float*>(sm)[(L.off_rcache + slot) * ENGINE1_BLOCK + tid];
+  };
+  auto ACT = [&](int buf, int k, int j) -> float& {
+    return reinterpret_cast<float*>(sm)[(L.off_act + (buf * L.S + k) * P::ACT_DIM + j) * ENGINE1_BLOCK + tid];
+  };
+  auto QH = [&](int w, int i) -> int32_t& { return sm[(L.off_qhead + w * L.qcap + i) * ENGINE1_BLOCK + tid]; };
+  auto QP = [&](int w, int i, int k) -> int32_t& {
+    return sm[(L.off_qpay + (w * L.qcap + i) * P::PW + k) * ENGINE1_BLOCK + tid];
+  };
   const int env = blockIdx.x * ENGINE1_BLOCK + tid;
   const bool env_live = env < sp.E;
   const int e = env_live ? env : sp.E - 1;
   const int n = sp.n_agents, S = sp.n_strategic, O = sp.obs_dim;
 
   if (tid < ENGINE_MAX_AGENTS) {
-    sm.kind_tab[tid] = sp.kind[tid];
-    sm.ip0_tab[tid] = sp.agent_iparam[tid][0];
+    kind_tab[tid] = sp.kind[tid];
+    ip0_tab[tid] = sp.agent_iparam[tid][0];
+    uint32_t in = 0;
+    for (int s = 0; s < n; ++s) in |= ((sp.adj[s] >> tid) & 1u) << s;
+    in_tab[tid] = in;
   }
   // ---- load env header, done sets, agent state (once per launch)
   int4 h = a.hdr[e];
@@ -86,43 +129,59 @@ __global__ void __launch_bounds__(ENGINE1_BLOCK) engine1_step_kernel(const Engin
   for (int w = 0; w < P::NWORDS; ++w) {
     const int4* src = reinterpret_cast<const int4*>(a.state + ((size_t)w * sp.E + e) * ENGINE1_SLOTS);
     const int4 lo = src[0], hi = src[1];
-    sm.state[w][0][tid] = lo.x; sm.state[w][1][tid] = lo.y; sm.state[w][2][tid] = lo.z; sm.state[w][3][tid] = lo.w;
-    sm.state[w][4][tid] = hi.x; sm.state[w][5][tid] = hi.y; sm.state[w][6][tid] = hi.z; sm.state[w][7][tid] = hi.w;
+    const int v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (k < n) ST(w, k) = v[k];
   }
   const bool cached_env = sp.env_kind != PHX_ENV_BASE;
   uint32_t rnone = 0, ocached = 0;
   if (cached_env) {
     rnone = a.reward_none[e];
     if (sp.env_kind == PHX_ENV_FSM) ocached = a.obs_cached[e];
+    const float4* rc = reinterpret_cast<const float4*>(a.reward_cache + (size_t)e * ENGINE1_SLOTS);
+    const float4 lo = rc[0], hi = rc[1];
+    const float v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (k < n) RC(k) = v[k];
   }
+  // actions of step t+1 are fetched with cp.async while step t runs
+  auto prefetch_actions = [&](int t_next) {
+    if (t_next < a.T) {
+      const float* src = a.io.actions + ((size_t)t_next * sp.E + e) * S * P::ACT_DIM;
+      for (int k = 0; k < S; ++k)
+#pragma unroll
+        for (int j = 0; j < P::ACT_DIM; ++j)
+          cp_async4(&ACT(t_next & 1, k, j), src + k * P::ACT_DIM + j);
+    }
+    cp_async_commit();
+  };
+  prefetch_actions(0);
   __syncthreads();
   uint32_t fault = 0;  // first fault in event order: events ARE sequential here
 
   Ctx ctx;
   ctx.spec = &sp;
   ctx.env_id = sp.env_offset + (uint32_t)e;
-  ctx.views = &sm.views[0][0][tid];
+  ctx.views = &VIEW(0);
   ctx.view_stride = ENGINE1_BLOCK;  // view word 0 of slot s at views[0][s][tid]
-  ctx.kind_tab = sm.kind_tab;
-  ctx.ip0_tab = sm.ip0_tab;
+  ctx.kind_tab = kind_tab;
+  ctx.ip0_tab = ip0_tab;
 
   auto bind = [&](int slot) {
     ctx.slot = slot;
     ctx.kind = sp.kind[slot];
     ctx.out_mask = sp.adj[slot];
   };
-  auto in_mask_of = [&](int slot) {
-    uint32_t in = 0;
-    for (int s = 0; s < n; ++s) in |= ((sp.adj[s] >> slot) & 1u) << s;
-    return in;
-  };
+  auto in_mask_of = [&](int slot) { return in_tab[slot]; };
   auto load_state = [&](int slot, int* st) {
 #pragma unroll
-    for (int w = 0; w < P::NWORDS; ++w) st[w] = sm.state[w][slot][tid];
+    for (int w = 0; w < P::NWORDS; ++w) st[w] = ST(w, slot);
   };
   auto store_state = [&](int slot, const int* st) {
 #pragma unroll
-    for (int w = 0; w < P::NWORDS; ++w) sm.state[w][slot][tid] = st[w];
+    for (int w = 0; w < P::NWORDS; ++w) ST(w, slot) = st[w];
   };
 
   for (int t = 0; t < a.T; ++t) {
@@ -133,6 +192,7 @@ __global__ void __launch_bounds__(ENGINE1_BLOCK) engine1_step_kernel(const Engin
     ctx.stage = h.z;
     const uint32_t done = term | trunc;  // agents without a context this step (env.py:344-348)
     int st[P::NWORDS > 0 ? P::NWORDS : 1];
+    prefetch_actions(t + 1);
 
     // ---- start-of-step snapshot of every agent's public state (network.py:208-222)
     if (P::VW > 0) {
@@ -142,7 +202,7 @@ __global__ void __launch_bounds__(ENGINE1_BLOCK) engine1_step_kernel(const Engin
         int v[P::VW > 0 ? P::VW : 1];
         P::view(ctx, st, v);
 #pragma unroll
-        for (int w = 0; w < P::VW; ++w) sm.views[w][s][tid] = v[w];
+        for (int w = 0; w < P::VW; ++w) VIEW(s) = v[w];
       }
     }
 
@@ -163,7 +223,7 @@ __global__ void __launch_bounds__(ENGINE1_BLOCK) engine1_step_kernel(const Engin
       rewarded = acting;
     }
     int cur = 0;
-    Emit1<P> out{&sm, &sp, cur, tid, 0, 0u, 0, 0u};
+    Emit1<P> out{sm, &sp, L, cur, tid, 0, 0u, 0, 0u};
     for (int s = 0; s < n; ++s) {
       if (!((acting >> s) & 1u) || ((done >> s) & 1u)) continue;
       bind(s);
@@ -177,8 +237,9 @@ __global__ void __launch_bounds__(ENGINE1_BLOCK) engine1_step_kernel(const Engin
       for (int j = 0; j < P::ACT_DIM; ++j) act[j] = 0.f;
       if (sidx >= 0) {
         has_action = a.io.action_mask ? a.io.action_mask[row * S + sidx] != 0 : true;
+        cp_async_wait<1>();  // this step's actions (issued one step ago) have landed
 #pragma unroll
-        for (int j = 0; j < P::ACT_DIM; ++j) act[j] = a.io.actions[(row * S + sidx) * P::ACT_DIM + j];
+        for (int j = 0; j < P::ACT_DIM; ++j) act[j] = ACT(t & 1, sidx, j);
       }
       P::act(ctx, st, has_action, act, out);
       store_state(s, st);
@@ -190,12 +251,11 @@ __global__ void __launch_bounds__(ENGINE1_BLOCK) engine1_step_kernel(const Engin
       for (int i = 0; i < n_cur; ++i, ++traced)
         if (traced < a.trace.cap)
           a.trace.rows[(size_t)e * a.trace.cap + traced] =
-              make_int4((int)sm.qhead[cur][i][tid], sm.qpay[cur][i][0][tid],
-                        P::PW > 1 ? sm.qpay[cur][i][P::PW > 1 ? 1 : 0][tid] : 0, 0);
+              make_int4(QH(cur, i), QP(cur, i, 0), P::PW > 1 ? QP(cur, i, P::PW > 1 ? 1 : 0) : 0, 0);
     }
 
     // ---- pre_message_resolution (env.py:170-173)
-    for (int s = 0; s < n; ++s) {
+    if (P::HAS_PRE) for (int s = 0; s < n; ++s) {
       if ((done >> s) & 1u) continue;
       bind(s);
       load_state(s, st);
@@ -209,10 +269,10 @@ __global__ void __launch_bounds__(ENGINE1_BLOCK) engine1_step_kernel(const Engin
         if (!fault) fault = PHX_FAULT_ROUND_LIMIT;
         break;
       }
-      Emit1<P> resp{&sm, &sp, cur ^ 1, tid, 0, 0u, 0, 0u};
+      Emit1<P> resp{sm, &sp, L, cur ^ 1, tid, 0, 0u, 0, 0u};
       uint32_t seen = 0;
       for (int i = 0; i < n_cur; ++i) {
-        const int r = (int)((sm.qhead[cur][i][tid] >> 8) & 0xFFu);
+        const int r = (int)(((uint32_t)QH(cur, i) >> 8) & 0xFFu);
         if ((seen >> r) & 1u) continue;
         seen |= 1u << r;  // receivers in first-arrival order (resolvers.py:126,142)
         if ((done >> r) & 1u) continue;  // no context: mail dropped (:143-144)
@@ -223,15 +283,15 @@ __global__ void __launch_bounds__(ENGINE1_BLOCK) engine1_step_kernel(const Engin
         load_state(r, st);
         if constexpr (P::BATCHED) P::batch_begin(ctx, st);
         for (int j = i; j < n_cur; ++j) {  // its batch, in push order
-          const uint32_t hd = sm.qhead[cur][j][tid];
+          const uint32_t hd = (uint32_t)QH(cur, j);
           if ((int)((hd >> 8) & 0xFFu) != r) continue;
           const int sender = (int)(hd & 0xFFu);
           if (!((ctx.in_mask >> sender) & 1u)) continue;  // delivery-time edge filter (:146-148)
           Msg m;
           m.sender = sender;
           m.type = (int)((hd >> 16) & 0xFFu);
-          m.p[0] = sm.qpay[cur][j][0][tid];
-          m.p[1] = P::PW > 1 ? sm.qpay[cur][j][P::PW > 1 ? 1 : 0][tid] : 0;
+          m.p[0] = QP(cur, j, 0);
+          m.p[1] = P::PW > 1 ? QP(cur, j, P::PW > 1 ? 1 : 0) : 0;
           if (!P::handle(ctx, st, m, resp) && !fault && !resp.fault) fault = PHX_FAULT_UNKNOWN_MSG_TYPE;
         }
         if constexpr (P::BATCHED) P::batch_end(ctx, st, resp);
@@ -242,8 +302,8 @@ __global__ void __launch_bounds__(ENGINE1_BLOCK) engine1_step_kernel(const Engin
         for (int i = 0; i < resp.n; ++i, ++traced)
           if (traced < a.trace.cap)
             a.trace.rows[(size_t)e * a.trace.cap + traced] =
-                make_int4((int)sm.qhead[cur ^ 1][i][tid], sm.qpay[cur ^ 1][i][0][tid],
-                          P::PW > 1 ? sm.qpay[cur ^ 1][i][P::PW > 1 ? 1 : 0][tid] : 0, round + 1);
+                make_int4(QH(cur ^ 1, i), QP(cur ^ 1, i, 0),
+                          P::PW > 1 ? QP(cur ^ 1, i, P::PW > 1 ? 1 : 0) : 0, round + 1);
       }
       cur ^= 1;
       n_cur = resp.n;
@@ -251,7 +311,7 @@ __global__ void __launch_bounds__(ENGINE1_BLOCK) engine1_step_kernel(const Engin
     if (TRACK && env_live) a.trace.cnt[e] = traced;
 
     // ---- post_message_resolution (env.py:175-178)
-    for (int s = 0; s < n; ++s) {
+    if (P::HAS_POST) for (int s = 0; s < n; ++s) {
       if ((done >> s) & 1u) continue;
       bind(s);
       load_state(s, st);
@@ -276,7 +336,7 @@ __global__ void __launch_bounds__(ENGINE1_BLOCK) engine1_step_kernel(const Engin
       } else if ((rewarded >> s) & 1u) {
         rew_val = P::reward(ctx, st);
         rew_now = true;
-        a.reward_cache[(size_t)e * ENGINE1_SLOTS + s] = rew_val;
+        RC(s) = rew_val;
       }
       if (P::terminated(ctx, st)) t_slots |= 1u << s;
       if (P::truncated(ctx, st)) u_slots |= 1u << s;
@@ -339,7 +399,7 @@ __global__ void __launch_bounds__(ENGINE1_BLOCK) engine1_step_kernel(const Engin
             rm = 1;
           }
           if (a.io.reward)
-            a.io.reward[orow] = rm == 1 ? a.reward_cache[(size_t)e * ENGINE1_SLOTS + s] : 0.f;
+            a.io.reward[orow] = rm == 1 ? RC(s) : 0.f;
         }
         if (a.io.obs_mask) a.io.obs_mask[orow] = om;
         if (a.io.reward_mask) a.io.reward_mask[orow] = rm;
@@ -373,7 +433,7 @@ __global__ void __launch_bounds__(ENGINE1_BLOCK) engine1_step_kernel(const Engin
           int v[P::VW > 0 ? P::VW : 1];
           P::view(ctx, st, v);
 #pragma unroll
-          for (int w = 0; w < P::VW; ++w) sm.views[w][s][tid] = v[w];
+          for (int w = 0; w < P::VW; ++w) VIEW(s) = v[w];
         }
       }
       uint32_t first_obs = sp.strategic_mask;
@@ -409,12 +469,21 @@ __global__ void __launch_bounds__(ENGINE1_BLOCK) engine1_step_kernel(const Engin
     if (cached_env) {
       a.reward_none[e] = rnone;
       if (sp.env_kind == PHX_ENV_FSM) a.obs_cached[e] = ocached;
+      float4* rc = reinterpret_cast<float4*>(a.reward_cache + (size_t)e * ENGINE1_SLOTS);
+      float v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = k < n ? RC(k) : 0.f;
+      rc[0] = make_float4(v[0], v[1], v[2], v[3]);
+      rc[1] = make_float4(v[4], v[5], v[6], v[7]);
     }
 #pragma unroll
     for (int w = 0; w < P::NWORDS; ++w) {
       int4* dst = reinterpret_cast<int4*>(a.state + ((size_t)w * sp.E + e) * ENGINE1_SLOTS);
-      dst[0] = make_int4(sm.state[w][0][tid], sm.state[w][1][tid], sm.state[w][2][tid], sm.state[w][3][tid]);
-      dst[1] = make_int4(sm.state[w][4][tid], sm.state[w][5][tid], sm.state[w][6][tid], sm.state[w][7][tid]);
+      int v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = k < n ? ST(w, k) : 0;
+      dst[0] = make_int4(v[0], v[1], v[2], v[3]);
+      dst[1] = make_int4(v[4], v[5], v[6], v[7]);
     }
     if (fault) raise_fault(a.faults, e, fault);
   }

@@ -93,7 +93,9 @@ class EngineFamily : public Family {
     if (rc != PHX_OK) return rc;
     G = s.n_agents <= 8 ? 8 : (s.n_agents <= 16 ? 16 : 32);
     // thread-per-env variant: <= 8 agents and a program that declares its queue bound
-    const bool eligible = P::Q1CAP > 0 && P::VW <= 1 && s.n_agents <= ENGINE1_SLOTS;
+    qcap1 = P::q1_cap(s);  // messages in flight per round, for THIS env class (0 = unsupported)
+    const bool eligible = P::Q1CAP > 0 && P::VW <= 1 && s.n_agents <= ENGINE1_SLOTS && qcap1 > 0 &&
+                          qcap1 <= P::Q1CAP;
     PHX_REQUIRE(s.exec_mode != PHX_EXEC_THREAD || eligible, PHX_ERR_UNSUPPORTED,
                 "PHX_EXEC_THREAD needs an env class with at most 8 agents whose device program "
                 "supports the thread-per-env engine");
@@ -129,6 +131,7 @@ class EngineFamily : public Family {
     EngineArgs<P> a;
     a.spec = espec;
     a.T = T;
+    a.qcap = qcap1;
     a.hdr = d_hdr;
     a.term = d_term;
     a.trunc = d_trunc;
@@ -195,7 +198,9 @@ class EngineFamily : public Family {
     EngineArgs<P> a = make_args(T, io);
     if constexpr (P::Q1CAP > 0 && P::VW <= 1) {
       if (thread_per_env) {
-        const size_t smem = sizeof(Engine1Smem<P>);
+        const Engine1Layout lay = engine1_layout<P>(spec.n_agents, spec.n_strategic, qcap1,
+                                                    spec.env_kind != PHX_ENV_BASE);
+        const size_t smem = sizeof(int32_t) * (size_t)lay.words;
         const int grid = (E + ENGINE1_BLOCK - 1) / ENGINE1_BLOCK;
         if (tracking()) {
           PHX_CUDA(cudaFuncSetAttribute(engine1_step_kernel<P, true>,
@@ -231,6 +236,7 @@ class EngineFamily : public Family {
   EngineSpec espec{};
   int G = 8;
   bool thread_per_env = false;
+  int qcap1 = 0;
   int32_t* d_state = nullptr;
   float* d_rcache = nullptr;
   uint32_t* d_rnone = nullptr;
