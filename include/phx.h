@@ -232,6 +232,13 @@ int32_t phx_get_field(phx_env* env, int32_t field, int32_t index, void* host_out
 int32_t phx_set_field(phx_env* env, int32_t field, int32_t index, const void* host_in,
                       uint64_t in_bytes);
 
+/* Reduce one int32 state column over the envs ON THE DEVICE (metrics: replaces a Python loop
+ * over env objects reading `agent.<attr>`, phantom/metrics.py:230-231,348-352).  The column
+ * `field` is viewed as rows of `width` int32 words; word `col` of every row is reduced.
+ * Returns the exact int64 sum, the min and the max over the E envs.  Synchronises.        */
+int32_t phx_reduce_field(phx_env* env, int32_t field, int32_t index, int32_t width, int32_t col,
+                         int64_t* host_sum, int32_t* host_min, int32_t* host_max);
+
 /* Resolver.tracked_messages (phantom/resolvers.py:41-60) of the LAST phx_step, for envs
  * [env_begin, env_end): host_counts int32 [n] messages recorded per env, host_msgs
  * int32 [n, trace_capacity, PHX_TRACE_WORDS] rows (sender_slot | recv_slot << 8 |

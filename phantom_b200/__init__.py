@@ -9,8 +9,8 @@ built library raises ImportError.
 __version__ = "0.1.0"
 
 from . import _lib  # noqa: F401  (fails loudly if libphx.so is missing)
-from . import (agents, context, decoders, encoders, errors, fsm, message, network, resolvers,
-               reward_functions, spaces, views)
+from . import (agents, context, decoders, encoders, errors, fsm, message, metrics, network,
+               resolvers, reward_functions, sharding, spaces, views)
 from .agents import Agent, StrategicAgent
 from .context import Context
 from .decoders import Decoder

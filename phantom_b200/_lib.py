@@ -106,6 +106,8 @@ SYMBOLS = {
     "phx_get_field": (C.c_int32, [_P, C.c_int32, C.c_int32, _P, C.c_uint64]),
     "phx_set_field": (C.c_int32, [_P, C.c_int32, C.c_int32, _P, C.c_uint64]),
     "phx_get_trace": (C.c_int32, [_P, C.c_int32, C.c_int32, _P, _P]),
+    "phx_reduce_field": (C.c_int32, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                     C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "phx_poll_errors": (C.c_int32, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                     C.POINTER(C.c_int32), C.c_int32]),
     "phx_selftest_ratio": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),

@@ -1,5 +1,7 @@
 // phx_abi.cu -- the C ABI of libphx (include/phx.h): handle management, argument checks,
 // dispatch to the device program families, host-buffer variants, field/trace/fault access.
+#include <climits>
+#include <cstdint>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -77,6 +79,30 @@ int32_t Family::field_ptr(int32_t field, int32_t index, void** p, size_t* bytes)
 
 using phx::Family;
 using phx::set_error;
+
+// K8 field_reduce: word `col` of every `width`-word row of an int32 column -> sum / min / max.
+// Grid-stride, warp-shuffle reduction, one atomic triple per block.
+__global__ void phx_field_reduce_kernel(const int32_t* col_base, int E, int width, int col,
+                                        unsigned long long* sum, int32_t* mn, int32_t* mx) {
+  long long s = 0;
+  int32_t lo = INT32_MAX, hi = INT32_MIN;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x) {
+    const int32_t v = col_base[(size_t)e * width + col];
+    s += v;
+    lo = min(lo, v);
+    hi = max(hi, v);
+  }
+  for (int off = 16; off > 0; off >>= 1) {
+    s += __shfl_xor_sync(0xFFFFFFFFu, s, off);
+    lo = min(lo, __shfl_xor_sync(0xFFFFFFFFu, lo, off));
+    hi = max(hi, __shfl_xor_sync(0xFFFFFFFFu, hi, off));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(sum, (unsigned long long)s);
+    atomicMin(mn, lo);
+    atomicMax(mx, hi);
+  }
+}
 
 struct phx_env {
   Family* fam;
@@ -338,6 +364,34 @@ int32_t phx_get_field(phx_env* env, int32_t field, int32_t index, void* host_out
 int32_t phx_set_field(phx_env* env, int32_t field, int32_t index, const void* host_in,
                       uint64_t in_bytes) {
   return field_copy(env, field, index, const_cast<void*>(host_in), in_bytes, true);
+}
+
+int32_t phx_reduce_field(phx_env* env, int32_t field, int32_t index, int32_t width, int32_t col,
+                         int64_t* host_sum, int32_t* host_min, int32_t* host_max) {
+  PHX_REQUIRE(env != nullptr, PHX_ERR_INVALID, "env is NULL");
+  Family* f = env->fam;
+  PHX_CUDA(cudaSetDevice(f->device));
+  void* d = nullptr;
+  size_t n = 0;
+  int32_t rc = f->field_ptr(field, index, &d, &n);
+  if (rc != PHX_OK) return rc;
+  PHX_REQUIRE(width >= 1 && col >= 0 && col < width &&
+                  n == sizeof(int32_t) * (size_t)f->E * (size_t)width,
+              PHX_ERR_INVALID, "width / col do not match the column's layout");
+  struct Acc { unsigned long long sum; int32_t mn, mx; } h{0ull, INT32_MAX, INT32_MIN};
+  Acc* dacc = nullptr;
+  PHX_CUDA(cudaMalloc(&dacc, sizeof(Acc)));
+  PHX_CUDA(cudaMemcpy(dacc, &h, sizeof(Acc), cudaMemcpyHostToDevice));
+  const int blocks = (f->E + 255) / 256 < 1184 ? (f->E + 255) / 256 : 1184;  // 8 blocks per SM
+  phx_field_reduce_kernel<<<blocks, 256>>>((const int32_t*)d, f->E, width, col, &dacc->sum,
+                                            &dacc->mn, &dacc->mx);
+  cudaError_t err = cudaMemcpy(&h, dacc, sizeof(Acc), cudaMemcpyDeviceToHost);
+  cudaFree(dacc);
+  PHX_CUDA(err);
+  if (host_sum) *host_sum = (int64_t)h.sum;
+  if (host_min) *host_min = h.mn;
+  if (host_max) *host_max = h.mx;
+  return PHX_OK;
 }
 
 int32_t phx_get_trace(phx_env* env, int32_t env_begin, int32_t env_end, int32_t* host_counts,

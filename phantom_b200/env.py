@@ -334,6 +334,21 @@ class PhantomEnv:
         col = self.field(L.FIELD_FAMILY + word, np.int32, width=self.tile_width)
         return col[:, agent._phx_slot].view(dtype)
 
+    def reduce_agent_column(self, agent: Agent, word: int) -> Dict[str, float]:
+        """phx_reduce_field: {sum, min, max, mean} of an agent's int32 state word over all envs,
+        computed on the device (no [E] column crosses PCIe)."""
+        self._ensure_handle()
+        info = self.family
+        if info.fast_column is not None and self.exec_name.startswith("fast"):
+            field, width, col = L.FIELD_FAMILY + 0, 4, word
+        else:
+            field, width, col = L.FIELD_FAMILY + word, self.tile_width, agent._phx_slot
+        s, lo, hi = C.c_int64(), C.c_int32(), C.c_int32()
+        L.check(L.lib.phx_reduce_field(self._handle, field, 0, width, col, C.byref(s),
+                                       C.byref(lo), C.byref(hi)))
+        return {"sum": float(s.value), "min": float(lo.value), "max": float(hi.value),
+                "mean": s.value / self.num_envs}
+
     def set_agent_column(self, agent: Agent, word: int, value) -> None:
         info = self.family
         if info.fast_column is not None and self.exec_name.startswith("fast"):
