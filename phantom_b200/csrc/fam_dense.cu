@@ -22,6 +22,8 @@
 //
 // Agent kind 0 = DenseAgent (strategic).  Payload types: 0 Signal(value), 1 Ack(value).
 // State words per agent: 0 signal, 1 total, 2 best, 3 best_sender, 4 acks, 5 ack_total.
+#include <climits>
+#include <cstdint>
 #include <cstring>
 #include <string>
 
@@ -60,8 +62,7 @@ struct alignas(16) DenseStage {  // one step's output rows of one env, 16-byte a
 
 struct DenseSmem {
   int32_t mb[DN_MAX * DN_STRIDE];  // mailbox, round 0
-  int32_t ack_to[DN_MAX];          // round 1: Ack receiver of every agent (-1 = none)
-  int32_t ack_val[DN_MAX];
+  int2 ack[DN_MAX];                // round 1: (Ack receiver of every agent or -1, Ack value)
   int32_t order_key[DN_MAX];       // trace only: first-arrival keys
   uint32_t sent[4];
   uint32_t any_ack;
@@ -119,17 +120,23 @@ __global__ void __launch_bounds__(DN_MAX) dense_step_kernel(const DenseArgs a) {
     const uint32_t sent_w = __ballot_sync(0xFFFFFFFFu, sends);
     if (lane == 0) sm.sent[warp] = sent_w;
     if (sends) {
-      // column write: mb[r][slot] for every neighbour r (lanes hit consecutive words)
+      // payload whitelist of the receivers, one mask test per 32 neighbours (network.py:323-331)
+      if (!(sp.flags & PHX_FLAG_NO_PAYLOAD_CHECKS) &&
+          ((adj[0] & ~sp.receiver_ok[DN_SIGNAL][0]) | (adj[1] & ~sp.receiver_ok[DN_SIGNAL][1]) |
+           (adj[2] & ~sp.receiver_ok[DN_SIGNAL][2]) | (adj[3] & ~sp.receiver_ok[DN_SIGNAL][3])))
+        fault = fault ? fault : PHX_FAULT_BAD_PAYLOAD_TYPE;
+      // column write: mb[r][slot] for every neighbour r (lanes hit consecutive words).  The
+      // receiver-tailored part (7 s + 3 r) % 5 is carried incrementally: +3 (mod 5) per r.
+      int tail = (7 * slot) % 5;
+      int32_t* col = sm.mb + slot;
 #pragma unroll
       for (int w = 0; w < 4; ++w) {
-        uint32_t m = adj[w];
-        while (m) {
-          const int r = w * 32 + __ffs(m) - 1;
-          m &= m - 1;
-          if (!((sp.receiver_ok[DN_SIGNAL][r >> 5] >> (r & 31)) & 1u) &&
-              !(sp.flags & PHX_FLAG_NO_PAYLOAD_CHECKS))
-            fault = fault ? fault : PHX_FAULT_BAD_PAYLOAD_TYPE;
-          sm.mb[r * DN_STRIDE + slot] = dn_tailored(st[0], slot, r);
+        const uint32_t m = adj[w];
+#pragma unroll 8
+        for (int b = 0; b < 32; ++b) {
+          if ((m >> b) & 1u) col[(w * 32 + b) * DN_STRIDE] = st[0] + tail;
+          tail += 3;
+          tail -= tail >= 5 ? 5 : 0;
         }
       }
     }
@@ -143,19 +150,21 @@ __global__ void __launch_bounds__(DN_MAX) dense_step_kernel(const DenseArgs a) {
     int ack_recv = -1;
     int first_sender = -1;
     if (is_agent && sp.round_limit != 0) {
-      int total = 0, best = 0, best_s = -1;
+      int total = 0, best = INT32_MIN, best_s = -1;
+      const int32_t* rowp = sm.mb + slot * DN_STRIDE;
 #pragma unroll
       for (int w = 0; w < 4; ++w) {
-        uint32_t m = adj[w] & sm.sent[w];  // symmetric graph: senders with an edge to me
-        while (m) {
-          const int s = w * 32 + __ffs(m) - 1;
-          m &= m - 1;
-          if (first_sender < 0) first_sender = s;
-          const int v = sm.mb[slot * DN_STRIDE + s];
-          total += v;
-          if (best_s < 0 || v > best) {  // strict: the FIRST sender attaining the max wins
-            best = v;
-            best_s = s;
+        const uint32_t m = adj[w] & sm.sent[w];  // symmetric graph: senders with an edge to me
+        if (TRACK && first_sender < 0 && m) first_sender = w * 32 + __ffs(m) - 1;
+#pragma unroll 8
+        for (int b = 0; b < 32; ++b) {
+          if ((m >> b) & 1u) {
+            const int v = rowp[w * 32 + b];
+            total += v;
+            if (v > best) {  // strict: the FIRST sender attaining the max wins
+              best = v;
+              best_s = w * 32 + b;
+            }
           }
         }
       }
@@ -169,8 +178,7 @@ __global__ void __launch_bounds__(DN_MAX) dense_step_kernel(const DenseArgs a) {
           fault = fault ? fault : PHX_FAULT_BAD_PAYLOAD_TYPE;
       }
     }
-    sm.ack_to[slot] = ack_recv;
-    sm.ack_val[slot] = st[2];
+    sm.ack[slot] = make_int2(ack_recv, st[2]);
     if (TRACK) sm.order_key[slot] = first_sender < 0 ? 0x7FFFFFFF : first_sender * DN_MAX + slot;
     const uint32_t acks_w = __ballot_sync(0xFFFFFFFFu, ack_recv >= 0);
     if (slot == 0) sm.any_ack = 0;
@@ -182,10 +190,12 @@ __global__ void __launch_bounds__(DN_MAX) dense_step_kernel(const DenseArgs a) {
     // ---- round 1: the Acks (same handle_batch override): count and sum
     if (is_agent && sp.round_limit != 1 && sp.round_limit != 0) {
       int acks = 0, ack_total = 0;
+#pragma unroll 8
       for (int r = 0; r < n; ++r) {  // broadcast reads
-        if (sm.ack_to[r] == slot) {
+        const int2 ak = sm.ack[r];
+        if (ak.x == slot) {
           acks += 1;
-          ack_total += sm.ack_val[r];
+          ack_total += ak.y;
         }
       }
       st[4] = acks;
@@ -214,9 +224,9 @@ __global__ void __launch_bounds__(DN_MAX) dense_step_kernel(const DenseArgs a) {
         }
         if (best_r < 0) break;
         last = best_k;
-        if (sm.ack_to[best_r] >= 0) {
+        if (sm.ack[best_r].x >= 0) {
           if (cnt < a.trace.cap)
-            rows[cnt] = trace_row(best_r, sm.ack_to[best_r], DN_ACK, sm.ack_val[best_r], 0, 1);
+            rows[cnt] = trace_row(best_r, sm.ack[best_r].x, DN_ACK, sm.ack[best_r].y, 0, 1);
           ++cnt;
         }
       }
