@@ -63,6 +63,7 @@ struct ScPlan {
 struct ScArgs {
   ScPlan p;
   int32_t T;
+  int32_t env_begin, env_count;  // sub-range of the handle's envs stepped by this launch
   int4* hdr;
   int4* shop;
   StepIO io;
@@ -96,11 +97,15 @@ __device__ __forceinline__ float sc_ratio(int num, float den, float rcp) {
 #ifndef SC_REWARD_F64
 #define SC_REWARD_F64 0   // 1: reference-literal float64 reward arithmetic
 #endif
+#ifndef SC_UNROLL
+#define SC_UNROLL 2        // unroll factor of the step loop (2: +8 %, 4: same as 2)
+#endif
 #ifndef SC_RING_DEPTH
 #define SC_RING_DEPTH 8   // action prefetch ring (steps in flight + 1)
 #endif
 constexpr int SC_BLOCK = SC_BLOCK_THREADS;
 constexpr int SC_RING = SC_RING_DEPTH;
+constexpr int SC_UNROLL_K = SC_UNROLL;
 
 // The NC order sizes of one (episode, step): rng stream SC_STREAM_ORDER, idx = customer.
 template <int NC>
@@ -130,8 +135,8 @@ __global__ void __launch_bounds__(SC_BLOCK) sc_fast_kernel(const ScArgs a) {
   // Threads past the last env re-run env E-1: they compute and store bit-identical values
   // (a benign duplicate), which keeps every `live` test out of the step loop.
   const int e_raw = blockIdx.x * SC_BLOCK + threadIdx.x;
-  const bool real = e_raw < p.E;
-  const int e = real ? e_raw : p.E - 1;
+  const bool real = e_raw < a.env_count;
+  const int e = a.env_begin + (real ? e_raw : a.env_count - 1);
   constexpr bool live = true;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nc = NC > 0 ? NC : p.nc;
@@ -141,7 +146,7 @@ __global__ void __launch_bounds__(SC_BLOCK) sc_fast_kernel(const ScArgs a) {
   const uint32_t all_customers = nc >= 32 ? 0xFFFFFFFFu : ((1u << nc) - 1u);
   const bool all_delivered = p.deliver_ord == all_customers;
   // vector path for obs needs a full warp and 16-byte aligned rows
-  const bool warp_full = (blockIdx.x * SC_BLOCK + warp * 32 + 32) <= (uint32_t)p.E;
+  const bool warp_full = (blockIdx.x * SC_BLOCK + warp * 32 + 32) <= (uint32_t)a.env_count;
   const bool vec_obs = SC_VEC_OBS && warp_full && ((p.E & 3) == 0);
   const uint32_t E = (uint32_t)p.E;
 
@@ -177,6 +182,7 @@ __global__ void __launch_bounds__(SC_BLOCK) sc_fast_kernel(const ScArgs a) {
   if (NC > 0 && SC_OVERLAP_RNG)
     sc_draw_orders<NC>(p, env_id, (uint32_t)h.y, (uint32_t)(h.x + 1), want_nxt);
 
+#pragma unroll(SC_UNROLL_K)
   for (int t = 0; t < a.T; ++t) {
     if (t + SC_RING - 1 < a.T)
       cp_async4(&act_ring[(t + SC_RING - 1) % SC_RING][threadIdx.x],
@@ -515,15 +521,28 @@ class SupplyChainFast final : public Family {
   }
 
   int32_t rollout(int32_t T, const StepIO& io, cudaStream_t stream) override {
+    return rollout_range(T, io, 0, E, stream);
+  }
+
+  bool supports_ranges() const override { return !tracking(); }
+
+  // Steps envs [env_begin, env_begin + env_count); the I/O planes keep the handle's full
+  // [T, E, ...] shape (row stride E), so chunks of one rollout can be pipelined with copies.
+  int32_t rollout_range(int32_t T, const StepIO& io, int32_t env_begin, int32_t env_count,
+                        cudaStream_t stream) override {
+    PHX_REQUIRE(env_begin >= 0 && env_count >= 1 && env_begin + env_count <= E, PHX_ERR_INVALID,
+                "env range out of bounds");
     ScArgs a;
     a.p = plan;
     a.T = T;
+    a.env_begin = env_begin;
+    a.env_count = env_count;
     a.hdr = d_hdr;
     a.shop = d_shop;
     a.io = io;
     a.faults = fault_sink();
     a.trace = trace_sink();
-    const int grid = (E + SC_BLOCK - 1) / SC_BLOCK;
+    const int grid = (env_count + SC_BLOCK - 1) / SC_BLOCK;
     const bool track = tracking();
     PHX_REQUIRE(!track || T == 1, PHX_ERR_INVALID,
                 "message tracking records one step: use phx_step (T == 1)");

@@ -26,6 +26,12 @@ Family::~Family() {
   cudaFree(d_trace_cnt);
   cudaFree(d_stage);
   if (own_stream) cudaStreamDestroy(own_stream);
+  if (copy_in) cudaStreamDestroy(copy_in);
+  if (copy_out) cudaStreamDestroy(copy_out);
+  for (int i = 0; i < 8; ++i) {
+    if (ev_in[i]) cudaEventDestroy(ev_in[i]);
+    if (ev_k[i]) cudaEventDestroy(ev_k[i]);
+  }
 }
 
 int32_t Family::base_init(const phx_spec& s, int32_t num_envs, int32_t dev, uint64_t sd,
@@ -56,6 +62,12 @@ int32_t Family::base_init(const phx_spec& s, int32_t num_envs, int32_t dev, uint
     PHX_CUDA(cudaMemset(d_trace_cnt, 0, sizeof(int32_t) * (size_t)E));
   }
   PHX_CUDA(cudaStreamCreateWithFlags(&own_stream, cudaStreamNonBlocking));
+  PHX_CUDA(cudaStreamCreateWithFlags(&copy_in, cudaStreamNonBlocking));
+  PHX_CUDA(cudaStreamCreateWithFlags(&copy_out, cudaStreamNonBlocking));
+  for (int i = 0; i < 8; ++i) {
+    PHX_CUDA(cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming));
+    PHX_CUDA(cudaEventCreateWithFlags(&ev_k[i], cudaEventDisableTiming));
+  }
   return PHX_OK;
 }
 
@@ -276,6 +288,8 @@ int32_t phx_rollout_host(phx_env* env, int32_t T, const float* actions,
   (void)n;
   if (total > f->stage_bytes) {
     PHX_CUDA(cudaStreamSynchronize(f->own_stream));
+    PHX_CUDA(cudaStreamSynchronize(f->copy_in));
+    PHX_CUDA(cudaStreamSynchronize(f->copy_out));
     if (f->d_stage) PHX_CUDA(cudaFree(f->d_stage));
     f->d_stage = nullptr;
     f->stage_bytes = 0;
@@ -292,12 +306,6 @@ int32_t phx_rollout_host(phx_env* env, int32_t T, const float* actions,
   uint8_t* d_term = p; p += b_u8;
   uint8_t* d_trunc = p; p += b_u8;
   uint8_t* d_all = p;
-  cudaStream_t st = f->own_stream;
-  if (actions)
-    PHX_CUDA(cudaMemcpyAsync(d_act, actions, TE * S * f->spec.act_dim * sizeof(float),
-                             cudaMemcpyHostToDevice, st));
-  if (action_mask)
-    PHX_CUDA(cudaMemcpyAsync(d_am, action_mask, TE * S, cudaMemcpyHostToDevice, st));
   phx::StepIO io{d_act,
                  action_mask ? d_am : nullptr,
                  obs ? d_obs : nullptr,
@@ -307,20 +315,45 @@ int32_t phx_rollout_host(phx_env* env, int32_t T, const float* actions,
                  term ? d_term : nullptr,
                  trunc ? d_trunc : nullptr,
                  all_done ? d_all : nullptr};
-  int32_t rc = f->rollout(T, io, st);
-  if (rc != PHX_OK) return rc;
-  if (obs)
-    PHX_CUDA(cudaMemcpyAsync(obs, d_obs, TE * S * f->spec.obs_dim * sizeof(float),
-                             cudaMemcpyDeviceToHost, st));
-  if (obs_mask) PHX_CUDA(cudaMemcpyAsync(obs_mask, d_om, TE * S, cudaMemcpyDeviceToHost, st));
-  if (reward)
-    PHX_CUDA(cudaMemcpyAsync(reward, d_rew, TE * S * sizeof(float), cudaMemcpyDeviceToHost, st));
-  if (reward_mask)
-    PHX_CUDA(cudaMemcpyAsync(reward_mask, d_rm, TE * S, cudaMemcpyDeviceToHost, st));
-  if (term) PHX_CUDA(cudaMemcpyAsync(term, d_term, TE * S, cudaMemcpyDeviceToHost, st));
-  if (trunc) PHX_CUDA(cudaMemcpyAsync(trunc, d_trunc, TE * S, cudaMemcpyDeviceToHost, st));
-  if (all_done) PHX_CUDA(cudaMemcpyAsync(all_done, d_all, TE * 2, cudaMemcpyDeviceToHost, st));
-  PHX_CUDA(cudaStreamSynchronize(st));
+  const size_t E = (size_t)f->E, A = (size_t)f->spec.act_dim, O = (size_t)f->spec.obs_dim;
+  // Copy env columns [b, b+c) of a [T, E, width-bytes-per-env] plane (2D: T rows, pitch E*w).
+  auto copy2d = [&](void* dst, const void* src, size_t w, size_t b, size_t c, cudaMemcpyKind k,
+                    cudaStream_t s) {
+    if (w == 0 || c == 0) return cudaSuccess;
+    return cudaMemcpy2DAsync((char*)dst + b * w, E * w, (const char*)src + b * w, E * w, c * w,
+                             (size_t)T, k, s);
+  };
+  // Chunked 3-stage pipeline (H2D | kernel | D2H on three streams) when the family can step
+  // env sub-ranges: PCIe is full duplex, so the input copy of chunk c+1 and the output copy of
+  // chunk c-1 overlap the kernel of chunk c.  Otherwise: one chunk.
+  const int chunks = (f->supports_ranges() && f->E >= 8192) ? 8 : 1;
+  const size_t per = (E + chunks - 1) / chunks;
+  for (int c = 0; c < chunks; ++c) {
+    const size_t b = (size_t)c * per;
+    if (b >= E) break;
+    const size_t n = (b + per <= E) ? per : E - b;
+    if (actions)
+      PHX_CUDA(copy2d(d_act, actions, S * A * sizeof(float), b, n, cudaMemcpyHostToDevice, f->copy_in));
+    if (action_mask)
+      PHX_CUDA(copy2d(d_am, action_mask, S, b, n, cudaMemcpyHostToDevice, f->copy_in));
+    PHX_CUDA(cudaEventRecord(f->ev_in[c], f->copy_in));
+    PHX_CUDA(cudaStreamWaitEvent(f->own_stream, f->ev_in[c], 0));
+    int32_t rc = chunks == 1 ? f->rollout(T, io, f->own_stream)
+                             : f->rollout_range(T, io, (int32_t)b, (int32_t)n, f->own_stream);
+    if (rc != PHX_OK) return rc;
+    PHX_CUDA(cudaEventRecord(f->ev_k[c], f->own_stream));
+    PHX_CUDA(cudaStreamWaitEvent(f->copy_out, f->ev_k[c], 0));
+    cudaStream_t so = f->copy_out;
+    if (obs) PHX_CUDA(copy2d(obs, d_obs, S * O * sizeof(float), b, n, cudaMemcpyDeviceToHost, so));
+    if (obs_mask) PHX_CUDA(copy2d(obs_mask, d_om, S, b, n, cudaMemcpyDeviceToHost, so));
+    if (reward) PHX_CUDA(copy2d(reward, d_rew, S * sizeof(float), b, n, cudaMemcpyDeviceToHost, so));
+    if (reward_mask) PHX_CUDA(copy2d(reward_mask, d_rm, S, b, n, cudaMemcpyDeviceToHost, so));
+    if (term) PHX_CUDA(copy2d(term, d_term, S, b, n, cudaMemcpyDeviceToHost, so));
+    if (trunc) PHX_CUDA(copy2d(trunc, d_trunc, S, b, n, cudaMemcpyDeviceToHost, so));
+    if (all_done) PHX_CUDA(copy2d(all_done, d_all, 2, b, n, cudaMemcpyDeviceToHost, so));
+  }
+  PHX_CUDA(cudaStreamSynchronize(f->copy_out));
+  PHX_CUDA(cudaStreamSynchronize(f->own_stream));
   return PHX_OK;
 }
 
