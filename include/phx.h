@@ -76,7 +76,9 @@ typedef enum phx_family {
                                   (tests/__init__.py:28-69)                           */
   PHX_FAMILY_MARKET = 3,       /* 3-stage FSM market (BASELINE config C3)             */
   PHX_FAMILY_STACKELBERG = 4,  /* leader/follower pricing game (BASELINE config C4)   */
-  PHX_FAMILY_DENSE = 5         /* dense-graph broadcast + batch aggregation (C5)      */
+  PHX_FAMILY_DENSE = 5,        /* dense-graph broadcast + batch aggregation (C5)      */
+  PHX_FAMILY_SUPPLY_CHAIN2 = 6 /* multi-shop supply chain with agent supertypes
+                                  (docs/user/tutorial2.rst)                           */
 } phx_family;
 
 typedef enum phx_exec_mode {

@@ -44,6 +44,18 @@ def patched_np_randint(stream: rng.StepStream):
         np.random.randint = orig
 
 
+@contextlib.contextmanager
+def patched_np_uniform(stream: rng.StepStream):
+    """Route `np.random.uniform(low, high)` (the reference's UniformFloatSampler.sample,
+    phantom/utils/samplers.py:142) to the contract stream while the block runs."""
+    orig = np.random.uniform
+    np.random.uniform = lambda low=0.0, high=1.0, size=None: stream.uniform(low, high)
+    try:
+        yield
+    finally:
+        np.random.uniform = orig
+
+
 def tracked_to_rows(tracked, slot_of: Dict[Any, int], type_of: Callable[[Any], int],
                     value_of: Callable[[Any], Sequence[float]]) -> np.ndarray:
     """Flatten Resolver.tracked_messages to rows (sender_slot, recv_slot, type, v0, v1)."""

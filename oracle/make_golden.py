@@ -168,6 +168,36 @@ def gen_dense_reference() -> None:
         print(name, {k: v.shape for k, v in out.items()})
 
 
+def gen_supply_chain2_reference() -> None:
+    """oracle/workloads/supply_chain2.py (tutorial-2 env with supertypes) on the UNMODIFIED
+    reference, its UniformFloatSampler drawing through the patched np.random.uniform."""
+    from .workloads import supply_chain2 as wl
+
+    ref = ref_shim.import_reference()
+    seed, n_env, n_ep, T, S = 20261021, 10, 2, 100, wl.N_SHOPS
+    r = np.random.RandomState(19)
+    actions = r.uniform(0, 100, size=(n_env, n_ep, T, S, 1)).astype(np.float32)
+    mask = (r.uniform(size=(n_env, n_ep, T, S)) > 0.08).astype(np.uint8)
+    per_env, weights = [], []
+    for e in range(n_env):
+        streams = {s: rng.StepStream(seed, e, s)
+                   for s in (wl.STREAM_ORDER, wl.STREAM_SAMPLER, wl.STREAM_SHOP_CHOICE)}
+        ws = []
+        with harness.patched_np_uniform(streams[wl.STREAM_SAMPLER]):
+            env = wl.build(ref, streams, ref.utils.samplers.UniformFloatSampler,
+                           enable_tracking=e < 3)
+            per_env.append(harness.run_generic(
+                env, harness.EpisodeClock(list(streams.values())), actions[e], mask[e], 4,
+                track=e < 3, state_fn=lambda env: (ws.append(wl.weights(env)), wl.state(env))[1]))
+        if e >= 3:
+            per_env[-1]["messages"] = []
+        weights.append(np.array(ws).reshape(n_ep, T, S))
+    out = pack_generic(per_env, actions, mask, seed, 3, wl.MESSAGE_TYPE_IDS)
+    out["weights"] = np.stack(weights)
+    np.savez_compressed(os.path.join(GOLDEN, "supply_chain2_reference.npz"), **out)
+    print("supply_chain2_reference.npz:", {k: v.shape for k, v in out.items()})
+
+
 def main() -> int:
     if not ref_shim.reference_available():
         print("reference not available")
@@ -177,6 +207,7 @@ def main() -> int:
     gen_market_reference()
     gen_stackelberg_reference()
     gen_dense_reference()
+    gen_supply_chain2_reference()
     return 0
 
 

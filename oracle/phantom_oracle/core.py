@@ -142,6 +142,23 @@ class ComparableSampler(Sampler[T]):
     __hash__ = object.__hash__
 
 
+class UniformFloatSampler(ComparableSampler[float]):
+    """utils/samplers.py:119-147: np.random.uniform(low, high) on every sample()."""
+
+    def __init__(self, low: float = 0.0, high: float = 1.0, clip_low=None, clip_high=None):
+        assert high >= low
+        self.low, self.high, self.clip_low, self.clip_high = low, high, clip_low, clip_high
+        super().__init__()
+
+    def sample(self) -> float:
+        import numpy as np
+
+        self._value = np.random.uniform(self.low, self.high)
+        if self.clip_low is not None or self.clip_high is not None:
+            self._value = np.clip(self._value, self.clip_low, self.clip_high)
+        return self._value
+
+
 @dataclasses.dataclass
 class Supertype(ABC):
     """supertype.py:14-30: sample() resolves Sampler-valued fields; env-managed

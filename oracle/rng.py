@@ -164,3 +164,12 @@ class StepStream:
 
     def uniform01(self) -> float:
         return uniform01(self.next_d24())
+
+    def uniform(self, low: float, high: float) -> float:
+        return uniform_f64(low, high, self.next_d24())
+
+
+def uniform_f64(low: float, high: float, draw: int) -> float:
+    """Contract version of np.random.uniform(low, high): low + (high - low) * (d24 / 2^24),
+    every operation rounded in float64 (device: __dmul_rn / __dadd_rn, no contraction)."""
+    return float(low) + (float(high) - float(low)) * (int(draw) / 16777216.0)

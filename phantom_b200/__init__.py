@@ -22,5 +22,7 @@ from .message import Message, MsgPayload, msg_payload
 from .network import Network, NetworkError
 from .reward_functions import RewardFunction
 from .stackelberg import StackelbergEnv
+from .supertype import Supertype
+from . import utils
 from .types import AgentID, PolicyID, StageID
 from .views import AgentView, EnvView, View

@@ -30,6 +30,7 @@ PHX_OK, PHX_ERR_INVALID, PHX_ERR_CUDA, PHX_ERR_UNSUPPORTED, PHX_ERR_NO_DEVICE = 
 ENV_BASE, ENV_FSM, ENV_STACKELBERG = 0, 1, 2
 # phx_family
 FAMILY_SUPPLY_CHAIN, FAMILY_MOCK, FAMILY_MARKET, FAMILY_STACKELBERG, FAMILY_DENSE = 1, 2, 3, 4, 5
+FAMILY_SUPPLY_CHAIN2 = 6
 # phx_exec_mode
 EXEC_AUTO, EXEC_QUEUE, EXEC_FAST, EXEC_THREAD = 0, 1, 2, 3
 EXEC_MODES = {"auto": EXEC_AUTO, "queue": EXEC_QUEUE, "fast": EXEC_FAST, "thread": EXEC_THREAD}

@@ -104,7 +104,7 @@ struct MockProgram {
   }
   __device__ static float reward(const Ctx& c, int* st) {
     st[2] += 1;
-    return c.kind == MK_CODEC ? c.spec->agent_fparam[c.slot][0] : 0.0f;  // Constant(value)
+    return c.kind == MK_CODEC ? (float)c.spec->agent_fparam[c.slot][0] : 0.0f;  // Constant(value)
   }
   __device__ static bool terminated(const Ctx& c, const int*) {
     return c.step == c.spec->agent_iparam[c.slot][0];

@@ -199,6 +199,9 @@ int32_t phx_create(const phx_spec* spec, int32_t num_envs, int32_t device, uint6
     case PHX_FAMILY_DENSE:
       fam = phx::make_dense_family(*spec);
       break;
+    case PHX_FAMILY_SUPPLY_CHAIN2:
+      fam = phx::make_supply_chain2_family(*spec);
+      break;
     default:
       set_error("no device program for family " + std::to_string(spec->family));
       return PHX_ERR_UNSUPPORTED;

@@ -59,8 +59,9 @@ struct EngineSpec {
   uint32_t env_offset;
   int32_t iparams[PHX_MAX_PARAMS];
   float fparams[PHX_MAX_PARAMS];
+  double dparams[4];                   // family parameters that must stay float64
   int32_t agent_iparam[ENGINE_MAX_AGENTS][4];
-  float agent_fparam[ENGINE_MAX_AGENTS][2];
+  double agent_fparam[ENGINE_MAX_AGENTS][2];
   int32_t codec_op[ENGINE_MAX_AGENTS][PHX_MAX_CODEC_OPS];  // opcode | length << 8
   float codec_val[ENGINE_MAX_AGENTS][PHX_MAX_CODEC_OPS];
 };

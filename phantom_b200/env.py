@@ -76,11 +76,24 @@ class PhantomEnv:
                  env_supertype=None, agent_supertypes=None, *, num_envs: int = 1,
                  device: int = 0, seed: int = 0, env_offset: int = 0,
                  exec_mode: Optional[str] = None, auto_reset: bool = False) -> None:
-        if env_supertype is not None or agent_supertypes is not None:
+        if env_supertype is not None:
             raise NotLowerableError(
-                "Supertype / Sampler per-env parameterisation is not lowered to the device "
-                "yet (SURVEY.md 8f row 2)")
+                "env supertypes are not lowered to the device yet (SURVEY.md 8f row 2)")
         self.network = network or Network()
+        # env.py:78-124: collect every Sampler of the agent supertypes once, in dict order
+        self._samplers: List[Any] = []
+        if agent_supertypes is not None:
+            from .utils.samplers import Sampler
+
+            for agent_id, st in agent_supertypes.items():
+                agent = self.network.agents[agent_id]
+                if isinstance(st, dict):
+                    st = agent.Supertype(**st)
+                st._managed = True
+                for value in st.__dict__.values():
+                    if isinstance(value, Sampler) and not any(value is x for x in self._samplers):
+                        self._samplers.append(value)
+                agent.supertype = st
         self.num_steps = num_steps
         self.env_supertype = None
         self.env_type = None

@@ -23,6 +23,7 @@ class FamilyInfo:
     trace_capacity: Callable                 # (env, agents) -> int
     # (env, agent, word[, value]) -> column: state access for a family's non-engine kernel
     fast_column: Optional[Callable] = None
+    supports_supertypes: bool = False
 
 
 REGISTRY: Dict[str, FamilyInfo] = {}

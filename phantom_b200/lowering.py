@@ -154,5 +154,10 @@ def lower(env, exec_mode: str = "auto", auto_reset: bool = False) -> L.PhxSpec:
         raise NotLowerableError(
             f"family '{info.name}' has no kernel for env kind {spec.env_kind}")
 
+    uses_supertypes = bool(getattr(env, "_samplers", None)) or any(
+        getattr(a, "supertype", None) is not None for a in agents)
+    if uses_supertypes and not info.supports_supertypes:
+        raise NotLowerableError(
+            f"family '{info.name}' has no device program for agent supertypes / samplers")
     info.collect(env, agents, spec)
     return spec

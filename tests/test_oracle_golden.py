@@ -184,3 +184,25 @@ def test_object_oracle_matches_dense_goldens(golden_dir):
                              3, state_fn=wl.state)
     for k in ["obs", "reward", "state", "obs_mask", "reward_mask", "all_done"]:
         assert np.array_equal(tr[k][0], g[k][0, 0]), k
+
+
+def test_object_oracle_matches_supply_chain2_golden(golden_dir):
+    """Tutorial-2 env with supertypes: oracle restatement (incl. its UniformFloatSampler) == the
+    reference, both drawing np.random.uniform through the contract stream."""
+    from oracle.workloads import supply_chain2 as wl
+
+    from .generic_parity import assert_oracle_trace_equal
+
+    g = np.load(os.path.join(golden_dir, "supply_chain2_reference.npz"))
+    seed, A, M = int(g["seed"]), g["actions"], g["action_mask"]
+    for e in range(4):
+        streams = {s: rng.StepStream(seed, e, s)
+                   for s in (wl.STREAM_ORDER, wl.STREAM_SAMPLER, wl.STREAM_SHOP_CHOICE)}
+        ws = []
+        with harness.patched_np_uniform(streams[wl.STREAM_SAMPLER]):
+            env = wl.build(po, streams, po.utils.samplers.UniformFloatSampler, enable_tracking=e < 3)
+            tr = harness.run_generic(
+                env, harness.EpisodeClock(list(streams.values())), A[e], M[e], 4, track=e < 3,
+                state_fn=lambda env: (ws.append(wl.weights(env)), wl.state(env))[1])
+        assert_oracle_trace_equal(tr, g, e)
+        assert np.array_equal(np.array(ws).reshape(g["weights"][e].shape), g["weights"][e])
