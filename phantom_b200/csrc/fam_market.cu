@@ -28,6 +28,7 @@ struct MarketProgram {
   // phase; no handler of this market ever answers a message
   static constexpr int PW = 2, NWORDS = 8, VW = 1, ACTCAP = 32, RESPCAP = 1, OBS_DIM = 3,
                        ACT_DIM = 1, Q1CAP = 0;  // 32 agents: tile engine only
+  static constexpr int RECVCAP = 32;  // max messages one agent receives in a round
   static constexpr bool BATCHED = false, HAS_PRE = true, HAS_POST = true;
 
   static int q1_cap(const phx_spec&) { return 0; }

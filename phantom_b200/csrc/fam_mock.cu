@@ -31,6 +31,7 @@ enum { MK_TEST_MESSAGE = 0, MK_REQUEST = 1, MK_RESPONSE = 2 };
 struct MockProgram {
   static constexpr int PW = 1, NWORDS = 5, VW = 0, ACTCAP = 32, RESPCAP = 32, OBS_DIM = 8,
                        ACT_DIM = 1, Q1CAP = 32;
+  static constexpr int RECVCAP = 32;  // max messages one agent receives in a round
   static constexpr bool BATCHED = false, HAS_PRE = false, HAS_POST = false;
 
   static int q1_cap(const phx_spec& s) { return s.n_agents * 4 < 32 ? 32 : 32; }

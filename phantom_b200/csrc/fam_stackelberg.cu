@@ -20,6 +20,7 @@ constexpr int SK_STREAM_VALUE = 2;
 struct StackelbergProgram {
   static constexpr int PW = 1, NWORDS = 4, VW = 0, ACTCAP = 8, RESPCAP = 8, OBS_DIM = 2,
                        ACT_DIM = 1, Q1CAP = 8;
+  static constexpr int RECVCAP = 8;  // max messages one agent receives in a round
   static constexpr bool BATCHED = false, HAS_PRE = true, HAS_POST = false;
 
   static int q1_cap(const phx_spec& s) { return s.n_agents - 1; }  // one message per follower

@@ -633,6 +633,7 @@ struct ScProgram {
                        ACT_DIM = 1;
   static constexpr int SEGCAP = SEGCAP_;
   static constexpr int Q1CAP = SEGCAP_;  // thread-per-env engine: messages in flight per round
+  static constexpr int RECVCAP = SEGCAP_;  // max messages one agent receives in a round
   static constexpr bool BATCHED = false, HAS_PRE = true, HAS_POST = false;
 
   static int q1_cap(const phx_spec& s) { return s.n_agents; }  // <= one message per agent and round

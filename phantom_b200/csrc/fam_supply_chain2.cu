@@ -31,6 +31,7 @@ constexpr int S2_STREAM_ORDER = 0, S2_STREAM_SAMPLER = 3, S2_STREAM_CHOICE = 4;
 struct Sc2Program {
   static constexpr int PW = 1, NWORDS = 6, VW = 0, ACTCAP = 1, RESPCAP = 8, OBS_DIM = 4,
                        ACT_DIM = 1, Q1CAP = 8;
+  static constexpr int RECVCAP = 8;  // max messages one agent receives in a round
   static constexpr bool BATCHED = false, HAS_PRE = true, HAS_POST = false;
 
   static int q1_cap(const phx_spec& s) { return s.n_agents; }
