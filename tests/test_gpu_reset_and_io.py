@@ -1,0 +1,111 @@
+"""a17 / boundary details on the device: masked reset (vector-env auto-reset building block),
+auto-reset inside engine rollouts, state column write-back, host-buffer rollouts and odd batch
+sizes, for every kernel variant."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import vectorised  # noqa: E402
+
+from .generic_parity import assert_batchsteps_equal  # noqa: E402
+
+
+@pytest.mark.parametrize("exec_mode", ["fast", "thread", "queue"])
+def test_masked_reset_only_touches_masked_envs(exec_mode):
+    """phx_reset(env_mask): masked envs restart (clock 0, episode+1, stock 0, sales kept --
+    supply_chain.py:149-150), the others continue untouched; checked against two vectorised
+    oracles stepped in lock step."""
+    import torch
+
+    from phantom_b200 import _lib as L
+    from phantom_b200.envs.supply_chain import SupplyChainEnv
+
+    E, seed = 777, 13  # odd size: partial warps / tiles / blocks
+    env = SupplyChainEnv(num_envs=E, seed=seed, exec_mode=exec_mode)
+    ref = vectorised.SupplyChainVec(E, seed)
+    env.reset_batch(); ref.reset()
+    r = np.random.RandomState(0)
+    for t in range(40):
+        a = r.uniform(0, 100, size=(E, 1, 1)).astype(np.float32)
+        out = env.step_batch(a)
+        want = ref.step(a[:, 0, 0])
+        assert np.array_equal(out.observations.cpu().numpy()[:, 0], want["obs"]), t
+        if t % 7 == 6:
+            mask = r.uniform(size=E) < 0.3
+            obs, om = env.reset_batch(torch.as_tensor(mask))
+            want_obs = ref.reset(mask)
+            got = obs.cpu().numpy()[:, 0]
+            assert np.array_equal(got[mask], want_obs[mask])
+            assert np.array_equal(om.cpu().numpy()[:, 0].astype(bool), mask)
+            assert np.array_equal(env.field(L.FIELD_STEP, np.int32), ref.step_no)
+            assert np.array_equal(env.field(L.FIELD_EPISODE, np.int32), ref.episode)
+    env.check_errors()
+    env.close()
+
+
+@pytest.mark.parametrize("exec_mode", ["thread", "queue"])
+def test_engine_auto_reset_rollout_equals_manual_resets(exec_mode):
+    """PHX_FLAG_AUTO_RESET inside a T-step engine rollout == stepping and resetting by hand
+    (Stackelberg: reward cache cleared, leaders observe the reset, followers do not)."""
+    from phantom_b200.envs.stackelberg_game import StackelbergGameEnv
+
+    E, T, seed = 300, 25, 4
+    A = np.random.RandomState(1).uniform(0, 1, size=(T, E, 4, 1)).astype(np.float32)
+    auto = StackelbergGameEnv(num_envs=E, seed=seed, num_steps=10, auto_reset=True, exec_mode=exec_mode)
+    manual = StackelbergGameEnv(num_envs=E, seed=seed, num_steps=10, exec_mode=exec_mode)
+    auto.reset_batch(); manual.reset_batch()
+    ro = auto.rollout_batch(A)
+    for t in range(T):
+        out = manual.step_batch(A[t])
+        done = bool(out.all_done.cpu().numpy()[0, 1])
+        rew_a, rm_a = ro.rewards[t].cpu().numpy(), ro.reward_mask[t].cpu().numpy()
+        assert np.array_equal(rm_a, out.reward_mask.cpu().numpy()), t
+        assert np.array_equal(rew_a[rm_a == 1], out.rewards.cpu().numpy()[rm_a == 1]), t
+        assert np.array_equal(ro.all_done[t].cpu().numpy(), out.all_done.cpu().numpy()), t
+        if done:
+            obs, om = manual.reset_batch()
+            assert np.array_equal(ro.obs_mask[t].cpu().numpy(), om.cpu().numpy()), t
+            sel = om.cpu().numpy().astype(bool)
+            assert np.array_equal(ro.observations[t].cpu().numpy()[sel], obs.cpu().numpy()[sel]), t
+        else:
+            sel = out.obs_mask.cpu().numpy().astype(bool)
+            assert np.array_equal(ro.obs_mask[t].cpu().numpy().astype(bool), sel), t
+            assert np.array_equal(ro.observations[t].cpu().numpy()[sel], out.observations.cpu().numpy()[sel]), t
+    auto.close(); manual.close()
+
+
+def test_set_field_roundtrip_and_effect():
+    """phx_set_field: writing a state column changes the dynamics accordingly."""
+    from phantom_b200.envs.supply_chain import SupplyChainEnv
+
+    for mode in ("fast", "thread"):
+        env = SupplyChainEnv(num_envs=16, seed=2, exec_mode=mode)
+        env.reset_batch()
+        shop = env.agents["SHOP"]
+        shop.stock = np.arange(16) * 5
+        assert np.array_equal(np.asarray(shop.stock), np.arange(16) * 5)
+        out = env.step_batch(np.zeros((16, 1, 1), np.float32))
+        stock_after = np.asarray(shop.stock)
+        assert np.array_equal(stock_after, np.arange(16) * 5 - np.asarray(shop.sales))
+        assert np.array_equal(out.observations.cpu().numpy()[:, 0, 0], (stock_after / 100).astype(np.float32))
+        env.close()
+
+
+def test_rollout_host_for_engine_families():
+    """phx_rollout_host (host buffers, unchunked path) on the generic engine == device path."""
+    from phantom_b200 import BatchStep
+    from phantom_b200.envs.stackelberg_game import StackelbergGameEnv
+
+    import torch
+
+    E, T, seed = 1500, 12, 8
+    A = np.random.RandomState(3).uniform(0, 1, size=(T, E, 4, 1)).astype(np.float32)
+    a, b = StackelbergGameEnv(num_envs=E, seed=seed), StackelbergGameEnv(num_envs=E, seed=seed)
+    a.reset_batch(); b.reset_batch()
+    dev = a.rollout_batch(A)
+    host = b.rollout_host(A)
+    hb = BatchStep(*[torch.as_tensor(host[k]).cuda() for k in
+                     ("observations", "obs_mask", "rewards", "reward_mask", "terminations", "truncations", "all_done")])
+    assert_batchsteps_equal(dev, hb)
+    a.close(); b.close()
