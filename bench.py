@@ -210,6 +210,46 @@ def run_ours(args):
         ms = float(t.item())
     env.check_errors()
 
+    # ---- single-step API (SURVEY 8(d) asks for both): T = 1 phx_step calls, 100 of them
+    # captured into one CUDA graph (a trainer that steps every env once per policy forward),
+    # lean outputs like the rollout above; each launch moves 4.7 MB, so this leg is
+    # launch/latency-bound and L2-resident by construction -- reported, not the headline
+    single = None
+    if rank == 0:
+        a1, o1 = acts[0], outs[0]
+        side = torch.cuda.Stream(dev)
+
+        def step_once(t, st):
+            L.check(L.lib.phx_step(env._handle, a1[t].data_ptr(), None,
+                                   o1.observations[t].data_ptr(), None, o1.rewards[t].data_ptr(),
+                                   None, None, None, o1.all_done[t].data_ptr(), st))
+
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for t in range(3):
+                step_once(t, side.cuda_stream)
+        side.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            for t in range(T):
+                step_once(t, torch.cuda.current_stream(dev).cuda_stream)
+        for _ in range(3):
+            graph.replay()
+        torch.cuda.synchronize()
+        reps = 50
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(reps):
+            graph.replay()
+        g1.record()
+        torch.cuda.synchronize()
+        us = g0.elapsed_time(g1) * 1e3 / (reps * T)
+        single = {"api": "phx_step, T=1, 100 launches per CUDA graph", "us_per_launch": us,
+                  "value": E / (us * 1e-6), "unit": "env-steps/s",
+                  "bytes_per_launch": E * (B_IO + B_STATE)}
+        env.check_errors()
+        env.reset_batch()
+
     # ---- e2e: same metric through the host-buffer C-ABI call (pinned host memory, H2D of
     # the actions and D2H of obs / reward / all_done inside the timed region)
     e2e_steps = max(3, min(args.steps, 12))
@@ -272,7 +312,11 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "api": "phx_rollout_host (pinned host buffers)"},
-            "gpu_launches": args.steps + args.warmup + e2e_steps + 2,
+            "single_step": single,
+            # kernels of ours inside the device-timed region (one sc_fast_kernel per bench step);
+            # the e2e region launches one kernel per pipeline chunk (8 per call)
+            "gpu_launches": args.steps,
+            "gpu_launches_e2e": e2e_steps * 8,
             "clocks": clocks.summary(),
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PHX_ABI_VERSION 1
+#define PHX_ABI_VERSION 2
 
 #define PHX_MAX_AGENTS 128  /* agent slots per env                                   */
 #define PHX_MAX_TYPES 16    /* payload types per env class                           */
@@ -40,6 +40,7 @@ extern "C" {
 #define PHX_MAX_PARAMS 16
 #define PHX_TRACE_WORDS 4   /* one traced message = 4 x int32 (see phx_get_trace)    */
 #define PHX_MAX_CODEC_OPS 6 /* encoder ops per agent (Chained/Dict encoder composition)*/
+#define PHX_MAX_BASE_CONNECTIONS 528 /* StochasticNetwork base connections (32*33/2)     */
 
 typedef enum phx_status {
   PHX_OK = 0,
@@ -93,15 +94,26 @@ enum {
   PHX_FLAG_IGNORE_CONNECTION_ERRORS = 1 << 0, /* Network(ignore_connection_errors=True)   */
   PHX_FLAG_NO_PAYLOAD_CHECKS = 1 << 1,        /* Network(enforce_msg_payload_checks=False)*/
   PHX_FLAG_TRACK_MESSAGES = 1 << 2,           /* BatchResolver(enable_tracking=True)      */
-  PHX_FLAG_AUTO_RESET = 1 << 3                /* reset an env in the step that ends its
+  PHX_FLAG_AUTO_RESET = 1 << 3,               /* reset an env in the step that ends its
                                                  episode; obs then holds the reset obs   */
+  PHX_FLAG_STOCHASTIC_NETWORK = 1 << 4,       /* StochasticNetwork: every env resamples its
+                                                 edges from base_* at reset
+                                                 (phantom/network.py:439-453); <= 32 agents */
+  PHX_FLAG_SHUFFLE_BATCHES = 1 << 5           /* BatchResolver(shuffle_batches=True),
+                                                 phantom/resolvers.py:150-151              */
 };
 
 typedef struct phx_stage {
   uint32_t acting[PHX_MASK_WORDS];   /* FSMStage.acting_agents as a slot bitmask         */
   uint32_t rewarded[PHX_MASK_WORDS]; /* FSMStage.rewarded_agents                         */
   int32_t rewarded_is_none;          /* rewarded_agents is None (phantom/fsm.py:315-317) */
-  int32_t next_stage;                /* the single next stage of a handler-less stage    */
+  int32_t next_stage;                /* next_stages[0]: the next stage of a handler-less
+                                        stage (phantom/fsm.py:284-292)                   */
+  int32_t handler;                   /* 0 = no env handler; > 0 = id of the family's device
+                                        stage handler (phantom/fsm.py:294-302)           */
+  uint32_t next_allowed;             /* FSMStage.next_stages as a stage bitmask; a handler
+                                        returning a stage outside it faults with
+                                        PHX_FAULT_BAD_TRANSITION (phantom/fsm.py:304-307) */
 } phx_stage;
 
 /* Flat description of one env class, lowered from the Python objects
@@ -146,6 +158,14 @@ typedef struct phx_spec {
    * evaluated in order into the agent's obs row; 0 terminates the list. */
   int32_t agent_codec_op[PHX_MAX_AGENTS][PHX_MAX_CODEC_OPS];
   float agent_codec_val[PHX_MAX_AGENTS][PHX_MAX_CODEC_OPS];
+
+  /* PHX_FLAG_STOCHASTIC_NETWORK: StochasticNetwork._base_connections in insertion order
+   * (phantom/network.py:379-399).  At every reset connection c of env e exists iff
+   * uniform01(stream 5, step 0, idx c) < base_rate[c]  (np.random.random() < rate). */
+  int32_t n_base_connections;
+  uint8_t base_u[PHX_MAX_BASE_CONNECTIONS];
+  uint8_t base_v[PHX_MAX_BASE_CONNECTIONS];
+  double base_rate[PHX_MAX_BASE_CONNECTIONS];
 } phx_spec;
 
 typedef struct phx_env phx_env; /* opaque */
@@ -160,6 +180,8 @@ typedef enum phx_field {
                                slots (only strategic slots are ever set), W words   */
   PHX_FIELD_TRUNCATED = 4,  /* uint32[E,W]                                           */
   PHX_FIELD_ERROR = 5,      /* uint32[E]   sticky fault word                         */
+  PHX_FIELD_ADJACENCY = 6,  /* uint32[E,n_agents] per-env adjacency rows of a
+                               StochasticNetwork (bit r of row s: edge s -> r)       */
   PHX_FIELD_FAMILY = 16
 } phx_field;
 

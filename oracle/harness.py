@@ -56,6 +56,64 @@ def patched_np_uniform(stream: rng.StepStream):
         np.random.uniform = orig
 
 
+@contextlib.contextmanager
+def patched_np_random(stream: rng.StepStream):
+    """Route `np.random.random()` (StochasticNetwork.add_connection / resample_connectivity,
+    phantom/network.py:389,446) to the contract stream: the c-th call after the stream's
+    begin() -- i.e. the c-th base connection of this reset -- gets draw idx c as a float64
+    d24 * 2^-24."""
+    orig = np.random.random
+    np.random.random = lambda size=None: stream.next_d24() / 16777216.0
+    try:
+        yield
+    finally:
+        np.random.random = orig
+
+
+def contract_shuffle(seed: int, env: int, episode: int, step: int, recv_slot: int, k: int,
+                     items: list) -> None:
+    """The contract's replacement of `np.random.shuffle(batch)` (phantom/resolvers.py:151):
+    Fisher-Yates from the back, as numpy's legacy shuffle walks it --
+        for i = n-1 .. 1:  j = randint(i + 1);  swap(items[i], items[j])
+    with randint(m) = (d24 * m) >> 24 and the draw taken from
+        stream = 0x100 + receiver slot,  idx = k * 256 + (n - 1 - i)
+    where k counts the batches this receiver has handled in this env step (one per round in
+    which it had mail).  Keyed by receiver so that all receivers of a round can shuffle in
+    parallel on the device."""
+    n = len(items)
+    assert n <= 256, "contract_shuffle: batches of at most 256 messages"
+    for i in range(n - 1, 0, -1):
+        d = rng.d24(seed, env, episode, step, 0x100 + recv_slot, k * 256 + (n - 1 - i))
+        j = rng.randint(i + 1, d)
+        items[i], items[j] = items[j], items[i]
+
+
+@contextlib.contextmanager
+def patched_np_shuffle(seed: int, env_index: int, clock: "EpisodeClock", env, slot_of):
+    """Route `np.random.shuffle(batch)` inside BatchResolver.resolve to contract_shuffle.
+    The receiver is read off the batch; the per-receiver batch counter restarts whenever the
+    env's (episode, step) coordinate changes."""
+    orig = np.random.shuffle
+    seen = {"key": None, "count": {}}
+
+    def shuffle(batch):
+        key = (clock.episode, env.current_step)
+        if seen["key"] != key:
+            seen["key"], seen["count"] = key, {}
+        if len(batch) == 0:
+            return
+        r = slot_of[batch[0].receiver_id]
+        k = seen["count"].get(r, 0)
+        seen["count"][r] = k + 1
+        contract_shuffle(seed, env_index, clock.episode, env.current_step, r, k, batch)
+
+    np.random.shuffle = shuffle
+    try:
+        yield
+    finally:
+        np.random.shuffle = orig
+
+
 def tracked_to_rows(tracked, slot_of: Dict[Any, int], type_of: Callable[[Any], int],
                     value_of: Callable[[Any], Sequence[float]]) -> np.ndarray:
     """Flatten Resolver.tracked_messages to rows (sender_slot, recv_slot, type, v0, v1)."""

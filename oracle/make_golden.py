@@ -198,6 +198,68 @@ def gen_supply_chain2_reference() -> None:
     print("supply_chain2_reference.npz:", {k: v.shape for k, v in out.items()})
 
 
+def gen_shuffle_and_stochastic_reference() -> None:
+    """SURVEY 8(f) rows 2 and 4 on the UNMODIFIED reference:
+    market_shuffle_reference.npz       C3 market with BatchResolver(shuffle_batches=True)
+    supply_chain2_stochastic_reference.npz   tutorial-2 env on a StochasticNetwork
+                                       (ignore_connection_errors) with shuffled batches;
+                                       records every episode's resampled graph."""
+    from .workloads import market
+    from .workloads import supply_chain2 as wl
+
+    ref = ref_shim.import_reference()
+    # ---- market + shuffle
+    seed, n_env, n_ep, T, S = 20261022, 4, 2, 99, market.N_MAKERS + market.N_TAKERS
+    actions, mask = generic_actions(n_env, n_ep, T, S, discrete_from=market.N_MAKERS, seed=23)
+    per_env = []
+    for e in range(n_env):
+        st = rng.StepStream(seed, e, market.STREAM_TAKER_VALUE)
+        env = market.build(ref, st, enable_tracking=e < 1, shuffle_batches=True)
+        clock = harness.EpisodeClock([st])
+        slot_of = {aid: i for i, aid in enumerate(env.agent_ids)}
+        with harness.patched_np_shuffle(seed, e, clock, env, slot_of):
+            per_env.append(harness.run_generic(env, clock, actions[e], mask[e], 3,
+                                               track=e < 1, state_fn=market_state))
+        if e >= 1:
+            per_env[-1]["messages"] = []
+    out = pack_generic(per_env, actions, mask, seed, 1, MESSAGE_TYPE_IDS)
+    np.savez_compressed(os.path.join(GOLDEN, "market_shuffle_reference.npz"), **out)
+    print("market_shuffle_reference.npz:", {k: v.shape for k, v in out.items()})
+
+    # ---- supply chain 2 on a stochastic network, with and without shuffled batches
+    for shuffle, name in ((True, "supply_chain2_stochastic_reference.npz"),
+                          (False, "supply_chain2_stochastic_plain_reference.npz")):
+        seed, n_env, n_ep, T, S = 20261023, 12, 3, 40, wl.N_SHOPS
+        rates = (0.75, 0.625)
+        r = np.random.RandomState(29)
+        actions = r.uniform(0, 100, size=(n_env, n_ep, T, S, 1)).astype(np.float32)
+        mask = (r.uniform(size=(n_env, n_ep, T, S)) > 0.08).astype(np.uint8)
+        per_env, adjs = [], []
+        for e in range(n_env):
+            streams = {s: rng.StepStream(seed, e, s)
+                       for s in (wl.STREAM_ORDER, wl.STREAM_SAMPLER, wl.STREAM_SHOP_CHOICE,
+                                 wl.STREAM_CONNECTIVITY)}
+            adj = []
+            with harness.patched_np_uniform(streams[wl.STREAM_SAMPLER]), \
+                    harness.patched_np_random(streams[wl.STREAM_CONNECTIVITY]):
+                env = wl.build(ref, streams, ref.utils.samplers.UniformFloatSampler, num_steps=T,
+                               enable_tracking=e < 4, rates=rates, shuffle_batches=shuffle)
+                clock = harness.EpisodeClock(list(streams.values()))
+                slot_of = {aid: i for i, aid in enumerate(env.agent_ids)}
+                with harness.patched_np_shuffle(seed, e, clock, env, slot_of):
+                    per_env.append(harness.run_generic(
+                        env, clock, actions[e], mask[e], 4, track=e < 4,
+                        state_fn=lambda env: (adj.append(wl.adjacency(env)), wl.state(env))[1]))
+            if e >= 4:
+                per_env[-1]["messages"] = []
+            adjs.append(np.array(adj).reshape(n_ep, T, 8, 8)[:, 0])  # the graph of each episode
+        out = pack_generic(per_env, actions, mask, seed, 4, wl.MESSAGE_TYPE_IDS)
+        out["adjacency"] = np.stack(adjs)
+        out["rates"] = np.array(rates)
+        np.savez_compressed(os.path.join(GOLDEN, name), **out)
+        print(name, {k: v.shape for k, v in out.items()}, "mean degree", out["adjacency"].mean())
+
+
 def main() -> int:
     if not ref_shim.reference_available():
         print("reference not available")
@@ -208,6 +270,7 @@ def main() -> int:
     gen_stackelberg_reference()
     gen_dense_reference()
     gen_supply_chain2_reference()
+    gen_shuffle_and_stochastic_reference()
     return 0
 
 

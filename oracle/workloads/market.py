@@ -38,7 +38,7 @@ TYPE_QUOTE, TYPE_ORDER, TYPE_FILL = 0, 1, 2
 
 
 def build(ph, stream, *, n_makers: int = N_MAKERS, n_takers: int = N_TAKERS,
-          num_steps: int = 99, enable_tracking: bool = False):
+          num_steps: int = 99, enable_tracking: bool = False, shuffle_batches: bool = False):
     """`stream`: oracle.rng.StepStream for STREAM_TAKER_VALUE (taker valuations at reset)."""
     from ..phantom_oracle.spaces import Box, Discrete
 
@@ -191,7 +191,8 @@ def build(ph, stream, *, n_makers: int = N_MAKERS, n_takers: int = N_TAKERS,
 
     agents = [MakerAgent(m) for m in maker_ids] + [TakerAgent(t) for t in taker_ids]
     agents.append(ClearingAgent("CLEARING"))
-    network = ph.Network(agents, ph.resolvers.BatchResolver(enable_tracking=enable_tracking))
+    network = ph.Network(agents, ph.resolvers.BatchResolver(enable_tracking=enable_tracking,
+                                                            shuffle_batches=shuffle_batches))
     network.add_connections_between(maker_ids, taker_ids)
     network.add_connections_between(["CLEARING"], maker_ids + taker_ids)
     everyone = maker_ids + taker_ids

@@ -17,6 +17,14 @@ literal "8 agents/env" reading of BASELINE config C2.
 RNG contract: stream 0 order size (idx = customer ordinal), stream 4 shop choice (idx = customer
 ordinal), stream 3 samplers at reset (step 0, idx = position in env._samplers).
 Device twin: phantom_b200/csrc/fam_supply_chain2.cu.
+
+Options exercising the "next" rows of SURVEY 8(f):
+  rates=(warehouse_rate, customer_rate)  builds a StochasticNetwork(ignore_connection_errors=
+      True) whose shop-warehouse / shop-customer connections exist with those probabilities,
+      re-drawn at every reset (phantom/network.py:340-453); stream 5 (step 0, idx = position in
+      _base_connections) replaces np.random.random().
+  shuffle_batches=True  BatchResolver(shuffle_batches=True) (phantom/resolvers.py:150-151);
+      np.random.shuffle is replaced by the contract's Fisher-Yates (oracle/harness.py).
 """
 from __future__ import annotations
 
@@ -31,8 +39,12 @@ STREAM_ORDER, STREAM_SAMPLER, STREAM_SHOP_CHOICE = 0, 3, 4
 MESSAGE_TYPE_IDS = {"OrderRequest": 0, "OrderResponse": 1, "StockRequest": 2, "StockResponse": 3}
 
 
+STREAM_CONNECTIVITY = 5
+
+
 def build(ph, streams, sampler_factory, *, n_shops: int = N_SHOPS, n_customers: int = N_CUSTOMERS,
-          num_steps: int = 100, enable_tracking: bool = False):
+          num_steps: int = 100, enable_tracking: bool = False, rates=None,
+          shuffle_batches: bool = False):
     """streams: {STREAM_ORDER: StepStream, STREAM_SHOP_CHOICE: StepStream};
     sampler_factory(low, high) -> a Sampler of the API in use whose sample() follows the
     contract (oracle: ContractUniformFloatSampler; reference: its own UniformFloatSampler with
@@ -129,9 +141,16 @@ def build(ph, streams, sampler_factory, *, n_shops: int = N_SHOPS, n_customers: 
 
     agents = [FactoryAgent("WAREHOUSE")] + [ShopAgent(s, "WAREHOUSE") for s in shop_ids]
     agents += [CustomerAgent(c, shop_ids) for c in customer_ids]
-    network = ph.Network(agents, ph.resolvers.BatchResolver(enable_tracking=enable_tracking))
-    network.add_connections_between(shop_ids, ["WAREHOUSE"])
-    network.add_connections_between(shop_ids, customer_ids)
+    resolver = ph.resolvers.BatchResolver(enable_tracking=enable_tracking,
+                                          shuffle_batches=shuffle_batches)
+    if rates is None:
+        network = ph.Network(agents, resolver)
+        network.add_connections_between(shop_ids, ["WAREHOUSE"])
+        network.add_connections_between(shop_ids, customer_ids)
+    else:
+        network = ph.StochasticNetwork(agents, resolver, ignore_connection_errors=True)
+        network.add_connections_between(shop_ids, ["WAREHOUSE"], rate=rates[0])
+        network.add_connections_between(shop_ids, customer_ids, rate=rates[1])
     supertypes = {s: ShopAgent.Supertype(sampler_factory(0.0, MAX_EXCESS_STOCK_WEIGHT))
                   for s in shop_ids}
     env = ph.PhantomEnv(num_steps=num_steps, network=network, agent_supertypes=supertypes)
@@ -145,6 +164,13 @@ def state(env):
         a = env.agents[s]
         rows.append([a.stock, a.sales, a.missed_sales, getattr(a, "delivered_stock", 0)])
     return np.array(rows, np.int64)
+
+
+def adjacency(env):
+    """Current graph as uint8 [n, n] in agent order (nx.DiGraph or the oracle's _DiGraph)."""
+    ids = list(env.agent_ids)
+    g = env.network.graph
+    return np.array([[1 if g.has_edge(u, v) else 0 for v in ids] for u in ids], np.uint8)
 
 
 def weights(env):

@@ -19,7 +19,7 @@ from .env import BatchStep, PhantomEnv
 from .errors import DeviceOnlyError, NotLowerableError
 from .fsm import FiniteStateMachineEnv, FSMStage
 from .message import Message, MsgPayload, msg_payload
-from .network import Network, NetworkError
+from .network import Network, NetworkError, StochasticNetwork
 from .reward_functions import RewardFunction
 from .stackelberg import StackelbergEnv
 from .supertype import Supertype

@@ -20,6 +20,8 @@ PHX_MASK_WORDS = 4
 PHX_MAX_PARAMS = 16
 PHX_TRACE_WORDS = 4
 PHX_MAX_CODEC_OPS = 6
+PHX_MAX_BASE_CONNECTIONS = 528
+PHX_ABI_VERSION = 2
 
 # phx_status
 PHX_OK, PHX_ERR_INVALID, PHX_ERR_CUDA, PHX_ERR_UNSUPPORTED, PHX_ERR_NO_DEVICE = 0, -1, -2, -3, -4
@@ -36,8 +38,10 @@ EXEC_AUTO, EXEC_QUEUE, EXEC_FAST, EXEC_THREAD = 0, 1, 2, 3
 EXEC_MODES = {"auto": EXEC_AUTO, "queue": EXEC_QUEUE, "fast": EXEC_FAST, "thread": EXEC_THREAD}
 # flags
 FLAG_IGNORE_CONNECTION_ERRORS, FLAG_NO_PAYLOAD_CHECKS, FLAG_TRACK_MESSAGES, FLAG_AUTO_RESET = 1, 2, 4, 8
+FLAG_STOCHASTIC_NETWORK, FLAG_SHUFFLE_BATCHES = 16, 32
 # phx_field
 FIELD_STEP, FIELD_EPISODE, FIELD_STAGE, FIELD_TERMINATED, FIELD_TRUNCATED, FIELD_ERROR = range(6)
+FIELD_ADJACENCY = 6
 FIELD_FAMILY = 16
 
 _MaskWords = C.c_uint32 * PHX_MASK_WORDS
@@ -49,6 +53,8 @@ class PhxStage(C.Structure):
         ("rewarded", _MaskWords),
         ("rewarded_is_none", C.c_int32),
         ("next_stage", C.c_int32),
+        ("handler", C.c_int32),
+        ("next_allowed", C.c_uint32),
     ]
 
 
@@ -83,6 +89,10 @@ class PhxSpec(C.Structure):
         ("agent_fparam", (C.c_double * 2) * PHX_MAX_AGENTS),
         ("agent_codec_op", (C.c_int32 * PHX_MAX_CODEC_OPS) * PHX_MAX_AGENTS),
         ("agent_codec_val", (C.c_float * PHX_MAX_CODEC_OPS) * PHX_MAX_AGENTS),
+        ("n_base_connections", C.c_int32),
+        ("base_u", C.c_uint8 * PHX_MAX_BASE_CONNECTIONS),
+        ("base_v", C.c_uint8 * PHX_MAX_BASE_CONNECTIONS),
+        ("base_rate", C.c_double * PHX_MAX_BASE_CONNECTIONS),
     ]
 
 

@@ -339,6 +339,10 @@ class DenseFamily final : public Family {
     PHX_REQUIRE(!(s.flags & PHX_FLAG_IGNORE_CONNECTION_ERRORS), PHX_ERR_UNSUPPORTED,
                 "dense family: ignore_connection_errors has no effect (agents only address "
                 "neighbours) and is not accepted");
+    PHX_REQUIRE(!(s.flags & (PHX_FLAG_STOCHASTIC_NETWORK | PHX_FLAG_SHUFFLE_BATCHES)),
+                PHX_ERR_UNSUPPORTED,
+                "dense family: StochasticNetwork / shuffle_batches are served by the queue engine "
+                "(<= 32 agents) only");
     std::memset(&dsp, 0, sizeof(dsp));
     dsp.E = E;
     dsp.n = s.n_agents;

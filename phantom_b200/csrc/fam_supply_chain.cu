@@ -415,7 +415,8 @@ class SupplyChainFast final : public Family {
                 PHX_ERR_INVALID, "supply-chain family: max_order / max_stock out of range");
     PHX_REQUIRE(is_canonical(s), PHX_ERR_UNSUPPORTED,
                 "PHX_EXEC_FAST needs the canonical supply-chain layout "
-                "[ShopAgent, FactoryAgent, CustomerAgent x N] with N <= 30");
+                "[ShopAgent, FactoryAgent, CustomerAgent x N] with N <= 30, a plain Network and "
+                "no shuffle_batches");
     PHX_CUDA(cudaMalloc(&d_shop, sizeof(int4) * (size_t)E));
     sc_init_kernel<<<(E + 255) / 256, 256>>>(E, d_hdr, d_shop);
     PHX_CUDA(cudaGetLastError());
@@ -424,6 +425,8 @@ class SupplyChainFast final : public Family {
   }
 
   static bool is_canonical(const phx_spec& s) {
+    // the static schedule assumes one graph for all envs and push-order batches
+    if (s.flags & (PHX_FLAG_STOCHASTIC_NETWORK | PHX_FLAG_SHUFFLE_BATCHES)) return false;
     if (s.n_agents < 3 || s.n_agents > 2 + SC_MAX_CUSTOMERS) return false;
     if (s.agent_kind[0] != SC_SHOP || s.agent_kind[1] != SC_FACTORY) return false;
     for (int i = 2; i < s.n_agents; ++i)

@@ -82,7 +82,8 @@ int32_t Family::field_ptr(int32_t field, int32_t index, void** p, size_t* bytes)
     default:
       break;
   }
-  if (field >= PHX_FIELD_FAMILY) return family_field(field, index, p, bytes);
+  if (field >= PHX_FIELD_FAMILY || field == PHX_FIELD_ADJACENCY)
+    return family_field(field, index, p, bytes);
   set_error("unknown field id " + std::to_string(field));
   return PHX_ERR_INVALID;
 }
@@ -147,6 +148,12 @@ static int32_t check_spec(const phx_spec* s) {
                 "n_stages out of range");
     PHX_REQUIRE(s->initial_stage >= 0 && s->initial_stage < s->n_stages, PHX_ERR_INVALID,
                 "initial_stage out of range");
+  }
+  if (s->flags & PHX_FLAG_STOCHASTIC_NETWORK) {
+    PHX_REQUIRE(s->n_agents <= 32, PHX_ERR_UNSUPPORTED,
+                "StochasticNetwork is implemented by the queue engine: at most 32 agents per env");
+    PHX_REQUIRE(s->n_base_connections >= 0 && s->n_base_connections <= PHX_MAX_BASE_CONNECTIONS,
+                PHX_ERR_INVALID, "n_base_connections out of range");
   }
   return PHX_OK;
 }

@@ -166,10 +166,37 @@ struct EngineArgs {
   uint32_t* reward_none;// [E]      bit slot: cached reward is None
   float* obs_cache;     // [E][G][O] FSM `_observations` (by slot)
   uint32_t* obs_cached; // [E]      bit slot: an obs is cached
+  uint32_t* adj_env;    // [E][G]   StochasticNetwork: per-env adjacency rows (nullptr otherwise)
+  const uint2* base_conn;  // [n_base] {u | v << 8, ceil(rate * 2^24)} in insertion order
+  int32_t n_base;
   StepIO io;
   FaultSink faults;
   TraceSink trace;
 };
+
+// StochasticNetwork.resample_connectivity (network.py:439-448): base connection c of an env
+// exists for this episode iff np.random.random() < rate, i.e. under the RNG contract
+// d24(stream 5, step 0, idx c) * 2^-24 < rate  <=>  d24 < ceil(rate * 2^24) (integer compare,
+// threshold precomputed on the host).  Edges are always added in both directions, so the row
+// of a slot is also its column.
+constexpr uint32_t RNG_STREAM_CONNECTIVITY = 5;
+
+__device__ __forceinline__ bool base_connection_exists(uint64_t seed, uint32_t env_id,
+                                                        uint32_t episode, int c, uint32_t thr) {
+  return (rng_d24_hi(seed, env_id, episode, 0u, RNG_STREAM_CONNECTIVITY, (uint32_t)c) >> 8) < thr;
+}
+
+__device__ inline uint32_t resample_adj_row(uint64_t seed, const uint2* base, int n_base,
+                                            uint32_t env_id, uint32_t episode, int slot) {
+  uint32_t row = 0;
+  for (int c = 0; c < n_base; ++c) {
+    const uint2 bc = base[c];
+    const int u = bc.x & 0xFF, v = (bc.x >> 8) & 0xFF;
+    if (u != slot && v != slot) continue;
+    if (base_connection_exists(seed, env_id, episode, c, bc.y)) row |= 1u << (u == slot ? v : u);
+  }
+  return row;
+}
 
 __device__ __forceinline__ uint32_t tile_mask(int G) {
   return G >= 32 ? 0xFFFFFFFFu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
@@ -196,6 +223,44 @@ struct BlockSmem {
   TileSmem<P, G> tiles[ENGINE_BLOCK / G];
 };
 
+// BatchResolver(shuffle_batches=True), resolvers.py:146-151: the batch is first reduced to the
+// messages whose edge still exists, then shuffled.  Contract replacement of
+// np.random.shuffle (oracle/harness.py contract_shuffle): Fisher-Yates from the back,
+//   for i = n-1 .. 1:  j = randint(i + 1);  swap(list[i], list[j])
+// draws from stream 0x100 + receiver slot, idx = k_batch * 256 + (n - 1 - i), where k_batch
+// counts the non-empty batches this receiver has shuffled in this env step.  Keyed by receiver,
+// so all receiver lanes shuffle concurrently.  Returns the live count.
+__device__ inline int shuffle_batch(const Ctx& ctx, uint16_t* list, int n, int& k_batch) {
+  int live = 0;
+  for (int j = 0; j < n; ++j) {
+    const uint16_t ent = list[j];
+    if ((ctx.in_mask >> (ent & 0xFF)) & 1u) list[live++] = ent;
+  }
+  if (live == 0) return 0;
+  const uint32_t stream = 0x100u + (uint32_t)ctx.slot;
+  const uint32_t idx0 = (uint32_t)k_batch * 256u;
+  Philox4 blk{};
+  uint32_t blk_id = 0xFFFFFFFFu;
+  for (int i = live - 1; i > 0; --i) {
+    const uint32_t idx = idx0 + (uint32_t)(live - 1 - i);
+    if (idx / 5u != blk_id) {
+      blk_id = idx / 5u;
+      blk = rng_block(ctx.spec->seed, ctx.env_id, ctx.episode, (uint32_t)ctx.step, stream, blk_id);
+    }
+    const uint32_t sl = idx % 5u;
+    uint32_t d = rng_slot_hi(blk, 4);
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (sl == (uint32_t)q) d = rng_slot_hi(blk, q);
+    const int j = rng_randint(d, (uint32_t)(i + 1));
+    const uint16_t t = list[i];
+    list[i] = list[j];
+    list[j] = t;
+  }
+  ++k_batch;
+  return live;
+}
+
 // One resolver round (resolvers.py:137-158).
 //  1. The tile partitions the current queue by receiver with a STABLE counting sort: segments
 //     are visited in global push order; the lanes take one entry each, `__match_any_sync`
@@ -212,8 +277,9 @@ template <class P, int G, bool TRACK, class QC, class QN>
 __device__ __forceinline__ int engine_round(const EngineArgs<P>& a, const Ctx& ctx, int* st,
                                             bool has_ctx, QC& qc, QN& qn, TileSmem<P, G>& ts,
                                             int round, uint32_t tmask, uint32_t& fault_key,
-                                            int& traced, int e, bool trace_lane) {
+                                            int& traced, int e, bool trace_lane, int& k_batch) {
   constexpr int INF = 0x7FFFFFFF;
+  const bool shuffle = (ctx.spec->flags & PHX_FLAG_SHUFFLE_BATCHES) != 0;
   const int slot = ctx.slot;
   const int lane = threadIdx.x & 31;
   const uint32_t below = (1u << lane) - 1u;
@@ -264,7 +330,8 @@ __device__ __forceinline__ int engine_round(const EngineArgs<P>& a, const Ctx& c
     first = first_idx[slot];
     if (has_ctx) {  // done agents: mail dropped silently (resolvers.py:143-144)
       if constexpr (P::BATCHED) P::batch_begin(ctx, st);
-      const int n_mine = ts.rcnt[slot];
+      int n_mine = ts.rcnt[slot];
+      if (shuffle) n_mine = shuffle_batch(ctx, &ts.sorted[slot][0], n_mine, k_batch);
       for (int j = 0; j < n_mine; ++j) {
         const int ent = ts.sorted[slot][j];
         const int seg = ent & 0xFF, k = ent >> 8;
@@ -286,6 +353,8 @@ __device__ __forceinline__ int engine_round(const EngineArgs<P>& a, const Ctx& c
     if constexpr (P::BATCHED) {
       if (has_ctx) P::batch_begin(ctx, st);
     }
+    int n_mine = 0;  // shuffle only: the batch is collected first, handled after the shuffle
+    bool overflow = false;
     for (int si = 0; si < nseg; ++si) {
       const int seg = qc.order[si];
       const int c = qc.cnt[seg];
@@ -295,12 +364,33 @@ __device__ __forceinline__ int engine_round(const EngineArgs<P>& a, const Ctx& c
         if (first == INF) first = pos;  // first-arrival position of this receiver
         if (!has_ctx) continue;         // done agent: mail dropped (resolvers.py:143-144)
         if (!((ctx.in_mask >> seg) & 1u)) continue;  // delivery-time edge filter (:146-148)
+        if (shuffle) {
+          if (n_mine < P::RECVCAP) ts.sorted[slot][n_mine++] = (uint16_t)(seg | (k << 8));
+          else overflow = true;
+          continue;
+        }
         Msg m;
         m.sender = seg;
         m.type = (int)((hd >> 16) & 0xFFu);
         m.p[0] = qc.pay[0][k][seg];
         m.p[1] = P::PW > 1 ? qc.pay[P::PW > 1 ? 1 : 0][k][seg] : 0;
         if (!P::handle(ctx, st, m, resp)) bad_type = true;  // agents.py:140-143
+      }
+    }
+    if (shuffle) {
+      if (overflow)
+        fault_key = min(fault_key, ((uint32_t)(round + 1) << 16) | ((uint32_t)slot << 8) |
+                                       PHX_FAULT_QUEUE_OVERFLOW);
+      n_mine = shuffle_batch(ctx, &ts.sorted[slot][0], n_mine, k_batch);
+      for (int j = 0; j < n_mine; ++j) {
+        const int ent = ts.sorted[slot][j];
+        const int seg = ent & 0xFF, k = ent >> 8;
+        Msg m;
+        m.sender = seg;
+        m.type = (int)((qc.head[k][seg] >> 16) & 0xFFu);
+        m.p[0] = qc.pay[0][k][seg];
+        m.p[1] = P::PW > 1 ? qc.pay[P::PW > 1 ? 1 : 0][k][seg] : 0;
+        if (!P::handle(ctx, st, m, resp)) bad_type = true;
       }
     }
     if constexpr (P::BATCHED) {
@@ -407,6 +497,7 @@ __global__ void __launch_bounds__(ENGINE_BLOCK) engine_step_kernel(const EngineA
     for (int s = 0; s < sp.n_agents; ++s) in |= ((sp.adj[s] >> slot) & 1u) << s;
     ctx.in_mask = in;
   }
+  if (a.adj_env) ctx.out_mask = ctx.in_mask = a.adj_env[(size_t)e * G + slot];
 
   // actions are prefetched one step ahead (a step of this kernel is far longer than the HBM
   // latency), so the acting phase never waits on the load
@@ -489,6 +580,7 @@ __global__ void __launch_bounds__(ENGINE_BLOCK) engine_step_kernel(const EngineA
     if (has_ctx) P::pre(ctx, st);
 
     // ---- BatchResolver.resolve (resolvers.py:128-163)
+    int k_batch = 0;  // batches this receiver has shuffled in this step (shuffle_batches only)
     for (int round = 0; pending > 0; ++round) {
       if (sp.round_limit >= 0 && round >= sp.round_limit) {  // resolvers.py:160-163
         fault_key = min(fault_key, ((uint32_t)(round + 1) << 16) | (0xFFu << 8) | PHX_FAULT_ROUND_LIMIT);
@@ -496,11 +588,11 @@ __global__ void __launch_bounds__(ENGINE_BLOCK) engine_step_kernel(const EngineA
       }
       if (round == 0)
         pending = engine_round<P, G, TRACK>(a, ctx, st, has_ctx, ts.qa, ts.qr[0], ts, round, tmask,
-                                            fault_key, traced, e, trace_lane);
+                                            fault_key, traced, e, trace_lane, k_batch);
       else
         pending = engine_round<P, G, TRACK>(a, ctx, st, has_ctx, ts.qr[(round - 1) & 1],
                                             ts.qr[round & 1], ts, round, tmask, fault_key, traced,
-                                            e, trace_lane);
+                                            e, trace_lane, k_batch);
     }
     if (trace_lane) a.trace.cnt[e] = traced;
 
@@ -622,6 +714,10 @@ __global__ void __launch_bounds__(ENGINE_BLOCK) engine_step_kernel(const EngineA
       ctx.step = 0;
       ctx.episode = (uint32_t)h.y;
       ctx.stage = h.z;
+      if (a.adj_env)  // Network.reset of a StochasticNetwork resamples first (network.py:450-453)
+        ctx.out_mask = ctx.in_mask =
+            is_agent ? resample_adj_row(sp.seed, a.base_conn, a.n_base, ctx.env_id, ctx.episode, slot)
+                     : 0u;
       if (is_agent) P::reset_agent(ctx, st);
       rnone = cached_env ? sp.strategic_mask : 0u;
       if (P::VW > 0) {
@@ -659,6 +755,7 @@ __global__ void __launch_bounds__(ENGINE_BLOCK) engine_step_kernel(const EngineA
 #pragma unroll
     for (int w = 0; w < P::NWORDS; ++w) a.state[((size_t)w * sp.E + e) * G + slot] = st[w];
     if (cached_env) a.reward_cache[(size_t)e * G + slot] = rcache;
+    if (a.adj_env) a.adj_env[(size_t)e * G + slot] = ctx.out_mask;
   }
   // first fault of the env in event order (phase, then agent order)
   const uint32_t fk = __reduce_min_sync(tmask, fault_key);
@@ -707,6 +804,14 @@ engine_reset_kernel(const EngineArgs<P> a, const uint8_t* env_mask, float* obs, 
   ctx.ip0_tab = bs.ip0_tab;
   ctx.out_mask = is_agent ? sp.adj[slot] : 0u;
   ctx.in_mask = 0;
+  if (a.adj_env) {
+    // StochasticNetwork.reset resamples the edges before the agents reset (network.py:450-453);
+    // the constructor's own sample (add_connection, :389-391) is the draw of "episode -1"
+    ctx.out_mask = is_agent ? resample_adj_row(sp.seed, a.base_conn, a.n_base, ctx.env_id,
+                                               agents_only ? 0xFFFFFFFFu : ctx.episode, slot)
+                            : 0u;
+    if (env_live) a.adj_env[(size_t)e * G + slot] = ctx.out_mask;
+  }
   if (is_agent) P::reset_agent(ctx, st);  // Network.reset -> agent.reset() (network.py:179-184)
   if (agents_only) {  // PhantomEnv.__init__ ends with agent.reset() only (env.py:122-124)
     if (env_live) {

@@ -169,12 +169,23 @@ __global__ void __launch_bounds__(ENGINE1_BLOCK) engine1_step_kernel(const Engin
   ctx.kind_tab = kind_tab;
   ctx.ip0_tab = ip0_tab;
 
+  // StochasticNetwork: the env's own 8 x 8 adjacency, one byte per row (rows == columns)
+  const bool stochastic = a.adj_env != nullptr;
+  uint64_t adj64 = 0;
+  if (stochastic) {
+    const uint4* src = reinterpret_cast<const uint4*>(a.adj_env + (size_t)e * ENGINE1_SLOTS);
+    const uint4 lo = src[0], hi = src[1];
+    const uint32_t v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) adj64 |= (uint64_t)(v[k] & 0xFFu) << (8 * k);
+  }
+  auto row_of = [&](int slot) { return (uint32_t)(adj64 >> (8 * slot)) & 0xFFu; };
   auto bind = [&](int slot) {
     ctx.slot = slot;
     ctx.kind = sp.kind[slot];
-    ctx.out_mask = sp.adj[slot];
+    ctx.out_mask = stochastic ? row_of(slot) : sp.adj[slot];
   };
-  auto in_mask_of = [&](int slot) { return in_tab[slot]; };
+  auto in_mask_of = [&](int slot) { return stochastic ? row_of(slot) : in_tab[slot]; };
   auto load_state = [&](int slot, int* st) {
 #pragma unroll
     for (int w = 0; w < P::NWORDS; ++w) st[w] = ST(w, slot);
@@ -420,6 +431,15 @@ __global__ void __launch_bounds__(ENGINE1_BLOCK) engine1_step_kernel(const Engin
       ctx.episode = (uint32_t)h.y;
       ctx.stage = h.z;
       rnone = cached_env ? sp.strategic_mask : 0u;
+      if (stochastic) {  // StochasticNetwork.reset: resample, then reset agents (network.py:450-453)
+        adj64 = 0;
+        for (int c = 0; c < a.n_base; ++c) {
+          const uint2 bc = a.base_conn[c];
+          const int u = bc.x & 0xFF, v = (bc.x >> 8) & 0xFF;
+          if (base_connection_exists(sp.seed, ctx.env_id, ctx.episode, c, bc.y))
+            adj64 |= (1ull << (8 * u + v)) | (1ull << (8 * v + u));
+        }
+      }
       for (int s = 0; s < n; ++s) {
         bind(s);
         load_state(s, st);
@@ -475,6 +495,11 @@ __global__ void __launch_bounds__(ENGINE1_BLOCK) engine1_step_kernel(const Engin
       for (int k = 0; k < 8; ++k) v[k] = k < n ? RC(k) : 0.f;
       rc[0] = make_float4(v[0], v[1], v[2], v[3]);
       rc[1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+    if (stochastic) {
+      uint4* dst = reinterpret_cast<uint4*>(a.adj_env + (size_t)e * ENGINE1_SLOTS);
+      dst[0] = make_uint4(row_of(0), row_of(1), row_of(2), row_of(3));
+      dst[1] = make_uint4(row_of(4), row_of(5), row_of(6), row_of(7));
     }
 #pragma unroll
     for (int w = 0; w < P::NWORDS; ++w) {

@@ -1,8 +1,11 @@
 // phx_engine_host.cuh -- host side of the generic queue engine: a Family implementation that
 // owns the state of E envs of a device program P and launches engine_step_kernel<P, G>.
 #pragma once
+#include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "phx_engine.cuh"
 #include "phx_engine1.cuh"
@@ -85,6 +88,8 @@ class EngineFamily : public Family {
     cudaFree(d_rnone);
     cudaFree(d_ocache);
     cudaFree(d_ocached);
+    cudaFree(d_adj);
+    cudaFree(d_base);
   }
 
   int32_t init(const phx_spec& s) override {
@@ -95,8 +100,9 @@ class EngineFamily : public Family {
     G = s.n_agents <= 8 ? 8 : (s.n_agents <= 16 ? 16 : 32);
     // thread-per-env variant: <= 8 agents and a program that declares its queue bound
     qcap1 = P::q1_cap(s);  // messages in flight per round, for THIS env class (0 = unsupported)
+    // (shuffle_batches needs the per-receiver batch lists of the tile engine)
     const bool eligible = P::Q1CAP > 0 && P::VW <= 1 && s.n_agents <= ENGINE1_SLOTS && qcap1 > 0 &&
-                          qcap1 <= P::Q1CAP;
+                          qcap1 <= P::Q1CAP && !(s.flags & PHX_FLAG_SHUFFLE_BATCHES);
     PHX_REQUIRE(s.exec_mode != PHX_EXEC_THREAD || eligible, PHX_ERR_UNSUPPORTED,
                 "PHX_EXEC_THREAD needs an env class with at most 8 agents whose device program "
                 "supports the thread-per-env engine");
@@ -116,6 +122,26 @@ class EngineFamily : public Family {
         PHX_CUDA(cudaMalloc(&d_ocached, sizeof(uint32_t) * (size_t)E));
         PHX_CUDA(cudaMemset(d_ocached, 0, sizeof(uint32_t) * (size_t)E));
       }
+    }
+    if (s.flags & PHX_FLAG_STOCHASTIC_NETWORK) {
+      // per-env adjacency rows + the base-connection table with integer thresholds
+      PHX_REQUIRE(s.n_base_connections >= 0 && s.n_base_connections <= PHX_MAX_BASE_CONNECTIONS,
+                  PHX_ERR_INVALID, "n_base_connections out of range");
+      std::vector<uint2> base((size_t)s.n_base_connections + 1);
+      for (int c = 0; c < s.n_base_connections; ++c) {
+        PHX_REQUIRE(s.base_u[c] < s.n_agents && s.base_v[c] < s.n_agents, PHX_ERR_INVALID,
+                    "base connection names an agent slot outside the env");
+        const double r = s.base_rate[c];
+        PHX_REQUIRE(r == r, PHX_ERR_INVALID, "base connection rate is NaN");
+        // uniform01 < r  <=>  d24 < ceil(r * 2^24); r * 2^24 is exact in float64
+        const double scaled = std::ceil(std::min(std::max(r, 0.0), 1.0) * 16777216.0);
+        base[c] = make_uint2((uint32_t)s.base_u[c] | ((uint32_t)s.base_v[c] << 8), (uint32_t)scaled);
+      }
+      n_base = s.n_base_connections;
+      PHX_CUDA(cudaMalloc(&d_base, sizeof(uint2) * base.size()));
+      PHX_CUDA(cudaMemcpy(d_base, base.data(), sizeof(uint2) * base.size(), cudaMemcpyHostToDevice));
+      PHX_CUDA(cudaMalloc(&d_adj, sizeof(uint32_t) * n));
+      PHX_CUDA(cudaMemset(d_adj, 0, sizeof(uint32_t) * n));
     }
     engine_init_kernel<P><<<(E + 255) / 256, 256>>>(E, G, d_hdr, d_state, P::NWORDS);
     PHX_CUDA(cudaGetLastError());
@@ -141,6 +167,9 @@ class EngineFamily : public Family {
     a.reward_none = d_rnone;
     a.obs_cache = d_ocache;
     a.obs_cached = d_ocached;
+    a.adj_env = d_adj;
+    a.base_conn = d_base;
+    a.n_base = n_base;
     a.io = io;
     a.faults = fault_sink();
     a.trace = trace_sink();
@@ -222,6 +251,13 @@ class EngineFamily : public Family {
   }
 
   int32_t family_field(int32_t field, int32_t, void** p, size_t* bytes) override {
+    if (field == PHX_FIELD_ADJACENCY) {  // uint32 [E, G]: G >= n_agents slots per env
+      PHX_REQUIRE(d_adj != nullptr, PHX_ERR_INVALID,
+                  "PHX_FIELD_ADJACENCY needs PHX_FLAG_STOCHASTIC_NETWORK");
+      *p = d_adj;
+      *bytes = sizeof(uint32_t) * (size_t)E * G;
+      return PHX_OK;
+    }
     const int w = field - PHX_FIELD_FAMILY;
     if (w >= 0 && w < P::NWORDS) {
       *p = d_state + (size_t)w * E * G;
@@ -243,6 +279,9 @@ class EngineFamily : public Family {
   uint32_t* d_rnone = nullptr;
   float* d_ocache = nullptr;
   uint32_t* d_ocached = nullptr;
+  uint32_t* d_adj = nullptr;  // StochasticNetwork only
+  uint2* d_base = nullptr;
+  int32_t n_base = 0;
   std::string name;
 };
 

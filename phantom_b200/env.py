@@ -339,6 +339,13 @@ class PhantomEnv:
         name = self.exec_name
         return int(name.split("G=")[1].rstrip(")")) if "G=" in name else 0
 
+    def adjacency(self) -> np.ndarray:
+        """Per-env graphs of a StochasticNetwork: uint8 [E, n_agents, n_agents], entry [e, s, r]
+        = 1 iff env e currently has the edge s -> r (network.py:439-448 run per env)."""
+        rows = self.field(L.FIELD_ADJACENCY, np.uint32, width=self.tile_width)
+        n = self.spec.n_agents
+        return ((rows[:, :n, None] >> np.arange(n, dtype=np.uint32)[None, None, :]) & 1).astype(np.uint8)
+
     def agent_column(self, agent: Agent, word: int, dtype=np.int32) -> np.ndarray:
         """State word `word` of `agent` for every env: array [E]."""
         info = self.family

@@ -118,12 +118,13 @@ FAMILY = register(FamilyInfo(
 
 class MarketEnv(ph.FiniteStateMachineEnv):
     def __init__(self, n_makers: int = N_MAKERS, n_takers: int = N_TAKERS, *, num_steps: int = 99,
-                 enable_tracking: bool = False, **batch_kwargs):
+                 enable_tracking: bool = False, shuffle_batches: bool = False, **batch_kwargs):
         maker_ids = [f"M{i + 1}" for i in range(n_makers)]
         taker_ids = [f"T{i + 1}" for i in range(n_takers)]
         agents = [MakerAgent(m) for m in maker_ids] + [TakerAgent(t) for t in taker_ids]
         agents.append(ClearingAgent("CLEARING"))
-        network = ph.Network(agents, ph.resolvers.BatchResolver(enable_tracking=enable_tracking))
+        network = ph.Network(agents, ph.resolvers.BatchResolver(
+            enable_tracking=enable_tracking, shuffle_batches=shuffle_batches))
         network.add_connections_between(maker_ids, taker_ids)
         network.add_connections_between(["CLEARING"], maker_ids + taker_ids)
         everyone = maker_ids + taker_ids

@@ -147,14 +147,23 @@ FAMILY = register(FamilyInfo(
 class SupplyChain2Env(ph.PhantomEnv):
     def __init__(self, n_shops: int = N_SHOPS, n_customers: int = N_CUSTOMERS, *,
                  num_steps: int = 100, agent_supertypes="default", enable_tracking: bool = False,
-                 **batch_kwargs):
+                 rates=None, shuffle_batches: bool = False, **batch_kwargs):
+        """rates=(warehouse_rate, customer_rate): StochasticNetwork with those connection
+        probabilities and ignore_connection_errors=True (oracle/workloads/supply_chain2.py)."""
         shop_ids = [f"SHOP{i + 1}" for i in range(n_shops)]
         customer_ids = [f"CUST{i + 1}" for i in range(n_customers)]
         agents = [FactoryAgent("WAREHOUSE")] + [ShopAgent(s, "WAREHOUSE") for s in shop_ids]
         agents += [CustomerAgent(c, shop_ids) for c in customer_ids]
-        network = ph.Network(agents, ph.resolvers.BatchResolver(enable_tracking=enable_tracking))
-        network.add_connections_between(shop_ids, ["WAREHOUSE"])
-        network.add_connections_between(shop_ids, customer_ids)
+        resolver = ph.resolvers.BatchResolver(enable_tracking=enable_tracking,
+                                              shuffle_batches=shuffle_batches)
+        if rates is None:
+            network = ph.Network(agents, resolver)
+            network.add_connections_between(shop_ids, ["WAREHOUSE"])
+            network.add_connections_between(shop_ids, customer_ids)
+        else:
+            network = ph.StochasticNetwork(agents, resolver, ignore_connection_errors=True)
+            network.add_connections_between(shop_ids, ["WAREHOUSE"], rate=rates[0])
+            network.add_connections_between(shop_ids, customer_ids, rate=rates[1])
         if agent_supertypes == "default":  # the tutorial's training setup (tutorial2.rst:334-340)
             agent_supertypes = {
                 s: {"excess_stock_weight": UniformFloatSampler(0.0, MAX_EXCESS_STOCK_WEIGHT)}

@@ -118,6 +118,19 @@ def lower(env, exec_mode: str = "auto", auto_reset: bool = False) -> L.PhxSpec:
         spec.trace_capacity = int(info.trace_capacity(env, agents))
     if auto_reset:
         flags |= L.FLAG_AUTO_RESET
+    if getattr(res, "shuffle_batches", False):
+        flags |= L.FLAG_SHUFFLE_BATCHES
+    base = getattr(net, "_base_connections", None)
+    if base is not None:  # StochasticNetwork (phantom/network.py:340-453)
+        if len(base) > L.PHX_MAX_BASE_CONNECTIONS:
+            raise NotLowerableError(
+                f"more than {L.PHX_MAX_BASE_CONNECTIONS} StochasticNetwork base connections")
+        if len(agents) > 32:
+            raise NotLowerableError("StochasticNetwork lowers to the queue engine: <= 32 agents")
+        flags |= L.FLAG_STOCHASTIC_NETWORK
+        spec.n_base_connections = len(base)
+        for c, (u, v, rate) in enumerate(base):
+            spec.base_u[c], spec.base_v[c], spec.base_rate[c] = slot[u], slot[v], float(rate)
     spec.flags = flags
 
     # step-loop kind

@@ -144,3 +144,53 @@ class Network:
 
     def __len__(self) -> int:
         return len(self.agents)
+
+
+class StochasticNetwork(Network):
+    """Network whose edges are re-drawn at every reset (reference: phantom/network.py:340-453).
+
+    Host side keeps `_base_connections` = [(u, v, rate)] in insertion order; the graph the
+    host object shows (`has_edge`, `neighbours`, `adjacency_matrix`) is the set of POSSIBLE
+    edges (rate > 0).  The per-env, per-episode graphs live on the device: every env resamples
+    base connection c at reset with `uniform01(stream 5, step 0, idx c) < rate`
+    (csrc/phx_engine.cuh `resample_adj_row`); read them with `PhantomEnv.adjacency()`.
+
+    As in the reference (network.py:370-378) the constructor does not accept `connections`
+    (its `_base_connections` list does not exist yet when the base constructor runs).
+    """
+
+    def __init__(self, agents: Optional[Iterable[Agent]] = None,
+                 resolver: Optional[Resolver] = None,
+                 connections: Optional[Iterable[Tuple[AgentID, AgentID]]] = None,
+                 ignore_connection_errors: bool = False,
+                 enforce_msg_payload_checks: bool = True) -> None:
+        super().__init__(agents, resolver, connections, ignore_connection_errors,
+                         enforce_msg_payload_checks)
+        self._base_connections: List[Tuple[AgentID, AgentID, float]] = []
+
+    def add_connection(self, u: AgentID, v: AgentID, rate: float = 1.0) -> None:
+        for x in (u, v):
+            if x not in self.agents:
+                raise ValueError(f"Agent with ID = '{x}' does not exist.")
+        rate = float(rate)
+        if rate > 0.0:
+            self._succ[u][v] = None
+            self._succ[v][u] = None
+        self._base_connections.append((u, v, rate))
+
+    def add_connections_from(self, ebunch) -> None:
+        for c in ebunch:
+            if len(c) == 2:
+                self.add_connection(c[0], c[1])
+            elif len(c) == 3:
+                self.add_connection(c[0], c[1], c[2])
+            else:
+                raise ValueError(f"Ill-formatted connection tuple {c}.")
+
+    def add_connections_between(self, us: Iterable[AgentID], vs: Iterable[AgentID],
+                                rate: float = 1.0) -> None:
+        for u, v in itertools.product(us, vs):
+            self.add_connection(u, v, rate)
+
+    def resample_connectivity(self) -> None:
+        raise DeviceOnlyError("connectivity is resampled per env by the reset kernel")

@@ -7,7 +7,7 @@ from __future__ import annotations
 
 from typing import List, Optional
 
-from .errors import DeviceOnlyError, NotLowerableError
+from .errors import DeviceOnlyError
 from .message import Message
 
 
@@ -36,9 +36,5 @@ class BatchResolver(Resolver):
     def __init__(self, enable_tracking: bool = False, round_limit: Optional[int] = None,
                  shuffle_batches: bool = False) -> None:
         super().__init__(enable_tracking)
-        if shuffle_batches:
-            raise NotLowerableError(
-                "BatchResolver(shuffle_batches=True) has no device implementation yet "
-                "(SURVEY.md 8f row 4)")
         self.round_limit = round_limit
         self.shuffle_batches = shuffle_batches

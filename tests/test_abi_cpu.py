@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_spec_layout_matches_compiled_struct():
     assert L.lib.phx_sizeof_spec() == C.sizeof(L.PhxSpec)
-    assert L.lib.phx_abi_version() == 1
+    assert L.lib.phx_abi_version() == L.PHX_ABI_VERSION == 2
 
 
 def test_no_cpu_fallback():
@@ -109,8 +109,16 @@ def test_python_logic_is_never_silently_ignored():
         env.spec
     with pytest.raises(ph.DeviceOnlyError):
         ph.Network([Plain("x")]).send("x", "x", None)
-    with pytest.raises(ph.NotLowerableError):
-        ph.resolvers.BatchResolver(shuffle_batches=True)
+    # shuffle_batches lowers to a flag (resolvers.py:150-151 runs inside the round kernel)
+    from phantom_b200 import _lib as L
+    from phantom_b200.envs.supply_chain2 import SupplyChain2Env
+
+    spec = SupplyChain2Env(shuffle_batches=True, rates=(0.5, 0.75)).spec
+    assert spec.flags & L.FLAG_SHUFFLE_BATCHES and spec.flags & L.FLAG_STOCHASTIC_NETWORK
+    assert spec.flags & L.FLAG_IGNORE_CONNECTION_ERRORS
+    assert spec.n_base_connections == 2 * 1 + 2 * 5
+    assert [spec.base_rate[c] for c in range(12)] == [0.5] * 2 + [0.75] * 10
+    assert (spec.base_u[0], spec.base_v[0]) == (1, 0) and (spec.base_u[2], spec.base_v[2]) == (1, 3)
 
 
 def test_network_construction_api_and_errors():

@@ -206,3 +206,71 @@ def test_object_oracle_matches_supply_chain2_golden(golden_dir):
                 state_fn=lambda env: (ws.append(wl.weights(env)), wl.state(env))[1])
         assert_oracle_trace_equal(tr, g, e)
         assert np.array_equal(np.array(ws).reshape(g["weights"][e].shape), g["weights"][e])
+
+
+def test_object_oracle_matches_market_shuffle_golden(golden_dir):
+    """BatchResolver(shuffle_batches=True): oracle restatement == reference under the contract's
+    Fisher-Yates, and the shuffle is observable (differs from the unshuffled run)."""
+    from oracle import make_golden
+    from oracle.workloads import market
+
+    from .generic_parity import assert_oracle_trace_equal
+
+    g = np.load(os.path.join(golden_dir, "market_shuffle_reference.npz"))
+    seed, A, M = int(g["seed"]), g["actions"], g["action_mask"]
+    e = 0
+    st = rng.StepStream(seed, e, market.STREAM_TAKER_VALUE)
+    env = market.build(po, st, enable_tracking=True, shuffle_batches=True)
+    clock = harness.EpisodeClock([st])
+    slot_of = {aid: i for i, aid in enumerate(env.agent_ids)}
+    with harness.patched_np_shuffle(seed, e, clock, env, slot_of):
+        tr = harness.run_generic(env, clock, A[e], M[e], 3, track=True,
+                                 state_fn=make_golden.market_state)
+    assert_oracle_trace_equal(tr, g, e)
+    rows = [(0, ep, t, s, r, make_golden.MESSAGE_TYPE_IDS[n], v0, v1)
+            for (ep, t, s, r, n, v0, v1) in tr["messages"]]
+    assert np.array_equal(np.asarray(rows, np.int64), g["messages"])
+    # same env without shuffling ends up in a different state
+    st = rng.StepStream(seed, e, market.STREAM_TAKER_VALUE)
+    plain = harness.run_generic(market.build(po, st), harness.EpisodeClock([st]), A[e][:1], M[e][:1],
+                                3, state_fn=make_golden.market_state)
+    assert not np.array_equal(plain["state"][0], g["state"][e, 0])
+
+
+def test_object_oracle_matches_stochastic_network_golden(golden_dir):
+    """StochasticNetwork (resampled per episode, ignore_connection_errors) + shuffled batches:
+    oracle restatement == reference, graphs included; edge frequencies follow the rates."""
+    from oracle.workloads import supply_chain2 as wl
+
+    from .generic_parity import assert_oracle_trace_equal
+
+    g = np.load(os.path.join(golden_dir, "supply_chain2_stochastic_reference.npz"))
+    seed, A, M, rates = int(g["seed"]), g["actions"], g["action_mask"], tuple(g["rates"])
+    T = A.shape[2]
+    for e in range(5):
+        streams = {s: rng.StepStream(seed, e, s)
+                   for s in (wl.STREAM_ORDER, wl.STREAM_SAMPLER, wl.STREAM_SHOP_CHOICE,
+                             wl.STREAM_CONNECTIVITY)}
+        adj = []
+        with harness.patched_np_uniform(streams[wl.STREAM_SAMPLER]), \
+                harness.patched_np_random(streams[wl.STREAM_CONNECTIVITY]):
+            env = wl.build(po, streams, po.utils.samplers.UniformFloatSampler, num_steps=T,
+                           enable_tracking=e < 4, rates=rates, shuffle_batches=True)
+            clock = harness.EpisodeClock(list(streams.values()))
+            slot_of = {aid: i for i, aid in enumerate(env.agent_ids)}
+            with harness.patched_np_shuffle(seed, e, clock, env, slot_of):
+                tr = harness.run_generic(
+                    env, clock, A[e], M[e], 4, track=e < 4,
+                    state_fn=lambda env: (adj.append(wl.adjacency(env)), wl.state(env))[1])
+        assert_oracle_trace_equal(tr, g, e)
+        assert np.array_equal(np.array(adj).reshape(-1, T, 8, 8)[:, 0], g["adjacency"][e])
+    # the contract draw reproduces the graphs directly: connection c exists iff d24 * 2^-24 < rate
+    base = [(1, 0), (2, 0)] + [(s, c) for s in (1, 2) for c in range(3, 8)]
+    rate = [rates[0]] * 2 + [rates[1]] * 10
+    for e in range(g["adjacency"].shape[0]):
+        for ep in range(g["adjacency"].shape[1]):
+            want = np.zeros((8, 8), np.uint8)
+            for c, (u, v) in enumerate(base):
+                if rng.d24(seed, e, ep, 0, wl.STREAM_CONNECTIVITY, c) / 16777216.0 < rate[c]:
+                    want[u, v] = want[v, u] = 1
+            assert np.array_equal(want, g["adjacency"][e, ep]), (e, ep)
