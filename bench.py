@@ -37,6 +37,32 @@ B_STATE = 2 * (8 + 16)  # header (step, episode) + shop state, read once + writt
 
 
 # ------------------------------------------------------------------------------ helpers
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the bench kernel, from the
+    committed ncu --set full capture (profiles/traffic.json names the source file)."""
+    try:
+        with open(os.path.join(REPO, "profiles", "traffic.json")) as f:
+            t = json.load(f)
+        return int(t["dram_bytes_read"]) + int(t["dram_bytes_write"]), t["source"]
+    except Exception:
+        return None, None
+
+
+def port_calibration():
+    """port speed / unmodified-reference speed, measured where both can run (the build
+    container; tools/calibrate_port.py)."""
+    try:
+        with open(os.path.join(REPO, "tests", "golden", "port_calibration.json")) as f:
+            return float(json.load(f)["port_over_reference"])
+    except Exception:
+        return None
+
+
+WORKLOAD = ("supply-chain C2: 65536 envs/GPU x 8 agent slots (7 used), 100-step episodes; "
+            "one bench step = one phx_rollout launch = 100 env transitions per env, "
+            "auto-reset at the episode end")
+
+
 def measured_peak_gbs():
     try:
         with open(os.path.join(REPO, "MEASURED_PEAKS.json")) as f:
@@ -140,12 +166,16 @@ def cpu_baseline(seconds: float, cores: int):
         wall = time.perf_counter() - t0
     steps = sum(n for n, _ in res)
     rate = sum(n / dt for n, dt in res)
+    cal = port_calibration()
     return {
         "value": rate, "unit": "env-steps/s", "cores": cores, "kind": "port",
         "sample": (f"{cores} processes x {seconds:.0f} s of 100-step supply-chain episodes on "
                    f"oracle.phantom_oracle (Python restatement of PhantomEnv.step; the "
                    f"reference itself is Python and cannot travel to the GPU box), "
                    f"{steps} env-steps, wall {wall:.1f} s"),
+        # the port runs this loop `port_over_reference` times as fast as the unmodified
+        # reference on one core of the build container (tests/golden/port_calibration.json)
+        "port_over_reference": cal,
     }
 
 
@@ -286,6 +316,7 @@ def run_ours(args):
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
+        traffic, traffic_src = ncu_traffic()
         bytes_per_launch = E * (T * B_IO + B_STATE)
         launch_ms = ms / args.steps
         achieved = bytes_per_launch / (launch_ms * 1e-3) / 1e9
@@ -295,9 +326,7 @@ def run_ours(args):
             "warmup": args.warmup, "ms_per_step": launch_ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
             "config": {
-                "workload": "supply-chain C2: 65536 envs/GPU x 8 agent slots (7 used), "
-                            "100-step episodes; one bench step = one phx_rollout launch = "
-                            "100 env transitions per env, auto-reset at the episode end",
+                "workload": WORKLOAD,
                 "envs_per_gpu": E, "transitions_per_launch": T, "kernel": env.exec_name,
                 "l2": f"inputs larger than L2: {NBUF} rotating action/output sets of "
                       f"{(acts[0].numel() * 4 + bytes_per_launch) / 1e6:.0f} MB",
@@ -305,7 +334,8 @@ def run_ours(args):
             },
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": bytes_per_launch,
                 "kernel": "sc_fast_kernel<5,false>",
             },
@@ -348,8 +378,10 @@ def run_reference(args):
         "value": value, "unit": "env-steps/s", "n_gpus": args.gpus, "steps": len(rates),
         "warmup": 1, "ms_per_step": args.cpu_seconds * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "python-int", "data": "synthetic",
-        "config": {"workload": "supply-chain C2 dynamics, CPU: one env object per process, "
-                               f"{cores} processes, 100-step episodes"},
+        "config": {"workload": WORKLOAD,
+                   "cpu": f"same dynamics on the host: one env object per process, {cores} "
+                          f"processes, 100-step episodes incl. reset; each step = a "
+                          f"{args.cpu_seconds:.0f} s sample"},
         "cpu_baseline": dict(best, value=value),
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
