@@ -138,7 +138,7 @@ def _cpu_worker(args):
     from oracle import harness, rng
     from oracle.workloads import supply_chain as wl
 
-    st = rng.StepStream(SEED, worker, 0)
+    st = wl.order_stream(SEED, worker)
     env = wl.build(po, st)
     clock = harness.EpisodeClock([st])
     acts = np.random.RandomState(worker).uniform(0, 100, size=(T_EPISODE, 1)).astype(np.float32)

@@ -45,7 +45,7 @@ def gen_supply_chain_reference() -> None:
     keys = None
     per_env = []
     for e in range(n_env):
-        stream = rng.StepStream(seed, e, 0)
+        stream = rng.PackedStream(seed, e, 0, 5, 5)  # supply_chain.py:12,64: 5 customers, randint(5)
         env = sc.SupplyChainEnv()
         env.network.resolver.enable_tracking = e < 3
         clock = harness.EpisodeClock([stream])

@@ -31,6 +31,24 @@ Derived distributions:
                                            bias <= n / 2^24)
   uniform01() := d24 * 2**-24             (float32-exact, in [0, 1))
 
+Packed small-integer draws (contract v3).  A call site that draws K values of randint(n)
+per step with a small n (the supply chain's customers, supply_chain.py:64: K = 5, n = 5)
+takes its draws as the base-n digits of 32-bit Philox words, extracted by multiply-high
+(exact arithmetic decoding of the fraction word / 2^32):
+
+      x_0 = word;   digit_r = (x_r * n) >> 32;   x_{r+1} = (x_r * n) mod 2^32
+
+  a word yields kpw(n) digits, kpw = the largest j with n^j <= 2^16 (every digit is then
+  within 2^-16 relative of uniform -- the same order as the 24-bit draws' n / 2^24; n = 5:
+  6 digits).  The site consumes W = ceil(K / kpw) words per step; draw i of step s is digit
+  i % kpw of word number g = s * W + i // kpw of the site's word sequence, and
+
+      word g = w[g & 3] of Philox4x32-10( key = seed,
+                   ctr = (env, episode, g >> 2, (stream << 16) | 0x8000) )
+
+  so consecutive steps share blocks: with K <= kpw ONE Philox block serves FOUR env steps
+  (the device's fused step kernel spent 30 % of its instructions on one block per step).
+
 Philox4x32-10 is Salmon et al., "Parallel random numbers: as easy as 1, 2, 3" (SC'11),
 with the standard Random123 constants; checked below against the Random123 known-answer
 vectors.
@@ -123,6 +141,75 @@ def uniform01(draw: int) -> float:
 
 def uniform01_np(draws) -> np.ndarray:
     return np.asarray(draws, dtype=np.uint32).astype(np.float32) * np.float32(2.0**-24)
+
+
+# ------------------------------------------------------------------ packed draws (v3)
+def digits_per_word(n: int) -> int:
+    j, pw = 1, int(n)
+    while pw * n <= 65536:
+        pw *= n
+        j += 1
+    return j
+
+
+def packed_word(seed: int, env: int, episode: int, stream: int, g: int) -> int:
+    words = philox4x32((env, episode, (g >> 2) & MASK, ((stream & 0xFFFF) << 16) | 0x8000),
+                       (seed & MASK, (seed >> 32) & MASK))
+    return words[g & 3]
+
+
+def packed_randint(seed: int, env: int, episode: int, step: int, stream: int, n: int, K: int,
+                   i: int) -> int:
+    """Draw i (0 <= i < K) of the K randint(n) draws this site makes in `step`."""
+    kpw = digits_per_word(n)
+    W = (K + kpw - 1) // kpw
+    x = packed_word(seed, env, episode, stream, step * W + i // kpw)
+    d = 0
+    for _ in range(i % kpw + 1):
+        prod = x * n
+        d, x = prod >> 32, prod & MASK
+    return d
+
+
+def packed_randint_np(seed: int, env, episode, step, stream: int, n: int, K: int) -> np.ndarray:
+    """All K draws of a step, vectorised: env/episode/step broadcast -> int32 [..., K]."""
+    kpw = digits_per_word(n)
+    W = (K + kpw - 1) // kpw
+    env, episode, step = np.broadcast_arrays(np.asarray(env, np.int64), np.asarray(episode, np.int64),
+                                             np.asarray(step, np.int64))
+    out = np.zeros(env.shape + (K,), np.int32)
+    for q in range(W):
+        g = step * W + q
+        w = philox4x32_np(env, episode, (g >> 2) & MASK, ((stream & 0xFFFF) << 16) | 0x8000,
+                          seed & MASK, (seed >> 32) & MASK)
+        x = np.choose(g & 3, w).astype(np.uint64)
+        for r in range(kpw):
+            i = q * kpw + r
+            if i >= K:
+                break
+            prod = x * np.uint64(n)
+            out[..., i] = (prod >> np.uint64(32)).astype(np.int32)
+            x = prod & np.uint64(MASK)
+    return out
+
+
+class PackedStream:
+    """Sequential view of a packed site: the i-th randint(n) call after begin() is draw i.
+    `n` and the number of draws per step `K` are fixed per site (they define the word layout)."""
+
+    def __init__(self, seed: int, env: int, stream: int, n: int, K: int):
+        self.seed, self.env, self.stream, self.n, self.K = seed, env, stream, int(n), int(K)
+        self.episode = self.step = self.k = 0
+
+    def begin(self, episode: int, step: int) -> None:
+        self.episode, self.step, self.k = episode, step, 0
+
+    def randint(self, n: int) -> int:
+        assert int(n) == self.n and self.k < self.K, "packed site: fixed n, at most K draws per step"
+        d = packed_randint(self.seed, self.env, self.episode, self.step, self.stream, self.n,
+                           self.K, self.k)
+        self.k += 1
+        return d
 
 
 # Random123 known-answer vectors for philox4x32-10 (kat_vectors in the Random123

@@ -60,10 +60,8 @@ class SupplyChainVec:
         self.step_no += 1
         # decode_action: min(int(round(a)), max_stock - stock); round == rint on float32
         ask = np.minimum(np.rint(a).astype(np.int64), self.max_stock - self.stock)
-        idx = np.arange(self.nc, dtype=np.int64)[None, :]
-        draws = rng.d24_np(self.seed, self.env_ids[:, None], self.episode[:, None],
-                           self.step_no[:, None], self.STREAM, idx)
-        orders = rng.randint_np(self.max_order, draws).astype(np.int64)
+        orders = rng.packed_randint_np(self.seed, self.env_ids, self.episode, self.step_no,
+                                       self.STREAM, self.max_order, self.nc).astype(np.int64)
         self.sales[:] = 0
         self.missed[:] = 0
         for i in range(self.nc):  # serial order fill, round 0

@@ -11,7 +11,7 @@ Follows /root/reference/examples/environments/supply_chain/supply_chain.py:
 
 The only change is the RNG call site (:64): instead of process-global
 `np.random.randint`, the customer pulls from the env's counter-based stream
-(oracle/rng.py, stream 0, idx = customer index).  tests/test_oracle_golden.py proves this
+(oracle/rng.py packed draws, stream 0, draw i = customer index; `order_stream` below).  tests/test_oracle_golden.py proves this
 file == the unmodified example with `np.random.randint` patched to the same stream.
 
 Device twin: phantom_b200/csrc/fam_supply_chain.cuh.
@@ -33,11 +33,19 @@ PAYLOAD_TYPE_IDS = {
 }
 
 
+def order_stream(seed: int, env: int, *, n_customers: int = 5, max_order: int = 5):
+    """The contract stream of the customers' order sizes for global env index `env`:
+    K = n_customers packed draws of randint(max_order) per step (oracle/rng.py)."""
+    from .. import rng
+
+    return rng.PackedStream(seed, env, STREAM_CUSTOMER_ORDER, max_order, n_customers)
+
+
 def build(ph, stream, *, n_customers: int = 5, max_order: int = 5, max_stock: int = 100,
           num_steps: int = 100, enable_tracking: bool = False):
     """Return a supply-chain PhantomEnv built with API module `ph`.
 
-    `stream` is an oracle.rng.StepStream (or anything with .randint(n))."""
+    `stream`: `order_stream(...)` (or anything with .randint(n))."""
 
     @ph.msg_payload("CustomerAgent", "ShopAgent")
     class OrderRequest:

@@ -49,6 +49,7 @@ constexpr float SC_MAX_ABS_ACTION = 1048576.0f;  // action contract: finite, |a|
 // Static schedule of one step on the canonical topology (see make_plan).
 struct ScPlan {
   int32_t E, num_steps, nc, max_order, max_stock;
+  int32_t digits_per_word, words_per_step;  // packed draws of the customers' order sizes
   uint32_t flags;
   uint32_t fault[2];     // [shop supplied an action?] -> first fault in event order, 0 = none
   uint32_t deliver_ord;  // bit i: CUSTi's OrderRequest reaches the shop's handler
@@ -88,9 +89,6 @@ __device__ __forceinline__ float sc_ratio(int num, float den, float rcp) {
 #ifndef SC_BLOCK_THREADS
 #define SC_BLOCK_THREADS 64
 #endif
-#ifndef SC_OVERLAP_RNG
-#define SC_OVERLAP_RNG 0  // 1: draw step t+1's orders during step t
-#endif
 #ifndef SC_VEC_OBS
 #define SC_VEC_OBS 0      // 1: obs rows transposed through smem into 16-byte stores
 #endif
@@ -100,25 +98,29 @@ __device__ __forceinline__ float sc_ratio(int num, float den, float rcp) {
 #ifndef SC_UNROLL
 #define SC_UNROLL 2        // unroll factor of the step loop (2: +8 %, 4: same as 2)
 #endif
+#ifndef SC_PAIR
+#define SC_PAIR 0         // 1: two steps per loop trip, their two Philox blocks interleaved
+                          //    (measured slower: 55.0 vs 51.7 us -- the IMAD.WIDE bursts
+                          //    throttle the FMA pipe)
+#endif
 #ifndef SC_RING_DEPTH
 #define SC_RING_DEPTH 8   // action prefetch ring (steps in flight + 1)
 #endif
 constexpr int SC_BLOCK = SC_BLOCK_THREADS;
 constexpr int SC_RING = SC_RING_DEPTH;
 constexpr int SC_UNROLL_K = SC_UNROLL;
+constexpr int SC_TAIL_UNROLL = SC_PAIR ? 1 : SC_UNROLL_K;
 
-// The NC order sizes of one (episode, step): rng stream SC_STREAM_ORDER, idx = customer.
+// The NC order sizes of one (episode, step): packed draws (phx_rng.cuh) of RNG stream
+// SC_STREAM_ORDER, draw i = customer i.  NC <= kpw(max_order) here (the host checks), so a step
+// consumes ONE 32-bit word and one Philox block serves four steps.
 template <int NC>
 __device__ __forceinline__ void sc_draw_orders(const ScPlan& p, uint32_t env_id, uint32_t episode,
-                                               uint32_t step, int (&want)[NC > 0 ? NC : 1]) {
+                                               uint32_t step, PackedWords& words,
+                                               int (&want)[NC > 0 ? NC : 1]) {
+  uint32_t x = words.word(p.seed, env_id, episode, step, SC_STREAM_ORDER);
 #pragma unroll
-  for (int b = 0; b < (NC + 4) / 5; ++b) {
-    const Philox4 blk = rng_block(p.seed, env_id, episode, step, SC_STREAM_ORDER, b);
-#pragma unroll
-    for (int k = 0; k < 5; ++k)
-      if (b * 5 + k < NC)
-        want[b * 5 + k] = rng_randint(rng_slot_hi(blk, k), (uint32_t)p.max_order);
-  }
+  for (int i = 0; i < NC; ++i) want[i] = rng_next_digit(x, (uint32_t)p.max_order);
 }
 
 // One thread per env; T steps per launch with the env state in registers.
@@ -144,7 +146,9 @@ __global__ void __launch_bounds__(SC_BLOCK) sc_fast_kernel(const ScArgs a) {
   const float cap_f = p.cap_f, rcp_cap = p.rcp_cap;
   const float max_stock_f = p.max_stock_f, rcp_stock = p.rcp_stock;
   const uint32_t all_customers = nc >= 32 ? 0xFFFFFFFFu : ((1u << nc) - 1u);
-  const bool all_delivered = p.deliver_ord == all_customers;
+  // the NC > 0 instantiations without tracking are only launched when every customer's order
+  // is delivered (rollout_range checks; other graphs take the runtime-N path)
+  const bool all_delivered = (NC > 0 && !TRACK) ? true : p.deliver_ord == all_customers;
   // vector path for obs needs a full warp and 16-byte aligned rows
   const bool warp_full = (blockIdx.x * SC_BLOCK + warp * 32 + 32) <= (uint32_t)a.env_count;
   const bool vec_obs = SC_VEC_OBS && warp_full && ((p.E & 3) == 0);
@@ -175,15 +179,9 @@ __global__ void __launch_bounds__(SC_BLOCK) sc_fast_kernel(const ScArgs a) {
     cp_async_commit();
   }
 
-  // customers' OrderRequest sizes (supply_chain.py:64): RNG stream 0, idx = customer.  The
-  // draws of step t+1 depend only on the (episode, step) coordinates, so they are computed
-  // during step t: the two independent Philox chains then overlap the serial order fill.
-  int want_nxt[NC > 0 ? NC : 1];
-  if (NC > 0 && SC_OVERLAP_RNG)
-    sc_draw_orders<NC>(p, env_id, (uint32_t)h.y, (uint32_t)(h.x + 1), want_nxt);
-
-#pragma unroll(SC_UNROLL_K)
-  for (int t = 0; t < a.T; ++t) {
+  PackedWords words;  // current Philox block of the order-size word sequence
+  // One env transition.  `want` = this step's order sizes when NC > 0 (drawn by the caller).
+  auto one_step = [&](const int t, const int (&want)[NC > 0 ? NC : 1]) {
     if (t + SC_RING - 1 < a.T)
       cp_async4(&act_ring[(t + SC_RING - 1) % SC_RING][threadIdx.x],
                 a.io.actions + row + (uint32_t)(SC_RING - 1) * E);
@@ -196,17 +194,6 @@ __global__ void __launch_bounds__(SC_BLOCK) sc_fast_kernel(const ScArgs a) {
     const bool at_max = h.x == p.num_steps;  // env.py:312-318
     const bool wrap = (p.flags & PHX_FLAG_AUTO_RESET) && at_max;
 
-    int want[NC > 0 ? NC : 1];
-    if (NC > 0 && !SC_OVERLAP_RNG) {
-      sc_draw_orders<NC>(p, env_id, (uint32_t)h.y, (uint32_t)h.x, want);
-    } else if (NC > 0) {
-#pragma unroll
-      for (int i = 0; i < (NC > 0 ? NC : 1); ++i) want[i] = want_nxt[i];
-      // unconditional (one wasted draw on the last step) so that it shares a basic block
-      // with the fill below and the scheduler can interleave the two
-      sc_draw_orders<NC>(p, env_id, (uint32_t)(wrap ? h.y + 1 : h.y),
-                         (uint32_t)(wrap ? 1 : h.x + 1), want_nxt);
-    }
 
     // ---- acting phase (env.py:320-336), agent order SHOP, WAREHOUSE, CUST1..N
     // ShopAgent.decode_action: min(int(round(a)), max_stock - stock); python round() of a
@@ -233,14 +220,14 @@ __global__ void __launch_bounds__(SC_BLOCK) sc_fast_kernel(const ScArgs a) {
     int sold_each[NC > 0 ? NC : 1];
     (void)sold_each;
     if (NC == 0) {  // runtime-N path: draw and fill in place
-      for (int b = 0; b * 5 < nc; ++b) {
-        const Philox4 blk =
-            rng_block(p.seed, env_id, (uint32_t)h.y, (uint32_t)h.x, SC_STREAM_ORDER, b);
-#pragma unroll
-        for (int k = 0; k < 5; ++k) {
-          const int i = b * 5 + k;
-          const int w = rng_randint(rng_slot_hi(blk, k), (uint32_t)p.max_order);
-          if (i < nc && ((p.deliver_ord >> i) & 1u)) {
+      int i = 0;
+      for (int q = 0; q < p.words_per_step; ++q) {
+        uint32_t x = words.word(p.seed, env_id, (uint32_t)h.y,
+                                (uint32_t)h.x * (uint32_t)p.words_per_step + (uint32_t)q,
+                                SC_STREAM_ORDER);
+        for (int r = 0; r < p.digits_per_word && i < nc; ++r, ++i) {
+          const int w = rng_next_digit(x, (uint32_t)p.max_order);
+          if ((p.deliver_ord >> i) & 1u) {
             const int sold = min(w, s.x);
             s.x -= sold;
             wanted_total += w;
@@ -344,6 +331,34 @@ __global__ void __launch_bounds__(SC_BLOCK) sc_fast_kernel(const ScArgs a) {
     }
 
     row += E;
+  };
+
+  // customers' OrderRequest sizes (supply_chain.py:64): RNG stream 0, idx = customer.  The
+  // draws depend only on the (episode, step) coordinates, never on the env state, so the loop
+  // advances TWO steps per trip and draws both steps' orders first: the two Philox chains are
+  // independent and interleave in the issue stream (a single chain is 10 dependent
+  // multiply -> xor rounds, which 3.5 warps per scheduler cannot hide).
+  const bool auto_reset = (p.flags & PHX_FLAG_AUTO_RESET) != 0;
+  int t = 0;
+  if (NC > 0 && SC_PAIR) {
+#pragma unroll 1
+    for (; t + 1 < a.T; t += 2) {
+      const int step_a = h.x + 1;
+      const bool wrap_a = auto_reset && step_a == p.num_steps;
+      const int step_b = wrap_a ? 1 : step_a + 1;
+      const int ep_b = wrap_a ? h.y + 1 : h.y;
+      int want_a[NC > 0 ? NC : 1], want_b[NC > 0 ? NC : 1];
+      sc_draw_orders<NC>(p, env_id, (uint32_t)h.y, (uint32_t)step_a, words, want_a);
+      sc_draw_orders<NC>(p, env_id, (uint32_t)ep_b, (uint32_t)step_b, words, want_b);
+      one_step(t, want_a);
+      one_step(t + 1, want_b);
+    }
+  }
+#pragma unroll(SC_TAIL_UNROLL)
+  for (; t < a.T; ++t) {
+    int want[NC > 0 ? NC : 1];
+    if (NC > 0) sc_draw_orders<NC>(p, env_id, (uint32_t)h.y, (uint32_t)(h.x + 1), words, want);
+    one_step(t, want);
   }
 
   if (real) {
@@ -457,6 +472,8 @@ class SupplyChainFast final : public Family {
     p.nc = s.n_agents - 2;
     p.max_order = s.iparams[0];
     p.max_stock = s.iparams[1];
+    p.digits_per_word = rng_digits_per_word((uint32_t)p.max_order);
+    p.words_per_step = (p.nc + p.digits_per_word - 1) / p.digits_per_word;
     p.flags = s.flags;
     p.seed = seed;
     p.env_offset = (uint32_t)env_offset;
@@ -589,7 +606,9 @@ class SupplyChainFast final : public Family {
     else if (!lean) sc_fast_kernel<NC_, TRACK_, false, true><<<grid, SC_BLOCK, 0, stream>>>(a);    \
     else sc_fast_kernel<NC_, TRACK_, false, false><<<grid, SC_BLOCK, 0, stream>>>(a);              \
   } while (0)
-    if (plan.nc == 5) {
+    const bool all_delivered = plan.deliver_ord == (1u << plan.nc) - 1u;
+    // the NC = 5 instantiation draws a step's orders from one word
+    if (plan.nc == 5 && plan.words_per_step == 1 && (track || all_delivered)) {
       if (track) SC_LAUNCH(5, true);
       else SC_LAUNCH(5, false);
     } else {
@@ -668,8 +687,9 @@ struct ScProgram {
       const int ask = min(__float2int_rn(a0), sp.iparams[1] - st[0]);  // supply_chain.py:136-142
       out.send(sp.agent_iparam[c.slot][0], SC_STOCK_REQUEST, ask);
     } else if (c.kind == SC_CUSTOMER) {  // supply_chain.py:61-67
-      const int want = rng_randint(c.rand24_hi(SC_STREAM_ORDER, (uint32_t)sp.agent_iparam[c.slot][1]),
-                                   (uint32_t)sp.iparams[0]);
+      const int want = rng_packed_randint(sp.seed, c.env_id, c.episode, (uint32_t)c.step,
+                                          SC_STREAM_ORDER, (uint32_t)sp.iparams[0],
+                                          (uint32_t)sp.iparams[2], (uint32_t)sp.agent_iparam[c.slot][1]);
       out.send(sp.agent_iparam[c.slot][0], SC_ORDER_REQUEST, want);
     }
   }
@@ -736,6 +756,7 @@ class SupplyChainQueue final : public EngineFamily<ScProgram<SEGCAP_>> {
                     s.iparams[1] <= (1 << 20) && customers >= 1,
                 PHX_ERR_INVALID, "supply-chain family: parameters out of range");
     phx_spec t = s;  // obs denominators and their correctly rounded reciprocals
+    t.iparams[2] = customers;  // K of the packed order-size draws (ScProgram::act)
     t.fparams[0] = (double)s.iparams[1];
     t.fparams[1] = (double)(1.0f / (float)s.iparams[1]);
     t.fparams[2] = (double)(customers * s.iparams[0]);

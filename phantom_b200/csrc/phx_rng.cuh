@@ -78,4 +78,83 @@ __device__ __forceinline__ float rng_uniform01(uint32_t d24_hi) {
   return (float)(d24_hi >> 8) * 5.9604644775390625e-8f;
 }
 
+// ---------------------------------------------------------------------------------------
+// Packed small-integer draws (contract v3, oracle/rng.py "packed draws").
+//
+// A call site that draws K values of randint(n) per step with a small n (the supply chain's
+// customers: K = 5, n = 5) does not need 24 bits per draw.  Its draws are the base-n digits of
+// 32-bit Philox words, extracted by multiply-high (exact arithmetic decoding of the fraction
+// word / 2^32):
+//     x_0 = word;   digit_r = (x_r * n) >> 32;   x_{r+1} = (x_r * n) mod 2^32
+// A word yields kpw(n) digits, kpw = the largest j with n^j <= 2^16 (so every digit's
+// distribution is within 2^-16 relative of uniform; n = 5: 6 digits).  The site consumes
+//     W = ceil(K / kpw) words per step;   draw i of step s = digit (i % kpw) of word number
+//     g = s * W + i / kpw  of the site's word sequence;
+//     word g = w[g & 3] of Philox4x32-10(key = seed,
+//                                        ctr = (env, episode, g >> 2, (stream << 16) | 0x8000))
+// so consecutive steps share Philox blocks: with K <= kpw one block serves FOUR steps.
+__host__ __device__ inline int rng_digits_per_word(uint32_t n) {
+  int j = 1;
+  uint64_t pw = n;
+  while (pw * n <= 65536ull) {
+    pw *= n;
+    ++j;
+  }
+  return j;
+}
+
+__device__ __forceinline__ Philox4 rng_word_block(uint64_t seed, uint32_t env, uint32_t episode,
+                                                  uint32_t block, uint32_t stream) {
+  return philox4x32_10(env, episode, block, (stream << 16) | 0x8000u, (uint32_t)seed,
+                       (uint32_t)(seed >> 32));
+}
+
+// Per-thread cache of the current block of one site's word sequence.
+struct PackedWords {
+  Philox4 blk;
+  uint32_t block = 0xFFFFFFFFu, episode = 0xFFFFFFFFu;
+
+  // word number g of (env, episode, stream)
+  __device__ __forceinline__ uint32_t word(uint64_t seed, uint32_t env, uint32_t ep, uint32_t g,
+                                           uint32_t stream) {
+    const uint32_t b = g >> 2;
+    if (b != block || ep != episode) {
+      blk = rng_word_block(seed, env, ep, b, stream);
+      block = b;
+      episode = ep;
+    }
+    const uint32_t q = g & 3u;
+    uint32_t x = blk.w[0];
+    if (q == 1u) x = blk.w[1];
+    if (q == 2u) x = blk.w[2];
+    if (q == 3u) x = blk.w[3];
+    return x;
+  }
+};
+
+// next digit of x: returns it and advances x
+__device__ __forceinline__ int rng_next_digit(uint32_t& x, uint32_t n) {
+  const uint64_t prod = (uint64_t)x * n;
+  x = (uint32_t)prod;
+  return (int)(prod >> 32);
+}
+
+// draw i (of K per step) of a packed site, stand-alone (one block + i % kpw + 1 multiplies)
+__device__ __forceinline__ int rng_packed_randint(uint64_t seed, uint32_t env, uint32_t episode,
+                                                  uint32_t step, uint32_t stream, uint32_t n,
+                                                  uint32_t K, uint32_t i) {
+  const uint32_t kpw = (uint32_t)rng_digits_per_word(n);
+  const uint32_t W = (K + kpw - 1u) / kpw;
+  const uint32_t g = step * W + i / kpw;
+  const Philox4 b = rng_word_block(seed, env, episode, g >> 2, stream);
+  const uint32_t q = g & 3u;
+  uint32_t x = b.w[0];
+  if (q == 1u) x = b.w[1];
+  if (q == 2u) x = b.w[2];
+  if (q == 3u) x = b.w[3];
+  int d = 0;
+  for (uint32_t r = 0; r <= i % kpw; ++r) d = rng_next_digit(x, n);
+  return d;
+}
+
 }  // namespace phx

@@ -36,7 +36,7 @@ def build_pair(case_seed: int, exec_mode: str):
         env.max_order, env.max_stock = 5, 100
         return env
 
-    st = rng.StepStream(seed, 0, 0)
+    st = wl.order_stream(seed, 0, n_customers=nc)
     ref = wl.build(po, st, n_customers=nc, num_steps=12, enable_tracking=True)
     ref.network.ignore_connection_errors = True
     ref.network.agents = {k: ref.network.agents[k] for k in order}

@@ -25,7 +25,7 @@ def test_supply_chain_metrics_match_oracle_attributes():
     }
     seed = 5
     env = SupplyChainEnv(seed=seed)
-    st = rng.StepStream(seed, 0, 0)
+    st = wl.order_stream(seed, 0)
     ref = wl.build(po, st)
     clock = harness.EpisodeClock([st])
     clock.on_reset(); ref.reset(); env.reset()

@@ -169,7 +169,7 @@ def test_dict_api_drop_in_matches_oracle(sc, ph):
     object-level oracle stepping the same env definition."""
     seed = 31
     env = sc.SupplyChainEnv(seed=seed)
-    st = rng.StepStream(seed, 0, 0)
+    st = wl.order_stream(seed, 0)
     ref = wl.build(po, st)
     clock = harness.EpisodeClock([st])
     assert env.agent_ids == ref.agent_ids and env.strategic_agent_ids == ["SHOP"]
@@ -277,7 +277,7 @@ def test_ignore_connection_errors_drops_undeliverable_mail(sc):
     env = sc.SupplyChainEnv(seed=seed)
     env.network.ignore_connection_errors = True
     del env.network._succ["SHOP"]["CUST2"], env.network._succ["CUST2"]["SHOP"]
-    st = rng.StepStream(seed, 0, 0)
+    st = wl.order_stream(seed, 0)
     ref = wl.build(po, st)
     ref.network.ignore_connection_errors = True
     del ref.network.graph._succ["SHOP"]["CUST2"], ref.network.graph._succ["CUST2"]["SHOP"]
@@ -405,7 +405,7 @@ def test_queue_engine_any_agent_order(sc, ph):
     env = build(ph, sc)
     assert env.exec_name.startswith("thread-per-env")
     # oracle twin with the same order
-    st = rng.StepStream(seed, 0, 0)
+    st = wl.order_stream(seed, 0, n_customers=3)
     ref_full = wl.build(po, st, n_customers=3, num_steps=20, enable_tracking=True)
     order = ["CUST1", "CUST2", "WAREHOUSE", "CUST3", "SHOP"]
     ref_full.network.agents = {k: ref_full.network.agents[k] for k in order}

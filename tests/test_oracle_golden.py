@@ -42,6 +42,36 @@ def test_contract_scalar_equals_vectorised():
     assert rng.d24(9, 3, 0, 1, 0, 5) == rng.philox4x32((3, 0, 1, 1), (9, 0))[0] >> 8
 
 
+def test_packed_draws():
+    """Contract v3: base-n digits of Philox words; scalar == vectorised == PackedStream, one
+    block serves four steps when K <= kpw, and the digits are uniform and uncorrelated."""
+    assert [rng.digits_per_word(n) for n in (2, 5, 16, 255, 256)] == [16, 6, 4, 2, 2]
+    for n, K in [(5, 5), (5, 7), (255, 30), (2, 20), (16, 9)]:
+        a = rng.packed_randint_np(7, np.arange(3)[:, None], 1, np.arange(9)[None, :], 0, n, K)
+        assert a.shape == (3, 9, K) and a.min() >= 0 and a.max() < n
+        for e in range(3):
+            st = rng.PackedStream(7, e, 0, n, K)
+            for step in range(9):
+                st.begin(1, step)
+                want = [rng.packed_randint(7, e, 1, step, 0, n, K, i) for i in range(K)]
+                assert a[e, step].tolist() == want == [st.randint(n) for _ in range(K)]
+    # word layout: K = n = 5 -> draw i of step s = digit i of word s; word s = w[s & 3] of
+    # block s >> 2 with the 0x8000 marker in the counter's stream word
+    w = rng.philox4x32((3, 2, 6 >> 2, 0x8000), (9, 0))
+    x, digits = w[6 & 3], []
+    for _ in range(5):
+        x *= 5
+        digits.append(x >> 32)
+        x &= 0xFFFFFFFF
+    assert [rng.packed_randint(9, 3, 2, 6, 0, 5, 5, i) for i in range(5)] == digits
+    big = rng.packed_randint_np(3, np.arange(20000)[:, None], 0, np.arange(1, 11)[None, :], 0, 5, 5)
+    freq = np.bincount(big.ravel(), minlength=5) / big.size
+    assert np.abs(freq - 0.2).max() < 0.003
+    flat = big.reshape(-1, 5).astype(np.float64)
+    c = np.corrcoef(flat.T)
+    assert np.abs(c - np.eye(5)).max() < 0.01
+
+
 def test_survey_probe_trace():
     """SURVEY.md 3.6 / 8c probe: np.random.seed(0) orders (4,0,3,3,3 then ...) are not
     reproducible under the contract stream, but the dynamics are: feed the same orders."""
@@ -72,7 +102,7 @@ def test_object_oracle_matches_reference_golden(sc_golden):
     g = sc_golden
     seed, A, M = int(g["seed"]), g["actions"], g["action_mask"]
     for e in range(A.shape[0]):
-        st = rng.StepStream(seed, e, wl.STREAM_CUSTOMER_ORDER)
+        st = wl.order_stream(seed, e)
         env = wl.build(po, st, enable_tracking=e < 3)
         tr = harness.run_supply_chain(env, harness.EpisodeClock([st]), A[e], M[e], track=e < 3)
         for k in ["reset_obs"] + STEP_KEYS:
