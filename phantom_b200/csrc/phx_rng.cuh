@@ -132,6 +132,35 @@ struct PackedWords {
   }
 };
 
+// Sequential reader of one site's word sequence for K <= kpw sites (one word per step): the
+// four words of a block are handed out in step order and the next block is fetched when they
+// run out -- no per-step block compare or word select.  Steps must be consumed consecutively;
+// call flush() when the (episode, step) coordinates jump (reset / auto-reset wrap).
+struct PackedWordQueue {
+  uint32_t w0, w1, w2, w3;
+  int left = 0;
+
+  __device__ __forceinline__ void flush() { left = 0; }
+
+  // the word of `step` (word number g = step)
+  __device__ __forceinline__ uint32_t take(uint64_t seed, uint32_t env, uint32_t ep, uint32_t step,
+                                           uint32_t stream) {
+    if (left == 0) {
+      const Philox4 b = rng_word_block(seed, env, ep, step >> 2, stream);
+      w0 = b.w[0]; w1 = b.w[1]; w2 = b.w[2]; w3 = b.w[3];
+      const uint32_t skip = step & 3u;  // 0 except right after a flush
+      if (skip >= 1u) { w0 = w1; w1 = w2; w2 = w3; }
+      if (skip >= 2u) { w0 = w1; w1 = w2; }
+      if (skip >= 3u) { w0 = w1; }
+      left = 4 - (int)skip;
+    }
+    const uint32_t x = w0;
+    w0 = w1; w1 = w2; w2 = w3;
+    --left;
+    return x;
+  }
+};
+
 // next digit of x: returns it and advances x
 __device__ __forceinline__ int rng_next_digit(uint32_t& x, uint32_t n) {
   const uint64_t prod = (uint64_t)x * n;
