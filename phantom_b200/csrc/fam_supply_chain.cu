@@ -65,6 +65,7 @@ struct ScArgs {
   ScPlan p;
   int32_t T;
   int32_t env_begin, env_count;  // sub-range of the handle's envs stepped by this launch
+  int32_t vec_actions;           // 16-byte action copies are legal (alignment, full warps)
   int4* hdr;
   int4* shop;
   StepIO io;
@@ -95,22 +96,8 @@ __device__ __forceinline__ float sc_ratio(int num, float den, float rcp) {
 #ifndef SC_REWARD_F64
 #define SC_REWARD_F64 0   // 1: reference-literal float64 reward arithmetic
 #endif
-#ifndef SC_UNROLL
-#define SC_UNROLL 8        // unroll factor of the step loop (= ring depth: static ring slots;
-                          // 36.9 us vs 38.9 us at 2 or 4)
-#endif
-#ifndef SC_PAIR
-#define SC_PAIR 0         // 1: two steps per loop trip, their two Philox blocks interleaved
-                          //    (measured slower: 55.0 vs 51.7 us -- the IMAD.WIDE bursts
-                          //    throttle the FMA pipe)
-#endif
-#ifndef SC_RING_DEPTH
-#define SC_RING_DEPTH 8   // action prefetch ring (steps in flight + 1)
-#endif
 constexpr int SC_BLOCK = SC_BLOCK_THREADS;
-constexpr int SC_RING = SC_RING_DEPTH;
-constexpr int SC_UNROLL_K = SC_UNROLL;
-constexpr int SC_TAIL_UNROLL = SC_PAIR ? 1 : SC_UNROLL_K;
+constexpr int SC_RING = 8;  // action ring: two groups of four steps
 
 // The NC order sizes of one (episode, step): packed draws (phx_rng.cuh) of RNG stream
 // SC_STREAM_ORDER, draw i = customer i.  NC <= kpw(max_order) here (the host checks), so a step
@@ -168,35 +155,55 @@ __global__ void __launch_bounds__(SC_BLOCK) sc_fast_kernel(const ScArgs a) {
   // row = t * E + e indexes every [T,E,...] plane (the host guarantees T * E * 3 < 2^32)
   uint32_t row = (uint32_t)e;
 
-  // Actions are prefetched SC_RING-1 steps ahead with cp.async (LDGSTS) into a per-thread
-  // shared-memory ring.  HBM latency is ~0.6 us = more than one whole step of this kernel
-  // (measured: a register prefetch one step ahead still stalled 31% of all warp samples on
-  // its scoreboard); the async copy has no register to wait on and the ring gives it
-  // SC_RING-1 steps to land.
-  __shared__ float act_ring[SC_RING][SC_BLOCK];
+  // Actions reach the kernel through a shared-memory ring filled by cp.async (LDGSTS), four
+  // steps per copy group, one to two groups ahead.  HBM latency is ~0.6 us = more than a whole
+  // step of this kernel (measured: a register prefetch one step ahead still stalled 31 % of all
+  // warp samples on its scoreboard); the async copy has no register to wait on.
+  //   vector form (a.vec_actions): ONE 16-byte LDGSTS per lane moves a warp's 32 actions of
+  //     FOUR steps (lane -> step lane/8, env quad lane%8: the 32 actions of a step are 128
+  //     contiguous bytes of the [T,E] plane) -- per step 1/4 of a copy instruction instead of a
+  //     whole one plus its address arithmetic.  Lanes read what other lanes copied, hence the
+  //     __syncwarp() after each wait and before a slot is overwritten.
+  //   scalar form: every lane copies its own four actions (any alignment, partial warps).
+  __shared__ __align__(16) float act_ring[SC_RING][SC_BLOCK];
+  const int T = a.T;
+  const bool vec = a.vec_actions != 0;
+  const int cj = lane >> 3;  // vector form: the step (within a group) this lane copies
+  const float* src = vec ? a.io.actions + (size_t)cj * E + (size_t)(e - lane + 4 * (lane & 7))
+                         : a.io.actions + e;
+  float* const dst = vec ? &act_ring[cj][warp * 32 + 4 * (lane & 7)] : &act_ring[0][threadIdx.x];
+  // copies the actions of steps tg .. tg+3 into slots slot0 .. slot0+3 and commits the group
+  auto fetch_group = [&](const int tg, const int slot0) {
+    if (vec) {
+      if (tg + cj < T) cp_async16(dst + slot0 * SC_BLOCK, src);
+    } else {
 #pragma unroll
-  for (int k = 0; k < SC_RING - 1; ++k) {
-    if (k < a.T) cp_async4(&act_ring[k][threadIdx.x], a.io.actions + row + (uint32_t)k * E);
+      for (int k = 0; k < 4; ++k)
+        if (tg + k < T) cp_async4(dst + (slot0 + k) * SC_BLOCK, src + (size_t)k * E);
+    }
+    src += (size_t)4 * E;
     cp_async_commit();
-  }
+  };
+  fetch_group(0, 0);
+  fetch_group(4, 4);
 
   // the order-size word sequence: NC > 0 consumes one word per step, in step order
   PackedWordQueue wordq;
   PackedWords words;  // runtime-N path: several words per step
-  // One env transition.  `want` = this step's order sizes when NC > 0 (drawn by the caller).
-  auto one_step = [&](const int t, const int (&want)[NC > 0 ? NC : 1]) {
-    if (t + SC_RING - 1 < a.T)
-      cp_async4(&act_ring[(t + SC_RING - 1) % SC_RING][threadIdx.x],
-                a.io.actions + row + (uint32_t)(SC_RING - 1) * E);
-    cp_async_commit();
-    cp_async_wait<SC_RING - 1>();  // this step's copy (issued SC_RING-1 steps ago) has landed
-    const float act = act_ring[t % SC_RING][threadIdx.x];
+  const bool auto_reset = (p.flags & PHX_FLAG_AUTO_RESET) != 0;
+  // One env transition with action `act`.
+  auto one_step = [&](const float act) {
+    // customers' OrderRequest sizes (supply_chain.py:64): packed draws, one word per step
+    int want[NC > 0 ? NC : 1];
+    if (NC > 0) {
+      sc_draw_orders<NC>(p, env_id, (uint32_t)h.y, (uint32_t)(h.x + 1), wordq, want);
+      if (auto_reset && h.x + 1 == p.num_steps) wordq.flush();  // next step: (episode + 1, 1)
+    }
     bool has = true;
     if (HAS_MASK) has = live ? (a.io.action_mask[row] != 0) : false;
     h.x += 1;  // env.py:252
     const bool at_max = h.x == p.num_steps;  // env.py:312-318
-    const bool wrap = (p.flags & PHX_FLAG_AUTO_RESET) && at_max;
-
+    const bool wrap = auto_reset && at_max;
 
     // ---- acting phase (env.py:320-336), agent order SHOP, WAREHOUSE, CUST1..N
     // ShopAgent.decode_action: min(int(round(a)), max_stock - stock); python round() of a
@@ -336,38 +343,26 @@ __global__ void __launch_bounds__(SC_BLOCK) sc_fast_kernel(const ScArgs a) {
     row += E;
   };
 
-  // customers' OrderRequest sizes (supply_chain.py:64): RNG stream 0, idx = customer.  The
-  // draws depend only on the (episode, step) coordinates, never on the env state, so the loop
-  // advances TWO steps per trip and draws both steps' orders first: the two Philox chains are
-  // independent and interleave in the issue stream (a single chain is 10 dependent
-  // multiply -> xor rounds, which 3.5 warps per scheduler cannot hide).
-  const bool auto_reset = (p.flags & PHX_FLAG_AUTO_RESET) != 0;
-  int t = 0;
-  if (NC > 0 && SC_PAIR) {
+  int t0 = 0;
 #pragma unroll 1
-    for (; t + 1 < a.T; t += 2) {
-      const int step_a = h.x + 1;
-      const bool wrap_a = auto_reset && step_a == p.num_steps;
-      const int step_b = wrap_a ? 1 : step_a + 1;
-      const int ep_b = wrap_a ? h.y + 1 : h.y;
-      int want_a[NC > 0 ? NC : 1], want_b[NC > 0 ? NC : 1];
-      sc_draw_orders<NC>(p, env_id, (uint32_t)h.y, (uint32_t)step_a, wordq, want_a);
-      if (wrap_a) wordq.flush();
-      sc_draw_orders<NC>(p, env_id, (uint32_t)ep_b, (uint32_t)step_b, wordq, want_b);
-      if (auto_reset && step_b == p.num_steps) wordq.flush();
-      one_step(t, want_a);
-      one_step(t + 1, want_b);
-    }
+  for (; t0 + SC_RING <= T; t0 += SC_RING) {
+    cp_async_wait<1>();  // steps t0 .. t0+3 have landed (t0+4 .. t0+7 may be in flight)
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) one_step(act_ring[j][threadIdx.x]);
+    __syncwarp();  // every lane has read slots 0..3
+    fetch_group(t0 + 8, 0);
+    cp_async_wait<1>();
+    __syncwarp();
+#pragma unroll
+    for (int j = 4; j < 8; ++j) one_step(act_ring[j][threadIdx.x]);
+    __syncwarp();
+    fetch_group(t0 + 12, 4);
   }
-#pragma unroll(SC_TAIL_UNROLL)
-  for (; t < a.T; ++t) {
-    int want[NC > 0 ? NC : 1];
-    if (NC > 0) {
-      sc_draw_orders<NC>(p, env_id, (uint32_t)h.y, (uint32_t)(h.x + 1), wordq, want);
-      if (auto_reset && h.x + 1 == p.num_steps) wordq.flush();  // next step: (episode + 1, 1)
-    }
-    one_step(t, want);
-  }
+  cp_async_wait<0>();  // tail (< 8 steps): both of its groups were issued above
+  __syncwarp();
+#pragma unroll 1
+  for (int t = t0; t < T; ++t) one_step(act_ring[t - t0][threadIdx.x]);
 
   if (real) {
     *reinterpret_cast<int2*>(a.hdr + e) = h;
@@ -565,6 +560,9 @@ class SupplyChainFast final : public Family {
     a.T = T;
     a.env_begin = env_begin;
     a.env_count = env_count;
+    // the vector action copy reads 4 consecutive envs of one step with one 16-byte cp.async
+    a.vec_actions = (E % 4 == 0) && (env_begin % 4 == 0) && (env_count % 32 == 0) &&
+                    (reinterpret_cast<uintptr_t>(io.actions) % 16 == 0);
     a.hdr = d_hdr;
     a.shop = d_shop;
     a.io = io;

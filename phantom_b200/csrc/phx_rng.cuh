@@ -163,7 +163,8 @@ struct PackedWordQueue {
 
 // next digit of x: returns it and advances x
 __device__ __forceinline__ int rng_next_digit(uint32_t& x, uint32_t n) {
-  const uint64_t prod = (uint64_t)x * n;
+  uint64_t prod;  // one IMAD.WIDE.U32 (plain C++ widens n to 64 bits and adds a zero high part)
+  asm("mul.wide.u32 %0, %1, %2;" : "=l"(prod) : "r"(x), "r"(n));
   x = (uint32_t)prod;
   return (int)(prod >> 32);
 }
