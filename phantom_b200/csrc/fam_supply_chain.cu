@@ -97,7 +97,11 @@ __device__ __forceinline__ float sc_ratio(int num, float den, float rcp) {
 #define SC_REWARD_F64 0   // 1: reference-literal float64 reward arithmetic
 #endif
 constexpr int SC_BLOCK = SC_BLOCK_THREADS;
-constexpr int SC_RING = 8;  // action ring: two groups of four steps
+#ifndef SC_GROUPS
+#define SC_GROUPS 3       // action ring = SC_GROUPS copy groups of four steps
+#endif
+constexpr int SC_NG = SC_GROUPS;
+constexpr int SC_RING = 4 * SC_NG;
 
 // The NC order sizes of one (episode, step): packed draws (phx_rng.cuh) of RNG stream
 // SC_STREAM_ORDER, draw i = customer i.  NC <= kpw(max_order) here (the host checks), so a step
@@ -184,8 +188,8 @@ __global__ void __launch_bounds__(SC_BLOCK) sc_fast_kernel(const ScArgs a) {
     src += (size_t)4 * E;
     cp_async_commit();
   };
-  fetch_group(0, 0);
-  fetch_group(4, 4);
+#pragma unroll
+  for (int g = 0; g < SC_NG; ++g) fetch_group(4 * g, 4 * g);
 
   // the order-size word sequence: NC > 0 consumes one word per step, in step order
   PackedWordQueue wordq;
@@ -343,23 +347,23 @@ __global__ void __launch_bounds__(SC_BLOCK) sc_fast_kernel(const ScArgs a) {
     row += E;
   };
 
+  // The loop body covers the whole ring (SC_NG groups), so every ring slot is a compile-time
+  // offset.  Measured (us/launch): SC_NG = 2: 35.9, 3: 34.1, 4: 35.3, 6: 39.4 (instruction
+  // cache); a one-group body with a runtime slot: 34.9 (3 groups) .. 36.6 (8 groups).
   int t0 = 0;
 #pragma unroll 1
   for (; t0 + SC_RING <= T; t0 += SC_RING) {
-    cp_async_wait<1>();  // steps t0 .. t0+3 have landed (t0+4 .. t0+7 may be in flight)
-    __syncwarp();
 #pragma unroll
-    for (int j = 0; j < 4; ++j) one_step(act_ring[j][threadIdx.x]);
-    __syncwarp();  // every lane has read slots 0..3
-    fetch_group(t0 + 8, 0);
-    cp_async_wait<1>();
-    __syncwarp();
+    for (int g = 0; g < SC_NG; ++g) {
+      cp_async_wait<SC_NG - 1>();  // group g has landed (the SC_NG-1 younger ones may be in flight)
+      __syncwarp();
 #pragma unroll
-    for (int j = 4; j < 8; ++j) one_step(act_ring[j][threadIdx.x]);
-    __syncwarp();
-    fetch_group(t0 + 12, 4);
+      for (int j = 0; j < 4; ++j) one_step(act_ring[4 * g + j][threadIdx.x]);
+      __syncwarp();  // every lane has read slots 4g .. 4g+3
+      fetch_group(t0 + SC_RING + 4 * g, 4 * g);
+    }
   }
-  cp_async_wait<0>();  // tail (< 8 steps): both of its groups were issued above
+  cp_async_wait<0>();  // tail (< SC_RING steps): its groups were issued above
   __syncwarp();
 #pragma unroll 1
   for (int t = t0; t < T; ++t) one_step(act_ring[t - t0][threadIdx.x]);
