@@ -86,7 +86,7 @@ __device__ __forceinline__ float sc_ratio(int num, float den, float rcp) {
   return __fmaf_rn(r, rcp, q);
 }
 
-// Tuning knobs (defaults = the measured best, see profiles/README.md; override with -D for A/B)
+// Tuning knobs (defaults = the measured best; override with -D for A/B)
 #ifndef SC_BLOCK_THREADS
 #define SC_BLOCK_THREADS 64
 #endif
