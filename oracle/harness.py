@@ -180,12 +180,14 @@ def run_supply_chain(env, clock: EpisodeClock, actions: np.ndarray,
 
 
 def run_generic(env, clock: EpisodeClock, actions: np.ndarray, action_mask: np.ndarray,
-                obs_dim: int, track: bool = False, state_fn=None) -> Dict[str, np.ndarray]:
+                obs_dim: int, track: bool = False, state_fn=None,
+                convert=None) -> Dict[str, np.ndarray]:
     """Run actions.shape[0] episodes x actions.shape[1] steps of ANY env built with the
     plugin API and record the tensors of the C-ABI layout.
 
     actions f32 [n_ep, T, S, A]; action_mask u8 [n_ep, T, S] (0 => agent absent from the
-    `actions` mapping).  Discrete action spaces receive int(round(a[0])).
+    `actions` mapping).  Discrete action spaces receive int(round(a[0])); `convert(s, a)`
+    overrides how strategic agent s's action row becomes the value handed to the env.
     Outputs (S = strategic agents in env order):
       obs f32 [n_ep,T,S,O] (zero padded), obs_mask u8, reward f64, reward_mask u8 (0 absent,
       1 value, 2 None), term/trunc u8 (255 = key absent), all_done u8 [..,2];
@@ -227,7 +229,10 @@ def run_generic(env, clock: EpisodeClock, actions: np.ndarray, action_mask: np.n
             for s, aid in enumerate(ids):
                 if action_mask[ep, t, s]:
                     a = actions[ep, t, s]
-                    acts[aid] = int(round(float(a[0]))) if discrete[s] else a
+                    if convert is not None:
+                        acts[aid] = convert(s, a)
+                    else:
+                        acts[aid] = int(round(float(a[0]))) if discrete[s] else a
             if track:
                 env.network.resolver.clear_tracked_messages()
             step = env.step(acts)

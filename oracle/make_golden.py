@@ -260,6 +260,38 @@ def gen_shuffle_and_stochastic_reference() -> None:
         print(name, {k: v.shape for k, v in out.items()}, "mean degree", out["adjacency"].mean())
 
 
+SIMPLE_MARKET_WIDE_BUYERS = ((0.3, 0.1, 0.9), (0.8, 0.5, 1.0), (0.6, 0.0, 1.0), (0.5, 0.25, 0.25))
+
+
+def gen_simple_market_reference() -> None:
+    """The reference's own examples/environments/simple_market modules, UNMODIFIED (imported by
+    oracle/workloads/simple_market.py:build_reference), under the contract RNG:
+      simple_market_reference.npz       the example script's cast: 3 buyers + 2 sellers, 10 steps
+      simple_market_wide_reference.npz  4 buyers with non-degenerate type samplers + 3 sellers
+                                        (np.mean over three prices), 12 steps"""
+    from .workloads import simple_market as wl
+
+    for name, buyers, n_sellers, T, n_env, n_ep, seed in (
+            ("simple_market_reference.npz", wl.EXAMPLE_BUYERS, wl.EXAMPLE_SELLERS, 10, 8, 3, 20261024),
+            ("simple_market_wide_reference.npz", SIMPLE_MARKET_WIDE_BUYERS, 3, 12, 6, 2, 20261025)):
+        actions, mask = wl.actions_for(n_env, n_ep, T, len(buyers), n_sellers, seed % 1000)
+        per_env = []
+        for e in range(n_env):
+            coords = wl.Coords(seed, e)
+            with wl.contract_rng(coords, {f"b{i + 1}": i for i in range(len(buyers))}):
+                env, _ = wl.build_reference(buyers, n_sellers, T)
+                clock = harness.EpisodeClock([coords])
+                tr = harness.run_generic(env, clock, actions[e], mask[e], wl.OBS_DIM,
+                                         state_fn=wl.state, convert=wl.to_action(env))
+            tr["messages"] = []
+            per_env.append(tr)
+        out = pack_generic(per_env, actions, mask, seed, 0, {})
+        out["buyers"] = np.array(buyers, np.float64)
+        out["n_sellers"] = np.int64(n_sellers)
+        np.savez_compressed(os.path.join(GOLDEN, name), **out)
+        print(name, {k: v.shape for k, v in out.items()})
+
+
 def main() -> int:
     if not ref_shim.reference_available():
         print("reference not available")
@@ -271,6 +303,7 @@ def main() -> int:
     gen_dense_reference()
     gen_supply_chain2_reference()
     gen_shuffle_and_stochastic_reference()
+    gen_simple_market_reference()
     return 0
 
 

@@ -304,3 +304,28 @@ def test_object_oracle_matches_stochastic_network_golden(golden_dir):
                 if rng.d24(seed, e, ep, 0, wl.STREAM_CONNECTIVITY, c) / 16777216.0 < rate[c]:
                     want[u, v] = want[v, u] = 1
             assert np.array_equal(want, g["adjacency"][e, ep]), (e, ep)
+
+
+@pytest.mark.parametrize("name", ["simple_market_reference.npz", "simple_market_wide_reference.npz"])
+def test_object_oracle_matches_simple_market_golden(golden_dir, name):
+    """The reference's own simple_market example (env-level post_message_resolution + custom
+    EnvView field, two-stage FSM, three RNG call sites): oracle restatement == the unmodified
+    example modules run by the reference, float64 state included."""
+    from oracle.workloads import simple_market as sm
+
+    from .generic_parity import assert_oracle_trace_equal
+
+    g = np.load(os.path.join(golden_dir, name))
+    seed, A, M = int(g["seed"]), g["actions"], g["action_mask"]
+    buyers, n_sellers, T = [tuple(b) for b in g["buyers"]], int(g["n_sellers"]), A.shape[2]
+    for e in range(A.shape[0]):
+        coords = sm.Coords(seed, e)
+        with sm.contract_rng(coords, {f"b{i + 1}": i for i in range(len(buyers))}):
+            env, _ = sm.build(po, po.utils.samplers.UniformFloatSampler, buyers, n_sellers, T)
+            tr = harness.run_generic(env, harness.EpisodeClock([coords]), A[e], M[e], sm.OBS_DIM,
+                                     state_fn=sm.state, convert=sm.to_action(env))
+        assert_oracle_trace_equal(tr, g, e)
+    # the fixture exercises what it is meant to: ties between sellers, withheld buyer actions,
+    # None rewards at the first buyer observation, and a moving avg_price in the sellers' obs
+    assert (g["reward_mask"] == 2).any() and (M == 0).any()
+    assert len(np.unique(g["state"][..., -1, 0])) > 10
