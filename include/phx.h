@@ -78,6 +78,8 @@ typedef enum phx_family {
   PHX_FAMILY_MARKET = 3,       /* 3-stage FSM market (BASELINE config C3)             */
   PHX_FAMILY_STACKELBERG = 4,  /* leader/follower pricing game (BASELINE config C4)   */
   PHX_FAMILY_DENSE = 5,        /* dense-graph broadcast + batch aggregation (C5)      */
+  PHX_FAMILY_SIMPLE_MARKET = 7,/* examples/environments/simple_market/ (2-stage FSM, env-level
+                                  post_message_resolution + custom EnvView field)         */
   PHX_FAMILY_SUPPLY_CHAIN2 = 6 /* multi-shop supply chain with agent supertypes
                                   (docs/user/tutorial2.rst)                           */
 } phx_family;
@@ -182,6 +184,9 @@ typedef enum phx_field {
   PHX_FIELD_ERROR = 5,      /* uint32[E]   sticky fault word                         */
   PHX_FIELD_ADJACENCY = 6,  /* uint32[E,n_agents] per-env adjacency rows of a
                                StochasticNetwork (bit r of row s: edge s -> r)       */
+  PHX_FIELD_ENV_STATE = 7,  /* int32 [E]   env-level state word `index` of env classes that keep
+                               state of their own (e.g. simple_market's avg_price, float64
+                               bits in words 0/1)                                        */
   PHX_FIELD_FAMILY = 16
 } phx_field;
 

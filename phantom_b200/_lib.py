@@ -33,6 +33,7 @@ ENV_BASE, ENV_FSM, ENV_STACKELBERG = 0, 1, 2
 # phx_family
 FAMILY_SUPPLY_CHAIN, FAMILY_MOCK, FAMILY_MARKET, FAMILY_STACKELBERG, FAMILY_DENSE = 1, 2, 3, 4, 5
 FAMILY_SUPPLY_CHAIN2 = 6
+FAMILY_SIMPLE_MARKET = 7
 # phx_exec_mode
 EXEC_AUTO, EXEC_QUEUE, EXEC_FAST, EXEC_THREAD = 0, 1, 2, 3
 EXEC_MODES = {"auto": EXEC_AUTO, "queue": EXEC_QUEUE, "fast": EXEC_FAST, "thread": EXEC_THREAD}
@@ -42,6 +43,7 @@ FLAG_STOCHASTIC_NETWORK, FLAG_SHUFFLE_BATCHES = 16, 32
 # phx_field
 FIELD_STEP, FIELD_EPISODE, FIELD_STAGE, FIELD_TERMINATED, FIELD_TRUNCATED, FIELD_ERROR = range(6)
 FIELD_ADJACENCY = 6
+FIELD_ENV_STATE = 7
 FIELD_FAMILY = 16
 
 _MaskWords = C.c_uint32 * PHX_MASK_WORDS

@@ -82,7 +82,7 @@ int32_t Family::field_ptr(int32_t field, int32_t index, void** p, size_t* bytes)
     default:
       break;
   }
-  if (field >= PHX_FIELD_FAMILY || field == PHX_FIELD_ADJACENCY)
+  if (field >= PHX_FIELD_FAMILY || field == PHX_FIELD_ADJACENCY || field == PHX_FIELD_ENV_STATE)
     return family_field(field, index, p, bytes);
   set_error("unknown field id " + std::to_string(field));
   return PHX_ERR_INVALID;
@@ -208,6 +208,9 @@ int32_t phx_create(const phx_spec* spec, int32_t num_envs, int32_t device, uint6
       break;
     case PHX_FAMILY_SUPPLY_CHAIN2:
       fam = phx::make_supply_chain2_family(*spec);
+      break;
+    case PHX_FAMILY_SIMPLE_MARKET:
+      fam = phx::make_simple_market_family(*spec);
       break;
     default:
       set_error("no device program for family " + std::to_string(spec->family));

@@ -29,10 +29,32 @@
 // `messages[receiver]`, resolvers.py:126,142).  Handlers of different receivers only touch
 // their own agent's state, so all receivers of a round run in parallel.
 #pragma once
+#include <type_traits>
+
 #include "phx_common.cuh"
 #include "phx_rng.cuh"
 
 namespace phx {
+
+// ENV-LEVEL state and hooks (optional part of the device-program interface).  An env class may
+// keep state of its own, publish it to the agents as extra EnvView fields and update it in an
+// override of PhantomEnv.post_message_resolution (phantom/env.py:175-178) -- the reference's
+// simple_market example does (simple_mkt_env.py:46-58: avg_price = mean of the sellers'
+// prices).  A program opts in with
+//     static constexpr int ENVW = <words>;                         // persisted int32 [ENVW][E]
+//     template <class Acc> static void env_post(const Ctx&, int* env, Acc agent_word);
+// `env_post` runs after the agents' post hooks; `agent_word(slot, w)` reads word w of any
+// agent's state (w must be a compile-time constant at the call site).  `Ctx::env` is the
+// START-OF-STEP snapshot of the env words, because the reference builds the EnvView once, in
+// _make_ctxs (env.py:338-348), before any message is handled.
+template <class P, class = void>
+struct EnvWords {
+  static constexpr int value = 0;
+};
+template <class P>
+struct EnvWords<P, std::void_t<decltype(P::ENVW)>> {
+  static constexpr int value = P::ENVW;
+};
 
 constexpr int ENGINE_BLOCK = 128;
 constexpr int ENGINE_MAX_AGENTS = 32;
@@ -84,6 +106,7 @@ struct Ctx {
   uint32_t in_mask;    // adjacency column: bit s = edge s -> slot
   const int* views;    // start-of-step snapshot, [slot][VW] (this env's tile, shared memory)
   int view_stride;
+  const int* env;      // start-of-step snapshot of the env-level words (custom EnvView fields)
   const int8_t* kind_tab;   // per-slot tables staged in shared memory (dynamic lookups by
   const int32_t* ip0_tab;   // sender / receiver slot would serialise on the constant bank)
   __device__ __forceinline__ float proportion_time_elapsed() const {
@@ -166,6 +189,7 @@ struct EngineArgs {
   uint32_t* reward_none;// [E]      bit slot: cached reward is None
   float* obs_cache;     // [E][G][O] FSM `_observations` (by slot)
   uint32_t* obs_cached; // [E]      bit slot: an obs is cached
+  int32_t* env_state;   // [ENVW][E] env-level words of the program (nullptr if ENVW == 0)
   uint32_t* adj_env;    // [E][G]   StochasticNetwork: per-env adjacency rows (nullptr otherwise)
   const uint2* base_conn;  // [n_base] {u | v << 8, ceil(rate * 2^24)} in insertion order
   int32_t n_base;
@@ -481,11 +505,19 @@ __global__ void __launch_bounds__(ENGINE_BLOCK) engine_step_kernel(const EngineA
     if (sp.env_kind == PHX_ENV_FSM) ocached = a.obs_cached[e];
   }
   uint32_t fault_key = 0xFFFFFFFFu;  // (phase << 16 | slot << 8 | code), smallest wins
+  // env-level words: every lane of the tile keeps the same copy
+  constexpr int EW = EnvWords<P>::value;
+  int envw[EW > 0 ? EW : 1], envsnap[EW > 0 ? EW : 1];
+  if constexpr (EW > 0) {
+#pragma unroll
+    for (int w = 0; w < EW; ++w) envw[w] = a.env_state[(size_t)w * sp.E + e];
+  }
 
   Ctx ctx;
   ctx.spec = &sp;
   ctx.slot = slot;
   ctx.kind = kind;
+  ctx.env = envsnap;
   ctx.env_id = sp.env_offset + (uint32_t)e;
   ctx.views = &ts.views[0][0];
   ctx.view_stride = P::VW > 0 ? P::VW : 1;
@@ -530,6 +562,10 @@ __global__ void __launch_bounds__(ENGINE_BLOCK) engine_step_kernel(const EngineA
     ctx.stage = h.z;
     const bool was_done = ((term | trunc) & slot_bit) != 0;
     const bool has_ctx = is_agent && !was_done;  // env.py:344-348: no context for done agents
+    if constexpr (EW > 0) {  // the EnvView of this step (env.py:340)
+#pragma unroll
+      for (int w = 0; w < EW; ++w) envsnap[w] = envw[w];
+    }
 
     // ---- start-of-step snapshot of every agent's public state (network.py:208-222)
     if (P::VW > 0) {
@@ -596,8 +632,12 @@ __global__ void __launch_bounds__(ENGINE_BLOCK) engine_step_kernel(const EngineA
     }
     if (trace_lane) a.trace.cnt[e] = traced;
 
-    // ---- post_message_resolution (env.py:175-178)
+    // ---- post_message_resolution (env.py:175-178), then the env class's own override
     if (has_ctx) P::post(ctx, st);
+    if constexpr (EW > 0)
+      P::env_post(ctx, envw, [&](int s_, auto w_) {
+        return __shfl_sync(tmask, st[decltype(w_)::value], s_, G);
+      });
 
     // ---- outputs for strategic agents (env.py:273-303; fsm.py:322-378;
     // stackelberg.py:149-194)
@@ -720,6 +760,10 @@ __global__ void __launch_bounds__(ENGINE_BLOCK) engine_step_kernel(const EngineA
                      : 0u;
       if (is_agent) P::reset_agent(ctx, st);
       rnone = cached_env ? sp.strategic_mask : 0u;
+      if constexpr (EW > 0) {  // reset() builds a fresh EnvView (fsm.py:232-236)
+#pragma unroll
+        for (int w = 0; w < EW; ++w) envsnap[w] = envw[w];
+      }
       if (P::VW > 0) {
         if (is_agent) P::view(ctx, st, &ts.views[slot][0]);
         __syncwarp(tmask);
@@ -750,6 +794,10 @@ __global__ void __launch_bounds__(ENGINE_BLOCK) engine_step_kernel(const EngineA
       if (cached_env) {
         a.reward_none[e] = rnone;
         if (sp.env_kind == PHX_ENV_FSM) a.obs_cached[e] = ocached;
+      }
+      if constexpr (EW > 0) {
+#pragma unroll
+        for (int w = 0; w < EW; ++w) a.env_state[(size_t)w * sp.E + e] = envw[w];
       }
     }
 #pragma unroll
@@ -790,10 +838,17 @@ engine_reset_kernel(const EngineArgs<P> a, const uint8_t* env_mask, float* obs, 
   h.x = 0;
   h.y += 1;
   h.z = sp.env_kind == PHX_ENV_FSM ? sp.initial_stage : 0;
+  constexpr int EW = EnvWords<P>::value;
+  int envw[EW > 0 ? EW : 1];  // env-level words survive a reset unless the program says otherwise
+  if constexpr (EW > 0) {
+#pragma unroll
+    for (int w = 0; w < EW; ++w) envw[w] = a.env_state[(size_t)w * sp.E + e];
+  }
   Ctx ctx;
   ctx.spec = &sp;
   ctx.slot = slot;
   ctx.kind = is_agent ? sp.kind[slot] : -1;
+  ctx.env = envw;
   ctx.step = 0;
   ctx.stage = h.z;
   ctx.env_id = sp.env_offset + (uint32_t)e;

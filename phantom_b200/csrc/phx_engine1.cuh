@@ -161,8 +161,16 @@ __global__ void __launch_bounds__(ENGINE1_BLOCK) engine1_step_kernel(const Engin
   __syncthreads();
   uint32_t fault = 0;  // first fault in event order: events ARE sequential here
 
+  constexpr int EW = EnvWords<P>::value;
+  int envw[EW > 0 ? EW : 1], envsnap[EW > 0 ? EW : 1];
+  if constexpr (EW > 0) {
+#pragma unroll
+    for (int w = 0; w < EW; ++w) envw[w] = a.env_state[(size_t)w * sp.E + e];
+  }
+
   Ctx ctx;
   ctx.spec = &sp;
+  ctx.env = envsnap;
   ctx.env_id = sp.env_offset + (uint32_t)e;
   ctx.views = &VIEW(0);
   ctx.view_stride = ENGINE1_BLOCK;  // view word 0 of slot s at views[0][s][tid]
@@ -204,6 +212,10 @@ __global__ void __launch_bounds__(ENGINE1_BLOCK) engine1_step_kernel(const Engin
     const uint32_t done = term | trunc;  // agents without a context this step (env.py:344-348)
     int st[P::NWORDS > 0 ? P::NWORDS : 1];
     prefetch_actions(t + 1);
+    if constexpr (EW > 0) {  // the EnvView of this step (env.py:340)
+#pragma unroll
+      for (int w = 0; w < EW; ++w) envsnap[w] = envw[w];
+    }
 
     // ---- start-of-step snapshot of every agent's public state (network.py:208-222)
     if (P::VW > 0) {
@@ -329,6 +341,8 @@ __global__ void __launch_bounds__(ENGINE1_BLOCK) engine1_step_kernel(const Engin
       P::post(ctx, st);
       store_state(s, st);
     }
+    if constexpr (EW > 0)  // the env class's own post_message_resolution override
+      P::env_post(ctx, envw, [&](int s_, auto w_) { return ST(decltype(w_)::value, s_); });
 
     // ---- outputs, strategic agents in order (env.py:273-303; fsm.py:322-378;
     // stackelberg.py:149-194).  Pass 1: callbacks + caches; pass 2 (needs the terminal flag): rows.
@@ -446,6 +460,10 @@ __global__ void __launch_bounds__(ENGINE1_BLOCK) engine1_step_kernel(const Engin
         P::reset_agent(ctx, st);
         store_state(s, st);
       }
+      if constexpr (EW > 0) {  // reset() builds a fresh EnvView (fsm.py:232-236)
+#pragma unroll
+        for (int w = 0; w < EW; ++w) envsnap[w] = envw[w];
+      }
       if (P::VW > 0) {
         for (int s = 0; s < n; ++s) {
           bind(s);
@@ -495,6 +513,10 @@ __global__ void __launch_bounds__(ENGINE1_BLOCK) engine1_step_kernel(const Engin
       for (int k = 0; k < 8; ++k) v[k] = k < n ? RC(k) : 0.f;
       rc[0] = make_float4(v[0], v[1], v[2], v[3]);
       rc[1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+    if constexpr (EW > 0) {
+#pragma unroll
+      for (int w = 0; w < EW; ++w) a.env_state[(size_t)w * sp.E + e] = envw[w];
     }
     if (stochastic) {
       uint4* dst = reinterpret_cast<uint4*>(a.adj_env + (size_t)e * ENGINE1_SLOTS);

@@ -90,6 +90,7 @@ class EngineFamily : public Family {
     cudaFree(d_ocached);
     cudaFree(d_adj);
     cudaFree(d_base);
+    cudaFree(d_env);
   }
 
   int32_t init(const phx_spec& s) override {
@@ -122,6 +123,10 @@ class EngineFamily : public Family {
         PHX_CUDA(cudaMalloc(&d_ocached, sizeof(uint32_t) * (size_t)E));
         PHX_CUDA(cudaMemset(d_ocached, 0, sizeof(uint32_t) * (size_t)E));
       }
+    }
+    if (EnvWords<P>::value > 0) {  // env-level words start at zero (e.g. avg_price = 0.0)
+      PHX_CUDA(cudaMalloc(&d_env, sizeof(int32_t) * (size_t)E * EnvWords<P>::value));
+      PHX_CUDA(cudaMemset(d_env, 0, sizeof(int32_t) * (size_t)E * EnvWords<P>::value));
     }
     if (s.flags & PHX_FLAG_STOCHASTIC_NETWORK) {
       // per-env adjacency rows + the base-connection table with integer thresholds
@@ -167,6 +172,7 @@ class EngineFamily : public Family {
     a.reward_none = d_rnone;
     a.obs_cache = d_ocache;
     a.obs_cached = d_ocached;
+    a.env_state = d_env;
     a.adj_env = d_adj;
     a.base_conn = d_base;
     a.n_base = n_base;
@@ -250,12 +256,19 @@ class EngineFamily : public Family {
                      : launch_step<32>(a, stream);
   }
 
-  int32_t family_field(int32_t field, int32_t, void** p, size_t* bytes) override {
+  int32_t family_field(int32_t field, int32_t index, void** p, size_t* bytes) override {
     if (field == PHX_FIELD_ADJACENCY) {  // uint32 [E, G]: G >= n_agents slots per env
       PHX_REQUIRE(d_adj != nullptr, PHX_ERR_INVALID,
                   "PHX_FIELD_ADJACENCY needs PHX_FLAG_STOCHASTIC_NETWORK");
       *p = d_adj;
       *bytes = sizeof(uint32_t) * (size_t)E * G;
+      return PHX_OK;
+    }
+    if (field == PHX_FIELD_ENV_STATE) {  // int32 [E]: env-level word `index`
+      PHX_REQUIRE(index >= 0 && index < EnvWords<P>::value, PHX_ERR_INVALID,
+                  "PHX_FIELD_ENV_STATE: this env class has no such env-level word");
+      *p = d_env + (size_t)index * E;
+      *bytes = sizeof(int32_t) * (size_t)E;
       return PHX_OK;
     }
     const int w = field - PHX_FIELD_FAMILY;
@@ -279,6 +292,7 @@ class EngineFamily : public Family {
   uint32_t* d_rnone = nullptr;
   float* d_ocache = nullptr;
   uint32_t* d_ocached = nullptr;
+  int32_t* d_env = nullptr;   // [ENVW][E] env-level words (programs with ENVW > 0)
   uint32_t* d_adj = nullptr;  // StochasticNetwork only
   uint2* d_base = nullptr;
   int32_t n_base = 0;

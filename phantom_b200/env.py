@@ -22,7 +22,7 @@ import numpy as np
 from . import _lib as L
 from .agents import Agent, StrategicAgent
 from .context import Context
-from .errors import NotLowerableError
+from .errors import DeviceOnlyError, NotLowerableError
 from .message import Message
 from .network import Network, NetworkError
 from .types import AgentID
@@ -153,6 +153,18 @@ class PhantomEnv:
 
     def render(self) -> None:
         return None
+
+    # env-level hooks of the step loop (phantom/env.py:170-183).  They run inside the fused
+    # kernel; an env class that overrides one must be backed by a device program that
+    # implements the override (class attribute __phx_device_env__ = True), see lowering.py.
+    def pre_message_resolution(self) -> None:
+        raise DeviceOnlyError("pre_message_resolution runs inside the fused step kernel")
+
+    def post_message_resolution(self) -> None:
+        raise DeviceOnlyError("post_message_resolution runs inside the fused step kernel")
+
+    def resolve_network(self) -> None:
+        raise DeviceOnlyError("resolve_network runs inside the fused step kernel")
 
     # ---------------------------------------------------------------- device plumbing
     @property

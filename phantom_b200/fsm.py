@@ -8,9 +8,19 @@ from __future__ import annotations
 
 from typing import Callable, Dict, Mapping, Optional, Sequence
 
+import dataclasses
+
 from .env import PhantomEnv
 from .network import Network
 from .types import AgentID, StageID
+from .views import EnvView
+
+
+@dataclasses.dataclass(frozen=True)
+class FSMEnvView(EnvView):
+    """reference: phantom/fsm.py:66-73"""
+
+    stage: StageID
 
 
 class FSMValidationError(Exception):
@@ -83,6 +93,11 @@ class FiniteStateMachineEnv(PhantomEnv):
             return self._initial_stage
         col = self.field(L.FIELD_STAGE, np.int32)
         return ids[int(col[0])] if self.num_envs == 1 else col
+
+    def view(self, agent_views=None) -> FSMEnvView:
+        step = self.current_step if self.num_envs == 1 else 0
+        stage = self.current_stage if self.num_envs == 1 else self._initial_stage
+        return FSMEnvView(step, step / self.num_steps, stage)
 
     def is_fsm_deterministic(self) -> bool:
         return all(len(s.next_stages) == 1 for s in self._stages.values())

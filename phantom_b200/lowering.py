@@ -48,10 +48,36 @@ def _check_no_python_logic(agent: Agent) -> None:
         "(__phx_family__ / __phx_kind__); phantom_b200 has no CPU fallback")
 
 
+_ENV_LEVEL_HOOKS = ("pre_message_resolution", "post_message_resolution", "resolve_network", "view")
+
+
+def _check_env_hooks(env) -> None:
+    """An env class may override the env-level hooks of the step loop (phantom/env.py:166-183;
+    the reference's simple_market example does).  Such an override runs on the GPU or not at
+    all: the class must declare that its device program implements it
+    (`__phx_device_env__ = True`); a plain Python override would be silently ignored."""
+    from .env import PhantomEnv
+    from .fsm import FiniteStateMachineEnv
+    from .stackelberg import StackelbergEnv
+
+    for klass in type(env).__mro__:
+        if klass in (PhantomEnv, FiniteStateMachineEnv, StackelbergEnv, object):
+            break
+        if klass.__dict__.get("__phx_device_env__", False):
+            return
+        for name in _ENV_LEVEL_HOOKS:
+            if name in klass.__dict__:
+                raise NotLowerableError(
+                    f"env class '{klass.__name__}' overrides '{name}' in Python but the step loop "
+                    "runs on the GPU; only env classes backed by a device program "
+                    "(__phx_device_env__) can supply env-level hooks (no CPU fallback)")
+
+
 def lower(env, exec_mode: str = "auto", auto_reset: bool = False) -> L.PhxSpec:
     from .fsm import FiniteStateMachineEnv
     from .stackelberg import StackelbergEnv
 
+    _check_env_hooks(env)
     net = env.network
     agents: List[Agent] = list(net.agents.values())
     if not agents:

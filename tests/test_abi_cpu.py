@@ -141,3 +141,27 @@ def test_network_construction_api_and_errors():
     assert list(sub.agents) == ["mm", "inv"]
     with pytest.raises(ValueError, match="square"):
         net.add_connections_with_adjmat(["mm", "inv"], np.zeros((2, 3)))
+
+
+def test_env_level_hooks_must_be_device_programs():
+    """A Python override of an env-level hook cannot run: lowering refuses it (no CPU fallback)."""
+    from phantom_b200.envs import simple_market as sm
+    from phantom_b200.errors import NotLowerableError
+
+    class Tweaked(sm.SimpleMarketEnv):
+        __phx_device_env__ = False
+
+        def post_message_resolution(self):
+            self.avg_price = 1.0
+
+    import phantom_b200 as ph
+    from phantom_b200.utils.samplers import UniformFloatSampler
+
+    agents = [sm.BuyerAgent("b1", 0.5, supertype=sm.BuyerSupertype(UniformFloatSampler(0.1, 0.2))),
+              sm.SellerAgent("s1")]
+    net = ph.Network(agents)
+    net.add_connections_between(["b1"], ["s1"])
+    env = Tweaked(num_steps=4, network=net)
+    with pytest.raises(NotLowerableError):
+        env.spec  # lowering happens here; no device needed
+    assert sm.example_env(num_envs=4).spec.family == L.FAMILY_SIMPLE_MARKET
