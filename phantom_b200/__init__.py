@@ -16,10 +16,12 @@ from .context import Context
 from .decoders import Decoder
 from .encoders import Encoder
 from .env import BatchStep, PhantomEnv
+from .env_wrappers import SingleAgentEnvAdapter
 from .errors import DeviceOnlyError, NotLowerableError
 from .fsm import FiniteStateMachineEnv, FSMStage
 from .message import Message, MsgPayload, msg_payload
 from .network import Network, NetworkError, StochasticNetwork
+from .policy import Policy
 from .reward_functions import RewardFunction
 from .stackelberg import StackelbergEnv
 from .supertype import Supertype

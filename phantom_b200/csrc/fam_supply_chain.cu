@@ -699,7 +699,8 @@ struct ScProgram {
     } else if (c.kind == SC_CUSTOMER) {  // supply_chain.py:61-67
       const int want = rng_packed_randint(sp.seed, c.env_id, c.episode, (uint32_t)c.step,
                                           SC_STREAM_ORDER, (uint32_t)sp.iparams[0],
-                                          (uint32_t)sp.iparams[2], (uint32_t)sp.agent_iparam[c.slot][1]);
+                                          (uint32_t)sp.iparams[2], (uint32_t)sp.iparams[3],
+                                          (uint32_t)sp.agent_iparam[c.slot][1]);
       out.send(sp.agent_iparam[c.slot][0], SC_ORDER_REQUEST, want);
     }
   }
@@ -766,7 +767,9 @@ class SupplyChainQueue final : public EngineFamily<ScProgram<SEGCAP_>> {
                     s.iparams[1] <= (1 << 20) && customers >= 1,
                 PHX_ERR_INVALID, "supply-chain family: parameters out of range");
     phx_spec t = s;  // obs denominators and their correctly rounded reciprocals
-    t.iparams[2] = customers;  // K of the packed order-size draws (ScProgram::act)
+    // packed order-size draws (ScProgram::act): digits per word, words per step
+    t.iparams[2] = rng_digits_per_word((uint32_t)s.iparams[0]);
+    t.iparams[3] = (customers + t.iparams[2] - 1) / t.iparams[2];
     t.fparams[0] = (double)s.iparams[1];
     t.fparams[1] = (double)(1.0f / (float)s.iparams[1]);
     t.fparams[2] = (double)(customers * s.iparams[0]);

@@ -169,12 +169,11 @@ __device__ __forceinline__ int rng_next_digit(uint32_t& x, uint32_t n) {
   return (int)(prod >> 32);
 }
 
-// draw i (of K per step) of a packed site, stand-alone (one block + i % kpw + 1 multiplies)
+// draw i of a packed site, stand-alone (one block + i % kpw + 1 multiplies); kpw =
+// rng_digits_per_word(n) and W = ceil(K / kpw) are precomputed on the host
 __device__ __forceinline__ int rng_packed_randint(uint64_t seed, uint32_t env, uint32_t episode,
                                                   uint32_t step, uint32_t stream, uint32_t n,
-                                                  uint32_t K, uint32_t i) {
-  const uint32_t kpw = (uint32_t)rng_digits_per_word(n);
-  const uint32_t W = (K + kpw - 1u) / kpw;
+                                                  uint32_t kpw, uint32_t W, uint32_t i) {
   const uint32_t g = step * W + i / kpw;
   const Philox4 b = rng_word_block(seed, env, episode, g >> 2, stream);
   const uint32_t q = g & 3u;

@@ -165,3 +165,16 @@ def test_env_level_hooks_must_be_device_programs():
     with pytest.raises(NotLowerableError):
         env.spec  # lowering happens here; no device needed
     assert sm.example_env(num_envs=4).spec.family == L.FAMILY_SIMPLE_MARKET
+
+
+def test_single_agent_adapter_validation():
+    """SingleAgentEnvAdapter's constructor checks (env_wrappers.py:47-68) run before any device
+    work, with the reference's messages."""
+    from phantom_b200.envs import simple_market as sm
+
+    with pytest.raises(ValueError, match="not found in underlying env"):
+        ph.SingleAgentEnvAdapter(sm.example_env, "nobody", {})
+    with pytest.raises(ValueError, match="found in agent ID to policy mapping"):
+        ph.SingleAgentEnvAdapter(sm.example_env, "s1", {"s1": (ph.Policy, {})})
+    with pytest.raises(ValueError, match="has not been defined a policy"):
+        ph.SingleAgentEnvAdapter(sm.example_env, "s1", {"b1": (ph.Policy, {})})
