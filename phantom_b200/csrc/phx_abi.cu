@@ -329,41 +329,51 @@ int32_t phx_rollout_host(phx_env* env, int32_t T, const float* actions,
                  trunc ? d_trunc : nullptr,
                  all_done ? d_all : nullptr};
   const size_t E = (size_t)f->E, A = (size_t)f->spec.act_dim, O = (size_t)f->spec.obs_dim;
-  // Copy env columns [b, b+c) of a [T, E, width-bytes-per-env] plane (2D: T rows, pitch E*w).
-  auto copy2d = [&](void* dst, const void* src, size_t w, size_t b, size_t c, cudaMemcpyKind k,
-                    cudaStream_t s) {
-    if (w == 0 || c == 0) return cudaSuccess;
-    return cudaMemcpy2DAsync((char*)dst + b * w, E * w, (const char*)src + b * w, E * w, c * w,
-                             (size_t)T, k, s);
+  // Chunked 3-stage pipeline (H2D | kernel | D2H on three streams), chunked along TIME: the rows
+  // [t0, t1) of every [T, E, ...] plane are one contiguous block, so each transfer is a single
+  // large 1-D copy (env-range chunks needed pitched 2-D copies of 16-98 KB rows, which PCIe
+  // moves ~10 % slower), and every family can do it -- a chunk is just a shorter rollout that
+  // continues from the state the previous launch left in HBM.  PCIe is full duplex: the input
+  // copy of chunk c+1 and the output copy of chunk c-1 overlap the kernel of chunk c.
+  const int chunks = (T >= 8 && TE >= 65536 && !f->tracking()) ? 8 : 1;
+  auto copy1d = [&](void* dst, const void* src, size_t row_bytes, size_t t0, size_t nt,
+                    cudaMemcpyKind k, cudaStream_t st) {
+    if (row_bytes == 0 || nt == 0) return cudaSuccess;
+    return cudaMemcpyAsync((char*)dst + t0 * row_bytes, (const char*)src + t0 * row_bytes,
+                           nt * row_bytes, k, st);
   };
-  // Chunked 3-stage pipeline (H2D | kernel | D2H on three streams) when the family can step
-  // env sub-ranges: PCIe is full duplex, so the input copy of chunk c+1 and the output copy of
-  // chunk c-1 overlap the kernel of chunk c.  Otherwise: one chunk.
-  const int chunks = (f->supports_ranges() && f->E >= 8192) ? 8 : 1;
-  const size_t per = (E + chunks - 1) / chunks;
   for (int c = 0; c < chunks; ++c) {
-    const size_t b = (size_t)c * per;
-    if (b >= E) break;
-    const size_t n = (b + per <= E) ? per : E - b;
+    const size_t t0 = (size_t)T * c / chunks, t1 = (size_t)T * (c + 1) / chunks;
+    const size_t nt = t1 - t0;
+    if (nt == 0) continue;
     if (actions)
-      PHX_CUDA(copy2d(d_act, actions, S * A * sizeof(float), b, n, cudaMemcpyHostToDevice, f->copy_in));
+      PHX_CUDA(copy1d(d_act, actions, E * S * A * sizeof(float), t0, nt, cudaMemcpyHostToDevice, f->copy_in));
     if (action_mask)
-      PHX_CUDA(copy2d(d_am, action_mask, S, b, n, cudaMemcpyHostToDevice, f->copy_in));
+      PHX_CUDA(copy1d(d_am, action_mask, E * S, t0, nt, cudaMemcpyHostToDevice, f->copy_in));
     PHX_CUDA(cudaEventRecord(f->ev_in[c], f->copy_in));
     PHX_CUDA(cudaStreamWaitEvent(f->own_stream, f->ev_in[c], 0));
-    int32_t rc = chunks == 1 ? f->rollout(T, io, f->own_stream)
-                             : f->rollout_range(T, io, (int32_t)b, (int32_t)n, f->own_stream);
+    phx::StepIO ic = io;  // the chunk's rows of every plane
+    ic.actions = io.actions + t0 * E * S * A;
+    if (ic.action_mask) ic.action_mask += t0 * E * S;
+    if (ic.obs) ic.obs += t0 * E * S * O;
+    if (ic.obs_mask) ic.obs_mask += t0 * E * S;
+    if (ic.reward) ic.reward += t0 * E * S;
+    if (ic.reward_mask) ic.reward_mask += t0 * E * S;
+    if (ic.term) ic.term += t0 * E * S;
+    if (ic.trunc) ic.trunc += t0 * E * S;
+    if (ic.all_done) ic.all_done += t0 * E * 2;
+    const int32_t rc = f->rollout((int32_t)nt, ic, f->own_stream);
     if (rc != PHX_OK) return rc;
     PHX_CUDA(cudaEventRecord(f->ev_k[c], f->own_stream));
     PHX_CUDA(cudaStreamWaitEvent(f->copy_out, f->ev_k[c], 0));
     cudaStream_t so = f->copy_out;
-    if (obs) PHX_CUDA(copy2d(obs, d_obs, S * O * sizeof(float), b, n, cudaMemcpyDeviceToHost, so));
-    if (obs_mask) PHX_CUDA(copy2d(obs_mask, d_om, S, b, n, cudaMemcpyDeviceToHost, so));
-    if (reward) PHX_CUDA(copy2d(reward, d_rew, S * sizeof(float), b, n, cudaMemcpyDeviceToHost, so));
-    if (reward_mask) PHX_CUDA(copy2d(reward_mask, d_rm, S, b, n, cudaMemcpyDeviceToHost, so));
-    if (term) PHX_CUDA(copy2d(term, d_term, S, b, n, cudaMemcpyDeviceToHost, so));
-    if (trunc) PHX_CUDA(copy2d(trunc, d_trunc, S, b, n, cudaMemcpyDeviceToHost, so));
-    if (all_done) PHX_CUDA(copy2d(all_done, d_all, 2, b, n, cudaMemcpyDeviceToHost, so));
+    if (obs) PHX_CUDA(copy1d(obs, d_obs, E * S * O * sizeof(float), t0, nt, cudaMemcpyDeviceToHost, so));
+    if (obs_mask) PHX_CUDA(copy1d(obs_mask, d_om, E * S, t0, nt, cudaMemcpyDeviceToHost, so));
+    if (reward) PHX_CUDA(copy1d(reward, d_rew, E * S * sizeof(float), t0, nt, cudaMemcpyDeviceToHost, so));
+    if (reward_mask) PHX_CUDA(copy1d(reward_mask, d_rm, E * S, t0, nt, cudaMemcpyDeviceToHost, so));
+    if (term) PHX_CUDA(copy1d(term, d_term, E * S, t0, nt, cudaMemcpyDeviceToHost, so));
+    if (trunc) PHX_CUDA(copy1d(trunc, d_trunc, E * S, t0, nt, cudaMemcpyDeviceToHost, so));
+    if (all_done) PHX_CUDA(copy1d(all_done, d_all, E * 2, t0, nt, cudaMemcpyDeviceToHost, so));
   }
   PHX_CUDA(cudaStreamSynchronize(f->copy_out));
   PHX_CUDA(cudaStreamSynchronize(f->own_stream));
