@@ -109,3 +109,28 @@ def test_rollout_host_for_engine_families():
                      ("observations", "obs_mask", "rewards", "reward_mask", "terminations", "truncations", "all_done")])
     assert_batchsteps_equal(dev, hb)
     a.close(); b.close()
+
+
+def test_rollout_host_pipeline_chunks_along_time():
+    """phx_rollout_host's three-stream pipeline splits a long rollout into 8 chunks of the time
+    axis (T * E >= 65 536, T >= 8): uneven chunk lengths (T = 13 -> 1 or 2 steps each), an FSM
+    env class whose reward / observation caches and stage must carry across the chunk launches,
+    auto-reset inside a chunk -- all identical to one device rollout."""
+    from phantom_b200 import BatchStep
+    from phantom_b200.envs import simple_market as sm
+    from phantom_b200.envs.supply_chain import SupplyChainEnv
+
+    import torch
+
+    keys = ("observations", "obs_mask", "rewards", "reward_mask", "terminations", "truncations", "all_done")
+    for make, S, T, E in ((lambda: sm.example_env(num_envs=6000, seed=4, num_steps=5, auto_reset=True), 5, 13, 6000),
+                          (lambda: SupplyChainEnv(num_envs=8192, seed=4, num_steps=7, auto_reset=True), 1, 29, 8192)):
+        A = np.random.RandomState(5).uniform(0, 1, size=(T, E, S, 1)).astype(np.float32)
+        a, b = make(), make()
+        a.reset_batch(); b.reset_batch()
+        dev = a.rollout_batch(A)
+        host = b.rollout_host(A)
+        hb = BatchStep(*[torch.as_tensor(host[k]).cuda() for k in keys])
+        assert_batchsteps_equal(dev, hb)
+        a.check_errors(); b.check_errors()
+        a.close(); b.close()
