@@ -551,12 +551,10 @@ class SupplyChainFast final : public Family {
     return rollout_range(T, io, 0, E, stream);
   }
 
-  bool supports_ranges() const override { return !tracking(); }
-
   // Steps envs [env_begin, env_begin + env_count); the I/O planes keep the handle's full
-  // [T, E, ...] shape (row stride E), so chunks of one rollout can be pipelined with copies.
+  // [T, E, ...] shape (row stride E).
   int32_t rollout_range(int32_t T, const StepIO& io, int32_t env_begin, int32_t env_count,
-                        cudaStream_t stream) override {
+                        cudaStream_t stream) {
     PHX_REQUIRE(env_begin >= 0 && env_count >= 1 && env_begin + env_count <= E, PHX_ERR_INVALID,
                 "env range out of bounds");
     ScArgs a;

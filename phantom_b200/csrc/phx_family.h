@@ -20,12 +20,6 @@ class Family {
   virtual int32_t reset(const uint8_t* env_mask, float* obs, uint8_t* obs_mask,
                         cudaStream_t stream) = 0;
   virtual int32_t rollout(int32_t T, const StepIO& io, cudaStream_t stream) = 0;
-  // Optional: step only envs [env_begin, env_begin + env_count) (I/O planes keep row stride E).
-  // Lets phx_rollout_host pipeline host<->device copies with compute, chunk by chunk.
-  virtual bool supports_ranges() const { return false; }
-  virtual int32_t rollout_range(int32_t, const StepIO&, int32_t, int32_t, cudaStream_t) {
-    return PHX_ERR_UNSUPPORTED;
-  }
   // Family state columns (field >= PHX_FIELD_FAMILY); returns PHX_ERR_INVALID if unknown.
   virtual int32_t family_field(int32_t field, int32_t index, void** dev_ptr, size_t* bytes) = 0;
   virtual const char* exec_name() const = 0;
