@@ -10,12 +10,18 @@
 //                          examples/environments/digital_ads_market/digital_ads_market.py:429-510)
 //
 // Mapping: ONE THREAD BLOCK PER ENV, thread == agent slot (the north star's layout; it pays
-// here because an env has 128 agents and 16 256 messages per step).  The per-env message
-// queue is a MAILBOX in shared memory, mb[receiver][sender] (66 KB, row stride 129 words so
-// that both the senders' column writes and the receivers' row reads are bank-conflict free).
-// The reference's batch order for a receiver (global push order = sender slot order) is the
-// mailbox row order; the receivers' first-arrival order only matters for the order in which
-// the Acks are pushed, i.e. for the message trace, and is reconstructed there.
+// here because an env has 128 agents and 16 256 messages per step).  On this family's message
+// graph the queue never has to be materialised: a Signal's payload is a function of the
+// sender's value and the (sender, receiver) pair, so round 0 is a PULL -- every sender
+// publishes one word in shared memory (vals[sender], 512 B per env instead of a 66 KB
+// mailbox), and every receiver walks its senders in slot order (= the reference's batch order
+// for a receiver: global push order) reading vals[s] as a warp-wide broadcast and re-deriving
+// the receiver-tailored part from a 5-entry register table.  Round 1 is a PUSH: an Ack is two
+// shared-memory integer atomics on the receiver's counters (integer sums are order
+// independent).  Measured: 0.62 ms per 16 384 x 8 launch against 2.15 ms for the mailbox
+// version (which spent ~15 instructions per message, most of them on the 16 256 mailbox
+// writes and the 128-deep Ack scan of every agent).  The receivers' first-arrival order only matters for the order in which the Acks
+// are pushed, i.e. for the message trace, and is reconstructed there.
 // Outputs of a step are staged in shared memory and written with TMA bulk stores
 // (cp.async.bulk.global.shared::cta, SASS UBLKCP): one env's rows are contiguous in every
 // [T,E,S,...] plane.
@@ -33,7 +39,6 @@ namespace phx {
 namespace {
 
 constexpr int DN_MAX = 128;       // agents per env == threads per block
-constexpr int DN_STRIDE = 129;    // mailbox row stride (words)
 constexpr int DN_WORDS = 6;
 enum { DN_SIGNAL = 0, DN_ACK = 1 };
 
@@ -61,8 +66,10 @@ struct alignas(16) DenseStage {  // one step's output rows of one env, 16-byte a
 };
 
 struct DenseSmem {
-  int32_t mb[DN_MAX * DN_STRIDE];  // mailbox, round 0
-  int2 ack[DN_MAX];                // round 1: (Ack receiver of every agent or -1, Ack value)
+  alignas(16) int32_t vals[DN_MAX];  // round 0: the Signal value every sender published
+  int32_t ack_cnt[DN_MAX];         // round 1: Acks received / their sum, by receiver
+  int32_t ack_sum[DN_MAX];
+  int2 ack[DN_MAX];                // trace: (Ack receiver of every agent or -1, Ack value)
   int32_t order_key[DN_MAX];       // trace only: first-arrival keys
   uint32_t sent[4];
   uint32_t any_ack;
@@ -92,6 +99,12 @@ __global__ void __launch_bounds__(DN_MAX) dense_step_kernel(const DenseArgs a) {
 #pragma unroll
   for (int w = 0; w < DN_WORDS; ++w) st[w] = a.state[((size_t)w * sp.E + e) * DN_MAX + slot];
   uint32_t fault = 0;
+  // Signal(value + (7 s + 3 r) % 5): (7 s + 3 r) % 5 == ((2 s) % 5 + (3 r) % 5) % 5; the sender
+  // part is a compile-time constant of the unrolled sender loop, the receiver part selects one
+  // of five per-lane registers
+  int tailtab[5];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) tailtab[k] = (k + 3 * slot) % 5;
   const bool bulk = (n % 16) == 0;  // plane sizes multiples of 16 bytes
   const bool ok_send_signal = ((sp.sender_ok[DN_SIGNAL][slot >> 5] >> (slot & 31)) & 1u) ||
                               (sp.flags & PHX_FLAG_NO_PAYLOAD_CHECKS);
@@ -125,23 +138,12 @@ __global__ void __launch_bounds__(DN_MAX) dense_step_kernel(const DenseArgs a) {
           ((adj[0] & ~sp.receiver_ok[DN_SIGNAL][0]) | (adj[1] & ~sp.receiver_ok[DN_SIGNAL][1]) |
            (adj[2] & ~sp.receiver_ok[DN_SIGNAL][2]) | (adj[3] & ~sp.receiver_ok[DN_SIGNAL][3])))
         fault = fault ? fault : PHX_FAULT_BAD_PAYLOAD_TYPE;
-      // column write: mb[r][slot] for every neighbour r (lanes hit consecutive words).  The
-      // receiver-tailored part (7 s + 3 r) % 5 is carried incrementally: +3 (mod 5) per r.
-      int tail = (7 * slot) % 5;
-      int32_t* col = sm.mb + slot;
-#pragma unroll
-      for (int w = 0; w < 4; ++w) {
-        const uint32_t m = adj[w];
-#pragma unroll 8
-        for (int b = 0; b < 32; ++b) {
-          if ((m >> b) & 1u) col[(w * 32 + b) * DN_STRIDE] = st[0] + tail;
-          tail += 3;
-          tail -= tail >= 5 ? 5 : 0;
-        }
-      }
+      sm.vals[slot] = st[0];  // one word per sender; the receivers pull
     }
     // ---- pre_message_resolution
     st[1] = 0; st[2] = 0; st[3] = -1; st[4] = 0; st[5] = 0;
+    sm.ack_cnt[slot] = 0;
+    sm.ack_sum[slot] = 0;
     __syncthreads();
 
     // ---- round 0: handle_batch over this receiver's mailbox row (batch order = sender order)
@@ -151,19 +153,25 @@ __global__ void __launch_bounds__(DN_MAX) dense_step_kernel(const DenseArgs a) {
     int first_sender = -1;
     if (is_agent && sp.round_limit != 0) {
       int total = 0, best = INT32_MIN, best_s = -1;
-      const int32_t* rowp = sm.mb + slot * DN_STRIDE;
 #pragma unroll
       for (int w = 0; w < 4; ++w) {
         const uint32_t m = adj[w] & sm.sent[w];  // symmetric graph: senders with an edge to me
         if (TRACK && first_sender < 0 && m) first_sender = w * 32 + __ffs(m) - 1;
-#pragma unroll 8
-        for (int b = 0; b < 32; ++b) {
-          if ((m >> b) & 1u) {
-            const int v = rowp[w * 32 + b];
-            total += v;
-            if (v > best) {  // strict: the FIRST sender attaining the max wins
-              best = v;
-              best_s = w * 32 + b;
+        if (m == 0u) continue;
+#pragma unroll
+        for (int b4 = 0; b4 < 32; b4 += 4) {
+          const int4 q = *reinterpret_cast<const int4*>(&sm.vals[w * 32 + b4]);  // broadcast
+          const int qv[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int sdr = w * 32 + b4 + k;
+            if ((m >> (b4 + k)) & 1u) {
+              const int v = qv[k] + tailtab[(2 * sdr) % 5];
+              total += v;
+              if (v > best) {  // strict: the FIRST sender attaining the max wins
+                best = v;
+                best_s = sdr;
+              }
             }
           }
         }
@@ -178,8 +186,15 @@ __global__ void __launch_bounds__(DN_MAX) dense_step_kernel(const DenseArgs a) {
           fault = fault ? fault : PHX_FAULT_BAD_PAYLOAD_TYPE;
       }
     }
-    sm.ack[slot] = make_int2(ack_recv, st[2]);
-    if (TRACK) sm.order_key[slot] = first_sender < 0 ? 0x7FFFFFFF : first_sender * DN_MAX + slot;
+    if (TRACK) {
+      sm.ack[slot] = make_int2(ack_recv, st[2]);
+      sm.order_key[slot] = first_sender < 0 ? 0x7FFFFFFF : first_sender * DN_MAX + slot;
+    }
+    // round 1, pushed: Ack(best) lands on its receiver's counters
+    if (ack_recv >= 0 && sp.round_limit != 1) {
+      atomicAdd(&sm.ack_cnt[ack_recv], 1);
+      atomicAdd(&sm.ack_sum[ack_recv], st[2]);
+    }
     const uint32_t acks_w = __ballot_sync(0xFFFFFFFFu, ack_recv >= 0);
     if (slot == 0) sm.any_ack = 0;
     __syncthreads();
@@ -189,17 +204,8 @@ __global__ void __launch_bounds__(DN_MAX) dense_step_kernel(const DenseArgs a) {
 
     // ---- round 1: the Acks (same handle_batch override): count and sum
     if (is_agent && sp.round_limit != 1 && sp.round_limit != 0) {
-      int acks = 0, ack_total = 0;
-#pragma unroll 8
-      for (int r = 0; r < n; ++r) {  // broadcast reads
-        const int2 ak = sm.ack[r];
-        if (ak.x == slot) {
-          acks += 1;
-          ack_total += ak.y;
-        }
-      }
-      st[4] = acks;
-      st[5] = ack_total;
+      st[4] = sm.ack_cnt[slot];
+      st[5] = sm.ack_sum[slot];
     }
 
     if (TRACK && slot == 0) {  // Resolver.tracked_messages of this step, global push order
@@ -210,7 +216,7 @@ __global__ void __launch_bounds__(DN_MAX) dense_step_kernel(const DenseArgs a) {
         for (int r = 0; r < n; ++r)
           if ((a.adj[s * 4 + (r >> 5)] >> (r & 31)) & 1u) {
             if (cnt < a.trace.cap)
-              rows[cnt] = trace_row(s, r, DN_SIGNAL, sm.mb[r * DN_STRIDE + s], 0, 0);
+              rows[cnt] = trace_row(s, r, DN_SIGNAL, dn_tailored(sm.vals[s], s, r), 0, 0);
             ++cnt;
           }
       }
@@ -414,7 +420,7 @@ class DenseFamily final : public Family {
     return PHX_ERR_INVALID;
   }
 
-  const char* exec_name() const override { return "queue(block-per-env,G=128)"; }
+  const char* exec_name() const override { return "block-per-env(G=128, pull/push)"; }
 
  private:
   DenseSpec dsp{};
