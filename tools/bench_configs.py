@@ -82,6 +82,7 @@ def main():
     from phantom_b200.envs.market import MarketEnv
     from phantom_b200.envs.stackelberg_game import StackelbergGameEnv
     from phantom_b200.envs.supply_chain import SupplyChainEnv
+    from phantom_b200.envs import simple_market as sm
 
     cfgs = [
         ("C2-fast", lambda **k: SupplyChainEnv(exec_mode="fast", **k), 1, 3, 100, 65536, 48, None, True),
@@ -96,6 +97,12 @@ def main():
         ("C4-stackelberg-thread", lambda **k: StackelbergGameEnv(exec_mode="thread", **k), 4, 2, 100, 131072,
          2 * (16 + 8 + 8 * (16 + 4) + 4), None, False),
         ("C5-dense", lambda **k: DenseEnv(**k), 128, 3, 8, 16384, 2 * (16 + 6 * 128 * 4), None, False),
+        # the reference's simple_market example (3 buyers + 2 sellers, 10-step episodes); state =
+        # header + 19 words x 8 slots + reward / obs caches + env words
+        ("X-simple-market-thread", lambda **k: sm.example_env(num_steps=10, exec_mode="thread", **k),
+         5, 3, 100, 65536, 2 * (16 + 8 + 19 * 8 * 4 + 8 * 4 + 8 * 12 + 8 + 8), 0, False),
+        ("X-simple-market-queue", lambda **k: sm.example_env(num_steps=10, exec_mode="queue", **k),
+         5, 3, 100, 65536, 2 * (16 + 8 + 19 * 8 * 4 + 8 * 4 + 8 * 12 + 8 + 8), 0, False),
     ]
     for name, mk, S, O, T, E, bst, binf, lean in cfgs:
         if args.only and args.only not in name:
