@@ -275,6 +275,19 @@ int32_t phx_reduce_field(phx_env* env, int32_t field, int32_t index, int32_t wid
 int32_t phx_get_trace(phx_env* env, int32_t env_begin, int32_t env_end, int32_t* host_counts,
                       int32_t* host_msgs);
 
+/* Run-time specialisation of the step kernel to ONE handle's env class.  The generic engines
+ * interpret the lowered env class (agent counts, kinds, adjacency, stage tables) at run time;
+ * phx_jit_source writes the text of a CUDA translation unit in which those are compile-time
+ * constants (needs `buf_bytes` >= the text + NUL; *needed always receives the size; the unit
+ * #includes files of phantom_b200/csrc, compile it with that directory on the include path:
+ *   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -cubin -I <csrc> unit.cu),
+ * and phx_load_specialised loads the resulting cubin; from then on phx_step / phx_rollout of
+ * this handle launch the specialised kernel (same results, bit for bit).  Supported by the
+ * thread-per-env engine (env classes of at most 8 agents); PHX_ERR_UNSUPPORTED otherwise.  The
+ * library contains no compiler: the host binding runs nvcc and caches cubins.            */
+int32_t phx_jit_source(phx_env* env, char* buf, uint64_t buf_bytes, uint64_t* needed);
+int32_t phx_load_specialised(phx_env* env, const char* cubin_path);
+
 /* Collect device faults.  n_bad = envs whose error word is set, first_env / code = the
  * lowest such env and its phx_fault.  clear != 0 zeroes the words.  Synchronises.       */
 int32_t phx_poll_errors(phx_env* env, int32_t* n_bad, int32_t* first_env, int32_t* code,

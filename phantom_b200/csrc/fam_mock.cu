@@ -29,6 +29,9 @@ enum { MK_AGENT = 0, MK_STRATEGIC = 1, MK_ECHO = 2, MK_CODEC = 3 };
 enum { MK_TEST_MESSAGE = 0, MK_REQUEST = 1, MK_RESPONSE = 2 };
 
 struct MockProgram {
+  // run-time specialisation (phx_jit.cuh): where this program lives and what it is called
+  static constexpr const char* JIT_SOURCE = "fam_mock.cu";
+  static constexpr const char* JIT_NAME = "MockProgram";
   static constexpr int PW = 1, NWORDS = 5, VW = 0, ACTCAP = 32, RESPCAP = 32, OBS_DIM = 8,
                        ACT_DIM = 1, Q1CAP = 32;
   static constexpr int RECVCAP = 32;  // max messages one agent receives in a round
@@ -118,6 +121,8 @@ struct MockProgram {
 
 }  // namespace
 
+#ifndef PHX_JIT_TU  // a specialised translation unit only needs the program above
 Family* make_mock_family(const phx_spec&) { return new EngineFamily<MockProgram>(); }
+#endif
 
 }  // namespace phx

@@ -45,6 +45,9 @@ template <int W>
 using WordC = std::integral_constant<int, W>;
 
 struct SimpleMarketProgram {
+  // run-time specialisation (phx_jit.cuh): where this program lives and what it is called
+  static constexpr const char* JIT_SOURCE = "fam_simple_market.cu";
+  static constexpr const char* JIT_NAME = "SimpleMarketProgram";
   // a seller prices every neighbour in the acting phase; no handler answers a message
   static constexpr int PW = 2, NWORDS = 19, VW = 0, ACTCAP = 32, RESPCAP = 1, OBS_DIM = 3,
                        ACT_DIM = 1, Q1CAP = 16, ENVW = 2;
@@ -248,6 +251,7 @@ struct SimpleMarketProgram {
   }
 };
 
+#ifndef PHX_JIT_TU
 class SimpleMarketFamily final : public EngineFamily<SimpleMarketProgram> {
  public:
   int32_t init(const phx_spec& s) override {
@@ -261,9 +265,12 @@ class SimpleMarketFamily final : public EngineFamily<SimpleMarketProgram> {
     return EngineFamily<SimpleMarketProgram>::init(t);
   }
 };
+#endif
 
 }  // namespace
 
+#ifndef PHX_JIT_TU  // a specialised translation unit only needs the program above
 Family* make_simple_market_family(const phx_spec&) { return new SimpleMarketFamily(); }
+#endif
 
 }  // namespace phx

@@ -18,6 +18,9 @@ enum { SK_PRICE = 0, SK_DEMAND = 1, SK_ACK = 2 };
 constexpr int SK_STREAM_VALUE = 2;
 
 struct StackelbergProgram {
+  // run-time specialisation (phx_jit.cuh): where this program lives and what it is called
+  static constexpr const char* JIT_SOURCE = "fam_stackelberg.cu";
+  static constexpr const char* JIT_NAME = "StackelbergProgram";
   static constexpr int PW = 1, NWORDS = 4, VW = 0, ACTCAP = 8, RESPCAP = 8, OBS_DIM = 2,
                        ACT_DIM = 1, Q1CAP = 8;
   static constexpr int RECVCAP = 8;  // max messages one agent receives in a round
@@ -118,6 +121,8 @@ struct StackelbergProgram {
 
 }  // namespace
 
+#ifndef PHX_JIT_TU  // a specialised translation unit only needs the program above
 Family* make_stackelberg_family(const phx_spec&) { return new EngineFamily<StackelbergProgram>(); }
+#endif
 
 }  // namespace phx

@@ -417,6 +417,7 @@ __global__ void sc_init_kernel(int E, int4* hdr, int4* shop) {
   shop[e] = make_int4(0, 0, 0, 0);
 }
 
+#ifndef PHX_JIT_TU  // host side of the fast kernel: not part of a specialised engine unit
 class SupplyChainFast final : public Family {
  public:
   ~SupplyChainFast() override {
@@ -650,6 +651,8 @@ class SupplyChainFast final : public Family {
 };
 
 
+#endif  // PHX_JIT_TU
+
 // ---------------------------------------------------------------------------------------
 // The same agents as a device program of the generic queue engine (phx_engine.cuh): any agent
 // order and topology (one shop and one factory per env), messages routed dynamically.
@@ -658,6 +661,9 @@ class SupplyChainFast final : public Family {
 //                           shop -> its factory);  [slot][1] = customer ordinal (RNG idx)
 template <int SEGCAP_>
 struct ScProgram {
+  // run-time specialisation (thread-per-env engine: SEGCAP_ == 8)
+  static constexpr const char* JIT_SOURCE = "fam_supply_chain.cu";
+  static constexpr const char* JIT_NAME = "ScProgram<8>";
   // every agent sends at most one message in the acting phase; the shop answers every order
   static constexpr int PW = 1, NWORDS = 4, VW = 0, ACTCAP = 1, RESPCAP = SEGCAP_, OBS_DIM = 3,
                        ACT_DIM = 1;
@@ -753,6 +759,7 @@ struct ScProgram {
   }
 };
 
+#ifndef PHX_JIT_TU
 template <int SEGCAP_>
 class SupplyChainQueue final : public EngineFamily<ScProgram<SEGCAP_>> {
  public:
@@ -776,8 +783,11 @@ class SupplyChainQueue final : public EngineFamily<ScProgram<SEGCAP_>> {
   }
 };
 
+#endif  // PHX_JIT_TU
+
 }  // namespace
 
+#ifndef PHX_JIT_TU
 Family* make_supply_chain_family(const phx_spec& s) {
   const bool canonical = SupplyChainFast::is_canonical(s);
   if (s.exec_mode == PHX_EXEC_FAST || (s.exec_mode == PHX_EXEC_AUTO && canonical))
@@ -800,5 +810,7 @@ int32_t selftest_ratio(int32_t device, int32_t den, int32_t lo, int32_t count, f
   PHX_CUDA(err);
   return PHX_OK;
 }
+
+#endif  // PHX_JIT_TU
 
 }  // namespace phx

@@ -29,6 +29,9 @@ enum { S2_ORDER_REQUEST = 0, S2_ORDER_RESPONSE = 1, S2_STOCK_REQUEST = 2, S2_STO
 constexpr int S2_STREAM_ORDER = 0, S2_STREAM_SAMPLER = 3, S2_STREAM_CHOICE = 4;
 
 struct Sc2Program {
+  // run-time specialisation (phx_jit.cuh): where this program lives and what it is called
+  static constexpr const char* JIT_SOURCE = "fam_supply_chain2.cu";
+  static constexpr const char* JIT_NAME = "Sc2Program";
   static constexpr int PW = 1, NWORDS = 6, VW = 0, ACTCAP = 1, RESPCAP = 8, OBS_DIM = 4,
                        ACT_DIM = 1, Q1CAP = 8;
   static constexpr int RECVCAP = 8;  // max messages one agent receives in a round
@@ -138,6 +141,8 @@ struct Sc2Program {
 
 }  // namespace
 
+#ifndef PHX_JIT_TU  // a specialised translation unit only needs the program above
 Family* make_supply_chain2_family(const phx_spec&) { return new EngineFamily<Sc2Program>(); }
+#endif
 
 }  // namespace phx

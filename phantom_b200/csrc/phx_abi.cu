@@ -468,6 +468,26 @@ int32_t phx_get_trace(phx_env* env, int32_t env_begin, int32_t env_end, int32_t*
   return PHX_OK;
 }
 
+int32_t phx_jit_source(phx_env* env, char* buf, uint64_t buf_bytes, uint64_t* needed) {
+  PHX_REQUIRE(env != nullptr, PHX_ERR_INVALID, "env is NULL");
+  std::string text;
+  const int32_t rc = env->fam->jit_source(text);
+  if (rc != PHX_OK) return rc;
+  if (needed) *needed = (uint64_t)text.size() + 1;
+  if (buf == nullptr || buf_bytes == 0) return PHX_OK;  // size query
+  PHX_REQUIRE(buf_bytes >= text.size() + 1, PHX_ERR_INVALID, "buffer too small for the source text");
+  std::memcpy(buf, text.c_str(), text.size() + 1);
+  return PHX_OK;
+}
+
+int32_t phx_load_specialised(phx_env* env, const char* cubin_path) {
+  PHX_REQUIRE(env != nullptr, PHX_ERR_INVALID, "env is NULL");
+  Family* f = env->fam;
+  PHX_CUDA(cudaSetDevice(f->device));
+  PHX_CUDA(cudaDeviceSynchronize());
+  return f->load_specialised(cubin_path);
+}
+
 int32_t phx_poll_errors(phx_env* env, int32_t* n_bad, int32_t* first_env, int32_t* code,
                         int32_t clear) {
   PHX_REQUIRE(env != nullptr, PHX_ERR_INVALID, "env is NULL");

@@ -18,6 +18,15 @@
 
 namespace phx {
 
+// Agent loops: a specialised unit (PHX_JIT_TU) knows the agent count at compile time and unrolls
+// them completely, so that every agent's callbacks are compiled for ITS kind, slot and masks;
+// the generic build leaves the choice to the compiler, as before.
+#ifdef PHX_JIT_TU
+#define PHX_AGENT_UNROLL _Pragma("unroll")
+#else
+#define PHX_AGENT_UNROLL
+#endif
+
 constexpr int ENGINE1_BLOCK = 128;
 constexpr int ENGINE1_SLOTS = 8;  // == the G of the HBM state layout [NWORDS][E][8]
 
@@ -86,12 +95,21 @@ struct Emit1 {
   }
 };
 
-template <class P, bool TRACK>
-__global__ void __launch_bounds__(ENGINE1_BLOCK) engine1_step_kernel(const EngineArgs<P> a) {
+// Where the kernel reads the lowered env class from.  SpecFromArgs: the kernel parameter
+// (constant bank; one precompiled kernel serves every env class of a family).  A specialised
+// build (phx_jit.cuh) substitutes a compile-time constant spec, which lets the compiler unroll
+// the agent loops and fold every mask / kind / table lookup of THIS env class.
+struct SpecFromArgs {
+  template <class A>
+  __device__ __forceinline__ static const EngineSpec& get(const A& a) { return a.spec; }
+};
+
+template <class P, bool TRACK, class SP>
+__device__ __forceinline__ void engine1_step_body(const EngineArgs<P>& a) {
   static_assert(P::VW <= 1, "thread-per-env engine: views of at most one word per agent");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   int32_t* sm = reinterpret_cast<int32_t*>(smem_raw);
-  const EngineSpec& sp = a.spec;
+  const EngineSpec& sp = SP::get(a);
   const int tid = threadIdx.x;
   const Engine1Layout L = engine1_layout<P>(sp.n_agents, sp.n_strategic, a.qcap,
                                             sp.env_kind != PHX_ENV_BASE);
@@ -219,6 +237,7 @@ __global__ void __launch_bounds__(ENGINE1_BLOCK) engine1_step_kernel(const Engin
 
     // ---- start-of-step snapshot of every agent's public state (network.py:208-222)
     if (P::VW > 0) {
+      PHX_AGENT_UNROLL
       for (int s = 0; s < n; ++s) {
         bind(s);
         load_state(s, st);
@@ -247,6 +266,7 @@ __global__ void __launch_bounds__(ENGINE1_BLOCK) engine1_step_kernel(const Engin
     }
     int cur = 0;
     Emit1<P> out{sm, &sp, L, cur, tid, 0, 0u, 0, 0u};
+    PHX_AGENT_UNROLL
     for (int s = 0; s < n; ++s) {
       if (!((acting >> s) & 1u) || ((done >> s) & 1u)) continue;
       bind(s);
@@ -278,7 +298,9 @@ __global__ void __launch_bounds__(ENGINE1_BLOCK) engine1_step_kernel(const Engin
     }
 
     // ---- pre_message_resolution (env.py:170-173)
-    if (P::HAS_PRE) for (int s = 0; s < n; ++s) {
+    if (P::HAS_PRE)
+      PHX_AGENT_UNROLL
+      for (int s = 0; s < n; ++s) {
       if ((done >> s) & 1u) continue;
       bind(s);
       load_state(s, st);
@@ -334,7 +356,9 @@ __global__ void __launch_bounds__(ENGINE1_BLOCK) engine1_step_kernel(const Engin
     if (TRACK && env_live) a.trace.cnt[e] = traced;
 
     // ---- post_message_resolution (env.py:175-178)
-    if (P::HAS_POST) for (int s = 0; s < n; ++s) {
+    if (P::HAS_POST)
+      PHX_AGENT_UNROLL
+      for (int s = 0; s < n; ++s) {
       if ((done >> s) & 1u) continue;
       bind(s);
       load_state(s, st);
@@ -347,6 +371,7 @@ __global__ void __launch_bounds__(ENGINE1_BLOCK) engine1_step_kernel(const Engin
     // ---- outputs, strategic agents in order (env.py:273-303; fsm.py:322-378;
     // stackelberg.py:149-194).  Pass 1: callbacks + caches; pass 2 (needs the terminal flag): rows.
     uint32_t obs_slots = 0, rew_slots = 0, t_slots = 0, u_slots = 0;
+    PHX_AGENT_UNROLL
     for (int s = 0; s < n; ++s) {
       const int sidx = sp.sidx[s];
       if (sidx < 0 || ((done >> s) & 1u)) continue;
@@ -397,6 +422,7 @@ __global__ void __launch_bounds__(ENGINE1_BLOCK) engine1_step_kernel(const Engin
     if (sp.env_kind == PHX_ENV_FSM) h.z = next_stage;
 
     if (env_live) {
+      PHX_AGENT_UNROLL
       for (int s = 0; s < n; ++s) {
         const int sidx = sp.sidx[s];
         if (sidx < 0) continue;
@@ -454,6 +480,7 @@ __global__ void __launch_bounds__(ENGINE1_BLOCK) engine1_step_kernel(const Engin
             adj64 |= (1ull << (8 * u + v)) | (1ull << (8 * v + u));
         }
       }
+      PHX_AGENT_UNROLL
       for (int s = 0; s < n; ++s) {
         bind(s);
         load_state(s, st);
@@ -465,6 +492,7 @@ __global__ void __launch_bounds__(ENGINE1_BLOCK) engine1_step_kernel(const Engin
         for (int w = 0; w < EW; ++w) envsnap[w] = envw[w];
       }
       if (P::VW > 0) {
+        PHX_AGENT_UNROLL
         for (int s = 0; s < n; ++s) {
           bind(s);
           load_state(s, st);
@@ -477,6 +505,7 @@ __global__ void __launch_bounds__(ENGINE1_BLOCK) engine1_step_kernel(const Engin
       uint32_t first_obs = sp.strategic_mask;
       if (sp.env_kind == PHX_ENV_FSM) first_obs &= sp.stage_acting[sp.initial_stage];
       if (sp.env_kind == PHX_ENV_STACKELBERG) first_obs &= sp.leaders;
+      PHX_AGENT_UNROLL
       for (int s = 0; s < n; ++s) {
         const int sidx = sp.sidx[s];
         if (sidx < 0) continue;
@@ -534,6 +563,11 @@ __global__ void __launch_bounds__(ENGINE1_BLOCK) engine1_step_kernel(const Engin
     }
     if (fault) raise_fault(a.faults, e, fault);
   }
+}
+
+template <class P, bool TRACK>
+__global__ void __launch_bounds__(ENGINE1_BLOCK) engine1_step_kernel(const EngineArgs<P> a) {
+  engine1_step_body<P, TRACK, SpecFromArgs>(a);
 }
 
 }  // namespace phx

@@ -3,6 +3,7 @@
 #pragma once
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -70,6 +71,65 @@ inline int32_t make_engine_spec(const phx_spec& s, int32_t E, uint64_t seed, int
   return PHX_OK;
 }
 
+// ---------------------------------------------------------------- run-time specialisation
+// The generic engines interpret the lowered env class (EngineSpec) at run time: every agent
+// loop, mask test and per-slot table lookup is data driven, which costs an order of magnitude
+// in instructions for small env classes (C4: ~1 700 per env-step).  A specialised build bakes
+// the EngineSpec of ONE handle into the translation unit as a `__device__ constexpr` object;
+// the same kernel body (engine1_step_body) then sees compile-time agent counts, kinds, masks
+// and stage tables, and the compiler unrolls and folds them.  libphx only produces the source
+// text and loads the cubin; the host binding runs nvcc (phantom_b200/jit.py) and caches the
+// result, so there is no compiler inside the library and no link-time dependency on the driver.
+template <class P, class = void>
+struct HasJit : std::false_type {};
+template <class P>
+struct HasJit<P, std::void_t<decltype(P::JIT_SOURCE)>> : std::true_type {};
+
+template <class T>
+inline void jit_emit(std::string& o, const T& v) {
+  if constexpr (std::is_floating_point<T>::value) {
+    char buf[64];
+    std::snprintf(buf, sizeof(buf), std::is_same<T, float>::value ? "%.9gf" : "%.17g", (double)v);
+    std::string t(buf);
+    // "1f" / "1" are not floating literals: make sure there is a '.' or an exponent
+    const bool is_f = std::is_same<T, float>::value;
+    std::string body = is_f ? t.substr(0, t.size() - 1) : t;
+    if (body.find_first_of(".eEn") == std::string::npos) body += ".0";  // (n: nan / inf)
+    if (body.find("inf") != std::string::npos || body.find("nan") != std::string::npos)
+      body = "0.0";  // parameters are validated finite; never reached
+    o += body + (is_f ? "f" : "");
+  } else if constexpr (std::is_unsigned<T>::value) {
+    o += std::to_string((unsigned long long)v) + (sizeof(T) == 8 ? "ull" : "u");
+  } else {
+    o += std::to_string((long long)v);
+  }
+}
+template <class T, size_t N>
+inline void jit_emit(std::string& o, const T (&a)[N]) {
+  o += "{";
+  for (size_t i = 0; i < N; ++i) {
+    if (i) o += ", ";
+    jit_emit(o, a[i]);
+  }
+  o += "}";
+}
+// EngineSpec as a C++ aggregate initialiser, fields in declaration order (phx_engine.cuh).
+inline std::string jit_spec_literal(const EngineSpec& d) {
+  std::string o = "{\n  ";
+  auto f = [&](const auto& v) {
+    jit_emit(o, v);
+    o += ",\n  ";
+  };
+  f(d.E); f(d.n_agents); f(d.n_strategic); f(d.num_steps); f(d.round_limit); f(d.env_kind);
+  f(d.flags); f(d.obs_dim); f(d.act_dim); f(d.kind); f(d.sidx); f(d.adj); f(d.sender_ok);
+  f(d.receiver_ok); f(d.strategic_mask); f(d.kind_mask); f(d.n_stages); f(d.initial_stage);
+  f(d.stage_acting); f(d.stage_rewarded); f(d.stage_rewarded_none); f(d.stage_next);
+  f(d.leaders); f(d.followers); f(d.seed); f(d.env_offset); f(d.iparams); f(d.fparams);
+  f(d.dparams); f(d.agent_iparam); f(d.agent_fparam); f(d.codec_op); f(d.codec_val);
+  o += "}";
+  return o;
+}
+
 template <class P>
 __global__ void engine_init_kernel(int E, int G, int4* hdr, int32_t* state, int nwords) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -91,6 +151,7 @@ class EngineFamily : public Family {
     cudaFree(d_adj);
     cudaFree(d_base);
     cudaFree(d_env);
+    if (jit_lib) cudaLibraryUnload(jit_lib);
   }
 
   int32_t init(const phx_spec& s) override {
@@ -238,6 +299,12 @@ class EngineFamily : public Family {
                                                     spec.env_kind != PHX_ENV_BASE);
         const size_t smem = sizeof(int32_t) * (size_t)lay.words;
         const int grid = (E + ENGINE1_BLOCK - 1) / ENGINE1_BLOCK;
+        if (jit_kernel && !tracking()) {  // the build specialised for this handle's env class
+          void* args[] = {(void*)&a};
+          PHX_CUDA(cudaLaunchKernel((const void*)jit_kernel, dim3(grid), dim3(ENGINE1_BLOCK), args,
+                                    smem, stream));
+          return PHX_OK;
+        }
         if (tracking()) {
           PHX_CUDA(cudaFuncSetAttribute(engine1_step_kernel<P, true>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -254,6 +321,59 @@ class EngineFamily : public Family {
     return G == 8 ? launch_step<8>(a, stream)
            : G == 16 ? launch_step<16>(a, stream)
                      : launch_step<32>(a, stream);
+  }
+
+  int32_t jit_source(std::string& out) override {
+    if constexpr (HasJit<P>::value && P::Q1CAP > 0 && P::VW <= 1) {
+      PHX_REQUIRE(thread_per_env, PHX_ERR_UNSUPPORTED,
+                  "run-time specialisation is built for the thread-per-env engine "
+                  "(env classes of at most 8 agents)");
+      out = std::string("// generated by libphx (phx_jit_source): the thread-per-env step kernel of \n// ") +
+            P::JIT_NAME + " with this handle's lowered env class as a compile-time constant\n"
+            "#define PHX_JIT_TU 1\n#include \"" + P::JIT_SOURCE + "\"\n"
+            "namespace phx {\nnamespace {\n__device__ constexpr EngineSpec kSpec = " +
+            jit_spec_literal(espec) + ";\n"
+            "struct ConstSpec {\n  template <class A>\n"
+            "  __device__ __forceinline__ static const EngineSpec& get(const A&) { return kSpec; }\n};\n"
+            "}  // namespace\n"
+            "extern \"C\" __global__ void __launch_bounds__(ENGINE1_BLOCK)\n"
+            "phx_jit_step(const EngineArgs<" + P::JIT_NAME + "> a) {\n"
+            "  engine1_step_body<" + P::JIT_NAME + ", false, ConstSpec>(a);\n}\n}  // namespace phx\n";
+      return PHX_OK;
+    } else {
+      return Family::jit_source(out);
+    }
+  }
+
+  int32_t load_specialised(const char* cubin_path) override {
+    if constexpr (HasJit<P>::value && P::Q1CAP > 0 && P::VW <= 1) {
+      PHX_REQUIRE(thread_per_env, PHX_ERR_UNSUPPORTED,
+                  "run-time specialisation is built for the thread-per-env engine");
+      PHX_REQUIRE(cubin_path != nullptr, PHX_ERR_INVALID, "cubin path is NULL");
+      cudaLibrary_t lib = nullptr;
+      PHX_CUDA(cudaLibraryLoadFromFile(&lib, cubin_path, nullptr, nullptr, 0, nullptr, nullptr, 0));
+      cudaKernel_t k = nullptr;
+      cudaError_t err = cudaLibraryGetKernel(&k, lib, "phx_jit_step");
+      if (err != cudaSuccess) {
+        cudaLibraryUnload(lib);
+        PHX_CUDA(err);
+      }
+      const Engine1Layout lay = engine1_layout<P>(spec.n_agents, spec.n_strategic, qcap1,
+                                                  spec.env_kind != PHX_ENV_BASE);
+      err = cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(sizeof(int32_t) * (size_t)lay.words));
+      if (err != cudaSuccess) {
+        cudaLibraryUnload(lib);
+        PHX_CUDA(err);
+      }
+      if (jit_lib) cudaLibraryUnload(jit_lib);
+      jit_lib = lib;
+      jit_kernel = k;
+      name = "thread-per-env(G=8, specialised)";
+      return PHX_OK;
+    } else {
+      return Family::load_specialised(cubin_path);
+    }
   }
 
   int32_t family_field(int32_t field, int32_t index, void** p, size_t* bytes) override {
@@ -292,6 +412,8 @@ class EngineFamily : public Family {
   uint32_t* d_rnone = nullptr;
   float* d_ocache = nullptr;
   uint32_t* d_ocached = nullptr;
+  cudaLibrary_t jit_lib = nullptr;   // specialised build of the step kernel (load_specialised)
+  cudaKernel_t jit_kernel = nullptr;
   int32_t* d_env = nullptr;   // [ENVW][E] env-level words (programs with ENVW > 0)
   uint32_t* d_adj = nullptr;  // StochasticNetwork only
   uint2* d_base = nullptr;

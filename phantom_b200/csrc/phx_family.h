@@ -5,6 +5,7 @@
 // stage, done sets, fault words, message trace) lives here; the agent state columns and the
 // kernels live in fam_<name>.cu.
 #pragma once
+#include <string>
 #include <vector>
 
 #include "phx_common.cuh"
@@ -20,6 +21,19 @@ class Family {
   virtual int32_t reset(const uint8_t* env_mask, float* obs, uint8_t* obs_mask,
                         cudaStream_t stream) = 0;
   virtual int32_t rollout(int32_t T, const StepIO& io, cudaStream_t stream) = 0;
+  // Run-time specialisation (include/phx.h: phx_jit_source / phx_load_specialised): the text of a
+  // translation unit whose step kernel has THIS handle's lowered env class as a compile-time
+  // constant, and the loader of its compiled cubin.  Families without one: PHX_ERR_UNSUPPORTED.
+  virtual int32_t jit_source(std::string& out) {
+    (void)out;
+    set_error("this env class / kernel variant has no run-time specialisation");
+    return PHX_ERR_UNSUPPORTED;
+  }
+  virtual int32_t load_specialised(const char* cubin_path) {
+    (void)cubin_path;
+    set_error("this env class / kernel variant has no run-time specialisation");
+    return PHX_ERR_UNSUPPORTED;
+  }
   // Family state columns (field >= PHX_FIELD_FAMILY); returns PHX_ERR_INVALID if unknown.
   virtual int32_t family_field(int32_t field, int32_t index, void** dev_ptr, size_t* bytes) = 0;
   virtual const char* exec_name() const = 0;

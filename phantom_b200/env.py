@@ -204,6 +204,14 @@ class PhantomEnv:
         for a in self.agents.values():
             a._phx_env = self
 
+    def specialise(self) -> "PhantomEnv":
+        """Switch this handle to a build of the step kernel specialised to its env class
+        (phantom_b200/jit.py; thread-per-env engine).  Same results, fewer instructions."""
+        from . import jit
+
+        jit.specialise(self)
+        return self
+
     def close(self) -> None:
         if self._handle is not None:
             L.lib.phx_destroy(self._handle)

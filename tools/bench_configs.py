@@ -29,6 +29,8 @@ def peak():
 def measure(name, make_env, S, O, T, E, b_state, steps, binary_from=None, lean=False):
     env = make_env(num_envs=E, seed=0, auto_reset=True)
     env.reset_batch()
+    if name.endswith("-jit"):
+        env.specialise()  # step kernel rebuilt with this env class as a compile-time constant
     dev = torch.device("cuda", 0)
     nbuf = max(2, int(np.ceil(200e6 / (T * E * S * (4 + 4 * O + 8)))))
     gen = torch.Generator(device=dev).manual_seed(7)
@@ -96,10 +98,16 @@ def main():
          2 * (16 + 8 + 8 * (16 + 4) + 4), None, False),
         ("C4-stackelberg-thread", lambda **k: StackelbergGameEnv(exec_mode="thread", **k), 4, 2, 100, 131072,
          2 * (16 + 8 + 8 * (16 + 4) + 4), None, False),
+        ("C2-thread-jit", lambda **k: SupplyChainEnv(exec_mode="thread", **k), 1, 3, 100, 65536,
+         2 * (16 + 8 + 8 * 16), None, False),
+        ("C4-stackelberg-thread-jit", lambda **k: StackelbergGameEnv(exec_mode="thread", **k), 4, 2, 100,
+         131072, 2 * (16 + 8 + 8 * (16 + 4) + 4), None, False),
         ("C5-dense", lambda **k: DenseEnv(**k), 128, 3, 8, 16384, 2 * (16 + 6 * 128 * 4), None, False),
         # the reference's simple_market example (3 buyers + 2 sellers, 10-step episodes); state =
         # header + 19 words x 8 slots + reward / obs caches + env words
         ("X-simple-market-thread", lambda **k: sm.example_env(num_steps=10, exec_mode="thread", **k),
+         5, 3, 100, 65536, 2 * (16 + 8 + 19 * 8 * 4 + 8 * 4 + 8 * 12 + 8 + 8), 0, False),
+        ("X-simple-market-thread-jit", lambda **k: sm.example_env(num_steps=10, exec_mode="thread", **k),
          5, 3, 100, 65536, 2 * (16 + 8 + 19 * 8 * 4 + 8 * 4 + 8 * 12 + 8 + 8), 0, False),
         ("X-simple-market-queue", lambda **k: sm.example_env(num_steps=10, exec_mode="queue", **k),
          5, 3, 100, 65536, 2 * (16 + 8 + 19 * 8 * 4 + 8 * 4 + 8 * 12 + 8 + 8), 0, False),
