@@ -24,6 +24,9 @@ constexpr int MKT_NO_QUOTE = 1 << 20;
 constexpr int MKT_STREAM_VALUE = 1;
 
 struct MarketProgram {
+  // run-time specialisation: where this program lives and what it is called
+  static constexpr const char* JIT_SOURCE = "fam_market.cu";
+  static constexpr const char* JIT_NAME = "MarketProgram";
   // a maker quotes up to 24 takers and the clearing agent settles with 31 agents in the acting
   // phase; no handler of this market ever answers a message
   static constexpr int PW = 2, NWORDS = 8, VW = 1, ACTCAP = 32, RESPCAP = 1, OBS_DIM = 3,
@@ -161,6 +164,8 @@ struct MarketProgram {
 
 }  // namespace
 
+#ifndef PHX_JIT_TU
 Family* make_market_family(const phx_spec&) { return new EngineFamily<MarketProgram>(); }
+#endif
 
 }  // namespace phx

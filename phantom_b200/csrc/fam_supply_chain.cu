@@ -661,9 +661,9 @@ class SupplyChainFast final : public Family {
 //                           shop -> its factory);  [slot][1] = customer ordinal (RNG idx)
 template <int SEGCAP_>
 struct ScProgram {
-  // run-time specialisation (thread-per-env engine: SEGCAP_ == 8)
+  // run-time specialisation: where this program lives and what it is called
   static constexpr const char* JIT_SOURCE = "fam_supply_chain.cu";
-  static constexpr const char* JIT_NAME = "ScProgram<8>";
+  static constexpr const char* JIT_NAME = SEGCAP_ == 8 ? "ScProgram<8>" : "ScProgram<32>";
   // every agent sends at most one message in the acting phase; the shop answers every order
   static constexpr int PW = 1, NWORDS = 4, VW = 0, ACTCAP = 1, RESPCAP = SEGCAP_, OBS_DIM = 3,
                        ACT_DIM = 1;

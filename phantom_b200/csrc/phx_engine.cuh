@@ -461,13 +461,22 @@ __device__ __forceinline__ int engine_round(const EngineArgs<P>& a, const Ctx& c
 // interface: view / act / pre / handle / post / encode / reward / terminated / truncated /
 // reset_agent).  encode and reward receive the mutable agent state: the reference's
 // callbacks may have side effects (the KAT agents count their calls).
-template <class P, int G, bool TRACK>
-__global__ void __launch_bounds__(ENGINE_BLOCK) engine_step_kernel(const EngineArgs<P> a) {
+// Where a step kernel reads the lowered env class from.  SpecFromArgs: the kernel parameter
+// (constant bank; one precompiled kernel serves every env class of a family).  A specialised
+// build (phx_engine_host.cuh: jit_source) substitutes a compile-time constant spec, which lets
+// the compiler fold every flag, stage table and mask of THIS env class.
+struct SpecFromArgs {
+  template <class A>
+  __device__ __forceinline__ static const EngineSpec& get(const A& a) { return a.spec; }
+};
+
+template <class P, int G, bool TRACK, class SP>
+__device__ __forceinline__ void engine_step_body(const EngineArgs<P>& a) {
   constexpr int TPB = ENGINE_BLOCK / G;  // env tiles per block
   extern __shared__ __align__(16) unsigned char smem_raw[];
   BlockSmem<P, G>& bs = *reinterpret_cast<BlockSmem<P, G>*>(smem_raw);
 
-  const EngineSpec& sp = a.spec;
+  const EngineSpec& sp = SP::get(a);
   const int tb = threadIdx.x / G;
   const int slot = threadIdx.x % G;
   const int env = blockIdx.x * TPB + tb;
@@ -808,6 +817,11 @@ __global__ void __launch_bounds__(ENGINE_BLOCK) engine_step_kernel(const EngineA
   // first fault of the env in event order (phase, then agent order)
   const uint32_t fk = __reduce_min_sync(tmask, fault_key);
   if (env_live && slot == 0 && fk != 0xFFFFFFFFu) raise_fault(a.faults, e, fk & 0xFFu);
+}
+
+template <class P, int G, bool TRACK>
+__global__ void __launch_bounds__(ENGINE_BLOCK) engine_step_kernel(const EngineArgs<P> a) {
+  engine_step_body<P, G, TRACK, SpecFromArgs>(a);
 }
 
 // PhantomEnv.reset / FiniteStateMachineEnv.reset / StackelbergEnv.reset for masked envs.

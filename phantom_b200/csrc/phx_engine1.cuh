@@ -95,15 +95,6 @@ struct Emit1 {
   }
 };
 
-// Where the kernel reads the lowered env class from.  SpecFromArgs: the kernel parameter
-// (constant bank; one precompiled kernel serves every env class of a family).  A specialised
-// build (phx_jit.cuh) substitutes a compile-time constant spec, which lets the compiler unroll
-// the agent loops and fold every mask / kind / table lookup of THIS env class.
-struct SpecFromArgs {
-  template <class A>
-  __device__ __forceinline__ static const EngineSpec& get(const A& a) { return a.spec; }
-};
-
 template <class P, bool TRACK, class SP>
 __device__ __forceinline__ void engine1_step_body(const EngineArgs<P>& a) {
   static_assert(P::VW <= 1, "thread-per-env engine: views of at most one word per agent");

@@ -76,7 +76,7 @@ inline int32_t make_engine_spec(const phx_spec& s, int32_t E, uint64_t seed, int
 // loop, mask test and per-slot table lookup is data driven, which costs an order of magnitude
 // in instructions for small env classes (C4: ~1 700 per env-step).  A specialised build bakes
 // the EngineSpec of ONE handle into the translation unit as a `__device__ constexpr` object;
-// the same kernel body (engine1_step_body) then sees compile-time agent counts, kinds, masks
+// the same kernel body (engine1_step_body / engine_step_body) then sees compile-time agent counts, kinds, masks
 // and stage tables, and the compiler unrolls and folds them.  libphx only produces the source
 // text and loads the cubin; the host binding runs nvcc (phantom_b200/jit.py) and caches the
 // result, so there is no compiler inside the library and no link-time dependency on the driver.
@@ -248,6 +248,12 @@ class EngineFamily : public Family {
     constexpr int TPB = ENGINE_BLOCK / GG;
     const size_t smem = sizeof(BlockSmem<P, GG>);
     const int grid = (E + TPB - 1) / TPB;
+    if (jit_kernel && !tracking()) {  // the build specialised for this handle's env class
+      void* args[] = {(void*)&a};
+      PHX_CUDA(cudaLaunchKernel((const void*)jit_kernel, dim3(grid), dim3(ENGINE_BLOCK), args, smem,
+                                stream));
+      return PHX_OK;
+    }
     if (tracking()) {
       PHX_CUDA(cudaFuncSetAttribute(engine_step_kernel<P, GG, true>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -324,44 +330,52 @@ class EngineFamily : public Family {
   }
 
   int32_t jit_source(std::string& out) override {
-    if constexpr (HasJit<P>::value && P::Q1CAP > 0 && P::VW <= 1) {
-      PHX_REQUIRE(thread_per_env, PHX_ERR_UNSUPPORTED,
-                  "run-time specialisation is built for the thread-per-env engine "
-                  "(env classes of at most 8 agents)");
-      out = std::string("// generated by libphx (phx_jit_source): the thread-per-env step kernel of \n// ") +
-            P::JIT_NAME + " with this handle's lowered env class as a compile-time constant\n"
+    if constexpr (HasJit<P>::value) {
+      const bool thread_ok = P::Q1CAP > 0 && P::VW <= 1;
+      PHX_REQUIRE(!thread_per_env || thread_ok, PHX_ERR_UNSUPPORTED, "no specialisation");
+      const std::string prog = P::JIT_NAME;
+      const std::string body =
+          thread_per_env ? "engine1_step_body<" + prog + ", false, ConstSpec>(a);"
+                         : "engine_step_body<" + prog + ", " + std::to_string(G) + ", false, ConstSpec>(a);";
+      const std::string bound = thread_per_env ? "ENGINE1_BLOCK" : "ENGINE_BLOCK";
+      out = std::string("// generated by libphx (phx_jit_source): the ") +
+            (thread_per_env ? "thread-per-env" : "tile") + " step kernel of\n// " + prog +
+            " with this handle's lowered env class as a compile-time constant\n"
             "#define PHX_JIT_TU 1\n#include \"" + P::JIT_SOURCE + "\"\n"
             "namespace phx {\nnamespace {\n__device__ constexpr EngineSpec kSpec = " +
             jit_spec_literal(espec) + ";\n"
             "struct ConstSpec {\n  template <class A>\n"
             "  __device__ __forceinline__ static const EngineSpec& get(const A&) { return kSpec; }\n};\n"
             "}  // namespace\n"
-            "extern \"C\" __global__ void __launch_bounds__(ENGINE1_BLOCK)\n"
-            "phx_jit_step(const EngineArgs<" + P::JIT_NAME + "> a) {\n"
-            "  engine1_step_body<" + P::JIT_NAME + ", false, ConstSpec>(a);\n}\n}  // namespace phx\n";
+            "extern \"C\" __global__ void __launch_bounds__(" + bound + ")\n"
+            "phx_jit_step(const EngineArgs<" + prog + "> a) {\n  " + body + "\n}\n}  // namespace phx\n";
       return PHX_OK;
     } else {
       return Family::jit_source(out);
     }
   }
 
+  size_t step_smem_bytes() const {
+    if constexpr (P::Q1CAP > 0 && P::VW <= 1) {
+      if (thread_per_env) {
+        const Engine1Layout lay = engine1_layout<P>(spec.n_agents, spec.n_strategic, qcap1,
+                                                    spec.env_kind != PHX_ENV_BASE);
+        return sizeof(int32_t) * (size_t)lay.words;
+      }
+    }
+    return G == 8 ? sizeof(BlockSmem<P, 8>) : G == 16 ? sizeof(BlockSmem<P, 16>) : sizeof(BlockSmem<P, 32>);
+  }
+
   int32_t load_specialised(const char* cubin_path) override {
-    if constexpr (HasJit<P>::value && P::Q1CAP > 0 && P::VW <= 1) {
-      PHX_REQUIRE(thread_per_env, PHX_ERR_UNSUPPORTED,
-                  "run-time specialisation is built for the thread-per-env engine");
+    if constexpr (HasJit<P>::value) {
       PHX_REQUIRE(cubin_path != nullptr, PHX_ERR_INVALID, "cubin path is NULL");
       cudaLibrary_t lib = nullptr;
       PHX_CUDA(cudaLibraryLoadFromFile(&lib, cubin_path, nullptr, nullptr, 0, nullptr, nullptr, 0));
       cudaKernel_t k = nullptr;
       cudaError_t err = cudaLibraryGetKernel(&k, lib, "phx_jit_step");
-      if (err != cudaSuccess) {
-        cudaLibraryUnload(lib);
-        PHX_CUDA(err);
-      }
-      const Engine1Layout lay = engine1_layout<P>(spec.n_agents, spec.n_strategic, qcap1,
-                                                  spec.env_kind != PHX_ENV_BASE);
-      err = cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)(sizeof(int32_t) * (size_t)lay.words));
+      if (err == cudaSuccess)
+        err = cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)step_smem_bytes());
       if (err != cudaSuccess) {
         cudaLibraryUnload(lib);
         PHX_CUDA(err);
@@ -369,7 +383,8 @@ class EngineFamily : public Family {
       if (jit_lib) cudaLibraryUnload(jit_lib);
       jit_lib = lib;
       jit_kernel = k;
-      name = "thread-per-env(G=8, specialised)";
+      name = thread_per_env ? std::string("thread-per-env(G=8, specialised)")
+                            : std::string("queue(G=") + std::to_string(G) + ", specialised)";
       return PHX_OK;
     } else {
       return Family::load_specialised(cubin_path);

@@ -39,6 +39,21 @@ def test_specialised_simple_market_matches_reference_golden(golden_dir):
     run_device_vs_golden(make, g).close()
 
 
+def test_specialised_tile_engine_matches_reference_golden(golden_dir):
+    """The lane-per-agent tiling (C3, 32 agents, three FSM stages) specialised: flags, stage tables
+    and masks fold; the golden of the unmodified reference still matches bit for bit."""
+    from phantom_b200.envs.market import MarketEnv
+
+    g = np.load(os.path.join(golden_dir, "market_reference.npz"))
+
+    def make(**kw):
+        env = MarketEnv(**kw).specialise()
+        assert env.exec_name == "queue(G=32, specialised)"
+        return env
+
+    run_device_vs_golden(make, g).close()
+
+
 def test_specialised_equals_generic_at_scale_and_caches():
     """Auto-reset rollouts at 16 384 envs: specialised == generic; the second specialise() of an
     identical handle is a cache hit (no compile); an env class without a specialisation says so."""
@@ -68,5 +83,5 @@ def test_specialised_equals_generic_at_scale_and_caches():
     fast = SupplyChainEnv(num_envs=64)
     fast.reset_batch()
     with pytest.raises(RuntimeError, match="no run-time specialisation"):
-        fast.specialise()
+        fast.specialise()  # the schedule-specialised fast kernel has nothing left to fold
     fast.close()

@@ -102,6 +102,10 @@ def main():
          2 * (16 + 8 + 8 * 16), None, False),
         ("C4-stackelberg-thread-jit", lambda **k: StackelbergGameEnv(exec_mode="thread", **k), 4, 2, 100,
          131072, 2 * (16 + 8 + 8 * (16 + 4) + 4), None, False),
+        ("C3-market-jit", lambda **k: MarketEnv(**k), 31, 3, 99, 32768,
+         2 * (16 + 8 + 32 * (8 * 4 + 4 + 12) + 8), 7, False),
+        ("C4-stackelberg-queue-jit", lambda **k: StackelbergGameEnv(exec_mode="queue", **k), 4, 2, 100,
+         131072, 2 * (16 + 8 + 8 * (16 + 4) + 4), None, False),
         ("C5-dense", lambda **k: DenseEnv(**k), 128, 3, 8, 16384, 2 * (16 + 6 * 128 * 4), None, False),
         # the reference's simple_market example (3 buyers + 2 sellers, 10-step episodes); state =
         # header + 19 words x 8 slots + reward / obs caches + env words
