@@ -356,8 +356,10 @@ class PhantomEnv:
     @property
     def tile_width(self) -> int:
         """Lanes per env of the queue engine (state columns are [E, G], slot-major)."""
-        name = self.exec_name
-        return int(name.split("G=")[1].rstrip(")")) if "G=" in name else 0
+        import re
+
+        m = re.search(r"G=(\d+)", self.exec_name)
+        return int(m.group(1)) if m else 0
 
     def adjacency(self) -> np.ndarray:
         """Per-env graphs of a StochasticNetwork: uint8 [E, n_agents, n_agents], entry [e, s, r]

@@ -36,7 +36,9 @@ def test_specialised_simple_market_matches_reference_golden(golden_dir):
         env = sm.example_env(buyers, n_sellers, T, exec_mode="thread", **kw)
         return env.specialise()
 
-    run_device_vs_golden(make, g).close()
+    from .test_gpu_simple_market import market_state
+
+    run_device_vs_golden(make, g, state_fn=market_state).close()
 
 
 def test_specialised_tile_engine_matches_reference_golden(golden_dir):
