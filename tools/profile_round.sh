@@ -18,7 +18,9 @@ $full -k regex:sc_fast -s 6 -c 1 -o $out/prof_sc_fast_${tag} \
 $full -k regex:engine_step -s 3 -c 1 -o $out/prof_engine_c3_${tag} \
     python tools/bench_configs.py --only C3 --steps 3 > /dev/null 2>&1
 $full -k regex:engine1_step -s 3 -c 1 -o $out/prof_engine1_c4_${tag} \
-    python tools/bench_configs.py --only C4-thread --steps 3 > /dev/null 2>&1
+    python tools/bench_configs.py --only C4-stackelberg-thread --steps 3 > /dev/null 2>&1
+$full -k regex:phx_jit_step -s 3 -c 1 -o $out/prof_jit_c4_${tag} \
+    python tools/bench_configs.py --only C4-stackelberg-thread-jit --steps 3 > /dev/null 2>&1
 $full -k regex:dense_step -s 3 -c 1 -o $out/prof_dense_c5_${tag} \
     python tools/bench_configs.py --only C5 --steps 3 > /dev/null 2>&1
 python tools/bench_configs.py --steps 20 > $out/bench_configs_${tag}.jsonl 2>&1
