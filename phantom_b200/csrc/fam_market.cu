@@ -49,6 +49,17 @@ struct MarketProgram {
     return PHX_OK;
   }
 
+  // The clearing agent's per-maker words are addressed by a run-time maker ordinal; a plain
+  // st[k] would push the whole state array of EVERY lane to local memory (the C3 profile showed
+  // the spill stores among the top stalls), a compare chain keeps it in registers.
+  __device__ static int maker_word(const int* st, int k) {
+    int v = 0;
+#pragma unroll
+    for (int j = 0; j < 7; ++j)
+      if (j == k) v = st[j];
+    return v;
+  }
+
   __device__ static void view(const Ctx& c, const int* st, int* v) {
     v[0] = c.kind == MKT_MAKER ? st[0] : 0;  // MakerView(inventory)
   }
@@ -72,7 +83,7 @@ struct MarketProgram {
     } else if (c.stage == sp.iparams[5]) {  // ClearingAgent.generate_messages, CLEARING stage
       for (uint32_t m = c.neighbours_of_kind(MKT_MAKER); m; m &= m - 1) {
         const int r = __ffs(m) - 1;
-        const int w = st[c.iparam0_of(r)];
+        const int w = maker_word(st, c.iparam0_of(r));
         out.send(r, MKT_FILL, w & 0xFF, w >> 8);
       }
       for (uint32_t m = c.neighbours_of_kind(MKT_TAKER); m; m &= m - 1) {
@@ -124,8 +135,10 @@ struct MarketProgram {
     }
     if (m.type != MKT_ORDER) return false;
     const int mk = m.p[0];
-    if ((st[mk] & 0xFF) < sp.iparams[3]) {  // first come, first served
-      st[mk] += 1 + (m.p[1] << 8);
+    if ((maker_word(st, mk) & 0xFF) < sp.iparams[3]) {  // first come, first served
+#pragma unroll
+      for (int j = 0; j < 7; ++j)
+        if (j == mk) st[j] += 1 + (m.p[1] << 8);
       st[7] |= 1 << c.iparam0_of(m.sender);
     }
     return true;
