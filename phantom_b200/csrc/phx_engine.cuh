@@ -140,6 +140,8 @@ struct TileQueue {
   int32_t pay[PW][SEGCAP][G];
   uint8_t cnt[G];             // entries per segment
   uint8_t order[G];           // segment visiting order
+  uint16_t ordcnt[G];         // the same, with the segment's length: order[i] | cnt[order[i]] << 8
+                              // (one load per lane instead of two dependent ones)
   int32_t nseg;
 };
 
@@ -326,8 +328,8 @@ __device__ __forceinline__ int engine_round(const EngineArgs<P>& a, const Ctx& c
     // then walks only the non-empty segments (a ballot) and gets (segment, length) by shuffle.
     // (Walking all 32 segments with two dependent shared-memory byte loads each was a third of
     // all stall samples of the C3 profile: in a market step 7, 24 or 1 segments hold mail.)
-    const int my_seg = slot < nseg ? (int)qc.order[slot] : 0;
-    const int my_cnt = slot < nseg ? (int)qc.cnt[my_seg] : 0;
+    const int my_oc = slot < nseg ? (int)qc.ordcnt[slot] : 0;
+    const int my_seg = my_oc & 0xFF, my_cnt = my_oc >> 8;
     for (uint32_t live_segs = __ballot_sync(tmask, my_cnt > 0); live_segs; live_segs &= live_segs - 1) {
       const int si = __ffs(live_segs) - 1;
       const int seg = __shfl_sync(tmask, my_seg, si);
@@ -446,7 +448,10 @@ __device__ __forceinline__ int engine_round(const EngineArgs<P>& a, const Ctx& c
     nrecv += fj != INF;
     rank += fj < first;
   }
-  if (first != INF) qn.order[rank] = (uint8_t)slot;
+  if (first != INF) {
+    qn.order[rank] = (uint8_t)slot;
+    qn.ordcnt[rank] = (uint16_t)(slot | (resp.n << 8));
+  }
   if (slot == 0) qn.nseg = nrecv;
   __syncwarp(tmask);
   if (TRACK && trace_lane) {
@@ -609,6 +614,7 @@ __device__ __forceinline__ void engine_step_body(const EngineArgs<P>& a) {
     if (has_ctx && (acting & slot_bit)) P::act(ctx, st, strategic && has_action_now, act, out);
     ts.qa.cnt[slot] = (uint8_t)out.n;
     ts.qa.order[slot] = (uint8_t)slot;
+    ts.qa.ordcnt[slot] = (uint16_t)(slot | (out.n << 8));
     if (slot == 0) ts.qa.nseg = sp.n_agents;
     if (out.fault) fault_key = min(fault_key, (0u << 16) | ((uint32_t)slot << 8) | out.fault);
     int pending = __reduce_add_sync(tmask, out.n);
