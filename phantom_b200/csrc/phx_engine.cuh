@@ -338,7 +338,16 @@ __device__ __forceinline__ int engine_round(const EngineArgs<P>& a, const Ctx& c
         const int k = k0 + slot;
         const bool valid = k < c;
         const int r = valid ? (int)((qc.head[valid ? k : 0][seg] >> 8) & 0xFFu) : 0x100 + slot;
-        const uint32_t peers = __match_any_sync(tmask, r);
+        // lanes holding an entry for the same receiver.  Built from six ballots (validity + the
+        // five bits of r): __match_any_sync is one instruction but ~100 cycles of latency, and
+        // this loop has nothing to overlap it with -- it was 15 % of all stall samples on C3.
+        uint32_t peers = __ballot_sync(tmask, valid);
+#pragma unroll
+        for (int b = 0; b < 5; ++b) {
+          const bool bit = (r >> b) & 1;
+          const uint32_t with_bit = __ballot_sync(tmask, bit);
+          peers &= bit ? with_bit : ~with_bit;
+        }
         const int rank = __popc(peers & below);
         const int base = valid ? ts.rcnt[r] : 0;
         __syncwarp(tmask);  // every peer has read the group's base before its leader bumps it
