@@ -580,7 +580,9 @@ __device__ __forceinline__ void engine_step_body(const EngineArgs<P>& a) {
 #pragma unroll
     for (int j = 0; j < P::ACT_DIM; ++j) act[j] = act_next[j];
     const bool has_action_now = has_next != 0;
-    if (strategic && env_live && t + 1 < a.T) {
+    // next step's action is prefetched here on narrow tiles (short steps: the load needs the
+    // whole step to land) and after the acting phase on 32-lane tiles (see below)
+    if (G < 32 && strategic && env_live && t + 1 < a.T) {
       const size_t arow = (row + sp.E) * S + sidx;
 #pragma unroll
       for (int j = 0; j < P::ACT_DIM; ++j) act_next[j] = a.io.actions[arow * P::ACT_DIM + j];
@@ -621,6 +623,15 @@ __device__ __forceinline__ void engine_step_body(const EngineArgs<P>& a) {
     }
     Emit<decltype(ts.qa)> out{&ts.qa, &sp, slot, ctx.out_mask, 0, 0u};
     if (has_ctx && (acting & slot_bit)) P::act(ctx, st, strategic && has_action_now, act, out);
+    // 32-lane tiles: issued after the acting phase, so that the loaded value is not live across
+    // the program's act() call (it was spilled to local memory right after the load, which made
+    // the "prefetch" wait for the load: 5 % of all stall samples on C3)
+    if (G >= 32 && strategic && env_live && t + 1 < a.T) {
+      const size_t arow = (row + sp.E) * S + sidx;
+#pragma unroll
+      for (int j = 0; j < P::ACT_DIM; ++j) act_next[j] = a.io.actions[arow * P::ACT_DIM + j];
+      if (a.io.action_mask) has_next = a.io.action_mask[arow];
+    }
     ts.qa.cnt[slot] = (uint8_t)out.n;
     ts.qa.order[slot] = (uint8_t)slot;
     ts.qa.ordcnt[slot] = (uint16_t)(slot | (out.n << 8));
