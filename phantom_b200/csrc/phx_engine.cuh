@@ -136,7 +136,8 @@ struct Ctx {
 template <int G, int SEGCAP, int PW>
 struct TileQueue {
   static constexpr int CAP = SEGCAP;
-  uint32_t head[SEGCAP][G];   // sender | recv << 8 | type << 16
+  uint16_t head[SEGCAP][G];   // recv | type << 8 (the sender is the segment; 16 bits keep the
+                              // 32-agent tile at 13 KB: 4 instead of 3 blocks per SM)
   int32_t pay[PW][SEGCAP][G];
   uint8_t cnt[G];             // entries per segment
   uint8_t order[G];           // segment visiting order
@@ -171,7 +172,7 @@ struct Emit {
       fault = PHX_FAULT_QUEUE_OVERFLOW;
       return;
     }
-    q->head[n][slot] = (uint32_t)slot | ((uint32_t)recv << 8) | ((uint32_t)type << 16);
+    q->head[n][slot] = (uint16_t)((uint32_t)recv | ((uint32_t)type << 8));
     q->pay[0][n][slot] = p0;
     if (sizeof(q->pay) / sizeof(q->pay[0]) > 1) q->pay[sizeof(q->pay) / sizeof(q->pay[0]) > 1 ? 1 : 0][n][slot] = p1;
     ++n;
@@ -337,7 +338,7 @@ __device__ __forceinline__ int engine_round(const EngineArgs<P>& a, const Ctx& c
       for (int k0 = 0; k0 < c; k0 += G) {
         const int k = k0 + slot;
         const bool valid = k < c;
-        const int r = valid ? (int)((qc.head[valid ? k : 0][seg] >> 8) & 0xFFu) : 0x100 + slot;
+        const int r = valid ? (int)(qc.head[valid ? k : 0][seg] & 0xFFu) : 0x100 + slot;
         // lanes holding an entry for the same receiver.  Built from six ballots (validity + the
         // five bits of r): __match_any_sync is one instruction but ~100 cycles of latency, and
         // this loop has nothing to overlap it with -- it was 15 % of all stall samples on C3.
@@ -380,7 +381,7 @@ __device__ __forceinline__ int engine_round(const EngineArgs<P>& a, const Ctx& c
         if (!((ctx.in_mask >> seg) & 1u)) continue;  // delivery-time edge filter (:146-148)
         Msg m;
         m.sender = seg;  // a segment holds the messages of one sender
-        m.type = (int)((qc.head[k][seg] >> 16) & 0xFFu);
+        m.type = (int)(qc.head[k][seg] >> 8);
         m.p[0] = qc.pay[0][k][seg];
         m.p[1] = P::PW > 1 ? qc.pay[P::PW > 1 ? 1 : 0][k][seg] : 0;
         if (!P::handle(ctx, st, m, resp)) bad_type = true;  // agents.py:140-143
@@ -401,8 +402,8 @@ __device__ __forceinline__ int engine_round(const EngineArgs<P>& a, const Ctx& c
       const int seg = qc.order[si];
       const int c = qc.cnt[seg];
       for (int k = 0; k < c; ++k, ++pos) {
-        const uint32_t hd = qc.head[k][seg];
-        if ((int)((hd >> 8) & 0xFFu) != slot) continue;
+        const uint32_t hd = qc.head[k][seg];  // recv | type << 8
+        if ((int)(hd & 0xFFu) != slot) continue;
         if (first == INF) first = pos;  // first-arrival position of this receiver
         if (!has_ctx) continue;         // done agent: mail dropped (resolvers.py:143-144)
         if (!((ctx.in_mask >> seg) & 1u)) continue;  // delivery-time edge filter (:146-148)
@@ -413,7 +414,7 @@ __device__ __forceinline__ int engine_round(const EngineArgs<P>& a, const Ctx& c
         }
         Msg m;
         m.sender = seg;
-        m.type = (int)((hd >> 16) & 0xFFu);
+        m.type = (int)(hd >> 8);
         m.p[0] = qc.pay[0][k][seg];
         m.p[1] = P::PW > 1 ? qc.pay[P::PW > 1 ? 1 : 0][k][seg] : 0;
         if (!P::handle(ctx, st, m, resp)) bad_type = true;  // agents.py:140-143
@@ -429,7 +430,7 @@ __device__ __forceinline__ int engine_round(const EngineArgs<P>& a, const Ctx& c
         const int seg = ent & 0xFF, k = ent >> 8;
         Msg m;
         m.sender = seg;
-        m.type = (int)((qc.head[k][seg] >> 16) & 0xFFu);
+        m.type = (int)(qc.head[k][seg] >> 8);
         m.p[0] = qc.pay[0][k][seg];
         m.p[1] = P::PW > 1 ? qc.pay[P::PW > 1 ? 1 : 0][k][seg] : 0;
         if (!P::handle(ctx, st, m, resp)) bad_type = true;
@@ -469,7 +470,7 @@ __device__ __forceinline__ int engine_round(const EngineArgs<P>& a, const Ctx& c
       for (int k = 0; k < qn.cnt[seg]; ++k) {
         if (traced < a.trace.cap)
           a.trace.rows[(size_t)e * a.trace.cap + traced] =
-              make_int4((int)qn.head[k][seg], qn.pay[0][k][seg],
+              make_int4((int)(((uint32_t)qn.head[k][seg] << 8) | (uint32_t)seg), qn.pay[0][k][seg],
                         P::PW > 1 ? qn.pay[P::PW > 1 ? 1 : 0][k][seg] : 0, round + 1);
         ++traced;
       }
@@ -647,7 +648,7 @@ __device__ __forceinline__ void engine_step_body(const EngineArgs<P>& a) {
         for (int k = 0; k < ts.qa.cnt[si]; ++k) {
           if (traced < a.trace.cap)
             a.trace.rows[(size_t)e * a.trace.cap + traced] =
-                make_int4((int)ts.qa.head[k][si], ts.qa.pay[0][k][si],
+                make_int4((int)(((uint32_t)ts.qa.head[k][si] << 8) | (uint32_t)si), ts.qa.pay[0][k][si],
                           P::PW > 1 ? ts.qa.pay[P::PW > 1 ? 1 : 0][k][si] : 0, 0);
           ++traced;
         }
