@@ -32,6 +32,12 @@ struct MarketProgram {
   static constexpr int PW = 2, NWORDS = 8, VW = 1, ACTCAP = 32, RESPCAP = 1, OBS_DIM = 3,
                        ACT_DIM = 1, Q1CAP = 0;  // 32 agents: tile engine only
   static constexpr int RECVCAP = 32;  // max messages one agent receives in a round
+  // compact acting queue: a maker quotes its taker neighbours, a taker sends at most one order,
+  // the clearing agent settles with every neighbour -- 7 x 25 + 24 + 31 = 230 entries at most
+  static constexpr int ACTTOTAL = 256;
+  __host__ __device__ static int act_cap(int kind, int out_degree) {
+    return kind == 1 /* MKT_TAKER */ ? 1 : out_degree;
+  }
   static constexpr bool BATCHED = false, HAS_PRE = true, HAS_POST = true;
 
   static int q1_cap(const phx_spec&) { return 0; }

@@ -131,19 +131,57 @@ struct Ctx {
 };
 
 // Segmented queue of one env in shared memory.  Entry (seg, k): head word + PW payload
-// words.  Layout is word-major so that the lanes of a tile writing their own segments hit
-// different banks.
+// words; the segment is the SENDER's slot.  Two layouts behind one accessor interface:
+//   TileQueue     every segment has SEGCAP entries, word-major ([k][seg]): the lanes of a tile
+//                 writing their own segments hit different banks
+//   CompactQueue  segment s occupies [base[s], base[s+1]) of one flat array; the per-segment
+//                 capacities come from the lowered env class (P::act_cap(kind, out-degree)).
+//                 A 32-agent market step holds at most 230 acting-phase messages, the
+//                 fixed layout reserves 32 x 32 = 1024 entries for them: compacting takes the
+//                 tile from 13 KB to 6 KB of shared memory and doubles the resident warps.
 template <int G, int SEGCAP, int PW>
 struct TileQueue {
-  static constexpr int CAP = SEGCAP;
-  uint16_t head[SEGCAP][G];   // recv | type << 8 (the sender is the segment; 16 bits keep the
-                              // 32-agent tile at 13 KB: 4 instead of 3 blocks per SM)
+  uint16_t head[SEGCAP][G];   // recv | type << 8 (the sender is the segment)
   int32_t pay[PW][SEGCAP][G];
   uint8_t cnt[G];             // entries per segment
   uint8_t order[G];           // segment visiting order
   uint16_t ordcnt[G];         // the same, with the segment's length: order[i] | cnt[order[i]] << 8
                               // (one load per lane instead of two dependent ones)
   int32_t nseg;
+  __device__ __forceinline__ uint16_t& hd(int k, int seg) { return head[k][seg]; }
+  __device__ __forceinline__ int32_t& py(int w, int k, int seg) { return pay[w][k][seg]; }
+  __device__ __forceinline__ int cap_of(int) const { return SEGCAP; }
+};
+
+template <int G, int TOTAL, int PW>
+struct CompactQueue {
+  uint16_t head[TOTAL];
+  int32_t pay[PW][TOTAL];
+  uint16_t base[G + 1];       // set once per launch from the lowered env class
+  uint8_t cnt[G];
+  uint8_t order[G];
+  uint16_t ordcnt[G];
+  int32_t nseg;
+  __device__ __forceinline__ uint16_t& hd(int k, int seg) { return head[base[seg] + k]; }
+  __device__ __forceinline__ int32_t& py(int w, int k, int seg) { return pay[w][base[seg] + k]; }
+  __device__ __forceinline__ int cap_of(int seg) const { return base[seg + 1] - base[seg]; }
+};
+
+// A program opts into the compact acting queue with
+//     static constexpr int ACTTOTAL = <entries>;
+//     __host__ __device__ static int act_cap(int kind, int out_degree);   // sends per step, at most
+template <class P, class = void>
+struct HasActTotal : std::false_type {};
+template <class P>
+struct HasActTotal<P, std::void_t<decltype(P::ACTTOTAL)>> : std::true_type {};
+
+template <class P, int G, bool COMPACT = HasActTotal<P>::value>
+struct ActQueueOf {
+  using type = TileQueue<G, P::ACTCAP, P::PW>;
+};
+template <class P, int G>
+struct ActQueueOf<P, G, true> {
+  using type = CompactQueue<G, P::ACTTOTAL, P::PW>;
 };
 
 // Emission cursor of one lane: appends to the lane's own segment after the reference's send
@@ -168,13 +206,13 @@ struct Emit {
         return;
       }
     }
-    if (n >= Q::CAP) {
+    if (n >= q->cap_of(slot)) {
       fault = PHX_FAULT_QUEUE_OVERFLOW;
       return;
     }
-    q->head[n][slot] = (uint16_t)((uint32_t)recv | ((uint32_t)type << 8));
-    q->pay[0][n][slot] = p0;
-    if (sizeof(q->pay) / sizeof(q->pay[0]) > 1) q->pay[sizeof(q->pay) / sizeof(q->pay[0]) > 1 ? 1 : 0][n][slot] = p1;
+    q->hd(n, slot) = (uint16_t)((uint32_t)recv | ((uint32_t)type << 8));
+    q->py(0, n, slot) = p0;
+    if (sizeof(q->pay) / sizeof(q->pay[0]) > 1) q->py(sizeof(q->pay) / sizeof(q->pay[0]) > 1 ? 1 : 0, n, slot) = p1;
     ++n;
   }
 };
@@ -235,7 +273,7 @@ __device__ __forceinline__ uint32_t tile_mask(int G) {
 // alternate between the response rounds (RESPCAP per agent).
 template <class P, int G>
 struct TileSmem {
-  TileQueue<G, P::ACTCAP, P::PW> qa;
+  typename ActQueueOf<P, G>::type qa;
   TileQueue<G, P::RESPCAP, P::PW> qr[2];
   int32_t views[G][P::VW > 0 ? P::VW : 1];
   int32_t first_idx[G];
@@ -338,7 +376,7 @@ __device__ __forceinline__ int engine_round(const EngineArgs<P>& a, const Ctx& c
       for (int k0 = 0; k0 < c; k0 += G) {
         const int k = k0 + slot;
         const bool valid = k < c;
-        const int r = valid ? (int)(qc.head[valid ? k : 0][seg] & 0xFFu) : 0x100 + slot;
+        const int r = valid ? (int)(qc.hd(valid ? k : 0, seg) & 0xFFu) : 0x100 + slot;
         // lanes holding an entry for the same receiver.  Built from six ballots (validity + the
         // five bits of r): __match_any_sync is one instruction but ~100 cycles of latency, and
         // this loop has nothing to overlap it with -- it was 15 % of all stall samples on C3.
@@ -381,9 +419,9 @@ __device__ __forceinline__ int engine_round(const EngineArgs<P>& a, const Ctx& c
         if (!((ctx.in_mask >> seg) & 1u)) continue;  // delivery-time edge filter (:146-148)
         Msg m;
         m.sender = seg;  // a segment holds the messages of one sender
-        m.type = (int)(qc.head[k][seg] >> 8);
-        m.p[0] = qc.pay[0][k][seg];
-        m.p[1] = P::PW > 1 ? qc.pay[P::PW > 1 ? 1 : 0][k][seg] : 0;
+        m.type = (int)(qc.hd(k, seg) >> 8);
+        m.p[0] = qc.py(0, k, seg);
+        m.p[1] = P::PW > 1 ? qc.py(P::PW > 1 ? 1 : 0, k, seg) : 0;
         if (!P::handle(ctx, st, m, resp)) bad_type = true;  // agents.py:140-143
       }
       if constexpr (P::BATCHED) {
@@ -402,7 +440,7 @@ __device__ __forceinline__ int engine_round(const EngineArgs<P>& a, const Ctx& c
       const int seg = qc.order[si];
       const int c = qc.cnt[seg];
       for (int k = 0; k < c; ++k, ++pos) {
-        const uint32_t hd = qc.head[k][seg];  // recv | type << 8
+        const uint32_t hd = qc.hd(k, seg);  // recv | type << 8
         if ((int)(hd & 0xFFu) != slot) continue;
         if (first == INF) first = pos;  // first-arrival position of this receiver
         if (!has_ctx) continue;         // done agent: mail dropped (resolvers.py:143-144)
@@ -415,8 +453,8 @@ __device__ __forceinline__ int engine_round(const EngineArgs<P>& a, const Ctx& c
         Msg m;
         m.sender = seg;
         m.type = (int)(hd >> 8);
-        m.p[0] = qc.pay[0][k][seg];
-        m.p[1] = P::PW > 1 ? qc.pay[P::PW > 1 ? 1 : 0][k][seg] : 0;
+        m.p[0] = qc.py(0, k, seg);
+        m.p[1] = P::PW > 1 ? qc.py(P::PW > 1 ? 1 : 0, k, seg) : 0;
         if (!P::handle(ctx, st, m, resp)) bad_type = true;  // agents.py:140-143
       }
     }
@@ -430,9 +468,9 @@ __device__ __forceinline__ int engine_round(const EngineArgs<P>& a, const Ctx& c
         const int seg = ent & 0xFF, k = ent >> 8;
         Msg m;
         m.sender = seg;
-        m.type = (int)(qc.head[k][seg] >> 8);
-        m.p[0] = qc.pay[0][k][seg];
-        m.p[1] = P::PW > 1 ? qc.pay[P::PW > 1 ? 1 : 0][k][seg] : 0;
+        m.type = (int)(qc.hd(k, seg) >> 8);
+        m.p[0] = qc.py(0, k, seg);
+        m.p[1] = P::PW > 1 ? qc.py(P::PW > 1 ? 1 : 0, k, seg) : 0;
         if (!P::handle(ctx, st, m, resp)) bad_type = true;
       }
     }
@@ -470,8 +508,8 @@ __device__ __forceinline__ int engine_round(const EngineArgs<P>& a, const Ctx& c
       for (int k = 0; k < qn.cnt[seg]; ++k) {
         if (traced < a.trace.cap)
           a.trace.rows[(size_t)e * a.trace.cap + traced] =
-              make_int4((int)(((uint32_t)qn.head[k][seg] << 8) | (uint32_t)seg), qn.pay[0][k][seg],
-                        P::PW > 1 ? qn.pay[P::PW > 1 ? 1 : 0][k][seg] : 0, round + 1);
+              make_int4((int)(((uint32_t)qn.hd(k, seg) << 8) | (uint32_t)seg), qn.py(0, k, seg),
+                        P::PW > 1 ? qn.py(P::PW > 1 ? 1 : 0, k, seg) : 0, round + 1);
         ++traced;
       }
     }
@@ -518,6 +556,19 @@ __device__ __forceinline__ void engine_step_body(const EngineArgs<P>& a) {
   const int kind = slot < sp.n_agents ? sp.kind[slot] : -1;
   const int sidx = slot < sp.n_agents ? sp.sidx[slot] : -1;
   const bool strategic = sidx >= 0;
+  if constexpr (HasActTotal<P>::value) {
+    // compact acting queue: segment capacities from the lowered env class, exclusive prefix sums
+    // (the host has checked that they fit P::ACTTOTAL)
+    int incl = slot < sp.n_agents ? min(P::ACTCAP, P::act_cap(kind, __popc(sp.adj[slot]))) : 0;
+#pragma unroll
+    for (int off = 1; off < G; off <<= 1) {
+      const int v = __shfl_up_sync(tmask, incl, off, G);
+      if (slot >= off) incl += v;
+    }
+    ts.qa.base[slot + 1] = (uint16_t)incl;
+    if (slot == 0) ts.qa.base[0] = 0;
+    __syncwarp(tmask);
+  }
   const uint32_t slot_bit = 1u << slot;
   const int S = sp.n_strategic, O = sp.obs_dim;
 
@@ -648,8 +699,8 @@ __device__ __forceinline__ void engine_step_body(const EngineArgs<P>& a) {
         for (int k = 0; k < ts.qa.cnt[si]; ++k) {
           if (traced < a.trace.cap)
             a.trace.rows[(size_t)e * a.trace.cap + traced] =
-                make_int4((int)(((uint32_t)ts.qa.head[k][si] << 8) | (uint32_t)si), ts.qa.pay[0][k][si],
-                          P::PW > 1 ? ts.qa.pay[P::PW > 1 ? 1 : 0][k][si] : 0, 0);
+                make_int4((int)(((uint32_t)ts.qa.hd(k, si) << 8) | (uint32_t)si), ts.qa.py(0, k, si),
+                          P::PW > 1 ? ts.qa.py(P::PW > 1 ? 1 : 0, k, si) : 0, 0);
           ++traced;
         }
     }

@@ -160,6 +160,18 @@ class EngineFamily : public Family {
     rc = P::validate(s);
     if (rc != PHX_OK) return rc;
     G = s.n_agents <= 8 ? 8 : (s.n_agents <= 16 ? 16 : 32);
+    if constexpr (HasActTotal<P>::value) {  // compact acting queue: the capacities must fit
+      PHX_REQUIRE(!(s.flags & PHX_FLAG_STOCHASTIC_NETWORK), PHX_ERR_UNSUPPORTED,
+                  "this family's compact acting queue is sized from a fixed graph");
+      int total = 0;
+      for (int i = 0; i < s.n_agents; ++i) {
+        int deg = 0;
+        for (int r = 0; r < s.n_agents; ++r) deg += mask_bit(s.adjacency[i], r);
+        total += std::min((int)P::ACTCAP, P::act_cap(s.agent_kind[i], deg));
+      }
+      PHX_REQUIRE(total <= P::ACTTOTAL, PHX_ERR_UNSUPPORTED,
+                  "acting-phase fan-out of this env class exceeds the family's queue");
+    }
     // thread-per-env variant: <= 8 agents and a program that declares its queue bound
     qcap1 = P::q1_cap(s);  // messages in flight per round, for THIS env class (0 = unsupported)
     // (shuffle_batches needs the per-receiver batch lists of the tile engine)
