@@ -245,7 +245,7 @@ def run_ours(args):
     # lean outputs like the rollout above; each launch moves 4.7 MB, so this leg is
     # launch/latency-bound and L2-resident by construction -- reported, not the headline
     single = None
-    if rank == 0:
+    if rank == 0 and not args.timed_only:
         a1, o1 = acts[0], outs[0]
         side = torch.cuda.Stream(dev)
 
@@ -282,6 +282,14 @@ def run_ours(args):
 
     # ---- e2e: same metric through the host-buffer C-ABI call (pinned host memory, H2D of
     # the actions and D2H of obs / reward / all_done inside the timed region)
+    if args.timed_only:  # profiling aid: only the device-timed region (see tools/profile_round.sh)
+        if rank == 0:
+            print(json.dumps({"timed_only": True, "ms_per_step": ms / args.steps,
+                              "gpu_launches": args.steps}), flush=True)
+        env.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
     e2e_steps = max(3, min(args.steps, 12))
     h_act = torch.empty((T, E, 1, 1), dtype=torch.float32).pin_memory()
     h_act.copy_(acts[0].cpu())
@@ -398,6 +406,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=8.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--timed-only", action="store_true",
+                    help="profiling aid: run only the warm-up and the device-timed launches")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -10,7 +10,7 @@ mkdir -p $out
 python bench.py > $out/bench_${tag}.json 2> $out/bench_${tag}.err
 tail -c 3000 $out/bench_${tag}.json
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
-    --log-file $out/launches_${tag}.csv python bench.py --steps 20 --warmup 3 --no-cpu-baseline \
+    --log-file $out/launches_${tag}.csv python bench.py --steps 20 --warmup 3 --timed-only \
     > $out/bench_under_ncu_${tag}.log 2>&1
 full="ncu --set full --clock-control none --import-source on -f"
 $full -k regex:sc_fast -s 6 -c 1 -o $out/prof_sc_fast_${tag} \
