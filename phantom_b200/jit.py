@@ -61,7 +61,13 @@ def source(env) -> str:
 def compile_unit(text: str, cache: Optional[str] = None) -> str:
     """text -> path of the cubin (compiled once per distinct text / source tree / nvcc)."""
     cache = cache or CACHE
-    os.makedirs(cache, exist_ok=True)
+    try:
+        os.makedirs(cache, exist_ok=True)
+        if not os.access(cache, os.W_OK):
+            raise OSError("not writable")
+    except OSError:  # read-only install: fall back to a per-user scratch directory
+        cache = os.path.join(tempfile.gettempdir(), f"phx_jit_{os.getuid()}")
+        os.makedirs(cache, exist_ok=True)
     nvcc = _nvcc()
     key = hashlib.sha256(text.encode() + _tree_digest() + nvcc.encode()).hexdigest()[:24]
     cubin = os.path.join(cache, key + ".cubin")
