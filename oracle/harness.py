@@ -250,7 +250,8 @@ def run_generic(env, clock: EpisodeClock, actions: np.ndarray, action_mask: np.n
                 ep_states.append(state_fn(env))
             if track:
                 for k, m in enumerate(env.network.resolver.tracked_messages):
-                    vals = [int(v) for v in m.payload.__dict__.values()][:2] + [0, 0]
+                    conv = float if track == "raw" else int  # "raw": keep float payload fields
+                    vals = [conv(v) for v in m.payload.__dict__.values()][:2] + [0, 0]
                     msgs.append((ep, t, slot_of[m.sender_id], slot_of[m.receiver_id],
                                  type(m.payload).__name__, vals[0], vals[1]))
         if state_fn is not None:

@@ -281,11 +281,19 @@ def gen_simple_market_reference() -> None:
             with wl.contract_rng(coords, {f"b{i + 1}": i for i in range(len(buyers))}):
                 env, _ = wl.build_reference(buyers, n_sellers, T)
                 clock = harness.EpisodeClock([coords])
+                env.network.resolver.enable_tracking = e < 2
                 tr = harness.run_generic(env, clock, actions[e], mask[e], wl.OBS_DIM,
-                                         state_fn=wl.state, convert=wl.to_action(env))
-            tr["messages"] = []
+                                         state_fn=wl.state, convert=wl.to_action(env),
+                                         track="raw" if e < 2 else False)
             per_env.append(tr)
+        rows = [(e, ep, t, s, r, {"Price": 0, "Order": 1}[name], v0)
+                for e in range(2) for (ep, t, s, r, name, v0, v1) in per_env[e]["messages"]]
+        for tr in per_env:
+            tr["messages"] = []
         out = pack_generic(per_env, actions, mask, seed, 0, {})
+        # Resolver.tracked_messages of envs 0 and 1: (env, episode, step, sender slot, receiver
+        # slot, type, value) with the float64 price / the order volume as the value
+        out["messages"] = np.asarray(rows, np.float64).reshape(-1, 7)
         out["buyers"] = np.array(buyers, np.float64)
         out["n_sellers"] = np.int64(n_sellers)
         np.savez_compressed(os.path.join(GOLDEN, name), **out)

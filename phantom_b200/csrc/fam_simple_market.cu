@@ -74,8 +74,6 @@ struct SimpleMarketProgram {
                 "simple-market family: obs_dim 3, act_dim 1, 2 payload types");
     PHX_REQUIRE(s.iparams[0] >= 1 && s.iparams[0] <= SM_MAX_SELLERS, PHX_ERR_UNSUPPORTED,
                 "simple-market family: 1..7 sellers");
-    PHX_REQUIRE(!(s.flags & PHX_FLAG_TRACK_MESSAGES), PHX_ERR_UNSUPPORTED,
-                "simple-market family: message tracking is not built (float64 payloads)");
     return PHX_OK;
   }
 

@@ -490,8 +490,11 @@ class PhantomEnv:
             sender, recv, ptype = r[0] & 0xFF, (r[0] >> 8) & 0xFF, (r[0] >> 16) & 0xFF
             cls = info.payload_types[ptype]
             names = [f.name for f in __import__("dataclasses").fields(cls)]
-            vals = [int(r[1]), int(r[2])][: len(names)]
-            msgs.append(Message(ids[sender], ids[recv], cls(*vals)))
+            if hasattr(cls, "_phx_decode"):  # payloads that are not plain int fields
+                payload = cls._phx_decode(int(r[1]), int(r[2]))
+            else:
+                payload = cls(*[int(r[1]), int(r[2])][: len(names)])
+            msgs.append(Message(ids[sender], ids[recv], payload))
         return msgs
 
     def is_terminated(self) -> bool:

@@ -28,6 +28,12 @@ MAX_SELLERS = 7
 class Price:
     price: float
 
+    @classmethod
+    def _phx_decode(cls, lo: int, hi: int) -> "Price":
+        """the device payload is the float64 price, low / high word"""
+        bits = (np.uint64(hi & 0xFFFFFFFF) << np.uint64(32)) | np.uint64(lo & 0xFFFFFFFF)
+        return cls(float(np.array([bits], np.uint64).view(np.float64)[0]))
+
 
 @ph.msg_payload()
 class Order:
@@ -151,7 +157,7 @@ FAMILY = register(FamilyInfo(
     act_dim=1,
     env_kinds=(L.ENV_FSM,),
     collect=_collect,
-    trace_capacity=lambda env, agents: 0,
+    trace_capacity=lambda env, agents: len(agents) * len(agents),
     supports_supertypes=True,
 ))
 
@@ -192,7 +198,7 @@ class SimpleMarketEnv(ph.FiniteStateMachineEnv):
 
 
 def example_env(buyers=((0.2, 0.2, 0.2), (0.9, 1.0, 1.0), (0.9, 0.5, 0.5)), n_sellers: int = 2,
-                num_steps: int = 10, **batch_kwargs) -> SimpleMarketEnv:
+                num_steps: int = 10, enable_tracking: bool = False, **batch_kwargs) -> SimpleMarketEnv:
     """The cast of example_simple_market.py:9-30; buyers = (demand_prob, value low, value high)."""
     from phantom_b200.utils.samplers import UniformFloatSampler
 
@@ -201,6 +207,6 @@ def example_env(buyers=((0.2, 0.2, 0.2), (0.9, 1.0, 1.0), (0.9, 0.5, 0.5)), n_se
     agents = [BuyerAgent(b, p, supertype=BuyerSupertype(UniformFloatSampler(lo, hi)))
               for b, (p, lo, hi) in zip(buyer_ids, buyers)]
     agents += [SellerAgent(s) for s in seller_ids]
-    network = ph.Network(agents)
+    network = ph.Network(agents, ph.resolvers.BatchResolver(enable_tracking=enable_tracking))
     network.add_connections_between(buyer_ids, seller_ids)
     return SimpleMarketEnv(num_steps=num_steps, network=network, **batch_kwargs)

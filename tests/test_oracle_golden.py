@@ -322,9 +322,16 @@ def test_object_oracle_matches_simple_market_golden(golden_dir, name):
         coords = sm.Coords(seed, e)
         with sm.contract_rng(coords, {f"b{i + 1}": i for i in range(len(buyers))}):
             env, _ = sm.build(po, po.utils.samplers.UniformFloatSampler, buyers, n_sellers, T)
+            env.network.resolver.enable_tracking = e < 2
             tr = harness.run_generic(env, harness.EpisodeClock([coords]), A[e], M[e], sm.OBS_DIM,
-                                     state_fn=sm.state, convert=sm.to_action(env))
+                                     state_fn=sm.state, convert=sm.to_action(env),
+                                     track="raw" if e < 2 else False)
         assert_oracle_trace_equal(tr, g, e)
+        if e < 2:  # Resolver.tracked_messages: global order, float64 prices
+            slot_rows = [(ep, t, s, r, {"Price": 0, "Order": 1}[name], v0)
+                         for (ep, t, s, r, name, v0, v1) in tr["messages"]]
+            gm = g["messages"]
+            assert np.array_equal(np.asarray(slot_rows, np.float64), gm[gm[:, 0] == e][:, 1:])
     # the fixture exercises what it is meant to: ties between sellers, withheld buyer actions,
     # None rewards at the first buyer observation, and a moving avg_price in the sellers' obs
     assert (g["reward_mask"] == 2).any() and (M == 0).any()
