@@ -52,6 +52,12 @@ struct SimpleMarketProgram {
   static constexpr int PW = 2, NWORDS = 19, VW = 0, ACTCAP = 32, RESPCAP = 1, OBS_DIM = 3,
                        ACT_DIM = 1, Q1CAP = 16, ENVW = 2;
   static constexpr int RECVCAP = 32;
+  // compact acting queue (phx_engine.cuh): a seller prices its neighbours, a buyer sends at most
+  // one order -- 7 sellers x 25 buyers + 25 = 200 entries for a 32-agent market
+  static constexpr int ACTTOTAL = 256;
+  __host__ __device__ static int act_cap(int kind, int out_degree) {
+    return kind == 1 /* SM_SELLER */ ? out_degree : 1;
+  }
   static constexpr bool BATCHED = false, HAS_PRE = false, HAS_POST = false;
 
   // thread-per-env engine: messages in flight in one round = the largest acting-phase fan-out
