@@ -113,6 +113,14 @@ def main():
          5, 3, 100, 65536, 2 * (16 + 8 + 19 * 8 * 4 + 8 * 4 + 8 * 12 + 8 + 8), 0, False),
         ("X-simple-market-thread-jit", lambda **k: sm.example_env(num_steps=10, exec_mode="thread", **k),
          5, 3, 100, 65536, 2 * (16 + 8 + 19 * 8 * 4 + 8 * 4 + 8 * 12 + 8 + 8), 0, False),
+        # a 32-agent market (7 sellers + 25 buyers; SURVEY 6 probed the reference at ~1.5 k
+        # env-steps/s per core on 8 + 24): lane-per-agent tiling, compact acting queue
+        ("X-simple-market-32", lambda **k: sm.example_env(
+            tuple((0.5, 0.1, 0.9) for _ in range(25)), 7, 10, **k),
+         32, 3, 50, 32768, 2 * (16 + 8 + 19 * 32 * 4 + 32 * 4 + 32 * 12 + 8 + 8), 0, False),
+        ("X-simple-market-32-jit", lambda **k: sm.example_env(
+            tuple((0.5, 0.1, 0.9) for _ in range(25)), 7, 10, **k),
+         32, 3, 50, 32768, 2 * (16 + 8 + 19 * 32 * 4 + 32 * 4 + 32 * 12 + 8 + 8), 0, False),
         ("X-simple-market-queue", lambda **k: sm.example_env(num_steps=10, exec_mode="queue", **k),
          5, 3, 100, 65536, 2 * (16 + 8 + 19 * 8 * 4 + 8 * 4 + 8 * 12 + 8 + 8), 0, False),
     ]
