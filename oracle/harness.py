@@ -181,7 +181,7 @@ def run_supply_chain(env, clock: EpisodeClock, actions: np.ndarray,
 
 def run_generic(env, clock: EpisodeClock, actions: np.ndarray, action_mask: np.ndarray,
                 obs_dim: int, track: bool = False, state_fn=None,
-                convert=None) -> Dict[str, np.ndarray]:
+                convert=None, flatten=None) -> Dict[str, np.ndarray]:
     """Run actions.shape[0] episodes x actions.shape[1] steps of ANY env built with the
     plugin API and record the tensors of the C-ABI layout.
 
@@ -214,7 +214,8 @@ def run_generic(env, clock: EpisodeClock, actions: np.ndarray, action_mask: np.n
     def put_obs(dst, dmask, obs):
         for s, aid in enumerate(ids):
             if aid in obs:
-                v = np.asarray(obs[aid], np.float32).reshape(-1)
+                v = (flatten(obs[aid]) if flatten is not None
+                     else np.asarray(obs[aid], np.float32).reshape(-1))
                 dst[s, : v.size] = v
                 dmask[s] = 1
 

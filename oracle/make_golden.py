@@ -300,6 +300,38 @@ def gen_simple_market_reference() -> None:
         print(name, {k: v.shape for k, v in out.items()})
 
 
+def gen_digital_ads_reference() -> None:
+    """The reference's examples/environments/digital_ads_market/digital_ads_market.py, UNMODIFIED
+    (oracle/workloads/digital_ads.py:build_reference), under the contract RNG:
+      digital_ads_reference.npz       2 + 2 + 2 advertisers, first-price auction (8 agents)
+      digital_ads_wide_reference.npz  10 + 10 + 10 advertisers, second-price auction (32 agents)"""
+    from .workloads import digital_ads as wl
+
+    for name, per_theme, strategy, n_env, n_ep, seed in (
+            ("digital_ads_reference.npz", 2, "first", 8, 2, 20261026),
+            ("digital_ads_wide_reference.npz", 10, "second", 3, 2, 20261027)):
+        theme = {"travel": per_theme, "tech": per_theme, "sport": per_theme}
+        budgets = ([(5.0, 15.001, 5.0, 15.0)] * per_theme + [(7.0, 17.001, 7.0, 17.0)] * per_theme +
+                   [(10.0, 20.001, 10.0, 20.0)] * per_theme)
+        S, T = 3 * per_theme, 20
+        actions, mask = wl.actions_for(n_env, n_ep, T, S, seed % 1000)
+        per_env = []
+        for e in range(n_env):
+            coords = wl.Coords(seed, e)
+            with wl.contract_rng(coords):
+                env = wl.build_reference(theme, budgets, T, strategy)
+                tr = harness.run_generic(env, harness.EpisodeClock([coords]), actions[e], mask[e],
+                                         wl.OBS_DIM, state_fn=wl.state, flatten=wl.flatten_obs)
+            tr["messages"] = []
+            per_env.append(tr)
+        out = pack_generic(per_env, actions, mask, seed, 0, {})
+        out["per_theme"], out["budgets"] = np.int64(per_theme), np.array(budgets, np.float64)
+        out["second_price"] = np.int64(strategy == "second")
+        np.savez_compressed(os.path.join(GOLDEN, name), **out)
+        print(name, {k: v.shape for k, v in out.items()}, "terminated:",
+              int((out["term"] == 1).sum()), "clicks:", float(out["reward"].sum()))
+
+
 def main() -> int:
     if not ref_shim.reference_available():
         print("reference not available")
@@ -312,6 +344,7 @@ def main() -> int:
     gen_supply_chain2_reference()
     gen_shuffle_and_stochastic_reference()
     gen_simple_market_reference()
+    gen_digital_ads_reference()
     return 0
 
 
