@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PHX_ABI_VERSION 2
+#define PHX_ABI_VERSION 3
 
 #define PHX_MAX_AGENTS 128  /* agent slots per env                                   */
 #define PHX_MAX_TYPES 16    /* payload types per env class                           */
@@ -80,6 +80,8 @@ typedef enum phx_family {
   PHX_FAMILY_DENSE = 5,        /* dense-graph broadcast + batch aggregation (C5)      */
   PHX_FAMILY_SIMPLE_MARKET = 7,/* examples/environments/simple_market/ (2-stage FSM, env-level
                                   post_message_resolution + custom EnvView field)         */
+  PHX_FAMILY_DIGITAL_ADS = 8,  /* examples/environments/digital_ads_market/ (auction in a
+                                  handle_batch override, three response rounds)           */
   PHX_FAMILY_SUPPLY_CHAIN2 = 6 /* multi-shop supply chain with agent supertypes
                                   (docs/user/tutorial2.rst)                           */
 } phx_family;
@@ -154,7 +156,7 @@ typedef struct phx_spec {
   double fparams[PHX_MAX_PARAMS];
   int32_t agent_iparam[PHX_MAX_AGENTS][4]; /* per-slot family parameters, e.g. the slot
                                               of the peer an agent addresses           */
-  double agent_fparam[PHX_MAX_AGENTS][2];
+  double agent_fparam[PHX_MAX_AGENTS][4];
   /* Encoder composition (phantom/encoders.py:64-131) lowered to a per-agent op list:
    * op = opcode | length << 8 (opcode 0 constant, 1 proportion_time_elapsed, 2 current_step),
    * evaluated in order into the agent's obs row; 0 terminates the list. */

@@ -21,7 +21,7 @@ PHX_MAX_PARAMS = 16
 PHX_TRACE_WORDS = 4
 PHX_MAX_CODEC_OPS = 6
 PHX_MAX_BASE_CONNECTIONS = 528
-PHX_ABI_VERSION = 2
+PHX_ABI_VERSION = 3
 
 # phx_status
 PHX_OK, PHX_ERR_INVALID, PHX_ERR_CUDA, PHX_ERR_UNSUPPORTED, PHX_ERR_NO_DEVICE = 0, -1, -2, -3, -4
@@ -34,6 +34,7 @@ ENV_BASE, ENV_FSM, ENV_STACKELBERG = 0, 1, 2
 FAMILY_SUPPLY_CHAIN, FAMILY_MOCK, FAMILY_MARKET, FAMILY_STACKELBERG, FAMILY_DENSE = 1, 2, 3, 4, 5
 FAMILY_SUPPLY_CHAIN2 = 6
 FAMILY_SIMPLE_MARKET = 7
+FAMILY_DIGITAL_ADS = 8
 # phx_exec_mode
 EXEC_AUTO, EXEC_QUEUE, EXEC_FAST, EXEC_THREAD = 0, 1, 2, 3
 EXEC_MODES = {"auto": EXEC_AUTO, "queue": EXEC_QUEUE, "fast": EXEC_FAST, "thread": EXEC_THREAD}
@@ -88,7 +89,7 @@ class PhxSpec(C.Structure):
         ("iparams", C.c_int32 * PHX_MAX_PARAMS),
         ("fparams", C.c_double * PHX_MAX_PARAMS),
         ("agent_iparam", (C.c_int32 * 4) * PHX_MAX_AGENTS),
-        ("agent_fparam", (C.c_double * 2) * PHX_MAX_AGENTS),
+        ("agent_fparam", (C.c_double * 4) * PHX_MAX_AGENTS),
         ("agent_codec_op", (C.c_int32 * PHX_MAX_CODEC_OPS) * PHX_MAX_AGENTS),
         ("agent_codec_val", (C.c_float * PHX_MAX_CODEC_OPS) * PHX_MAX_AGENTS),
         ("n_base_connections", C.c_int32),

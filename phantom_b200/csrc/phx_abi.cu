@@ -212,6 +212,9 @@ int32_t phx_create(const phx_spec* spec, int32_t num_envs, int32_t device, uint6
     case PHX_FAMILY_SIMPLE_MARKET:
       fam = phx::make_simple_market_family(*spec);
       break;
+    case PHX_FAMILY_DIGITAL_ADS:
+      fam = phx::make_digital_ads_family(*spec);
+      break;
     default:
       set_error("no device program for family " + std::to_string(spec->family));
       return PHX_ERR_UNSUPPORTED;

@@ -83,7 +83,7 @@ struct EngineSpec {
   float fparams[PHX_MAX_PARAMS];
   double dparams[4];                   // family parameters that must stay float64
   int32_t agent_iparam[ENGINE_MAX_AGENTS][4];
-  double agent_fparam[ENGINE_MAX_AGENTS][2];
+  double agent_fparam[ENGINE_MAX_AGENTS][4];
   int32_t codec_op[ENGINE_MAX_AGENTS][PHX_MAX_CODEC_OPS];  // opcode | length << 8
   float codec_val[ENGINE_MAX_AGENTS][PHX_MAX_CODEC_OPS];
 };

@@ -43,12 +43,14 @@ class UniformFloatSampler(ComparableSampler[float]):
 
     def __init__(self, low: float = 0.0, high: float = 1.0, clip_low=None, clip_high=None) -> None:
         assert high >= low
-        if clip_low is not None or clip_high is not None:
-            raise NotLowerableError("UniformFloatSampler clipping is not lowered to the device")
         self.low, self.high, self.clip_low, self.clip_high = low, high, clip_low, clip_high
         super().__init__()
 
-    def device_desc(self):
+    def device_desc(self, allow_clip: bool = False):
+        """(kind, low, high); families that implement np.clip on the device (samplers.py:144-145)
+        pass allow_clip and read clip_low / clip_high themselves."""
+        if not allow_clip and (self.clip_low is not None or self.clip_high is not None):
+            raise NotLowerableError("this family does not lower UniformFloatSampler clipping")
         return (KIND_UNIFORM_FLOAT, float(self.low), float(self.high))
 
 
