@@ -75,6 +75,18 @@ def measure(name, make_env, S, O, T, E, b_state, steps, binary_from=None, lean=F
     env.close()
 
 
+def _ads_env(per_theme, **k):
+    from phantom_b200.envs import digital_ads_market as da
+    from phantom_b200.utils.samplers import UniformFloatSampler as U
+
+    b = ([(5.0, 15.001, 5.0, 15.0)] * per_theme + [(7.0, 17.001, 7.0, 17.0)] * per_theme +
+         [(10.0, 20.001, 10.0, 20.0)] * per_theme)
+    st = {f"ADV_{i + 1}": da.AdvertiserAgent.Supertype(budget=U(*x)) for i, x in enumerate(b)}
+    return da.DigitalAdsEnv(num_steps=20, num_agents_theme={"travel": per_theme, "tech": per_theme,
+                                                            "sport": per_theme},
+                            agent_supertypes=st, **k)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=20)
@@ -121,6 +133,14 @@ def main():
         ("X-simple-market-32-jit", lambda **k: sm.example_env(
             tuple((0.5, 0.1, 0.9) for _ in range(25)), 7, 10, **k),
          32, 3, 50, 32768, 2 * (16 + 8 + 19 * 32 * 4 + 32 * 4 + 32 * 12 + 8 + 8), 0, False),
+        # the reference's digital_ads_market example, 10 + 10 + 10 advertisers (SURVEY 6 probed the
+        # reference at ~650 env-steps/s per core on 122 agents)
+        ("X-digital-ads-32", lambda **k: _ads_env(10, **k), 30, 3, 40, 32768,
+         2 * (16 + 8 + 15 * 32 * 4 + 32 * 4 + 32 * 12 + 8 + 32 * 4), None, False),
+        ("X-digital-ads-8-thread", lambda **k: _ads_env(2, exec_mode="thread", **k), 6, 3, 100, 65536,
+         2 * (16 + 8 + 15 * 8 * 4 + 8 * 4 + 8 * 12 + 8 + 8 * 4), None, False),
+        ("X-digital-ads-8-thread-jit", lambda **k: _ads_env(2, exec_mode="thread", **k), 6, 3, 100, 65536,
+         2 * (16 + 8 + 15 * 8 * 4 + 8 * 4 + 8 * 12 + 8 + 8 * 4), None, False),
         ("X-simple-market-queue", lambda **k: sm.example_env(num_steps=10, exec_mode="queue", **k),
          5, 3, 100, 65536, 2 * (16 + 8 + 19 * 8 * 4 + 8 * 4 + 8 * 12 + 8 + 8), 0, False),
     ]
