@@ -15,6 +15,8 @@ Reference lines followed (all under /root/reference/phantom/):
 from __future__ import annotations
 
 import dataclasses
+
+import numpy as np
 from abc import ABC, abstractmethod
 from typing import Any, Dict, Generic, Hashable, List, Optional, Sequence, Tuple, TypeVar
 
@@ -172,6 +174,26 @@ class Supertype(ABC):
                 v = v.value if hasattr(self, "_managed") else v.sample()
             out[name] = v
         return self.__class__(**out)
+
+    def to_obs_space_compatible_type(self):
+        """supertype.py:32-41,64-85: fields as observation-space compatible values (numbers
+        become float32 arrays of shape (1,))."""
+
+        def conv(name, obj):
+            if isinstance(obj, dict):
+                return {k: conv(k, v) for k, v in obj.items()}
+            if isinstance(obj, (float, int)):
+                return np.array([obj], dtype=np.float32)
+            if isinstance(obj, list):
+                return [conv(f"{name}[{i}]", v) for i, v in enumerate(obj)]
+            if isinstance(obj, tuple):
+                return tuple(conv(f"{name}[{i}]", v) for i, v in enumerate(obj))
+            if isinstance(obj, np.ndarray):
+                return obj
+            raise ValueError(
+                f"Can't encode field '{name}' with type '{type(obj)}' into obs space compatible type")
+
+        return {name: conv(name, getattr(self, name)) for name in self.__dataclass_fields__}
 
 
 # ----------------------------------------------------------------------------- agents

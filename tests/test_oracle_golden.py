@@ -336,3 +336,61 @@ def test_object_oracle_matches_simple_market_golden(golden_dir, name):
     # None rewards at the first buyer observation, and a moving avg_price in the sellers' obs
     assert (g["reward_mask"] == 2).any() and (M == 0).any()
     assert len(np.unique(g["state"][..., -1, 0])) > 10
+
+
+@pytest.mark.parametrize("name", ["digital_ads_reference.npz", "digital_ads_wide_reference.npz"])
+def test_oracle_port_runs_the_digital_ads_example(golden_dir, name):
+    """The UNMODIFIED example file executed on the oracle port (its `import phantom` bound to
+    oracle.phantom_oracle) reproduces the fixture the same file produced on the reference: pins
+    the port's StochasticNetwork, FSM caches, handle_batch override dispatch, done-agent dropout
+    and env-managed clipped samplers.  Needs the example source, i.e. the build container."""
+    import importlib.util
+    import sys
+
+    from oracle import ref_shim
+    from oracle.workloads import digital_ads as wl
+
+    from .generic_parity import assert_oracle_trace_equal
+
+    path = os.path.join(ref_shim.REFERENCE_ROOT,
+                        "examples/environments/digital_ads_market/digital_ads_market.py")
+    if not os.path.exists(path):
+        pytest.skip("reference examples are only available in the build container")
+    ref_shim.install(with_reference=False)  # gymnasium & co stubs only
+    import types
+    import typing
+
+    # the file also defines metric classes at module level (:594-684, not on the step path): give
+    # the port's namespace the two names they derive from
+    port = types.ModuleType("phantom")
+    port.__dict__.update(po.__dict__)
+    T = typing.TypeVar("T")
+    class Metric(typing.Generic[T]):
+        pass
+
+    port.metrics = types.SimpleNamespace(Metric=Metric, SimpleAgentMetric=lambda *a, **k: None)
+    saved = {k: sys.modules.get(k) for k in ("phantom",)}
+    sys.modules["phantom"] = port
+    try:
+        spec = importlib.util.spec_from_file_location("_port_digital_ads", path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    g = np.load(os.path.join(golden_dir, name))
+    seed, A, M, per_theme = int(g["seed"]), g["actions"], g["action_mask"], int(g["per_theme"])
+    theme = {"travel": per_theme, "tech": per_theme, "sport": per_theme}
+    for e in range(min(A.shape[0], 4)):
+        coords = wl.Coords(seed, e)
+        with wl.contract_rng(coords):
+            st = {f"ADV_{i + 1}": mod.AdvertiserAgent.Supertype(
+                budget=po.utils.samplers.UniformFloatSampler(*b)) for i, b in enumerate(g["budgets"])}
+            env = mod.DigitalAdsEnv(num_steps=A.shape[2], num_agents_theme=theme, agent_supertypes=st)
+            env.agents["ADX"].strategy = "second" if int(g["second_price"]) else "first"
+            tr = harness.run_generic(env, harness.EpisodeClock([coords]), A[e], M[e], wl.OBS_DIM,
+                                     state_fn=wl.state, flatten=wl.flatten_obs)
+        assert_oracle_trace_equal(tr, g, e)
