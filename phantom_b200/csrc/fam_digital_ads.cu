@@ -48,6 +48,11 @@ struct DigitalAdsProgram {
                        ACT_DIM = 1, Q1CAP = 8;
   static constexpr int RECVCAP = 32;
   static constexpr bool BATCHED = true, HAS_PRE = true, HAS_POST = false;
+  // compact response queues: only the exchange answers a round with many messages (one per
+  // agent at most: the forwarded impression, or Ads + one AuctionResult per bidder); the
+  // publisher answers with one ImpressionResult, an advertiser never answers
+  static constexpr int RESPTOTAL = 96;
+  __host__ __device__ static int resp_cap(int kind, int) { return kind == 0 /* exchange */ ? 32 : 1; }
 
   static int q1_cap(const phx_spec& s) { return s.n_agents; }
 

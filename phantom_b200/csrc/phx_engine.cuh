@@ -175,6 +175,22 @@ struct HasActTotal : std::false_type {};
 template <class P>
 struct HasActTotal<P, std::void_t<decltype(P::ACTTOTAL)>> : std::true_type {};
 
+// ... and into compact RESPONSE queues with RESPTOTAL / resp_cap (an exchange that answers a
+// round with 31 messages next to 31 agents that answer with at most one).
+template <class P, class = void>
+struct HasRespTotal : std::false_type {};
+template <class P>
+struct HasRespTotal<P, std::void_t<decltype(P::RESPTOTAL)>> : std::true_type {};
+
+template <class P, int G, bool COMPACT = HasRespTotal<P>::value>
+struct RespQueueOf {
+  using type = TileQueue<G, P::RESPCAP, P::PW>;
+};
+template <class P, int G>
+struct RespQueueOf<P, G, true> {
+  using type = CompactQueue<G, P::RESPTOTAL, P::PW>;
+};
+
 template <class P, int G, bool COMPACT = HasActTotal<P>::value>
 struct ActQueueOf {
   using type = TileQueue<G, P::ACTCAP, P::PW>;
@@ -274,7 +290,7 @@ __device__ __forceinline__ uint32_t tile_mask(int G) {
 template <class P, int G>
 struct TileSmem {
   typename ActQueueOf<P, G>::type qa;
-  TileQueue<G, P::RESPCAP, P::PW> qr[2];
+  typename RespQueueOf<P, G>::type qr[2];
   int32_t views[G][P::VW > 0 ? P::VW : 1];
   int32_t first_idx[G];
   uint16_t sorted[G][P::RECVCAP];  // per receiver: its batch as (segment | entry << 8), push order
@@ -567,6 +583,17 @@ __device__ __forceinline__ void engine_step_body(const EngineArgs<P>& a) {
     }
     ts.qa.base[slot + 1] = (uint16_t)incl;
     if (slot == 0) ts.qa.base[0] = 0;
+    __syncwarp(tmask);
+  }
+  if constexpr (HasRespTotal<P>::value) {  // the same for the two response queues
+    int incl = slot < sp.n_agents ? min(P::RESPCAP, P::resp_cap(kind, __popc(sp.adj[slot]))) : 0;
+#pragma unroll
+    for (int off = 1; off < G; off <<= 1) {
+      const int v = __shfl_up_sync(tmask, incl, off, G);
+      if (slot >= off) incl += v;
+    }
+    ts.qr[0].base[slot + 1] = ts.qr[1].base[slot + 1] = (uint16_t)incl;
+    if (slot == 0) ts.qr[0].base[0] = ts.qr[1].base[0] = 0;
     __syncwarp(tmask);
   }
   const uint32_t slot_bit = 1u << slot;

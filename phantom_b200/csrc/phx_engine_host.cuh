@@ -172,6 +172,16 @@ class EngineFamily : public Family {
       PHX_REQUIRE(total <= P::ACTTOTAL, PHX_ERR_UNSUPPORTED,
                   "acting-phase fan-out of this env class exceeds the family's queue");
     }
+    if constexpr (HasRespTotal<P>::value) {  // compact response queues, sized from the full graph
+      int total = 0;
+      for (int i = 0; i < s.n_agents; ++i) {
+        int deg = 0;
+        for (int r = 0; r < s.n_agents; ++r) deg += mask_bit(s.adjacency[i], r);
+        total += std::min((int)P::RESPCAP, P::resp_cap(s.agent_kind[i], deg));
+      }
+      PHX_REQUIRE(total <= P::RESPTOTAL, PHX_ERR_UNSUPPORTED,
+                  "response fan-out of this env class exceeds the family's queue");
+    }
     // thread-per-env variant: <= 8 agents and a program that declares its queue bound
     qcap1 = P::q1_cap(s);  // messages in flight per round, for THIS env class (0 = unsupported)
     // (shuffle_batches needs the per-receiver batch lists of the tile engine)
