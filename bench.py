@@ -193,6 +193,21 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # keep each rank (and the pinned host buffers it first-touches) on the CPUs next to its
+        # GPU: with several ranks per box the host side of the e2e copies is NUMA-sensitive
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(local)
+            words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+            cpus = {64 * w + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1}
+            cpus &= set(os.sched_getaffinity(0))
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+        except Exception:
+            pass
+    if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
     E, T = E_PER_GPU, T_EPISODE
