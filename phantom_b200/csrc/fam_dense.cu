@@ -158,6 +158,24 @@ __global__ void __launch_bounds__(DN_MAX) dense_step_kernel(const DenseArgs a) {
         const uint32_t m = adj[w] & sm.sent[w];  // symmetric graph: senders with an edge to me
         if (TRACK && first_sender < 0 && m) first_sender = w * 32 + __ffs(m) - 1;
         if (m == 0u) continue;
+        if (m == 0xFFFFFFFFu) {  // dense graphs: all 32 senders of this word, no per-bit tests
+#pragma unroll
+          for (int b4 = 0; b4 < 32; b4 += 4) {
+            const int4 q = *reinterpret_cast<const int4*>(&sm.vals[w * 32 + b4]);  // broadcast
+            const int qv[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int sdr = w * 32 + b4 + k;
+              const int v = qv[k] + tailtab[(2 * sdr) % 5];
+              total += v;
+              if (v > best) {
+                best = v;
+                best_s = sdr;
+              }
+            }
+          }
+          continue;
+        }
 #pragma unroll
         for (int b4 = 0; b4 < 32; b4 += 4) {
           const int4 q = *reinterpret_cast<const int4*>(&sm.vals[w * 32 + b4]);  // broadcast
