@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PHX_ABI_VERSION 3
+#define PHX_ABI_VERSION 4
 
 #define PHX_MAX_AGENTS 128  /* agent slots per env                                   */
 #define PHX_MAX_TYPES 16    /* payload types per env class                           */
@@ -59,8 +59,11 @@ typedef enum phx_fault {
   PHX_FAULT_ROUND_LIMIT = 4,      /* RuntimeError, phantom/resolvers.py:160-163        */
   PHX_FAULT_BAD_TRANSITION = 5,   /* FSMRuntimeError, phantom/fsm.py:304-307           */
   PHX_FAULT_QUEUE_OVERFLOW = 6,   /* engine capacity exceeded (no reference analogue)  */
-  PHX_FAULT_INVALID_ACTION = 7    /* non-finite / out-of-contract action value
+  PHX_FAULT_INVALID_ACTION = 7,   /* non-finite / out-of-contract action value
                                      (ValueError/OverflowError from int(round(a)))     */
+  PHX_FAULT_UNRESOLVED_MAIL = 8   /* a stage handler that does not call resolve_network()
+                                     left messages queued: the reference would carry them
+                                     into a later step's resolve; the device does not     */
 } phx_fault;
 
 /* Which step loop drives the env (phantom/env.py, fsm.py, stackelberg.py). */
@@ -107,17 +110,35 @@ enum {
                                                  phantom/resolvers.py:150-151              */
 };
 
+/* The device form of an FSM stage's env handler (phantom/fsm.py:294-307).  The reference calls an
+ * arbitrary Python function that may run self.resolve_network() and returns the next stage;
+ * the device evaluates the declarative equivalent
+ *     [self.resolve_network()]; return then_stage if <lhs> <cmp> rhs else else_stage
+ * after the stage's message resolution, on the env's state at that point. */
+typedef enum phx_rule_lhs {
+  PHX_RULE_ALWAYS = 0,     /* unconditional: returns then_stage                            */
+  PHX_RULE_STEP = 1,       /* env.current_step (already incremented, phantom/fsm.py:266)   */
+  PHX_RULE_AGENT_WORD = 2, /* int32 state word `word` of agent slot `slot`                 */
+  PHX_RULE_ENV_WORD = 3    /* int32 env-level word `word` (families with env-level state)  */
+} phx_rule_lhs;
+typedef enum phx_cmp { PHX_CMP_LT = 0, PHX_CMP_LE, PHX_CMP_EQ, PHX_CMP_NE, PHX_CMP_GE, PHX_CMP_GT } phx_cmp;
+
 typedef struct phx_stage {
   uint32_t acting[PHX_MASK_WORDS];   /* FSMStage.acting_agents as a slot bitmask         */
   uint32_t rewarded[PHX_MASK_WORDS]; /* FSMStage.rewarded_agents                         */
   int32_t rewarded_is_none;          /* rewarded_agents is None (phantom/fsm.py:315-317) */
   int32_t next_stage;                /* next_stages[0]: the next stage of a handler-less
                                         stage (phantom/fsm.py:284-292)                   */
-  int32_t handler;                   /* 0 = no env handler; > 0 = id of the family's device
-                                        stage handler (phantom/fsm.py:294-302)           */
+  int32_t handler;                   /* 0 = no env handler; 1 = the rule below
+                                        (phantom/fsm.py:294-302)                         */
   uint32_t next_allowed;             /* FSMStage.next_stages as a stage bitmask; a handler
                                         returning a stage outside it faults with
                                         PHX_FAULT_BAD_TRANSITION (phantom/fsm.py:304-307) */
+  int32_t rule_resolves;             /* the handler calls self.resolve_network() (a stage
+                                        WITH a handler is not resolved otherwise,
+                                        phantom/fsm.py:280-283)                          */
+  int32_t rule_lhs, rule_slot, rule_word, rule_cmp, rule_rhs; /* phx_rule_lhs, phx_cmp   */
+  int32_t rule_then, rule_else;      /* stage indices                                    */
 } phx_stage;
 
 /* Flat description of one env class, lowered from the Python objects

@@ -136,4 +136,25 @@ def build_classes(ph):
         return network
 
     ns.finish_network = finish_network
+
+    def stage_handler(then, lhs="always", cmp="==", rhs=0, otherwise=None, resolve_network=True):
+        """A Python env stage handler (reference: phantom/fsm.py:294-302) with the meaning of
+        phantom_b200.fsm.StageRule: [env.resolve_network()]; return then if lhs <cmp> rhs else
+        otherwise."""
+        import operator
+
+        op = {"<": operator.lt, "<=": operator.le, "==": operator.eq, "!=": operator.ne,
+              ">=": operator.ge, ">": operator.gt}[cmp]
+
+        def handler(env):
+            if resolve_network:
+                env.resolve_network()
+            if lhs == "always":
+                return then
+            value = env.current_step if lhs == "step" else getattr(env.agents[lhs[1]], lhs[2])
+            return then if op(value, rhs) else otherwise
+
+        return handler
+
+    ns.stage_handler = stage_handler
     return ns

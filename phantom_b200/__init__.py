@@ -18,7 +18,7 @@ from .encoders import Encoder
 from .env import BatchStep, PhantomEnv
 from .env_wrappers import SingleAgentEnvAdapter
 from .errors import DeviceOnlyError, NotLowerableError
-from .fsm import FiniteStateMachineEnv, FSMStage
+from .fsm import FiniteStateMachineEnv, FSMStage, StageRule
 from .message import Message, MsgPayload, msg_payload
 from .network import Network, NetworkError, StochasticNetwork
 from .policy import Policy

@@ -21,13 +21,16 @@ PHX_MAX_PARAMS = 16
 PHX_TRACE_WORDS = 4
 PHX_MAX_CODEC_OPS = 6
 PHX_MAX_BASE_CONNECTIONS = 528
-PHX_ABI_VERSION = 3
+PHX_ABI_VERSION = 4
 
 # phx_status
 PHX_OK, PHX_ERR_INVALID, PHX_ERR_CUDA, PHX_ERR_UNSUPPORTED, PHX_ERR_NO_DEVICE = 0, -1, -2, -3, -4
 # phx_fault
 (FAULT_NONE, FAULT_NO_EDGE, FAULT_BAD_PAYLOAD_TYPE, FAULT_UNKNOWN_MSG_TYPE, FAULT_ROUND_LIMIT,
- FAULT_BAD_TRANSITION, FAULT_QUEUE_OVERFLOW, FAULT_INVALID_ACTION) = range(8)
+ FAULT_BAD_TRANSITION, FAULT_QUEUE_OVERFLOW, FAULT_INVALID_ACTION, FAULT_UNRESOLVED_MAIL) = range(9)
+# phx_rule_lhs / phx_cmp (device form of an FSM stage handler)
+RULE_ALWAYS, RULE_STEP, RULE_AGENT_WORD, RULE_ENV_WORD = range(4)
+CMP_LT, CMP_LE, CMP_EQ, CMP_NE, CMP_GE, CMP_GT = range(6)
 # phx_env_kind
 ENV_BASE, ENV_FSM, ENV_STACKELBERG = 0, 1, 2
 # phx_family
@@ -58,6 +61,14 @@ class PhxStage(C.Structure):
         ("next_stage", C.c_int32),
         ("handler", C.c_int32),
         ("next_allowed", C.c_uint32),
+        ("rule_resolves", C.c_int32),
+        ("rule_lhs", C.c_int32),
+        ("rule_slot", C.c_int32),
+        ("rule_word", C.c_int32),
+        ("rule_cmp", C.c_int32),
+        ("rule_rhs", C.c_int32),
+        ("rule_then", C.c_int32),
+        ("rule_else", C.c_int32),
     ]
 
 

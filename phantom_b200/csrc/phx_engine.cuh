@@ -86,7 +86,29 @@ struct EngineSpec {
   double agent_fparam[ENGINE_MAX_AGENTS][4];
   int32_t codec_op[ENGINE_MAX_AGENTS][PHX_MAX_CODEC_OPS];  // opcode | length << 8
   float codec_val[ENGINE_MAX_AGENTS][PHX_MAX_CODEC_OPS];
+  // device form of the stages' env handlers (fsm.py:294-307; include/phx.h phx_stage.rule_*)
+  int8_t stage_rule[PHX_MAX_STAGES][8];  // {handler, resolves, lhs, cmp, slot, word, then, else}
+  int32_t stage_rule_rhs[PHX_MAX_STAGES];
+  uint8_t stage_allowed[PHX_MAX_STAGES];  // FSMStage.next_stages as a stage bitmask
 };
+
+enum { SR_HANDLER = 0, SR_RESOLVES, SR_LHS, SR_CMP, SR_SLOT, SR_WORD, SR_THEN, SR_ELSE };
+
+// `return then_stage if lhs <cmp> rhs else else_stage` of a stage handler.
+__device__ __forceinline__ int stage_rule_pick(const EngineSpec& sp, int stage, int lhs) {
+  const int rhs = sp.stage_rule_rhs[stage];
+  bool c = true;
+  switch (sp.stage_rule[stage][SR_CMP]) {
+    case PHX_CMP_LT: c = lhs < rhs; break;
+    case PHX_CMP_LE: c = lhs <= rhs; break;
+    case PHX_CMP_EQ: c = lhs == rhs; break;
+    case PHX_CMP_NE: c = lhs != rhs; break;
+    case PHX_CMP_GE: c = lhs >= rhs; break;
+    default: c = lhs > rhs; break;
+  }
+  if (sp.stage_rule[stage][SR_LHS] == PHX_RULE_ALWAYS) c = true;
+  return c ? sp.stage_rule[stage][SR_THEN] : sp.stage_rule[stage][SR_ELSE];
+}
 
 struct Msg {
   int sender, type;
@@ -687,9 +709,14 @@ __device__ __forceinline__ void engine_step_body(const EngineArgs<P>& a) {
     // ---- acting phase (env.py:320-336; fsm.py:276-277; stackelberg.py:133-140)
     uint32_t acting = 0xFFFFFFFFu, observing = sp.strategic_mask, rewarded = sp.strategic_mask;
     int next_stage = h.z;
+    // a stage WITH an env handler is resolved only if the handler does it (fsm.py:280-283), and
+    // its next stage is known only after that (fsm.py:294-302)
+    bool handled = false, resolves = true;
     if (sp.env_kind == PHX_ENV_FSM) {
       acting = sp.stage_acting[h.z];
       next_stage = sp.stage_next[h.z];
+      handled = sp.stage_rule[h.z][SR_HANDLER] != 0;
+      resolves = !handled || sp.stage_rule[h.z][SR_RESOLVES] != 0;
       if (!sp.stage_rewarded_none[h.z]) {  // fsm.py:315-320
         rewarded = sp.stage_rewarded[h.z];
         observing = sp.stage_acting[next_stage];
@@ -734,7 +761,11 @@ __device__ __forceinline__ void engine_step_body(const EngineArgs<P>& a) {
 
     // ---- pre_message_resolution for every live context, in agent order (env.py:170-173);
     // hooks only touch their own agent, so order across agents is immaterial
-    if (has_ctx) P::pre(ctx, st);
+    if (!resolves && pending > 0) {  // the mail would wait for a later step's resolve
+      fault_key = min(fault_key, (1u << 16) | (0xFFu << 8) | PHX_FAULT_UNRESOLVED_MAIL);
+      pending = 0;
+    }
+    if (has_ctx && resolves) P::pre(ctx, st);
 
     // ---- BatchResolver.resolve (resolvers.py:128-163)
     int k_batch = 0;  // batches this receiver has shuffled in this step (shuffle_batches only)
@@ -754,11 +785,40 @@ __device__ __forceinline__ void engine_step_body(const EngineArgs<P>& a) {
     if (trace_lane) a.trace.cnt[e] = traced;
 
     // ---- post_message_resolution (env.py:175-178), then the env class's own override
-    if (has_ctx) P::post(ctx, st);
-    if constexpr (EW > 0)
-      P::env_post(ctx, envw, [&](int s_, auto w_) {
-        return __shfl_sync(tmask, st[decltype(w_)::value], s_, G);
-      });
+    if (has_ctx && resolves) P::post(ctx, st);
+    if constexpr (EW > 0) {
+      if (resolves)  // uniform over the tile: the stage is an env-level word
+        P::env_post(ctx, envw, [&](int s_, auto w_) {
+          return __shfl_sync(tmask, st[decltype(w_)::value], s_, G);
+        });
+    }
+
+    // ---- the stage's env handler picks the next stage (fsm.py:294-307)
+    if (handled) {
+      const int lk = sp.stage_rule[h.z][SR_LHS];
+      int lhs = h.x;
+      if (lk == PHX_RULE_AGENT_WORD) {
+        const int rs = sp.stage_rule[h.z][SR_SLOT], rw = sp.stage_rule[h.z][SR_WORD];
+        int mine = 0;
+#pragma unroll
+        for (int w = 0; w < P::NWORDS; ++w)
+          if (w == rw) mine = st[w];
+        lhs = __shfl_sync(tmask, mine, rs, G);
+      } else if (lk == PHX_RULE_ENV_WORD) {
+        if constexpr (EW > 0) {
+          const int rw = sp.stage_rule[h.z][SR_WORD];
+#pragma unroll
+          for (int w = 0; w < EW; ++w)
+            if (w == rw) lhs = envw[w];
+        }
+      }
+      next_stage = stage_rule_pick(sp, h.z, lhs);
+      if (!((sp.stage_allowed[h.z] >> next_stage) & 1u)) {
+        fault_key = min(fault_key, (0xFFFEu << 16) | (0xFFu << 8) | PHX_FAULT_BAD_TRANSITION);
+        next_stage = h.z;
+      }
+      if (!sp.stage_rewarded_none[h.z]) observing = sp.stage_acting[next_stage];
+    }
 
     // ---- outputs for strategic agents (env.py:273-303; fsm.py:322-378;
     // stackelberg.py:149-194)

@@ -242,9 +242,14 @@ __device__ __forceinline__ void engine1_step_body(const EngineArgs<P>& a) {
     // ---- acting phase, agents in order (env.py:320-336; fsm.py:276-277; stackelberg.py:133-140)
     uint32_t acting = 0xFFFFFFFFu, observing = sp.strategic_mask, rewarded = sp.strategic_mask;
     int next_stage = h.z;
+    // a stage WITH an env handler is resolved only if the handler does it (fsm.py:280-283), and
+    // its next stage is known only after that (fsm.py:294-302)
+    bool handled = false, resolves = true;
     if (sp.env_kind == PHX_ENV_FSM) {
       acting = sp.stage_acting[h.z];
       next_stage = sp.stage_next[h.z];
+      handled = sp.stage_rule[h.z][SR_HANDLER] != 0;
+      resolves = !handled || sp.stage_rule[h.z][SR_RESOLVES] != 0;
       if (!sp.stage_rewarded_none[h.z]) {
         rewarded = sp.stage_rewarded[h.z];
         observing = sp.stage_acting[next_stage];
@@ -288,8 +293,13 @@ __device__ __forceinline__ void engine1_step_body(const EngineArgs<P>& a) {
               make_int4(QH(cur, i), QP(cur, i, 0), P::PW > 1 ? QP(cur, i, P::PW > 1 ? 1 : 0) : 0, 0);
     }
 
+    if (!resolves && n_cur > 0) {  // the mail would wait for a later step's resolve
+      if (!fault) fault = PHX_FAULT_UNRESOLVED_MAIL;
+      n_cur = 0;
+    }
+
     // ---- pre_message_resolution (env.py:170-173)
-    if (P::HAS_PRE)
+    if (P::HAS_PRE && resolves)
       PHX_AGENT_UNROLL
       for (int s = 0; s < n; ++s) {
       if ((done >> s) & 1u) continue;
@@ -347,7 +357,7 @@ __device__ __forceinline__ void engine1_step_body(const EngineArgs<P>& a) {
     if (TRACK && env_live) a.trace.cnt[e] = traced;
 
     // ---- post_message_resolution (env.py:175-178)
-    if (P::HAS_POST)
+    if (P::HAS_POST && resolves)
       PHX_AGENT_UNROLL
       for (int s = 0; s < n; ++s) {
       if ((done >> s) & 1u) continue;
@@ -356,8 +366,35 @@ __device__ __forceinline__ void engine1_step_body(const EngineArgs<P>& a) {
       P::post(ctx, st);
       store_state(s, st);
     }
-    if constexpr (EW > 0)  // the env class's own post_message_resolution override
-      P::env_post(ctx, envw, [&](int s_, auto w_) { return ST(decltype(w_)::value, s_); });
+    if constexpr (EW > 0) {  // the env class's own post_message_resolution override
+      if (resolves)
+        P::env_post(ctx, envw, [&](int s_, auto w_) { return ST(decltype(w_)::value, s_); });
+    }
+
+    // ---- the stage's env handler picks the next stage (fsm.py:294-307)
+    if (handled) {
+      const int lk = sp.stage_rule[h.z][SR_LHS];
+      int lhs = h.x;
+      if (lk == PHX_RULE_AGENT_WORD) {
+        const int rs = sp.stage_rule[h.z][SR_SLOT], rw = sp.stage_rule[h.z][SR_WORD];
+#pragma unroll
+        for (int w = 0; w < P::NWORDS; ++w)
+          if (w == rw) lhs = ST(w, rs);
+      } else if (lk == PHX_RULE_ENV_WORD) {
+        if constexpr (EW > 0) {
+          const int rw = sp.stage_rule[h.z][SR_WORD];
+#pragma unroll
+          for (int w = 0; w < EW; ++w)
+            if (w == rw) lhs = envw[w];
+        }
+      }
+      next_stage = stage_rule_pick(sp, h.z, lhs);
+      if (!((sp.stage_allowed[h.z] >> next_stage) & 1u)) {
+        if (!fault) fault = PHX_FAULT_BAD_TRANSITION;
+        next_stage = h.z;
+      }
+      if (!sp.stage_rewarded_none[h.z]) observing = sp.stage_acting[next_stage];
+    }
 
     // ---- outputs, strategic agents in order (env.py:273-303; fsm.py:322-378;
     // stackelberg.py:149-194).  Pass 1: callbacks + caches; pass 2 (needs the terminal flag): rows.

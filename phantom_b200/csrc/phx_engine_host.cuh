@@ -18,7 +18,7 @@ inline uint32_t low_mask(const uint32_t* words) { return words[0]; }
 
 // Lowers the generic part of phx_spec into the engine's kernel-parameter form.
 inline int32_t make_engine_spec(const phx_spec& s, int32_t E, uint64_t seed, int64_t env_offset,
-                                EngineSpec* out) {
+                                EngineSpec* out, int nwords, int envwords) {
   PHX_REQUIRE(s.n_agents <= ENGINE_MAX_AGENTS, PHX_ERR_UNSUPPORTED,
               "queue engine (tile variant) supports up to 32 agents per env");
   EngineSpec& d = *out;
@@ -55,9 +55,41 @@ inline int32_t make_engine_spec(const phx_spec& s, int32_t E, uint64_t seed, int
     d.stage_acting[k] = s.stages[k].acting[0];
     d.stage_rewarded[k] = s.stages[k].rewarded[0];
     d.stage_rewarded_none[k] = (uint8_t)(s.stages[k].rewarded_is_none != 0);
-    PHX_REQUIRE(s.stages[k].next_stage >= 0 && s.stages[k].next_stage < s.n_stages,
-                PHX_ERR_INVALID, "FSM stage has an invalid next_stage");
-    d.stage_next[k] = (int8_t)s.stages[k].next_stage;
+    const phx_stage& g = s.stages[k];
+    d.stage_allowed[k] = (uint8_t)(g.next_allowed & 0xFFu);
+    if (g.handler == 0) {
+      PHX_REQUIRE(g.next_stage >= 0 && g.next_stage < s.n_stages, PHX_ERR_INVALID,
+                  "FSM stage has an invalid next_stage");
+      d.stage_next[k] = (int8_t)g.next_stage;
+      continue;
+    }
+    // a stage with an env handler: the declarative rule (include/phx.h phx_stage.rule_*)
+    PHX_REQUIRE(g.handler == 1, PHX_ERR_UNSUPPORTED, "unknown FSM stage handler kind");
+    PHX_REQUIRE(g.rule_lhs >= PHX_RULE_ALWAYS && g.rule_lhs <= PHX_RULE_ENV_WORD &&
+                    g.rule_cmp >= PHX_CMP_LT && g.rule_cmp <= PHX_CMP_GT,
+                PHX_ERR_INVALID, "FSM stage rule: bad lhs / cmp");
+    // the RETURNED stage may be outside next_stages (a run-time FSMRuntimeError in the reference,
+    // fsm.py:304-307), but it must be a stage index the kernel can hold
+    PHX_REQUIRE(g.rule_then >= 0 && g.rule_then < PHX_MAX_STAGES && g.rule_else >= 0 &&
+                    g.rule_else < PHX_MAX_STAGES,
+                PHX_ERR_INVALID, "FSM stage rule: stage index out of range");
+    if (g.rule_lhs == PHX_RULE_AGENT_WORD)
+      PHX_REQUIRE(g.rule_slot >= 0 && g.rule_slot < s.n_agents && g.rule_word >= 0 &&
+                      g.rule_word < nwords,
+                  PHX_ERR_INVALID, "FSM stage rule: no such agent state word");
+    if (g.rule_lhs == PHX_RULE_ENV_WORD)
+      PHX_REQUIRE(g.rule_word >= 0 && g.rule_word < envwords, PHX_ERR_INVALID,
+                  "FSM stage rule: no such env-level word");
+    d.stage_next[k] = (int8_t)k;
+    d.stage_rule[k][SR_HANDLER] = 1;
+    d.stage_rule[k][SR_RESOLVES] = (int8_t)(g.rule_resolves != 0);
+    d.stage_rule[k][SR_LHS] = (int8_t)g.rule_lhs;
+    d.stage_rule[k][SR_CMP] = (int8_t)g.rule_cmp;
+    d.stage_rule[k][SR_SLOT] = (int8_t)g.rule_slot;
+    d.stage_rule[k][SR_WORD] = (int8_t)g.rule_word;
+    d.stage_rule[k][SR_THEN] = (int8_t)g.rule_then;
+    d.stage_rule[k][SR_ELSE] = (int8_t)g.rule_else;
+    d.stage_rule_rhs[k] = g.rule_rhs;
   }
   d.leaders = s.leaders[0];
   d.followers = s.followers[0];
@@ -126,6 +158,7 @@ inline std::string jit_spec_literal(const EngineSpec& d) {
   f(d.stage_acting); f(d.stage_rewarded); f(d.stage_rewarded_none); f(d.stage_next);
   f(d.leaders); f(d.followers); f(d.seed); f(d.env_offset); f(d.iparams); f(d.fparams);
   f(d.dparams); f(d.agent_iparam); f(d.agent_fparam); f(d.codec_op); f(d.codec_val);
+  f(d.stage_rule); f(d.stage_rule_rhs); f(d.stage_allowed);
   o += "}";
   return o;
 }
@@ -155,7 +188,7 @@ class EngineFamily : public Family {
   }
 
   int32_t init(const phx_spec& s) override {
-    int32_t rc = make_engine_spec(s, E, seed, env_offset, &espec);
+    int32_t rc = make_engine_spec(s, E, seed, env_offset, &espec, P::NWORDS, EnvWords<P>::value);
     if (rc != PHX_OK) return rc;
     rc = P::validate(s);
     if (rc != PHX_OK) return rc;

@@ -57,6 +57,9 @@ def _fault_exception(code: int, env_index: int) -> Exception:
             "FiniteStateMachineEnv attempted invalid transition." + where),
         L.FAULT_QUEUE_OVERFLOW: RuntimeError("device message queue capacity exceeded." + where),
         L.FAULT_INVALID_ACTION: ValueError("action is non-finite or outside the contract." + where),
+        L.FAULT_UNRESOLVED_MAIL: RuntimeError(
+            "an FSM stage handler left messages unresolved; the device does not carry mail "
+            "into a later step." + where),
     }.get(code, RuntimeError(f"device fault {code}{where}"))
 
 

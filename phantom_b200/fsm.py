@@ -2,7 +2,10 @@
 
 Host side: stage registration and the reference's validation errors.  The stage-gated step
 loop, the reward / observation caches and the transition run on the device
-(PHX_ENV_FSM); only handler-less (deterministic) stages lower.
+(PHX_ENV_FSM).  Handler-less (deterministic) stages lower as they are; a stage WITH an env
+handler (fsm.py:294-307) lowers when the handler is a `StageRule` -- the declarative form of
+`[self.resolve_network()]; return A if <state> <cmp> <const> else B`, evaluated on the device
+after the stage's message resolution.  An arbitrary Python handler raises NotLowerableError.
 """
 from __future__ import annotations
 
@@ -29,6 +32,44 @@ class FSMValidationError(Exception):
 
 class FSMRuntimeError(Exception):
     pass
+
+
+class StageRule:
+    """Device-lowerable env stage handler (reference: the `handler` of `FSMStage`,
+    phantom/fsm.py:33-63, called at fsm.py:294-302).
+
+    Stands for the Python handler ::
+
+        def handler(env):
+            if resolve_network: env.resolve_network()       # fsm.py:280-283: a stage with a
+            value = <lhs>                                   # handler is resolved only by it
+            return then if value <cmp> rhs else otherwise
+
+    lhs:  "always" | "step" (env.current_step) | ("agent", agent_id, column) where column is a
+          device_column attribute name of that agent's class or a state word index |
+          ("env", word) for families with env-level words.
+    cmp:  one of "<", "<=", "==", "!=", ">=", ">".
+    A returned stage outside the stage's `next_stages` faults the env with FSMRuntimeError
+    (fsm.py:304-307).  The object is callable only so that it can sit where the reference
+    expects a handler; calling it on the host raises DeviceOnlyError.
+    """
+
+    CMPS = ("<", "<=", "==", "!=", ">=", ">")
+
+    def __init__(self, then: StageID, lhs="always", cmp: str = "==", rhs: int = 0,
+                 otherwise: Optional[StageID] = None, resolve_network: bool = True) -> None:
+        if cmp not in self.CMPS:
+            raise ValueError(f"StageRule: unknown comparison '{cmp}'")
+        if lhs != "always" and otherwise is None:
+            raise ValueError("StageRule: a conditional rule needs `otherwise`")
+        self.then, self.lhs, self.cmp, self.rhs = then, lhs, cmp, int(rhs)
+        self.otherwise = then if otherwise is None else otherwise
+        self.resolve_network = bool(resolve_network)
+
+    def __call__(self, *args, **kwargs):
+        from .errors import DeviceOnlyError
+
+        raise DeviceOnlyError("a StageRule is evaluated by the fused step kernel")
 
 
 class FSMStage:

@@ -73,6 +73,51 @@ def _check_env_hooks(env) -> None:
                     "(__phx_device_env__) can supply env-level hooks (no CPU fallback)")
 
 
+def _lower_stage_rule(out, sid, st, stage_ids, agents, slot) -> None:
+    """FSMStage.handler -> phx_stage.rule_* (reference: phantom/fsm.py:294-307)."""
+    from .fsm import StageRule
+
+    rule = st.handler
+    if not isinstance(rule, StageRule):
+        raise NotLowerableError(
+            f"FSM stage '{sid}' has a Python handler; only a phantom_b200.fsm.StageRule "
+            "(or no handler) lowers to the device")
+
+    def stage_index(x):
+        # a stage the FSM does not know can only be *returned* at run time, where the reference
+        # raises FSMRuntimeError (fsm.py:304-307): give it an index outside every next_allowed
+        return stage_ids.index(x) if x in stage_ids else L.PHX_MAX_STAGES - 1
+
+    for x in (rule.then, rule.otherwise):
+        if x not in stage_ids and len(stage_ids) >= L.PHX_MAX_STAGES:
+            raise NotLowerableError("StageRule returns an unknown stage and no spare stage index is left")
+    out.handler = 1
+    out.rule_resolves = int(rule.resolve_network)
+    out.rule_cmp = StageRule.CMPS.index(rule.cmp)
+    out.rule_rhs = rule.rhs
+    out.rule_then = stage_index(rule.then)
+    out.rule_else = stage_index(rule.otherwise)
+    if rule.lhs == "always":
+        out.rule_lhs = L.RULE_ALWAYS
+    elif rule.lhs == "step":
+        out.rule_lhs = L.RULE_STEP
+    elif isinstance(rule.lhs, tuple) and len(rule.lhs) == 3 and rule.lhs[0] == "agent":
+        _, aid, column = rule.lhs
+        if aid not in slot:
+            raise NotLowerableError(f"StageRule of stage '{sid}': unknown agent '{aid}'")
+        if isinstance(column, str):
+            desc = getattr(type(agents[slot[aid]]), column, None)
+            if not hasattr(desc, "word") or getattr(desc, "dtype", "int32") != "int32":
+                raise NotLowerableError(
+                    f"StageRule of stage '{sid}': '{column}' is not an int32 device column of '{aid}'")
+            column = desc.word
+        out.rule_lhs, out.rule_slot, out.rule_word = L.RULE_AGENT_WORD, slot[aid], int(column)
+    elif isinstance(rule.lhs, tuple) and len(rule.lhs) == 2 and rule.lhs[0] == "env":
+        out.rule_lhs, out.rule_word = L.RULE_ENV_WORD, int(rule.lhs[1])
+    else:
+        raise NotLowerableError(f"StageRule of stage '{sid}': unknown lhs {rule.lhs!r}")
+
+
 def lower(env, exec_mode: str = "auto", auto_reset: bool = False) -> L.PhxSpec:
     from .fsm import FiniteStateMachineEnv
     from .stackelberg import StackelbergEnv
@@ -170,9 +215,7 @@ def lower(env, exec_mode: str = "auto", auto_reset: bool = False) -> L.PhxSpec:
         for k, sid in enumerate(stage_ids):
             st = env._stages[sid]
             if st.handler is not None:
-                raise NotLowerableError(
-                    f"FSM stage '{sid}' has a Python handler; only handler-less "
-                    "(deterministic) stages lower to the device (SURVEY.md 8f row 4)")
+                _lower_stage_rule(spec.stages[k], sid, st, stage_ids, agents, slot)
             for aid in st.acting_agents:
                 L.set_mask(spec.stages[k].acting, slot[aid])
             if st.rewarded_agents is None:
@@ -180,7 +223,10 @@ def lower(env, exec_mode: str = "auto", auto_reset: bool = False) -> L.PhxSpec:
             else:
                 for aid in st.rewarded_agents:
                     L.set_mask(spec.stages[k].rewarded, slot[aid])
-            spec.stages[k].next_stage = stage_ids.index(st.next_stages[0])
+            for nxt in st.next_stages:
+                spec.stages[k].next_allowed |= 1 << stage_ids.index(nxt)
+            if st.handler is None:
+                spec.stages[k].next_stage = stage_ids.index(st.next_stages[0])
     elif isinstance(env, StackelbergEnv):
         spec.env_kind = L.ENV_STACKELBERG
         for aid in env.leader_agents:

@@ -222,6 +222,129 @@ def scenario_fsm_validation(K):
     assert env.is_fsm_deterministic()
 
 
+def scenario_fsm_one_state_with_handler(K):
+    """/root/reference/tests/fsm/test_one_state.py:15-69: one stage registered through the
+    FSMStage DECORATOR whose env handler returns the stage itself (and does not resolve the
+    network).  `K.stage_handler` is a Python function on the oracle / reference and a
+    `StageRule` on the device."""
+    ph = K.ph
+
+    class OneStateFSMEnvWithHandler(ph.FiniteStateMachineEnv):
+        def __init__(self):
+            network = K.finish_network(ph.Network([K.MockStrategicAgent("agent")]))
+            network.add_connection("agent", "agent")
+            super().__init__(num_steps=2, network=network, initial_stage="UNIT")
+
+        handle = ph.FSMStage(stage_id="UNIT", acting_agents=["agent"], next_stages=["UNIT"])(
+            K.stage_handler("UNIT", resolve_network=False))
+
+    env = OneStateFSMEnvWithHandler()
+    obs, info = env.reset()
+    approx_obs(obs, {"agent": np.array([0.0])})
+    assert env.current_stage == "UNIT"
+    assert counts(env.agents["agent"]) == (0, 1, 0)
+
+    step = env.step({"agent": np.array([0])})
+    assert env.current_stage == "UNIT"
+    assert counts(env.agents["agent"]) == (1, 2, 1)
+    approx_obs(step.observations, {"agent": np.array([0.5])})
+    assert step.rewards == {"agent": 0}
+    assert step.terminations == {"agent": False, "__all__": False}
+    assert step.truncations == {"agent": False, "__all__": False}
+    assert step.infos == {"agent": {}}
+
+    step = env.step({"agent": np.array([0])})
+    assert env.current_stage == "UNIT"
+    assert counts(env.agents["agent"]) == (2, 3, 2)
+    approx_obs(step.observations, {"agent": np.array([1.0])})
+    assert step.rewards == {"agent": 0}
+    assert step.terminations == {"agent": False, "__all__": False}
+    assert step.truncations == {"agent": False, "__all__": True}
+    assert step.infos == {"agent": {}}
+    return env
+
+
+def scenario_fsm_invalid_transition_runtime(K):
+    """/root/reference/tests/fsm/test_fsm_validation.py:145-174: a handler returning a stage
+    outside the stage's next_stages raises FSMRuntimeError from step() (fsm.py:304-307); and
+    tests/fsm/test_is_fsm_deterministic.py:27-47: stages with two next stages and handlers
+    make the FSM non-deterministic."""
+    ph = K.ph
+    network = K.finish_network(ph.Network([K.MockStrategicAgent("agent")]))
+    env = ph.FiniteStateMachineEnv(
+        num_steps=1, network=network, initial_stage="StageA",
+        stages=[ph.FSMStage(stage_id="StageA", acting_agents=["agent"], next_stages=["StageA"],
+                            handler=K.stage_handler("StageB"))])
+    env.reset()
+    with pytest.raises(ph.fsm.FSMRuntimeError):
+        env.step({"agent": np.array([0])})
+
+    env2 = ph.FiniteStateMachineEnv(
+        num_steps=1, network=K.finish_network(ph.Network([])), initial_stage="A",
+        stages=[ph.FSMStage(stage_id="A", acting_agents=[], next_stages=["A", "B"],
+                            handler=K.stage_handler("B")),
+                ph.FSMStage(stage_id="B", acting_agents=[], next_stages=["A", "B"],
+                            handler=K.stage_handler("A"))])
+    assert not env2.is_fsm_deterministic()
+
+
+def _fsm_state_driven(K, **kw):
+    ph = K.ph
+    agents = [K.MockStrategicAgent("s"), K.MockStrategicAgent("t"),
+              K.EchoAgent("a", seed_value=4), K.EchoAgent("b")]
+    network = ph.Network(agents)
+    network.add_connection("a", "b")
+    return ph.FiniteStateMachineEnv(
+        num_steps=6, network=K.finish_network(network), initial_stage="FILL",
+        stages=[
+            # the handler resolves the network, then looks at what the resolution did to `b`
+            ph.FSMStage(stage_id="FILL", acting_agents=["s", "a"], rewarded_agents=["s"],
+                        next_stages=["FILL", "DRAIN"],
+                        handler=K.stage_handler("DRAIN", ("agent", "b", "handled_count"), ">=", 4,
+                                                otherwise="FILL")),
+            # no messages in this stage: the handler only looks at the clock
+            ph.FSMStage(stage_id="DRAIN", acting_agents=["t"], rewarded_agents=["t"],
+                        next_stages=["FILL", "DRAIN"],
+                        handler=K.stage_handler("FILL", "step", ">=", 4, otherwise="DRAIN",
+                                                resolve_network=False)),
+        ], **kw)
+
+
+# (stage after the step, observations, rewards, truncations["__all__"], a.handled_count,
+#  b.handled_count, b.handled_total) -- produced by the UNMODIFIED reference running this
+# scenario (oracle/workloads/mock.py classes on phantom imported through oracle/ref_shim.py) and
+# identically by the oracle port; DESIGN.md 3 records the run.
+FSM_STATE_DRIVEN_TRACE = [
+    ("FILL", {"s": 1 / 6}, {"s": 0.0}, False, 1, 2, 5),
+    ("DRAIN", {"t": 2 / 6}, {"t": None}, False, 2, 4, 10),
+    ("DRAIN", {"t": 3 / 6}, {"t": 0.0}, False, 2, 4, 10),
+    ("FILL", {"s": 4 / 6}, {"s": 0.0}, False, 2, 4, 10),
+    ("DRAIN", {"t": 5 / 6}, {"t": 0.0}, False, 3, 6, 15),
+    ("FILL", {"s": 1.0, "t": 5 / 6}, {"s": 0.0, "t": 0.0}, True, 3, 6, 15),
+]
+
+
+def scenario_fsm_handler_state_driven(K):
+    """Handler-driven (non-deterministic) transitions, fsm.py:294-307: the next stage depends on
+    agent state AFTER the handler's own resolve_network() (three resolver rounds of echo
+    messages), and the observing set `acting_agents[next_stage]` (fsm.py:319-320) follows it."""
+    env = _fsm_state_driven(K)
+    obs, _ = env.reset()
+    approx_obs(obs, {"s": np.array([0.0])})
+    assert env.current_stage == "FILL"
+    for want_stage, want_obs, want_rew, all_trunc, ac, bc, bt in FSM_STATE_DRIVEN_TRACE:
+        step = env.step({"s": np.array([0]), "t": np.array([0])})
+        assert env.current_stage == want_stage
+        approx_obs(step.observations, {k: np.array([v]) for k, v in want_obs.items()})
+        assert dict(step.rewards) == want_rew
+        assert step.terminations == {"s": False, "t": False, "__all__": False}
+        assert step.truncations == {"s": False, "t": False, "__all__": all_trunc}
+        assert int(env.agents["a"].handled_count) == ac
+        assert int(env.agents["b"].handled_count) == bc
+        assert int(env.agents["b"].handled_total) == bt
+    return env
+
+
 def scenario_stackelberg(K):
     """/root/reference/tests/test_stackelberg.py:10-74"""
     ph = K.ph
@@ -415,6 +538,9 @@ ALL = [
     scenario_fsm_odd_even_two_agents,
     scenario_fsm_one_state,
     scenario_fsm_validation,
+    scenario_fsm_one_state_with_handler,
+    scenario_fsm_invalid_transition_runtime,
+    scenario_fsm_handler_state_driven,
     scenario_stackelberg,
     scenario_tracking_golden_vector,
     scenario_resolver_round_ordering,

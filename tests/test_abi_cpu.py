@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_spec_layout_matches_compiled_struct():
     assert L.lib.phx_sizeof_spec() == C.sizeof(L.PhxSpec)
-    assert L.lib.phx_abi_version() == L.PHX_ABI_VERSION == 3
+    assert L.lib.phx_abi_version() == L.PHX_ABI_VERSION == 4
 
 
 def test_no_cpu_fallback():
@@ -85,6 +85,44 @@ def test_lowering_fsm_and_stackelberg_tables():
     assert [s.stages[k].rewarded_is_none for k in range(3)] == [0, 0, 0]
     s = StackelbergGameEnv().spec
     assert (s.env_kind, s.leaders[0], s.followers[0]) == (L.ENV_STACKELBERG, 0b0001, 0b1110)
+
+
+def test_lowering_fsm_stage_handlers():
+    """FSMStage.handler (fsm.py:294-307): a StageRule lowers to phx_stage.rule_*, a Python
+    callable is refused, a rule returning an unknown stage gets an index outside next_allowed."""
+    import phantom_b200 as ph
+    from phantom_b200.envs import mock
+
+    class NS:
+        pass
+
+    K = NS()
+    K.ph, K.MockStrategicAgent, K.EchoAgent = ph, mock.MockStrategicAgent, mock.EchoAgent
+    K.finish_network, K.stage_handler = (lambda n: n), ph.StageRule
+    from . import kat_scenarios as kats
+
+    s = kats._fsm_state_driven(K).spec
+    fill, drain = s.stages[0], s.stages[1]
+    assert (fill.handler, fill.rule_resolves, fill.next_allowed) == (1, 1, 0b11)
+    assert (fill.rule_lhs, fill.rule_slot, fill.rule_word) == (L.RULE_AGENT_WORD, 3, 3)  # b.handled_count
+    assert (fill.rule_cmp, fill.rule_rhs, fill.rule_then, fill.rule_else) == (L.CMP_GE, 4, 1, 0)
+    assert (drain.handler, drain.rule_resolves, drain.rule_lhs) == (1, 0, L.RULE_STEP)
+    assert (drain.rule_cmp, drain.rule_rhs, drain.rule_then, drain.rule_else) == (L.CMP_GE, 4, 0, 1)
+
+    def one_stage(handler):
+        return ph.FiniteStateMachineEnv(
+            num_steps=1, network=ph.Network([mock.MockStrategicAgent("agent")]), initial_stage="A",
+            stages=[ph.FSMStage(stage_id="A", acting_agents=["agent"], next_stages=["A"],
+                                handler=handler)])
+
+    s = one_stage(ph.StageRule("B")).spec  # "B" is no stage: FSMRuntimeError at run time
+    assert s.stages[0].rule_then == L.PHX_MAX_STAGES - 1 and s.stages[0].next_allowed == 1
+    with pytest.raises(ph.NotLowerableError):
+        one_stage(lambda env: "A").spec
+    with pytest.raises(ph.NotLowerableError):
+        one_stage(ph.StageRule("A", ("agent", "agent", "no_such_column"), "<", 1, otherwise="A")).spec
+    with pytest.raises(ph.DeviceOnlyError):
+        ph.StageRule("A")()
 
 
 def test_python_logic_is_never_silently_ignored():

@@ -21,6 +21,7 @@ def K():
     ns.finish_network = lambda network: network
     ns.CodecAgent = mock.CodecAgent
     ns.ElapsedTime, ns.CurrentStep = ph.encoders.ElapsedTime, ph.encoders.CurrentStep
+    ns.stage_handler = ph.StageRule  # the device form of an env stage handler
     return ns
 
 
@@ -66,3 +67,80 @@ def test_batched_kat_every_env_identical(K):
     assert out.obs_mask.cpu().numpy().tolist() == [[1, 1]] * 3000  # terminal flush of the caches
     assert out.reward_mask.cpu().numpy().tolist() == [[1, 1]] * 3000
     env.close()
+
+
+@pytest.mark.parametrize("exec_mode", ["thread", "queue"])
+def test_handler_driven_fsm_envs_diverge(K, exec_mode, monkeypatch):
+    """Handler-driven transitions (fsm.py:294-307) across a batch whose envs take DIFFERENT
+    paths through the FSM: env e starts with b.handled_count = e % 7, so the FILL stage's rule
+    (`b.handled_count >= 4` after the handler's resolve_network()) fires at a different step per
+    env.  Stage column, observation / reward masks and the echo counters are compared per env
+    with the oracle stepping one env object per start value."""
+    import numpy as np
+
+    import oracle.phantom_oracle as po
+    from oracle.workloads import mock as omock
+
+    monkeypatch.setattr(K.ph.PhantomEnv, "default_exec_mode", exec_mode)
+    E, T = 70, 6
+    env = kats._fsm_state_driven(K, num_envs=E)
+    env.reset_batch()
+    start = np.arange(E, dtype=np.int32) % 7
+    env.agents["b"].handled_count = start
+    stage_ids = ["FILL", "DRAIN"]
+    got_stage, got_om, got_rm, got_bc = [], [], [], []
+    acts = np.zeros((E, 2, 1), np.float32)
+    for _ in range(T):
+        out = env.step_batch(acts)
+        got_stage.append(np.asarray(env.current_stage).copy())
+        got_om.append(out.obs_mask.cpu().numpy().copy())
+        got_rm.append(out.reward_mask.cpu().numpy().copy())
+        got_bc.append(np.asarray(env.agents["b"].handled_count).copy())
+    env.close()
+
+    KO = omock.build_classes(po)
+    for k in range(7):
+        ref = kats._fsm_state_driven(KO)
+        ref.reset()
+        ref.agents["b"].handled_count = int(k)
+        for t in range(T):
+            step = ref.step({"s": np.array([0]), "t": np.array([0])})
+            rows = np.nonzero(start == k)[0]
+            assert (got_stage[t][rows] == stage_ids.index(ref.current_stage)).all(), (k, t)
+            want_om = [int(a in step.observations) for a in ("s", "t")]
+            assert (got_om[t][rows] == want_om).all(), (k, t)
+            # reward mask: 1 = a float reward, 2 = the key is present with value None
+            want_rm = [0 if a not in step.rewards else (2 if step.rewards[a] is None else 1)
+                       for a in ("s", "t")]
+            assert (got_rm[t][rows] == want_rm).all(), (k, t)
+            assert (got_bc[t][rows] == ref.agents["b"].handled_count).all(), (k, t)
+
+
+def test_handler_without_resolve_leaves_mail(K):
+    """A stage handler that never calls resolve_network() while agents sent messages: the
+    reference keeps that mail queued for some later resolve; the device refuses (sticky fault,
+    RuntimeError) instead of silently dropping it."""
+    import numpy as np
+
+    ph = K.ph
+    network = ph.Network([K.MockStrategicAgent("s"), K.EchoAgent("a", seed_value=4), K.EchoAgent("b")])
+    network.add_connection("a", "b")
+    env = ph.FiniteStateMachineEnv(
+        num_steps=3, network=network, initial_stage="X",
+        stages=[ph.FSMStage(stage_id="X", acting_agents=["s", "a"], next_stages=["X"],
+                            handler=ph.StageRule("X", resolve_network=False))])
+    env.reset()
+    with pytest.raises(RuntimeError, match="unresolved"):
+        env.step({"s": np.array([0])})
+    env.close()
+
+
+def test_python_stage_handler_is_not_lowerable(K):
+    ph = K.ph
+    network = ph.Network([K.MockStrategicAgent("s")])
+    env = ph.FiniteStateMachineEnv(
+        num_steps=3, network=network, initial_stage="X",
+        stages=[ph.FSMStage(stage_id="X", acting_agents=["s"], next_stages=["X"],
+                            handler=lambda e: "X")])
+    with pytest.raises(ph.NotLowerableError):
+        env.reset()
