@@ -34,6 +34,11 @@
 #include <string>
 
 #include "phx_engine_host.cuh"
+// output store hints: 1 = every output row streaming (st.global.cs), the measured best
+// (tools/ab_variants.sh, profiles/r01_ab_store_hints.txt); 0 = reward only, 2 = none, 3 = write-through
+#ifndef SC_OUT_HINT
+#define SC_OUT_HINT 1
+#endif
 #include "phx_family.h"
 #include "phx_rng.cuh"
 
@@ -299,9 +304,24 @@ __global__ void __launch_bounds__(SC_BLOCK) sc_fast_kernel(const ScArgs a) {
 
     {  // three strided 4-byte stores per row beat a shared-memory transpose into 16-byte stores
       float* o = a.io.obs + (size_t)row * 3;
+#if SC_OUT_HINT == 1  // every output streaming (evict-first): the rows are never re-read on
+      // the device, and a launch writes 118 MB into a 126 MB L2
+      __stcs(o, o0); __stcs(o + 1, o1); __stcs(o + 2, o2);
+      st_stream(a.io.reward + row, reward);
+      __stcs(reinterpret_cast<uchar2*>(a.io.all_done) + row, make_uchar2(0, at_max ? 1 : 0));
+#elif SC_OUT_HINT == 2  // no hints
+      o[0] = o0; o[1] = o1; o[2] = o2;
+      a.io.reward[row] = reward;
+      reinterpret_cast<uchar2*>(a.io.all_done)[row] = make_uchar2(0, at_max ? 1 : 0);
+#elif SC_OUT_HINT == 3  // write-through
+      __stwt(o, o0); __stwt(o + 1, o1); __stwt(o + 2, o2);
+      __stwt(a.io.reward + row, reward);
+      __stwt(reinterpret_cast<uchar2*>(a.io.all_done) + row, make_uchar2(0, at_max ? 1 : 0));
+#else
       o[0] = o0; o[1] = o1; o[2] = o2;
       st_stream(a.io.reward + row, reward);
       reinterpret_cast<uchar2*>(a.io.all_done)[row] = make_uchar2(0, at_max ? 1 : 0);
+#endif
       if (FULL_IO) {
         a.io.obs_mask[row] = 1;
         a.io.reward_mask[row] = 1;
