@@ -1,6 +1,7 @@
 // phx_engine_host.cuh -- host side of the generic queue engine: a Family implementation that
 // owns the state of E envs of a device program P and launches engine_step_kernel<P, G>.
 #pragma once
+#include <cstdlib>
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -384,6 +385,20 @@ class EngineFamily : public Family {
                      : launch_step<32>(a, stream);
   }
 
+  template <int GG>
+  int generic_blocks_per_sm() {
+    int nb = 0;
+    const size_t smem = sizeof(BlockSmem<P, GG>);
+    if (cudaFuncSetAttribute(engine_step_kernel<P, GG, false>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, engine_step_kernel<P, GG, false>,
+                                                      ENGINE_BLOCK, smem) != cudaSuccess) {
+      cudaGetLastError();
+      return 0;
+    }
+    return nb;
+  }
+
   int32_t jit_source(std::string& out) override {
     if constexpr (HasJit<P>::value) {
       const bool thread_ok = P::Q1CAP > 0 && P::VW <= 1;
@@ -392,7 +407,24 @@ class EngineFamily : public Family {
       const std::string body =
           thread_per_env ? "engine1_step_body<" + prog + ", false, ConstSpec>(a);"
                          : "engine_step_body<" + prog + ", " + std::to_string(G) + ", false, ConstSpec>(a);";
-      const std::string bound = thread_per_env ? "ENGINE1_BLOCK" : "ENGINE_BLOCK";
+      std::string bound = thread_per_env ? "ENGINE1_BLOCK" : "ENGINE_BLOCK";
+      if (!thread_per_env) {
+        // With the agent loops unrolled over a compile-time agent count the tile kernel can need
+        // far more registers than the generic build (simple_market on 32-lane tiles: 173 vs 119,
+        // 2 instead of 4 resident blocks per SM).  PHX_JIT_MINBLOCKS = k | auto (the generic
+        // kernel's residency) adds a min-blocks launch bound; measured (profiles/
+        // r01_ab_jit_minblocks.txt) it helps that env class (15.4 -> 13.0 ms, generic 9.6) but
+        // costs C4 on 8-lane tiles (3.5 -> 4.2 ms), so the default stays unbounded.
+        int nb = 0;
+        if (const char* ov = std::getenv("PHX_JIT_MINBLOCKS")) {
+          if (std::string(ov) == "auto")
+            nb = G == 8 ? generic_blocks_per_sm<8>()
+                 : G == 16 ? generic_blocks_per_sm<16>() : generic_blocks_per_sm<32>();
+          else
+            nb = std::atoi(ov);
+        }
+        if (nb > 0) bound += ", " + std::to_string(nb);
+      }
       out = std::string("// generated by libphx (phx_jit_source): the ") +
             (thread_per_env ? "thread-per-env" : "tile") + " step kernel of\n// " + prog +
             " with this handle's lowered env class as a compile-time constant\n"
