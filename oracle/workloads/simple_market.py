@@ -124,7 +124,7 @@ def build_reference(buyers=EXAMPLE_BUYERS, n_sellers: int = EXAMPLE_SELLERS, num
 
 
 def build(ph, UniformFloatSampler, buyers=EXAMPLE_BUYERS, n_sellers: int = EXAMPLE_SELLERS,
-          num_steps: int = 10):
+          num_steps: int = 10, seller_stage_handler=None):
     """The same env restated against plugin-API module `ph`.  Returns (env, buyer_ordinal)."""
     from ..phantom_oracle.spaces import Box, Discrete
 
@@ -208,11 +208,15 @@ def build(ph, UniformFloatSampler, buyers=EXAMPLE_BUYERS, n_sellers: int = EXAMP
         def __init__(self, num_steps, network, buyer_ids, seller_ids):
             self.avg_price = 0.0
             self._seller_ids = seller_ids
+            # seller_stage_handler (not in the example): a Python env handler of the Sellers stage
+            # (fsm.py:294-302), the twin of a device StageRule
             super().__init__(num_steps, network, initial_stage="Sellers", stages=[
                 ph.FSMStage(stage_id="Buyers", next_stages=["Sellers"], acting_agents=buyer_ids,
                             rewarded_agents=buyer_ids),
-                ph.FSMStage(stage_id="Sellers", next_stages=["Buyers"], acting_agents=seller_ids,
-                            rewarded_agents=seller_ids)])
+                ph.FSMStage(stage_id="Sellers", acting_agents=seller_ids, rewarded_agents=seller_ids,
+                            next_stages=(["Buyers"] if seller_stage_handler is None
+                                         else ["Buyers", "Sellers"]),
+                            handler=seller_stage_handler)])
 
         def view(self, neighbour_id=None):
             return self.View(avg_price=self.avg_price, **super().view({}).__dict__)

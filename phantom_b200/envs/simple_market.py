@@ -173,14 +173,17 @@ class SimpleMarketEnv(ph.FiniteStateMachineEnv):
     class View(FSMEnvView):
         avg_price: float
 
-    def __init__(self, num_steps, network, **batch_kwargs):
+    def __init__(self, num_steps, network, seller_stage_handler=None, **batch_kwargs):
         buyers = [aid for aid, a in network.agents.items() if isinstance(a, BuyerAgent)]
         sellers = [aid for aid, a in network.agents.items() if isinstance(a, SellerAgent)]
+        # `seller_stage_handler` (not in the example): an env handler for the Sellers stage, e.g.
+        # a StageRule on the env-level avg_price words -- sellers re-price until it fires
         stages = [
             ph.FSMStage(stage_id="Buyers", next_stages=["Sellers"], acting_agents=buyers,
                         rewarded_agents=buyers),
-            ph.FSMStage(stage_id="Sellers", next_stages=["Buyers"], acting_agents=sellers,
-                        rewarded_agents=sellers),
+            ph.FSMStage(stage_id="Sellers", acting_agents=sellers, rewarded_agents=sellers,
+                        next_stages=["Buyers"] if seller_stage_handler is None else ["Buyers", "Sellers"],
+                        handler=seller_stage_handler),
         ]
         super().__init__(num_steps, network, stages=stages, initial_stage="Sellers", **batch_kwargs)
 
