@@ -364,7 +364,11 @@ def run_ours(args):
             },
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                    "api": "phx_rollout_host (pinned host buffers)"},
+                    "api": "phx_rollout_host (pinned host buffers)",
+                    # the link that bounds it: device->host rate of one rank's result rows
+                    # (profiles/r01_pcie_peak.json: plain pinned D2H of this size = 56.3 GB/s)
+                    "bound": "pcie d2h",
+                    "d2h_GBps_per_gpu": d2h * e2e_value / (world * E * T) / 1e9},
             "single_step": single,
             # kernels of ours inside the device-timed region (one sc_fast_kernel per bench step);
             # the e2e region launches one kernel per pipeline chunk (8 per call)
