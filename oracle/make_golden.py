@@ -300,6 +300,40 @@ def gen_simple_market_reference() -> None:
         print(name, {k: v.shape for k, v in out.items()})
 
 
+# the tape of tests/test_gpu_simple_market.py::test_simple_market_handler_driven_on_env_word
+SIMPLE_MARKET_HANDLER_TAPE = dict(T=10, n_env=12, n_ep=2, seed=5, action_seed=9)
+
+
+def gen_simple_market_handler_reference() -> None:
+    """simple_market_handler_reference.npz: the reference's simple_market example classes,
+    UNMODIFIED, with an env HANDLER on the Sellers stage (fsm.py:294-307;
+    workloads/simple_market.py:seller_handler_avg_price -- resolve_network(), then Buyers once
+    avg_price >= 0.5, else Sellers again), under the contract RNG.  Same cast and action tape as
+    the device-vs-oracle GPU test, so  device == oracle (GPU test)  and  oracle == reference
+    (tests/test_oracle_golden.py, this fixture)  close the chain."""
+    from .workloads import simple_market as wl
+
+    c = SIMPLE_MARKET_HANDLER_TAPE
+    buyers, n_sellers = wl.EXAMPLE_BUYERS, wl.EXAMPLE_SELLERS
+    actions, mask = wl.actions_for(c["n_env"], c["n_ep"], c["T"], len(buyers), n_sellers,
+                                   c["action_seed"])
+    per_env = []
+    for e in range(c["n_env"]):
+        coords = wl.Coords(c["seed"], e)
+        with wl.contract_rng(coords, {f"b{i + 1}": i for i in range(len(buyers))}):
+            env, _ = wl.build_reference(buyers, n_sellers, c["T"],
+                                        seller_stage_handler=wl.seller_handler_avg_price)
+            tr = harness.run_generic(env, harness.EpisodeClock([coords]), actions[e], mask[e],
+                                     wl.OBS_DIM, state_fn=wl.state, convert=wl.to_action(env))
+        tr["messages"] = []
+        per_env.append(tr)
+    out = pack_generic(per_env, actions, mask, c["seed"], 0, {})
+    out["buyers"] = np.array(buyers, np.float64)
+    out["n_sellers"] = np.int64(n_sellers)
+    np.savez_compressed(os.path.join(GOLDEN, "simple_market_handler_reference.npz"), **out)
+    print("simple_market_handler_reference.npz", {k: v.shape for k, v in out.items()})
+
+
 def gen_digital_ads_reference() -> None:
     """The reference's examples/environments/digital_ads_market/digital_ads_market.py, UNMODIFIED
     (oracle/workloads/digital_ads.py:build_reference), under the contract RNG:
@@ -344,6 +378,7 @@ def main() -> int:
     gen_supply_chain2_reference()
     gen_shuffle_and_stochastic_reference()
     gen_simple_market_reference()
+    gen_simple_market_handler_reference()
     gen_digital_ads_reference()
     return 0
 

@@ -99,9 +99,20 @@ def _ids(n_buyers: int, n_sellers: int):
     return [f"b{i + 1}" for i in range(n_buyers)], [f"s{i + 1}" for i in range(n_sellers)]
 
 
-def build_reference(buyers=EXAMPLE_BUYERS, n_sellers: int = EXAMPLE_SELLERS, num_steps: int = 10):
+def seller_handler_avg_price(env):
+    """Env handler of the Sellers stage used by the handler-driven fixture (fsm.py:294-302): the
+    sellers price again until the average price reaches 0.5.  Device twin:
+    StageRule("Buyers", ("env", 1), ">=", 0x3FE00000, otherwise="Sellers")."""
+    env.resolve_network()
+    return "Buyers" if env.avg_price >= 0.5 else "Sellers"
+
+
+def build_reference(buyers=EXAMPLE_BUYERS, n_sellers: int = EXAMPLE_SELLERS, num_steps: int = 10,
+                    seller_stage_handler=None):
     """The unmodified example classes, wired the way example_simple_market.py:9-30 does.
-    Returns (env, buyer_ordinal)."""
+    Returns (env, buyer_ordinal).  `seller_stage_handler`: the example's env object is built as
+    is and its Sellers stage is then re-registered with that env handler and both next stages
+    (the classes stay unmodified; only the stage table of this instance changes)."""
     from .. import ref_shim
 
     ph = ref_shim.import_reference()
@@ -120,6 +131,10 @@ def build_reference(buyers=EXAMPLE_BUYERS, n_sellers: int = EXAMPLE_SELLERS, num
     network = ph.Network(agents)
     network.add_connections_between(buyer_ids, seller_ids)
     env = simple_mkt_env.SimpleMarketEnv(num_steps=num_steps, network=network)
+    if seller_stage_handler is not None:
+        env._stages["Sellers"] = ph.FSMStage(
+            stage_id="Sellers", acting_agents=seller_ids, rewarded_agents=seller_ids,
+            next_stages=["Buyers", "Sellers"], handler=seller_stage_handler)
     return env, {b: i for i, b in enumerate(buyer_ids)}
 
 

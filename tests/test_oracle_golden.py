@@ -338,6 +338,37 @@ def test_object_oracle_matches_simple_market_golden(golden_dir, name):
     assert len(np.unique(g["state"][..., -1, 0])) > 10
 
 
+def test_object_oracle_matches_simple_market_handler_golden(golden_dir):
+    """Handler-driven FSM transitions (fsm.py:294-307): the oracle restatement of simple_market
+    with a Python env handler on the Sellers stage == the UNMODIFIED example classes run by the
+    reference with the same handler (oracle/make_golden.py:gen_simple_market_handler_reference).
+    The GPU test test_simple_market_handler_driven_on_env_word compares the device (StageRule on
+    the env-level avg_price word) with this oracle on the same cast and action tape."""
+    from oracle.workloads import simple_market as sm
+
+    from .generic_parity import assert_oracle_trace_equal
+
+    g = np.load(os.path.join(golden_dir, "simple_market_handler_reference.npz"))
+    seed, A, M = int(g["seed"]), g["actions"], g["action_mask"]
+    buyers, n_sellers, T = [tuple(b) for b in g["buyers"]], int(g["n_sellers"]), A.shape[2]
+    A2, M2 = sm.actions_for(A.shape[0], A.shape[1], T, len(buyers), n_sellers, 9)
+    assert seed == 5 and np.array_equal(A, A2) and np.array_equal(M, M2)  # the GPU test's tape
+    for e in range(A.shape[0]):
+        coords = sm.Coords(seed, e)
+        with sm.contract_rng(coords, {f"b{i + 1}": i for i in range(len(buyers))}):
+            env, _ = sm.build(po, po.utils.samplers.UniformFloatSampler, buyers, n_sellers, T,
+                              seller_stage_handler=sm.seller_handler_avg_price)
+            tr = harness.run_generic(env, harness.EpisodeClock([coords]), A[e], M[e], sm.OBS_DIM,
+                                     state_fn=sm.state, convert=sm.to_action(env))
+        assert_oracle_trace_equal(tr, g, e)
+    # both outcomes of the handler occur: steps after which the sellers observe again (the FSM
+    # stayed in / returned to Sellers) and steps after which only buyers do
+    sellers_next = g["obs_mask"][..., len(buyers):].any(axis=-1)
+    assert sellers_next.any() and (~sellers_next).any()
+    # and the handler made envs leave the example's strict Sellers/Buyers alternation
+    assert (sellers_next[:, :, :-1] & sellers_next[:, :, 1:]).any()
+
+
 @pytest.mark.parametrize("name", ["digital_ads_reference.npz", "digital_ads_wide_reference.npz"])
 def test_oracle_port_runs_the_digital_ads_example(golden_dir, name):
     """The UNMODIFIED example file executed on the oracle port (its `import phantom` bound to
