@@ -15,3 +15,33 @@ def K():
 @pytest.mark.parametrize("scenario", kats.ALL, ids=lambda f: f.__name__)
 def test_kat_on_oracle(K, scenario):
     scenario(K)
+
+
+def test_handler_kats_on_the_unmodified_reference():
+    """The three handler-driven FSM scenarios (fsm.py:294-307; two restate the reference's own
+    tests, one is authored) executed by the UNMODIFIED reference, imported through
+    oracle/ref_shim.py in a fresh interpreter: the expectations hard-coded in
+    tests/kat_scenarios.py (FSM_STATE_DRIVEN_TRACE ...) are the reference's, not the port's.
+    Only possible where /root/reference exists (the build container)."""
+    import os
+    import subprocess
+    import sys
+
+    from oracle import ref_shim
+
+    if not os.path.isdir(os.path.join(ref_shim.REFERENCE_ROOT, "phantom")):
+        pytest.skip("the reference is only available in the build container")
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "from oracle import ref_shim\n"
+        "from oracle.workloads import mock\n"
+        "from tests import kat_scenarios as k\n"
+        "K = mock.build_classes(ref_shim.import_reference())\n"
+        "for f in (k.scenario_fsm_one_state_with_handler, k.scenario_fsm_invalid_transition_runtime,\n"
+        "          k.scenario_fsm_handler_state_driven, k.scenario_fsm_one_state,\n"
+        "          k.scenario_fsm_odd_even_two_agents):\n"
+        "    f(K)\n"
+        "print('reference ok')\n")
+    out = subprocess.run([sys.executable, "-c", code], cwd=repo, capture_output=True, text=True,
+                         timeout=300)
+    assert out.returncode == 0 and "reference ok" in out.stdout, out.stderr[-2000:]
