@@ -91,6 +91,8 @@ def _lower_stage_rule(out, sid, st, stage_ids, agents, slot) -> None:
     for x in (rule.then, rule.otherwise):
         if x not in stage_ids and len(stage_ids) >= L.PHX_MAX_STAGES:
             raise NotLowerableError("StageRule returns an unknown stage and no spare stage index is left")
+    if not -2 ** 31 <= rule.rhs < 2 ** 31:
+        raise NotLowerableError(f"StageRule of stage '{sid}': rhs {rule.rhs} is not an int32")
     out.handler = 1
     out.rule_resolves = int(rule.resolve_network)
     out.rule_cmp = StageRule.CMPS.index(rule.cmp)

@@ -121,6 +121,10 @@ def test_lowering_fsm_stage_handlers():
         one_stage(lambda env: "A").spec
     with pytest.raises(ph.NotLowerableError):
         one_stage(ph.StageRule("A", ("agent", "agent", "no_such_column"), "<", 1, otherwise="A")).spec
+    with pytest.raises(ph.NotLowerableError):  # the rule's constant travels as an int32
+        one_stage(ph.StageRule("A", "step", "<", 2 ** 31, otherwise="A")).spec
+    with pytest.raises(ValueError):
+        ph.StageRule("A", "step", "~", 1, otherwise="A")
     with pytest.raises(ph.DeviceOnlyError):
         ph.StageRule("A")()
 
