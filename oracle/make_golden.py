@@ -334,6 +334,29 @@ def gen_simple_market_handler_reference() -> None:
     print("simple_market_handler_reference.npz", {k: v.shape for k, v in out.items()})
 
 
+FSM_HANDLER_FUZZ_CASES = 40
+
+
+def gen_fsm_handler_fuzz_reference() -> None:
+    """fsm_handler_fuzz_reference.json: tests/kat_scenarios.py:run_random_handler_fsm (random
+    FiniteStateMachineEnvs with env stage handlers, fsm.py:294-307) executed by the UNMODIFIED
+    reference for case seeds 0..39: per step the stage, observations, rewards, done flags, the
+    mock agents' call counters and the echo agents' message counters; or the exception type."""
+    import json
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from tests import kat_scenarios as kats
+
+    from .workloads import mock
+
+    K = mock.build_classes(ref_shim.import_reference())
+    out = {str(s): kats.run_random_handler_fsm(K, s) for s in range(FSM_HANDLER_FUZZ_CASES)}
+    with open(os.path.join(GOLDEN, "fsm_handler_fuzz_reference.json"), "w") as f:
+        json.dump(out, f, separators=(",", ":"))
+    raised = sorted(int(s) for s, t in out.items() if t[-1][0] == "raise")
+    print("fsm_handler_fuzz_reference.json", len(out), "cases; raising:", raised)
+
+
 def gen_digital_ads_reference() -> None:
     """The reference's examples/environments/digital_ads_market/digital_ads_market.py, UNMODIFIED
     (oracle/workloads/digital_ads.py:build_reference), under the contract RNG:
@@ -379,6 +402,7 @@ def main() -> int:
     gen_shuffle_and_stochastic_reference()
     gen_simple_market_reference()
     gen_simple_market_handler_reference()
+    gen_fsm_handler_fuzz_reference()
     gen_digital_ads_reference()
     return 0
 

@@ -549,3 +549,94 @@ ALL = [
     scenario_done_agent_mail_is_dropped,
     scenario_codec_composition,
 ]
+
+
+# ---------------------------------------------------------------- random handler-driven FSMs
+def random_handler_fsm(K, case_seed, **kw):
+    """A random FiniteStateMachineEnv over the mock agents: 1-4 stages with random acting /
+    rewarded sets, handler-less stages and stages with env handlers (`K.stage_handler`: always /
+    clock / echo-agent counters after the handler's own resolve_network()), next_stages that
+    sometimes do NOT contain what the handler returns (FSMRuntimeError at run time), strategic
+    agents that terminate mid-episode, echo agents exchanging halving messages.  Deterministic in
+    `case_seed`; used as a differential fuzz oracle-vs-reference (CPU) and device-vs-oracle (GPU)."""
+    r = np.random.RandomState(case_seed)
+    ph = K.ph
+    strat = [f"s{i}" for i in range(int(r.randint(1, 4)))]
+    echo = [f"e{i}" for i in range(int(r.randint(0, 4)))]
+    seeds = {e: int(r.choice([0, 0, 3, 4, 9])) for e in echo}
+    agents = [K.MockStrategicAgent(a, num_steps=(int(r.randint(1, 7)) if r.uniform() < 0.3 else None))
+              for a in strat]
+    agents += [K.EchoAgent(e, seed_value=seeds[e]) for e in echo]
+    agents = [agents[i] for i in r.permutation(len(agents))]
+    network = ph.Network(agents)
+    for i in range(len(echo)):
+        for j in range(i + 1, len(echo)):
+            if r.uniform() < 0.6:
+                network.add_connection(echo[i], echo[j])
+    sids = [f"S{k}" for k in range(int(r.randint(1, 5)))]
+    stages = []
+    for sid in sids:
+        acting = [a for a in strat + echo if r.uniform() < 0.6]
+        rewarded = None if r.uniform() < 0.3 else [a for a in strat if r.uniform() < 0.6]
+        kinds = ["none", "always", "step"] + (["agent"] if echo else [])
+        kind = kinds[int(r.randint(len(kinds)))]
+        then, otherwise = (sids[int(r.randint(len(sids)))] for _ in range(2))
+        if kind == "none":
+            stages.append(ph.FSMStage(stage_id=sid, acting_agents=acting, rewarded_agents=rewarded,
+                                      next_stages=[then]))
+            continue
+        sends = any(seeds.get(a, 0) > 0 for a in acting)
+        resolve = True if sends else bool(r.uniform() < 0.5)
+        cmp = ["<", "<=", "==", "!=", ">=", ">"][int(r.randint(6))]
+        if kind == "always":
+            handler = K.stage_handler(then, resolve_network=resolve)
+            returned = [then]
+        elif kind == "step":
+            handler = K.stage_handler(then, "step", cmp, int(r.randint(1, 7)), otherwise=otherwise,
+                                      resolve_network=resolve)
+            returned = [then, otherwise]
+        else:
+            column = ["handled_count", "handled_total"][int(r.randint(2))]
+            handler = K.stage_handler(then, ("agent", echo[int(r.randint(len(echo)))], column), cmp,
+                                      int(r.randint(0, 30)), otherwise=otherwise,
+                                      resolve_network=resolve)
+            returned = [then, otherwise]
+        allowed = [s for s in sids if s in returned or r.uniform() < 0.3]
+        if r.uniform() < 0.1:  # a handler that may return a stage outside next_stages
+            allowed = [s for s in allowed if s != returned[-1]] or [sids[0]]
+        stages.append(ph.FSMStage(stage_id=sid, acting_agents=acting, rewarded_agents=rewarded,
+                                  next_stages=allowed, handler=handler))
+    env = ph.FiniteStateMachineEnv(num_steps=8, network=K.finish_network(network),
+                                   initial_stage=sids[int(r.randint(len(sids)))], stages=stages, **kw)
+    return env, strat, echo
+
+
+def run_random_handler_fsm(K, case_seed):
+    """Steps the random FSM to the end of its episode (or its first exception) and returns a
+    plain-Python trace that is comparable across implementations."""
+    env, strat, echo = random_handler_fsm(K, case_seed)
+
+    def plain(d):
+        return {k: (None if v is None else
+                    [round(float(x), 6) for x in np.asarray(v, np.float64).reshape(-1)])
+                for k, v in d.items()}
+
+    obs, _ = env.reset()
+    trace = [("reset", str(env.current_stage), plain(obs))]
+    for t in range(8):
+        try:
+            step = env.step({a: np.array([0]) for a in strat})
+        except Exception as exc:  # the implementations must agree on the exception type too
+            trace.append(("raise", type(exc).__name__))
+            break
+        trace.append((
+            "step", str(env.current_stage), plain(step.observations), plain(step.rewards),
+            {k: bool(v) for k, v in step.terminations.items()},
+            {k: bool(v) for k, v in step.truncations.items()},
+            [list(map(int, counts(env.agents[a]))) for a in strat],
+            [[int(env.agents[e].handled_count), int(env.agents[e].handled_total)] for e in echo]))
+        if step.terminations["__all__"] or step.truncations["__all__"]:
+            break
+    if hasattr(env, "close"):
+        env.close()
+    return trace

@@ -144,3 +144,22 @@ def test_python_stage_handler_is_not_lowerable(K):
                             handler=lambda e: "X")])
     with pytest.raises(ph.NotLowerableError):
         env.reset()
+
+
+@pytest.mark.parametrize("exec_mode", ["thread", "queue"])
+def test_random_handler_fsms_match_the_reference(K, exec_mode, monkeypatch):
+    """Differential fuzz of handler-driven FSM transitions on the device: 40 random
+    FiniteStateMachineEnvs (tests/kat_scenarios.py:random_handler_fsm -- random stage tables,
+    StageRules on the clock / echo-agent counters, invalid transitions, agents terminating
+    mid-episode) == the traces of the UNMODIFIED reference running the same case seeds with
+    Python handlers (tests/golden/fsm_handler_fuzz_reference.json)."""
+    import json
+    import os
+
+    monkeypatch.setattr(K.ph.PhantomEnv, "default_exec_mode", exec_mode)
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden",
+                        "fsm_handler_fuzz_reference.json")
+    want = json.load(open(path))
+    for s in range(len(want)):
+        got = json.loads(json.dumps(kats.run_random_handler_fsm(K, s)))
+        assert got == want[str(s)], f"case seed {s}"

@@ -45,3 +45,20 @@ def test_handler_kats_on_the_unmodified_reference():
     out = subprocess.run([sys.executable, "-c", code], cwd=repo, capture_output=True, text=True,
                          timeout=300)
     assert out.returncode == 0 and "reference ok" in out.stdout, out.stderr[-2000:]
+
+
+def test_random_handler_fsms_match_the_reference(K):
+    """Differential fuzz of the FSM env-handler path (fsm.py:294-307): 40 random
+    FiniteStateMachineEnvs (tests/kat_scenarios.py:random_handler_fsm) on the oracle port ==
+    the traces the UNMODIFIED reference produced for the same case seeds
+    (tests/golden/fsm_handler_fuzz_reference.json, oracle/make_golden.py)."""
+    import json
+    import os
+
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden",
+                        "fsm_handler_fuzz_reference.json")
+    want = json.load(open(path))
+    assert len(want) == 40 and sum(t[-1][0] == "raise" for t in want.values()) >= 2
+    for s in range(len(want)):
+        got = json.loads(json.dumps(kats.run_random_handler_fsm(K, s)))
+        assert got == want[str(s)], f"case seed {s}"
