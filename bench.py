@@ -1,15 +1,22 @@
 #!/usr/bin/env python
-"""bench.py -- env-steps/s of the supply-chain hot path (BASELINE config C2).
+"""bench.py -- env-steps/s of the env-step hot path on the BASELINE configs.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--configs C2,C3,C4,C5]
 
-Workload: 65 536 parallel supply-chain envs per GPU (8 agent slots, 7 used), 100-step
-episodes, synthetic uniform actions.  One bench "step" = ONE launch of the fused step
-kernel through the C ABI (`phx_rollout`, T = 100 env transitions per env, auto-reset at the
-episode boundary) = 6 553 600 env-steps per GPU.  See DESIGN.md "Measurement".
+Headline (the JSON line's top-level keys) = BASELINE config C2: 65 536 parallel supply-chain
+envs per GPU (8 agent slots, 7 used), 100-step episodes, synthetic uniform actions.  One bench
+"step" = ONE launch of the fused step kernel through the C ABI (`phx_rollout`, T = 100 env
+transitions per env, auto-reset at the episode boundary) = 6 553 600 env-steps per GPU.  The K
+timed launches are captured in one CUDA graph (no launch gaps inside the timed region).
 
-Prints ONE JSON line (rank 0).  Keys follow the driver contract; `roofline`,
-`cpu_baseline`, `e2e`, `clocks`, `gpu_launches` are described in DESIGN.md.
+`configs` holds one sub-record per further BASELINE config -- C3 (3-stage FSM market, 32 768
+envs x 32 agents), C4 (Stackelberg, 131 072 envs x 4 agents, sharded over the N GPUs), C5
+(dense graph, 16 384 envs x 128 agents, sharded) -- each with its own kernel, roofline,
+cpu_baseline and e2e.  See DESIGN.md "Measurement".
+
+Prints ONE JSON line (rank 0).  Keys follow the driver contract; `roofline`, `cpu_baseline`,
+`e2e`, `clocks`, `gpu_launches`, `configs`, `gather` are described in DESIGN.md.
 """
 from __future__ import annotations
 
@@ -28,12 +35,56 @@ REPO = os.path.dirname(os.path.abspath(__file__))
 if REPO not in sys.path:
     sys.path.insert(0, REPO)
 
-E_PER_GPU = 65536
-T_EPISODE = 100
 SEED = 0
-# algorithmic HBM bytes: per env-step I/O and per-launch state traffic
-B_IO = 4 + 12 + 4 + 2  # action f32, obs 3 x f32, reward f32, all_done 2 x u8
-B_STATE = 2 * (8 + 16)  # header (step, episode) + shop state, read once + written once
+REF_COPY = os.path.join(REPO, "baseline", "_ref")  # unmodified reference sources (git-ignored)
+
+# ------------------------------------------------------------------------------ configs
+# Algorithmic HBM bytes: bytes per launch = E * (T * b_io + b_state);
+#   b_io    per env-step: actions + every output plane the launch writes
+#   b_state per env and launch: persisted state, read once + written once
+CONFIGS = {
+    "C2": dict(
+        workload=("supply-chain C2: 65536 envs/GPU x 8 agent slots (7 used), 100-step episodes; "
+                  "one bench step = one phx_rollout launch = 100 env transitions per env, "
+                  "auto-reset at the episode end"),
+        E=65536, scaling="weak", T=100, S=1, O=3, lean=True, act_scale=100.0, binary_from=None,
+        b_io=4 + 12 + 4 + 2, b_state=2 * (8 + 16), nbuf=4),
+    "C3": dict(
+        workload=("FSM market C3: 32768 envs/GPU x 32 agents (7 makers + 24 takers strategic + "
+                  "clearing), 3 stages, 99-step episodes; one bench step = one phx_rollout launch "
+                  "= 99 transitions per env, auto-reset"),
+        E=32768, scaling="weak", T=99, S=31, O=3, lean=False, act_scale=1.0, binary_from=7,
+        b_io=31 * (4 + 12 + 4 + 4) + 2, b_state=2 * (16 + 8 + 32 * (8 * 4 + 4 + 12) + 8), nbuf=2),
+    "C4": dict(
+        workload=("Stackelberg C4: 131072 envs in total (sharded over the GPUs) x 4 agents, "
+                  "100-step episodes; one bench step = one phx_rollout launch = 100 transitions "
+                  "per env, auto-reset"),
+        E=131072, scaling="strong", T=100, S=4, O=2, lean=False, act_scale=1.0, binary_from=None,
+        b_io=4 * (4 + 8 + 4 + 4) + 2, b_state=2 * (16 + 8 + 8 * (16 + 4) + 4), nbuf=2),
+    "C5": dict(
+        workload=("dense graph C5: 16384 envs in total (sharded over the GPUs) x 128 agents, "
+                  "complete graph, BatchResolver(round_limit=2), 16 256 + 128 messages per step, "
+                  "8-step episodes; one bench step = one phx_rollout launch = 8 transitions per "
+                  "env, auto-reset"),
+        E=16384, scaling="strong", T=8, S=128, O=3, lean=False, act_scale=1.0, binary_from=None,
+        b_io=128 * (4 + 12 + 4 + 4) + 2, b_state=2 * (16 + 6 * 128 * 4), nbuf=2),
+}
+
+
+def make_env(name, **kw):
+    if name == "C2":
+        from phantom_b200.envs.supply_chain import SupplyChainEnv
+        return SupplyChainEnv(**kw)
+    if name == "C3":
+        from phantom_b200.envs.market import MarketEnv
+        return MarketEnv(**kw)
+    if name == "C4":
+        from phantom_b200.envs.stackelberg_game import StackelbergGameEnv
+        return StackelbergGameEnv(**kw)
+    if name == "C5":
+        from phantom_b200.envs.dense import DenseEnv
+        return DenseEnv(**kw)
+    raise ValueError(name)
 
 
 # ------------------------------------------------------------------------------ helpers
@@ -58,11 +109,6 @@ def port_calibration():
         return None
 
 
-WORKLOAD = ("supply-chain C2: 65536 envs/GPU x 8 agent slots (7 used), 100-step episodes; "
-            "one bench step = one phx_rollout launch = 100 env transitions per env, "
-            "auto-reset at the episode end")
-
-
 def measured_peak_gbs():
     try:
         with open(os.path.join(REPO, "MEASURED_PEAKS.json")) as f:
@@ -71,8 +117,18 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def cpu_model():
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                return ln.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled while the timed regions run."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -85,7 +141,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={self.Q}",
-                 "--format=csv,noheader,nounits", "-lms", "50"],
+                 "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -129,62 +185,366 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-# ------------------------------------------------------------------- CPU baseline (port)
-def _cpu_worker(args):
-    """Steps one oracle env (the Python restatement of the reference loop, which runs at the
-    reference's own speed: same object graph, same per-message work) for `seconds`."""
-    worker, seconds = args
-    import oracle.phantom_oracle as po
-    from oracle import harness, rng
-    from oracle.workloads import supply_chain as wl
+# ----------------------------------------------------------------- CPU arms (host cores)
+class _NativeStream:
+    """The reference draws from process-global numpy generators; the TIMED baselines keep that
+    ('the timed baseline runs without the patch')."""
 
-    st = wl.order_stream(SEED, worker)
-    env = wl.build(po, st)
-    clock = harness.EpisodeClock([st])
-    acts = np.random.RandomState(worker).uniform(0, 100, size=(T_EPISODE, 1)).astype(np.float32)
-    clock.on_reset(); env.reset()
-    for t in range(20):  # warm-up
-        clock.on_step(env); env.step({"SHOP": acts[t]})
-    clock.on_reset(); env.reset()
+    def randint(self, n):
+        return int(np.random.randint(n))
+
+
+def _reference_module():
+    """The UNMODIFIED reference, imported from baseline/_ref (a copy of /root/reference's
+    phantom/ + examples/ made by __graft_entry__.build(); it travels to the GPU box) through
+    the third-party stub shim.  None if the copy is absent."""
+    root = REF_COPY if os.path.isdir(os.path.join(REF_COPY, "phantom")) else None
+    if root is None and os.path.isdir("/root/reference/phantom"):
+        root = "/root/reference"
+    if root is None:
+        return None, None
+    os.environ["PHX_REFERENCE_ROOT"] = root
+    from oracle import ref_shim
+
+    ref_shim.REFERENCE_ROOT = root
+    return ref_shim.import_reference(), ref_shim
+
+
+def _cpu_env(kind: str, cfg: str, worker: int):
+    """(env, step_fn(t), T): one env object of config `cfg` on the reference (`kind` =
+    "reference") or on the oracle port, with its pre-generated action tape."""
+    r = np.random.RandomState(1000 + worker)
+    if kind == "reference":
+        ph, shim = _reference_module()
+        assert ph is not None, "baseline/_ref is absent"
+    else:
+        import oracle.phantom_oracle as ph
+    if cfg == "C2":
+        T = 100
+        acts = r.uniform(0, 100, size=(T, 1)).astype(np.float32)
+        if kind == "reference":  # the reference's own example file, imported unmodified
+            env = shim.import_reference_supply_chain().SupplyChainEnv()
+        else:
+            from oracle.workloads import supply_chain as wl
+            env = wl.build(ph, _NativeStream())
+        return env, (lambda t: env.step({"SHOP": acts[t]})), T
+    if cfg == "C3":
+        from oracle.workloads import market as wl
+        T = 99
+        env = wl.build(ph, _NativeStream(), num_steps=T)
+        ids = env.strategic_agent_ids
+        a = r.uniform(0, 1, size=(T, len(ids), 1)).astype(np.float32)
+        tape = [{aid: (a[t, s] if s < wl.N_MAKERS else int(a[t, s, 0] > 0.4))
+                 for s, aid in enumerate(ids)} for t in range(T)]
+    elif cfg == "C4":
+        from oracle.workloads import stackelberg as wl
+        T = 100
+        env = wl.build(ph, _NativeStream(), num_steps=T)
+        ids = env.strategic_agent_ids
+        a = r.uniform(0, 1, size=(T, len(ids), 1)).astype(np.float32)
+        tape = [{aid: a[t, s] for s, aid in enumerate(ids)} for t in range(T)]
+    elif cfg == "C5":
+        from oracle.workloads import dense as wl
+        T = 8
+        env = wl.build(ph, num_steps=T)
+        ids = env.strategic_agent_ids
+        a = r.uniform(0, 1, size=(T, len(ids), 1)).astype(np.float32)
+        tape = [{aid: a[t, s] for s, aid in enumerate(ids)} for t in range(T)]
+    else:
+        raise ValueError(cfg)
+    return env, (lambda t: env.step(tape[t])), T
+
+
+def _cpu_worker(args):
+    """Steps ONE env object for `seconds` (whole episodes incl. reset) and returns
+    (env-steps, elapsed).  One process = one core."""
+    kind, cfg, worker, seconds, warm_steps = args
+    os.environ.setdefault("PYTHONHASHSEED", "1")
+    env, step, T = _cpu_env(kind, cfg, worker)
+    env.reset()
+    for t in range(min(warm_steps, T)):
+        step(t)
+    env.reset()
     n, t0 = 0, time.perf_counter()
     while True:
-        for t in range(T_EPISODE):
-            clock.on_step(env)
-            env.step({"SHOP": acts[t]})
-        n += T_EPISODE
-        clock.on_reset(); env.reset()
+        for t in range(T):
+            step(t)
+        n += T
+        env.reset()
         if time.perf_counter() - t0 >= seconds:
             break
     return n, time.perf_counter() - t0
 
 
-def cpu_baseline(seconds: float, cores: int):
+def cpu_rate(kind: str, cfg: str, seconds: float, cores: int, warm_steps: int = 20):
+    """Aggregate env-steps/s of `cores` processes, each stepping its own env object."""
     ctx = mp.get_context("spawn")
     with ctx.Pool(cores) as pool:
         t0 = time.perf_counter()
-        res = pool.map(_cpu_worker, [(w, seconds) for w in range(cores)])
+        res = pool.map(_cpu_worker, [(kind, cfg, w, seconds, warm_steps) for w in range(cores)])
         wall = time.perf_counter() - t0
-    steps = sum(n for n, _ in res)
-    rate = sum(n / dt for n, dt in res)
-    cal = port_calibration()
-    return {
-        "value": rate, "unit": "env-steps/s", "cores": cores, "kind": "port",
-        "sample": (f"{cores} processes x {seconds:.0f} s of 100-step supply-chain episodes on "
-                   f"oracle.phantom_oracle (Python restatement of PhantomEnv.step; the "
-                   f"reference itself is Python and cannot travel to the GPU box), "
-                   f"{steps} env-steps, wall {wall:.1f} s"),
-        # the port runs this loop `port_over_reference` times as fast as the unmodified
-        # reference on one core of the build container (tests/golden/port_calibration.json)
-        "port_over_reference": cal,
-    }
+    return sum(n / dt for n, dt in res), sum(n for n, _ in res), wall
+
+
+def cpu_kind():
+    """"reference" when the unmodified reference's sources are present (baseline/_ref, or
+    /root/reference in the build container); the import itself happens in the worker processes."""
+    return ("reference" if os.path.isdir(os.path.join(REF_COPY, "phantom")) or
+            os.path.isdir("/root/reference/phantom") else "port")
+
+
+def cpu_baseline(cfg: str, seconds: float, cores: int, kind=None):
+    kind = kind or cpu_kind()
+    rate, steps, wall = cpu_rate(kind, cfg, seconds, cores)
+    what = ("the UNMODIFIED reference (baseline/_ref, imported through oracle/ref_shim.py; "
+            "native np.random)" if kind == "reference" else
+            "oracle.phantom_oracle (Python restatement of PhantomEnv.step; baseline/_ref absent)")
+    out = {"value": rate, "unit": "env-steps/s", "cores": cores, "kind": kind,
+           "sample": (f"{cores} processes x {seconds:.0f} s, one env object each, whole "
+                      f"{CONFIGS[cfg]['T']}-step episodes incl. reset, on {what}; {steps} "
+                      f"env-steps, wall {wall:.1f} s"),
+           "cpu_model": cpu_model()}
+    if kind == "port":
+        out["port_over_reference"] = port_calibration()
+    return out
+
+
+def cpu_single_core(cfg: str, kind: str, windows: int = 5, seconds: float = 2.0):
+    """one env object, one core, median of `windows` timed windows after a
+    200-step warm-up."""
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(1) as pool:
+        res = [pool.apply(_cpu_worker, ((kind, cfg, 0, seconds, 200),)) for _ in range(windows)]
+    rates = sorted(n / dt for n, dt in res)
+    return {"value": rates[len(rates) // 2], "unit": "env-steps/s", "cores": 1, "kind": kind,
+            "windows": windows, "min": rates[0], "max": rates[-1]}
 
 
 # ----------------------------------------------------------------------------- our arm
+def _timed_launches(torch, dev, launch, K: int, W: int, world: int):
+    """W warm-up launches, then EXACTLY K launches timed with CUDA events on the launch stream.
+    The K launches are captured into CUDA graphs of up to 1000 nodes (launch i uses buffer set
+    i % NBUF, baked into the node), so the timed region holds no host launch gaps; falls back
+    to eager launches if the capture is refused."""
+    import torch.distributed as dist
+
+    for i in range(W):
+        launch(i, torch.cuda.current_stream(dev).cuda_stream)
+    torch.cuda.synchronize()
+    glen = min(K, 1000)
+    graph, mode = None, "eager"
+    try:
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side, capture_error_mode="relaxed"):
+            for i in range(glen):
+                launch(W + i, torch.cuda.current_stream(dev).cuda_stream)
+        g.replay()
+        torch.cuda.synchronize()
+        graph, mode = g, f"cuda-graph({glen} launches per replay)"
+    except Exception:
+        torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    done = 0
+    if graph is not None:
+        for _ in range(K // glen):
+            graph.replay()
+        done = (K // glen) * glen
+    for i in range(done, K):
+        launch(W + i, torch.cuda.current_stream(dev).cuda_stream)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms, mode
+
+
+def run_config(name, args, torch, dev, rank, world, local):
+    """Device-timed launches + e2e (host buffers) of one config on this rank's shard.  Returns
+    the sub-record pieces (rank 0 assembles)."""
+    import torch.distributed as dist
+
+    from phantom_b200 import _lib as L
+
+    c = CONFIGS[name]
+    T, S, O = c["T"], c["S"], c["O"]
+    if c["scaling"] == "weak":
+        E, offset = c["E"], rank * c["E"]
+    else:
+        E, offset = c["E"] // world, rank * (c["E"] // world)
+    env = make_env(name, num_envs=E, seed=SEED, device=local, env_offset=offset, auto_reset=True)
+    env.reset_batch()
+    NBUF = c["nbuf"]
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    acts, outs = [], []
+    for _ in range(NBUF):
+        a = torch.rand((T, E, S, 1), generator=gen, device=dev)
+        if c["binary_from"] is not None:
+            a[:, :, c["binary_from"]:] = (a[:, :, c["binary_from"]:] > 0.4).float()
+        if c["act_scale"] != 1.0:
+            a *= c["act_scale"]
+        acts.append(a)
+        outs.append(env._alloc_outputs((T,)))
+    lean = c["lean"]
+
+    def launch(i, stream):
+        o = outs[i % NBUF]
+        p = lambda t: None if lean else t.data_ptr()
+        L.check(L.lib.phx_rollout(env._handle, T, acts[i % NBUF].data_ptr(), None,
+                                  o.observations.data_ptr(), p(o.obs_mask), o.rewards.data_ptr(),
+                                  p(o.reward_mask), p(o.terminations), p(o.truncations),
+                                  o.all_done.data_ptr(), stream))
+
+    K = args.steps if name == "C2" else max(3, min(args.steps, args.sub_steps))
+    W = args.warmup if name == "C2" else max(3, min(args.warmup, 5))
+    ms, mode = _timed_launches(torch, dev, launch, K, W, world)
+    env.check_errors()
+    rec = {"E": E, "T": T, "K": K, "W": W, "ms": ms, "mode": mode, "kernel": env.exec_name,
+           "env": env, "acts": acts, "outs": outs}
+    if args.timed_only:
+        return rec
+
+    # ---- e2e: the same metric through the host-buffer C-ABI call (pinned host memory, H2D of
+    # the actions and D2H of every output plane the device-timed launch writes, inside the call)
+    e2e_steps = max(3, min(K, 12)) if name == "C2" else 3
+    pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()
+    h_act = pin((T, E, S, 1), torch.float32)
+    h_act.copy_(acts[0].cpu())
+    h_obs, h_rew = pin((T, E, S, O), torch.float32), pin((T, E, S), torch.float32)
+    h_all = pin((T, E, 2), torch.uint8)
+    h_u8 = [None] * 4 if lean else [pin((T, E, S), torch.uint8) for _ in range(4)]
+    hp = lambda t: None if t is None else t.data_ptr()
+
+    def launch_host():
+        L.check(L.lib.phx_rollout_host(env._handle, T, h_act.data_ptr(), None, h_obs.data_ptr(),
+                                       hp(h_u8[0]), h_rew.data_ptr(), hp(h_u8[1]), hp(h_u8[2]),
+                                       hp(h_u8[3]), h_all.data_ptr()))
+
+    for _ in range(2):
+        launch_host()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        launch_host()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    env.check_errors()
+    rec.update(e2e_s=e2e_s, e2e_steps=e2e_steps, h2d=h_act.numel() * 4,
+               d2h=(h_obs.numel() * 4 + h_rew.numel() * 4 + h_all.numel() +
+                    sum(t.numel() for t in h_u8 if t is not None)))
+    del h_act, h_obs, h_rew, h_all, h_u8
+    return rec
+
+
+def config_record(name, rec, world, peak, peak_src, with_cpu, args):
+    c = CONFIGS[name]
+    E, T, K = rec["E"], rec["T"], rec["K"]
+    launch_ms = rec["ms"] / K
+    value = world * E * T * K / (rec["ms"] * 1e-3)
+    bytes_per_launch = E * (T * c["b_io"] + c["b_state"])
+    achieved = bytes_per_launch / (launch_ms * 1e-3) / 1e9
+    out = {
+        "workload": c["workload"], "kernel": rec["kernel"], "envs_per_gpu": E,
+        "transitions_per_launch": T, "scaling": c["scaling"], "steps": K, "warmup": rec["W"],
+        "value": value, "unit": "env-steps/s", "ms_per_step": launch_ms, "timing": rec["mode"],
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "algorithmic_bytes_per_launch": bytes_per_launch,
+                     "algorithmic_bytes_per_env_step": c["b_io"] + c["b_state"] / T,
+                     "peak_source": peak_src},
+    }
+    if "e2e_s" in rec:
+        e2e_value = world * E * T * rec["e2e_steps"] / rec["e2e_s"]
+        out["e2e"] = {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": rec["h2d"],
+                      "d2h_bytes_per_step": rec["d2h"], "steps": rec["e2e_steps"],
+                      "api": "phx_rollout_host (pinned host buffers)"}
+    if with_cpu:
+        out["cpu_baseline"] = cpu_baseline(name, args.cpu_seconds if name == "C2" else
+                                           args.sub_cpu_seconds, os.cpu_count() or 1)
+    return out
+
+
+def bench_gather(torch, dev, env, acts, rank, world, T, E):
+    """The trainer gather in the path: every launch writes its lean planes
+    straight into a packed block (sharding.PackedOutputs) and ONE NCCL collective per launch
+    moves it, double-buffered so that the collective of launch i overlaps the kernel of launch
+    i+1.  Timed on the device, max over ranks."""
+    import torch.distributed as dist
+
+    from phantom_b200.sharding import LEAN_PLANES, PackedOutputs, gather_packed
+
+    total = world * E
+    res = {}
+    for label, lead_T, dst in (("rollout_T100_allgather", T, None), ("rollout_T100_gather0", T, 0),
+                               ("step_T1_allgather", None, None)):
+        packed = [PackedOutputs.for_env(env, lead_T, LEAN_PLANES, total_envs=total,
+                                        world_size=world) for _ in range(2)]
+        recv = [torch.empty((world, packed[0].nbytes), dtype=torch.uint8, device=dev)
+                if (dst is None or rank == dst) else None for _ in range(2)]
+        n_launch = 10 if lead_T else 100
+        pending = [None, None]
+
+        def one(i):
+            b = i % 2
+            if pending[b] is not None:
+                pending[b].wait()
+            a = acts[i % len(acts)]
+            packed[b].launch(env, a if lead_T else a[i % T])
+            g = gather_packed(packed[b], total, dst=dst, out=recv[b], async_op=True)
+            pending[b] = g
+
+        for i in range(3):
+            one(i)
+        for p in pending:
+            if p is not None:
+                p.wait()
+        pending[:] = [None, None]
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n_launch):
+            one(i)
+        for p in pending:
+            if p is not None:
+                p.wait()
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        steps_per_launch = lead_T or 1
+        nbytes = packed[0].nbytes
+        # bytes ENTERING the busiest GPU per launch: (world - 1) blocks
+        rx = (world - 1) * nbytes
+        res[label] = {
+            "us_per_launch": ms * 1e3 / n_launch, "launches": n_launch,
+            "block_bytes_per_rank": nbytes,
+            "value_with_gather": world * E * steps_per_launch * n_launch / (ms * 1e-3),
+            "unit": "env-steps/s", "rx_bytes_per_launch": rx,
+            "rx_GBps": rx * n_launch / (ms * 1e-3) / 1e9,
+            "nvlink_peak_GBps": 770.0,  # measured peer-copy rate per direction (B200_PROFILING.md)
+            "collective": "ncclAllGather" if dst is None else "ncclGather(dst=0) = grouped send/recv",
+        }
+        env.check_errors()
+    return res
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
-
-    from phantom_b200.envs.supply_chain import SupplyChainEnv
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -207,53 +567,24 @@ def run_ours(args):
                 os.sched_setaffinity(0, cpus)
         except Exception:
             pass
+    # host threads of the e2e path (compact-wire expansion inside phx_rollout_host): an equal
+    # share of the cores this rank may run on
+    os.environ.setdefault("PHX_HOST_THREADS",
+                          str(max(1, min(32, len(os.sched_getaffinity(0)) // max(world, 1)))))
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    E, T = E_PER_GPU, T_EPISODE
-    env = SupplyChainEnv(num_envs=E, seed=SEED, device=local, env_offset=rank * E,
-                         auto_reset=True)
-    env.reset_batch()
-
-    # inputs larger than L2: NBUF independent action / output sets (each 26 + 118 MB) are
-    # cycled, so a launch never finds its inputs or output lines in the 126 MB L2
-    NBUF = 4
-    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-    acts = [torch.rand((T, E, 1, 1), generator=gen, device=dev) * 100.0 for _ in range(NBUF)]
-    outs = [env._alloc_outputs((T,)) for _ in range(NBUF)]
-    # the base env never terminates agents early: the four per-agent mask planes are
-    # constant, so the trainer-facing outputs are obs, reward and all_done
     from phantom_b200 import _lib as L
-    import ctypes as C
 
-    stream = torch.cuda.current_stream(dev).cuda_stream
-
-    def launch(i):
-        o = outs[i % NBUF]
-        L.check(L.lib.phx_rollout(env._handle, T, acts[i % NBUF].data_ptr(), None,
-                                  o.observations.data_ptr(), None, o.rewards.data_ptr(), None,
-                                  None, None, o.all_done.data_ptr(), stream))
-
-    for i in range(args.warmup):
-        launch(i)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-        torch.cuda.synchronize()
-
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    names = [n for n in args.configs.split(",") if n in CONFIGS]
+    if "C2" not in names:
+        names.insert(0, "C2")
+    recs = {}
     with ClockSampler(local) as clocks:
-        ev0.record()
-        for i in range(args.steps):
-            launch(i)
-        ev1.record()
-        torch.cuda.synchronize()
-    ms = ev0.elapsed_time(ev1)
-    if world > 1:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    env.check_errors()
+        head = run_config("C2", args, torch, dev, rank, world, local)
+    recs["C2"] = head
+    env, acts, outs = head["env"], head["acts"], head["outs"]
+    E, T = head["E"], head["T"]
 
     # ---- single-step API (SURVEY 8(d) asks for both): T = 1 phx_step calls, 100 of them
     # captured into one CUDA graph (a trainer that steps every env once per policy forward),
@@ -289,129 +620,141 @@ def run_ours(args):
         g1.record()
         torch.cuda.synchronize()
         us = g0.elapsed_time(g1) * 1e3 / (reps * T)
+        c2 = CONFIGS["C2"]
         single = {"api": "phx_step, T=1, 100 launches per CUDA graph", "us_per_launch": us,
                   "value": E / (us * 1e-6), "unit": "env-steps/s",
-                  "bytes_per_launch": E * (B_IO + B_STATE)}
+                  "bytes_per_launch": E * (c2["b_io"] + c2["b_state"])}
         env.check_errors()
         env.reset_batch()
 
-    # ---- e2e: same metric through the host-buffer C-ABI call (pinned host memory, H2D of
-    # the actions and D2H of obs / reward / all_done inside the timed region)
-    if args.timed_only:  # profiling aid: only the device-timed region (see tools/profile_round.sh)
+    if args.timed_only:  # profiling aid: only the device-timed region (tools/profile_round.sh)
         if rank == 0:
-            print(json.dumps({"timed_only": True, "ms_per_step": ms / args.steps,
-                              "gpu_launches": args.steps}), flush=True)
+            print(json.dumps({"timed_only": True, "ms_per_step": head["ms"] / head["K"],
+                              "gpu_launches": head["K"]}), flush=True)
         env.close()
         if world > 1:
             dist.destroy_process_group()
         return
-    e2e_steps = max(3, min(args.steps, 12))
-    h_act = torch.empty((T, E, 1, 1), dtype=torch.float32).pin_memory()
-    h_act.copy_(acts[0].cpu())
-    h_obs = torch.empty((T, E, 1, 3), dtype=torch.float32).pin_memory()
-    h_rew = torch.empty((T, E, 1), dtype=torch.float32).pin_memory()
-    h_all = torch.empty((T, E, 2), dtype=torch.uint8).pin_memory()
 
-    def launch_host():
-        L.check(L.lib.phx_rollout_host(env._handle, T, h_act.data_ptr(), None, h_obs.data_ptr(),
-                                       None, h_rew.data_ptr(), None, None, None,
-                                       h_all.data_ptr()))
-
-    for _ in range(2):
-        launch_host()
+    gather = None
     if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        launch_host()
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    env.check_errors()
-    h2d = h_act.numel() * 4
-    d2h = h_obs.numel() * 4 + h_rew.numel() * 4 + h_all.numel()
+        try:
+            gather = bench_gather(torch, dev, env, acts, rank, world, T, E)
+        except Exception as exc:  # never lose the headline to the secondary measurement
+            gather = {"error": repr(exc)}
+    env.close()
+    del head["env"], head["acts"], head["outs"], env, acts, outs
+    torch.cuda.empty_cache()
 
-    env_steps_per_launch = E * T
-    value = world * env_steps_per_launch * args.steps / (ms * 1e-3)
-    e2e_value = world * env_steps_per_launch * e2e_steps / e2e_s
+    sub_clocks = {}
+    for name in names:
+        if name == "C2":
+            continue
+        try:
+            with ClockSampler(local) as ck:
+                r = run_config(name, args, torch, dev, rank, world, local)
+            r["env"].close()
+            del r["env"], r["acts"], r["outs"]
+            torch.cuda.empty_cache()
+            recs[name] = r
+            sub_clocks[name] = ck.summary()
+        except Exception as exc:
+            recs[name] = {"error": repr(exc)}
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
         traffic, traffic_src = ncu_traffic()
-        bytes_per_launch = E * (T * B_IO + B_STATE)
-        launch_ms = ms / args.steps
-        achieved = bytes_per_launch / (launch_ms * 1e-3) / 1e9
+        with_cpu = world == 1 and not args.no_cpu_baseline
+        c2 = config_record("C2", head, world, peak, peak_src, with_cpu, args)
+        nb = CONFIGS["C2"]["nbuf"]
         line = {
             "metric": "env-steps/sec (65k parallel supply-chain envs)",
-            "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": launch_ms, "higher_is_better": True,
+            "value": c2["value"], "unit": "env-steps/s", "n_gpus": world, "steps": head["K"],
+            "warmup": head["W"], "ms_per_step": c2["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
             "config": {
-                "workload": WORKLOAD,
-                "envs_per_gpu": E, "transitions_per_launch": T, "kernel": env.exec_name,
-                "l2": f"inputs larger than L2: {NBUF} rotating action/output sets of "
-                      f"{(acts[0].numel() * 4 + bytes_per_launch) / 1e6:.0f} MB",
+                "workload": c2["workload"],
+                "envs_per_gpu": E, "transitions_per_launch": T, "kernel": c2["kernel"],
+                "l2": f"inputs larger than L2: {nb} rotating action/output sets of "
+                      f"{(E * T * 4 + c2['roofline']['algorithmic_bytes_per_launch']) / 1e6:.0f} MB",
+                "timing": c2["timing"],
                 "parallelism": f"env-sharded x{world}, no data-path collective",
             },
-            "roofline": {
-                "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
-                "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": bytes_per_launch,
-                "kernel": "sc_fast_kernel<5,false>",
-            },
-            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                    "api": "phx_rollout_host (pinned host buffers)",
-                    # the link that bounds it: device->host rate of one rank's result rows
-                    # (profiles/r01_pcie_peak.json: plain pinned D2H of this size = 56.3 GB/s)
-                    "bound": "pcie d2h",
-                    "d2h_GBps_per_gpu": d2h * e2e_value / (world * E * T) / 1e9},
+            "roofline": dict(c2["roofline"], traffic=traffic, traffic_source=traffic_src,
+                             kernel="sc_fast_kernel"),
+            "e2e": dict(c2["e2e"], bound="pcie / host expansion",
+                        d2h_GBps_per_gpu=c2["e2e"]["d2h_bytes_per_step"] * c2["e2e"]["value"] /
+                        (world * E * T) / 1e9,
+                        host_threads=int(os.environ.get("PHX_HOST_THREADS", "1"))),
             "single_step": single,
-            # kernels of ours inside the device-timed region (one sc_fast_kernel per bench step);
-            # the e2e region launches one kernel per pipeline chunk (8 per call)
-            "gpu_launches": args.steps,
-            "gpu_launches_e2e": e2e_steps * 8,
+            # kernels of ours inside the device-timed region (one per bench step); the e2e region
+            # launches one kernel per pipeline chunk (8 per call)
+            "gpu_launches": head["K"],
+            "gpu_launches_e2e": head["e2e_steps"] * 8,
             "clocks": clocks.summary(),
         }
-        if world == 1 and not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
-            line["cpu_baseline"] = cpu_baseline(args.cpu_seconds, cores)
+        if "cpu_baseline" in c2:
+            line["cpu_baseline"] = c2["cpu_baseline"]
+        if gather is not None:
+            line["gather"] = gather
+        subs = {}
+        for name in names:
+            if name == "C2":
+                continue
+            r = recs[name]
+            if "error" in r:
+                subs[name] = r
+                continue
+            subs[name] = config_record(name, r, world, peak, peak_src, with_cpu, args)
+            subs[name]["clocks"] = sub_clocks.get(name)
+            line["gpu_launches"] += r["K"]
+        line["configs"] = subs
         print(json.dumps(line), flush=True)
-    env.close()
     if world > 1:
         dist.destroy_process_group()
 
 
 # ---------------------------------------------------------------------- reference arm
 def run_reference(args):
+    """The reference's own CPU implementation of the path on the box's host cores: the
+    UNMODIFIED reference from baseline/_ref when present (kind "reference"), else the oracle
+    port.  Each "step" = one bounded all-core sample of cpu_seconds."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    # each "step" = a bounded sample: all cores stepping 100-step episodes for cpu_seconds
+    kind = cpu_kind()
     t0 = time.perf_counter()
-    rates = []
-    for _ in range(max(1, args.warmup and 1)):
-        cpu_baseline(min(2.0, args.cpu_seconds), cores)
-    for _ in range(max(1, min(args.steps, 3))):
-        rates.append(cpu_baseline(args.cpu_seconds, cores))
-    best = max(rates, key=lambda r: r["value"])
-    value = float(np.mean([r["value"] for r in rates]))
+    if args.warmup:
+        cpu_rate(kind, "C2", min(2.0, args.cpu_seconds), cores)
+    samples = [cpu_baseline("C2", args.cpu_seconds, cores, kind)
+               for _ in range(max(1, min(args.steps, 3)))]
+    best = max(samples, key=lambda r: r["value"])
+    value = float(np.mean([r["value"] for r in samples]))
+    single = cpu_single_core("C2", kind)
+    subs = {}
+    for name in [n for n in args.configs.split(",") if n in CONFIGS and n != "C2"]:
+        try:
+            subs[name] = {"workload": CONFIGS[name]["workload"],
+                          "cpu_baseline": cpu_baseline(name, args.sub_cpu_seconds, cores, kind)}
+            subs[name]["value"] = subs[name]["cpu_baseline"]["value"]
+        except Exception as exc:
+            subs[name] = {"error": repr(exc)}
     line = {
         "impl": "reference", "metric": "env-steps/sec (65k parallel supply-chain envs)",
-        "value": value, "unit": "env-steps/s", "n_gpus": args.gpus, "steps": len(rates),
-        "warmup": 1, "ms_per_step": args.cpu_seconds * 1e3, "higher_is_better": True,
+        "value": value, "unit": "env-steps/s", "n_gpus": args.gpus, "steps": len(samples),
+        "warmup": 1 if args.warmup else 0, "ms_per_step": args.cpu_seconds * 1e3,
+        "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "python-int", "data": "synthetic",
-        "config": {"workload": WORKLOAD,
-                   "cpu": f"same dynamics on the host: one env object per process, {cores} "
-                          f"processes, 100-step episodes incl. reset; each step = a "
-                          f"{args.cpu_seconds:.0f} s sample"},
+        "config": {"workload": CONFIGS["C2"]["workload"],
+                   "cpu": f"same dynamics on the host ({kind}): one env object per process, "
+                          f"{cores} processes, 100-step episodes incl. reset; each step = a "
+                          f"{args.cpu_seconds:.0f} s sample; {cpu_model()}"},
         "cpu_baseline": dict(best, value=value),
+        "single_core": single,
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
+        "configs": subs,
         "wall_s": time.perf_counter() - t0,
     }
     print(json.dumps(line), flush=True)
@@ -420,10 +763,14 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20000)
+    ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--configs", default="C2,C3,C4,C5")
+    ap.add_argument("--sub-steps", type=int, default=10,
+                    help="timed launches of the C3/C4/C5 sub-records (<= --steps)")
     ap.add_argument("--cpu-seconds", type=float, default=8.0)
+    ap.add_argument("--sub-cpu-seconds", type=float, default=4.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--timed-only", action="store_true",
                     help="profiling aid: run only the warm-up and the device-timed launches")

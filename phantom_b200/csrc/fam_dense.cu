@@ -259,6 +259,9 @@ __global__ void __launch_bounds__(DN_MAX) dense_step_kernel(const DenseArgs a) {
 
     // ---- outputs (env.py:273-303): every agent observes and is rewarded; nobody terminates
     const bool at_max = h.x == sp.num_steps;
+    // the reward belongs to the step that just ran: computed BEFORE an auto-reset clears the
+    // state (only the observation is replaced by the reset observation, as in the engines)
+    const float rew = (float)st[5] * (1.0f / 1024.0f);
     if ((sp.flags & PHX_FLAG_AUTO_RESET) && at_max) {
       h.x = 0;
       h.y += 1;
@@ -269,7 +272,6 @@ __global__ void __launch_bounds__(DN_MAX) dense_step_kernel(const DenseArgs a) {
     const float o0 = (float)st[1] * (1.0f / 131072.0f);  // powers of two: exact
     const float o1 = (float)st[2] * (1.0f / 1024.0f);
     const float o2 = (float)st[4] * (1.0f / 128.0f);
-    const float rew = (float)st[5] * (1.0f / 1024.0f);
     if (bulk) {
       // the previous use of this stage buffer (step t-2) must have been read out
       if (slot == 0) bulk_wait_read<1>();

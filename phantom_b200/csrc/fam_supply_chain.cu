@@ -26,8 +26,8 @@
 //    a step is data independent, so the routing rules are evaluated once per
 //    handle on the host (make_plan) into a static schedule, and the kernel executes the
 //    handler bodies in that order with the whole env state in registers.
-//  * (queue engine, fam_supply_chain_queue) -- any agent order / topology, messages routed
-//    dynamically through the shared-memory queue of phx_queue.cuh.
+//  * ScProgram below -- the same agents as a device program of the generic queue engines
+//    (phx_engine1.cuh / phx_engine.cuh): any agent order / topology, messages routed dynamically.
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -549,8 +549,10 @@ class SupplyChainFast final : public Family {
     a.T = T;
     a.env_begin = env_begin;
     a.env_count = env_count;
-    // the vector action copy reads 4 consecutive envs of one step with one 16-byte cp.async
-    a.vec_actions = (E % 4 == 0) && (env_begin % 4 == 0) && (env_count % 32 == 0) &&
+    // the vector action copy reads 4 consecutive envs of one step with one 16-byte cp.async; every
+    // warp of every block must be a full warp of real envs (a clamped warp would compute an
+    // unaligned source address), hence env_count % SC_BLOCK and not % 32
+    a.vec_actions = (E % 4 == 0) && (env_begin % 4 == 0) && (env_count % SC_BLOCK == 0) &&
                     (reinterpret_cast<uintptr_t>(io.actions) % 16 == 0);
     a.hdr = d_hdr;
     a.shop = d_shop;

@@ -225,7 +225,13 @@ int32_t phx_create(const phx_spec* spec, int32_t num_envs, int32_t device, uint6
     delete fam;
     return rc;
   }
-  *out = new (std::nothrow) phx_env{fam};
+  phx_env* h = new (std::nothrow) phx_env{fam};
+  if (h == nullptr) {
+    delete fam;
+    set_error("out of host memory allocating the env handle");
+    return PHX_ERR_INVALID;
+  }
+  *out = h;
   return PHX_OK;
 }
 
@@ -447,11 +453,14 @@ int32_t phx_reduce_field(phx_env* env, int32_t field, int32_t index, int32_t wid
   struct Acc { unsigned long long sum; int32_t mn, mx; } h{0ull, INT32_MAX, INT32_MIN};
   Acc* dacc = nullptr;
   PHX_CUDA(cudaMalloc(&dacc, sizeof(Acc)));
+  // steps issued on non-blocking streams are not ordered before the legacy default stream
+  PHX_CUDA(cudaDeviceSynchronize());
   PHX_CUDA(cudaMemcpy(dacc, &h, sizeof(Acc), cudaMemcpyHostToDevice));
   const int blocks = (f->E + 255) / 256 < 1184 ? (f->E + 255) / 256 : 1184;  // 8 blocks per SM
   phx_field_reduce_kernel<<<blocks, 256>>>((const int32_t*)d, f->E, width, col, &dacc->sum,
                                             &dacc->mn, &dacc->mx);
-  cudaError_t err = cudaMemcpy(&h, dacc, sizeof(Acc), cudaMemcpyDeviceToHost);
+  cudaError_t err = cudaGetLastError();
+  if (err == cudaSuccess) err = cudaMemcpy(&h, dacc, sizeof(Acc), cudaMemcpyDeviceToHost);
   cudaFree(dacc);
   PHX_CUDA(err);
   if (host_sum) *host_sum = (int64_t)h.sum;

@@ -167,14 +167,27 @@ class AggregatedAgentMetric(SimpleMetric):
 def logging_helper(env: PhantomEnv, metrics: Dict[str, Metric],
                    metric_values: DefaultDict[str, List[float]]) -> None:
     """metrics.py:355-370: record every metric whose FSM-stage filter matches the env's
-    current stage (batched FSM envs are stepped in lock step: env 0's stage is the stage)."""
+    current stage.  A batch of FSM envs need not be in lock step (handler-driven StageRule
+    transitions, auto-reset): when the stages differ across the batch the value is recorded per
+    env, NaN where that env's stage is filtered out (and `not_recorded` if no env matches)."""
     for metric_id, metric in metrics.items():
         stage = None
+        env_ok = None
         if isinstance(env, FiniteStateMachineEnv) and metric.fsm_stages is not None:
             stage = env.current_stage
             if not isinstance(stage, (str, int)) and np.ndim(stage) > 0:
-                stage = list(env._stages)[int(np.asarray(stage).ravel()[0])]
-        if stage is None or stage in metric.fsm_stages:
+                col = np.asarray(stage).ravel()
+                ids = list(env._stages)
+                allowed = [i for i, sid in enumerate(ids) if sid in metric.fsm_stages]
+                env_ok = np.isin(col, allowed)
+                stage = ids[int(col[0])] if (col == col[0]).all() else None
+        if env_ok is not None and stage is None:  # stages differ across the batch
+            if not env_ok.any():
+                value = not_recorded
+            else:
+                value = np.array(metric.extract(env), dtype=np.float64, copy=True)
+                value = np.where(env_ok.reshape((-1,) + (1,) * (value.ndim - 1)), value, np.nan)
+        elif stage is None or stage in metric.fsm_stages:
             value = metric.extract(env)
         else:
             value = not_recorded

@@ -1,6 +1,6 @@
 """Resolvers (reference: phantom/resolvers.py:17-163).
 
-The round loop itself is device code (csrc/phx_queue.cuh); these classes carry the
+The round loop itself is device code (csrc/phx_engine.cuh, phx_engine1.cuh); these classes carry the
 resolver *configuration* into the spec: round_limit, tracking, shuffle.
 """
 from __future__ import annotations

@@ -78,7 +78,11 @@ class VectorEnv:
     def reset(self, env_mask=None) -> Dict[AgentID, Any]:
         """{agent_id: obs [E, O_a]} for the agents the reference's reset() returns."""
         obs, mask = self.env.reset_batch(env_mask)
-        mask_host = mask[0].cpu().numpy()  # the observing set is the same in every env
+        # an agent is returned if ANY reset env observed it: reset_batch zeroes the mask plane
+        # and the kernel writes only the rows of the masked envs, and an agent's encode may
+        # return None in some envs only (digital_ads); per-env presence is `reset_obs_mask`
+        self.reset_obs_mask = {aid: mask[:, s].bool() for s, aid in enumerate(self.agent_ids)}
+        mask_host = mask.any(0).cpu().numpy()
         return {aid: obs[:, s, : self._obs_dims[aid]]
                 for s, aid in enumerate(self.agent_ids) if mask_host[s]}
 

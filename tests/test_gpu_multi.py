@@ -15,7 +15,8 @@ def _worker(rank, world, port, total, T):
     import torch.distributed as dist
 
     from phantom_b200.envs.supply_chain import SupplyChainEnv
-    from phantom_b200.sharding import gather_step, make_shard, shard_range
+    from phantom_b200.sharding import (LEAN_PLANES, PackedOutputs, gather_packed, gather_step,
+                                       make_shard, shard_range)
 
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), LOCAL_RANK=str(rank))
     torch.cuda.set_device(rank)
@@ -28,12 +29,23 @@ def _worker(rank, world, port, total, T):
         env.reset_batch()
         local = env.rollout_batch(A[:, off:off + cnt])
         whole = gather_step(local, total)
+        # the zero-copy route: a second episode whose kernels write straight into the packed
+        # block (lean planes), one ncclAllGather of the block, overlapping nothing here
+        packed = PackedOutputs.for_env(env, T, LEAN_PLANES, total_envs=total, world_size=world)
+        packed.launch(env, A[:, off:off + cnt])
+        got = gather_packed(packed, total, async_op=True).wait().whole()
+        only0 = gather_packed(packed, total, dst=0)
         if rank == 0:
             ref = SupplyChainEnv(num_envs=total, seed=21, device=0)
             ref.reset_batch()
             want = ref.rollout_batch(A)
             for a, b in zip(whole, want):
                 assert torch.equal(a.cpu(), b.cpu())
+            want2 = ref.rollout_batch(A)
+            for name in LEAN_PLANES:
+                assert torch.equal(getattr(got, name).cpu(), getattr(want2, name).cpu()), name
+                assert torch.equal(getattr(only0.whole(), name).cpu(), getattr(want2, name).cpu()), name
+            assert got.obs_mask is None
             ref.close()
         env.close()
     finally:

@@ -145,6 +145,29 @@ def test_full_size_against_vectorised_oracle(sc):
     env.close()
 
 
+@pytest.mark.parametrize("E", [1, 31, 32, 33, 96, 160, 224])
+def test_small_and_ragged_env_counts_against_vectorised_oracle(sc, E):
+    """Env counts around the block / warp sizes of the fast kernel (E % 64 == 32 once selected
+    the vector action copy for a block whose second warp holds no env: ADVICE r1)."""
+    T, seed = 23, 77
+    A = np.random.RandomState(E).uniform(0, 100, size=(T, E, 1, 1)).astype(np.float32)
+    env = sc.SupplyChainEnv(num_envs=E, seed=seed)
+    assert env.exec_name.startswith("fast")
+    v = vectorised.SupplyChainVec(E, seed)
+    obs0, _ = env.reset_batch()
+    assert np.array_equal(obs0.cpu().numpy()[:, 0], v.reset())
+    ro = env.rollout_batch(A)
+    obs = ro.observations.cpu().numpy()[:, :, 0]
+    rew = ro.rewards.cpu().numpy()[:, :, 0]
+    for t in range(T):
+        ref = v.step(A[t, :, 0, 0])
+        assert np.array_equal(obs[t], ref["obs"]), t
+        assert np.array_equal(rew[t], ref["reward"].astype(np.float32)), t
+    assert np.array_equal(shop_state(env), ref["state"])
+    env.check_errors()
+    env.close()
+
+
 def test_sharding_invariance(sc):
     """Results do not depend on how envs are split over handles (multi-GPU sharding uses
     env_offset; here two handles on one GPU)."""

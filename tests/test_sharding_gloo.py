@@ -10,7 +10,8 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from phantom_b200.env import BatchStep
-from phantom_b200.sharding import gather_step, pack_step, shard_range, unpack_step
+from phantom_b200.sharding import (LEAN_PLANES, PLANES, PackedOutputs, block_layout, gather_packed,
+                                    gather_step, pack_step, shard_range, unpack_step)
 
 
 def test_shard_range_partitions_exactly():
@@ -43,9 +44,26 @@ def fake_step(env_ids: torch.Tensor, S=2, O=3, T=None) -> BatchStep:
 def test_pack_unpack_roundtrip():
     for T in (None, 4):
         step = fake_step(torch.arange(10), T=T)
-        back = unpack_step(pack_step(step), 2, 3)
+        packed = pack_step(step)
+        back = unpack_step(packed)
         for a, b in zip(step, back):
-            assert torch.equal(a, b)
+            assert torch.equal(a, b) and a.dtype == b.dtype  # u8 planes stay u8: no widening
+        # ONE block: 10 envs x 2 agents x (12 + 4 + 4) bytes + 20 all_done bytes, plane aligned
+        assert packed.block.dtype == torch.uint8 and packed.block.is_contiguous()
+        for v in back:
+            assert v.untyped_storage().data_ptr() == packed.block.untyped_storage().data_ptr()
+
+
+def test_block_layout_is_aligned_and_lean_planes_are_null():
+    table, nbytes = block_layout((100,), 8192, 1, 3)
+    assert list(table) == list(PLANES) and nbytes % 256 == 0
+    for off, _, _ in table.values():
+        assert off % 256 == 0
+    lean = PackedOutputs((5,), 7, 1, 3, "cpu", planes=LEAN_PLANES)
+    assert lean.step.obs_mask is None and lean.step.terminations is None
+    assert lean.step.observations.shape == (5, 7, 1, 3) and lean.step.all_done.shape == (5, 7, 2)
+    payload = 5 * 7 * (12 + 4 + 2)
+    assert payload <= lean.nbytes < payload + 3 * 256
 
 
 def _worker(rank, world, port, total):
@@ -59,6 +77,22 @@ def _worker(rank, world, port, total):
             want = fake_step(torch.arange(total), T=T)
             for a, b in zip(whole, want):
                 assert torch.equal(a, b), (rank, T)
+            # the zero-copy route: results written into the packed block's views, one collective
+            cap = max(shard_range(total, r, world)[1] for r in range(world))
+            lead = () if T is None else (T,)
+            packed = PackedOutputs(lead, count, 2, 3, "cpu", capacity_envs=cap)
+            for name in PLANES:
+                getattr(packed.step, name).copy_(getattr(local, name))
+            got = gather_packed(packed, total, async_op=True).wait()
+            for r in range(world):
+                o, c = shard_range(total, r, world)
+                for a, b in zip(got.rank_step(r), fake_step(torch.arange(o, o + c), T=T)):
+                    assert torch.equal(a, b), (rank, r, T)
+            only0 = gather_packed(packed, total, dst=0)  # gather to the trainer rank only
+            assert (only0 is None) == (rank != 0)
+            if rank == 0:
+                for a, b in zip(only0.whole(), want):
+                    assert torch.equal(a, b), (rank, T, "gather dst=0")
     finally:
         dist.destroy_process_group()
 
