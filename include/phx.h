@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PHX_ABI_VERSION 4
+#define PHX_ABI_VERSION 5
 
 #define PHX_MAX_AGENTS 128  /* agent slots per env                                   */
 #define PHX_MAX_TYPES 16    /* payload types per env class                           */
@@ -321,6 +321,18 @@ int32_t phx_poll_errors(phx_env* env, int32_t* n_bad, int32_t* first_env, int32_
  * Lets tests compare the device arithmetic exhaustively against numpy's float32(n / den). */
 int32_t phx_selftest_ratio(int32_t device, int32_t den, int32_t lo, int32_t count,
                            float* host_out);
+
+/* Self-test hooks of the host side of phx_rollout_host (no GPU needed).  Families whose result
+ * rows are small integers send them across PCIe in a compact wire format and expand them into
+ * the caller's float32 planes on `threads` host threads (supply chain: one 32-bit word per
+ * env-step, phantom_b200/csrc/phx_sc_wire.h; the planes replace what the reference computes in
+ * encode_observation / compute_reward, supply_chain.py:124-147).  phx_selftest_wire_expand runs
+ * that expansion on `n` words into obs float[n,3], reward float[n], all_done uint8[n,2];
+ * phx_selftest_wire_pack builds one word. */
+int32_t phx_selftest_wire_expand(int32_t max_stock, int32_t cap, const uint32_t* wire, uint64_t n,
+                                 int32_t threads, float* obs, float* reward, uint8_t* all_done);
+uint32_t phx_selftest_wire_pack(int32_t stock, int32_t sales, int32_t missed, int32_t truncated,
+                                int32_t was_reset);
 
 #ifdef __cplusplus
 }

@@ -21,7 +21,7 @@ PHX_MAX_PARAMS = 16
 PHX_TRACE_WORDS = 4
 PHX_MAX_CODEC_OPS = 6
 PHX_MAX_BASE_CONNECTIONS = 528
-PHX_ABI_VERSION = 4
+PHX_ABI_VERSION = 5
 
 # phx_status
 PHX_OK, PHX_ERR_INVALID, PHX_ERR_CUDA, PHX_ERR_UNSUPPORTED, PHX_ERR_NO_DEVICE = 0, -1, -2, -3, -4
@@ -138,6 +138,9 @@ SYMBOLS = {
     "phx_poll_errors": (C.c_int32, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                     C.POINTER(C.c_int32), C.c_int32]),
     "phx_selftest_ratio": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
+    "phx_selftest_wire_expand": (C.c_int32, [C.c_int32, C.c_int32, _P, C.c_uint64, C.c_int32,
+                                             _P, _P, _P]),
+    "phx_selftest_wire_pack": (C.c_uint32, [C.c_int32] * 5),
 }
 
 

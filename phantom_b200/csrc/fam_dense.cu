@@ -22,6 +22,17 @@
 // version (which spent ~15 instructions per message, most of them on the 16 256 mailbox
 // writes and the 128-deep Ack scan of every agent).  The receivers' first-arrival order only matters for the order in which the Acks
 // are pushed, i.e. for the message trace, and is reconstructed there.
+// On the benchmark's graph -- complete, every agent acting -- round 0 does not even need the
+// pull: handle_batch's aggregation (sum, max, FIRST arg-max) over "everybody but me" is a
+// BLOCK REDUCTION.  A Signal is value[s] + ((2 s) % 5 + (3 r) % 5) % 5, i.e. the sender's value
+// plus a term that depends on the sender only through its class c = (2 s) % 5; so the max over
+// senders is the max over the five classes of (class maximum + tail_r[c]), the first arg-max is
+// the lowest slot among the classes' first arg-maxes, and "but me" is handled by keeping the
+// best TWO senders of every class.  Warp REDUX.MAX / REDUX.ADD + one shared-memory atomic per
+// warp and class replace the 127-message scan of every receiver (~520 instructions per agent
+// and step -> ~100); any other graph / partial action set takes the pull path, in the same
+// kernel, per env and step (the choice is block-uniform).  This is the north star's
+// "warp-ballot / shfl reductions for BatchResolver aggregation".
 // Outputs of a step are staged in shared memory and written with TMA bulk stores
 // (cp.async.bulk.global.shared::cta, SASS UBLKCP): one env's rows are contiguous in every
 // [T,E,S,...] plane.
@@ -45,6 +56,7 @@ enum { DN_SIGNAL = 0, DN_ACK = 1 };
 struct DenseSpec {
   int32_t E, n, num_steps, round_limit;
   uint32_t flags;
+  int32_t complete;  // the graph is complete (every agent is connected to every other agent)
   uint32_t sender_ok[2][4], receiver_ok[2][4];
 };
 
@@ -73,6 +85,10 @@ struct DenseSmem {
   int32_t order_key[DN_MAX];       // trace only: first-arrival keys
   uint32_t sent[4];
   uint32_t any_ack;
+  // reduction form of round 0 (complete graph, everybody sent): per sender class c = (2 s) % 5
+  // the best and second-best sender as keys value * 128 + (127 - slot), and the sum of all values
+  int32_t top1[5], top2[5];
+  int32_t val_sum;
   DenseStage stage[2];
 };
 
@@ -105,6 +121,18 @@ __global__ void __launch_bounds__(DN_MAX) dense_step_kernel(const DenseArgs a) {
   int tailtab[5];
 #pragma unroll
   for (int k = 0; k < 5; ++k) tailtab[k] = (k + 3 * slot) % 5;
+  // reduction form of round 0: this sender's class, the class populations and "all n agents"
+  const int myclass = (2 * slot) % 5;
+  int class_cnt[5];
+  uint32_t full_w[4];
+#pragma unroll
+  for (int c = 0; c < 5; ++c) {
+    const int s0 = (3 * c) % 5;  // (2 s) % 5 == c  <=>  s % 5 == (3 c) % 5
+    class_cnt[c] = s0 < n ? (n - 1 - s0) / 5 + 1 : 0;
+  }
+#pragma unroll
+  for (int w = 0; w < 4; ++w)
+    full_w[w] = n >= 32 * (w + 1) ? 0xFFFFFFFFu : (n > 32 * w ? (1u << (n - 32 * w)) - 1u : 0u);
   const bool bulk = (n % 16) == 0;  // plane sizes multiples of 16 bytes
   const bool ok_send_signal = ((sp.sender_ok[DN_SIGNAL][slot >> 5] >> (slot & 31)) & 1u) ||
                               (sp.flags & PHX_FLAG_NO_PAYLOAD_CHECKS);
@@ -144,6 +172,8 @@ __global__ void __launch_bounds__(DN_MAX) dense_step_kernel(const DenseArgs a) {
     st[1] = 0; st[2] = 0; st[3] = -1; st[4] = 0; st[5] = 0;
     sm.ack_cnt[slot] = 0;
     sm.ack_sum[slot] = 0;
+    if (slot < 5) sm.top1[slot] = sm.top2[slot] = -1;
+    if (slot == 5) sm.val_sum = 0;
     __syncthreads();
 
     // ---- round 0: handle_batch over this receiver's mailbox row (batch order = sender order)
@@ -151,7 +181,51 @@ __global__ void __launch_bounds__(DN_MAX) dense_step_kernel(const DenseArgs a) {
     if (any_sent && sp.round_limit == 0) fault = fault ? fault : PHX_FAULT_ROUND_LIMIT;
     int ack_recv = -1;
     int first_sender = -1;
-    if (is_agent && sp.round_limit != 0) {
+    // everybody sent over a complete graph: every receiver's batch is "all agents but me"
+    const bool reduce_form = !TRACK && sp.complete && sp.round_limit != 0 && n >= 2 &&
+                             sm.sent[0] == full_w[0] && sm.sent[1] == full_w[1] &&
+                             sm.sent[2] == full_w[2] && sm.sent[3] == full_w[3];
+    if (reduce_form) {  // block-uniform
+      const int key = is_agent ? st[0] * 128 + (127 - slot) : -1;
+      const int wsum = __reduce_add_sync(0xFFFFFFFFu, is_agent ? st[0] : 0);
+      if (lane == 0) atomicAdd(&sm.val_sum, wsum);
+#pragma unroll
+      for (int c = 0; c < 5; ++c) {
+        const int m = __reduce_max_sync(0xFFFFFFFFu, myclass == c ? key : -1);
+        if (lane == 0 && m >= 0) atomicMax(&sm.top1[c], m);
+      }
+      __syncthreads();
+#pragma unroll
+      for (int c = 0; c < 5; ++c) {  // the best sender of every class after its overall best
+        const int t1 = sm.top1[c];
+        const int m = __reduce_max_sync(0xFFFFFFFFu, (myclass == c && key != t1) ? key : -1);
+        if (lane == 0 && m >= 0) atomicMax(&sm.top2[c], m);
+      }
+      __syncthreads();
+      if (is_agent) {
+        int best = INT32_MIN, best_s = -1, tails = 0;
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {
+          const int t1 = sm.top1[c];
+          const int k = (127 - (t1 & 127)) == slot ? sm.top2[c] : t1;  // "but me"
+          tails += class_cnt[c] * tailtab[c];
+          if (k >= 0) {
+            const int v = (k >> 7) + tailtab[c], sdr = 127 - (k & 127);
+            if (v > best || (v == best && sdr < best_s)) {  // the FIRST sender attaining the max
+              best = v;
+              best_s = sdr;
+            }
+          }
+        }
+        st[1] = sm.val_sum - st[0] + tails - (myclass + 3 * slot) % 5;  // tailtab[myclass]
+        st[2] = best;
+        st[3] = best_s;
+        ack_recv = best_s;
+        if (!ok_send_ack || (!((sp.receiver_ok[DN_ACK][best_s >> 5] >> (best_s & 31)) & 1u) &&
+                             !(sp.flags & PHX_FLAG_NO_PAYLOAD_CHECKS)))
+          fault = fault ? fault : PHX_FAULT_BAD_PAYLOAD_TYPE;
+      }
+    } else if (is_agent && sp.round_limit != 0) {
       int total = 0, best = INT32_MIN, best_s = -1;
 #pragma unroll
       for (int w = 0; w < 4; ++w) {
@@ -382,11 +456,14 @@ class DenseFamily final : public Family {
       }
     uint32_t h_adj[DN_MAX * 4];
     std::memset(h_adj, 0, sizeof(h_adj));
+    dsp.complete = 1;
     for (int i = 0; i < s.n_agents; ++i) {
       for (int w = 0; w < 4; ++w) h_adj[i * 4 + w] = s.adjacency[i][w];
-      for (int j = 0; j < s.n_agents; ++j)
+      for (int j = 0; j < s.n_agents; ++j) {
         PHX_REQUIRE(mask_bit(s.adjacency[i], j) == mask_bit(s.adjacency[j], i), PHX_ERR_INVALID,
                     "dense family needs a symmetric graph (Network.add_connection always is)");
+        if (mask_bit(s.adjacency[i], j) != (i != j)) dsp.complete = 0;
+      }
     }
     PHX_CUDA(cudaMalloc(&d_adj, sizeof(h_adj)));
     PHX_CUDA(cudaMemcpy(d_adj, h_adj, sizeof(h_adj), cudaMemcpyHostToDevice));

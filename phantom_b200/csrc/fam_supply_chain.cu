@@ -30,8 +30,10 @@
 //    (phx_engine1.cuh / phx_engine.cuh): any agent order / topology, messages routed dynamically.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "phx_engine_host.cuh"
 // output store hints: 1 = every output row streaming (st.global.cs), the measured best
@@ -41,6 +43,7 @@
 #endif
 #include "phx_family.h"
 #include "phx_rng.cuh"
+#include "phx_sc_wire.h"
 
 namespace phx {
 namespace {
@@ -367,6 +370,390 @@ __global__ void __launch_bounds__(SC_BLOCK) sc_fast_kernel(const ScArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// sc_fast2_kernel -- the bench kernel (round 2).  Same schedule, same results, ~40 % fewer
+// instructions and a much shorter dependent chain per step than sc_fast_kernel:
+//
+//  * CLOSED-FORM ORDER FILL.  The shop serves its customers' orders serially
+//    (handle_order_request, supply_chain.py:104-122): sold_i = min(want_i, stock); stock -=
+//    sold_i.  Without message tracking only the totals are observable, and for the whole batch
+//        stock_after = max(max(stock, 0) - D, 0),   D = sum_i want_i
+//    (greedy fill sells min(D, stock) when stock >= 0; a negative stock -- reachable through
+//    negative actions -- is "sold" to the first customer, sold_1 = min(want_1, stock) = stock,
+//    which leaves 0 for the others: the reference's quirk, reproduced).  sales = stock_before -
+//    stock_after and missed = D - sales as before.  10 dependent instructions become 2.
+//  * ORDER TOTAL FROM ONE MULTIPLY.  The five order sizes of a step are the first five base-n
+//    digits of the fraction word / 2^32 (phx_rng.cuh, packed draws), so the 5-digit number they
+//    form is N = umulhi(word, n^5) -- ONE IMAD.HI -- and D = digitsum_n(N) is one byte load from a
+//    n^5-entry table in shared memory (3 125 B for n = 5; built on the host).  Was: five chained
+//    IMAD.WIDE + four adds.
+//  * PHILOX-ALIGNED GROUPS.  Word number g = current_step of a (env, episode) lives in Philox
+//    block g >> 2, so whenever every env of a warp is at a step with g % 4 == 0 the next FOUR
+//    steps take their words from ONE block at compile-time positions: no word queue, no per-step
+//    refill branch.  The state-independent parts of the four steps (word -> D, action -> rint)
+//    are computed first and are independent of each other, the four 7-instruction state updates
+//    follow, then the four output rows: the scheduler sees three batches of independent work
+//    instead of one 100-instruction chain.  Steps that are not aligned (the first three after a
+//    reset, the episode's last step, envs of one warp at different clocks) take the single-step
+//    path -- 4 % of the bench's steps.
+//  Valid for: 5 customers whose orders are all delivered, no action mask, no tracking,
+//  max_order^5 <= SC2_MAX_TABLE (rollout_range checks; everything else runs sc_fast_kernel).
+constexpr int SC2_MAX_TABLE = 16384;
+constexpr int SC2_RING = 16;  // action ring: four copy groups of four steps
+
+struct Sc2Args {
+  ScArgs a;
+  const uint8_t* dsum;  // [n^5] digit sums, device memory
+  uint32_t pow5;        // n^5
+  // compact wire plane of the host-buffer path (phx_sc_wire.h): one 32-bit word per env-step,
+  // [T, E]; *wire_overflow is set if a value of the launch does not fit its field
+  uint32_t* wire;
+  uint32_t* wire_overflow;
+};
+
+template <bool FULL_IO, bool VEC>
+__global__ void __launch_bounds__(SC_BLOCK) sc_fast2_kernel(const Sc2Args args) {
+  const ScArgs& a = args.a;
+  const ScPlan& p = a.p;
+  extern __shared__ __align__(16) unsigned char sc2_smem[];
+  float (*act_ring)[SC_BLOCK] = reinterpret_cast<float (*)[SC_BLOCK]>(sc2_smem);
+  const uint8_t* dsum = sc2_smem + sizeof(float) * SC2_RING * SC_BLOCK;
+  {  // digit-sum table -> shared memory (4-byte words; the host pads the table to 16 bytes)
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(args.dsum);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(sc2_smem + sizeof(float) * SC2_RING * SC_BLOCK);
+    for (uint32_t i = threadIdx.x; i < (args.pow5 + 3u) / 4u; i += SC_BLOCK) dst[i] = src[i];
+  }
+  const int e_raw = blockIdx.x * SC_BLOCK + threadIdx.x;
+  const bool real = e_raw < a.env_count;
+  const int e = a.env_begin + (real ? e_raw : a.env_count - 1);  // benign duplicates past the end
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t env_id = p.env_offset + (uint32_t)e;
+  const float cap_f = p.cap_f, rcp_cap = p.rcp_cap;
+  const float max_stock_f = p.max_stock_f, rcp_stock = p.rcp_stock;
+  const uint32_t E = (uint32_t)p.E;
+  const uint32_t pow5 = args.pow5;
+  const int max_stock = p.max_stock, num_steps = p.num_steps;
+  const bool auto_reset = (p.flags & PHX_FLAG_AUTO_RESET) != 0;
+
+  int2 h = *reinterpret_cast<const int2*>(a.hdr + e);
+  int4 s = a.shop[e];
+  bool bad_action = false;
+  uint32_t row = (uint32_t)e;  // t * E + e (the host guarantees T * E * 3 < 2^32)
+
+  // ---- action ring (cp.async, see sc_fast_kernel): copy group m = steps 4m .. 4m+3 -> slots
+  // (4m .. 4m+3) % 16; group m+4 is fetched as soon as every slot of group m has been read
+  const int T = a.T;
+  const int cj = lane >> 3;
+  const float* src = VEC ? a.io.actions + (size_t)cj * E + (size_t)(e - lane + 4 * (lane & 7))
+                         : a.io.actions + e;
+  float* const dst = VEC ? &act_ring[cj][warp * 32 + 4 * (lane & 7)] : &act_ring[0][threadIdx.x];
+  int fetch_t = 0;  // first step of the next group to fetch
+  auto fetch_group = [&]() {
+    const int slot0 = fetch_t & (SC2_RING - 1);
+    if (VEC) {
+      if (fetch_t + cj < T) cp_async16(dst + slot0 * SC_BLOCK, src);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (fetch_t + k < T) cp_async4(dst + (slot0 + k) * SC_BLOCK, src + (size_t)k * E);
+    }
+    src += (size_t)4 * E;
+    fetch_t += 4;
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int g = 0; g < 4; ++g) fetch_group();
+  __syncthreads();  // the table
+
+  // ---- the three parts of a step
+  // state update: acting phase + pre hook + round 0 (orders) + round 1 (delivery); returns k =
+  // 10 * sales - stock for the reward
+  auto update = [&](const int r, const int D) {
+    const int ask = min(r, max_stock - s.x);        // decode_action, supply_chain.py:136-142
+    const int before = s.x;
+    const int after = max(max(before, 0) - D, 0);   // handle_order_request x 5, closed form
+    s.y = before - after;                           // sales
+    s.z = D - s.y;                                  // missed_sales
+    s.w = ask;                                      // handle_stock_response, :98-102 (the
+    s.x = min(after + ask, max_stock);              // kernel is only launched if it is delivered)
+  };
+  // outputs of the step; `wrap`: the step ends the episode and the env is reset in place
+  auto emit = [&](const bool at_max, const bool wrap) {
+    const float reward = sc_ratio(10 * s.y - s.x, 10.0f, 0.1f);
+    if (wrap) {  // Network.reset -> ShopAgent.reset clears the stock only
+      s.x = 0;
+      h.x = 0;
+      h.y += 1;
+    }
+    const float o0 = sc_ratio(s.x, max_stock_f, rcp_stock);
+    const float o1 = sc_ratio(s.y, cap_f, rcp_cap);
+    const float o2 = sc_ratio(s.z, cap_f, rcp_cap);
+    float* o = a.io.obs + (size_t)row * 3;
+    __stcs(o, o0); __stcs(o + 1, o1); __stcs(o + 2, o2);
+    st_stream(a.io.reward + row, reward);
+    __stcs(reinterpret_cast<uchar2*>(a.io.all_done) + row, make_uchar2(0, at_max ? 1 : 0));
+    if (FULL_IO) {
+      __stcs(a.io.obs_mask + row, (uint8_t)1);
+      __stcs(a.io.reward_mask + row, (uint8_t)1);
+      __stcs(a.io.term + row, (uint8_t)0);
+      __stcs(a.io.trunc + row, (uint8_t)0);
+    }
+    row += E;
+  };
+  auto decode = [&](const float act) {
+    if (!(fabsf(act) <= SC_MAX_ABS_ACTION)) bad_action = true;
+    return __float2int_rn(act);  // python round() of a float32 is round-half-even == cvt.rni
+  };
+
+  PackedWords words;  // single-step path: block cache
+  int t = 0;
+  while (t < T) {
+    // top up the ring: group (fetch_t / 4 - 4)'s slots are free once t has passed them
+    if (t >= fetch_t - 12) {
+      __syncwarp();
+      fetch_group();
+    }
+    cp_async_wait<2>();  // all but the two youngest groups have landed: steps <= t + 4
+    __syncwarp();
+    const int g = h.x + 1;
+    const bool can4 = (g & 3) == 0 && t + 4 <= T && (!auto_reset || g + 3 < num_steps);
+    if (__all_sync(0xFFFFFFFFu, can4)) {
+      // ---- four steps from one Philox block
+      const Philox4 b = rng_word_block(p.seed, env_id, (uint32_t)h.y, (uint32_t)g >> 2,
+                                       SC_STREAM_ORDER);
+      int D[4], r[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        D[k] = dsum[__umulhi(b.w[k], pow5)];
+        r[k] = decode(act_ring[(t + k) & (SC2_RING - 1)][threadIdx.x]);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        h.x += 1;  // env.py:252
+        update(r[k], D[k]);
+        emit(h.x == num_steps, false);  // (no wrap inside an aligned group, see can4)
+      }
+      t += 4;
+    } else {
+      const uint32_t x = words.word(p.seed, env_id, (uint32_t)h.y, (uint32_t)g, SC_STREAM_ORDER);
+      const int D = dsum[__umulhi(x, pow5)];
+      const int r = decode(act_ring[t & (SC2_RING - 1)][threadIdx.x]);
+      h.x += 1;
+      update(r, D);
+      emit(h.x == num_steps, auto_reset && h.x == num_steps);
+      t += 1;
+    }
+  }
+  cp_async_wait<0>();
+
+  if (real) {
+    *reinterpret_cast<int2*>(a.hdr + e) = h;
+    a.shop[e] = s;
+    // first fault in event order: a bad action is detected in decode_action, before any send
+    const uint32_t fault = bad_action ? (uint32_t)PHX_FAULT_INVALID_ACTION : p.fault[1];
+    if (fault) raise_fault(a.faults, e, fault);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// sc_fast3_kernel -- TIME-PARALLEL form of the same schedule.  sc_fast2_kernel
+// is latency bound: 65 536 envs are 2 048 warps = 3.5 per scheduler, each walking a ~75
+// instruction dependent chain per step (measured: 4 % faster than sc_fast_kernel for 25 % fewer
+// instructions).  But only SEVEN of those instructions depend on the env's state:
+//
+//     stock' = min(max(max(stock, 0) - D, 0) + min(r, max_stock - stock), max_stock)
+//
+// with D (order total: Philox word -> digit sum) and r (rint of the action) functions of
+// (env, step) alone, and the output rows functions of (stock', sales, missed) alone.  So a block
+// of FOUR warps owns 32 envs and works in chunks of 16 steps:
+//   phase A  warp w, lane e: the four steps of Philox block w of the chunk -- one Philox block,
+//            four (r, D) pairs -> shared memory                          [parallel over (e, t)]
+//   phase B  warp 0, lane e: the 16-step recurrence of env e, 7 instructions per step,
+//            (stock, sales, missed, reward numerator) -> shared memory   [serial in t]
+//   phase C  warp w, lane e: four output rows (4 correctly rounded quotients, 5 stores each)
+//                                                                        [parallel over (e, t)]
+// Same instruction count, four times the warps (13.8 per scheduler) and nearly all of the work
+// in independent batches.  Every thread tracks the clock of its lane's env (it does not depend
+// on the state), so the (episode, step) RNG coordinates and the truncation flags need no
+// communication.  The step groups are aligned to the Philox blocks of the block's first env; an
+// env at another clock phase just evaluates two Philox blocks for its four steps (PackedWords).
+constexpr int SC3_ENVS = 32;   // envs per block: one lane per env in every warp
+constexpr int SC3_CHUNK = 16;  // steps per chunk = four Philox blocks
+
+__device__ __noinline__ Philox4 sc3_refill(uint64_t seed, uint32_t env_id, uint32_t ep, uint32_t blk) {
+  return rng_word_block(seed, env_id, ep, blk, SC_STREAM_ORDER);
+}
+
+// W = warps per block (4: one step group per warp and chunk; 2: two groups per warp, for builds
+// that want more registers per thread).
+template <bool FULL_IO, int W, bool WIRE>
+__global__ void __launch_bounds__(SC3_ENVS * W, W == 4 ? 14 : 16) sc_fast3_kernel(const Sc2Args args) {
+  const ScArgs& a = args.a;
+  const ScPlan& p = a.p;
+  constexpr int GROUPS = 4 / W;  // step groups per thread and chunk
+  __shared__ int2 in_rd[SC3_CHUNK][SC3_ENVS];   // (r, D) of every (step, env) of the chunk
+  __shared__ int4 out_st[SC3_CHUNK][SC3_ENVS];  // (stock for the obs, sales, missed, 10*sales-stock)
+  __shared__ uint32_t bad[SC3_ENVS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int e_raw = blockIdx.x * SC3_ENVS + lane;
+  const bool real = e_raw < a.env_count;
+  const int e = a.env_begin + (real ? e_raw : a.env_count - 1);  // benign duplicates past the end
+  const uint32_t env_id = p.env_offset + (uint32_t)e;
+  const uint32_t E = (uint32_t)p.E;
+  const uint32_t pow5 = args.pow5;
+  const uint8_t* __restrict__ dsum = args.dsum;
+  const int max_stock = p.max_stock, num_steps = p.num_steps, T = a.T;
+
+  const int2 h0 = *reinterpret_cast<const int2*>(a.hdr + e);
+  // an env wraps (auto-reset) when its clock reaches num_steps exactly; one that is already past
+  // it (stepped on without auto-reset before) never does
+  const bool wraps = (p.flags & PHX_FLAG_AUTO_RESET) != 0 && h0.x < num_steps;
+  int4 s = make_int4(0, 0, 0, 0);
+  if (warp == 0) {
+    s = a.shop[e];
+    bad[lane] = 0;
+  }
+  bool bad_action = false;
+  // virtual time u = t + shift: the groups u >> 2 are the Philox blocks of the block's first env
+  const int shift = (__shfl_sync(0xFFFFFFFFu, h0.x, 0) + 1) & 3;
+  const int u_end = T + shift;
+
+  // clock of step t (t steps after the launch started): steps since the episode began (= step
+  // number - 1) and episode
+  auto clock_at = [&](int t, int& since, int& ep) {
+    since = h0.x + t;
+    ep = h0.y;
+    if (wraps) {
+      const int q = since / num_steps;
+      since -= q * num_steps;
+      ep += q;
+    }
+  };
+
+  for (int u0 = 0; u0 < u_end; u0 += SC3_CHUNK) {
+    // ---- phase A: (r, D) of this thread's step groups
+#pragma unroll
+    for (int m = 0; m < GROUPS; ++m) {
+      const int ub = u0 + 4 * (warp + W * m);
+      const int ua = max(ub, shift), uz = min(ub + 4, u_end);  // valid steps [ua, uz)
+      if (ua < uz) {
+        float act[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          act[k] = ub + k >= ua && ub + k < uz
+                       ? __ldcs(a.io.actions + (size_t)(ub + k - shift) * E + e) : 0.f;
+        int since, ep;
+        clock_at(ua - shift, since, ep);
+        uint32_t blk = (uint32_t)(since + 1) >> 2, blk_ep = (uint32_t)ep;
+        Philox4 b = rng_word_block(p.seed, env_id, blk_ep, blk, SC_STREAM_ORDER);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (ub + k >= ua && ub + k < uz) {
+            const uint32_t g = (uint32_t)since + 1u;  // step number = word number
+            if ((g >> 2) != blk || (uint32_t)ep != blk_ep) {  // not block aligned / episode ended
+              blk = g >> 2;
+              blk_ep = (uint32_t)ep;
+              b = sc3_refill(p.seed, env_id, blk_ep, blk);
+            }
+            const uint32_t q = g & 3u;
+            const uint32_t x = q == 0u ? b.w[0] : q == 1u ? b.w[1] : q == 2u ? b.w[2] : b.w[3];
+            const int D = __ldg(dsum + __umulhi(x, pow5));
+            if (!(fabsf(act[k]) <= SC_MAX_ABS_ACTION)) bad_action = true;
+            // python round() of a float32 is round-half-even == cvt.rni
+            in_rd[(ub + k) & (SC3_CHUNK - 1)][lane] = make_int2(__float2int_rn(act[k]), D);
+            since += 1;
+            if (wraps && since == num_steps) {
+              since = 0;
+              ep += 1;
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // ---- phase B: the recurrence, one lane per env
+    if (warp == 0) {
+      const int c_begin = max(u0, shift), c_end = min(u0 + SC3_CHUNK, u_end);
+      int since, ep;
+      clock_at(c_begin - shift, since, ep);
+#pragma unroll 4
+      for (int u = c_begin; u < c_end; ++u) {
+        const int2 rd = in_rd[u & (SC3_CHUNK - 1)][lane];
+        const int ask = min(rd.x, max_stock - s.x);       // decode_action, supply_chain.py:136-142
+        const int before = s.x;
+        const int after = max(max(before, 0) - rd.y, 0);  // handle_order_request x 5, closed form
+        s.y = before - after;                             // sales
+        s.z = rd.y - s.y;                                 // missed_sales
+        s.w = ask;                                        // handle_stock_response, :98-102
+        s.x = min(after + ask, max_stock);
+        const int k = 10 * s.y - s.x;                     // reward numerator (before a reset)
+        since += 1;
+        if (wraps && since == num_steps) {                // ShopAgent.reset clears the stock only
+          since = 0;
+          s.x = 0;
+        }
+        out_st[u & (SC3_CHUNK - 1)][lane] = make_int4(s.x, s.y, s.z, k);
+      }
+    }
+    __syncthreads();
+    // ---- phase C: the output rows of this thread's step groups
+#pragma unroll
+    for (int m = 0; m < GROUPS; ++m) {
+      const int ub = u0 + 4 * (warp + W * m);
+      const int ua = max(ub, shift), uz = min(ub + 4, u_end);
+      if (ua < uz) {
+        int since, ep;
+        clock_at(ua - shift, since, ep);
+        // truncation: the step whose number equals num_steps (env.py:312-318)
+        const int k_max = num_steps - 1 - since;  // position of that step in the group, if any
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (ub + k >= ua && ub + k < uz) {
+            const int j = ub + k - ua;
+            const bool at_max = wraps ? (j == k_max) : (since + j + 1 == num_steps);
+            const int4 v = out_st[(ub + k) & (SC3_CHUNK - 1)][lane];
+            const uint32_t row = (uint32_t)(ub + k - shift) * E + (uint32_t)e;
+            const float reward = sc_ratio(v.w, 10.0f, 0.1f);
+            const float o0 = sc_ratio(v.x, p.max_stock_f, p.rcp_stock);
+            const float o1 = sc_ratio(v.y, p.cap_f, p.rcp_cap);
+            const float o2 = sc_ratio(v.z, p.cap_f, p.rcp_cap);
+            float* o = a.io.obs + (size_t)row * 3;
+            __stcs(o, o0); __stcs(o + 1, o1); __stcs(o + 2, o2);
+            st_stream(a.io.reward + row, reward);
+            __stcs(reinterpret_cast<uchar2*>(a.io.all_done) + row, make_uchar2(0, at_max ? 1 : 0));
+            if (FULL_IO) {
+              __stcs(a.io.obs_mask + row, (uint8_t)1);
+              __stcs(a.io.reward_mask + row, (uint8_t)1);
+              __stcs(a.io.term + row, (uint8_t)0);
+              __stcs(a.io.trunc + row, (uint8_t)0);
+            }
+            if (WIRE) {  // the same row as ONE word (phx_sc_wire.h), for the host-buffer path
+              const int stock_pre = 10 * v.y - v.w;  // the stock the reward saw (before a reset)
+              const bool fits = stock_pre >= -SCW_STOCK_BIAS && stock_pre < SCW_STOCK_BIAS &&
+                                (uint32_t)v.y <= SCW_FIELD_MAX && (uint32_t)v.z <= SCW_FIELD_MAX;
+              if (!fits) *args.wire_overflow = 1u;
+              __stcs(args.wire + row, scw_pack(stock_pre, v.y, v.z, at_max, wraps && at_max));
+            }
+          }
+        }
+      }
+    }
+  }
+
+  // an out-of-contract action may have been seen by any of the warps of an env
+  if (bad_action) atomicOr(&bad[lane], 1u);
+  __syncthreads();
+  if (warp == 0 && real) {
+    int since, ep;
+    clock_at(T, since, ep);
+    *reinterpret_cast<int2*>(a.hdr + e) = make_int2(since, ep);
+    a.shop[e] = s;
+    // first fault in event order: a bad action is detected in decode_action, before any send
+    const uint32_t fault = bad[lane] ? (uint32_t)PHX_FAULT_INVALID_ACTION : p.fault[1];
+    if (fault) raise_fault(a.faults, e, fault);
+  }
+}
+
 // float32(n / den) through the kernel's own routine, for the exhaustive parity test.
 __global__ void sc_ratio_selftest_kernel(int lo, int n, float den, float rcp, float* out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -409,6 +796,8 @@ class SupplyChainFast final : public Family {
   ~SupplyChainFast() override {
     cudaFree(d_shop);
     cudaFree(d_scratch);
+    cudaFree(d_dsum);
+    if (h_wire) cudaFreeHost(h_wire);
   }
 
   int32_t init(const phx_spec& s) override {
@@ -523,6 +912,20 @@ class SupplyChainFast final : public Family {
     if (tracking())
       PHX_REQUIRE(s.trace_capacity >= 2 * (1 + p.nc), PHX_ERR_INVALID,
                   "trace_capacity must be >= 2 * (1 + n_customers) for the supply chain");
+    // sc_fast2_kernel: digit sums of the 5-digit base-max_order numbers (the order total of a step)
+    pow5 = 0;
+    const uint64_t n = (uint64_t)p.max_order;
+    if (p.nc == 5 && p.words_per_step == 1 && n * n * n * n * n <= (uint64_t)SC2_MAX_TABLE) {
+      pow5 = (uint32_t)(n * n * n * n * n);
+      std::vector<uint8_t> tab((pow5 + 15u) & ~15u, 0);
+      for (uint32_t v = 0; v < pow5; ++v) {
+        uint32_t x = v, sum = 0;
+        for (int k = 0; k < 5; ++k) { sum += x % (uint32_t)n; x /= (uint32_t)n; }
+        tab[v] = (uint8_t)sum;
+      }
+      PHX_CUDA(cudaMalloc(&d_dsum, tab.size()));
+      PHX_CUDA(cudaMemcpy(d_dsum, tab.data(), tab.size(), cudaMemcpyHostToDevice));
+    }
     return PHX_OK;
   }
 
@@ -541,7 +944,8 @@ class SupplyChainFast final : public Family {
   // Steps envs [env_begin, env_begin + env_count); the I/O planes keep the handle's full
   // [T, E, ...] shape (row stride E).
   int32_t rollout_range(int32_t T, const StepIO& io, int32_t env_begin, int32_t env_count,
-                        cudaStream_t stream) {
+                        cudaStream_t stream, uint32_t* wire = nullptr,
+                        uint32_t* wire_overflow = nullptr) {
     PHX_REQUIRE(env_begin >= 0 && env_count >= 1 && env_begin + env_count <= E, PHX_ERR_INVALID,
                 "env range out of bounds");
     ScArgs a;
@@ -596,6 +1000,38 @@ class SupplyChainFast final : public Family {
       if (!a.io.all_done) a.io.all_done = q;
     }
     const bool mask = a.io.action_mask != nullptr;
+    const bool all_delivered_ = plan.deliver_ord == (1u << plan.nc) - 1u;
+    PHX_REQUIRE(wire == nullptr || wire_ok(lean && !mask), PHX_ERR_INVALID,
+                "compact wire output is not available for this launch");
+    if (pow5 != 0 && !mask && !track && all_delivered_ && plan.delivery_ok && !use_v1) {
+      // the round-2 kernels
+      Sc2Args b;
+      b.a = a;
+      b.dsum = d_dsum;
+      b.pow5 = pow5;
+      if (sc_variant == 3 && plan.num_steps >= 4) {  // the time-parallel kernel (default)
+        const int grid3 = (env_count + SC3_ENVS - 1) / SC3_ENVS;
+        const bool w2 = sc_warps == 2;
+        b.wire = wire;
+        b.wire_overflow = wire_overflow;
+        if (wire) {  // host-buffer path: float planes (fallback) + the compact wire plane
+          if (!w2) sc_fast3_kernel<false, 4, true><<<grid3, SC3_ENVS * 4, 0, stream>>>(b);
+          else sc_fast3_kernel<false, 2, true><<<grid3, SC3_ENVS * 2, 0, stream>>>(b);
+        } else if (lean && !w2) sc_fast3_kernel<false, 4, false><<<grid3, SC3_ENVS * 4, 0, stream>>>(b);
+        else if (lean) sc_fast3_kernel<false, 2, false><<<grid3, SC3_ENVS * 2, 0, stream>>>(b);
+        else if (!w2) sc_fast3_kernel<true, 4, false><<<grid3, SC3_ENVS * 4, 0, stream>>>(b);
+        else sc_fast3_kernel<true, 2, false><<<grid3, SC3_ENVS * 2, 0, stream>>>(b);
+        PHX_CUDA(cudaGetLastError());
+        return PHX_OK;
+      }
+      const size_t smem = sizeof(float) * SC2_RING * SC_BLOCK + ((pow5 + 15u) & ~15u);
+      if (lean && a.vec_actions) sc_fast2_kernel<false, true><<<grid, SC_BLOCK, smem, stream>>>(b);
+      else if (lean) sc_fast2_kernel<false, false><<<grid, SC_BLOCK, smem, stream>>>(b);
+      else if (a.vec_actions) sc_fast2_kernel<true, true><<<grid, SC_BLOCK, smem, stream>>>(b);
+      else sc_fast2_kernel<true, false><<<grid, SC_BLOCK, smem, stream>>>(b);
+      PHX_CUDA(cudaGetLastError());
+      return PHX_OK;
+    }
 #define SC_LAUNCH(NC_, TRACK_)                                                              \
   do {                                                                                      \
     if (mask && !lean) sc_fast_kernel<NC_, TRACK_, true, true><<<grid, SC_BLOCK, 0, stream>>>(a);  \
@@ -619,6 +1055,90 @@ class SupplyChainFast final : public Family {
     return PHX_OK;
   }
 
+  // The compact wire word is produced by sc_fast3_kernel only, for the lean output layout.
+  bool wire_ok(bool lean_no_mask) const {
+    const bool all_delivered_ = plan.deliver_ord == (1u << plan.nc) - 1u;
+    return lean_no_mask && pow5 != 0 && !tracking() && all_delivered_ && plan.delivery_ok &&
+           sc_variant == 3 && plan.num_steps >= 4 && plan.max_stock < SCW_STOCK_BIAS &&
+           plan.nc * plan.max_order <= (int)SCW_FIELD_MAX && !no_wire;
+  }
+
+  // phx_rollout_host for the lean layout (obs + reward + all_done): the results cross PCIe as
+  // ONE 32-bit word per env-step (4 B instead of 18 B) and are expanded to the caller's float32
+  // planes by the host thread pool, chunk by chunk, while later chunks are still in flight.
+  // The expansion evaluates the same correctly rounded quotients as the kernel, so the planes
+  // are bit-identical to the device path's (tests/test_gpu_reset_and_io.py).  The kernel also
+  // writes the float planes into the device staging block: if any value of the call did not
+  // fit its wire field (|stock| >= 2^15, sales or missed outside 0..127 -- out-of-distribution
+  // actions), the planes are copied instead.
+  int32_t rollout_host(int32_t T, const StepIO& h) override {
+    const bool lean = h.obs && h.reward && h.all_done && !h.obs_mask && !h.reward_mask &&
+                      !h.term && !h.trunc && !h.action_mask;
+    if (!wire_ok(lean) || T < 8 || (size_t)T * E < 65536 ||
+        (uint64_t)T * (uint64_t)E * 3ull >= (1ull << 32))
+      return Family::rollout_host(T, h);
+    const size_t TE = (size_t)T * E;
+    auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t b_act = up(TE * 4), b_obs = up(TE * 12), b_rew = up(TE * 4), b_all = up(TE * 2),
+                 b_wire = up(TE * 4);
+    const size_t total = b_act + b_obs + b_rew + b_all + b_wire + 256;
+    int32_t rc = ensure_stage(total);
+    if (rc != PHX_OK) return rc;
+    if (TE * 4 > h_wire_bytes) {  // pinned landing buffer of the wire plane
+      if (h_wire) cudaFreeHost(h_wire);
+      h_wire = nullptr;
+      h_wire_bytes = 0;
+      PHX_CUDA(cudaMallocHost(&h_wire, TE * 4));
+      h_wire_bytes = TE * 4;
+    }
+    uint8_t* q = (uint8_t*)d_stage;
+    float* d_act = (float*)q; q += b_act;
+    float* d_obs = (float*)q; q += b_obs;
+    float* d_rew = (float*)q; q += b_rew;
+    uint8_t* d_all = q; q += b_all;
+    uint32_t* d_wire = (uint32_t*)q; q += b_wire;
+    uint32_t* d_over = (uint32_t*)q;
+    PHX_CUDA(cudaMemsetAsync(d_over, 0, sizeof(uint32_t), own_stream));
+    ScWireParams wp{plan.max_stock, plan.nc * plan.max_order};
+    static const int kFrac[9] = {0, 2, 6, 14, 28, 46, 64, 82, 100};  // see Family::rollout_host
+    auto bound = [&](int c) { return ((size_t)T * kFrac[c] + 50) / 100; };
+    for (int c = 0; c < 8; ++c) {
+      const size_t t0 = bound(c), nt = bound(c + 1) - t0;
+      if (nt == 0) continue;
+      PHX_CUDA(cudaMemcpyAsync(d_act + t0 * E, h.actions + t0 * E, nt * E * 4,
+                               cudaMemcpyHostToDevice, copy_in));
+      PHX_CUDA(cudaEventRecord(ev_in[c], copy_in));
+      PHX_CUDA(cudaStreamWaitEvent(own_stream, ev_in[c], 0));
+      StepIO ic{d_act + t0 * E, nullptr, d_obs + t0 * E * 3, nullptr, d_rew + t0 * E, nullptr,
+                nullptr, nullptr, d_all + t0 * E * 2};
+      rc = rollout_range((int32_t)nt, ic, 0, E, own_stream, d_wire + t0 * E, d_over);
+      if (rc != PHX_OK) return rc;
+      PHX_CUDA(cudaEventRecord(ev_k[c], own_stream));
+      PHX_CUDA(cudaStreamWaitEvent(copy_out, ev_k[c], 0));
+      PHX_CUDA(cudaMemcpyAsync(h_wire + t0 * E, d_wire + t0 * E, nt * E * 4,
+                               cudaMemcpyDeviceToHost, copy_out));
+      PHX_CUDA(cudaEventRecord(ev_out[c], copy_out));
+    }
+    uint32_t over = 0;
+    PHX_CUDA(cudaMemcpyAsync(&over, d_over, sizeof(over), cudaMemcpyDeviceToHost, copy_out));
+    // expand chunk c while the copies of the later chunks run
+    for (int c = 0; c < 8; ++c) {
+      const size_t t0 = bound(c), nt = bound(c + 1) - t0;
+      if (nt == 0) continue;
+      PHX_CUDA(cudaEventSynchronize(ev_out[c]));
+      sc_wire_expand(host_pool(), wp, h_wire + t0 * E, nt * E, h.obs + t0 * E * 3,
+                     h.reward + t0 * E, h.all_done + t0 * E * 2);
+    }
+    PHX_CUDA(cudaStreamSynchronize(copy_out));
+    PHX_CUDA(cudaStreamSynchronize(own_stream));
+    if (over) {  // a value did not fit the wire format: take the float planes the kernel wrote
+      PHX_CUDA(cudaMemcpy(h.obs, d_obs, TE * 12, cudaMemcpyDeviceToHost));
+      PHX_CUDA(cudaMemcpy(h.reward, d_rew, TE * 4, cudaMemcpyDeviceToHost));
+      PHX_CUDA(cudaMemcpy(h.all_done, d_all, TE * 2, cudaMemcpyDeviceToHost));
+    }
+    return PHX_OK;
+  }
+
   int32_t family_field(int32_t field, int32_t, void** p, size_t* bytes) override {
     if (field == PHX_FIELD_FAMILY + 0) {
       *p = d_shop;
@@ -633,6 +1153,17 @@ class SupplyChainFast final : public Family {
 
  private:
   ScPlan plan{};
+  uint32_t* h_wire = nullptr;  // pinned landing buffer of the compact wire plane (rollout_host)
+  size_t h_wire_bytes = 0;
+  uint8_t* d_dsum = nullptr;  // digit-sum table of sc_fast2_kernel (nullptr: not applicable)
+  uint32_t pow5 = 0;
+  // PHX_SC_KERNEL = 1 | 2 | 3 picks sc_fast_kernel / sc_fast2_kernel / sc_fast3_kernel (default 3)
+  // where more than one is valid: A/B measurements and the cross-kernel parity tests
+  const int sc_variant = std::getenv("PHX_SC_KERNEL") ? std::atoi(std::getenv("PHX_SC_KERNEL")) : 3;
+  const bool use_v1 = sc_variant == 1;
+  // PHX_NO_WIRE=1 (read when the handle is created) keeps phx_rollout_host on the float planes
+  const bool no_wire = std::getenv("PHX_NO_WIRE") != nullptr && std::getenv("PHX_NO_WIRE")[0] == '1';
+  const int sc_warps = std::getenv("PHX_SC_WARPS") ? std::atoi(std::getenv("PHX_SC_WARPS")) : 4;
   int4* d_shop = nullptr;
   void* d_scratch = nullptr;  // planes the caller did not ask for (non-lean layouts)
   size_t scratch_bytes = 0;

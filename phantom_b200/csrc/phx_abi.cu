@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "phx_family.h"
+#include "phx_sc_wire.h"
 
 namespace phx {
 
@@ -31,6 +32,7 @@ Family::~Family() {
   for (int i = 0; i < 8; ++i) {
     if (ev_in[i]) cudaEventDestroy(ev_in[i]);
     if (ev_k[i]) cudaEventDestroy(ev_k[i]);
+    if (ev_out[i]) cudaEventDestroy(ev_out[i]);
   }
 }
 
@@ -67,6 +69,7 @@ int32_t Family::base_init(const phx_spec& s, int32_t num_envs, int32_t dev, uint
   for (int i = 0; i < 8; ++i) {
     PHX_CUDA(cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming));
     PHX_CUDA(cudaEventCreateWithFlags(&ev_k[i], cudaEventDisableTiming));
+    PHX_CUDA(cudaEventCreateWithFlags(&ev_out[i], cudaEventDisableTiming));
   }
   return PHX_OK;
 }
@@ -87,6 +90,124 @@ int32_t Family::field_ptr(int32_t field, int32_t index, void** p, size_t* bytes)
   set_error("unknown field id " + std::to_string(field));
   return PHX_ERR_INVALID;
 }
+
+int32_t Family::ensure_stage(size_t total) {
+  if (total > stage_bytes) {
+    PHX_CUDA(cudaStreamSynchronize(own_stream));
+    PHX_CUDA(cudaStreamSynchronize(copy_in));
+    PHX_CUDA(cudaStreamSynchronize(copy_out));
+    if (d_stage) PHX_CUDA(cudaFree(d_stage));
+    d_stage = nullptr;
+    stage_bytes = 0;
+    PHX_CUDA(cudaMalloc(&d_stage, total));
+    stage_bytes = total;
+  }
+  return PHX_OK;
+}
+
+int32_t Family::rollout_host(int32_t T, const StepIO& h) {
+  const float* actions = h.actions;
+  const uint8_t* action_mask = h.action_mask;
+  float *obs = h.obs, *reward = h.reward;
+  uint8_t *obs_mask = h.obs_mask, *reward_mask = h.reward_mask, *term = h.term, *trunc = h.trunc,
+          *all_done = h.all_done;
+  Family* f = this;
+  const size_t n = (size_t)T * f->E * (size_t)(f->spec.n_strategic > 0 ? f->spec.n_strategic : 1);
+  const size_t S = f->spec.n_strategic;
+  const size_t TE = (size_t)T * f->E;
+  auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+  // carve one staging block: actions | action_mask | obs | obs_mask | reward | reward_mask |
+  // term | trunc | all_done
+  const size_t b_act = up(TE * S * f->spec.act_dim * sizeof(float));
+  const size_t b_am = up(TE * S);
+  const size_t b_obs = up(TE * S * f->spec.obs_dim * sizeof(float));
+  const size_t b_u8 = up(TE * S);
+  const size_t b_rew = up(TE * S * sizeof(float));
+  const size_t b_all = up(TE * 2);
+  const size_t total = b_act + b_am + b_obs + 4 * b_u8 + b_rew + b_all;
+  (void)n;
+  {
+    const int32_t rc = ensure_stage(total);
+    if (rc != PHX_OK) return rc;
+  }
+  uint8_t* p = (uint8_t*)f->d_stage;
+  float* d_act = (float*)p; p += b_act;
+  uint8_t* d_am = p; p += b_am;
+  float* d_obs = (float*)p; p += b_obs;
+  uint8_t* d_om = p; p += b_u8;
+  float* d_rew = (float*)p; p += b_rew;
+  uint8_t* d_rm = p; p += b_u8;
+  uint8_t* d_term = p; p += b_u8;
+  uint8_t* d_trunc = p; p += b_u8;
+  uint8_t* d_all = p;
+  phx::StepIO io{d_act,
+                 action_mask ? d_am : nullptr,
+                 obs ? d_obs : nullptr,
+                 obs_mask ? d_om : nullptr,
+                 reward ? d_rew : nullptr,
+                 reward_mask ? d_rm : nullptr,
+                 term ? d_term : nullptr,
+                 trunc ? d_trunc : nullptr,
+                 all_done ? d_all : nullptr};
+  const size_t E = (size_t)f->E, A = (size_t)f->spec.act_dim, O = (size_t)f->spec.obs_dim;
+  // Chunked 3-stage pipeline (H2D | kernel | D2H on three streams), chunked along TIME: the rows
+  // [t0, t1) of every [T, E, ...] plane are one contiguous block, so each transfer is a single
+  // large 1-D copy (env-range chunks needed pitched 2-D copies of 16-98 KB rows, which PCIe
+  // moves ~10 % slower), and every family can do it -- a chunk is just a shorter rollout that
+  // continues from the state the previous launch left in HBM.  PCIe is full duplex: the input
+  // copy of chunk c+1 and the output copy of chunk c-1 overlap the kernel of chunk c.
+  const int chunks = (T >= 8 && TE >= 65536 && !f->tracking()) ? 8 : 1;
+  auto copy1d = [&](void* dst, const void* src, size_t row_bytes, size_t t0, size_t nt,
+                    cudaMemcpyKind k, cudaStream_t st) {
+    if (row_bytes == 0 || nt == 0) return cudaSuccess;
+    return cudaMemcpyAsync((char*)dst + t0 * row_bytes, (const char*)src + t0 * row_bytes,
+                           nt * row_bytes, k, st);
+  };
+  // Chunk boundaries grow geometrically at the front: the first output copy can only start after
+  // the first chunk's input copy and kernel, so a short first chunk shortens the pipeline fill
+  // (uniform eighths: 3.3 MB of actions = 80 us before the D2H engine has anything to do).
+  static const int kFrac[9] = {0, 2, 6, 14, 28, 46, 64, 82, 100};  // percent of T, cumulative
+  auto bound = [&](int c) {
+    return chunks == 1 ? (size_t)(c ? T : 0) : ((size_t)T * kFrac[c] + 50) / 100;
+  };
+  for (int c = 0; c < chunks; ++c) {
+    const size_t t0 = bound(c), t1 = bound(c + 1);
+    const size_t nt = t1 - t0;
+    if (nt == 0) continue;
+    if (actions)
+      PHX_CUDA(copy1d(d_act, actions, E * S * A * sizeof(float), t0, nt, cudaMemcpyHostToDevice, f->copy_in));
+    if (action_mask)
+      PHX_CUDA(copy1d(d_am, action_mask, E * S, t0, nt, cudaMemcpyHostToDevice, f->copy_in));
+    PHX_CUDA(cudaEventRecord(f->ev_in[c], f->copy_in));
+    PHX_CUDA(cudaStreamWaitEvent(f->own_stream, f->ev_in[c], 0));
+    phx::StepIO ic = io;  // the chunk's rows of every plane
+    ic.actions = io.actions + t0 * E * S * A;
+    if (ic.action_mask) ic.action_mask += t0 * E * S;
+    if (ic.obs) ic.obs += t0 * E * S * O;
+    if (ic.obs_mask) ic.obs_mask += t0 * E * S;
+    if (ic.reward) ic.reward += t0 * E * S;
+    if (ic.reward_mask) ic.reward_mask += t0 * E * S;
+    if (ic.term) ic.term += t0 * E * S;
+    if (ic.trunc) ic.trunc += t0 * E * S;
+    if (ic.all_done) ic.all_done += t0 * E * 2;
+    const int32_t rc = f->rollout((int32_t)nt, ic, f->own_stream);
+    if (rc != PHX_OK) return rc;
+    PHX_CUDA(cudaEventRecord(f->ev_k[c], f->own_stream));
+    PHX_CUDA(cudaStreamWaitEvent(f->copy_out, f->ev_k[c], 0));
+    cudaStream_t so = f->copy_out;
+    if (obs) PHX_CUDA(copy1d(obs, d_obs, E * S * O * sizeof(float), t0, nt, cudaMemcpyDeviceToHost, so));
+    if (obs_mask) PHX_CUDA(copy1d(obs_mask, d_om, E * S, t0, nt, cudaMemcpyDeviceToHost, so));
+    if (reward) PHX_CUDA(copy1d(reward, d_rew, E * S * sizeof(float), t0, nt, cudaMemcpyDeviceToHost, so));
+    if (reward_mask) PHX_CUDA(copy1d(reward_mask, d_rm, E * S, t0, nt, cudaMemcpyDeviceToHost, so));
+    if (term) PHX_CUDA(copy1d(term, d_term, E * S, t0, nt, cudaMemcpyDeviceToHost, so));
+    if (trunc) PHX_CUDA(copy1d(trunc, d_trunc, E * S, t0, nt, cudaMemcpyDeviceToHost, so));
+    if (all_done) PHX_CUDA(copy1d(all_done, d_all, E * 2, t0, nt, cudaMemcpyDeviceToHost, so));
+  }
+  PHX_CUDA(cudaStreamSynchronize(f->copy_out));
+  PHX_CUDA(cudaStreamSynchronize(f->own_stream));
+  return PHX_OK;
+}
+
 
 }  // namespace phx
 
@@ -294,106 +415,8 @@ int32_t phx_rollout_host(phx_env* env, int32_t T, const float* actions,
   PHX_REQUIRE(T >= 1, PHX_ERR_INVALID, "T must be >= 1");
   Family* f = env->fam;
   PHX_CUDA(cudaSetDevice(f->device));
-  const size_t n = (size_t)T * f->E * (size_t)(f->spec.n_strategic > 0 ? f->spec.n_strategic : 1);
-  const size_t S = f->spec.n_strategic;
-  const size_t TE = (size_t)T * f->E;
-  auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
-  // carve one staging block: actions | action_mask | obs | obs_mask | reward | reward_mask |
-  // term | trunc | all_done
-  const size_t b_act = up(TE * S * f->spec.act_dim * sizeof(float));
-  const size_t b_am = up(TE * S);
-  const size_t b_obs = up(TE * S * f->spec.obs_dim * sizeof(float));
-  const size_t b_u8 = up(TE * S);
-  const size_t b_rew = up(TE * S * sizeof(float));
-  const size_t b_all = up(TE * 2);
-  const size_t total = b_act + b_am + b_obs + 4 * b_u8 + b_rew + b_all;
-  (void)n;
-  if (total > f->stage_bytes) {
-    PHX_CUDA(cudaStreamSynchronize(f->own_stream));
-    PHX_CUDA(cudaStreamSynchronize(f->copy_in));
-    PHX_CUDA(cudaStreamSynchronize(f->copy_out));
-    if (f->d_stage) PHX_CUDA(cudaFree(f->d_stage));
-    f->d_stage = nullptr;
-    f->stage_bytes = 0;
-    PHX_CUDA(cudaMalloc(&f->d_stage, total));
-    f->stage_bytes = total;
-  }
-  uint8_t* p = (uint8_t*)f->d_stage;
-  float* d_act = (float*)p; p += b_act;
-  uint8_t* d_am = p; p += b_am;
-  float* d_obs = (float*)p; p += b_obs;
-  uint8_t* d_om = p; p += b_u8;
-  float* d_rew = (float*)p; p += b_rew;
-  uint8_t* d_rm = p; p += b_u8;
-  uint8_t* d_term = p; p += b_u8;
-  uint8_t* d_trunc = p; p += b_u8;
-  uint8_t* d_all = p;
-  phx::StepIO io{d_act,
-                 action_mask ? d_am : nullptr,
-                 obs ? d_obs : nullptr,
-                 obs_mask ? d_om : nullptr,
-                 reward ? d_rew : nullptr,
-                 reward_mask ? d_rm : nullptr,
-                 term ? d_term : nullptr,
-                 trunc ? d_trunc : nullptr,
-                 all_done ? d_all : nullptr};
-  const size_t E = (size_t)f->E, A = (size_t)f->spec.act_dim, O = (size_t)f->spec.obs_dim;
-  // Chunked 3-stage pipeline (H2D | kernel | D2H on three streams), chunked along TIME: the rows
-  // [t0, t1) of every [T, E, ...] plane are one contiguous block, so each transfer is a single
-  // large 1-D copy (env-range chunks needed pitched 2-D copies of 16-98 KB rows, which PCIe
-  // moves ~10 % slower), and every family can do it -- a chunk is just a shorter rollout that
-  // continues from the state the previous launch left in HBM.  PCIe is full duplex: the input
-  // copy of chunk c+1 and the output copy of chunk c-1 overlap the kernel of chunk c.
-  const int chunks = (T >= 8 && TE >= 65536 && !f->tracking()) ? 8 : 1;
-  auto copy1d = [&](void* dst, const void* src, size_t row_bytes, size_t t0, size_t nt,
-                    cudaMemcpyKind k, cudaStream_t st) {
-    if (row_bytes == 0 || nt == 0) return cudaSuccess;
-    return cudaMemcpyAsync((char*)dst + t0 * row_bytes, (const char*)src + t0 * row_bytes,
-                           nt * row_bytes, k, st);
-  };
-  // Chunk boundaries grow geometrically at the front: the first output copy can only start after
-  // the first chunk's input copy and kernel, so a short first chunk shortens the pipeline fill
-  // (uniform eighths: 3.3 MB of actions = 80 us before the D2H engine has anything to do).
-  static const int kFrac[9] = {0, 2, 6, 14, 28, 46, 64, 82, 100};  // percent of T, cumulative
-  auto bound = [&](int c) {
-    return chunks == 1 ? (size_t)(c ? T : 0) : ((size_t)T * kFrac[c] + 50) / 100;
-  };
-  for (int c = 0; c < chunks; ++c) {
-    const size_t t0 = bound(c), t1 = bound(c + 1);
-    const size_t nt = t1 - t0;
-    if (nt == 0) continue;
-    if (actions)
-      PHX_CUDA(copy1d(d_act, actions, E * S * A * sizeof(float), t0, nt, cudaMemcpyHostToDevice, f->copy_in));
-    if (action_mask)
-      PHX_CUDA(copy1d(d_am, action_mask, E * S, t0, nt, cudaMemcpyHostToDevice, f->copy_in));
-    PHX_CUDA(cudaEventRecord(f->ev_in[c], f->copy_in));
-    PHX_CUDA(cudaStreamWaitEvent(f->own_stream, f->ev_in[c], 0));
-    phx::StepIO ic = io;  // the chunk's rows of every plane
-    ic.actions = io.actions + t0 * E * S * A;
-    if (ic.action_mask) ic.action_mask += t0 * E * S;
-    if (ic.obs) ic.obs += t0 * E * S * O;
-    if (ic.obs_mask) ic.obs_mask += t0 * E * S;
-    if (ic.reward) ic.reward += t0 * E * S;
-    if (ic.reward_mask) ic.reward_mask += t0 * E * S;
-    if (ic.term) ic.term += t0 * E * S;
-    if (ic.trunc) ic.trunc += t0 * E * S;
-    if (ic.all_done) ic.all_done += t0 * E * 2;
-    const int32_t rc = f->rollout((int32_t)nt, ic, f->own_stream);
-    if (rc != PHX_OK) return rc;
-    PHX_CUDA(cudaEventRecord(f->ev_k[c], f->own_stream));
-    PHX_CUDA(cudaStreamWaitEvent(f->copy_out, f->ev_k[c], 0));
-    cudaStream_t so = f->copy_out;
-    if (obs) PHX_CUDA(copy1d(obs, d_obs, E * S * O * sizeof(float), t0, nt, cudaMemcpyDeviceToHost, so));
-    if (obs_mask) PHX_CUDA(copy1d(obs_mask, d_om, E * S, t0, nt, cudaMemcpyDeviceToHost, so));
-    if (reward) PHX_CUDA(copy1d(reward, d_rew, E * S * sizeof(float), t0, nt, cudaMemcpyDeviceToHost, so));
-    if (reward_mask) PHX_CUDA(copy1d(reward_mask, d_rm, E * S, t0, nt, cudaMemcpyDeviceToHost, so));
-    if (term) PHX_CUDA(copy1d(term, d_term, E * S, t0, nt, cudaMemcpyDeviceToHost, so));
-    if (trunc) PHX_CUDA(copy1d(trunc, d_trunc, E * S, t0, nt, cudaMemcpyDeviceToHost, so));
-    if (all_done) PHX_CUDA(copy1d(all_done, d_all, E * 2, t0, nt, cudaMemcpyDeviceToHost, so));
-  }
-  PHX_CUDA(cudaStreamSynchronize(f->copy_out));
-  PHX_CUDA(cudaStreamSynchronize(f->own_stream));
-  return PHX_OK;
+  phx::StepIO h{actions, action_mask, obs, obs_mask, reward, reward_mask, term, trunc, all_done};
+  return f->rollout_host(T, h);
 }
 
 static int32_t field_copy(phx_env* env, int32_t field, int32_t index, void* host, uint64_t bytes,
@@ -536,6 +559,21 @@ int32_t phx_poll_errors(phx_env* env, int32_t* n_bad, int32_t* first_env, int32_
 int32_t phx_selftest_ratio(int32_t device, int32_t den, int32_t lo, int32_t count,
                            float* host_out) {
   return phx::selftest_ratio(device, den, lo, count, host_out);
+}
+
+int32_t phx_selftest_wire_expand(int32_t max_stock, int32_t cap, const uint32_t* wire, uint64_t n,
+                                 int32_t threads, float* obs, float* reward, uint8_t* all_done) {
+  PHX_REQUIRE(max_stock > 0 && cap > 0 && threads >= 1 && wire && obs && reward && all_done,
+              PHX_ERR_INVALID, "bad arguments");
+  phx::HostPool pool(threads);
+  phx::sc_wire_expand(pool, phx::ScWireParams{max_stock, cap}, wire, (size_t)n, obs, reward,
+                      all_done);
+  return PHX_OK;
+}
+
+uint32_t phx_selftest_wire_pack(int32_t stock, int32_t sales, int32_t missed, int32_t truncated,
+                                int32_t was_reset) {
+  return phx::scw_pack(stock, sales, missed, truncated != 0, was_reset != 0);
 }
 
 }  // extern "C"

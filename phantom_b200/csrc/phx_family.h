@@ -5,10 +5,12 @@
 // stage, done sets, fault words, message trace) lives here; the agent state columns and the
 // kernels live in fam_<name>.cu.
 #pragma once
+#include <memory>
 #include <string>
 #include <vector>
 
 #include "phx_common.cuh"
+#include "phx_hostpool.h"
 
 namespace phx {
 
@@ -34,6 +36,10 @@ class Family {
     set_error("this env class / kernel variant has no run-time specialisation");
     return PHX_ERR_UNSUPPORTED;
   }
+  // phx_rollout_host: every pointer of `host` is HOST memory.  The default stages the planes in
+  // device memory and runs a chunked three-stream pipeline (H2D | kernel | D2H); a family may
+  // override it with a cheaper wire format for its results.
+  virtual int32_t rollout_host(int32_t T, const StepIO& host);
   // Family state columns (field >= PHX_FIELD_FAMILY); returns PHX_ERR_INVALID if unknown.
   virtual int32_t family_field(int32_t field, int32_t index, void** dev_ptr, size_t* bytes) = 0;
   virtual const char* exec_name() const = 0;
@@ -62,7 +68,13 @@ class Family {
   size_t stage_bytes = 0;
   cudaStream_t own_stream = nullptr;
   cudaStream_t copy_in = nullptr, copy_out = nullptr;  // phx_rollout_host pipeline
-  cudaEvent_t ev_in[8] = {}, ev_k[8] = {};
+  cudaEvent_t ev_in[8] = {}, ev_k[8] = {}, ev_out[8] = {};
+  int32_t ensure_stage(size_t bytes);  // (re)allocates d_stage to at least `bytes`
+  HostPool& host_pool() {              // host threads of the *_host entry points, built on demand
+    if (!pool_) pool_.reset(new HostPool(HostPool::default_threads()));
+    return *pool_;
+  }
+  std::unique_ptr<HostPool> pool_;
 
   FaultSink fault_sink() const { return FaultSink{d_err, d_nfaults}; }
   TraceSink trace_sink() const { return TraceSink{d_trace, d_trace_cnt, spec.trace_capacity}; }

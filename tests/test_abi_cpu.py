@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_spec_layout_matches_compiled_struct():
     assert L.lib.phx_sizeof_spec() == C.sizeof(L.PhxSpec)
-    assert L.lib.phx_abi_version() == L.PHX_ABI_VERSION == 4
+    assert L.lib.phx_abi_version() == L.PHX_ABI_VERSION == 5
 
 
 def test_no_cpu_fallback():
@@ -220,3 +220,41 @@ def test_single_agent_adapter_validation():
         ph.SingleAgentEnvAdapter(sm.example_env, "s1", {"s1": (ph.Policy, {})})
     with pytest.raises(ValueError, match="has not been defined a policy"):
         ph.SingleAgentEnvAdapter(sm.example_env, "s1", {"b1": (ph.Policy, {})})
+
+
+def _aligned(shape, dtype, skew=0):
+    nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    raw = np.empty(nbytes + 128, np.uint8)
+    off = (-raw.ctypes.data) % 64 + skew * np.dtype(dtype).itemsize
+    return raw[off:off + nbytes].view(dtype).reshape(shape)
+
+
+@pytest.mark.parametrize("threads,skew", [(1, 0), (3, 0), (8, 0), (2, 1)])
+def test_wire_expansion_equals_the_reference_formulas(threads, skew):
+    """Host side of phx_rollout_host's compact supply-chain wire format (no GPU needed): one
+    32-bit word per env-step expands to exactly the float32 values the reference computes --
+    obs = float32(n / d) (supply_chain.py:124-134), reward = float32(sales - 0.1 * stock)
+    (:144-147) -- on the vector path (aligned planes), the scalar path (skewed planes) and the
+    ragged tails of every thread's slice."""
+    r = np.random.RandomState(threads)
+    n = 20011
+    stock = r.randint(-32768, 32768, n)
+    stock[:4000] = r.randint(0, 101, 4000)
+    sales, missed = r.randint(0, 128, n), r.randint(0, 128, n)
+    trunc, reset = r.randint(0, 2, n), r.randint(0, 2, n)
+    words = (((stock + 32768) & 0xFFFF).astype(np.uint32) | (sales.astype(np.uint32) << 16) |
+             (missed.astype(np.uint32) << 23) | (trunc.astype(np.uint32) << 30) |
+             (reset.astype(np.uint32) << 31))
+    for i in range(0, n, 997):  # the device-side packer agrees on the layout
+        assert L.lib.phx_selftest_wire_pack(int(stock[i]), int(sales[i]), int(missed[i]),
+                                            int(trunc[i]), int(reset[i])) == words[i]
+    obs, rew, ad = _aligned((n, 3), np.float32, skew), _aligned((n,), np.float32, skew), \
+        _aligned((n, 2), np.uint8, skew)
+    L.check(L.lib.phx_selftest_wire_expand(100, 25, words.ctypes.data, n, threads,
+                                           obs.ctypes.data, rew.ctypes.data, ad.ctypes.data))
+    shown = np.where(reset == 1, 0, stock)
+    want = np.stack([(shown / 100).astype(np.float32), (sales / 25).astype(np.float32),
+                     (missed / 25).astype(np.float32)], axis=1)
+    assert np.array_equal(obs, want)
+    assert np.array_equal(rew, (sales - 0.1 * stock).astype(np.float32))
+    assert np.array_equal(ad[:, 1], trunc) and not ad[:, 0].any()

@@ -134,3 +134,55 @@ def test_rollout_host_pipeline_chunks_along_time():
         assert_batchsteps_equal(dev, hb)
         a.check_errors(); b.check_errors()
         a.close(); b.close()
+
+
+def _host_planes(T, E):
+    import torch
+
+    pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()
+    return pin((T, E, 1, 3), torch.float32), pin((T, E, 1), torch.float32), pin((T, E, 2), torch.uint8)
+
+
+@pytest.mark.parametrize("lo,hi,expect_wire", [(0.0, 100.0, True), (-40.0, 140.0, True),
+                                               (-60000.0, 100.0, False)])
+def test_rollout_host_compact_wire_equals_device_planes(lo, hi, expect_wire, monkeypatch):
+    """The lean host-buffer call of the supply chain moves ONE 32-bit word per env-step across
+    PCIe and expands it on host threads (csrc/phx_sc_wire.*): the float32 planes must equal the
+    device path's bit for bit -- in distribution, with negative stock / sales (values outside the
+    wire fields: the call falls back to the float planes the kernel also wrote), across
+    auto-reset wraps and over two consecutive calls."""
+    import torch
+
+    from phantom_b200 import _lib as L
+    from phantom_b200.envs.supply_chain import SupplyChainEnv
+
+    E, T, seed = 8192, 29, 14
+    r = np.random.RandomState(7)
+    tapes = [r.uniform(lo, hi, size=(T, E, 1, 1)).astype(np.float32) for _ in range(2)]
+    dev = SupplyChainEnv(num_envs=E, seed=seed, num_steps=13, auto_reset=True)
+    host = SupplyChainEnv(num_envs=E, seed=seed, num_steps=13, auto_reset=True)
+    monkeypatch.setenv("PHX_NO_WIRE", "1")
+    plain = SupplyChainEnv(num_envs=E, seed=seed, num_steps=13, auto_reset=True)
+    for env in (dev, host, plain):
+        env.reset_batch()
+    h_obs, h_rew, h_all = _host_planes(T, E)
+    p_obs, p_rew, p_all = _host_planes(T, E)
+    for A in tapes:
+        want = dev.rollout_batch(A)
+        a = torch.as_tensor(A).pin_memory()
+        for env, (o, rw, ad) in ((host, (h_obs, h_rew, h_all)), (plain, (p_obs, p_rew, p_all))):
+            o.fill_(-1.0); rw.fill_(-1.0); ad.fill_(7)
+            L.check(L.lib.phx_rollout_host(env._handle, T, a.data_ptr(), None, o.data_ptr(), None,
+                                           rw.data_ptr(), None, None, None, ad.data_ptr()))
+            assert torch.equal(o, want.observations.cpu())
+            assert torch.equal(rw, want.rewards.cpu())
+            assert torch.equal(ad, want.all_done.cpu())
+    if not expect_wire:  # the out-of-range tape really left the wire fields
+        stock = np.asarray(dev.agents["SHOP"].stock)
+        assert stock.min() < -32768 or np.asarray(dev.agents["SHOP"].sales).min() < 0
+    shop = lambda env: np.stack([np.asarray(getattr(env.agents["SHOP"], c))
+                                 for c in ("stock", "sales", "missed_sales")], 1)
+    assert np.array_equal(shop(dev), shop(host)) and np.array_equal(shop(dev), shop(plain))
+    for env in (dev, host, plain):
+        env.check_errors()
+        env.close()

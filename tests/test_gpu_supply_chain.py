@@ -168,6 +168,34 @@ def test_small_and_ragged_env_counts_against_vectorised_oracle(sc, E):
     env.close()
 
 
+@pytest.mark.parametrize("num_steps,T,E", [(10, 57, 1000), (100, 100, 4096), (7, 40, 333), (4, 19, 64),
+                                           (3, 11, 100)])
+def test_fast_kernel_variants_agree(sc, monkeypatch, num_steps, T, E):
+    """The three schedule-specialised kernels (PHX_SC_KERNEL = 1: round-1 thread-per-env, 2:
+    closed-form fill + aligned groups, 3: time-parallel, with 4 or 2 warps per 32 envs) produce
+    identical planes and state, with auto-reset wraps inside the launch, launches that start at
+    every clock phase (three consecutive rollouts of T steps) and negative actions."""
+    r = np.random.RandomState(T)
+    A = [r.uniform(-30, 130, size=(T, E, 1, 1)).astype(np.float32) for _ in range(3)]
+    results = []
+    for variant, warps in ((1, 4), (2, 4), (3, 4), (3, 2)):
+        monkeypatch.setenv("PHX_SC_KERNEL", str(variant))
+        monkeypatch.setenv("PHX_SC_WARPS", str(warps))
+        env = sc.SupplyChainEnv(num_envs=E, seed=12, num_steps=num_steps, auto_reset=True)
+        env.reset_batch()
+        outs = [[x.clone() for x in env.rollout_batch(a)] for a in A]
+        results.append((outs, shop_state(env), env.field(0, np.int32), env.field(1, np.int32)))
+        env.check_errors()
+        env.close()
+    base = results[0]
+    for other in results[1:]:
+        for oa, ob in zip(base[0], other[0]):
+            for x, y in zip(oa, ob):
+                assert torch.equal(x, y)
+        assert np.array_equal(base[1], other[1])
+        assert np.array_equal(base[2], other[2]) and np.array_equal(base[3], other[3])
+
+
 def test_sharding_invariance(sc):
     """Results do not depend on how envs are split over handles (multi-GPU sharding uses
     env_offset; here two handles on one GPU)."""
