@@ -60,7 +60,10 @@ CONFIGS = {
                   "100-step episodes; one bench step = one phx_rollout launch = 100 transitions "
                   "per env, auto-reset"),
         E=131072, scaling="strong", T=100, S=4, O=2, lean=False, act_scale=1.0, binary_from=None,
-        b_io=4 * (4 + 8 + 4 + 4) + 2, b_state=2 * (16 + 8 + 8 * (16 + 4) + 4), nbuf=2),
+        b_io=4 * (4 + 8 + 4 + 4) + 2, b_state=2 * (16 + 8 + 8 * (16 + 4) + 4), nbuf=2,
+        # env.specialise(): the step kernel is rebuilt at run time (nvcc -cubin, cached) with this
+        # env class as a compile-time constant and its STATIC message schedule (phantom_b200/jit.py)
+        specialise=True),
     "C5": dict(
         workload=("dense graph C5: 16384 envs in total (sharded over the GPUs) x 128 agents, "
                   "complete graph, BatchResolver(round_limit=2), 16 256 + 128 messages per step, "
@@ -382,6 +385,11 @@ def run_config(name, args, torch, dev, rank, world, local):
         E, offset = c["E"] // world, rank * (c["E"] // world)
     env = make_env(name, num_envs=E, seed=SEED, device=local, env_offset=offset, auto_reset=True)
     env.reset_batch()
+    if c.get("specialise"):
+        try:
+            env.specialise()
+        except Exception as exc:  # no nvcc on the box: the generic kernel still measures
+            print(f"[bench] {name}: specialise() failed, generic kernel: {exc!r}", file=sys.stderr)
     NBUF = c["nbuf"]
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     acts, outs = [], []

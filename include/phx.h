@@ -61,9 +61,13 @@ typedef enum phx_fault {
   PHX_FAULT_QUEUE_OVERFLOW = 6,   /* engine capacity exceeded (no reference analogue)  */
   PHX_FAULT_INVALID_ACTION = 7,   /* non-finite / out-of-contract action value
                                      (ValueError/OverflowError from int(round(a)))     */
-  PHX_FAULT_UNRESOLVED_MAIL = 8   /* a stage handler that does not call resolve_network()
+  PHX_FAULT_UNRESOLVED_MAIL = 8,  /* a stage handler that does not call resolve_network()
                                      left messages queued: the reference would carry them
                                      into a later step's resolve; the device does not     */
+  PHX_FAULT_PLAN_MISMATCH = 9     /* a step kernel specialised with a STATIC message schedule
+                                     (phx_jit_source) saw a send its device program did not
+                                     declare: the program's act_sends / handle_sends signature
+                                     is wrong (no reference analogue; use the generic kernel) */
 } phx_fault;
 
 /* Which step loop drives the env (phantom/env.py, fsm.py, stackelberg.py). */
@@ -329,6 +333,11 @@ int32_t phx_selftest_ratio(int32_t device, int32_t den, int32_t lo, int32_t coun
  * encode_observation / compute_reward, supply_chain.py:124-147).  phx_selftest_wire_expand runs
  * that expansion on `n` words into obs float[n,3], reward float[n], all_done uint8[n,2];
  * phx_selftest_wire_pack builds one word. */
+/* phx_jit_source for an env class WITHOUT a device: the text of the specialised translation unit
+ * that a handle of `num_envs` envs of `spec` would get (build-time check that generated units
+ * compile; see phx_jit_source). */
+int32_t phx_selftest_jit_source(const phx_spec* spec, int32_t num_envs, uint64_t seed, char* buf,
+                                uint64_t buf_bytes, uint64_t* needed);
 int32_t phx_selftest_wire_expand(int32_t max_stock, int32_t cap, const uint32_t* wire, uint64_t n,
                                  int32_t threads, float* obs, float* reward, uint8_t* all_done);
 uint32_t phx_selftest_wire_pack(int32_t stock, int32_t sales, int32_t missed, int32_t truncated,

@@ -27,7 +27,8 @@ PHX_ABI_VERSION = 5
 PHX_OK, PHX_ERR_INVALID, PHX_ERR_CUDA, PHX_ERR_UNSUPPORTED, PHX_ERR_NO_DEVICE = 0, -1, -2, -3, -4
 # phx_fault
 (FAULT_NONE, FAULT_NO_EDGE, FAULT_BAD_PAYLOAD_TYPE, FAULT_UNKNOWN_MSG_TYPE, FAULT_ROUND_LIMIT,
- FAULT_BAD_TRANSITION, FAULT_QUEUE_OVERFLOW, FAULT_INVALID_ACTION, FAULT_UNRESOLVED_MAIL) = range(9)
+ FAULT_BAD_TRANSITION, FAULT_QUEUE_OVERFLOW, FAULT_INVALID_ACTION, FAULT_UNRESOLVED_MAIL,
+ FAULT_PLAN_MISMATCH) = range(10)
 # phx_rule_lhs / phx_cmp (device form of an FSM stage handler)
 RULE_ALWAYS, RULE_STEP, RULE_AGENT_WORD, RULE_ENV_WORD = range(4)
 CMP_LT, CMP_LE, CMP_EQ, CMP_NE, CMP_GE, CMP_GT = range(6)
@@ -138,6 +139,7 @@ SYMBOLS = {
     "phx_poll_errors": (C.c_int32, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                     C.POINTER(C.c_int32), C.c_int32]),
     "phx_selftest_ratio": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
+    "phx_selftest_jit_source": (C.c_int32, [C.POINTER(PhxSpec), C.c_int32, C.c_uint64, _P, C.c_uint64, _P]),
     "phx_selftest_wire_expand": (C.c_int32, [C.c_int32, C.c_int32, _P, C.c_uint64, C.c_int32,
                                              _P, _P, _P]),
     "phx_selftest_wire_pack": (C.c_uint32, [C.c_int32] * 5),

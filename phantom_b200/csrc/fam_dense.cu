@@ -28,11 +28,13 @@
 // plus a term that depends on the sender only through its class c = (2 s) % 5; so the max over
 // senders is the max over the five classes of (class maximum + tail_r[c]), the first arg-max is
 // the lowest slot among the classes' first arg-maxes, and "but me" is handled by keeping the
-// best TWO senders of every class.  Warp REDUX.MAX / REDUX.ADD + one shared-memory atomic per
-// warp and class replace the 127-message scan of every receiver (~520 instructions per agent
-// and step -> ~100); any other graph / partial action set takes the pull path, in the same
-// kernel, per env and step (the choice is block-uniform).  This is the north star's
-// "warp-ballot / shfl reductions for BatchResolver aggregation".
+// best TWO senders of every class.  Eleven warp reductions (REDUX.MAX / REDUX.ADD) per warp and
+// a 4-way merge per class replace the 127-message scan of every receiver (~520 instructions per
+// agent and step -> ~200); any other graph / partial action set takes the pull path, in the
+// same kernel, per env and step (the choice is block-uniform).  This is the north star's
+// "warp-ballot / shfl reductions for BatchResolver aggregation".  A step has three block
+// barriers: after the publish, after the Acks, and (shared with the next step's first one)
+// before thread 0 issues the TMA stores of the staged rows.
 // Outputs of a step are staged in shared memory and written with TMA bulk stores
 // (cp.async.bulk.global.shared::cta, SASS UBLKCP): one env's rows are contiguous in every
 // [T,E,S,...] plane.
@@ -87,8 +89,8 @@ struct DenseSmem {
   uint32_t any_ack;
   // reduction form of round 0 (complete graph, everybody sent): per sender class c = (2 s) % 5
   // the best and second-best sender as keys value * 128 + (127 - slot), and the sum of all values
-  int32_t top1[5], top2[5];
-  int32_t val_sum;
+  alignas(16) int2 wtop[5][4];   // [class][warp] (best, second best) keys of the warp's senders
+  alignas(16) int32_t wsum[4];   // [warp] sum of the warp's senders' values
   DenseStage stage[2];
 };
 
@@ -123,12 +125,12 @@ __global__ void __launch_bounds__(DN_MAX) dense_step_kernel(const DenseArgs a) {
   for (int k = 0; k < 5; ++k) tailtab[k] = (k + 3 * slot) % 5;
   // reduction form of round 0: this sender's class, the class populations and "all n agents"
   const int myclass = (2 * slot) % 5;
-  int class_cnt[5];
+  int tails_all = 0;  // sum over ALL senders s of tailtab[(2 s) % 5]
   uint32_t full_w[4];
 #pragma unroll
   for (int c = 0; c < 5; ++c) {
     const int s0 = (3 * c) % 5;  // (2 s) % 5 == c  <=>  s % 5 == (3 c) % 5
-    class_cnt[c] = s0 < n ? (n - 1 - s0) / 5 + 1 : 0;
+    tails_all += (s0 < n ? (n - 1 - s0) / 5 + 1 : 0) * tailtab[c];
   }
 #pragma unroll
   for (int w = 0; w < 4; ++w)
@@ -138,6 +140,19 @@ __global__ void __launch_bounds__(DN_MAX) dense_step_kernel(const DenseArgs a) {
                               (sp.flags & PHX_FLAG_NO_PAYLOAD_CHECKS);
   const bool ok_send_ack = ((sp.sender_ok[DN_ACK][slot >> 5] >> (slot & 31)) & 1u) ||
                            (sp.flags & PHX_FLAG_NO_PAYLOAD_CHECKS);
+  // TMA bulk stores of one step's staged rows (issued by thread 0 one barrier after the rows
+  // were written, so that no barrier exists for the stores alone)
+  auto issue_stores = [&](int t) {
+    const DenseStage& sg = sm.stage[t & 1];
+    const size_t base = ((size_t)t * sp.E + e) * n;
+    if (a.io.obs) bulk_store(a.io.obs + base * 3, sg.obs, (uint32_t)n * 12u);
+    if (a.io.reward) bulk_store(a.io.reward + base, sg.reward, (uint32_t)n * 4u);
+    if (a.io.obs_mask) bulk_store(a.io.obs_mask + base, sg.obs_mask, (uint32_t)n);
+    if (a.io.reward_mask) bulk_store(a.io.reward_mask + base, sg.reward_mask, (uint32_t)n);
+    if (a.io.term) bulk_store(a.io.term + base, sg.term, (uint32_t)n);
+    if (a.io.trunc) bulk_store(a.io.trunc + base, sg.trunc, (uint32_t)n);
+    bulk_commit();
+  };
 
   for (int t = 0; t < a.T; ++t) {
     const size_t row = (size_t)t * sp.E + e;
@@ -166,15 +181,33 @@ __global__ void __launch_bounds__(DN_MAX) dense_step_kernel(const DenseArgs a) {
           ((adj[0] & ~sp.receiver_ok[DN_SIGNAL][0]) | (adj[1] & ~sp.receiver_ok[DN_SIGNAL][1]) |
            (adj[2] & ~sp.receiver_ok[DN_SIGNAL][2]) | (adj[3] & ~sp.receiver_ok[DN_SIGNAL][3])))
         fault = fault ? fault : PHX_FAULT_BAD_PAYLOAD_TYPE;
-      sm.vals[slot] = st[0];  // one word per sender; the receivers pull
+      sm.vals[slot] = st[0];  // one word per sender; the receivers of the pull form read it
+    }
+    // reduce form, this warp's part: the sum of its senders' values and, per sender class, its
+    // best two senders as keys value * 128 + (127 - slot) (a higher key = a higher value, then
+    // the LOWER slot: the first sender attaining the maximum wins, as in the reference's scan)
+    if (!TRACK && sp.complete) {
+      const int key = sends ? st[0] * 128 + (127 - slot) : -1;
+      const int wsum = __reduce_add_sync(0xFFFFFFFFu, sends ? st[0] : 0);
+      int2 mine = make_int2(-1, -1);
+#pragma unroll
+      for (int c = 0; c < 5; ++c) {
+        const int kc = myclass == c ? key : -1;
+        const int t1 = __reduce_max_sync(0xFFFFFFFFu, kc);
+        const int t2 = __reduce_max_sync(0xFFFFFFFFu, kc == t1 ? -1 : kc);
+        if (lane == c) mine = make_int2(t1, t2);
+      }
+      if (lane < 5) sm.wtop[lane][warp] = mine;
+      if (lane == 5) sm.wsum[warp] = wsum;
     }
     // ---- pre_message_resolution
     st[1] = 0; st[2] = 0; st[3] = -1; st[4] = 0; st[5] = 0;
     sm.ack_cnt[slot] = 0;
     sm.ack_sum[slot] = 0;
-    if (slot < 5) sm.top1[slot] = sm.top2[slot] = -1;
-    if (slot == 5) sm.val_sum = 0;
+    // the staged rows of step t - 2 (same buffer as this step's) must have been read out
+    if (bulk && slot == 0) bulk_wait_read<0>();
     __syncthreads();
+    if (bulk && slot == 0 && t > 0) issue_stores(t - 1);
 
     // ---- round 0: handle_batch over this receiver's mailbox row (batch order = sender order)
     const uint32_t any_sent = sm.sent[0] | sm.sent[1] | sm.sent[2] | sm.sent[3];
@@ -186,29 +219,17 @@ __global__ void __launch_bounds__(DN_MAX) dense_step_kernel(const DenseArgs a) {
                              sm.sent[0] == full_w[0] && sm.sent[1] == full_w[1] &&
                              sm.sent[2] == full_w[2] && sm.sent[3] == full_w[3];
     if (reduce_form) {  // block-uniform
-      const int key = is_agent ? st[0] * 128 + (127 - slot) : -1;
-      const int wsum = __reduce_add_sync(0xFFFFFFFFu, is_agent ? st[0] : 0);
-      if (lane == 0) atomicAdd(&sm.val_sum, wsum);
-#pragma unroll
-      for (int c = 0; c < 5; ++c) {
-        const int m = __reduce_max_sync(0xFFFFFFFFu, myclass == c ? key : -1);
-        if (lane == 0 && m >= 0) atomicMax(&sm.top1[c], m);
-      }
-      __syncthreads();
-#pragma unroll
-      for (int c = 0; c < 5; ++c) {  // the best sender of every class after its overall best
-        const int t1 = sm.top1[c];
-        const int m = __reduce_max_sync(0xFFFFFFFFu, (myclass == c && key != t1) ? key : -1);
-        if (lane == 0 && m >= 0) atomicMax(&sm.top2[c], m);
-      }
-      __syncthreads();
       if (is_agent) {
-        int best = INT32_MIN, best_s = -1, tails = 0;
+        int best = INT32_MIN, best_s = -1;
 #pragma unroll
         for (int c = 0; c < 5; ++c) {
-          const int t1 = sm.top1[c];
-          const int k = (127 - (t1 & 127)) == slot ? sm.top2[c] : t1;  // "but me"
-          tails += class_cnt[c] * tailtab[c];
+          // merge the four warps' (best, second best) of class c into the block's
+          const int4 q01 = *reinterpret_cast<const int4*>(&sm.wtop[c][0]);  // warps 0, 1
+          const int4 q23 = *reinterpret_cast<const int4*>(&sm.wtop[c][2]);  // warps 2, 3
+          const int g1 = max(max(q01.x, q01.z), max(q23.x, q23.z));
+          const int g2 = max(max(q01.x == g1 ? q01.y : q01.x, q01.z == g1 ? q01.w : q01.z),
+                             max(q23.x == g1 ? q23.y : q23.x, q23.z == g1 ? q23.w : q23.z));
+          const int k = (127 - (g1 & 127)) == slot ? g2 : g1;  // "but me"
           if (k >= 0) {
             const int v = (k >> 7) + tailtab[c], sdr = 127 - (k & 127);
             if (v > best || (v == best && sdr < best_s)) {  // the FIRST sender attaining the max
@@ -217,7 +238,8 @@ __global__ void __launch_bounds__(DN_MAX) dense_step_kernel(const DenseArgs a) {
             }
           }
         }
-        st[1] = sm.val_sum - st[0] + tails - (myclass + 3 * slot) % 5;  // tailtab[myclass]
+        const int4 ws = *reinterpret_cast<const int4*>(sm.wsum);
+        st[1] = ws.x + ws.y + ws.z + ws.w - st[0] + tails_all - (myclass + 3 * slot) % 5;
         st[2] = best;
         st[3] = best_s;
         ack_recv = best_s;
@@ -287,12 +309,19 @@ __global__ void __launch_bounds__(DN_MAX) dense_step_kernel(const DenseArgs a) {
       atomicAdd(&sm.ack_cnt[ack_recv], 1);
       atomicAdd(&sm.ack_sum[ack_recv], st[2]);
     }
-    const uint32_t acks_w = __ballot_sync(0xFFFFFFFFu, ack_recv >= 0);
-    if (slot == 0) sm.any_ack = 0;
-    __syncthreads();
-    if (lane == 0 && acks_w) atomicOr(&sm.any_ack, 1u);
-    __syncthreads();
-    if (sm.any_ack && sp.round_limit == 1) fault = fault ? fault : PHX_FAULT_ROUND_LIMIT;
+    bool any_ack;
+    if (reduce_form) {  // every agent answered (n >= 2): no vote needed
+      any_ack = true;
+      __syncthreads();
+    } else {
+      const uint32_t acks_w = __ballot_sync(0xFFFFFFFFu, ack_recv >= 0);
+      if (slot == 0) sm.any_ack = 0;
+      __syncthreads();
+      if (lane == 0 && acks_w) atomicOr(&sm.any_ack, 1u);
+      __syncthreads();
+      any_ack = sm.any_ack != 0;
+    }
+    if (any_ack && sp.round_limit == 1) fault = fault ? fault : PHX_FAULT_ROUND_LIMIT;
 
     // ---- round 1: the Acks (same handle_batch override): count and sum
     if (is_agent && sp.round_limit != 1 && sp.round_limit != 0) {
@@ -347,9 +376,7 @@ __global__ void __launch_bounds__(DN_MAX) dense_step_kernel(const DenseArgs a) {
     const float o1 = (float)st[2] * (1.0f / 1024.0f);
     const float o2 = (float)st[4] * (1.0f / 128.0f);
     if (bulk) {
-      // the previous use of this stage buffer (step t-2) must have been read out
-      if (slot == 0) bulk_wait_read<1>();
-      __syncthreads();
+      // (this buffer's previous rows were read out before the step's first barrier)
       sg.obs[slot * 3 + 0] = o0;
       sg.obs[slot * 3 + 1] = o1;
       sg.obs[slot * 3 + 2] = o2;
@@ -358,18 +385,7 @@ __global__ void __launch_bounds__(DN_MAX) dense_step_kernel(const DenseArgs a) {
       sg.reward_mask[slot] = 1;
       sg.term[slot] = 0;
       sg.trunc[slot] = 0;
-      fence_async_smem();
-      __syncthreads();
-      if (slot == 0) {
-        const size_t base = row * n;
-        if (a.io.obs) bulk_store(a.io.obs + base * 3, sg.obs, (uint32_t)n * 12u);
-        if (a.io.reward) bulk_store(a.io.reward + base, sg.reward, (uint32_t)n * 4u);
-        if (a.io.obs_mask) bulk_store(a.io.obs_mask + base, sg.obs_mask, (uint32_t)n);
-        if (a.io.reward_mask) bulk_store(a.io.reward_mask + base, sg.reward_mask, (uint32_t)n);
-        if (a.io.term) bulk_store(a.io.term + base, sg.term, (uint32_t)n);
-        if (a.io.trunc) bulk_store(a.io.trunc + base, sg.trunc, (uint32_t)n);
-        bulk_commit();
-      }
+      fence_async_smem();  // issued by thread 0 after the NEXT barrier (issue_stores)
     } else if (is_agent) {
       const size_t o = row * n + slot;
       if (a.io.obs) {
@@ -381,12 +397,15 @@ __global__ void __launch_bounds__(DN_MAX) dense_step_kernel(const DenseArgs a) {
       if (a.io.term) a.io.term[o] = 0;
       if (a.io.trunc) a.io.trunc[o] = 0;
     }
-    if (!bulk) __syncthreads();  // mailbox / ack arrays are rewritten by the next step
     if (slot == 0 && a.io.all_done)
       reinterpret_cast<uchar2*>(a.io.all_done)[row] = make_uchar2(n == 0, at_max ? 1 : 0);
   }
+  __syncthreads();  // the last step's staged rows are complete
   if (slot == 0) {
-    bulk_wait<0>();
+    if (bulk) {
+      issue_stores(a.T - 1);
+      bulk_wait<0>();
+    }
     a.hdr[e] = h;
   }
 #pragma unroll

@@ -152,18 +152,19 @@ struct MarketProgram {
 
   __device__ static bool encode(const Ctx& c, int* st, float* obs) {
     if (c.kind == MKT_MAKER) {
-      obs[0] = __fdiv_rn((float)st[0], (float)c.spec->iparams[2]);
-      obs[1] = __fdiv_rn((float)st[2], 100.0f);
+      const float inv = (float)c.spec->iparams[2];  // (a constant in a specialised unit)
+      obs[0] = ratio_rn(st[0], inv, 1.0f / inv);
+      obs[1] = ratio_rn(st[2], 100.0f, 1.0f / 100.0f);
       obs[2] = 0.f;
     } else {
-      obs[0] = __fdiv_rn((float)st[0], 100.0f);
-      obs[1] = __fdiv_rn((float)(st[2] < 0 ? 100 : st[1]), 100.0f);
-      obs[2] = __fdiv_rn((float)st[3], 33.0f);
+      obs[0] = ratio_rn(st[0], 100.0f, 1.0f / 100.0f);
+      obs[1] = ratio_rn(st[2] < 0 ? 100 : st[1], 100.0f, 1.0f / 100.0f);
+      obs[2] = ratio_rn(st[3], 33.0f, 1.0f / 33.0f);
     }
     return true;
   }
   __device__ static float reward(const Ctx& c, int* st) {
-    return __fdiv_rn((float)(c.kind == MKT_MAKER ? st[3] : st[4]), 100.0f);
+    return ratio_rn(c.kind == MKT_MAKER ? st[3] : st[4], 100.0f, 1.0f / 100.0f);
   }
   __device__ static bool terminated(const Ctx& c, const int* st) {
     return c.kind == MKT_MAKER && st[0] <= 0;

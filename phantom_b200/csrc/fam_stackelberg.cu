@@ -39,6 +39,24 @@ struct StackelbergProgram {
 
   __device__ static void view(const Ctx&, const int*, int*) {}
 
+#ifndef PHX_JIT_TU
+  // Static send signature (phx_engine_host.cuh build_static_plan): what act() / handle() below
+  // may send, in emission order.
+  static void act_sends(const phx_spec& s, int slot, int, std::vector<SendSig>& out) {
+    if (s.agent_kind[slot] == SK_LEADER) {  // Price to every follower neighbour, slot order
+      for (int r = 0; r < s.n_agents; ++r)
+        if (s.agent_kind[r] == SK_FOLLOWER && mask_bit(s.adjacency[slot], r))
+          out.push_back(SendSig{r, SK_PRICE});
+    } else {
+      out.push_back(SendSig{s.agent_iparam[slot][1], SK_DEMAND});
+    }
+  }
+  static void handle_sends(const phx_spec& s, int slot, int type, int sender,
+                           std::vector<SendSig>& out) {
+    if (s.agent_kind[slot] == SK_LEADER && type == SK_DEMAND) out.push_back(SendSig{sender, SK_ACK});
+  }
+#endif
+
   template <class E>
   __device__ static void act(const Ctx& c, int* st, bool has_action, const float* action, E& out) {
     const EngineSpec& sp = *c.spec;
@@ -50,8 +68,14 @@ struct StackelbergProgram {
     }
     if (c.kind == SK_LEADER) {
       st[0] = max(0, min(100, __float2int_rn(__fmul_rn(a0, 100.0f))));
+#ifdef PHX_JIT_TU  // the neighbour mask is a constant: a countable loop unrolls to straight-line sends
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+        if ((c.neighbours_of_kind(SK_FOLLOWER) >> r) & 1u) out.send(r, SK_PRICE, st[0]);
+#else
       for (uint32_t m = c.neighbours_of_kind(SK_FOLLOWER); m; m &= m - 1)
         out.send(__ffs(m) - 1, SK_PRICE, st[0]);
+#endif
     } else {
       const int qty = max(0, min(10, __float2int_rn(__fmul_rn(a0, 10.0f))));
       out.send(sp.agent_iparam[c.slot][1], SK_DEMAND, qty);
@@ -96,16 +120,17 @@ struct StackelbergProgram {
 
   __device__ static bool encode(const Ctx& c, int* st, float* obs) {
     if (c.kind == SK_LEADER) {
-      obs[0] = __fdiv_rn((float)st[3], 30.0f);
-      obs[1] = __fdiv_rn((float)st[1], (float)c.spec->iparams[0]);
+      const float cap = (float)c.spec->iparams[0];  // (a constant in a specialised unit)
+      obs[0] = ratio_rn(st[3], 30.0f, 1.0f / 30.0f);
+      obs[1] = ratio_rn(st[1], cap, 1.0f / cap);
     } else {
-      obs[0] = __fdiv_rn((float)st[1], 100.0f);
-      obs[1] = __fdiv_rn((float)st[2], 10.0f);
+      obs[0] = ratio_rn(st[1], 100.0f, 1.0f / 100.0f);
+      obs[1] = ratio_rn(st[2], 10.0f, 1.0f / 10.0f);
     }
     return true;
   }
   __device__ static float reward(const Ctx& c, int* st) {
-    return __fdiv_rn((float)(c.kind == SK_LEADER ? st[2] : st[3]), 100.0f);
+    return ratio_rn(c.kind == SK_LEADER ? st[2] : st[3], 100.0f, 1.0f / 100.0f);
   }
   __device__ static bool terminated(const Ctx&, const int*) { return false; }
   __device__ static bool truncated(const Ctx&, const int*) { return false; }

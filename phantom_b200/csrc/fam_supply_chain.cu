@@ -88,10 +88,7 @@ struct ScArgs {
 // <= 20 < 29 bits, so the float64 rounding can never land on a float32 tie.  Checked
 // exhaustively on the device by tests/test_gpu_supply_chain.py::test_ratio_exhaustive.
 __device__ __forceinline__ float sc_ratio(int num, float den, float rcp) {
-  const float x = (float)num;
-  const float q = __fmul_rn(x, rcp);
-  const float r = __fmaf_rn(-den, q, x);
-  return __fmaf_rn(r, rcp, q);
+  return ratio_rn(num, den, rcp);  // phx_common.cuh
 }
 
 // Tuning knobs (defaults = the measured best; override with -D for A/B)
@@ -411,13 +408,17 @@ struct Sc2Args {
   uint32_t* wire_overflow;
 };
 
-template <bool FULL_IO, bool VEC>
+template <bool FULL_IO, bool VEC, bool WIRE>
 __global__ void __launch_bounds__(SC_BLOCK) sc_fast2_kernel(const Sc2Args args) {
   const ScArgs& a = args.a;
   const ScPlan& p = a.p;
   extern __shared__ __align__(16) unsigned char sc2_smem[];
   float (*act_ring)[SC_BLOCK] = reinterpret_cast<float (*)[SC_BLOCK]>(sc2_smem);
   const uint8_t* dsum = sc2_smem + sizeof(float) * SC2_RING * SC_BLOCK;
+  // Programmatic dependent launch: the next launch on the stream may start its blocks and run
+  // its prologue (the table fill below) while this grid is still stepping; it waits at
+  // griddep_wait() before it touches anything a previous kernel may have written.
+  griddep_launch_dependents();
   {  // digit-sum table -> shared memory (4-byte words; the host pads the table to 16 bytes)
     const uint32_t* src = reinterpret_cast<const uint32_t*>(args.dsum);
     uint32_t* dst = reinterpret_cast<uint32_t*>(sc2_smem + sizeof(float) * SC2_RING * SC_BLOCK);
@@ -435,6 +436,7 @@ __global__ void __launch_bounds__(SC_BLOCK) sc_fast2_kernel(const Sc2Args args) 
   const int max_stock = p.max_stock, num_steps = p.num_steps;
   const bool auto_reset = (p.flags & PHX_FLAG_AUTO_RESET) != 0;
 
+  griddep_wait();  // env state, actions: written by earlier work on the stream
   int2 h = *reinterpret_cast<const int2*>(a.hdr + e);
   int4 s = a.shop[e];
   bool bad_action = false;
@@ -480,6 +482,12 @@ __global__ void __launch_bounds__(SC_BLOCK) sc_fast2_kernel(const Sc2Args args) 
   // outputs of the step; `wrap`: the step ends the episode and the env is reset in place
   auto emit = [&](const bool at_max, const bool wrap) {
     const float reward = sc_ratio(10 * s.y - s.x, 10.0f, 0.1f);
+    if (WIRE) {  // the same row as ONE word (phx_sc_wire.h), for the host-buffer path
+      const bool fits = s.x >= -SCW_STOCK_BIAS && s.x < SCW_STOCK_BIAS &&
+                        (uint32_t)s.y <= SCW_FIELD_MAX && (uint32_t)s.z <= SCW_FIELD_MAX;
+      if (!fits) *args.wire_overflow = 1u;
+      __stcs(args.wire + row, scw_pack(s.x, s.y, s.z, at_max, wrap));
+    }
     if (wrap) {  // Network.reset -> ShopAgent.reset clears the stock only
       s.x = 0;
       h.x = 0;
@@ -1009,7 +1017,7 @@ class SupplyChainFast final : public Family {
       b.a = a;
       b.dsum = d_dsum;
       b.pow5 = pow5;
-      if (sc_variant == 3 && plan.num_steps >= 4) {  // the time-parallel kernel (default)
+      if (sc_variant == 3 && plan.num_steps >= 4) {  // the time-parallel kernel
         const int grid3 = (env_count + SC3_ENVS - 1) / SC3_ENVS;
         const bool w2 = sc_warps == 2;
         b.wire = wire;
@@ -1025,10 +1033,23 @@ class SupplyChainFast final : public Family {
         return PHX_OK;
       }
       const size_t smem = sizeof(float) * SC2_RING * SC_BLOCK + ((pow5 + 15u) & ~15u);
-      if (lean && a.vec_actions) sc_fast2_kernel<false, true><<<grid, SC_BLOCK, smem, stream>>>(b);
-      else if (lean) sc_fast2_kernel<false, false><<<grid, SC_BLOCK, smem, stream>>>(b);
-      else if (a.vec_actions) sc_fast2_kernel<true, true><<<grid, SC_BLOCK, smem, stream>>>(b);
-      else sc_fast2_kernel<true, false><<<grid, SC_BLOCK, smem, stream>>>(b);
+      b.wire = wire;
+      b.wire_overflow = wire_overflow;
+      void (*kern)(const Sc2Args) =
+          wire ? (a.vec_actions ? sc_fast2_kernel<false, true, true> : sc_fast2_kernel<false, false, true>)
+          : lean ? (a.vec_actions ? sc_fast2_kernel<false, true, false> : sc_fast2_kernel<false, false, false>)
+                 : (a.vec_actions ? sc_fast2_kernel<true, true, false> : sc_fast2_kernel<true, false, false>);
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(grid);
+      cfg.blockDim = dim3(SC_BLOCK);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = use_pdl ? 1 : 0;
+      PHX_CUDA(cudaLaunchKernelEx(&cfg, kern, b));
       PHX_CUDA(cudaGetLastError());
       return PHX_OK;
     }
@@ -1055,42 +1076,60 @@ class SupplyChainFast final : public Family {
     return PHX_OK;
   }
 
-  // The compact wire word is produced by sc_fast3_kernel only, for the lean output layout.
+  // The compact wire word is produced by sc_fast2_kernel / sc_fast3_kernel, for the lean layout.
   bool wire_ok(bool lean_no_mask) const {
     const bool all_delivered_ = plan.deliver_ord == (1u << plan.nc) - 1u;
     return lean_no_mask && pow5 != 0 && !tracking() && all_delivered_ && plan.delivery_ok &&
-           sc_variant == 3 && plan.num_steps >= 4 && plan.max_stock < SCW_STOCK_BIAS &&
+           (sc_variant == 2 || (sc_variant == 3 && plan.num_steps >= 4)) &&
+           plan.max_stock < SCW_STOCK_BIAS &&
            plan.nc * plan.max_order <= (int)SCW_FIELD_MAX && !no_wire;
   }
 
-  // phx_rollout_host for the lean layout (obs + reward + all_done): the results cross PCIe as
-  // ONE 32-bit word per env-step (4 B instead of 18 B) and are expanded to the caller's float32
-  // planes by the host thread pool, chunk by chunk, while later chunks are still in flight.
-  // The expansion evaluates the same correctly rounded quotients as the kernel, so the planes
-  // are bit-identical to the device path's (tests/test_gpu_reset_and_io.py).  The kernel also
-  // writes the float planes into the device staging block: if any value of the call did not
-  // fit its wire field (|stock| >= 2^15, sales or missed outside 0..127 -- out-of-distribution
-  // actions), the planes are copied instead.
+  // phx_rollout_host for the lean layout (obs + reward + all_done).  The float32 planes are
+  // 18 B per env-step and the call is bound by what can be written into HOST memory: the DMA
+  // engine of the device->host link on one side, the host's own cores on the other.  Both are
+  // used: the first `wire_chunks` time chunks cross PCIe as ONE 32-bit word per env-step (4 B,
+  // phx_sc_wire.h) and are expanded into the caller's planes by the host thread pool, while the
+  // DMA engine copies the float planes of the later chunks straight into place.  A small
+  // controller moves the split by one chunk per call towards the point where both finish
+  // together (a 16-vCPU VM next to one GPU ends near the middle; eight ranks sharing one root
+  // complex lean on the cores).  The expansion evaluates the same correctly rounded quotients as
+  // the kernel, so every plane is bit-identical to the device path's
+  // (tests/test_gpu_reset_and_io.py); the kernel writes the float planes of ALL rows into the
+  // device staging block, and if a value did not fit its wire field (|stock| >= 2^15, sales or
+  // missed outside 0..127: out-of-distribution actions) the wire rows are re-copied from there.
+  static constexpr int NCH = 14;  // time chunks; boundaries in percent of T, finer at the front
   int32_t rollout_host(int32_t T, const StepIO& h) override {
     const bool lean = h.obs && h.reward && h.all_done && !h.obs_mask && !h.reward_mask &&
                       !h.term && !h.trunc && !h.action_mask;
-    if (!wire_ok(lean) || T < 8 || (size_t)T * E < 65536 ||
-        (uint64_t)T * (uint64_t)E * 3ull >= (1ull << 32))
+    // Opt-in (PHX_WIRE_CHUNKS = k | auto, read when the handle is created): on the hosts measured
+    // so far -- 16- and 32-vCPU VMs -- the cores write the float planes at ~30 GB/s in total,
+    // slower than the link's DMA engine (~50 GB/s), so the default is the plain staged copy
+    // (profiles/r02_e2e_wire_sweep.txt).
+    if (wire_mode.empty() || wire_mode == "0" || !wire_ok(lean) || T < 2 * NCH ||
+        (size_t)T * E < 65536 || (uint64_t)T * (uint64_t)E * 3ull >= (1ull << 32))
       return Family::rollout_host(T, h);
+    static const int kFrac[NCH + 1] = {0, 2, 6, 12, 20, 28, 36, 44, 52, 60, 68, 76, 84, 92, 100};
+    auto bound = [&](int c) { return ((size_t)T * kFrac[c] + 50) / 100; };
     const size_t TE = (size_t)T * E;
     auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
     const size_t b_act = up(TE * 4), b_obs = up(TE * 12), b_rew = up(TE * 4), b_all = up(TE * 2),
                  b_wire = up(TE * 4);
-    const size_t total = b_act + b_obs + b_rew + b_all + b_wire + 256;
-    int32_t rc = ensure_stage(total);
+    int32_t rc = ensure_stage(b_act + b_obs + b_rew + b_all + b_wire + 256);
     if (rc != PHX_OK) return rc;
-    if (TE * 4 > h_wire_bytes) {  // pinned landing buffer of the wire plane
+    if (TE * 4 > h_wire_bytes) {  // pinned landing buffer of the wire words
       if (h_wire) cudaFreeHost(h_wire);
       h_wire = nullptr;
       h_wire_bytes = 0;
       PHX_CUDA(cudaMallocHost(&h_wire, TE * 4));
       h_wire_bytes = TE * 4;
     }
+    if (wire_chunks < 0) {  // first call: a fixed split, or a first guess for the controller
+      wire_fixed = wire_mode != "auto";
+      wire_chunks = wire_fixed ? std::atoi(wire_mode.c_str()) : std::min(NCH / 2, host_pool().size());
+      wire_chunks = std::max(0, std::min(NCH, wire_chunks));
+    }
+    const int nw = wire_chunks;
     uint8_t* q = (uint8_t*)d_stage;
     float* d_act = (float*)q; q += b_act;
     float* d_obs = (float*)q; q += b_obs;
@@ -1099,10 +1138,17 @@ class SupplyChainFast final : public Family {
     uint32_t* d_wire = (uint32_t*)q; q += b_wire;
     uint32_t* d_over = (uint32_t*)q;
     PHX_CUDA(cudaMemsetAsync(d_over, 0, sizeof(uint32_t), own_stream));
-    ScWireParams wp{plan.max_stock, plan.nc * plan.max_order};
-    static const int kFrac[9] = {0, 2, 6, 14, 28, 46, 64, 82, 100};  // see Family::rollout_host
-    auto bound = [&](int c) { return ((size_t)T * kFrac[c] + 50) / 100; };
-    for (int c = 0; c < 8; ++c) {
+    const ScWireParams wp{plan.max_stock, plan.nc * plan.max_order};
+    auto planes_d2h = [&](size_t t0, size_t nt, cudaStream_t st) -> cudaError_t {
+      cudaError_t e1 = cudaMemcpyAsync(h.obs + t0 * E * 3, d_obs + t0 * E * 3, nt * E * 12,
+                                       cudaMemcpyDeviceToHost, st);
+      if (e1 != cudaSuccess) return e1;
+      e1 = cudaMemcpyAsync(h.reward + t0 * E, d_rew + t0 * E, nt * E * 4, cudaMemcpyDeviceToHost, st);
+      if (e1 != cudaSuccess) return e1;
+      return cudaMemcpyAsync(h.all_done + t0 * E * 2, d_all + t0 * E * 2, nt * E * 2,
+                             cudaMemcpyDeviceToHost, st);
+    };
+    for (int c = 0; c < NCH; ++c) {
       const size_t t0 = bound(c), nt = bound(c + 1) - t0;
       if (nt == 0) continue;
       PHX_CUDA(cudaMemcpyAsync(d_act + t0 * E, h.actions + t0 * E, nt * E * 4,
@@ -1115,26 +1161,36 @@ class SupplyChainFast final : public Family {
       if (rc != PHX_OK) return rc;
       PHX_CUDA(cudaEventRecord(ev_k[c], own_stream));
       PHX_CUDA(cudaStreamWaitEvent(copy_out, ev_k[c], 0));
-      PHX_CUDA(cudaMemcpyAsync(h_wire + t0 * E, d_wire + t0 * E, nt * E * 4,
-                               cudaMemcpyDeviceToHost, copy_out));
+      if (c < nw)
+        PHX_CUDA(cudaMemcpyAsync(h_wire + t0 * E, d_wire + t0 * E, nt * E * 4,
+                                 cudaMemcpyDeviceToHost, copy_out));
+      else
+        PHX_CUDA(planes_d2h(t0, nt, copy_out));
       PHX_CUDA(cudaEventRecord(ev_out[c], copy_out));
     }
     uint32_t over = 0;
     PHX_CUDA(cudaMemcpyAsync(&over, d_over, sizeof(over), cudaMemcpyDeviceToHost, copy_out));
-    // expand chunk c while the copies of the later chunks run
-    for (int c = 0; c < 8; ++c) {
+    PHX_CUDA(cudaEventRecord(ev_out[NCH], copy_out));
+    // expand the wire chunks as they land, while the DMA engine works on the plane chunks
+    bool dma_done_early = false;  // everything had landed before the last expansion started
+    for (int c = 0; c < nw; ++c) {
       const size_t t0 = bound(c), nt = bound(c + 1) - t0;
       if (nt == 0) continue;
       PHX_CUDA(cudaEventSynchronize(ev_out[c]));
+      if (c == nw - 1) dma_done_early = cudaEventQuery(ev_out[NCH]) == cudaSuccess;
       sc_wire_expand(host_pool(), wp, h_wire + t0 * E, nt * E, h.obs + t0 * E * 3,
                      h.reward + t0 * E, h.all_done + t0 * E * 2);
     }
+    const bool cpu_done_early = cudaEventQuery(ev_out[NCH]) != cudaSuccess;  // DMA still busy
     PHX_CUDA(cudaStreamSynchronize(copy_out));
     PHX_CUDA(cudaStreamSynchronize(own_stream));
-    if (over) {  // a value did not fit the wire format: take the float planes the kernel wrote
-      PHX_CUDA(cudaMemcpy(h.obs, d_obs, TE * 12, cudaMemcpyDeviceToHost));
-      PHX_CUDA(cudaMemcpy(h.reward, d_rew, TE * 4, cudaMemcpyDeviceToHost));
-      PHX_CUDA(cudaMemcpy(h.all_done, d_all, TE * 2, cudaMemcpyDeviceToHost));
+    if (over && nw > 0) {  // a value did not fit the wire format: take the kernel's float planes
+      PHX_CUDA(planes_d2h(0, bound(nw), copy_out));
+      PHX_CUDA(cudaStreamSynchronize(copy_out));
+    }
+    if (!wire_fixed) {  // one chunk per call towards the balance point
+      if (dma_done_early && nw > 0) wire_chunks = nw - 1;
+      else if (cpu_done_early && nw < NCH) wire_chunks = nw + 1;
     }
     return PHX_OK;
   }
@@ -1153,14 +1209,23 @@ class SupplyChainFast final : public Family {
 
  private:
   ScPlan plan{};
-  uint32_t* h_wire = nullptr;  // pinned landing buffer of the compact wire plane (rollout_host)
+  uint32_t* h_wire = nullptr;  // pinned landing buffer of the compact wire words (rollout_host)
   size_t h_wire_bytes = 0;
+  int wire_chunks = -1;        // leading time chunks sent as wire words (rollout_host controller)
+  bool wire_fixed = false;     // PHX_WIRE_CHUNKS = k pins the split, "auto" lets the controller move it
+  const std::string wire_mode = std::getenv("PHX_WIRE_CHUNKS") ? std::getenv("PHX_WIRE_CHUNKS") : "";
   uint8_t* d_dsum = nullptr;  // digit-sum table of sc_fast2_kernel (nullptr: not applicable)
   uint32_t pow5 = 0;
-  // PHX_SC_KERNEL = 1 | 2 | 3 picks sc_fast_kernel / sc_fast2_kernel / sc_fast3_kernel (default 3)
+  // PHX_SC_KERNEL = 1 | 2 | 3 picks sc_fast_kernel / sc_fast2_kernel / sc_fast3_kernel (default 2:
+  // measured 30.7 us per 65 536 x 100 launch against 31.5 and 52.1, profiles/r02_ab_sc_kernels.txt)
   // where more than one is valid: A/B measurements and the cross-kernel parity tests
-  const int sc_variant = std::getenv("PHX_SC_KERNEL") ? std::atoi(std::getenv("PHX_SC_KERNEL")) : 3;
+  const int sc_variant = std::getenv("PHX_SC_KERNEL") ? std::atoi(std::getenv("PHX_SC_KERNEL")) : 2;
   const bool use_v1 = sc_variant == 1;
+  // PHX_PDL=1 launches sc_fast2_kernel with programmatic stream serialization (the next launch's
+  // blocks start while this grid runs and wait at griddepcontrol.wait).  Measured and rejected as
+  // a default: 55.9 us per launch against 30.3 -- the waiting blocks of the next launches take
+  // the schedulers' warp slots from the running one (profiles/r02_ab_sc_kernels.txt).
+  const bool use_pdl = std::getenv("PHX_PDL") != nullptr && std::getenv("PHX_PDL")[0] == '1';
   // PHX_NO_WIRE=1 (read when the handle is created) keeps phx_rollout_host on the float planes
   const bool no_wire = std::getenv("PHX_NO_WIRE") != nullptr && std::getenv("PHX_NO_WIRE")[0] == '1';
   const int sc_warps = std::getenv("PHX_SC_WARPS") ? std::atoi(std::getenv("PHX_SC_WARPS")) : 4;
@@ -1206,6 +1271,22 @@ struct ScProgram {
     PHX_REQUIRE(customers + 1 <= SEGCAP, PHX_ERR_UNSUPPORTED, "too many customers for this queue");
     return PHX_OK;
   }
+
+#ifndef PHX_JIT_TU
+  // Static send signature (phx_engine_host.cuh build_static_plan): what act() / handle() below
+  // may send, in emission order.
+  static void act_sends(const phx_spec& s, int slot, int, std::vector<SendSig>& out) {
+    if (s.agent_kind[slot] == SC_SHOP) out.push_back(SendSig{s.agent_iparam[slot][0], SC_STOCK_REQUEST});
+    if (s.agent_kind[slot] == SC_CUSTOMER) out.push_back(SendSig{s.agent_iparam[slot][0], SC_ORDER_REQUEST});
+  }
+  static void handle_sends(const phx_spec& s, int slot, int type, int sender,
+                           std::vector<SendSig>& out) {
+    if (s.agent_kind[slot] == SC_SHOP && type == SC_ORDER_REQUEST)
+      out.push_back(SendSig{sender, SC_ORDER_RESPONSE});
+    if (s.agent_kind[slot] == SC_FACTORY && type == SC_STOCK_REQUEST)
+      out.push_back(SendSig{sender, SC_STOCK_RESPONSE});
+  }
+#endif
 
   template <class E>
   __device__ static void act(const Ctx& c, int* st, bool has_action, const float* action, E& out) {

@@ -17,6 +17,7 @@ static thread_local std::string g_last_error;
 void set_error(const std::string& msg) { g_last_error = msg; }
 
 Family::~Family() {
+  if (device < 0) return;  // never initialised on a device (phx_selftest_jit_source)
   cudaSetDevice(device);
   cudaFree(d_hdr);
   cudaFree(d_term);
@@ -29,7 +30,7 @@ Family::~Family() {
   if (own_stream) cudaStreamDestroy(own_stream);
   if (copy_in) cudaStreamDestroy(copy_in);
   if (copy_out) cudaStreamDestroy(copy_out);
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < 16; ++i) {
     if (ev_in[i]) cudaEventDestroy(ev_in[i]);
     if (ev_k[i]) cudaEventDestroy(ev_k[i]);
     if (ev_out[i]) cudaEventDestroy(ev_out[i]);
@@ -66,7 +67,7 @@ int32_t Family::base_init(const phx_spec& s, int32_t num_envs, int32_t dev, uint
   PHX_CUDA(cudaStreamCreateWithFlags(&own_stream, cudaStreamNonBlocking));
   PHX_CUDA(cudaStreamCreateWithFlags(&copy_in, cudaStreamNonBlocking));
   PHX_CUDA(cudaStreamCreateWithFlags(&copy_out, cudaStreamNonBlocking));
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < 16; ++i) {
     PHX_CUDA(cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming));
     PHX_CUDA(cudaEventCreateWithFlags(&ev_k[i], cudaEventDisableTiming));
     PHX_CUDA(cudaEventCreateWithFlags(&ev_out[i], cudaEventDisableTiming));
@@ -294,6 +295,41 @@ int32_t phx_device_count(void) {
     return 0;
   }
   return n;
+}
+
+static Family* make_family(const phx_spec* spec) {
+  switch (spec->family) {
+    case PHX_FAMILY_SUPPLY_CHAIN: return phx::make_supply_chain_family(*spec);
+    case PHX_FAMILY_MOCK: return phx::make_mock_family(*spec);
+    case PHX_FAMILY_MARKET: return phx::make_market_family(*spec);
+    case PHX_FAMILY_STACKELBERG: return phx::make_stackelberg_family(*spec);
+    case PHX_FAMILY_DENSE: return phx::make_dense_family(*spec);
+    case PHX_FAMILY_SUPPLY_CHAIN2: return phx::make_supply_chain2_family(*spec);
+    case PHX_FAMILY_SIMPLE_MARKET: return phx::make_simple_market_family(*spec);
+    case PHX_FAMILY_DIGITAL_ADS: return phx::make_digital_ads_family(*spec);
+    default: return nullptr;
+  }
+}
+
+int32_t phx_selftest_jit_source(const phx_spec* spec, int32_t num_envs, uint64_t seed, char* buf,
+                                uint64_t buf_bytes, uint64_t* needed) {
+  int32_t rc = check_spec(spec);
+  if (rc != PHX_OK) return rc;
+  Family* fam = make_family(spec);
+  PHX_REQUIRE(fam != nullptr, PHX_ERR_UNSUPPORTED, "no device program for this family");
+  fam->spec = *spec;  // (no base_init / init: nothing here touches a device)
+  fam->E = num_envs;
+  fam->seed = seed;
+  std::string text;
+  rc = fam->jit_source_offline(text);
+  fam->device = -1;
+  delete fam;
+  if (rc != PHX_OK) return rc;
+  if (needed) *needed = (uint64_t)text.size() + 1;
+  if (buf == nullptr || buf_bytes == 0) return PHX_OK;
+  PHX_REQUIRE(buf_bytes >= text.size() + 1, PHX_ERR_INVALID, "buffer too small for the source text");
+  std::memcpy(buf, text.c_str(), text.size() + 1);
+  return PHX_OK;
 }
 
 int32_t phx_create(const phx_spec* spec, int32_t num_envs, int32_t device, uint64_t seed,

@@ -80,6 +80,21 @@ __device__ __forceinline__ int4 trace_row(int sender, int recv, int type, int p0
   return make_int4(sender | (recv << 8) | (type << 16), p0, p1, round);
 }
 
+// float32(num / den) as the reference computes it (Python float64 division, then a float32
+// cast): Markstein's FMA refinement with the correctly rounded reciprocal rcp = RN(1 / den)
+// yields the correctly rounded float32 quotient in four instructions (I2F, FMUL, 2 x FFMA) where
+// __fdiv_rn is a ~25-instruction subroutine -- a third of all instructions of the C4 step.
+// RN32(RN64(n / d)) == RN32(n / d) for the small integers of these env classes (the float64
+// rounding cannot land on a float32 tie).  Checked exhaustively on the device for |num| <= 2^21
+// and every denominator the shipped env classes use (tests/test_gpu_supply_chain.py
+// test_ratio_exhaustive).
+__device__ __forceinline__ float ratio_rn(int num, float den, float rcp) {
+  const float x = (float)num;
+  const float q = __fmul_rn(x, rcp);
+  const float r = __fmaf_rn(-den, q, x);
+  return __fmaf_rn(r, rcp, q);
+}
+
 // ------------------------------------------------------------------------ memory helpers
 __device__ __forceinline__ float ld_stream(const float* p) { return __ldcs(p); }
 __device__ __forceinline__ void st_stream(float* p, float v) { __stcs(p, v); }
@@ -123,6 +138,16 @@ __device__ __forceinline__ void bulk_wait_read() {  // smem source reusable
 template <int N>
 __device__ __forceinline__ void bulk_wait() {  // writes complete
   asm volatile("cp.async.bulk.wait_group %0;\n" ::"n"(N) : "memory");
+}
+// Programmatic dependent launch (griddepcontrol, sm_90+): launch_dependents lets the NEXT kernel
+// on the stream (if it was launched with cudaLaunchAttributeProgrammaticStreamSerialization)
+// start before this grid completes; wait blocks until every earlier grid has completed and its
+// memory operations are visible.  Both are no-ops for a normally launched kernel.
+__device__ __forceinline__ void griddep_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void griddep_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 __device__ __forceinline__ void fence_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");

@@ -115,6 +115,71 @@ struct Msg {
   int p[2];
 };
 
+// STATIC MESSAGE SCHEDULE of one env class (thread-per-env engine, specialised builds only).
+// On most env classes WHO may send WHAT to WHOM in which resolver round does not depend on the
+// data: it follows from the graph, the stage / turn and the device program.  A program that
+// declares its potential sends (act_sends / handle_sends, see fam_stackelberg.cu) lets the host
+// walk the reference's routing rules (SURVEY.md A.1 rules 2-7: acting order, Network.send checks,
+// first-arrival receiver order, delivery filter, responses into the next round) ONCE per phase
+// (PhantomEnv: one; FSM: per stage; Stackelberg: leaders' / followers' turn) into this table.
+// The specialised kernel then keeps every potential message in a FIXED slot -- registers after
+// unrolling -- with a valid bit, and calls the handlers in the planned order: no queue in shared
+// memory, no receiver scan, no send checks at run time (they were evaluated on the plan).  A send
+// the plan does not contain raises PHX_FAULT_PLAN_MISMATCH instead of being mis-routed.
+// Messages of a round are stored grouped by receiver, receivers in first-arrival order, a
+// receiver's batch in push order.  The plan is only built if no receiver of a response round
+// can hear from two different senders (then the order in which the responders of the previous
+// round are visited cannot be observed); every other env class keeps the dynamic queue.
+constexpr int SPL_PHASES = 8, SPL_ROUNDS = 4, SPL_MSGS = 16, SPL_AGENTS = 8, SPL_RESP = 4;
+struct StaticPlan {
+  int32_t n_phases;
+  int8_t n_rounds[SPL_PHASES];
+  int8_t n_msg[SPL_PHASES][SPL_ROUNDS];
+  int8_t sender[SPL_PHASES][SPL_ROUNDS][SPL_MSGS];
+  int8_t recv[SPL_PHASES][SPL_ROUNDS][SPL_MSGS];
+  int8_t type[SPL_PHASES][SPL_ROUNDS][SPL_MSGS];
+  // the slots of round r+1 that the handler of message i of round r may fill, in emission order
+  int8_t resp_n[SPL_PHASES][SPL_ROUNDS][SPL_MSGS];
+  int8_t resp_slot[SPL_PHASES][SPL_ROUNDS][SPL_MSGS][SPL_RESP];
+  // the slots of round 0 that agent s's acting-phase sends may fill, in emission order (one
+  // agent's sends are contiguous in push order but not in the receiver-grouped storage)
+  int8_t act_n[SPL_PHASES][SPL_AGENTS];
+  int8_t act_slot[SPL_PHASES][SPL_AGENTS][SPL_MSGS];
+};
+
+// Emission cursor of one callback under a static plan: the callback's potential sends are the
+// slots `slots[0..n)` of the target round, in emission order; an actual send takes the next
+// potential send with the same (receiver, type) -- actual sends are a subsequence of the
+// potential ones -- and anything else is a plan mismatch.  After inlining into an unrolled
+// specialised kernel every index here is a compile-time constant.
+struct PlanEmit {
+  const int8_t* slots;
+  int n;
+  const int8_t* recv;
+  const int8_t* type;
+  int* p0;
+  int* p1;
+  uint32_t* valid;
+  int k;
+  uint32_t fault;
+  __device__ __forceinline__ void send(int rcv, int typ, int a, int b = 0) {
+    if (fault) return;
+#pragma unroll
+    for (int j = 0; j < SPL_MSGS; ++j) {
+      if (j < k || j >= n) continue;
+      const int sl = slots[j];
+      if (recv[sl] == rcv && type[sl] == typ) {
+        p0[sl] = a;
+        p1[sl] = b;
+        *valid |= 1u << sl;
+        k = j + 1;
+        return;
+      }
+    }
+    fault = PHX_FAULT_PLAN_MISMATCH;
+  }
+};
+
 // What a device program sees of "its" agent and env: phantom.Context (context.py:11-40) with
 // the env view (views.py:27-34; fsm.py:66-73 adds the stage) and the neighbour views.
 struct Ctx {
@@ -260,6 +325,8 @@ struct EngineArgs {
   EngineSpec spec;
   int32_t T;
   int32_t qcap;         // thread-per-env engine: queue bound of this env class
+  int32_t stage_out;    // thread-per-env engine: every plane segment of a full block is 16-byte
+                        // aligned, so the output rows may go through shared memory + bulk stores
   int4* hdr;            // [E] step, episode, stage, -
   uint32_t* term;       // [E] PhantomEnv._terminations as a bitmask over agent slots
   uint32_t* trunc;      // [E]

@@ -36,11 +36,15 @@ constexpr int ENGINE1_SLOTS = 8;  // == the G of the HBM state layout [NWORDS][E
 struct Engine1Layout {
   int n, S, qcap;
   int off_state, off_views, off_rcache, off_act, off_qhead, off_qpay, off_tables, words;
+  // output staging (bytes from the start of the stage area, which begins at word `off_stage`):
+  // one step's rows of a full block of envs in the layout of the global planes
+  int off_stage, st_rew, st_om, st_rm, st_term, st_trunc, st_all, stage_bytes;
 };
 
 template <class P>
 __host__ __device__ inline Engine1Layout engine1_layout(int n_agents, int n_strategic, int qcap,
-                                                        bool cached_env) {
+                                                        bool cached_env, int obs_dim,
+                                                        bool with_stage) {
   Engine1Layout L;
   L.n = n_agents; L.S = n_strategic > 0 ? n_strategic : 1; L.qcap = qcap;
   int rows = 0;
@@ -51,7 +55,16 @@ __host__ __device__ inline Engine1Layout engine1_layout(int n_agents, int n_stra
   L.off_qhead = rows; rows += 2 * qcap;
   L.off_qpay = rows; rows += 2 * qcap * P::PW;
   L.off_tables = rows * ENGINE1_BLOCK;           // kind_tab / ip0_tab / in_tab, 32 words each
-  L.words = L.off_tables + 3 * ENGINE_MAX_AGENTS;
+  L.off_stage = (L.off_tables + 3 * ENGINE_MAX_AGENTS + 3) & ~3;  // 16-byte aligned
+  const int rowS = ENGINE1_BLOCK * L.S;          // strategic rows of a block
+  L.st_rew = rowS * obs_dim * 4;
+  L.st_om = L.st_rew + rowS * 4;
+  L.st_rm = L.st_om + rowS;
+  L.st_term = L.st_rm + rowS;
+  L.st_trunc = L.st_term + rowS;
+  L.st_all = L.st_trunc + rowS;
+  L.stage_bytes = L.st_all + ENGINE1_BLOCK * 2;
+  L.words = L.off_stage + (with_stage ? (L.stage_bytes + 3) / 4 : 0);
   return L;
 }
 
@@ -95,6 +108,12 @@ struct Emit1 {
   }
 };
 
+// Does the spec source of a specialised build carry a static message schedule?
+template <class SP, class = void>
+struct SpHasPlan : std::false_type {};
+template <class SP>
+struct SpHasPlan<SP, std::void_t<decltype(SP::plan())>> : std::true_type {};
+
 template <class P, bool TRACK, class SP>
 __device__ __forceinline__ void engine1_step_body(const EngineArgs<P>& a) {
   static_assert(P::VW <= 1, "thread-per-env engine: views of at most one word per agent");
@@ -103,7 +122,8 @@ __device__ __forceinline__ void engine1_step_body(const EngineArgs<P>& a) {
   const EngineSpec& sp = SP::get(a);
   const int tid = threadIdx.x;
   const Engine1Layout L = engine1_layout<P>(sp.n_agents, sp.n_strategic, a.qcap,
-                                            sp.env_kind != PHX_ENV_BASE);
+                                            sp.env_kind != PHX_ENV_BASE, sp.obs_dim,
+                                            a.stage_out != 0);
   int8_t* kind_tab = reinterpret_cast<int8_t*>(sm + L.off_tables);
   int32_t* ip0_tab = sm + L.off_tables + ENGINE_MAX_AGENTS;
   uint32_t* in_tab = reinterpret_cast<uint32_t*>(sm + L.off_tables + 2 * ENGINE_MAX_AGENTS);
@@ -169,6 +189,28 @@ __device__ __forceinline__ void engine1_step_body(const EngineArgs<P>& a) {
   prefetch_actions(0);
   __syncthreads();
   uint32_t fault = 0;  // first fault in event order: events ARE sequential here
+
+  // ---- OUTPUT STAGING.  With a thread per env a direct store of one float touches its own
+  // 32-byte sector (the rows of consecutive envs are S * O floats apart): C4 issued 29 sector
+  // writes per env-step, an order of magnitude more L1->L2 traffic than payload.  A block whose
+  // 128 envs are all live instead builds the step's rows in shared memory, in the layout of the
+  // global planes (the rows of consecutive envs are contiguous there), and thread 0 writes each
+  // plane segment with ONE TMA bulk store (cp.async.bulk, SASS UBLKCP).  Rows the reference
+  // would not return (mask 0) are written as zeros.
+  const bool staged = a.stage_out != 0 && (blockIdx.x + 1) * ENGINE1_BLOCK <= sp.E;  // block-uniform
+  unsigned char* const stage = reinterpret_cast<unsigned char*>(sm + L.off_stage);
+  auto put_obs = [&](size_t row, int sidx, int j, float v) {
+    if (staged) reinterpret_cast<float*>(stage)[(tid * S + sidx) * O + j] = v;
+    else if (env_live && a.io.obs) a.io.obs[(row * S + sidx) * O + j] = v;
+  };
+  auto put_rew = [&](size_t row, int sidx, float v) {
+    if (staged) reinterpret_cast<float*>(stage + L.st_rew)[tid * S + sidx] = v;
+    else if (env_live && a.io.reward) a.io.reward[row * S + sidx] = v;
+  };
+  auto put_u8 = [&](uint8_t* plane, int st_off, size_t row, int sidx, uint8_t v) {
+    if (staged) stage[st_off + tid * S + sidx] = v;
+    else if (env_live && plane) plane[row * S + sidx] = v;
+  };
 
   constexpr int EW = EnvWords<P>::value;
   int envw[EW > 0 ? EW : 1], envsnap[EW > 0 ? EW : 1];
@@ -260,6 +302,105 @@ __device__ __forceinline__ void engine1_step_body(const EngineArgs<P>& a) {
       observing = leaders_turn ? sp.followers : sp.leaders;
       rewarded = acting;
     }
+    if constexpr (SpHasPlan<SP>::value && !TRACK) {
+      // ---- STATIC SCHEDULE (see StaticPlan): acting phase, hooks and resolver rounds of this
+      // step's phase with every potential message in a fixed slot
+      const int phase = sp.env_kind == PHX_ENV_FSM ? h.z
+                        : sp.env_kind == PHX_ENV_STACKELBERG ? ((h.x & 1) == 1 ? 0 : 1) : 0;
+      auto route = [&](auto phc) {
+        constexpr int PH = decltype(phc)::value;
+        if constexpr (PH >= SP::N_PHASES) return;  // (keeps the unused phases out of the unit)
+        const StaticPlan& pl = SP::plan();
+        int p0[SPL_ROUNDS][SPL_MSGS], p1[SPL_ROUNDS][SPL_MSGS];
+        uint32_t valid[SPL_ROUNDS];
+#pragma unroll
+        for (int r = 0; r < SPL_ROUNDS; ++r) valid[r] = 0u;
+        // acting phase, agents in order (env.py:320-336)
+#pragma unroll
+        for (int s = 0; s < SPL_AGENTS; ++s) {
+          if (s >= n || !((acting >> s) & 1u) || ((done >> s) & 1u)) continue;
+          bind(s);
+          load_state(s, st);
+          const int sidx = sp.sidx[s];
+          bool has_action = false;
+          float act[P::ACT_DIM];
+#pragma unroll
+          for (int j = 0; j < P::ACT_DIM; ++j) act[j] = 0.f;
+          if (sidx >= 0) {
+            has_action = a.io.action_mask ? a.io.action_mask[row * S + sidx] != 0 : true;
+            cp_async_wait<1>();  // this step's actions (issued one step ago) have landed
+#pragma unroll
+            for (int j = 0; j < P::ACT_DIM; ++j) act[j] = ACT(t & 1, sidx, j);
+          }
+          PlanEmit em{pl.act_slot[PH][s], pl.act_n[PH][s], pl.recv[PH][0], pl.type[PH][0],
+                      p0[0], p1[0], &valid[0], 0, 0u};
+          P::act(ctx, st, has_action, act, em);
+          store_state(s, st);
+          if (em.fault && !fault) fault = em.fault;
+        }
+        if (!resolves) {  // the mail would wait for a later step's resolve
+          if (valid[0] && !fault) fault = PHX_FAULT_UNRESOLVED_MAIL;
+          return;
+        }
+        // pre_message_resolution (env.py:170-173)
+        if (P::HAS_PRE) {
+#pragma unroll
+          for (int s = 0; s < SPL_AGENTS; ++s) {
+            if (s >= n || ((done >> s) & 1u)) continue;
+            bind(s);
+            load_state(s, st);
+            P::pre(ctx, st);
+            store_state(s, st);
+          }
+        }
+        // BatchResolver.resolve (resolvers.py:128-163) along the plan
+#pragma unroll
+        for (int r = 0; r < SPL_ROUNDS; ++r) {
+          if (r >= pl.n_rounds[PH]) break;
+          if (valid[r] == 0u) break;  // queue empty: resolved
+          if (sp.round_limit >= 0 && r >= sp.round_limit) {
+            if (!fault) fault = PHX_FAULT_ROUND_LIMIT;
+            break;
+          }
+#pragma unroll
+          for (int i = 0; i < SPL_MSGS; ++i) {
+            if (i >= pl.n_msg[PH][r]) break;
+            const int rc = pl.recv[PH][r][i];
+            // (mail of done agents is dropped, resolvers.py:143-144; a message that was not
+            // sent leaves its handler's response slots invalid)
+            if (!((valid[r] >> i) & 1u) || ((done >> rc) & 1u)) continue;
+            // delivery-time edge filter (resolvers.py:146-148; matters with ignore_connection_errors)
+            if (!((in_mask_of(rc) >> pl.sender[PH][r][i]) & 1u)) continue;
+            bind(rc);
+            ctx.in_mask = in_mask_of(rc);
+            load_state(rc, st);
+            Msg m;
+            m.sender = pl.sender[PH][r][i];
+            m.type = pl.type[PH][r][i];
+            m.p[0] = p0[r][i];
+            m.p[1] = p1[r][i];
+            constexpr int RN = SPL_ROUNDS - 1;
+            const int rn = r + 1 < SPL_ROUNDS ? r + 1 : RN;
+            PlanEmit em{pl.resp_slot[PH][r][i], r + 1 < SPL_ROUNDS ? pl.resp_n[PH][r][i] : 0,
+                        pl.recv[PH][rn], pl.type[PH][rn], p0[rn], p1[rn], &valid[rn], 0, 0u};
+            if (!P::handle(ctx, st, m, em) && !fault && !em.fault) fault = PHX_FAULT_UNKNOWN_MSG_TYPE;
+            store_state(rc, st);
+            if (em.fault && !fault) fault = em.fault;
+          }
+        }
+        // (a plan never has more rounds than SPL_ROUNDS: the host refuses to build it otherwise)
+      };
+      switch (phase) {
+        case 0: route(std::integral_constant<int, 0>{}); break;
+        case 1: route(std::integral_constant<int, 1>{}); break;
+        case 2: route(std::integral_constant<int, 2>{}); break;
+        case 3: route(std::integral_constant<int, 3>{}); break;
+        case 4: route(std::integral_constant<int, 4>{}); break;
+        case 5: route(std::integral_constant<int, 5>{}); break;
+        case 6: route(std::integral_constant<int, 6>{}); break;
+        default: route(std::integral_constant<int, 7>{}); break;
+      }
+    } else {
     int cur = 0;
     Emit1<P> out{sm, &sp, L, cur, tid, 0, 0u, 0, 0u};
     PHX_AGENT_UNROLL
@@ -355,6 +496,7 @@ __device__ __forceinline__ void engine1_step_body(const EngineArgs<P>& a) {
       n_cur = resp.n;
     }
     if (TRACK && env_live) a.trace.cnt[e] = traced;
+    }
 
     // ---- post_message_resolution (env.py:175-178)
     if (P::HAS_POST && resolves)
@@ -399,6 +541,10 @@ __device__ __forceinline__ void engine1_step_body(const EngineArgs<P>& a) {
     // ---- outputs, strategic agents in order (env.py:273-303; fsm.py:322-378;
     // stackelberg.py:149-194).  Pass 1: callbacks + caches; pass 2 (needs the terminal flag): rows.
     uint32_t obs_slots = 0, rew_slots = 0, t_slots = 0, u_slots = 0;
+    if (staged) {  // the previous step's bulk stores have read the stage area
+      if (tid == 0) bulk_wait_read<0>();
+      __syncthreads();
+    }
     PHX_AGENT_UNROLL
     for (int s = 0; s < n; ++s) {
       const int sidx = sp.sidx[s];
@@ -421,22 +567,17 @@ __device__ __forceinline__ void engine1_step_body(const EngineArgs<P>& a) {
       store_state(s, st);
       obs_slots |= (uint32_t)obs_now << s;
       rew_slots |= (uint32_t)rew_now << s;
-      if (env_live) {
-        const size_t orow = row * S + sidx;
-        if (obs_now) {
-          if (a.io.obs) {
+      if (obs_now) {
 #pragma unroll
-            for (int j = 0; j < P::OBS_DIM; ++j)
-              if (j < O) a.io.obs[orow * O + j] = obs_val[j];
-          }
-          if (sp.env_kind == PHX_ENV_FSM) {
+        for (int j = 0; j < P::OBS_DIM; ++j)
+          if (j < O) put_obs(row, sidx, j, obs_val[j]);
+        if (env_live && sp.env_kind == PHX_ENV_FSM) {
 #pragma unroll
-            for (int j = 0; j < P::OBS_DIM; ++j)
-              if (j < O) a.obs_cache[((size_t)e * ENGINE1_SLOTS + s) * O + j] = obs_val[j];
-          }
+          for (int j = 0; j < P::OBS_DIM; ++j)
+            if (j < O) a.obs_cache[((size_t)e * ENGINE1_SLOTS + s) * O + j] = obs_val[j];
         }
-        if (sp.env_kind == PHX_ENV_BASE && a.io.reward) a.io.reward[orow] = rew_now ? rew_val : 0.f;
       }
+      if (sp.env_kind == PHX_ENV_BASE) put_rew(row, sidx, rew_now ? rew_val : 0.f);
     }
     term |= t_slots;
     trunc |= u_slots;
@@ -449,25 +590,28 @@ __device__ __forceinline__ void engine1_step_body(const EngineArgs<P>& a) {
     const bool terminal = all_term || all_trunc;
     if (sp.env_kind == PHX_ENV_FSM) h.z = next_stage;
 
-    if (env_live) {
+    if (env_live || staged) {
       PHX_AGENT_UNROLL
       for (int s = 0; s < n; ++s) {
         const int sidx = sp.sidx[s];
         if (sidx < 0) continue;
-        const size_t orow = row * S + sidx;
         const bool was_done = (done >> s) & 1u;
         const bool obs_now = (obs_slots >> s) & 1u;
+        bool obs_written = obs_now;
         uint8_t om = obs_now, rm = 0;
         if (sp.env_kind == PHX_ENV_BASE) {
           rm = (rew_slots >> s) & 1u;
+          if (was_done && staged) put_rew(row, sidx, 0.f);  // (pass 1 skips done agents)
         } else {
           const bool none = (rnone >> s) & 1u;
           if (sp.env_kind == PHX_ENV_FSM) {
             if (terminal) {  // fsm.py:360-375: flush the caches
               om = (ocached >> s) & 1u;
-              if (om && !obs_now && a.io.obs)
+              if (om && !obs_now) {
                 for (int j = 0; j < O; ++j)
-                  a.io.obs[orow * O + j] = a.obs_cache[((size_t)e * ENGINE1_SLOTS + s) * O + j];
+                  put_obs(row, sidx, j, a.obs_cache[((size_t)e * ENGINE1_SLOTS + s) * O + j]);
+                obs_written = true;
+              }
               rm = none ? 2 : 1;
             } else if (obs_now) {  // fsm.py:378
               rm = none ? 2 : 1;
@@ -477,15 +621,18 @@ __device__ __forceinline__ void engine1_step_body(const EngineArgs<P>& a) {
           } else if (obs_now && !none) {  // stackelberg.py:190-194
             rm = 1;
           }
-          if (a.io.reward)
-            a.io.reward[orow] = rm == 1 ? RC(s) : 0.f;
+          put_rew(row, sidx, rm == 1 ? RC(s) : 0.f);
         }
-        if (a.io.obs_mask) a.io.obs_mask[orow] = om;
-        if (a.io.reward_mask) a.io.reward_mask[orow] = rm;
-        if (a.io.term) a.io.term[orow] = was_done ? 255 : (uint8_t)((t_slots >> s) & 1u);
-        if (a.io.trunc) a.io.trunc[orow] = was_done ? 255 : (uint8_t)((u_slots >> s) & 1u);
+        if (staged && !obs_written)  // a staged row is always written: zeros where mask == 0
+          for (int j = 0; j < O; ++j) put_obs(row, sidx, j, 0.f);
+        put_u8(a.io.obs_mask, L.st_om, row, sidx, om);
+        put_u8(a.io.reward_mask, L.st_rm, row, sidx, rm);
+        put_u8(a.io.term, L.st_term, row, sidx, was_done ? 255 : (uint8_t)((t_slots >> s) & 1u));
+        put_u8(a.io.trunc, L.st_trunc, row, sidx, was_done ? 255 : (uint8_t)((u_slots >> s) & 1u));
       }
-      if (a.io.all_done)
+      if (staged)
+        reinterpret_cast<uchar2*>(stage + L.st_all)[tid] = make_uchar2(all_term, all_trunc);
+      else if (a.io.all_done)
         reinterpret_cast<uchar2*>(a.io.all_done)[row] = make_uchar2(all_term, all_trunc);
     }
 
@@ -543,18 +690,34 @@ __device__ __forceinline__ void engine1_step_body(const EngineArgs<P>& a) {
         bool got = false;
         if ((first_obs >> s) & 1u) got = P::encode(ctx, st, obs_val);
         store_state(s, st);
-        if (env_live) {
-          const size_t orow = row * S + sidx;
-          if (a.io.obs && got) {
+        if (got) {
 #pragma unroll
-            for (int j = 0; j < P::OBS_DIM; ++j)
-              if (j < O) a.io.obs[orow * O + j] = obs_val[j];
-          }
-          if (a.io.obs_mask) a.io.obs_mask[orow] = got;
+          for (int j = 0; j < P::OBS_DIM; ++j)
+            if (j < O) put_obs(row, sidx, j, obs_val[j]);
         }
+        put_u8(a.io.obs_mask, L.st_om, row, sidx, got);
+      }
+    }
+    if (staged) {  // this step's rows: one bulk store per plane segment of the block
+      fence_async_smem();
+      __syncthreads();
+      if (tid == 0) {
+        const size_t r0 = ((size_t)t * sp.E + (size_t)blockIdx.x * ENGINE1_BLOCK) * S;  // first row
+        const uint32_t rows = (uint32_t)(ENGINE1_BLOCK * S);
+        if (a.io.obs) bulk_store(a.io.obs + r0 * O, stage, rows * (uint32_t)O * 4u);
+        if (a.io.reward) bulk_store(a.io.reward + r0, stage + L.st_rew, rows * 4u);
+        if (a.io.obs_mask) bulk_store(a.io.obs_mask + r0, stage + L.st_om, rows);
+        if (a.io.reward_mask) bulk_store(a.io.reward_mask + r0, stage + L.st_rm, rows);
+        if (a.io.term) bulk_store(a.io.term + r0, stage + L.st_term, rows);
+        if (a.io.trunc) bulk_store(a.io.trunc + r0, stage + L.st_trunc, rows);
+        if (a.io.all_done)
+          bulk_store(a.io.all_done + ((size_t)t * sp.E + (size_t)blockIdx.x * ENGINE1_BLOCK) * 2,
+                     stage + L.st_all, (uint32_t)ENGINE1_BLOCK * 2u);
+        bulk_commit();
       }
     }
   }
+  if (staged && tid == 0) bulk_wait<0>();
 
   // ---- write back
   if (env_live) {

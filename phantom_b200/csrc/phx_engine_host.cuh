@@ -164,6 +164,143 @@ inline std::string jit_spec_literal(const EngineSpec& d) {
   return o;
 }
 
+// ------------------------------------------------------------------ static message schedule
+// A program opts in with two HOST functions that list its POTENTIAL sends, in emission order:
+//     static void act_sends(const phx_spec&, int slot, int phase, std::vector<SendSig>& out);
+//     static void handle_sends(const phx_spec&, int slot, int type, int sender,
+//                              std::vector<SendSig>& out);
+// `phase` = 0 under PhantomEnv, the stage index under the FSM env, 0 / 1 = leaders' / followers'
+// turn under the Stackelberg env.  An actual send must be one of the listed ones, in that order
+// (a subsequence); the specialised kernel checks it (PHX_FAULT_PLAN_MISMATCH).
+struct SendSig {
+  int recv, type;
+};
+template <class P, class = void>
+struct HasStaticSig : std::false_type {};
+template <class P>
+struct HasStaticSig<P, std::void_t<decltype(&P::act_sends), decltype(&P::handle_sends)>>
+    : std::true_type {};
+
+// Network.send's checks on the static graph (network.py:246-254): 0 = pushed.
+inline uint32_t plan_send_check(const phx_spec& s, int from, int to, int type) {
+  if (to < 0 || to >= s.n_agents || type < 0 || type >= s.n_payload_types) return PHX_FAULT_NO_EDGE;
+  if (!(s.flags & PHX_FLAG_IGNORE_CONNECTION_ERRORS) && !mask_bit(s.adjacency[from], to))
+    return PHX_FAULT_NO_EDGE;
+  if (!(s.flags & PHX_FLAG_NO_PAYLOAD_CHECKS) &&
+      (!mask_bit(s.type_sender_ok[type], from) || !mask_bit(s.type_receiver_ok[type], to)))
+    return PHX_FAULT_BAD_PAYLOAD_TYPE;
+  return 0;
+}
+
+// Walks SURVEY.md A.1 rules 2-7 over the potential sends of every phase.  Returns false (and
+// says why) if the env class has no static schedule under the rules stated at StaticPlan.
+template <class P>
+bool build_static_plan(const phx_spec& s, StaticPlan* out, std::string* why) {
+  auto fail = [&](const std::string& m) {
+    if (why) *why = m;
+    return false;
+  };
+  if (s.n_agents > SPL_AGENTS) return fail("more than 8 agents");
+  if (s.flags & (PHX_FLAG_STOCHASTIC_NETWORK | PHX_FLAG_SHUFFLE_BATCHES))
+    return fail("per-env graphs / shuffled batches are data dependent");
+  StaticPlan& pl = *out;
+  std::memset(&pl, 0, sizeof(pl));
+  pl.n_phases = s.env_kind == PHX_ENV_FSM ? s.n_stages : s.env_kind == PHX_ENV_STACKELBERG ? 2 : 1;
+  if (pl.n_phases > SPL_PHASES) return fail("too many phases");
+  struct M {
+    int sender, recv, type, src, k;  // src: message of the previous round (-1: acting), k-th send
+  };
+  for (int ph = 0; ph < pl.n_phases; ++ph) {
+    uint32_t acting = 0xFFFFFFFFu;
+    if (s.env_kind == PHX_ENV_FSM) acting = s.stages[ph].acting[0];
+    if (s.env_kind == PHX_ENV_STACKELBERG) acting = ph == 0 ? s.leaders[0] : s.followers[0];
+    // round 0 in push order: acting agents in slot order, their sends in emission order
+    std::vector<M> cur;
+    for (int a = 0; a < s.n_agents; ++a) {
+      if (!((acting >> a) & 1u)) continue;
+      std::vector<SendSig> sg;
+      P::act_sends(s, a, ph, sg);
+      if ((int)sg.size() > SPL_MSGS) return fail("an agent may send more than 16 messages");
+      for (int k = 0; k < (int)sg.size(); ++k) {
+        if (plan_send_check(s, a, sg[k].recv, sg[k].type)) return fail("a potential send faults");
+        cur.push_back(M{a, sg[k].recv, sg[k].type, a, k});
+      }
+    }
+    for (int r = 0; !cur.empty(); ++r) {
+      if (r >= SPL_ROUNDS) return fail("more than 4 resolver rounds");
+      if ((int)cur.size() > SPL_MSGS) return fail("more than 16 messages in a round");
+      // receivers in first-arrival order, batches in push order (resolvers.py:126,142)
+      std::vector<int> order;
+      for (const M& m : cur)
+        if (std::find(order.begin(), order.end(), m.recv) == order.end()) order.push_back(m.recv);
+      if (r > 0)
+        for (int rc : order) {
+          int snd = -1;
+          for (const M& m : cur)
+            if (m.recv == rc) {
+              if (snd >= 0 && snd != m.sender) return fail("a response batch has two senders");
+              snd = m.sender;
+            }
+        }
+      std::vector<M> stored;  // grouped by receiver
+      std::vector<int> slot_of(cur.size(), -1);
+      for (int rc : order)
+        for (size_t i = 0; i < cur.size(); ++i)
+          if (cur[i].recv == rc) {
+            slot_of[i] = (int)stored.size();
+            stored.push_back(cur[i]);
+          }
+      pl.n_rounds[ph] = (int8_t)(r + 1);
+      pl.n_msg[ph][r] = (int8_t)stored.size();
+      for (size_t i = 0; i < stored.size(); ++i) {
+        pl.sender[ph][r][i] = (int8_t)stored[i].sender;
+        pl.recv[ph][r][i] = (int8_t)stored[i].recv;
+        pl.type[ph][r][i] = (int8_t)stored[i].type;
+      }
+      // where each producer's sends landed
+      for (size_t i = 0; i < cur.size(); ++i) {
+        const M& m = cur[i];
+        if (r == 0) {
+          pl.act_slot[ph][m.src][m.k] = (int8_t)slot_of[i];
+          pl.act_n[ph][m.src] = (int8_t)std::max<int>(pl.act_n[ph][m.src], m.k + 1);
+        } else {
+          if (m.k >= SPL_RESP) return fail("a handler may answer with more than 4 messages");
+          pl.resp_slot[ph][r - 1][m.src][m.k] = (int8_t)slot_of[i];
+          pl.resp_n[ph][r - 1][m.src] = (int8_t)std::max<int>(pl.resp_n[ph][r - 1][m.src], m.k + 1);
+        }
+      }
+      // responses: receivers in order, each handling its batch in push order (agents.py:110-120)
+      std::vector<M> next;
+      for (size_t i = 0; i < stored.size(); ++i) {
+        const M& m = stored[i];
+        // delivery-time edge filter (resolvers.py:146-148): only with ignore_connection_errors
+        if (!mask_bit(s.adjacency[m.sender], m.recv)) continue;
+        std::vector<SendSig> sg;
+        P::handle_sends(s, m.recv, m.type, m.sender, sg);
+        for (int k = 0; k < (int)sg.size(); ++k) {
+          if (plan_send_check(s, m.recv, sg[k].recv, sg[k].type))
+            return fail("a potential response faults");
+          next.push_back(M{m.recv, sg[k].recv, sg[k].type, (int)i, k});
+        }
+      }
+      cur.swap(next);
+    }
+  }
+  return true;
+}
+
+inline std::string jit_plan_literal(const StaticPlan& p) {
+  std::string o = "{\n  ";
+  auto f = [&](const auto& v) {
+    jit_emit(o, v);
+    o += ",\n  ";
+  };
+  f(p.n_phases); f(p.n_rounds); f(p.n_msg); f(p.sender); f(p.recv); f(p.type); f(p.resp_n);
+  f(p.resp_slot); f(p.act_n); f(p.act_slot);
+  o += "}";
+  return o;
+}
+
 template <class P>
 __global__ void engine_init_kernel(int E, int G, int4* hdr, int32_t* state, int nwords) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -188,7 +325,9 @@ class EngineFamily : public Family {
     if (jit_lib) cudaLibraryUnload(jit_lib);
   }
 
-  int32_t init(const phx_spec& s) override {
+  // Host-only part of init(): lowers the spec and picks the tiling (no CUDA call), so that the
+  // specialised source of an env class can also be produced without a device (self-test hook).
+  int32_t layout(const phx_spec& s) {
     int32_t rc = make_engine_spec(s, E, seed, env_offset, &espec, P::NWORDS, EnvWords<P>::value);
     if (rc != PHX_OK) return rc;
     rc = P::validate(s);
@@ -226,6 +365,17 @@ class EngineFamily : public Family {
                 "supports the thread-per-env engine");
     thread_per_env = s.exec_mode == PHX_EXEC_THREAD || (s.exec_mode == PHX_EXEC_AUTO && eligible);
     PHX_REQUIRE(s.obs_dim <= P::OBS_DIM, PHX_ERR_INVALID, "obs_dim exceeds the family's OBS_DIM");
+    return PHX_OK;
+  }
+
+  int32_t jit_source_offline(std::string& out) override {
+    const int32_t rc = layout(spec);
+    return rc != PHX_OK ? rc : jit_source(out);
+  }
+
+  int32_t init(const phx_spec& s) override {
+    int32_t rc = layout(s);
+    if (rc != PHX_OK) return rc;
     const size_t n = (size_t)E * G;
     PHX_CUDA(cudaMalloc(&d_state, sizeof(int32_t) * n * (P::NWORDS > 0 ? P::NWORDS : 1)));
     PHX_CUDA(cudaMemset(d_state, 0, sizeof(int32_t) * n * (P::NWORDS > 0 ? P::NWORDS : 1)));
@@ -281,6 +431,18 @@ class EngineFamily : public Family {
     a.spec = espec;
     a.T = T;
     a.qcap = qcap1;
+    {  // output staging of the thread-per-env engine: see engine1_step_body
+      const size_t S = spec.n_strategic > 0 ? spec.n_strategic : 1;
+      auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+      // Default: specialised builds only.  Measured (C4, 131 072 envs x 100 steps): specialised
+      // 0.594 -> 0.424 ms; the generic build is instruction bound and loses to the two block
+      // barriers a step (0.878 -> 0.990 ms).  PHX_ENGINE1_STAGE = 0 | 1 forces it off / on.
+      const char* ov = std::getenv("PHX_ENGINE1_STAGE");
+      const bool want = ov ? ov[0] == '1' : (jit_kernel != nullptr && !tracking());
+      a.stage_out = want && ((size_t)E * S) % 16 == 0 && E % 8 == 0 &&
+                    al(io.obs) && al(io.obs_mask) && al(io.reward) && al(io.reward_mask) &&
+                    al(io.term) && al(io.trunc) && al(io.all_done);
+    }
     a.hdr = d_hdr;
     a.term = d_term;
     a.trunc = d_trunc;
@@ -358,7 +520,8 @@ class EngineFamily : public Family {
     if constexpr (P::Q1CAP > 0 && P::VW <= 1) {
       if (thread_per_env) {
         const Engine1Layout lay = engine1_layout<P>(spec.n_agents, spec.n_strategic, qcap1,
-                                                    spec.env_kind != PHX_ENV_BASE);
+                                                    spec.env_kind != PHX_ENV_BASE, spec.obs_dim,
+                                                    a.stage_out != 0);
         const size_t smem = sizeof(int32_t) * (size_t)lay.words;
         const int grid = (E + ENGINE1_BLOCK - 1) / ENGINE1_BLOCK;
         if (jit_kernel && !tracking()) {  // the build specialised for this handle's env class
@@ -425,14 +588,33 @@ class EngineFamily : public Family {
         }
         if (nb > 0) bound += ", " + std::to_string(nb);
       }
+      // static message schedule (thread-per-env engine, programs that declare their sends)
+      std::string plan_text, plan_members;
+      static_plan = false;
+      if constexpr (HasStaticSig<P>::value) {
+        StaticPlan pl;
+        std::string why;
+        const char* off = std::getenv("PHX_JIT_STATIC_PLAN");
+        if (thread_per_env && !P::BATCHED && !(off && off[0] == '0') &&
+            build_static_plan<P>(spec, &pl, &why)) {
+          static_plan = true;
+          plan_text = "__device__ constexpr StaticPlan kPlan = " + jit_plan_literal(pl) + ";\n";
+          plan_members =
+              "  static constexpr int N_PHASES = " + std::to_string(pl.n_phases) + ";\n"
+              "  __device__ __forceinline__ static const StaticPlan& plan() { return kPlan; }\n";
+        } else {
+          plan_text = "// no static message schedule: " + why + "\n";
+        }
+      }
       out = std::string("// generated by libphx (phx_jit_source): the ") +
             (thread_per_env ? "thread-per-env" : "tile") + " step kernel of\n// " + prog +
             " with this handle's lowered env class as a compile-time constant\n"
             "#define PHX_JIT_TU 1\n#include \"" + P::JIT_SOURCE + "\"\n"
             "namespace phx {\nnamespace {\n__device__ constexpr EngineSpec kSpec = " +
-            jit_spec_literal(espec) + ";\n"
+            jit_spec_literal(espec) + ";\n" + plan_text +
             "struct ConstSpec {\n  template <class A>\n"
-            "  __device__ __forceinline__ static const EngineSpec& get(const A&) { return kSpec; }\n};\n"
+            "  __device__ __forceinline__ static const EngineSpec& get(const A&) { return kSpec; }\n" +
+            plan_members + "};\n"
             "}  // namespace\n"
             "extern \"C\" __global__ void __launch_bounds__(" + bound + ")\n"
             "phx_jit_step(const EngineArgs<" + prog + "> a) {\n  " + body + "\n}\n}  // namespace phx\n";
@@ -446,7 +628,8 @@ class EngineFamily : public Family {
     if constexpr (P::Q1CAP > 0 && P::VW <= 1) {
       if (thread_per_env) {
         const Engine1Layout lay = engine1_layout<P>(spec.n_agents, spec.n_strategic, qcap1,
-                                                    spec.env_kind != PHX_ENV_BASE);
+                                                    spec.env_kind != PHX_ENV_BASE, spec.obs_dim,
+                                                    /*with_stage=*/true);
         return sizeof(int32_t) * (size_t)lay.words;
       }
     }
@@ -470,7 +653,8 @@ class EngineFamily : public Family {
       if (jit_lib) cudaLibraryUnload(jit_lib);
       jit_lib = lib;
       jit_kernel = k;
-      name = thread_per_env ? std::string("thread-per-env(G=8, specialised)")
+      name = thread_per_env ? std::string(static_plan ? "thread-per-env(G=8, specialised, static schedule)"
+                                                      : "thread-per-env(G=8, specialised)")
                             : std::string("queue(G=") + std::to_string(G) + ", specialised)";
       return PHX_OK;
     } else {
@@ -508,6 +692,7 @@ class EngineFamily : public Family {
   EngineSpec espec{};
   int G = 8;
   bool thread_per_env = false;
+  bool static_plan = false;  // the last jit_source() carried a StaticPlan
   int qcap1 = 0;
   int32_t* d_state = nullptr;
   float* d_rcache = nullptr;

@@ -31,6 +31,9 @@ class Family {
     set_error("this env class / kernel variant has no run-time specialisation");
     return PHX_ERR_UNSUPPORTED;
   }
+  // jit_source for a family object that was never initialised on a device (spec / E / seed /
+  // env_offset set by hand): the self-test hook phx_selftest_jit_source.
+  virtual int32_t jit_source_offline(std::string& out) { return jit_source(out); }
   virtual int32_t load_specialised(const char* cubin_path) {
     (void)cubin_path;
     set_error("this env class / kernel variant has no run-time specialisation");
@@ -68,7 +71,7 @@ class Family {
   size_t stage_bytes = 0;
   cudaStream_t own_stream = nullptr;
   cudaStream_t copy_in = nullptr, copy_out = nullptr;  // phx_rollout_host pipeline
-  cudaEvent_t ev_in[8] = {}, ev_k[8] = {}, ev_out[8] = {};
+  cudaEvent_t ev_in[16] = {}, ev_k[16] = {}, ev_out[16] = {};
   int32_t ensure_stage(size_t bytes);  // (re)allocates d_stage to at least `bytes`
   HostPool& host_pool() {              // host threads of the *_host entry points, built on demand
     if (!pool_) pool_.reset(new HostPool(HostPool::default_threads()));

@@ -60,6 +60,9 @@ def _fault_exception(code: int, env_index: int) -> Exception:
         L.FAULT_UNRESOLVED_MAIL: RuntimeError(
             "an FSM stage handler left messages unresolved; the device does not carry mail "
             "into a later step." + where),
+        L.FAULT_PLAN_MISMATCH: RuntimeError(
+            "a statically scheduled step kernel saw a send its device program did not declare "
+            "(act_sends / handle_sends); re-create the env without specialise()." + where),
     }.get(code, RuntimeError(f"device fault {code}{where}"))
 
 

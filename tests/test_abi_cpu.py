@@ -258,3 +258,34 @@ def test_wire_expansion_equals_the_reference_formulas(threads, skew):
     assert np.array_equal(obs, want)
     assert np.array_equal(rew, (sales - 0.1 * stock).astype(np.float32))
     assert np.array_equal(ad[:, 1], trunc) and not ad[:, 0].any()
+
+
+def test_static_schedule_unit_is_generated_and_compiles(tmp_path):
+    """phx_selftest_jit_source (no GPU): the specialised unit of the Stackelberg game carries the
+    static message schedule -- leaders' turn: one round of 3 Prices; followers' turn: 3 Demands,
+    then 3 Acks -- and compiles for sm_100a."""
+    import shutil
+    import subprocess
+
+    from phantom_b200 import jit
+    from phantom_b200.envs.stackelberg_game import StackelbergGameEnv
+
+    env = StackelbergGameEnv(num_envs=256, exec_mode="thread", auto_reset=True)
+    spec = env.spec
+    need = C.c_uint64(0)
+    L.check(L.lib.phx_selftest_jit_source(C.byref(spec), 256, 7, None, 0, C.byref(need)))
+    buf = C.create_string_buffer(need.value)
+    L.check(L.lib.phx_selftest_jit_source(C.byref(spec), 256, 7, buf, need.value, None))
+    text = buf.value.decode()
+    assert "constexpr StaticPlan kPlan" in text and "N_PHASES = 2" in text
+    plan = text[text.index("kPlan = {"):]
+    rows = [ln.strip() for ln in plan.splitlines()[1:4]]
+    assert rows[0] == "2," and rows[1].startswith("{1, 2, 0") and rows[2].startswith("{{3, 0, 0, 0}, {3, 3, 0, 0}")
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    unit = tmp_path / "unit.cu"
+    unit.write_text(text)
+    proc = subprocess.run([nvcc, *jit.ARCH, "-O3", "-std=c++17", "-cubin", "-I", jit.CSRC, "-o",
+                           str(tmp_path / "unit.cubin"), str(unit)], capture_output=True, text=True)
+    assert proc.returncode == 0, proc.stderr[-2000:]

@@ -87,3 +87,52 @@ def test_specialised_equals_generic_at_scale_and_caches():
     with pytest.raises(RuntimeError, match="no run-time specialisation"):
         fast.specialise()  # the schedule-specialised fast kernel has nothing left to fold
     fast.close()
+
+
+def test_static_schedule_supply_chain_and_stackelberg(monkeypatch):
+    """Specialised units of the thread-per-env engine carry a STATIC message schedule when the
+    device program declares its sends (csrc/phx_engine.cuh StaticPlan): every potential message
+    has a fixed slot and the handlers run in the planned order.  Must equal the dynamic queue --
+    with actions missing (conditional sends -> invalid slots), auto-reset wraps, and on a
+    supply chain whose agent order differs from the example's."""
+    import phantom_b200 as ph
+    from phantom_b200.envs import supply_chain as sc
+    from phantom_b200.envs.stackelberg_game import StackelbergGameEnv
+
+    def shuffled_chain(**kw):  # customers first, then the shop, the factory last
+        ids = [f"CUST{i + 1}" for i in range(3)]
+        agents = [sc.CustomerAgent(c, "SHOP") for c in ids] + [sc.ShopAgent("SHOP", "WAREHOUSE"),
+                                                               sc.FactoryAgent("WAREHOUSE")]
+        net = ph.Network(agents)
+        net.add_connection("SHOP", "WAREHOUSE")
+        net.add_connections_between(["SHOP"], ids)
+        return ph.PhantomEnv(num_steps=9, network=net, exec_mode="thread", **kw)
+
+    cases = ((lambda **kw: StackelbergGameEnv(exec_mode="thread", num_steps=10, **kw), 4, 1.0),
+             (lambda **kw: sc.SupplyChainEnv(exec_mode="thread", num_steps=9, **kw), 1, 100.0),
+             (shuffled_chain, 1, 100.0))
+    for make, S, scale in cases:
+        E, T = 4096, 47
+        r = np.random.RandomState(S)
+        A = (r.uniform(0, 1, size=(T, E, S, 1)) * scale).astype(np.float32)
+        M = (r.uniform(size=(T, E, S)) > 0.15).astype(np.uint8)
+        envs = []
+        for static in ("1", "0", None):
+            env = make(num_envs=E, seed=5, auto_reset=True)
+            env.reset_batch()
+            if static is not None:
+                monkeypatch.setenv("PHX_JIT_STATIC_PLAN", static)
+                env.specialise()
+                assert ("static schedule" in env.exec_name) == (static == "1"), env.exec_name
+            envs.append(env)
+        outs = [[x.clone() for x in env.rollout_batch(A, M)] for env in envs]
+        from phantom_b200 import BatchStep
+
+        for o in outs[:2]:
+            assert_batchsteps_equal(BatchStep(*o), BatchStep(*outs[2]))
+        outs = [[x.clone() for x in env.rollout_batch(A)] for env in envs]  # every action present
+        for o in outs[:2]:
+            assert_batchsteps_equal(BatchStep(*o), BatchStep(*outs[2]))
+        for env in envs:
+            env.check_errors()
+            env.close()

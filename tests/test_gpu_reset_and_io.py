@@ -143,46 +143,51 @@ def _host_planes(T, E):
     return pin((T, E, 1, 3), torch.float32), pin((T, E, 1), torch.float32), pin((T, E, 2), torch.uint8)
 
 
-@pytest.mark.parametrize("lo,hi,expect_wire", [(0.0, 100.0, True), (-40.0, 140.0, True),
-                                               (-60000.0, 100.0, False)])
-def test_rollout_host_compact_wire_equals_device_planes(lo, hi, expect_wire, monkeypatch):
-    """The lean host-buffer call of the supply chain moves ONE 32-bit word per env-step across
-    PCIe and expands it on host threads (csrc/phx_sc_wire.*): the float32 planes must equal the
-    device path's bit for bit -- in distribution, with negative stock / sales (values outside the
-    wire fields: the call falls back to the float planes the kernel also wrote), across
-    auto-reset wraps and over two consecutive calls."""
+@pytest.mark.parametrize("lo,hi,in_range", [(0.0, 100.0, True), (-40.0, 140.0, False),
+                                            (-60000.0, 100.0, False)])
+def test_rollout_host_wire_chunks_equal_device_planes(lo, hi, in_range, monkeypatch):
+    """The lean host-buffer call of the supply chain sends its first time chunks across PCIe as
+    ONE 32-bit word per env-step and expands them on host threads (csrc/phx_sc_wire.*) while the
+    DMA engine copies the float planes of the other chunks (opt-in: PHX_WIRE_CHUNKS).  Whatever the
+    split (some / all chunks as wire words, the adaptive controller, or none), the planes must equal the device
+    path's bit for bit -- in distribution, with negative stock / sales (outside the wire fields:
+    the wire rows are re-copied from the float planes the kernel also wrote), across auto-reset
+    wraps and over three consecutive calls."""
     import torch
 
     from phantom_b200 import _lib as L
     from phantom_b200.envs.supply_chain import SupplyChainEnv
 
-    E, T, seed = 8192, 29, 14
+    E, T, seed = 8192, 37, 14
     r = np.random.RandomState(7)
-    tapes = [r.uniform(lo, hi, size=(T, E, 1, 1)).astype(np.float32) for _ in range(2)]
+    tapes = [r.uniform(lo, hi, size=(T, E, 1, 1)).astype(np.float32) for _ in range(3)]
     dev = SupplyChainEnv(num_envs=E, seed=seed, num_steps=13, auto_reset=True)
-    host = SupplyChainEnv(num_envs=E, seed=seed, num_steps=13, auto_reset=True)
-    monkeypatch.setenv("PHX_NO_WIRE", "1")
-    plain = SupplyChainEnv(num_envs=E, seed=seed, num_steps=13, auto_reset=True)
-    for env in (dev, host, plain):
-        env.reset_batch()
+    dev.reset_batch()
+    want = [[x.cpu() for x in dev.rollout_batch(A)] for A in tapes]
+    want = [(w[0], w[2], w[6]) for w in want]
     h_obs, h_rew, h_all = _host_planes(T, E)
-    p_obs, p_rew, p_all = _host_planes(T, E)
-    for A in tapes:
-        want = dev.rollout_batch(A)
-        a = torch.as_tensor(A).pin_memory()
-        for env, (o, rw, ad) in ((host, (h_obs, h_rew, h_all)), (plain, (p_obs, p_rew, p_all))):
-            o.fill_(-1.0); rw.fill_(-1.0); ad.fill_(7)
-            L.check(L.lib.phx_rollout_host(env._handle, T, a.data_ptr(), None, o.data_ptr(), None,
-                                           rw.data_ptr(), None, None, None, ad.data_ptr()))
-            assert torch.equal(o, want.observations.cpu())
-            assert torch.equal(rw, want.rewards.cpu())
-            assert torch.equal(ad, want.all_done.cpu())
-    if not expect_wire:  # the out-of-range tape really left the wire fields
-        stock = np.asarray(dev.agents["SHOP"].stock)
-        assert stock.min() < -32768 or np.asarray(dev.agents["SHOP"].sales).min() < 0
     shop = lambda env: np.stack([np.asarray(getattr(env.agents["SHOP"], c))
                                  for c in ("stock", "sales", "missed_sales")], 1)
-    assert np.array_equal(shop(dev), shop(host)) and np.array_equal(shop(dev), shop(plain))
-    for env in (dev, host, plain):
+    if not in_range:  # the tape really leaves the wire fields
+        assert shop(dev)[:, 0].min() < -32768 or shop(dev)[:, 1].min() < 0
+    for chunks in ("5", "14", "auto", None):
+        if chunks is None:  # the default: plain staged copies of the float planes
+            monkeypatch.delenv("PHX_WIRE_CHUNKS", raising=False)
+        else:
+            monkeypatch.setenv("PHX_WIRE_CHUNKS", chunks)
+        env = SupplyChainEnv(num_envs=E, seed=seed, num_steps=13, auto_reset=True)
+        env.reset_batch()
+        for A, (o, rw, ad) in zip(tapes, want):
+            a = torch.as_tensor(A).pin_memory()
+            h_obs.fill_(-1.0); h_rew.fill_(-1.0); h_all.fill_(7)
+            L.check(L.lib.phx_rollout_host(env._handle, T, a.data_ptr(), None, h_obs.data_ptr(),
+                                           None, h_rew.data_ptr(), None, None, None,
+                                           h_all.data_ptr()))
+            assert torch.equal(h_obs, o), chunks
+            assert torch.equal(h_rew, rw), chunks
+            assert torch.equal(h_all, ad), chunks
+        assert np.array_equal(shop(dev), shop(env)), chunks
         env.check_errors()
         env.close()
+    dev.check_errors()
+    dev.close()

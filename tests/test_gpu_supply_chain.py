@@ -405,7 +405,8 @@ def test_ratio_exhaustive():
     (|n| <= 2^21) and the denominators of the shipped configs."""
     from phantom_b200 import _lib as L
 
-    for den in (100, 25, 5, 40, 65):
+    # (100, 25: supply chain; 10, 15, 30: Stackelberg game C4; 12, 33: FSM market C3)
+    for den in (100, 25, 5, 40, 65, 10, 15, 30, 12, 33):
         lo, count = -(1 << 21), (1 << 22) + 1
         out = np.empty(count, np.float32)
         L.check(L.lib.phx_selftest_ratio(0, den, lo, count, out.ctypes.data))
