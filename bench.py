@@ -54,7 +54,8 @@ CONFIGS = {
                   "clearing), 3 stages, 99-step episodes; one bench step = one phx_rollout launch "
                   "= 99 transitions per env, auto-reset"),
         E=32768, scaling="weak", T=99, S=31, O=3, lean=False, act_scale=1.0, binary_from=7,
-        b_io=31 * (4 + 12 + 4 + 4) + 2, b_state=2 * (16 + 8 + 32 * (8 * 4 + 4 + 12) + 8), nbuf=2),
+        b_io=31 * (4 + 12 + 4 + 4) + 2, b_state=2 * (16 + 8 + 32 * (8 * 4 + 4 + 12) + 8), nbuf=2,
+        specialise=True),
     "C4": dict(
         workload=("Stackelberg C4: 131072 envs in total (sharded over the GPUs) x 4 agents, "
                   "100-step episodes; one bench step = one phx_rollout launch = 100 transitions "

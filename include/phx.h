@@ -298,9 +298,19 @@ int32_t phx_reduce_field(phx_env* env, int32_t field, int32_t index, int32_t wid
 /* Resolver.tracked_messages (phantom/resolvers.py:41-60) of the LAST phx_step, for envs
  * [env_begin, env_end): host_counts int32 [n] messages recorded per env, host_msgs
  * int32 [n, trace_capacity, PHX_TRACE_WORDS] rows (sender_slot | recv_slot << 8 |
- * type << 16, payload0, payload1, round).  Needs PHX_FLAG_TRACK_MESSAGES.  Synchronises. */
+ * type << 16, payload0, payload1, round).  Needs PHX_FLAG_TRACK_MESSAGES.  Synchronises.
+ * (After a T-step rollout this is the trace of its LAST step; see phx_get_trace_step.) */
 int32_t phx_get_trace(phx_env* env, int32_t env_begin, int32_t env_end, int32_t* host_counts,
                       int32_t* host_msgs);
+
+/* The same for step `step` (0-based) of the LAST tracked launch: a T-step phx_rollout of a handle
+ * with PHX_FLAG_TRACK_MESSAGES records every step's messages (one slab of trace_capacity rows
+ * per (step, env) on the device), which is what the reference's rollout utility collects into
+ * Step.messages (phantom/utils/rollout.py:35-47, phantom/utils/rllib/rollout.py record_messages).
+ * phx_trace_steps = T of that launch; phx_get_trace = its last step. */
+int32_t phx_get_trace_step(phx_env* env, int32_t step, int32_t env_begin, int32_t env_end,
+                           int32_t* host_counts, int32_t* host_msgs);
+int32_t phx_trace_steps(const phx_env* env);
 
 /* Run-time specialisation of the step kernel to ONE handle's env class.  The generic engines
  * interpret the lowered env class (agent counts, kinds, adjacency, stage tables) at run time;

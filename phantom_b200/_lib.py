@@ -132,6 +132,8 @@ SYMBOLS = {
     "phx_get_field": (C.c_int32, [_P, C.c_int32, C.c_int32, _P, C.c_uint64]),
     "phx_set_field": (C.c_int32, [_P, C.c_int32, C.c_int32, _P, C.c_uint64]),
     "phx_get_trace": (C.c_int32, [_P, C.c_int32, C.c_int32, _P, _P]),
+    "phx_get_trace_step": (C.c_int32, [_P, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
+    "phx_trace_steps": (C.c_int32, [_P]),
     "phx_jit_source": (C.c_int32, [_P, _P, C.c_uint64, _P]),
     "phx_load_specialised": (C.c_int32, [_P, C.c_char_p]),
     "phx_reduce_field": (C.c_int32, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32,

@@ -331,7 +331,7 @@ __global__ void __launch_bounds__(DN_MAX) dense_step_kernel(const DenseArgs a) {
 
     if (TRACK && slot == 0) {  // Resolver.tracked_messages of this step, global push order
       int cnt = 0;
-      int4* rows = a.trace.rows + (size_t)e * a.trace.cap;
+      int4* rows = a.trace.rows + row * a.trace.cap;  // one slab of `cap` rows per (step, env)
       for (int s = 0; s < n; ++s) {
         if (!((sm.sent[s >> 5] >> (s & 31)) & 1u)) continue;
         for (int r = 0; r < n; ++r)
@@ -357,7 +357,7 @@ __global__ void __launch_bounds__(DN_MAX) dense_step_kernel(const DenseArgs a) {
           ++cnt;
         }
       }
-      a.trace.cnt[e] = cnt;
+      a.trace.cnt[row] = cnt;
     }
 
     // ---- outputs (env.py:273-303): every agent observes and is rewarded; nobody terminates
@@ -508,8 +508,10 @@ class DenseFamily final : public Family {
   }
 
   int32_t rollout(int32_t T, const StepIO& io, cudaStream_t stream) override {
-    PHX_REQUIRE(!tracking() || T == 1, PHX_ERR_INVALID,
-                "message tracking records one step: use phx_step (T == 1)");
+    if (tracking()) {
+      const int32_t rc = ensure_trace(T);
+      if (rc != PHX_OK) return rc;
+    }
     DenseArgs a;
     a.sp = dsp;
     a.T = T;

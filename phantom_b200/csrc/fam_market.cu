@@ -99,6 +99,133 @@ struct MarketProgram {
     }
   }
 
+#ifndef PHX_JIT_TU
+  // Host: is this env class one the collective resolve below was written for?  Every potential
+  // send must pass Network.send's checks on the static graph (so that no NO_EDGE /
+  // BAD_PAYLOAD_TYPE fault can occur at run time), the stages must be handler-less, and no
+  // data-dependent routing option may be on.
+  static bool collective_ok(const phx_spec& s) {
+    if (s.env_kind != PHX_ENV_FSM || s.n_agents > 32 || s.round_limit == 0) return false;
+    if (s.flags & (PHX_FLAG_STOCHASTIC_NETWORK | PHX_FLAG_SHUFFLE_BATCHES)) return false;
+    for (int k = 0; k < s.n_stages; ++k)
+      if (s.stages[k].handler != 0) return false;
+    const int cl = s.iparams[6];
+    for (int a = 0; a < s.n_agents; ++a) {
+      for (int r = 0; r < s.n_agents; ++r) {
+        if (!mask_bit(s.adjacency[a], r)) continue;
+        if (mask_bit(s.adjacency[a], r) != mask_bit(s.adjacency[r], a)) return false;
+        if (s.agent_kind[a] == MKT_MAKER && s.agent_kind[r] == MKT_TAKER &&
+            plan_send_check(s, a, r, MKT_QUOTE))
+          return false;
+        if (s.agent_kind[a] == MKT_CLEARING && s.agent_kind[r] != MKT_CLEARING &&
+            plan_send_check(s, a, r, MKT_FILL))
+          return false;
+      }
+      if (s.agent_kind[a] == MKT_TAKER && plan_send_check(s, a, cl, MKT_ORDER)) return false;
+    }
+    return true;
+  }
+#endif
+
+  // COLLECTIVE RESOLVE of one step (see phx_engine.cuh HasCollective): acting phase, pre hook and
+  // the (single) resolver round of the stage, for the whole tile, with the receivers pulling.
+  //   Quotes   a taker walks the quoting makers in slot order (= push order of its batch) and
+  //            reads each price with a shuffle: 7 shuffles instead of 7 x 24 queue entries.
+  //   Orders   the clearing agent admits orders first come first served per maker, up to
+  //            MAKER_CAPACITY (market.py: order dependent): the takers ordering maker k are a
+  //            ballot, a taker's place in that queue is a popcount of the lower lanes, and the
+  //            clearing agent's totals are a popcount and a REDUX.ADD of the admitted prices.
+  //   Fills    every maker / taker pulls its Fill from the clearing agent's registers.
+  // Handlers of different receivers only touch their own agent, and nobody answers a message in
+  // this market, so the order of the three groups is free -- except that a Fill's payload is
+  // what the clearing agent held in the acting phase, hence fills first.
+  static constexpr bool HAS_COLLECTIVE = true;
+  template <int G>
+  __device__ static void step_collective(const Ctx& c, int* st, bool has_ctx, bool acts,
+                                         bool has_action, const float* action, uint32_t tmask,
+                                         uint32_t& fault) {
+    const EngineSpec& sp = *c.spec;
+    const int shift = G >= 32 ? 0 : ((threadIdx.x & 31) / G * G);  // the tile's first lane
+    const uint32_t gmask = G >= 32 ? 0xFFFFFFFFu : ((1u << G) - 1u);
+    const int cl = sp.iparams[6];
+    const int ord = c.slot < sp.n_agents ? c.iparam0_of(c.slot) : 0;  // maker / taker ordinal
+    // ---- acting phase (env.py:320-336): who sends, with the payloads as of now
+    bool quote = false, order = false, fills = false;
+    if (acts) {
+      if (c.kind == MKT_MAKER) {
+        if (has_action) {
+          const float a0 = action[0];
+          if (!(fabsf(a0) <= 1048576.0f)) {
+            fault = PHX_FAULT_INVALID_ACTION;
+          } else {
+            st[2] = max(0, min(100, __float2int_rn(__fmul_rn(a0, 100.0f))));
+            quote = true;
+          }
+        }
+      } else if (c.kind == MKT_TAKER) {
+        order = has_action && __float2int_rn(action[0]) == 1 && st[2] >= 0 &&
+                ((c.out_mask >> cl) & 1u);  // (no edge: only reachable with ignore_connection_errors)
+      } else if (c.stage == sp.iparams[5]) {
+        fills = true;
+      }
+    }
+    const int q_price = st[2];
+    const int o_maker = st[2], o_price = st[1];
+    // ---- pre_message_resolution (env.py:170-173)
+    if (has_ctx) pre(c, st);
+    // ---- Fills: pulled from the clearing agent's registers
+    if (__shfl_sync(tmask, (int)fills, cl + shift)) {  // tile-uniform
+      int w_mine = 0;
+#pragma unroll
+      for (int j = 0; j < 7; ++j) {
+        const int wj = __shfl_sync(tmask, st[j], cl + shift);
+        if (j == ord) w_mine = wj;
+      }
+      const int accepted = __shfl_sync(tmask, st[7], cl + shift);
+      if (has_ctx && ((c.in_mask >> cl) & 1u)) {
+        if (c.kind == MKT_MAKER) {
+          st[0] -= w_mine & 0xFF;
+          st[1] += w_mine >> 8;
+          st[3] = w_mine >> 8;
+        } else if (c.kind == MKT_TAKER && ((accepted >> ord) & 1)) {
+          st[3] += 1;
+          st[4] = st[0] - st[1];
+        }
+      }
+    }
+    // ---- Quotes: the quoting makers in slot order
+    for (uint32_t qm = (__ballot_sync(tmask, quote) >> shift) & gmask; qm; qm &= qm - 1) {
+      const int m = __ffs(qm) - 1;
+      const int pm = __shfl_sync(tmask, q_price, m + shift);
+      if (has_ctx && c.kind == MKT_TAKER && ((c.in_mask >> m) & 1u) && c.view_of(m)[0] > 0 &&
+          pm < st[1]) {
+        st[1] = pm;
+        st[2] = c.iparam0_of(m);
+      }
+    }
+    // ---- Orders: first come (lowest taker slot), first served, per maker
+    if (__ballot_sync(tmask, order) != 0u) {  // tile-uniform
+      const uint32_t below = (1u << c.slot) - 1u;
+      const bool cl_live = __shfl_sync(tmask, (int)has_ctx, cl + shift) != 0;
+#pragma unroll
+      for (int mk = 0; mk < 7; ++mk) {
+        const bool mine = order && o_maker == mk;
+        const uint32_t queue = (__ballot_sync(tmask, mine) >> shift) & gmask;
+        if (queue == 0u) continue;  // tile-uniform
+        const int cur = __shfl_sync(tmask, st[mk], cl + shift);
+        const int room = sp.iparams[3] - (cur & 0xFF);
+        const bool admitted = mine && cl_live && __popc(queue & below) < room;
+        const int n_adm = __popc((__ballot_sync(tmask, admitted) >> shift) & gmask);
+        const int sum_p = __reduce_add_sync(tmask, admitted ? o_price : 0);
+        const uint32_t bits = __reduce_or_sync(tmask, admitted ? (1u << ord) : 0u);
+        if (c.slot == cl && n_adm > 0) {
+          st[mk] += n_adm + (sum_p << 8);
+          st[7] |= (int)bits;
+        }
+      }
+    }
+  }
+
   __device__ static void pre(const Ctx& c, int* st) {
     if (c.kind == MKT_TAKER && c.stage == c.spec->iparams[4]) {  // a new cycle
       st[1] = MKT_NO_QUOTE;

@@ -116,7 +116,7 @@ __device__ __forceinline__ void sc_draw_orders(const ScPlan& p, uint32_t env_id,
 
 // One thread per env; T steps per launch with the env state in registers.
 //   NC        number of customers if known at compile time (0 = runtime, up to 30)
-//   TRACK     record Resolver.tracked_messages rows (T == 1)
+//   TRACK     record Resolver.tracked_messages rows, one slab of `cap` rows per (step, env)
 //   HAS_MASK  an action_mask plane is supplied
 //   FULL_IO   all seven output planes are written; otherwise only obs, reward and all_done
 //             (the four per-agent mask planes are constant for this env class)
@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(SC_BLOCK) sc_fast_kernel(const ScArgs a) {
     int cnt = 0;
     int4* trow = nullptr;
     if (TRACK && real) {
-      trow = a.trace.rows + (size_t)e * a.trace.cap;
+      trow = a.trace.rows + (size_t)row * a.trace.cap;  // one slab per (step, env)
       if (has && p.push_req) trow[cnt++] = trace_row(0, 1, SC_STOCK_REQUEST, ask, 0, 0);
     }
 
@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(SC_BLOCK) sc_fast_kernel(const ScArgs a) {
       for (int i = 0; i < (NC > 0 ? NC : 1); ++i)
         if ((p.push_ordresp >> i) & 1u)
           trow[cnt++] = trace_row(0, 2 + i, SC_ORDER_RESPONSE, sold_each[i], 0, 1);
-      a.trace.cnt[e] = cnt;
+      a.trace.cnt[row] = cnt;
     }
 
     // ---- round 1, receiver SHOP: handle_stock_response (supply_chain.py:98-102)
@@ -973,8 +973,13 @@ class SupplyChainFast final : public Family {
     a.trace = trace_sink();
     const int grid = (env_count + SC_BLOCK - 1) / SC_BLOCK;
     const bool track = tracking();
-    PHX_REQUIRE(!track || T == 1, PHX_ERR_INVALID,
-                "message tracking records one step: use phx_step (T == 1)");
+    if (track) {
+      PHX_REQUIRE(env_begin == 0 && env_count == E, PHX_ERR_INVALID,
+                  "message tracking steps the whole handle");
+      const int32_t rc = ensure_trace(T);
+      if (rc != PHX_OK) return rc;
+      a.trace = trace_sink();
+    }
     PHX_REQUIRE((uint64_t)T * (uint64_t)E * 3ull < (1ull << 32), PHX_ERR_INVALID,
                 "T * num_envs too large for one launch (row index is 32-bit): split the rollout");
     // Two output layouts are compiled: "lean" = obs + reward + all_done, "full" = all seven

@@ -92,6 +92,27 @@ int32_t Family::field_ptr(int32_t field, int32_t index, void** p, size_t* bytes)
   return PHX_ERR_INVALID;
 }
 
+// Message tracing inside a T-step launch: one slab of `trace_capacity` rows per (step, env).
+int32_t Family::ensure_trace(int32_t T) {
+  PHX_REQUIRE(tracking() && T >= 1, PHX_ERR_INVALID, "handle was created without tracking");
+  const size_t rows = (size_t)T * E * spec.trace_capacity;
+  PHX_REQUIRE(rows * sizeof(int4) <= ((size_t)8 << 30), PHX_ERR_INVALID,
+              "message trace of this launch exceeds 8 GiB: track fewer envs or steps");
+  if (T > trace_T_cap) {
+    PHX_CUDA(cudaDeviceSynchronize());
+    cudaFree(d_trace);
+    cudaFree(d_trace_cnt);
+    d_trace = nullptr;
+    d_trace_cnt = nullptr;
+    PHX_CUDA(cudaMalloc(&d_trace, sizeof(int4) * rows));
+    PHX_CUDA(cudaMalloc(&d_trace_cnt, sizeof(int32_t) * (size_t)T * E));
+    PHX_CUDA(cudaMemset(d_trace_cnt, 0, sizeof(int32_t) * (size_t)T * E));
+    trace_T_cap = T;
+  }
+  trace_T = T;
+  return PHX_OK;
+}
+
 int32_t Family::ensure_stage(size_t total) {
   if (total > stage_bytes) {
     PHX_CUDA(cudaStreamSynchronize(own_stream));
@@ -528,23 +549,35 @@ int32_t phx_reduce_field(phx_env* env, int32_t field, int32_t index, int32_t wid
   return PHX_OK;
 }
 
-int32_t phx_get_trace(phx_env* env, int32_t env_begin, int32_t env_end, int32_t* host_counts,
-                      int32_t* host_msgs) {
+int32_t phx_get_trace_step(phx_env* env, int32_t step, int32_t env_begin, int32_t env_end,
+                           int32_t* host_counts, int32_t* host_msgs) {
   PHX_REQUIRE(env != nullptr && host_counts != nullptr && host_msgs != nullptr, PHX_ERR_INVALID,
               "NULL argument");
   Family* f = env->fam;
   PHX_REQUIRE(f->tracking(), PHX_ERR_INVALID, "handle was created without PHX_FLAG_TRACK_MESSAGES");
   PHX_REQUIRE(0 <= env_begin && env_begin <= env_end && env_end <= f->E, PHX_ERR_INVALID,
               "env range out of bounds");
+  PHX_REQUIRE(step >= 0 && step < f->trace_T, PHX_ERR_INVALID,
+              "step outside the last tracked launch (it recorded " + std::to_string(f->trace_T) +
+                  " step(s))");
   PHX_CUDA(cudaSetDevice(f->device));
   PHX_CUDA(cudaDeviceSynchronize());
   const size_t n = (size_t)(env_end - env_begin);
-  PHX_CUDA(cudaMemcpy(host_counts, f->d_trace_cnt + env_begin, sizeof(int32_t) * n,
+  const size_t first = (size_t)step * f->E + env_begin;
+  PHX_CUDA(cudaMemcpy(host_counts, f->d_trace_cnt + first, sizeof(int32_t) * n,
                       cudaMemcpyDeviceToHost));
-  PHX_CUDA(cudaMemcpy(host_msgs, f->d_trace + (size_t)env_begin * f->spec.trace_capacity,
+  PHX_CUDA(cudaMemcpy(host_msgs, f->d_trace + first * f->spec.trace_capacity,
                       sizeof(int4) * n * f->spec.trace_capacity, cudaMemcpyDeviceToHost));
   return PHX_OK;
 }
+
+int32_t phx_get_trace(phx_env* env, int32_t env_begin, int32_t env_end, int32_t* host_counts,
+                      int32_t* host_msgs) {
+  PHX_REQUIRE(env != nullptr, PHX_ERR_INVALID, "env is NULL");
+  return phx_get_trace_step(env, env->fam->trace_T - 1, env_begin, env_end, host_counts, host_msgs);
+}
+
+int32_t phx_trace_steps(const phx_env* env) { return env ? env->fam->trace_T : 0; }
 
 int32_t phx_jit_source(phx_env* env, char* buf, uint64_t buf_bytes, uint64_t* needed) {
   PHX_REQUIRE(env != nullptr, PHX_ERR_INVALID, "env is NULL");

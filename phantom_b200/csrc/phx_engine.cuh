@@ -320,6 +320,29 @@ struct Emit {
   }
 };
 
+// COLLECTIVE RESOLVE (optional part of the device-program interface, tile engine).  The queue
+// restates the reference literally: every message is an entry one lane writes and another lane
+// finds.  When an agent talks to MANY peers that is the wrong shape for a warp -- the sender
+// lane serialises its sends (C3: a maker writes 24 Quotes, the clearing agent 31 Fills, with
+// 1-7 of 32 lanes active), then every receiver searches the queue.  A program may therefore
+// resolve a step's mail itself with tile collectives -- the receivers PULL the sender's payload
+// with shuffles, first-come-first-served admission is a ballot + popcount rank, a batch
+// aggregation is a REDUX -- when the lowered env class has the shape it was written for:
+//     static constexpr bool HAS_COLLECTIVE = true;
+//     static bool collective_ok(const phx_spec&);            // host: canonical env class?
+//     template <int G> __device__ static void step_collective(const Ctx&, int* st, bool has_ctx,
+//                     bool acts, bool has_action, const float* action, uint32_t tmask,
+//                     uint32_t& fault);
+// step_collective replaces [act -> Network.send -> pre_message_resolution -> resolver rounds] of
+// one step for the whole tile (all lanes call it) and must leave every agent's state exactly
+// as the reference's order of events would (tests: goldens of the unmodified reference, the
+// sampled full-size oracle comparison, collective == queue on random tapes).  The queue path
+// stays the fallback for every other topology and for message tracking.
+template <class P, class = void>
+struct HasCollective : std::false_type {};
+template <class P>
+struct HasCollective<P, std::void_t<decltype(P::HAS_COLLECTIVE)>> : std::true_type {};
+
 template <class P>
 struct EngineArgs {
   EngineSpec spec;
@@ -327,6 +350,7 @@ struct EngineArgs {
   int32_t qcap;         // thread-per-env engine: queue bound of this env class
   int32_t stage_out;    // thread-per-env engine: every plane segment of a full block is 16-byte
                         // aligned, so the output rows may go through shared memory + bulk stores
+  int32_t collective;   // tile engine: the program resolves the mail itself (step_collective)
   int4* hdr;            // [E] step, episode, stage, -
   uint32_t* term;       // [E] PhantomEnv._terminations as a bitmask over agent slots
   uint32_t* trunc;      // [E]
@@ -447,7 +471,7 @@ template <class P, int G, bool TRACK, class QC, class QN>
 __device__ __forceinline__ int engine_round(const EngineArgs<P>& a, const Ctx& ctx, int* st,
                                             bool has_ctx, QC& qc, QN& qn, TileSmem<P, G>& ts,
                                             int round, uint32_t tmask, uint32_t& fault_key,
-                                            int& traced, int e, bool trace_lane, int& k_batch) {
+                                            int& traced, size_t row, bool trace_lane, int& k_batch) {
   constexpr int INF = 0x7FFFFFFF;
   const bool shuffle = (ctx.spec->flags & PHX_FLAG_SHUFFLE_BATCHES) != 0;
   const int slot = ctx.slot;
@@ -612,7 +636,7 @@ __device__ __forceinline__ int engine_round(const EngineArgs<P>& a, const Ctx& c
       const int seg = qn.order[si];
       for (int k = 0; k < qn.cnt[seg]; ++k) {
         if (traced < a.trace.cap)
-          a.trace.rows[(size_t)e * a.trace.cap + traced] =
+          a.trace.rows[row * a.trace.cap + traced] =
               make_int4((int)(((uint32_t)qn.hd(k, seg) << 8) | (uint32_t)seg), qn.py(0, k, seg),
                         P::PW > 1 ? qn.py(P::PW > 1 ? 1 : 0, k, seg) : 0, round + 1);
         ++traced;
@@ -794,6 +818,23 @@ __device__ __forceinline__ void engine_step_body(const EngineArgs<P>& a) {
       observing = leaders_turn ? sp.followers : sp.leaders;
       rewarded = acting;
     }
+    bool routed = false;
+    if constexpr (HasCollective<P>::value) {
+      if (a.collective && !TRACK) {  // tile-uniform: the program resolves this step's mail itself
+        uint32_t cf = 0;
+        P::template step_collective<G>(ctx, st, has_ctx, has_ctx && (acting & slot_bit) != 0,
+                                       strategic && has_action_now, act, tmask, cf);
+        if (cf) fault_key = min(fault_key, (0u << 16) | ((uint32_t)slot << 8) | cf);
+        if (G >= 32 && strategic && env_live && t + 1 < a.T) {  // next step's action (see below)
+          const size_t arow = (row + sp.E) * S + sidx;
+#pragma unroll
+          for (int j = 0; j < P::ACT_DIM; ++j) act_next[j] = a.io.actions[arow * P::ACT_DIM + j];
+          if (a.io.action_mask) has_next = a.io.action_mask[arow];
+        }
+        routed = true;
+      }
+    }
+    if (!routed) {
     Emit<decltype(ts.qa)> out{&ts.qa, &sp, slot, ctx.out_mask, 0, 0u};
     if (has_ctx && (acting & slot_bit)) P::act(ctx, st, strategic && has_action_now, act, out);
     // 32-lane tiles: issued after the acting phase, so that the loaded value is not live across
@@ -819,7 +860,7 @@ __device__ __forceinline__ void engine_step_body(const EngineArgs<P>& a) {
       for (int si = 0; si < sp.n_agents; ++si)
         for (int k = 0; k < ts.qa.cnt[si]; ++k) {
           if (traced < a.trace.cap)
-            a.trace.rows[(size_t)e * a.trace.cap + traced] =
+            a.trace.rows[row * a.trace.cap + traced] =
                 make_int4((int)(((uint32_t)ts.qa.hd(k, si) << 8) | (uint32_t)si), ts.qa.py(0, k, si),
                           P::PW > 1 ? ts.qa.py(P::PW > 1 ? 1 : 0, k, si) : 0, 0);
           ++traced;
@@ -843,13 +884,15 @@ __device__ __forceinline__ void engine_step_body(const EngineArgs<P>& a) {
       }
       if (round == 0)
         pending = engine_round<P, G, TRACK>(a, ctx, st, has_ctx, ts.qa, ts.qr[0], ts, round, tmask,
-                                            fault_key, traced, e, trace_lane, k_batch);
+                                            fault_key, traced, row, trace_lane, k_batch);
       else
         pending = engine_round<P, G, TRACK>(a, ctx, st, has_ctx, ts.qr[(round - 1) & 1],
                                             ts.qr[round & 1], ts, round, tmask, fault_key, traced,
-                                            e, trace_lane, k_batch);
+                                            row, trace_lane, k_batch);
     }
-    if (trace_lane) a.trace.cnt[e] = traced;
+    if (trace_lane) a.trace.cnt[row] = traced;
+
+    }
 
     // ---- post_message_resolution (env.py:175-178), then the env class's own override
     if (has_ctx && resolves) P::post(ctx, st);

@@ -430,7 +430,7 @@ __device__ __forceinline__ void engine1_step_body(const EngineArgs<P>& a) {
     if (TRACK && env_live) {
       for (int i = 0; i < n_cur; ++i, ++traced)
         if (traced < a.trace.cap)
-          a.trace.rows[(size_t)e * a.trace.cap + traced] =
+          a.trace.rows[row * a.trace.cap + traced] =
               make_int4(QH(cur, i), QP(cur, i, 0), P::PW > 1 ? QP(cur, i, P::PW > 1 ? 1 : 0) : 0, 0);
     }
 
@@ -488,14 +488,14 @@ __device__ __forceinline__ void engine1_step_body(const EngineArgs<P>& a) {
       if (TRACK && env_live) {
         for (int i = 0; i < resp.n; ++i, ++traced)
           if (traced < a.trace.cap)
-            a.trace.rows[(size_t)e * a.trace.cap + traced] =
+            a.trace.rows[row * a.trace.cap + traced] =
                 make_int4(QH(cur ^ 1, i), QP(cur ^ 1, i, 0),
                           P::PW > 1 ? QP(cur ^ 1, i, P::PW > 1 ? 1 : 0) : 0, round + 1);
       }
       cur ^= 1;
       n_cur = resp.n;
     }
-    if (TRACK && env_live) a.trace.cnt[e] = traced;
+    if (TRACK && env_live) a.trace.cnt[row] = traced;
     }
 
     // ---- post_message_resolution (env.py:175-178)

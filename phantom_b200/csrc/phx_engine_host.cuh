@@ -364,6 +364,10 @@ class EngineFamily : public Family {
                 "PHX_EXEC_THREAD needs an env class with at most 8 agents whose device program "
                 "supports the thread-per-env engine");
     thread_per_env = s.exec_mode == PHX_EXEC_THREAD || (s.exec_mode == PHX_EXEC_AUTO && eligible);
+    if constexpr (HasCollective<P>::value) {  // the program's collective resolve (tile engine)
+      const char* off = std::getenv("PHX_COLLECTIVE");
+      collective_ok_ = !(off && off[0] == '0') && P::collective_ok(s);
+    }
     PHX_REQUIRE(s.obs_dim <= P::OBS_DIM, PHX_ERR_INVALID, "obs_dim exceeds the family's OBS_DIM");
     return PHX_OK;
   }
@@ -422,7 +426,8 @@ class EngineFamily : public Family {
     if (rc != PHX_OK) return rc;
     PHX_CUDA(cudaDeviceSynchronize());
     name = thread_per_env ? std::string("thread-per-env(G=8)")
-                          : std::string("queue(G=") + std::to_string(G) + ")";
+                          : std::string("queue(G=") + std::to_string(G) +
+                                (collective_ok_ && !tracking() ? ", collective)" : ")");
     return PHX_OK;
   }
 
@@ -431,6 +436,7 @@ class EngineFamily : public Family {
     a.spec = espec;
     a.T = T;
     a.qcap = qcap1;
+    a.collective = collective_ok_ && !tracking() && !thread_per_env;
     {  // output staging of the thread-per-env engine: see engine1_step_body
       const size_t S = spec.n_strategic > 0 ? spec.n_strategic : 1;
       auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
@@ -438,7 +444,8 @@ class EngineFamily : public Family {
       // 0.594 -> 0.424 ms; the generic build is instruction bound and loses to the two block
       // barriers a step (0.878 -> 0.990 ms).  PHX_ENGINE1_STAGE = 0 | 1 forces it off / on.
       const char* ov = std::getenv("PHX_ENGINE1_STAGE");
-      const bool want = ov ? ov[0] == '1' : (jit_kernel != nullptr && !tracking());
+      // (one strategic agent: the rows of consecutive envs are already close together)
+      const bool want = ov ? ov[0] == '1' : (jit_kernel != nullptr && !tracking() && S >= 2);
       a.stage_out = want && ((size_t)E * S) % 16 == 0 && E % 8 == 0 &&
                     al(io.obs) && al(io.obs_mask) && al(io.reward) && al(io.reward_mask) &&
                     al(io.term) && al(io.trunc) && al(io.all_done);
@@ -514,8 +521,10 @@ class EngineFamily : public Family {
   }
 
   int32_t rollout(int32_t T, const StepIO& io, cudaStream_t stream) override {
-    PHX_REQUIRE(!tracking() || T == 1, PHX_ERR_INVALID,
-                "message tracking records one step: use phx_step (T == 1)");
+    if (tracking()) {
+      const int32_t rc = ensure_trace(T);
+      if (rc != PHX_OK) return rc;
+    }
     EngineArgs<P> a = make_args(T, io);
     if constexpr (P::Q1CAP > 0 && P::VW <= 1) {
       if (thread_per_env) {
@@ -655,7 +664,9 @@ class EngineFamily : public Family {
       jit_kernel = k;
       name = thread_per_env ? std::string(static_plan ? "thread-per-env(G=8, specialised, static schedule)"
                                                       : "thread-per-env(G=8, specialised)")
-                            : std::string("queue(G=") + std::to_string(G) + ", specialised)";
+                            : std::string("queue(G=") + std::to_string(G) +
+                                  (collective_ok_ && !tracking() ? ", collective, specialised)"
+                                                                 : ", specialised)");
       return PHX_OK;
     } else {
       return Family::load_specialised(cubin_path);
@@ -693,6 +704,7 @@ class EngineFamily : public Family {
   int G = 8;
   bool thread_per_env = false;
   bool static_plan = false;  // the last jit_source() carried a StaticPlan
+  bool collective_ok_ = false;  // the program resolves this env class's mail with tile collectives
   int qcap1 = 0;
   int32_t* d_state = nullptr;
   float* d_rcache = nullptr;

@@ -63,8 +63,11 @@ class Family {
   uint32_t* d_trunc = nullptr; // [W][E]
   uint32_t* d_err = nullptr;   // [E]
   uint32_t* d_nfaults = nullptr;  // [1]
-  int4* d_trace = nullptr;     // [E, cap]
-  int32_t* d_trace_cnt = nullptr;  // [E]
+  int4* d_trace = nullptr;     // [trace_T, E, cap]  the message trace of the last launch
+  int32_t* d_trace_cnt = nullptr;  // [trace_T, E]
+  int32_t trace_T = 1;         // steps of the last tracked launch
+  int32_t trace_T_cap = 1;     // steps the trace buffers can hold
+  int32_t ensure_trace(int32_t T);  // grows the trace buffers to T steps; records trace_T
 
   // staging for the *_host entry points
   void* d_stage = nullptr;

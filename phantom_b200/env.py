@@ -406,16 +406,26 @@ class PhantomEnv:
         col[:, agent._phx_slot] = np.asarray(value).astype(col.dtype)
         self.set_field(L.FIELD_FAMILY + word, col)
 
-    def tracked_messages_batch(self, env_begin: int = 0, env_end: Optional[int] = None):
-        """phx_get_trace: (counts [n], rows [n, cap, 4]) of the last step."""
+    def tracked_messages_batch(self, env_begin: int = 0, env_end: Optional[int] = None,
+                               step: Optional[int] = None):
+        """phx_get_trace / phx_get_trace_step: (counts [n], rows [n, cap, 4]) of step `step` of
+        the last tracked launch (default: its last step)."""
         self._ensure_handle()
         env_end = self.num_envs if env_end is None else env_end
         n, cap = env_end - env_begin, self.spec.trace_capacity
         counts = np.zeros(n, np.int32)
         rows = np.zeros((n, cap, L.PHX_TRACE_WORDS), np.int32)
-        L.check(L.lib.phx_get_trace(self._handle, env_begin, env_end, counts.ctypes.data,
-                                    rows.ctypes.data))
+        if step is None:
+            step = L.lib.phx_trace_steps(self._handle) - 1
+        L.check(L.lib.phx_get_trace_step(self._handle, int(step), env_begin, env_end,
+                                         counts.ctypes.data, rows.ctypes.data))
         return counts, rows
+
+    def rollout_messages(self, env_index: int = 0) -> List[List[Message]]:
+        """Resolver.tracked_messages of every step of the last tracked rollout, for one env:
+        [step][message] in the reference's push order (phantom/resolvers.py:41-60)."""
+        self._ensure_handle()
+        return [self._decode_trace(t, env_index) for t in range(L.lib.phx_trace_steps(self._handle))]
 
     # --------------------------------------------------- reference API (num_envs == 1)
     def _require_single(self, what: str) -> None:
@@ -487,9 +497,9 @@ class PhantomEnv:
         truncations["__all__"] = bool(all_done[1])
         return self.Step(observations, rewards, terminations, truncations, infos)
 
-    def _decode_trace(self) -> List[Message]:
+    def _decode_trace(self, step: Optional[int] = None, env_index: int = 0) -> List[Message]:
         info = self.family
-        counts, rows = self.tracked_messages_batch(0, 1)
+        counts, rows = self.tracked_messages_batch(env_index, env_index + 1, step)
         ids = self.agent_ids
         msgs = []
         for r in rows[0, : counts[0]]:

@@ -83,3 +83,30 @@ def run_device_trace_vs_golden(make_env, g, n_env):
                 want = gm[(gm[:, 0] == e) & (gm[:, 1] == ep) & (gm[:, 2] == t)][:, 3:8]
                 assert np.array_equal(device_trace_rows(env, e), want), (e, ep, t)
     env.close()
+
+
+def run_device_rollout_trace_vs_golden(make_env, g, n_env):
+    """The message trace recorded INSIDE one T-step rollout launch (one slab per (step, env),
+    phx_get_trace_step) == the reference's Resolver.tracked_messages of every step of a whole
+    episode, env by env; the output planes of the tracked launch equal the golden too."""
+    seed, A, M = int(g["seed"]), g["actions"], g["action_mask"]
+    gm = g["messages"]  # (env, ep, t, sender, recv, type, v0, v1)
+    env = make_env(num_envs=n_env, seed=seed, enable_tracking=True)
+    T = A.shape[2]
+    for ep in range(A.shape[1]):
+        env.reset_batch()
+        acts = np.ascontiguousarray(np.swapaxes(A[:n_env, ep], 0, 1))   # [T, E, S, A]
+        mask = np.ascontiguousarray(np.swapaxes(M[:n_env, ep], 0, 1))   # [T, E, S]
+        out = env.rollout_batch(acts, mask)
+        env.check_errors()
+        for t in range(T):
+            counts, rows = env.tracked_messages_batch(0, n_env, step=t)
+            for e in range(n_env):
+                r = rows[e, : counts[e]]
+                got = np.stack([r[:, 0] & 0xFF, (r[:, 0] >> 8) & 0xFF, (r[:, 0] >> 16) & 0xFF,
+                                r[:, 1], r[:, 2]], 1)
+                want = gm[(gm[:, 0] == e) & (gm[:, 1] == ep) & (gm[:, 2] == t)][:, 3:8]
+                assert np.array_equal(got, want), (e, ep, t)
+        om = out.obs_mask.cpu().numpy()
+        assert np.array_equal(np.swapaxes(om, 0, 1), g["obs_mask"][:n_env, ep])
+    env.close()

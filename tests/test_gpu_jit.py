@@ -50,7 +50,7 @@ def test_specialised_tile_engine_matches_reference_golden(golden_dir):
 
     def make(**kw):
         env = MarketEnv(**kw).specialise()
-        assert env.exec_name == "queue(G=32, specialised)"
+        assert env.exec_name == "queue(G=32, collective, specialised)"
         return env
 
     run_device_vs_golden(make, g).close()
