@@ -89,8 +89,11 @@ typedef enum phx_family {
                                   post_message_resolution + custom EnvView field)         */
   PHX_FAMILY_DIGITAL_ADS = 8,  /* examples/environments/digital_ads_market/ (auction in a
                                   handle_batch override, three response rounds)           */
-  PHX_FAMILY_SUPPLY_CHAIN2 = 6 /* multi-shop supply chain with agent supertypes
+  PHX_FAMILY_SUPPLY_CHAIN2 = 6,/* multi-shop supply chain with agent supertypes
                                   (docs/user/tutorial2.rst)                           */
+  PHX_FAMILY_USER = 100        /* a device program the CALLER compiled (phx_create_user):
+                                  the reference's "bring your own agent classes"
+                                  (phantom/agents.py:48-60) without rebuilding libphx */
 } phx_family;
 
 typedef enum phx_exec_mode {
@@ -229,6 +232,16 @@ int32_t phx_device_count(void);
  *              depend on how envs are split over handles)                             */
 int32_t phx_create(const phx_spec* spec, int32_t num_envs, int32_t device, uint64_t seed,
                    int64_t env_offset, phx_env** out);
+/* The same for an env class whose device program is NOT part of libphx (spec->family ==
+ * PHX_FAMILY_USER): `cubin_path` names a cubin compiled for sm_100a from a translation unit that
+ * ends with PHX_USER_PROGRAM(Prog) (phantom_b200/csrc/phx_user.cuh; compile with
+ * `nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -cubin -I <csrc>`).  The program
+ * supplies the callbacks of the agent classes (decode_action / generate_messages, message
+ * handlers, hooks, encode_observation, compute_reward, is_terminated / is_truncated, reset);
+ * libphx supplies the step loop, the state in HBM and every other entry point of this header.
+ * Env classes of at most 8 agents (thread-per-env engine). */
+int32_t phx_create_user(const phx_spec* spec, const char* cubin_path, int32_t num_envs,
+                        int32_t device, uint64_t seed, int64_t env_offset, phx_env** out);
 void phx_destroy(phx_env* env);
 
 int32_t phx_num_envs(const phx_env* env);

@@ -39,6 +39,7 @@ FAMILY_SUPPLY_CHAIN, FAMILY_MOCK, FAMILY_MARKET, FAMILY_STACKELBERG, FAMILY_DENS
 FAMILY_SUPPLY_CHAIN2 = 6
 FAMILY_SIMPLE_MARKET = 7
 FAMILY_DIGITAL_ADS = 8
+FAMILY_USER = 100
 # phx_exec_mode
 EXEC_AUTO, EXEC_QUEUE, EXEC_FAST, EXEC_THREAD = 0, 1, 2, 3
 EXEC_MODES = {"auto": EXEC_AUTO, "queue": EXEC_QUEUE, "fast": EXEC_FAST, "thread": EXEC_THREAD}
@@ -120,6 +121,8 @@ SYMBOLS = {
     "phx_device_count": (C.c_int32, []),
     "phx_create": (C.c_int32, [C.POINTER(PhxSpec), C.c_int32, C.c_int32, C.c_uint64, C.c_int64,
                                C.POINTER(_P)]),
+    "phx_create_user": (C.c_int32, [C.POINTER(PhxSpec), C.c_char_p, C.c_int32, C.c_int32, C.c_uint64,
+                                    C.c_int64, C.POINTER(_P)]),
     "phx_destroy": (None, [_P]),
     "phx_num_envs": (C.c_int32, [_P]),
     "phx_exec_name": (C.c_char_p, [_P]),

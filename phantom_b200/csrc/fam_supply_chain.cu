@@ -408,20 +408,20 @@ struct Sc2Args {
   uint32_t* wire_overflow;
 };
 
-template <bool FULL_IO, bool VEC, bool WIRE>
+template <bool FULL_IO, bool VEC, bool WIRE, int RING = SC2_RING>
 __global__ void __launch_bounds__(SC_BLOCK) sc_fast2_kernel(const Sc2Args args) {
   const ScArgs& a = args.a;
   const ScPlan& p = a.p;
   extern __shared__ __align__(16) unsigned char sc2_smem[];
   float (*act_ring)[SC_BLOCK] = reinterpret_cast<float (*)[SC_BLOCK]>(sc2_smem);
-  const uint8_t* dsum = sc2_smem + sizeof(float) * SC2_RING * SC_BLOCK;
+  const uint8_t* dsum = sc2_smem + sizeof(float) * RING * SC_BLOCK;
   // Programmatic dependent launch: the next launch on the stream may start its blocks and run
   // its prologue (the table fill below) while this grid is still stepping; it waits at
   // griddep_wait() before it touches anything a previous kernel may have written.
   griddep_launch_dependents();
   {  // digit-sum table -> shared memory (4-byte words; the host pads the table to 16 bytes)
     const uint32_t* src = reinterpret_cast<const uint32_t*>(args.dsum);
-    uint32_t* dst = reinterpret_cast<uint32_t*>(sc2_smem + sizeof(float) * SC2_RING * SC_BLOCK);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(sc2_smem + sizeof(float) * RING * SC_BLOCK);
     for (uint32_t i = threadIdx.x; i < (args.pow5 + 3u) / 4u; i += SC_BLOCK) dst[i] = src[i];
   }
   const int e_raw = blockIdx.x * SC_BLOCK + threadIdx.x;
@@ -451,7 +451,7 @@ __global__ void __launch_bounds__(SC_BLOCK) sc_fast2_kernel(const Sc2Args args) 
   float* const dst = VEC ? &act_ring[cj][warp * 32 + 4 * (lane & 7)] : &act_ring[0][threadIdx.x];
   int fetch_t = 0;  // first step of the next group to fetch
   auto fetch_group = [&]() {
-    const int slot0 = fetch_t & (SC2_RING - 1);
+    const int slot0 = fetch_t & (RING - 1);
     if (VEC) {
       if (fetch_t + cj < T) cp_async16(dst + slot0 * SC_BLOCK, src);
     } else {
@@ -464,7 +464,7 @@ __global__ void __launch_bounds__(SC_BLOCK) sc_fast2_kernel(const Sc2Args args) 
     cp_async_commit();
   };
 #pragma unroll
-  for (int g = 0; g < 4; ++g) fetch_group();
+  for (int g = 0; g < RING / 4; ++g) fetch_group();
   __syncthreads();  // the table
 
   // ---- the three parts of a step
@@ -517,11 +517,11 @@ __global__ void __launch_bounds__(SC_BLOCK) sc_fast2_kernel(const Sc2Args args) 
   int t = 0;
   while (t < T) {
     // top up the ring: group (fetch_t / 4 - 4)'s slots are free once t has passed them
-    if (t >= fetch_t - 12) {
+    if (t >= fetch_t - (RING - 4)) {
       __syncwarp();
       fetch_group();
     }
-    cp_async_wait<2>();  // all but the two youngest groups have landed: steps <= t + 4
+    cp_async_wait<RING / 4 - 2>();  // all but the youngest groups have landed: steps <= t + 7
     __syncwarp();
     const int g = h.x + 1;
     const bool can4 = (g & 3) == 0 && t + 4 <= T && (!auto_reset || g + 3 < num_steps);
@@ -533,7 +533,7 @@ __global__ void __launch_bounds__(SC_BLOCK) sc_fast2_kernel(const Sc2Args args) 
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         D[k] = dsum[__umulhi(b.w[k], pow5)];
-        r[k] = decode(act_ring[(t + k) & (SC2_RING - 1)][threadIdx.x]);
+        r[k] = decode(act_ring[(t + k) & (RING - 1)][threadIdx.x]);
       }
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
@@ -545,7 +545,7 @@ __global__ void __launch_bounds__(SC_BLOCK) sc_fast2_kernel(const Sc2Args args) 
     } else {
       const uint32_t x = words.word(p.seed, env_id, (uint32_t)h.y, (uint32_t)g, SC_STREAM_ORDER);
       const int D = dsum[__umulhi(x, pow5)];
-      const int r = decode(act_ring[t & (SC2_RING - 1)][threadIdx.x]);
+      const int r = decode(act_ring[t & (RING - 1)][threadIdx.x]);
       h.x += 1;
       update(r, D);
       emit(h.x == num_steps, auto_reset && h.x == num_steps);
@@ -1037,17 +1037,21 @@ class SupplyChainFast final : public Family {
         PHX_CUDA(cudaGetLastError());
         return PHX_OK;
       }
-      const size_t smem = sizeof(float) * SC2_RING * SC_BLOCK + ((pow5 + 15u) & ~15u);
       b.wire = wire;
       b.wire_overflow = wire_overflow;
       void (*kern)(const Sc2Args) =
           wire ? (a.vec_actions ? sc_fast2_kernel<false, true, true> : sc_fast2_kernel<false, false, true>)
           : lean ? (a.vec_actions ? sc_fast2_kernel<false, true, false> : sc_fast2_kernel<false, false, false>)
                  : (a.vec_actions ? sc_fast2_kernel<true, true, false> : sc_fast2_kernel<true, false, false>);
+      int ring = SC2_RING;
+      if (sc_ring == 32 && lean && !wire && a.vec_actions) {  // A/B: a deeper action ring
+        kern = sc_fast2_kernel<false, true, false, 32>;
+        ring = 32;
+      }
       cudaLaunchConfig_t cfg{};
       cfg.gridDim = dim3(grid);
       cfg.blockDim = dim3(SC_BLOCK);
-      cfg.dynamicSmemBytes = smem;
+      cfg.dynamicSmemBytes = sizeof(float) * ring * SC_BLOCK + ((pow5 + 15u) & ~15u);
       cfg.stream = stream;
       cudaLaunchAttribute attr[1];
       attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -1234,6 +1238,7 @@ class SupplyChainFast final : public Family {
   // PHX_NO_WIRE=1 (read when the handle is created) keeps phx_rollout_host on the float planes
   const bool no_wire = std::getenv("PHX_NO_WIRE") != nullptr && std::getenv("PHX_NO_WIRE")[0] == '1';
   const int sc_warps = std::getenv("PHX_SC_WARPS") ? std::atoi(std::getenv("PHX_SC_WARPS")) : 4;
+  const int sc_ring = std::getenv("PHX_SC_RING") ? std::atoi(std::getenv("PHX_SC_RING")) : 16;
   int4* d_shop = nullptr;
   void* d_scratch = nullptr;  // planes the caller did not ask for (non-lean layouts)
   size_t scratch_bytes = 0;

@@ -353,8 +353,8 @@ int32_t phx_selftest_jit_source(const phx_spec* spec, int32_t num_envs, uint64_t
   return PHX_OK;
 }
 
-int32_t phx_create(const phx_spec* spec, int32_t num_envs, int32_t device, uint64_t seed,
-                   int64_t env_offset, phx_env** out) {
+static int32_t create_common(const phx_spec* spec, const char* cubin_path, int32_t num_envs,
+                             int32_t device, uint64_t seed, int64_t env_offset, phx_env** out) {
   PHX_REQUIRE(out != nullptr, PHX_ERR_INVALID, "out is NULL");
   *out = nullptr;
   int32_t rc = check_spec(spec);
@@ -366,36 +366,10 @@ int32_t phx_create(const phx_spec* spec, int32_t num_envs, int32_t device, uint6
   PHX_REQUIRE(ndev > 0, PHX_ERR_NO_DEVICE,
               "no CUDA device visible: libphx has no CPU fallback by design");
   PHX_REQUIRE(device >= 0 && device < ndev, PHX_ERR_INVALID, "device index out of range");
-
-  Family* fam = nullptr;
-  switch (spec->family) {
-    case PHX_FAMILY_SUPPLY_CHAIN:
-      fam = phx::make_supply_chain_family(*spec);
-      break;
-    case PHX_FAMILY_MOCK:
-      fam = phx::make_mock_family(*spec);
-      break;
-    case PHX_FAMILY_MARKET:
-      fam = phx::make_market_family(*spec);
-      break;
-    case PHX_FAMILY_STACKELBERG:
-      fam = phx::make_stackelberg_family(*spec);
-      break;
-    case PHX_FAMILY_DENSE:
-      fam = phx::make_dense_family(*spec);
-      break;
-    case PHX_FAMILY_SUPPLY_CHAIN2:
-      fam = phx::make_supply_chain2_family(*spec);
-      break;
-    case PHX_FAMILY_SIMPLE_MARKET:
-      fam = phx::make_simple_market_family(*spec);
-      break;
-    case PHX_FAMILY_DIGITAL_ADS:
-      fam = phx::make_digital_ads_family(*spec);
-      break;
-    default:
-      set_error("no device program for family " + std::to_string(spec->family));
-      return PHX_ERR_UNSUPPORTED;
+  Family* fam = spec->family == PHX_FAMILY_USER ? phx::make_user_family(cubin_path) : make_family(spec);
+  if (fam == nullptr) {
+    set_error("no device program for family " + std::to_string(spec->family));
+    return PHX_ERR_UNSUPPORTED;
   }
   rc = fam->base_init(*spec, num_envs, device, seed, env_offset);
   if (rc == PHX_OK) rc = fam->init(*spec);
@@ -411,6 +385,21 @@ int32_t phx_create(const phx_spec* spec, int32_t num_envs, int32_t device, uint6
   }
   *out = h;
   return PHX_OK;
+}
+
+int32_t phx_create(const phx_spec* spec, int32_t num_envs, int32_t device, uint64_t seed,
+                   int64_t env_offset, phx_env** out) {
+  PHX_REQUIRE(spec == nullptr || spec->family != PHX_FAMILY_USER, PHX_ERR_INVALID,
+              "PHX_FAMILY_USER needs phx_create_user (a cubin path)");
+  return create_common(spec, nullptr, num_envs, device, seed, env_offset, out);
+}
+
+int32_t phx_create_user(const phx_spec* spec, const char* cubin_path, int32_t num_envs,
+                        int32_t device, uint64_t seed, int64_t env_offset, phx_env** out) {
+  PHX_REQUIRE(spec != nullptr && spec->family == PHX_FAMILY_USER, PHX_ERR_INVALID,
+              "phx_create_user: spec->family must be PHX_FAMILY_USER");
+  PHX_REQUIRE(cubin_path != nullptr, PHX_ERR_INVALID, "cubin_path is NULL");
+  return create_common(spec, cubin_path, num_envs, device, seed, env_offset, out);
 }
 
 void phx_destroy(phx_env* env) {

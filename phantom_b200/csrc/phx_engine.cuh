@@ -1108,9 +1108,8 @@ __global__ void __launch_bounds__(ENGINE_BLOCK) engine_step_kernel(const EngineA
 
 // PhantomEnv.reset / FiniteStateMachineEnv.reset / StackelbergEnv.reset for masked envs.
 template <class P, int G>
-__global__ void __launch_bounds__(ENGINE_BLOCK)
-engine_reset_kernel(const EngineArgs<P> a, const uint8_t* env_mask, float* obs, uint8_t* obs_mask,
-                    bool agents_only) {
+__device__ __forceinline__ void engine_reset_body(const EngineArgs<P>& a, const uint8_t* env_mask,
+                                                  float* obs, uint8_t* obs_mask, bool agents_only) {
   constexpr int TPB = ENGINE_BLOCK / G;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   BlockSmem<P, G>& bs = *reinterpret_cast<BlockSmem<P, G>*>(smem_raw);
@@ -1203,6 +1202,13 @@ engine_reset_kernel(const EngineArgs<P> a, const uint8_t* env_mask, float* obs, 
 #pragma unroll
     for (int w = 0; w < P::NWORDS; ++w) a.state[((size_t)w * sp.E + e) * G + slot] = st[w];
   }
+}
+
+template <class P, int G>
+__global__ void __launch_bounds__(ENGINE_BLOCK)
+engine_reset_kernel(const EngineArgs<P> a, const uint8_t* env_mask, float* obs, uint8_t* obs_mask,
+                    bool agents_only) {
+  engine_reset_body<P, G>(a, env_mask, obs, obs_mask, agents_only);
 }
 
 }  // namespace phx

@@ -41,19 +41,33 @@ struct Engine1Layout {
   int off_stage, st_rew, st_om, st_rm, st_term, st_trunc, st_all, stage_bytes;
 };
 
+// (run-time form: programs loaded from a user cubin are only known by their descriptor)
+__host__ __device__ inline Engine1Layout engine1_layout_rt(int nwords, int vw, int act_dim, int pw,
+                                                           int n_agents, int n_strategic, int qcap,
+                                                           bool cached_env, int obs_dim,
+                                                           bool with_stage);
+
 template <class P>
 __host__ __device__ inline Engine1Layout engine1_layout(int n_agents, int n_strategic, int qcap,
                                                         bool cached_env, int obs_dim,
                                                         bool with_stage) {
+  return engine1_layout_rt(P::NWORDS, P::VW, P::ACT_DIM, P::PW, n_agents, n_strategic, qcap,
+                           cached_env, obs_dim, with_stage);
+}
+
+__host__ __device__ inline Engine1Layout engine1_layout_rt(int nwords, int vw, int act_dim, int pw,
+                                                           int n_agents, int n_strategic, int qcap,
+                                                           bool cached_env, int obs_dim,
+                                                           bool with_stage) {
   Engine1Layout L;
   L.n = n_agents; L.S = n_strategic > 0 ? n_strategic : 1; L.qcap = qcap;
   int rows = 0;
-  L.off_state = rows; rows += P::NWORDS * n_agents;
-  L.off_views = rows; rows += P::VW > 0 ? n_agents : 0;
+  L.off_state = rows; rows += nwords * n_agents;
+  L.off_views = rows; rows += vw > 0 ? n_agents : 0;
   L.off_rcache = rows; rows += cached_env ? n_agents : 0;
-  L.off_act = rows; rows += 2 * L.S * P::ACT_DIM;
+  L.off_act = rows; rows += 2 * L.S * act_dim;
   L.off_qhead = rows; rows += 2 * qcap;
-  L.off_qpay = rows; rows += 2 * qcap * P::PW;
+  L.off_qpay = rows; rows += 2 * qcap * pw;
   L.off_tables = rows * ENGINE1_BLOCK;           // kind_tab / ip0_tab / in_tab, 32 words each
   L.off_stage = (L.off_tables + 3 * ENGINE_MAX_AGENTS + 3) & ~3;  // 16-byte aligned
   const int rowS = ENGINE1_BLOCK * L.S;          // strategic rows of a block

@@ -204,8 +204,16 @@ class PhantomEnv:
             return
         spec = self.spec
         h = C.c_void_p()
-        L.check(L.lib.phx_create(C.byref(spec), self.num_envs, self.device, self.seed,
-                                 self.env_offset, C.byref(h)))
+        info = self.family
+        if info.program_source is not None:  # the user's own device program (csrc/phx_user.cuh)
+            from . import jit
+
+            cubin = jit.compile_program(info.program_source)
+            L.check(L.lib.phx_create_user(C.byref(spec), cubin.encode(), self.num_envs,
+                                          self.device, self.seed, self.env_offset, C.byref(h)))
+        else:
+            L.check(L.lib.phx_create(C.byref(spec), self.num_envs, self.device, self.seed,
+                                     self.env_offset, C.byref(h)))
         self._handle = h
         for a in self.agents.values():
             a._phx_env = self

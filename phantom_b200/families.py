@@ -24,6 +24,10 @@ class FamilyInfo:
     # (env, agent, word[, value]) -> column: state access for a family's non-engine kernel
     fast_column: Optional[Callable] = None
     supports_supertypes: bool = False
+    # A family that is NOT compiled into libphx.so: path of the user's .cu device program (it
+    # ends with PHX_USER_PROGRAM(Prog), csrc/phx_user.cuh).  family_id must be FAMILY_USER; the
+    # file is compiled at run time (nvcc -cubin, cached) and loaded with phx_create_user.
+    program_source: Optional[str] = None
 
 
 REGISTRY: Dict[str, FamilyInfo] = {}
@@ -32,6 +36,23 @@ REGISTRY: Dict[str, FamilyInfo] = {}
 def register(info: FamilyInfo) -> FamilyInfo:
     REGISTRY[info.name] = info
     return info
+
+
+def register_user_family(name: str, program_source: str, payload_types: Sequence[type],
+                         obs_dim: int, act_dim: int, env_kinds: Tuple[int, ...] = (0, 1, 2),
+                         collect: Optional[Callable] = None,
+                         trace_capacity: Optional[Callable] = None) -> FamilyInfo:
+    """Register an env class family whose device program is the user's own .cu file -- the
+    reference's "subclass Agent and write handlers" (phantom/agents.py:48-60) without rebuilding
+    libphx.  Agent classes name the family with `__phx_family__ = name` and their kind id with
+    `__phx_kind__`; `payload_types[i]` is the device payload type id i."""
+    from . import _lib as L
+
+    return register(FamilyInfo(
+        name=name, family_id=L.FAMILY_USER, payload_types=tuple(payload_types), obs_dim=obs_dim,
+        act_dim=act_dim, env_kinds=tuple(env_kinds), collect=collect or (lambda env, agents, spec: None),
+        trace_capacity=trace_capacity or (lambda env, agents: 8 * len(agents)),
+        program_source=program_source))
 
 
 def get(name: str) -> FamilyInfo:

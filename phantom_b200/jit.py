@@ -58,7 +58,16 @@ def source(env) -> str:
     return buf.value.decode()
 
 
-def compile_unit(text: str, cache: Optional[str] = None) -> str:
+def compile_program(path: str, cache: Optional[str] = None) -> str:
+    """A user's device program (a .cu file ending with PHX_USER_PROGRAM(...), csrc/phx_user.cuh)
+    -> path of its cubin.  Files it includes with "..." are looked up next to it first."""
+    path = os.path.abspath(path)
+    with open(path) as f:
+        text = f.read()
+    return compile_unit(text, cache, include_dirs=[os.path.dirname(path)])
+
+
+def compile_unit(text: str, cache: Optional[str] = None, include_dirs=()) -> str:
     """text -> path of the cubin (compiled once per distinct text / source tree / nvcc)."""
     cache = cache or CACHE
     try:
@@ -78,7 +87,10 @@ def compile_unit(text: str, cache: Optional[str] = None) -> str:
         with open(unit, "w") as f:
             f.write(text)
         out = os.path.join(tmp, "unit.cubin")
-        cmd = [nvcc, *ARCH, "-O3", "-std=c++17", "-lineinfo", "-cubin", "-I", CSRC, "-o", out, unit]
+        cmd = [nvcc, *ARCH, "-O3", "-std=c++17", "-lineinfo", "-cubin", "-I", CSRC]
+        for d in include_dirs:
+            cmd += ["-I", d]
+        cmd += ["-o", out, unit]
         proc = subprocess.run(cmd, capture_output=True, text=True)
         if proc.returncode != 0:
             raise RuntimeError("nvcc failed on the specialised unit:\n" + proc.stderr[-4000:])
