@@ -408,7 +408,7 @@ struct Sc2Args {
   uint32_t* wire_overflow;
 };
 
-template <bool FULL_IO, bool VEC, bool WIRE, int RING = SC2_RING>
+template <bool FULL_IO, bool VEC, bool WIRE, int RING = SC2_RING, bool AR = false>
 __global__ void __launch_bounds__(SC_BLOCK) sc_fast2_kernel(const Sc2Args args) {
   const ScArgs& a = args.a;
   const ScPlan& p = a.p;
@@ -434,7 +434,8 @@ __global__ void __launch_bounds__(SC_BLOCK) sc_fast2_kernel(const Sc2Args args) 
   const uint32_t E = (uint32_t)p.E;
   const uint32_t pow5 = args.pow5;
   const int max_stock = p.max_stock, num_steps = p.num_steps;
-  const bool auto_reset = (p.flags & PHX_FLAG_AUTO_RESET) != 0;
+  // AR instantiation: launched only for handles with PHX_FLAG_AUTO_RESET (the flag as a constant)
+  const bool auto_reset = AR || (p.flags & PHX_FLAG_AUTO_RESET) != 0;
 
   griddep_wait();  // env state, actions: written by earlier work on the stream
   int2 h = *reinterpret_cast<const int2*>(a.hdr + e);
@@ -515,34 +516,69 @@ __global__ void __launch_bounds__(SC_BLOCK) sc_fast2_kernel(const Sc2Args args) 
 
   PackedWords words;  // single-step path: block cache
   int t = 0;
-  while (t < T) {
-    // top up the ring: group (fetch_t / 4 - 4)'s slots are free once t has passed them
+  // NB Philox blocks = 4 * NB aligned steps: all (r, D) pairs first (independent of the state
+  // and of each other: two Philox chains interleave), then the state updates and output rows
+  auto fast_groups = [&](auto nbc) {
+    constexpr int NB = decltype(nbc)::value;
+    const uint32_t blk0 = (uint32_t)(h.x + 1) >> 2;
+    int D[4 * NB], r[4 * NB];
+#pragma unroll
+    for (int q = 0; q < NB; ++q) {
+      const Philox4 b = rng_word_block(p.seed, env_id, (uint32_t)h.y, blk0 + q, SC_STREAM_ORDER);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        D[4 * q + k] = dsum[__umulhi(b.w[k], pow5)];
+        r[4 * q + k] = decode(act_ring[(t + 4 * q + k) & (RING - 1)][threadIdx.x]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4 * NB; ++k) {
+      h.x += 1;  // env.py:252
+      update(r[k], D[k]);
+      // (no wrap inside aligned groups, see `mine` below: with auto-reset no step of a group is
+      // the episode's last one)
+      emit(AR ? false : h.x == num_steps, false);
+    }
+    t += 4 * NB;
+  };
+  auto top_up = [&]() {
+    // group (fetch_t / 4 - RING / 4)'s slots are free once t has passed them
     if (t >= fetch_t - (RING - 4)) {
       __syncwarp();
       fetch_group();
     }
-    cp_async_wait<RING / 4 - 2>();  // all but the youngest groups have landed: steps <= t + 7
-    __syncwarp();
+  };
+  while (t < T) {
+    // How many aligned 4-step groups can EVERY env of the warp run from here?  (aligned: the
+    // next step's word is the first of a Philox block; no auto-reset wrap inside a group)
     const int g = h.x + 1;
-    const bool can4 = (g & 3) == 0 && t + 4 <= T && (!auto_reset || g + 3 < num_steps);
-    if (__all_sync(0xFFFFFFFFu, can4)) {
-      // ---- four steps from one Philox block
-      const Philox4 b = rng_word_block(p.seed, env_id, (uint32_t)h.y, (uint32_t)g >> 2,
-                                       SC_STREAM_ORDER);
-      int D[4], r[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        D[k] = dsum[__umulhi(b.w[k], pow5)];
-        r[k] = decode(act_ring[(t + k) & (RING - 1)][threadIdx.x]);
+    int mine = 0;
+    if ((g & 3) == 0) {
+      mine = (T - t) >> 2;
+      if (auto_reset) mine = min(mine, g <= num_steps ? (num_steps - g) >> 2 : 0);
+    }
+    int n = __reduce_min_sync(0xFFFFFFFFu, mine);
+    if (n > 0) {
+      // two groups per trip need a ring deep enough to keep their actions a trip ahead
+      for (; n >= 2 && RING >= 32; n -= 2) {
+        top_up();
+        top_up();
+        cp_async_wait<RING / 4 - 3>();  // steps <= t + 7 have landed
+        __syncwarp();
+        fast_groups(std::integral_constant<int, 2>{});
       }
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        h.x += 1;  // env.py:252
-        update(r[k], D[k]);
-        emit(h.x == num_steps, false);  // (no wrap inside an aligned group, see can4)
+      for (; n > 0; --n) {
+        top_up();
+        top_up();  // (after an 8-step trip the ring may be two groups behind)
+        cp_async_wait<RING / 4 - 2>();
+        __syncwarp();
+        fast_groups(std::integral_constant<int, 1>{});
       }
-      t += 4;
     } else {
+      top_up();
+      top_up();
+      cp_async_wait<RING / 4 - 2>();  // all but the youngest groups have landed: steps <= t + 3
+      __syncwarp();
       const uint32_t x = words.word(p.seed, env_id, (uint32_t)h.y, (uint32_t)g, SC_STREAM_ORDER);
       const int D = dsum[__umulhi(x, pow5)];
       const int r = decode(act_ring[t & (RING - 1)][threadIdx.x]);
@@ -1047,6 +1083,8 @@ class SupplyChainFast final : public Family {
       if (sc_ring == 32 && lean && !wire && a.vec_actions) {  // A/B: a deeper action ring
         kern = sc_fast2_kernel<false, true, false, 32>;
         ring = 32;
+      } else if (lean && !wire && a.vec_actions && (plan.flags & PHX_FLAG_AUTO_RESET)) {
+        kern = sc_fast2_kernel<false, true, false, SC2_RING, true>;  // the bench instantiation
       }
       cudaLaunchConfig_t cfg{};
       cfg.gridDim = dim3(grid);

@@ -17,6 +17,7 @@ void set_error(const std::string& msg);  // thread-local, read by phx_last_error
     cudaError_t err__ = (call);                                                     \
     if (err__ != cudaSuccess) {                                                     \
       ::phx::set_error(std::string(#call) + ": " + cudaGetErrorString(err__));      \
+      (void)cudaGetLastError(); /* do not leave it for an unrelated later check */  \
       return PHX_ERR_CUDA;                                                          \
     }                                                                               \
   } while (0)
