@@ -395,6 +395,12 @@ __global__ void __launch_bounds__(SC_BLOCK) sc_fast_kernel(const ScArgs a) {
 //    path -- 4 % of the bench's steps.
 //  Valid for: 5 customers whose orders are all delivered, no action mask, no tracking,
 //  max_order^5 <= SC2_MAX_TABLE (rollout_range checks; everything else runs sc_fast_kernel).
+#ifndef SC2_INNER_LOOP
+#define SC2_INNER_LOOP 0
+#endif
+#ifndef SC2_AR_INSTANCE
+#define SC2_AR_INSTANCE 0
+#endif
 constexpr int SC2_MAX_TABLE = 16384;
 constexpr int SC2_RING = 16;  // action ring: four copy groups of four steps
 
@@ -567,7 +573,12 @@ __global__ void __launch_bounds__(SC_BLOCK) sc_fast2_kernel(const Sc2Args args) 
         __syncwarp();
         fast_groups(std::integral_constant<int, 2>{});
       }
-      for (; n > 0; --n) {
+#if SC2_INNER_LOOP
+      for (; n > 0; --n)
+#else
+      if (n > 0)  // (one group per vote: measured faster than an inner loop over n, 30.2 vs 32.4 us)
+#endif
+      {
         top_up();
         top_up();  // (after an 8-step trip the ring may be two groups behind)
         cp_async_wait<RING / 4 - 2>();
@@ -794,6 +805,184 @@ __global__ void __launch_bounds__(SC3_ENVS * W, W == 4 ? 14 : 16) sc_fast3_kerne
     a.shop[e] = s;
     // first fault in event order: a bad action is detected in decode_action, before any send
     const uint32_t fault = bad[lane] ? (uint32_t)PHX_FAULT_INVALID_ACTION : p.fault[1];
+    if (fault) raise_fault(a.faults, e, fault);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// sc_fast4_kernel -- TWO LANES PER ENV, same warp, no barrier.  sc_fast2_kernel is bound by
+// dependent-issue latency at 3.5 warps per scheduler (E is fixed); sc_fast3_kernel doubled and
+// quadrupled the warps but paid for it with block barriers and 2.4x the instructions.  Here an
+// env is owned by the lanes L and L + 16 of one warp and the work of an 8-step trip (two Philox
+// blocks) is split WITHOUT divergence -- both lanes run the same instruction stream on
+// different data:
+//   lane p (0 / 1)   Philox block blk0 + p -> D of steps 4p .. 4p+3, rint of those four
+//                    actions, packed as r * 32 + D (|r| <= 2^20, D <= 25)
+//   exchange         four SHFL.BFLY (xor 16): both lanes now hold all eight (r, D) pairs
+//   recurrence       both lanes run the eight 7-instruction state updates (redundant: that is
+//                    the price, 56 instructions per trip) and keep the (stock, sales, missed)
+//                    of THEIR four steps
+//   outputs          lane p writes the rows of steps 4p .. 4p+3
+// Per env-step the pair issues ~94 thread-instructions instead of 73, on twice the warps.
+// Steps that are not part of an aligned trip (the first three after a reset, the last four of
+// an episode) run on both lanes, lane 0 writes.
+constexpr int SC4_THREADS = 64;  // 32 envs per block
+
+template <bool FULL_IO, bool AR, int RING>
+__global__ void __launch_bounds__(SC4_THREADS) sc_fast4_kernel(const Sc2Args args) {
+  const ScArgs& a = args.a;
+  const ScPlan& p = a.p;
+  __shared__ __align__(16) float act_ring[SC4_THREADS / 32][RING][16];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int half = lane >> 4, el = lane & 15;
+  // (launched only with env_count % 32 == 0: every warp owns 16 real envs)
+  const int e = a.env_begin + blockIdx.x * (SC4_THREADS / 2) + warp * 16 + el;
+  const uint32_t env_id = p.env_offset + (uint32_t)e;
+  const float cap_f = p.cap_f, rcp_cap = p.rcp_cap;
+  const float max_stock_f = p.max_stock_f, rcp_stock = p.rcp_stock;
+  const uint32_t E = (uint32_t)p.E;
+  const uint32_t pow5 = args.pow5;
+  const uint8_t* __restrict__ dsum = args.dsum;  // (global / L1: 3 KB, hot)
+  const int max_stock = p.max_stock, num_steps = p.num_steps, T = a.T;
+  const bool auto_reset = AR || (p.flags & PHX_FLAG_AUTO_RESET) != 0;
+
+  int2 h = *reinterpret_cast<const int2*>(a.hdr + e);
+  int4 s = a.shop[e];
+  bool bad_action = false;
+
+  // ---- action ring: fetch unit = 8 steps x 16 envs = 512 B = one 16-byte cp.async per lane
+  // (lane -> step lane / 4, env quad lane % 4)
+  const float* src = a.io.actions + (size_t)(lane >> 2) * E + (size_t)(e - el + 4 * (lane & 3));
+  int fetch_t = 0;
+  auto fetch_unit = [&]() {
+    if (fetch_t + (lane >> 2) < T)
+      cp_async16(&act_ring[warp][(fetch_t + (lane >> 2)) & (RING - 1)][4 * (lane & 3)], src);
+    src += (size_t)8 * E;
+    fetch_t += 8;
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int g = 0; g < RING / 8; ++g) fetch_unit();
+  auto top_up = [&](int t) {  // the unit (fetch_t - RING)'s slots are free once t has passed them
+    if (t >= fetch_t - (RING - 8)) {
+      __syncwarp();
+      fetch_unit();
+    }
+  };
+
+  auto update = [&](const int r, const int D) {
+    const int ask = min(r, max_stock - s.x);        // decode_action, supply_chain.py:136-142
+    const int before = s.x;
+    const int after = max(max(before, 0) - D, 0);   // handle_order_request x 5, closed form
+    s.y = before - after;                           // sales
+    s.z = D - s.y;                                  // missed_sales
+    s.w = ask;                                      // handle_stock_response, :98-102
+    s.x = min(after + ask, max_stock);
+  };
+  // one output row (t, e) from (stock shown, sales, missed, reward numerator)
+  auto emit = [&](const int t, const int stock, const int sales, const int missed, const int k,
+                  const bool at_max) {
+    const uint32_t row = (uint32_t)t * E + (uint32_t)e;
+    const float reward = sc_ratio(k, 10.0f, 0.1f);
+    const float o0 = sc_ratio(stock, max_stock_f, rcp_stock);
+    const float o1 = sc_ratio(sales, cap_f, rcp_cap);
+    const float o2 = sc_ratio(missed, cap_f, rcp_cap);
+    float* o = a.io.obs + (size_t)row * 3;
+    __stcs(o, o0); __stcs(o + 1, o1); __stcs(o + 2, o2);
+    st_stream(a.io.reward + row, reward);
+    __stcs(reinterpret_cast<uchar2*>(a.io.all_done) + row, make_uchar2(0, at_max ? 1 : 0));
+    if (FULL_IO) {
+      __stcs(a.io.obs_mask + row, (uint8_t)1);
+      __stcs(a.io.reward_mask + row, (uint8_t)1);
+      __stcs(a.io.term + row, (uint8_t)0);
+      __stcs(a.io.trunc + row, (uint8_t)0);
+    }
+  };
+  auto decode = [&](const float act) {
+    if (!(fabsf(act) <= SC_MAX_ABS_ACTION)) bad_action = true;
+    return __float2int_rn(act);  // python round() of a float32 is round-half-even == cvt.rni
+  };
+
+  PackedWords words;
+  int t = 0;
+  while (t < T) {
+    // aligned 8-step trips every env of the warp can run from here (no wrap inside a trip)
+    const int g = h.x + 1;
+    int mine = 0;
+    if ((g & 3) == 0) {
+      mine = (T - t) >> 3;
+      if (auto_reset) mine = min(mine, g <= num_steps ? (num_steps - g) >> 3 : 0);
+    }
+    int n = __reduce_min_sync(0xFFFFFFFFu, mine);
+    if (n > 0) {
+      for (; n > 0; --n) {
+        top_up(t);
+        top_up(t);
+        cp_async_wait<RING / 8 - 3>();  // all but the youngest units have landed: steps <= t + 7
+        __syncwarp();
+        // ---- my half of the trip: one Philox block, four (r, D) pairs
+        const Philox4 b = rng_word_block(p.seed, env_id, (uint32_t)h.y,
+                                         ((uint32_t)(h.x + 1) >> 2) + (uint32_t)half, SC_STREAM_ORDER);
+        int mine4[4], other4[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int D = __ldg(dsum + __umulhi(b.w[k], pow5));
+          const int r = decode(act_ring[warp][(t + 4 * half + k) & (RING - 1)][el]);
+          mine4[k] = r * 32 + D;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) other4[k] = __shfl_xor_sync(0xFFFFFFFFu, mine4[k], 16);
+        // ---- the recurrence over all eight steps (both lanes), keeping my four rows
+        int rs[4], ry[4], rz[4];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int v = (j < 4) == (half == 0) ? mine4[j & 3] : other4[j & 3];
+          update(v >> 5, v & 31);
+          if ((j >> 2) == half) {  // (a select, not a branch: three predicated moves)
+            rs[j & 3] = s.x;
+            ry[j & 3] = s.y;
+            rz[j & 3] = s.z;
+          }
+        }
+        // ---- my four output rows
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int step_no = h.x + 4 * half + k + 1;
+          emit(t + 4 * half + k, rs[k], ry[k], rz[k], 10 * ry[k] - rs[k],
+               AR ? false : step_no == num_steps);
+        }
+        h.x += 8;  // env.py:252, eight times
+        t += 8;
+      }
+    } else {
+      top_up(t);
+      top_up(t);
+      cp_async_wait<RING / 8 - 2>();
+      __syncwarp();
+      const uint32_t x = words.word(p.seed, env_id, (uint32_t)h.y, (uint32_t)g, SC_STREAM_ORDER);
+      const int D = __ldg(dsum + __umulhi(x, pow5));
+      const int r = decode(act_ring[warp][t & (RING - 1)][el]);
+      h.x += 1;
+      update(r, D);
+      const bool at_max = h.x == num_steps;
+      const int k = 10 * s.y - s.x;  // reward numerator: before a reset clears the stock
+      if (auto_reset && at_max) {    // Network.reset -> ShopAgent.reset clears the stock only
+        s.x = 0;
+        h.x = 0;
+        h.y += 1;
+      }
+      if (half == 0) emit(t, s.x, s.y, s.z, k, at_max);
+      t += 1;
+    }
+  }
+  cp_async_wait<0>();
+
+  bad_action = __shfl_xor_sync(0xFFFFFFFFu, (int)bad_action, 16) != 0 || bad_action;
+  if (half == 0) {
+    *reinterpret_cast<int2*>(a.hdr + e) = h;
+    a.shop[e] = s;
+    // first fault in event order: a bad action is detected in decode_action, before any send
+    const uint32_t fault = bad_action ? (uint32_t)PHX_FAULT_INVALID_ACTION : p.fault[1];
     if (fault) raise_fault(a.faults, e, fault);
   }
 }
@@ -1052,12 +1241,26 @@ class SupplyChainFast final : public Family {
     const bool all_delivered_ = plan.deliver_ord == (1u << plan.nc) - 1u;
     PHX_REQUIRE(wire == nullptr || wire_ok(lean && !mask), PHX_ERR_INVALID,
                 "compact wire output is not available for this launch");
-    if (pow5 != 0 && !mask && !track && all_delivered_ && plan.delivery_ok && !use_v1) {
+    // (short launches -- phx_step is T = 1 -- stay on sc_fast_kernel: the round-2 kernels fill a
+    // 3 KB table per block first, which costs a single-step launch 0.9 us: 2.95 vs 2.03 us)
+    if (pow5 != 0 && !mask && !track && all_delivered_ && plan.delivery_ok && !use_v1 &&
+        (T >= 4 || wire)) {
       // the round-2 kernels
       Sc2Args b;
       b.a = a;
       b.dsum = d_dsum;
       b.pow5 = pow5;
+      if (sc_variant == 4 && a.vec_actions && env_count % 32 == 0 && !wire) {  // two lanes per env
+        const int grid4 = env_count / (SC4_THREADS / 2);
+        const bool ar = (plan.flags & PHX_FLAG_AUTO_RESET) != 0;
+        void (*k4)(const Sc2Args) =
+            lean ? (ar ? (sc_ring == 32 ? sc_fast4_kernel<false, true, 32> : sc_fast4_kernel<false, true, 64>)
+                       : sc_fast4_kernel<false, false, 64>)
+                 : (ar ? sc_fast4_kernel<true, true, 64> : sc_fast4_kernel<true, false, 64>);
+        k4<<<grid4, SC4_THREADS, 0, stream>>>(b);
+        PHX_CUDA(cudaGetLastError());
+        return PHX_OK;
+      }
       if (sc_variant == 3 && plan.num_steps >= 4) {  // the time-parallel kernel
         const int grid3 = (env_count + SC3_ENVS - 1) / SC3_ENVS;
         const bool w2 = sc_warps == 2;
@@ -1083,9 +1286,12 @@ class SupplyChainFast final : public Family {
       if (sc_ring == 32 && lean && !wire && a.vec_actions) {  // A/B: a deeper action ring
         kern = sc_fast2_kernel<false, true, false, 32>;
         ring = 32;
-      } else if (lean && !wire && a.vec_actions && (plan.flags & PHX_FLAG_AUTO_RESET)) {
-        kern = sc_fast2_kernel<false, true, false, SC2_RING, true>;  // the bench instantiation
       }
+#if SC2_AR_INSTANCE
+      else if (lean && !wire && a.vec_actions && (plan.flags & PHX_FLAG_AUTO_RESET)) {
+        kern = sc_fast2_kernel<false, true, false, SC2_RING, true>;  // auto-reset as a constant
+      }
+#endif
       cudaLaunchConfig_t cfg{};
       cfg.gridDim = dim3(grid);
       cfg.blockDim = dim3(SC_BLOCK);

@@ -169,16 +169,17 @@ def test_small_and_ragged_env_counts_against_vectorised_oracle(sc, E):
 
 
 @pytest.mark.parametrize("num_steps,T,E", [(10, 57, 1000), (100, 100, 4096), (7, 40, 333), (4, 19, 64),
-                                           (3, 11, 100)])
+                                           (3, 11, 100), (24, 131, 2048), (100, 250, 1024)])
 def test_fast_kernel_variants_agree(sc, monkeypatch, num_steps, T, E):
     """The three schedule-specialised kernels (PHX_SC_KERNEL = 1: round-1 thread-per-env, 2:
-    closed-form fill + aligned groups, 3: time-parallel, with 4 or 2 warps per 32 envs) produce
+    closed-form fill + aligned groups, 3: time-parallel, with 4 or 2 warps per 32 envs, 4: two
+    lanes per env -- used when the env count is a multiple of 64, else 2) produce
     identical planes and state, with auto-reset wraps inside the launch, launches that start at
     every clock phase (three consecutive rollouts of T steps) and negative actions."""
     r = np.random.RandomState(T)
     A = [r.uniform(-30, 130, size=(T, E, 1, 1)).astype(np.float32) for _ in range(3)]
     results = []
-    for variant, warps in ((1, 4), (2, 4), (3, 4), (3, 2)):
+    for variant, warps in ((1, 4), (2, 4), (3, 4), (3, 2), (4, 4)):
         monkeypatch.setenv("PHX_SC_KERNEL", str(variant))
         monkeypatch.setenv("PHX_SC_WARPS", str(warps))
         env = sc.SupplyChainEnv(num_envs=E, seed=12, num_steps=num_steps, auto_reset=True)
