@@ -140,6 +140,27 @@ __global__ void __launch_bounds__(DN_MAX) dense_step_kernel(const DenseArgs a) {
                               (sp.flags & PHX_FLAG_NO_PAYLOAD_CHECKS);
   const bool ok_send_ack = ((sp.sender_ok[DN_ACK][slot >> 5] >> (slot & 31)) & 1u) ||
                            (sp.flags & PHX_FLAG_NO_PAYLOAD_CHECKS);
+  // loop invariants of the acting phase: does this agent have neighbours, and may all of them
+  // receive a Signal (payload whitelist of the receivers, network.py:323-331)?
+  const bool has_neighbours = (adj[0] | adj[1] | adj[2] | adj[3]) != 0u;
+  const bool signal_recv_ok =
+      (sp.flags & PHX_FLAG_NO_PAYLOAD_CHECKS) ||
+      !((adj[0] & ~sp.receiver_ok[DN_SIGNAL][0]) | (adj[1] & ~sp.receiver_ok[DN_SIGNAL][1]) |
+        (adj[2] & ~sp.receiver_ok[DN_SIGNAL][2]) | (adj[3] & ~sp.receiver_ok[DN_SIGNAL][3]));
+  // every agent may receive an Ack (the usual case): no per-step lookup of the arg-max sender's bit
+  const bool ack_recv_all_ok =
+      (sp.flags & PHX_FLAG_NO_PAYLOAD_CHECKS) ||
+      ((sp.receiver_ok[DN_ACK][0] & full_w[0]) == full_w[0] && (sp.receiver_ok[DN_ACK][1] & full_w[1]) == full_w[1] &&
+       (sp.receiver_ok[DN_ACK][2] & full_w[2]) == full_w[2] && (sp.receiver_ok[DN_ACK][3] & full_w[3]) == full_w[3]);
+  if (bulk) {  // the four mask planes of this env class are constant: staged once
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      sm.stage[b].obs_mask[slot] = 1;
+      sm.stage[b].reward_mask[slot] = 1;
+      sm.stage[b].term[slot] = 0;
+      sm.stage[b].trunc[slot] = 0;
+    }
+  }
   // TMA bulk stores of one step's staged rows (issued by thread 0 one barrier after the rows
   // were written, so that no barrier exists for the stores alone)
   auto issue_stores = [&](int t) {
@@ -170,19 +191,12 @@ __global__ void __launch_bounds__(DN_MAX) dense_step_kernel(const DenseArgs a) {
     if (has) {
       if (!(fabsf(act) <= 1048576.0f)) fault = fault ? fault : PHX_FAULT_INVALID_ACTION;
       st[0] = max(0, min(1000, __float2int_rn(__fmul_rn(act, 1000.0f))));
-      sends = (adj[0] | adj[1] | adj[2] | adj[3]) != 0u;
-      if (sends && !ok_send_signal) fault = fault ? fault : PHX_FAULT_BAD_PAYLOAD_TYPE;
+      sends = has_neighbours;
+      if (sends && !(ok_send_signal && signal_recv_ok)) fault = fault ? fault : PHX_FAULT_BAD_PAYLOAD_TYPE;
     }
     const uint32_t sent_w = __ballot_sync(0xFFFFFFFFu, sends);
     if (lane == 0) sm.sent[warp] = sent_w;
-    if (sends) {
-      // payload whitelist of the receivers, one mask test per 32 neighbours (network.py:323-331)
-      if (!(sp.flags & PHX_FLAG_NO_PAYLOAD_CHECKS) &&
-          ((adj[0] & ~sp.receiver_ok[DN_SIGNAL][0]) | (adj[1] & ~sp.receiver_ok[DN_SIGNAL][1]) |
-           (adj[2] & ~sp.receiver_ok[DN_SIGNAL][2]) | (adj[3] & ~sp.receiver_ok[DN_SIGNAL][3])))
-        fault = fault ? fault : PHX_FAULT_BAD_PAYLOAD_TYPE;
-      sm.vals[slot] = st[0];  // one word per sender; the receivers of the pull form read it
-    }
+    if (sends) sm.vals[slot] = st[0];  // one word per sender; the receivers of the pull form read it
     // reduce form, this warp's part: the sum of its senders' values and, per sender class, its
     // best two senders as keys value * 128 + (127 - slot) (a higher key = a higher value, then
     // the LOWER slot: the first sender attaining the maximum wins, as in the reference's scan)
@@ -219,16 +233,28 @@ __global__ void __launch_bounds__(DN_MAX) dense_step_kernel(const DenseArgs a) {
                              sm.sent[0] == full_w[0] && sm.sent[1] == full_w[1] &&
                              sm.sent[2] == full_w[2] && sm.sent[3] == full_w[3];
     if (reduce_form) {  // block-uniform
+      // merge the four warps' (best, second best) of every class into the block's: lane c of
+      // each warp merges class c (five lanes busy once) and the result reaches the other lanes by
+      // shuffle -- 10 SHFL instead of the same 70-instruction merge on all 128 lanes
+      int g1m = -1, g2m = -1;
+      if (lane < 5) {
+        const int4 q01 = *reinterpret_cast<const int4*>(&sm.wtop[lane][0]);  // warps 0, 1
+        const int4 q23 = *reinterpret_cast<const int4*>(&sm.wtop[lane][2]);  // warps 2, 3
+        g1m = max(max(q01.x, q01.z), max(q23.x, q23.z));
+        g2m = max(max(q01.x == g1m ? q01.y : q01.x, q01.z == g1m ? q01.w : q01.z),
+                  max(q23.x == g1m ? q23.y : q23.x, q23.z == g1m ? q23.w : q23.z));
+      }
+      int g1c[5], g2c[5];
+#pragma unroll
+      for (int c = 0; c < 5; ++c) {
+        g1c[c] = __shfl_sync(0xFFFFFFFFu, g1m, c);
+        g2c[c] = __shfl_sync(0xFFFFFFFFu, g2m, c);
+      }
       if (is_agent) {
         int best = INT32_MIN, best_s = -1;
 #pragma unroll
         for (int c = 0; c < 5; ++c) {
-          // merge the four warps' (best, second best) of class c into the block's
-          const int4 q01 = *reinterpret_cast<const int4*>(&sm.wtop[c][0]);  // warps 0, 1
-          const int4 q23 = *reinterpret_cast<const int4*>(&sm.wtop[c][2]);  // warps 2, 3
-          const int g1 = max(max(q01.x, q01.z), max(q23.x, q23.z));
-          const int g2 = max(max(q01.x == g1 ? q01.y : q01.x, q01.z == g1 ? q01.w : q01.z),
-                             max(q23.x == g1 ? q23.y : q23.x, q23.z == g1 ? q23.w : q23.z));
+          const int g1 = g1c[c], g2 = g2c[c];
           const int k = (127 - (g1 & 127)) == slot ? g2 : g1;  // "but me"
           if (k >= 0) {
             const int v = (k >> 7) + tailtab[c], sdr = 127 - (k & 127);
@@ -243,8 +269,8 @@ __global__ void __launch_bounds__(DN_MAX) dense_step_kernel(const DenseArgs a) {
         st[2] = best;
         st[3] = best_s;
         ack_recv = best_s;
-        if (!ok_send_ack || (!((sp.receiver_ok[DN_ACK][best_s >> 5] >> (best_s & 31)) & 1u) &&
-                             !(sp.flags & PHX_FLAG_NO_PAYLOAD_CHECKS)))
+        if (!ok_send_ack ||
+            (!ack_recv_all_ok && !((sp.receiver_ok[DN_ACK][best_s >> 5] >> (best_s & 31)) & 1u)))
           fault = fault ? fault : PHX_FAULT_BAD_PAYLOAD_TYPE;
       }
     } else if (is_agent && sp.round_limit != 0) {
@@ -380,11 +406,7 @@ __global__ void __launch_bounds__(DN_MAX) dense_step_kernel(const DenseArgs a) {
       sg.obs[slot * 3 + 0] = o0;
       sg.obs[slot * 3 + 1] = o1;
       sg.obs[slot * 3 + 2] = o2;
-      sg.reward[slot] = rew;
-      sg.obs_mask[slot] = 1;
-      sg.reward_mask[slot] = 1;
-      sg.term[slot] = 0;
-      sg.trunc[slot] = 0;
+      sg.reward[slot] = rew;  // (the four mask planes were staged once, before the loop)
       fence_async_smem();  // issued by thread 0 after the NEXT barrier (issue_stores)
     } else if (is_agent) {
       const size_t o = row * n + slot;
