@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PHX_ABI_VERSION 5
+#define PHX_ABI_VERSION 6
 
 #define PHX_MAX_AGENTS 128  /* agent slots per env                                   */
 #define PHX_MAX_TYPES 16    /* payload types per env class                           */
@@ -126,9 +126,28 @@ typedef enum phx_rule_lhs {
   PHX_RULE_ALWAYS = 0,     /* unconditional: returns then_stage                            */
   PHX_RULE_STEP = 1,       /* env.current_step (already incremented, phantom/fsm.py:266)   */
   PHX_RULE_AGENT_WORD = 2, /* int32 state word `word` of agent slot `slot`                 */
-  PHX_RULE_ENV_WORD = 3    /* int32 env-level word `word` (families with env-level state)  */
+  PHX_RULE_ENV_WORD = 3,   /* int32 env-level word `word` (families with env-level state)  */
+  PHX_RULE_CONST = 4       /* right-hand sides only: the int32 constant `rhs`              */
 } phx_rule_lhs;
 typedef enum phx_cmp { PHX_CMP_LT = 0, PHX_CMP_LE, PHX_CMP_EQ, PHX_CMP_NE, PHX_CMP_GE, PHX_CMP_GT } phx_cmp;
+
+/* handler == 2: the handler is an if / elif / ... / else chain.  Branch b holds when ALL of its
+ * n_terms comparisons `<lhs operand> <cmp> <rhs operand>` hold (an operand is a phx_rule_lhs kind
+ * + slot / word, the rhs may also be a constant); the first branch that holds returns its `then`
+ * stage, none -> rule_else.  (OR = two branches with the same `then`.) */
+#define PHX_RULE_BRANCHES 4
+#define PHX_RULE_TERMS 2
+typedef struct phx_rule_term {
+  int32_t lhs, slot, word;             /* left operand: phx_rule_lhs STEP / AGENT_WORD / ENV_WORD  */
+  int32_t cmp;                         /* phx_cmp                                                  */
+  int32_t rhs_kind, rhs_slot, rhs_word;/* right operand: phx_rule_lhs STEP / ..._WORD / CONST      */
+  int32_t rhs;                         /* the constant of PHX_RULE_CONST                           */
+} phx_rule_term;
+typedef struct phx_rule_branch {
+  int32_t n_terms;                     /* 1 .. PHX_RULE_TERMS                                      */
+  int32_t then;                        /* stage index returned when every term holds               */
+  phx_rule_term term[PHX_RULE_TERMS];
+} phx_rule_branch;
 
 typedef struct phx_stage {
   uint32_t acting[PHX_MASK_WORDS];   /* FSMStage.acting_agents as a slot bitmask         */
@@ -136,7 +155,8 @@ typedef struct phx_stage {
   int32_t rewarded_is_none;          /* rewarded_agents is None (phantom/fsm.py:315-317) */
   int32_t next_stage;                /* next_stages[0]: the next stage of a handler-less
                                         stage (phantom/fsm.py:284-292)                   */
-  int32_t handler;                   /* 0 = no env handler; 1 = the rule below
+  int32_t handler;                   /* 0 = no env handler; 1 = the single rule_* comparison
+                                        below; 2 = the rule_branch chain
                                         (phantom/fsm.py:294-302)                         */
   uint32_t next_allowed;             /* FSMStage.next_stages as a stage bitmask; a handler
                                         returning a stage outside it faults with
@@ -146,6 +166,8 @@ typedef struct phx_stage {
                                         phantom/fsm.py:280-283)                          */
   int32_t rule_lhs, rule_slot, rule_word, rule_cmp, rule_rhs; /* phx_rule_lhs, phx_cmp   */
   int32_t rule_then, rule_else;      /* stage indices                                    */
+  int32_t rule_n_branches;           /* handler == 2: 1 .. PHX_RULE_BRANCHES             */
+  phx_rule_branch rule_branch[PHX_RULE_BRANCHES];
 } phx_stage;
 
 /* Flat description of one env class, lowered from the Python objects

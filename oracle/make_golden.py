@@ -355,6 +355,13 @@ def gen_fsm_handler_fuzz_reference() -> None:
         json.dump(out, f, separators=(",", ":"))
     raised = sorted(int(s) for s, t in out.items() if t[-1][0] == "raise")
     print("fsm_handler_fuzz_reference.json", len(out), "cases; raising:", raised)
+    # the same with compound handlers (if / elif / else chains of 1-2 comparisons per branch)
+    out = {str(s): kats.run_random_handler_fsm(K, s, compound=True)
+           for s in range(FSM_HANDLER_FUZZ_CASES)}
+    with open(os.path.join(GOLDEN, "fsm_compound_fuzz_reference.json"), "w") as f:
+        json.dump(out, f, separators=(",", ":"))
+    raised = sorted(int(s) for s, t in out.items() if t[-1][0] == "raise")
+    print("fsm_compound_fuzz_reference.json", len(out), "cases; raising:", raised)
 
 
 def gen_digital_ads_reference() -> None:

@@ -137,22 +137,36 @@ def build_classes(ph):
 
     ns.finish_network = finish_network
 
-    def stage_handler(then, lhs="always", cmp="==", rhs=0, otherwise=None, resolve_network=True):
+    def stage_handler(then, lhs="always", cmp="==", rhs=0, otherwise=None, resolve_network=True,
+                      also=None, elifs=None):
         """A Python env stage handler (reference: phantom/fsm.py:294-302) with the meaning of
-        phantom_b200.fsm.StageRule: [env.resolve_network()]; return then if lhs <cmp> rhs else
-        otherwise."""
+        phantom_b200.fsm.StageRule: [env.resolve_network()]; an if / elif / else chain whose
+        branches are conjunctions of comparisons between the clock, agent attributes and
+        constants."""
         import operator
 
-        op = {"<": operator.lt, "<=": operator.le, "==": operator.eq, "!=": operator.ne,
-              ">=": operator.ge, ">": operator.gt}[cmp]
+        ops = {"<": operator.lt, "<=": operator.le, "==": operator.eq, "!=": operator.ne,
+               ">=": operator.ge, ">": operator.gt}
+        branches = [([(lhs, cmp, rhs)] + ([] if also is None else [tuple(also)]), then)]
+        for terms, stage in elifs or ():
+            single = isinstance(terms, tuple) and len(terms) == 3 and terms[1] in ops
+            branches.append(([terms] if single else list(terms), stage))
 
         def handler(env):
             if resolve_network:
                 env.resolve_network()
             if lhs == "always":
                 return then
-            value = env.current_step if lhs == "step" else getattr(env.agents[lhs[1]], lhs[2])
-            return then if op(value, rhs) else otherwise
+
+            def value(x):
+                if isinstance(x, tuple):
+                    return getattr(env.agents[x[1]], x[2])
+                return env.current_step if x == "step" else x
+
+            for terms, stage in branches:
+                if all(ops[c](value(l), value(r)) for l, c, r in terms):
+                    return stage
+            return otherwise
 
         return handler
 

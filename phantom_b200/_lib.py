@@ -21,7 +21,7 @@ PHX_MAX_PARAMS = 16
 PHX_TRACE_WORDS = 4
 PHX_MAX_CODEC_OPS = 6
 PHX_MAX_BASE_CONNECTIONS = 528
-PHX_ABI_VERSION = 5
+PHX_ABI_VERSION = 6
 
 # phx_status
 PHX_OK, PHX_ERR_INVALID, PHX_ERR_CUDA, PHX_ERR_UNSUPPORTED, PHX_ERR_NO_DEVICE = 0, -1, -2, -3, -4
@@ -30,7 +30,8 @@ PHX_OK, PHX_ERR_INVALID, PHX_ERR_CUDA, PHX_ERR_UNSUPPORTED, PHX_ERR_NO_DEVICE = 
  FAULT_BAD_TRANSITION, FAULT_QUEUE_OVERFLOW, FAULT_INVALID_ACTION, FAULT_UNRESOLVED_MAIL,
  FAULT_PLAN_MISMATCH) = range(10)
 # phx_rule_lhs / phx_cmp (device form of an FSM stage handler)
-RULE_ALWAYS, RULE_STEP, RULE_AGENT_WORD, RULE_ENV_WORD = range(4)
+RULE_ALWAYS, RULE_STEP, RULE_AGENT_WORD, RULE_ENV_WORD, RULE_CONST = range(5)
+PHX_RULE_BRANCHES, PHX_RULE_TERMS = 4, 2
 CMP_LT, CMP_LE, CMP_EQ, CMP_NE, CMP_GE, CMP_GT = range(6)
 # phx_env_kind
 ENV_BASE, ENV_FSM, ENV_STACKELBERG = 0, 1, 2
@@ -55,6 +56,15 @@ FIELD_FAMILY = 16
 _MaskWords = C.c_uint32 * PHX_MASK_WORDS
 
 
+class PhxRuleTerm(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in
+                ("lhs", "slot", "word", "cmp", "rhs_kind", "rhs_slot", "rhs_word", "rhs")]
+
+
+class PhxRuleBranch(C.Structure):
+    _fields_ = [("n_terms", C.c_int32), ("then", C.c_int32), ("term", PhxRuleTerm * 2)]
+
+
 class PhxStage(C.Structure):
     _fields_ = [
         ("acting", _MaskWords),
@@ -71,6 +81,8 @@ class PhxStage(C.Structure):
         ("rule_rhs", C.c_int32),
         ("rule_then", C.c_int32),
         ("rule_else", C.c_int32),
+        ("rule_n_branches", C.c_int32),
+        ("rule_branch", PhxRuleBranch * 4),
     ]
 
 

@@ -86,28 +86,59 @@ struct EngineSpec {
   double agent_fparam[ENGINE_MAX_AGENTS][4];
   int32_t codec_op[ENGINE_MAX_AGENTS][PHX_MAX_CODEC_OPS];  // opcode | length << 8
   float codec_val[ENGINE_MAX_AGENTS][PHX_MAX_CODEC_OPS];
-  // device form of the stages' env handlers (fsm.py:294-307; include/phx.h phx_stage.rule_*)
-  int8_t stage_rule[PHX_MAX_STAGES][8];  // {handler, resolves, lhs, cmp, slot, word, then, else}
-  int32_t stage_rule_rhs[PHX_MAX_STAGES];
+  // device form of the stages' env handlers (fsm.py:294-307; include/phx.h phx_stage.rule_*):
+  // an if / elif / else chain, each branch a conjunction of comparisons between two operands
+  int8_t stage_rule[PHX_MAX_STAGES][4];  // {handler, resolves, n_branches, else}
+  int8_t rule_branch[PHX_MAX_STAGES][PHX_RULE_BRANCHES][2];                    // {n_terms, then}
+  int8_t rule_term[PHX_MAX_STAGES][PHX_RULE_BRANCHES][PHX_RULE_TERMS][8];      // RT_*
+  int32_t rule_rhs[PHX_MAX_STAGES][PHX_RULE_BRANCHES][PHX_RULE_TERMS];         // PHX_RULE_CONST
   uint8_t stage_allowed[PHX_MAX_STAGES];  // FSMStage.next_stages as a stage bitmask
 };
 
-enum { SR_HANDLER = 0, SR_RESOLVES, SR_LHS, SR_CMP, SR_SLOT, SR_WORD, SR_THEN, SR_ELSE };
+enum { SR_HANDLER = 0, SR_RESOLVES, SR_BRANCHES, SR_ELSE };
+enum { RT_LHS = 0, RT_SLOT, RT_WORD, RT_CMP, RT_RHS, RT_RHS_SLOT, RT_RHS_WORD };
 
-// `return then_stage if lhs <cmp> rhs else else_stage` of a stage handler.
-__device__ __forceinline__ int stage_rule_pick(const EngineSpec& sp, int stage, int lhs) {
-  const int rhs = sp.stage_rule_rhs[stage];
-  bool c = true;
-  switch (sp.stage_rule[stage][SR_CMP]) {
-    case PHX_CMP_LT: c = lhs < rhs; break;
-    case PHX_CMP_LE: c = lhs <= rhs; break;
-    case PHX_CMP_EQ: c = lhs == rhs; break;
-    case PHX_CMP_NE: c = lhs != rhs; break;
-    case PHX_CMP_GE: c = lhs >= rhs; break;
-    default: c = lhs > rhs; break;
+__device__ __forceinline__ bool rule_compare(int cmp, int lhs, int rhs) {
+  switch (cmp) {
+    case PHX_CMP_LT: return lhs < rhs;
+    case PHX_CMP_LE: return lhs <= rhs;
+    case PHX_CMP_EQ: return lhs == rhs;
+    case PHX_CMP_NE: return lhs != rhs;
+    case PHX_CMP_GE: return lhs >= rhs;
+    default: return lhs > rhs;
   }
-  if (sp.stage_rule[stage][SR_LHS] == PHX_RULE_ALWAYS) c = true;
-  return c ? sp.stage_rule[stage][SR_THEN] : sp.stage_rule[stage][SR_ELSE];
+}
+
+// `if <terms of branch 0>: return then_0 / elif ...: return then_1 / ... / return else` of a
+// stage handler.  `operand(kind, slot, word, constant)` reads one operand from the env's state
+// (uniform over the threads of an env: the rule is part of the spec).
+// (a specialised unit folds the whole chain: the spec is a constant there, so unroll it)
+#ifdef PHX_JIT_TU
+#define PHX_RULE_UNROLL _Pragma("unroll")
+#else
+#define PHX_RULE_UNROLL _Pragma("unroll 1")
+#endif
+template <class Operand>
+__device__ __forceinline__ int stage_rule_pick(const EngineSpec& sp, int stage, Operand&& operand) {
+  const int nb = sp.stage_rule[stage][SR_BRANCHES];
+  PHX_RULE_UNROLL
+  for (int b = 0; b < PHX_RULE_BRANCHES; ++b) {
+    if (b >= nb) break;
+    bool all = true;
+    const int nt = sp.rule_branch[stage][b][0];
+    PHX_RULE_UNROLL
+    for (int k = 0; k < PHX_RULE_TERMS; ++k) {
+      if (k >= nt) break;
+      const int8_t* t = sp.rule_term[stage][b][k];
+      if (t[RT_LHS] == PHX_RULE_ALWAYS) continue;
+      const int lhs = operand((int)t[RT_LHS], (int)t[RT_SLOT], (int)t[RT_WORD], 0);
+      const int rhs = operand((int)t[RT_RHS], (int)t[RT_RHS_SLOT], (int)t[RT_RHS_WORD],
+                              sp.rule_rhs[stage][b][k]);
+      all = all && rule_compare(t[RT_CMP], lhs, rhs);
+    }
+    if (all) return sp.rule_branch[stage][b][1];
+  }
+  return sp.stage_rule[stage][SR_ELSE];
 }
 
 struct Msg {
@@ -905,24 +936,25 @@ __device__ __forceinline__ void engine_step_body(const EngineArgs<P>& a) {
 
     // ---- the stage's env handler picks the next stage (fsm.py:294-307)
     if (handled) {
-      const int lk = sp.stage_rule[h.z][SR_LHS];
-      int lhs = h.x;
-      if (lk == PHX_RULE_AGENT_WORD) {
-        const int rs = sp.stage_rule[h.z][SR_SLOT], rw = sp.stage_rule[h.z][SR_WORD];
-        int mine = 0;
+      next_stage = stage_rule_pick(sp, h.z, [&](int kind, int rs, int rw, int constant) {
+        int v = constant;
+        if (kind == PHX_RULE_STEP) {
+          v = h.x;
+        } else if (kind == PHX_RULE_AGENT_WORD) {
+          int mine = 0;
 #pragma unroll
-        for (int w = 0; w < P::NWORDS; ++w)
-          if (w == rw) mine = st[w];
-        lhs = __shfl_sync(tmask, mine, rs, G);
-      } else if (lk == PHX_RULE_ENV_WORD) {
-        if constexpr (EW > 0) {
-          const int rw = sp.stage_rule[h.z][SR_WORD];
+          for (int w = 0; w < P::NWORDS; ++w)
+            if (w == rw) mine = st[w];
+          v = __shfl_sync(tmask, mine, rs, G);
+        } else if (kind == PHX_RULE_ENV_WORD) {
+          if constexpr (EW > 0) {
 #pragma unroll
-          for (int w = 0; w < EW; ++w)
-            if (w == rw) lhs = envw[w];
+            for (int w = 0; w < EW; ++w)
+              if (w == rw) v = envw[w];
+          }
         }
-      }
-      next_stage = stage_rule_pick(sp, h.z, lhs);
+        return v;
+      });
       if (!((sp.stage_allowed[h.z] >> next_stage) & 1u)) {
         fault_key = min(fault_key, (0xFFFEu << 16) | (0xFFu << 8) | PHX_FAULT_BAD_TRANSITION);
         next_stage = h.z;

@@ -529,22 +529,23 @@ __device__ __forceinline__ void engine1_step_body(const EngineArgs<P>& a) {
 
     // ---- the stage's env handler picks the next stage (fsm.py:294-307)
     if (handled) {
-      const int lk = sp.stage_rule[h.z][SR_LHS];
-      int lhs = h.x;
-      if (lk == PHX_RULE_AGENT_WORD) {
-        const int rs = sp.stage_rule[h.z][SR_SLOT], rw = sp.stage_rule[h.z][SR_WORD];
+      next_stage = stage_rule_pick(sp, h.z, [&](int kind, int rs, int rw, int constant) {
+        int v = constant;
+        if (kind == PHX_RULE_STEP) {
+          v = h.x;
+        } else if (kind == PHX_RULE_AGENT_WORD) {
 #pragma unroll
-        for (int w = 0; w < P::NWORDS; ++w)
-          if (w == rw) lhs = ST(w, rs);
-      } else if (lk == PHX_RULE_ENV_WORD) {
-        if constexpr (EW > 0) {
-          const int rw = sp.stage_rule[h.z][SR_WORD];
+          for (int w = 0; w < P::NWORDS; ++w)
+            if (w == rw) v = ST(w, rs);
+        } else if (kind == PHX_RULE_ENV_WORD) {
+          if constexpr (EW > 0) {
 #pragma unroll
-          for (int w = 0; w < EW; ++w)
-            if (w == rw) lhs = envw[w];
+            for (int w = 0; w < EW; ++w)
+              if (w == rw) v = envw[w];
+          }
         }
-      }
-      next_stage = stage_rule_pick(sp, h.z, lhs);
+        return v;
+      });
       if (!((sp.stage_allowed[h.z] >> next_stage) & 1u)) {
         if (!fault) fault = PHX_FAULT_BAD_TRANSITION;
         next_stage = h.z;

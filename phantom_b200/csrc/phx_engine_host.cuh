@@ -65,32 +65,72 @@ inline int32_t make_engine_spec(const phx_spec& s, int32_t E, uint64_t seed, int
       continue;
     }
     // a stage with an env handler: the declarative rule (include/phx.h phx_stage.rule_*)
-    PHX_REQUIRE(g.handler == 1, PHX_ERR_UNSUPPORTED, "unknown FSM stage handler kind");
-    PHX_REQUIRE(g.rule_lhs >= PHX_RULE_ALWAYS && g.rule_lhs <= PHX_RULE_ENV_WORD &&
-                    g.rule_cmp >= PHX_CMP_LT && g.rule_cmp <= PHX_CMP_GT,
-                PHX_ERR_INVALID, "FSM stage rule: bad lhs / cmp");
-    // the RETURNED stage may be outside next_stages (a run-time FSMRuntimeError in the reference,
+    PHX_REQUIRE(g.handler == 1 || g.handler == 2, PHX_ERR_UNSUPPORTED,
+                "unknown FSM stage handler kind");
+    phx_rule_branch one{};  // handler == 1: the single comparison as a one-branch chain
+    const phx_rule_branch* br = g.rule_branch;
+    int nb = g.rule_n_branches;
+    if (g.handler == 1) {
+      one.n_terms = 1;
+      one.then = g.rule_then;
+      one.term[0].lhs = g.rule_lhs;
+      one.term[0].slot = g.rule_slot;
+      one.term[0].word = g.rule_word;
+      one.term[0].cmp = g.rule_cmp;
+      one.term[0].rhs_kind = PHX_RULE_CONST;
+      one.term[0].rhs = g.rule_rhs;
+      br = &one;
+      nb = 1;
+    }
+    PHX_REQUIRE(nb >= 1 && nb <= PHX_RULE_BRANCHES, PHX_ERR_INVALID,
+                "FSM stage rule: 1..PHX_RULE_BRANCHES branches");
+    // a RETURNED stage may be outside next_stages (a run-time FSMRuntimeError in the reference,
     // fsm.py:304-307), but it must be a stage index the kernel can hold
-    PHX_REQUIRE(g.rule_then >= 0 && g.rule_then < PHX_MAX_STAGES && g.rule_else >= 0 &&
-                    g.rule_else < PHX_MAX_STAGES,
-                PHX_ERR_INVALID, "FSM stage rule: stage index out of range");
-    if (g.rule_lhs == PHX_RULE_AGENT_WORD)
-      PHX_REQUIRE(g.rule_slot >= 0 && g.rule_slot < s.n_agents && g.rule_word >= 0 &&
-                      g.rule_word < nwords,
-                  PHX_ERR_INVALID, "FSM stage rule: no such agent state word");
-    if (g.rule_lhs == PHX_RULE_ENV_WORD)
-      PHX_REQUIRE(g.rule_word >= 0 && g.rule_word < envwords, PHX_ERR_INVALID,
-                  "FSM stage rule: no such env-level word");
+    PHX_REQUIRE(g.rule_else >= 0 && g.rule_else < PHX_MAX_STAGES, PHX_ERR_INVALID,
+                "FSM stage rule: stage index out of range");
+    auto operand_ok = [&](int kind, int slot, int word, bool rhs) {
+      if (kind == PHX_RULE_STEP) return true;
+      if (kind == PHX_RULE_AGENT_WORD)
+        return slot >= 0 && slot < s.n_agents && word >= 0 && word < nwords;
+      if (kind == PHX_RULE_ENV_WORD) return word >= 0 && word < envwords;
+      return rhs && kind == PHX_RULE_CONST;
+    };
     d.stage_next[k] = (int8_t)k;
     d.stage_rule[k][SR_HANDLER] = 1;
     d.stage_rule[k][SR_RESOLVES] = (int8_t)(g.rule_resolves != 0);
-    d.stage_rule[k][SR_LHS] = (int8_t)g.rule_lhs;
-    d.stage_rule[k][SR_CMP] = (int8_t)g.rule_cmp;
-    d.stage_rule[k][SR_SLOT] = (int8_t)g.rule_slot;
-    d.stage_rule[k][SR_WORD] = (int8_t)g.rule_word;
-    d.stage_rule[k][SR_THEN] = (int8_t)g.rule_then;
+    d.stage_rule[k][SR_BRANCHES] = (int8_t)nb;
     d.stage_rule[k][SR_ELSE] = (int8_t)g.rule_else;
-    d.stage_rule_rhs[k] = g.rule_rhs;
+    for (int b = 0; b < nb; ++b) {
+      PHX_REQUIRE(br[b].n_terms >= 1 && br[b].n_terms <= PHX_RULE_TERMS, PHX_ERR_INVALID,
+                  "FSM stage rule: 1..PHX_RULE_TERMS comparisons per branch");
+      PHX_REQUIRE(br[b].then >= 0 && br[b].then < PHX_MAX_STAGES, PHX_ERR_INVALID,
+                  "FSM stage rule: stage index out of range");
+      d.rule_branch[k][b][0] = (int8_t)br[b].n_terms;
+      d.rule_branch[k][b][1] = (int8_t)br[b].then;
+      for (int j = 0; j < br[b].n_terms; ++j) {
+        const phx_rule_term& t = br[b].term[j];
+        PHX_REQUIRE(t.cmp >= PHX_CMP_LT && t.cmp <= PHX_CMP_GT, PHX_ERR_INVALID,
+                    "FSM stage rule: bad lhs / cmp");
+        // `always` only as the single unconditional rule
+        const bool always = t.lhs == PHX_RULE_ALWAYS && br[b].n_terms == 1;
+        PHX_REQUIRE(always || (t.lhs != PHX_RULE_ALWAYS && operand_ok(t.lhs, t.slot, t.word, false)),
+                    PHX_ERR_INVALID,
+                    t.lhs == PHX_RULE_AGENT_WORD ? "FSM stage rule: no such agent state word"
+                    : t.lhs == PHX_RULE_ENV_WORD ? "FSM stage rule: no such env-level word"
+                                                 : "FSM stage rule: bad lhs / cmp");
+        PHX_REQUIRE(always || operand_ok(t.rhs_kind, t.rhs_slot, t.rhs_word, true), PHX_ERR_INVALID,
+                    "FSM stage rule: bad right-hand operand");
+        int8_t* o = d.rule_term[k][b][j];
+        o[RT_LHS] = (int8_t)t.lhs;
+        o[RT_SLOT] = (int8_t)t.slot;
+        o[RT_WORD] = (int8_t)t.word;
+        o[RT_CMP] = (int8_t)t.cmp;
+        o[RT_RHS] = (int8_t)t.rhs_kind;
+        o[RT_RHS_SLOT] = (int8_t)t.rhs_slot;
+        o[RT_RHS_WORD] = (int8_t)t.rhs_word;
+        d.rule_rhs[k][b][j] = t.rhs;
+      }
+    }
   }
   d.leaders = s.leaders[0];
   d.followers = s.followers[0];
@@ -159,7 +199,7 @@ inline std::string jit_spec_literal(const EngineSpec& d) {
   f(d.stage_acting); f(d.stage_rewarded); f(d.stage_rewarded_none); f(d.stage_next);
   f(d.leaders); f(d.followers); f(d.seed); f(d.env_offset); f(d.iparams); f(d.fparams);
   f(d.dparams); f(d.agent_iparam); f(d.agent_fparam); f(d.codec_op); f(d.codec_val);
-  f(d.stage_rule); f(d.stage_rule_rhs); f(d.stage_allowed);
+  f(d.stage_rule); f(d.rule_branch); f(d.rule_term); f(d.rule_rhs); f(d.stage_allowed);
   o += "}";
   return o;
 }

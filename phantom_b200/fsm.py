@@ -42,27 +42,53 @@ class StageRule:
 
         def handler(env):
             if resolve_network: env.resolve_network()       # fsm.py:280-283: a stage with a
-            value = <lhs>                                   # handler is resolved only by it
-            return then if value <cmp> rhs else otherwise
+            if <lhs> <cmp> <rhs> [and <also>]:              # handler is resolved only by it
+                return then
+            elif <terms of elifs[0]>: return <stage of elifs[0]>
+            ...
+            return otherwise
 
     lhs:  "always" | "step" (env.current_step) | ("agent", agent_id, column) where column is a
           device_column attribute name of that agent's class or a state word index |
           ("env", word) for families with env-level words.
     cmp:  one of "<", "<=", "==", "!=", ">=", ">".
+    rhs:  an int32 constant, or another operand ("step" / ("agent", ...) / ("env", word)).
+    also: a second comparison `(lhs, cmp, rhs)` that must hold as well (AND).
+    elifs: further branches `(terms, stage)` tried in order when the first does not hold, `terms`
+          one comparison `(lhs, cmp, rhs)` or a list of up to TERMS of them (AND).  OR is two
+          branches returning the same stage; up to BRANCHES branches in all.
     A returned stage outside the stage's `next_stages` faults the env with FSMRuntimeError
     (fsm.py:304-307).  The object is callable only so that it can sit where the reference
     expects a handler; calling it on the host raises DeviceOnlyError.
     """
 
     CMPS = ("<", "<=", "==", "!=", ">=", ">")
+    BRANCHES, TERMS = 4, 2  # include/phx.h PHX_RULE_BRANCHES / PHX_RULE_TERMS
 
-    def __init__(self, then: StageID, lhs="always", cmp: str = "==", rhs: int = 0,
-                 otherwise: Optional[StageID] = None, resolve_network: bool = True) -> None:
-        if cmp not in self.CMPS:
-            raise ValueError(f"StageRule: unknown comparison '{cmp}'")
+    def __init__(self, then: StageID, lhs="always", cmp: str = "==", rhs=0,
+                 otherwise: Optional[StageID] = None, resolve_network: bool = True,
+                 also=None, elifs=None) -> None:
         if lhs != "always" and otherwise is None:
             raise ValueError("StageRule: a conditional rule needs `otherwise`")
-        self.then, self.lhs, self.cmp, self.rhs = then, lhs, cmp, int(rhs)
+        if lhs == "always" and (also is not None or elifs):
+            raise ValueError("StageRule: an unconditional rule has no further comparisons")
+        first = [(lhs, cmp, rhs)] + ([] if also is None else [tuple(also)])
+        self.branches = [(first, then)]
+        for terms, stage in elifs or ():
+            terms = [tuple(terms)] if isinstance(terms, tuple) and len(terms) == 3 and \
+                isinstance(terms[1], str) and terms[1] in self.CMPS else [tuple(t) for t in terms]
+            self.branches.append((terms, stage))
+        if len(self.branches) > self.BRANCHES:
+            raise ValueError(f"StageRule: at most {self.BRANCHES} branches")
+        for terms, _ in self.branches:
+            if not 1 <= len(terms) <= self.TERMS:
+                raise ValueError(f"StageRule: 1..{self.TERMS} comparisons per branch")
+            for t in terms:
+                if len(t) != 3 or t[1] not in self.CMPS:
+                    raise ValueError(f"StageRule: unknown comparison {t!r}")
+                if t[0] == "always" and t is not first[0]:
+                    raise ValueError("StageRule: 'always' only as the single unconditional rule")
+        self.then, self.lhs, self.cmp, self.rhs = then, lhs, cmp, rhs
         self.otherwise = then if otherwise is None else otherwise
         self.resolve_network = bool(resolve_network)
 

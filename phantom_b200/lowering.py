@@ -16,6 +16,8 @@ from __future__ import annotations
 import ctypes as C
 from typing import List
 
+import numpy as np
+
 from . import _lib as L
 from . import families
 from .agents import Agent, StrategicAgent
@@ -88,36 +90,50 @@ def _lower_stage_rule(out, sid, st, stage_ids, agents, slot) -> None:
         # raises FSMRuntimeError (fsm.py:304-307): give it an index outside every next_allowed
         return stage_ids.index(x) if x in stage_ids else L.PHX_MAX_STAGES - 1
 
-    for x in (rule.then, rule.otherwise):
+    returned = [stage for _, stage in rule.branches] + [rule.otherwise]
+    for x in returned:
         if x not in stage_ids and len(stage_ids) >= L.PHX_MAX_STAGES:
             raise NotLowerableError("StageRule returns an unknown stage and no spare stage index is left")
-    if not -2 ** 31 <= rule.rhs < 2 ** 31:
-        raise NotLowerableError(f"StageRule of stage '{sid}': rhs {rule.rhs} is not an int32")
-    out.handler = 1
+
+    def operand(x, rhs):
+        """-> (kind, slot, word, constant) of one side of a comparison."""
+        if rhs and isinstance(x, (int, np.integer)) and not isinstance(x, bool):
+            if not -2 ** 31 <= int(x) < 2 ** 31:
+                raise NotLowerableError(f"StageRule of stage '{sid}': rhs {x} is not an int32")
+            return L.RULE_CONST, 0, 0, int(x)
+        if x == "step":
+            return L.RULE_STEP, 0, 0, 0
+        if isinstance(x, tuple) and len(x) == 3 and x[0] == "agent":
+            _, aid, column = x
+            if aid not in slot:
+                raise NotLowerableError(f"StageRule of stage '{sid}': unknown agent '{aid}'")
+            if isinstance(column, str):
+                desc = getattr(type(agents[slot[aid]]), column, None)
+                if not hasattr(desc, "word") or getattr(desc, "dtype", "int32") != "int32":
+                    raise NotLowerableError(
+                        f"StageRule of stage '{sid}': '{column}' is not an int32 device column of '{aid}'")
+                column = desc.word
+            return L.RULE_AGENT_WORD, slot[aid], int(column), 0
+        if isinstance(x, tuple) and len(x) == 2 and x[0] == "env":
+            return L.RULE_ENV_WORD, 0, int(x[1]), 0
+        side = "rhs" if rhs else "lhs"
+        raise NotLowerableError(f"StageRule of stage '{sid}': unknown {side} {x!r}")
+
+    out.handler = 2
     out.rule_resolves = int(rule.resolve_network)
-    out.rule_cmp = StageRule.CMPS.index(rule.cmp)
-    out.rule_rhs = rule.rhs
-    out.rule_then = stage_index(rule.then)
     out.rule_else = stage_index(rule.otherwise)
-    if rule.lhs == "always":
-        out.rule_lhs = L.RULE_ALWAYS
-    elif rule.lhs == "step":
-        out.rule_lhs = L.RULE_STEP
-    elif isinstance(rule.lhs, tuple) and len(rule.lhs) == 3 and rule.lhs[0] == "agent":
-        _, aid, column = rule.lhs
-        if aid not in slot:
-            raise NotLowerableError(f"StageRule of stage '{sid}': unknown agent '{aid}'")
-        if isinstance(column, str):
-            desc = getattr(type(agents[slot[aid]]), column, None)
-            if not hasattr(desc, "word") or getattr(desc, "dtype", "int32") != "int32":
-                raise NotLowerableError(
-                    f"StageRule of stage '{sid}': '{column}' is not an int32 device column of '{aid}'")
-            column = desc.word
-        out.rule_lhs, out.rule_slot, out.rule_word = L.RULE_AGENT_WORD, slot[aid], int(column)
-    elif isinstance(rule.lhs, tuple) and len(rule.lhs) == 2 and rule.lhs[0] == "env":
-        out.rule_lhs, out.rule_word = L.RULE_ENV_WORD, int(rule.lhs[1])
-    else:
-        raise NotLowerableError(f"StageRule of stage '{sid}': unknown lhs {rule.lhs!r}")
+    out.rule_n_branches = len(rule.branches)
+    for b, (terms, stage) in enumerate(rule.branches):
+        br = out.rule_branch[b]
+        br.n_terms, br.then = len(terms), stage_index(stage)
+        for k, (lhs, cmp, rhs) in enumerate(terms):
+            t = br.term[k]
+            t.cmp = StageRule.CMPS.index(cmp)
+            if lhs == "always":
+                t.lhs = L.RULE_ALWAYS
+                continue
+            t.lhs, t.slot, t.word, _ = operand(lhs, False)
+            t.rhs_kind, t.rhs_slot, t.rhs_word, t.rhs = operand(rhs, True)
 
 
 def lower(env, exec_mode: str = "auto", auto_reset: bool = False) -> L.PhxSpec:

@@ -552,14 +552,17 @@ ALL = [
 
 
 # ---------------------------------------------------------------- random handler-driven FSMs
-def random_handler_fsm(K, case_seed, **kw):
+def random_handler_fsm(K, case_seed, compound=False, **kw):
     """A random FiniteStateMachineEnv over the mock agents: 1-4 stages with random acting /
     rewarded sets, handler-less stages and stages with env handlers (`K.stage_handler`: always /
     clock / echo-agent counters after the handler's own resolve_network()), next_stages that
     sometimes do NOT contain what the handler returns (FSMRuntimeError at run time), strategic
     agents that terminate mid-episode, echo agents exchanging halving messages.  Deterministic in
-    `case_seed`; used as a differential fuzz oracle-vs-reference (CPU) and device-vs-oracle (GPU)."""
-    r = np.random.RandomState(case_seed)
+    `case_seed`; used as a differential fuzz oracle-vs-reference (CPU) and device-vs-oracle (GPU).
+    compound=True: most handlers are if / elif / else chains of up to four branches, each one or
+    two comparisons between the clock, echo-agent counters and constants (a different draw
+    sequence, its own golden)."""
+    r = np.random.RandomState(case_seed + (1000 if compound else 0))
     ph = K.ph
     strat = [f"s{i}" for i in range(int(r.randint(1, 4)))]
     echo = [f"e{i}" for i in range(int(r.randint(0, 4)))]
@@ -588,7 +591,31 @@ def random_handler_fsm(K, case_seed, **kw):
         sends = any(seeds.get(a, 0) > 0 for a in acting)
         resolve = True if sends else bool(r.uniform() < 0.5)
         cmp = ["<", "<=", "==", "!=", ">=", ">"][int(r.randint(6))]
-        if kind == "always":
+        if compound and kind != "always" and r.uniform() < 0.75:
+            def operand(rhs):
+                kinds_ = ["step"] + (["agent"] if echo else []) + (["const", "const"] if rhs else [])
+                k = kinds_[int(r.randint(len(kinds_)))]
+                if k == "step":
+                    return "step"
+                if k == "const":
+                    return int(r.randint(0, 12))
+                return ("agent", echo[int(r.randint(len(echo)))],
+                        ["handled_count", "handled_total"][int(r.randint(2))])
+
+            def term():
+                return (operand(False), ["<", "<=", "==", "!=", ">=", ">"][int(r.randint(6))],
+                        operand(True))
+
+            first = term()
+            also = term() if r.uniform() < 0.5 else None
+            elifs = []
+            for _ in range(int(r.randint(0, 4))):
+                terms = [term(), term()] if r.uniform() < 0.4 else term()
+                elifs.append((terms, sids[int(r.randint(len(sids)))]))
+            handler = K.stage_handler(then, first[0], first[1], first[2], otherwise=otherwise,
+                                      resolve_network=resolve, also=also, elifs=elifs)
+            returned = [then] + [st for _, st in elifs] + [otherwise]
+        elif kind == "always":
             handler = K.stage_handler(then, resolve_network=resolve)
             returned = [then]
         elif kind == "step":
@@ -611,10 +638,12 @@ def random_handler_fsm(K, case_seed, **kw):
     return env, strat, echo
 
 
-def run_random_handler_fsm(K, case_seed):
+def run_random_handler_fsm(K, case_seed, compound=False, prepare=None):
     """Steps the random FSM to the end of its episode (or its first exception) and returns a
     plain-Python trace that is comparable across implementations."""
-    env, strat, echo = random_handler_fsm(K, case_seed)
+    env, strat, echo = random_handler_fsm(K, case_seed, compound=compound)
+    if prepare is not None:
+        prepare(env)
 
     def plain(d):
         return {k: (None if v is None else

@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_spec_layout_matches_compiled_struct():
     assert L.lib.phx_sizeof_spec() == C.sizeof(L.PhxSpec)
-    assert L.lib.phx_abi_version() == L.PHX_ABI_VERSION == 5
+    assert L.lib.phx_abi_version() == L.PHX_ABI_VERSION == 6
 
 
 def test_no_cpu_fallback():
@@ -103,11 +103,15 @@ def test_lowering_fsm_stage_handlers():
 
     s = kats._fsm_state_driven(K).spec
     fill, drain = s.stages[0], s.stages[1]
-    assert (fill.handler, fill.rule_resolves, fill.next_allowed) == (1, 1, 0b11)
-    assert (fill.rule_lhs, fill.rule_slot, fill.rule_word) == (L.RULE_AGENT_WORD, 3, 3)  # b.handled_count
-    assert (fill.rule_cmp, fill.rule_rhs, fill.rule_then, fill.rule_else) == (L.CMP_GE, 4, 1, 0)
-    assert (drain.handler, drain.rule_resolves, drain.rule_lhs) == (1, 0, L.RULE_STEP)
-    assert (drain.rule_cmp, drain.rule_rhs, drain.rule_then, drain.rule_else) == (L.CMP_GE, 4, 0, 1)
+    assert (fill.handler, fill.rule_resolves, fill.next_allowed) == (2, 1, 0b11)
+    assert (fill.rule_n_branches, fill.rule_else) == (1, 0)
+    t = fill.rule_branch[0].term[0]
+    assert (fill.rule_branch[0].n_terms, fill.rule_branch[0].then) == (1, 1)
+    assert (t.lhs, t.slot, t.word) == (L.RULE_AGENT_WORD, 3, 3)  # b.handled_count
+    assert (t.cmp, t.rhs_kind, t.rhs) == (L.CMP_GE, L.RULE_CONST, 4)
+    t = drain.rule_branch[0].term[0]
+    assert (drain.handler, drain.rule_resolves, t.lhs) == (2, 0, L.RULE_STEP)
+    assert (t.cmp, t.rhs, drain.rule_branch[0].then, drain.rule_else) == (L.CMP_GE, 4, 0, 1)
 
     def one_stage(handler):
         return ph.FiniteStateMachineEnv(
@@ -116,7 +120,21 @@ def test_lowering_fsm_stage_handlers():
                                 handler=handler)])
 
     s = one_stage(ph.StageRule("B")).spec  # "B" is no stage: FSMRuntimeError at run time
-    assert s.stages[0].rule_then == L.PHX_MAX_STAGES - 1 and s.stages[0].next_allowed == 1
+    assert s.stages[0].rule_branch[0].then == L.PHX_MAX_STAGES - 1 and s.stages[0].next_allowed == 1
+    # an if / elif / else chain: (step >= 2 and step < 5) -> A; elif step == handled-by-column -> A
+    rule = ph.StageRule("A", "step", ">=", 2, otherwise="A", also=("step", "<", 5),
+                        elifs=[(("step", "==", "step"), "A"), ([("step", "!=", 7), ("step", ">", 0)], "A")])
+    g = one_stage(rule).spec.stages[0]
+    assert (g.handler, g.rule_n_branches) == (2, 3)
+    assert [g.rule_branch[b].n_terms for b in range(3)] == [2, 1, 2]
+    assert (g.rule_branch[0].term[1].cmp, g.rule_branch[0].term[1].rhs) == (L.CMP_LT, 5)
+    assert g.rule_branch[1].term[0].rhs_kind == L.RULE_STEP
+    with pytest.raises(ValueError):
+        ph.StageRule("A", also=("step", "<", 5))
+    with pytest.raises(ValueError):
+        ph.StageRule("A", "step", "<", 1, otherwise="A", elifs=[(("step", "<", k), "A") for k in range(4)])
+    with pytest.raises(ph.NotLowerableError):
+        one_stage(ph.StageRule("A", "step", "<", ("agent", "nobody", 0), otherwise="A")).spec
     with pytest.raises(ph.NotLowerableError):
         one_stage(lambda env: "A").spec
     with pytest.raises(ph.NotLowerableError):
@@ -289,3 +307,44 @@ def test_static_schedule_unit_is_generated_and_compiles(tmp_path):
     proc = subprocess.run([nvcc, *jit.ARCH, "-O3", "-std=c++17", "-cubin", "-I", jit.CSRC, "-o",
                            str(tmp_path / "unit.cubin"), str(unit)], capture_output=True, text=True)
     assert proc.returncode == 0, proc.stderr[-2000:]
+
+
+def test_compound_stage_rule_unit_compiles(tmp_path):
+    """The specialised unit of an FSM whose stage handlers are if / elif / else chains
+    (StageRule also= / elifs=, include/phx.h phx_rule_branch) is generated without a GPU and
+    compiles for sm_100a with the chain folded (no local-memory frame)."""
+    import shutil
+    import subprocess
+
+    import phantom_b200 as ph
+    from phantom_b200 import jit
+    from phantom_b200.envs import mock
+
+    class NS:
+        pass
+
+    K = NS()
+    K.ph, K.MockStrategicAgent, K.EchoAgent = ph, mock.MockStrategicAgent, mock.EchoAgent
+    K.finish_network, K.stage_handler = (lambda n: n), ph.StageRule
+    from . import kat_scenarios as kats
+
+    env = None
+    for seed in range(40):  # the first case with a three-branch chain
+        env, _, _ = kats.random_handler_fsm(K, seed, compound=True, num_envs=64, exec_mode="thread")
+        if max(st.rule_n_branches for st in env.spec.stages) >= 3:
+            break
+    spec = env.spec
+    need = C.c_uint64(0)
+    L.check(L.lib.phx_selftest_jit_source(C.byref(spec), 64, 7, None, 0, C.byref(need)))
+    buf = C.create_string_buffer(need.value)
+    L.check(L.lib.phx_selftest_jit_source(C.byref(spec), 64, 7, buf, need.value, None))
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    unit = tmp_path / "unit.cu"
+    unit.write_text(buf.value.decode())
+    proc = subprocess.run([nvcc, *jit.ARCH, "-O3", "-std=c++17", "-cubin", "-Xptxas", "-v", "-I",
+                           jit.CSRC, "-o", str(tmp_path / "unit.cubin"), str(unit)],
+                          capture_output=True, text=True)
+    assert proc.returncode == 0, proc.stderr[-2000:]
+    assert " 0 bytes stack frame" in proc.stderr, proc.stderr[-1500:]

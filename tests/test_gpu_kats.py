@@ -163,3 +163,29 @@ def test_random_handler_fsms_match_the_reference(K, exec_mode, monkeypatch):
     for s in range(len(want)):
         got = json.loads(json.dumps(kats.run_random_handler_fsm(K, s)))
         assert got == want[str(s)], f"case seed {s}"
+    # compound StageRules: if / elif / else chains of one or two comparisons per branch, operands
+    # on both sides (clock, echo-agent counters, constants)
+    want = json.load(open(path.replace("fsm_handler_fuzz", "fsm_compound_fuzz")))
+    for s in range(len(want)):
+        got = json.loads(json.dumps(kats.run_random_handler_fsm(K, s, compound=True)))
+        assert got == want[str(s)], f"compound case seed {s}"
+
+
+def test_compound_stage_rules_specialised(K, monkeypatch):
+    """The same compound-handler cases through run-time specialised units of the thread-per-env
+    engine (the rule chain is a compile-time constant there and folds)."""
+    import json
+    import os
+
+    monkeypatch.setattr(K.ph.PhantomEnv, "default_exec_mode", "thread")
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden",
+                        "fsm_compound_fuzz_reference.json")
+    want = json.load(open(path))
+
+    def prepare(env):
+        env.specialise()
+        assert "specialised" in env.exec_name
+
+    for s in (0, 3, 4, 7, 11, 19, 34):
+        got = json.loads(json.dumps(kats.run_random_handler_fsm(K, s, compound=True, prepare=prepare)))
+        assert got == want[str(s)], f"compound case seed {s}"

@@ -62,3 +62,9 @@ def test_random_handler_fsms_match_the_reference(K):
     for s in range(len(want)):
         got = json.loads(json.dumps(kats.run_random_handler_fsm(K, s)))
         assert got == want[str(s)], f"case seed {s}"
+    # compound handlers: if / elif / else chains over the clock, agent counters and constants
+    want = json.load(open(path.replace("fsm_handler_fuzz", "fsm_compound_fuzz")))
+    assert len(want) == 40 and sum(t[-1][0] == "raise" for t in want.values()) >= 2
+    for s in range(len(want)):
+        got = json.loads(json.dumps(kats.run_random_handler_fsm(K, s, compound=True)))
+        assert got == want[str(s)], f"compound case seed {s}"
