@@ -101,7 +101,9 @@ typedef enum phx_exec_mode {
   PHX_EXEC_QUEUE = 1,  /* force the generic engine with a tile of lanes per env       */
   PHX_EXEC_FAST = 2,   /* force the schedule-specialised kernel; create fails if the
                           spec is outside its domain                                  */
-  PHX_EXEC_THREAD = 3  /* force the generic engine with one thread per env (<= 8 agents) */
+  PHX_EXEC_THREAD = 3, /* force the generic engine with one thread per env (<= 8 agents) */
+  PHX_EXEC_WIDE = 4    /* force the generic engine with one 128-lane block per env (chosen
+                          automatically for 33..128 agents; programs that support it)   */
 } phx_exec_mode;
 
 enum {

@@ -364,16 +364,19 @@ def gen_fsm_handler_fuzz_reference() -> None:
     print("fsm_compound_fuzz_reference.json", len(out), "cases; raising:", raised)
 
 
-def gen_digital_ads_reference() -> None:
+def gen_digital_ads_reference(only=slice(None)) -> None:
     """The reference's examples/environments/digital_ads_market/digital_ads_market.py, UNMODIFIED
     (oracle/workloads/digital_ads.py:build_reference), under the contract RNG:
       digital_ads_reference.npz       2 + 2 + 2 advertisers, first-price auction (8 agents)
-      digital_ads_wide_reference.npz  10 + 10 + 10 advertisers, second-price auction (32 agents)"""
+      digital_ads_wide_reference.npz  10 + 10 + 10 advertisers, second-price auction (32 agents)
+      digital_ads_full_reference.npz  40 + 40 + 40 advertisers, the example's SHIPPED size
+                                      (digital_ads_market.py:687-689; 122 agents), first price"""
     from .workloads import digital_ads as wl
 
     for name, per_theme, strategy, n_env, n_ep, seed in (
             ("digital_ads_reference.npz", 2, "first", 8, 2, 20261026),
-            ("digital_ads_wide_reference.npz", 10, "second", 3, 2, 20261027)):
+            ("digital_ads_wide_reference.npz", 10, "second", 3, 2, 20261027),
+            ("digital_ads_full_reference.npz", 40, "first", 2, 2, 20261028))[only]:
         theme = {"travel": per_theme, "tech": per_theme, "sport": per_theme}
         budgets = ([(5.0, 15.001, 5.0, 15.0)] * per_theme + [(7.0, 17.001, 7.0, 17.0)] * per_theme +
                    [(10.0, 20.001, 10.0, 20.0)] * per_theme)

@@ -42,8 +42,9 @@ FAMILY_SIMPLE_MARKET = 7
 FAMILY_DIGITAL_ADS = 8
 FAMILY_USER = 100
 # phx_exec_mode
-EXEC_AUTO, EXEC_QUEUE, EXEC_FAST, EXEC_THREAD = 0, 1, 2, 3
-EXEC_MODES = {"auto": EXEC_AUTO, "queue": EXEC_QUEUE, "fast": EXEC_FAST, "thread": EXEC_THREAD}
+EXEC_AUTO, EXEC_QUEUE, EXEC_FAST, EXEC_THREAD, EXEC_WIDE = 0, 1, 2, 3, 4
+EXEC_MODES = {"auto": EXEC_AUTO, "queue": EXEC_QUEUE, "fast": EXEC_FAST, "thread": EXEC_THREAD,
+              "wide": EXEC_WIDE}
 # flags
 FLAG_IGNORE_CONNECTION_ERRORS, FLAG_NO_PAYLOAD_CHECKS, FLAG_TRACK_MESSAGES, FLAG_AUTO_RESET = 1, 2, 4, 8
 FLAG_STOCHASTIC_NETWORK, FLAG_SHUFFLE_BATCHES = 16, 32

@@ -25,13 +25,16 @@
 //   advertiser 0,1 left  2,3 type.budget  4,5 bid  6 step_clicks  7 step_wins  8 current user
 //              9,10 total_requests[1,2]  11,12 total_wins[1,2]  13,14 total_clicks[1,2]
 //   exchange   0 user of the impression on offer;  batch scratch: 1 bids seen, 2,3 highest bid,
-//              4,5 second highest, 6 winner slot, 7 bidder mask
+//              4,5 second highest, 6 winner slot, 7 + 15,16,17 bidder mask (slots 0-31, 32-127)
 // iparams: 0 exchange slot, 1 publisher slot, 2 second-price auction?, 3 + (user-1)*4 + theme =
 //          ceil(click probability * 2^24).
 // agent_iparam[advertiser] = {index of its sampler in env._samplers or -1, theme id}
 // agent_fparam[advertiser] = {low (or the constant budget), high, clip_low, clip_high}
 // RNG (24-bit draws): stream 3 samplers (step 0), stream 9 the impression's user, stream 10 the click.
 #include "phx_engine_host.cuh"
+#ifndef PHX_JIT_TU
+#include "phx_engine_wide_host.cuh"
+#endif
 
 namespace phx {
 namespace {
@@ -44,7 +47,7 @@ struct DigitalAdsProgram {
   static constexpr const char* JIT_SOURCE = "fam_digital_ads.cu";
   static constexpr const char* JIT_NAME = "DigitalAdsProgram";
   // acting phase: one message per agent; the exchange answers a round with up to 31 messages
-  static constexpr int PW = 2, NWORDS = 15, VW = 0, ACTCAP = 1, RESPCAP = 32, OBS_DIM = 3,
+  static constexpr int PW = 2, NWORDS = 18, VW = 0, ACTCAP = 1, RESPCAP = 32, OBS_DIM = 3,
                        ACT_DIM = 1, Q1CAP = 8;
   static constexpr int RECVCAP = 32;
   static constexpr bool BATCHED = true, HAS_PRE = true, HAS_POST = false;
@@ -53,6 +56,15 @@ struct DigitalAdsProgram {
   // publisher answers with one ImpressionResult, an advertiser never answers
   static constexpr int RESPTOTAL = 96;
   __host__ __device__ static int resp_cap(int kind, int) { return kind == 0 /* exchange */ ? 32 : 1; }
+  // the 128-lane block engine sizes its queues from the env class (phx_engine_wide.cuh): the
+  // exchange answers a round with one message per agent at most, everybody else with one
+  static constexpr bool WIDE_OK = true;
+  __host__ __device__ static int wide_act_cap(int, int, int) { return 1; }
+  __host__ __device__ static int wide_resp_cap(int kind, int, int n_agents) {
+    return kind == 0 /* exchange */ ? n_agents : 1;
+  }
+  // word of the exchange's bidder mask that holds slot s
+  __device__ static int bidder_word(int s) { return s < 32 ? 7 : 14 + (s >> 5); }
 
   static int q1_cap(const phx_spec& s) { return s.n_agents; }
 
@@ -76,9 +88,9 @@ struct DigitalAdsProgram {
     st[w + 1] = __double2hiint(v);
   }
 
-  template <class E>
-  __device__ static void act(const Ctx& c, int* st, bool has_action, const float* action, E& out) {
-    const EngineSpec& sp = *c.spec;
+  template <class C, class E>
+  __device__ static void act(const C& c, int* st, bool has_action, const float* action, E& out) {
+    const auto& sp = *c.spec;
     if (c.kind == DA_PUBLISHER) {  // generate_messages :163-164: np.random.choice([1, 2])
       const int user = 1 + rng_randint(c.rand24_hi(DA_STREAM_USER, 0u), 2u);
       out.send(sp.iparams[0], DA_IMPRESSION, user);
@@ -99,25 +111,30 @@ struct DigitalAdsProgram {
     if (bid > 0.0) out.send(sp.iparams[0], DA_BID, __double2loint(bid), __double2hiint(bid));
   }
 
-  __device__ static void view(const Ctx&, const int*, int*) {}
-  __device__ static void pre(const Ctx& c, int* st) {
+  template <class C>
+  __device__ static void view(const C&, const int*, int*) {}
+  template <class C>
+  __device__ static void pre(const C& c, int* st) {
     if (c.kind == DA_ADVERTISER) st[6] = st[7] = 0;  // :240-246, every step
   }
-  __device__ static void post(const Ctx&, int*) {}
+  template <class C>
+  __device__ static void post(const C&, int*) {}
 
   // AdExchangeAgent.handle_batch :429-454
-  __device__ static void batch_begin(const Ctx& c, int* st) {
+  template <class C>
+  __device__ static void batch_begin(const C& c, int* st) {
     if (c.kind == DA_EXCHANGE) st[1] = 0;
   }
 
-  template <class E>
-  __device__ static bool handle(const Ctx& c, int* st, const Msg& m, E& out) {
-    const EngineSpec& sp = *c.spec;
+  template <class C, class E>
+  __device__ static bool handle(const C& c, int* st, const Msg& m, E& out) {
+    const auto& sp = *c.spec;
     if (c.kind == DA_EXCHANGE) {
       if (m.type == DA_IMPRESSION) {  // :417-427: forward to every advertiser, list order
         st[0] = m.p[0];
-        for (uint32_t adv = sp.kind_mask[DA_ADVERTISER]; adv; adv &= adv - 1)
-          out.send(__ffs(adv) - 1, DA_IMPRESSION, m.p[0]);
+        for (int adv = c.next_of_kind(DA_ADVERTISER, -1); adv >= 0;
+             adv = c.next_of_kind(DA_ADVERTISER, adv))
+          out.send(adv, DA_IMPRESSION, m.p[0]);
         return true;
       }
       if (m.type != DA_BID) return false;
@@ -128,7 +145,7 @@ struct DigitalAdsProgram {
         put(st, 2, bid);
         put(st, 4, bid);
         st[6] = m.sender;
-        st[7] = 0;
+        st[7] = st[15] = st[16] = st[17] = 0;
       } else if (bid > dbl(st, 2)) {
         put(st, 4, dbl(st, 2));
         put(st, 2, bid);
@@ -137,7 +154,16 @@ struct DigitalAdsProgram {
         put(st, 4, bid);
       }
       st[1] += 1;
-      st[7] |= 1 << m.sender;
+      {
+        const int bw = bidder_word(m.sender);
+        const int bit = (int)(1u << (m.sender & 31));
+        if (bw == 7) st[7] |= bit;
+        if (C::MASK_WORDS > 1) {
+          if (bw == 15) st[15] |= bit;
+          if (bw == 16) st[16] |= bit;
+          if (bw == 17) st[17] |= bit;
+        }
+      }
       return true;
     }
     if (c.kind == DA_PUBLISHER) {  // handle_ads :167-193
@@ -174,23 +200,27 @@ struct DigitalAdsProgram {
     return false;
   }
 
-  template <class E>
-  __device__ static void batch_end(const Ctx& c, int* st, E& out) {
+  template <class C, class E>
+  __device__ static void batch_end(const C& c, int* st, E& out) {
     if (c.kind != DA_EXCHANGE || st[1] == 0) return;
-    const EngineSpec& sp = *c.spec;
+    const auto& sp = *c.spec;
     // auction :456-496: the highest bid wins; cost = it (first price) or the runner-up's bid
     const double cost = (sp.iparams[2] && st[1] > 1) ? dbl(st, 4) : dbl(st, 2);
     const int winner = st[6];
     const int theme = sp.agent_iparam[winner][1];
     out.send(sp.iparams[1], DA_ADS, winner, theme | (st[0] << 8));
-    for (uint32_t b = (uint32_t)st[7]; b; b &= b - 1) {  // every bidder, batch (= slot) order
-      const int adv = __ffs(b) - 1;
-      const double charged = adv == winner ? cost : 0.0;
-      out.send(adv, DA_RESULT, __double2loint(charged), __double2hiint(charged));
+#pragma unroll
+    for (int w = 0; w < C::MASK_WORDS; ++w) {  // every bidder, batch (= slot) order
+      for (uint32_t b = (uint32_t)(w == 0 ? st[7] : st[14 + w]); b; b &= b - 1) {
+        const int adv = 32 * w + __ffs(b) - 1;
+        const double charged = adv == winner ? cost : 0.0;
+        out.send(adv, DA_RESULT, __double2loint(charged), __double2hiint(charged));
+      }
     }
   }
 
-  __device__ static bool encode(const Ctx& c, int* st, float* obs) {
+  template <class C>
+  __device__ static bool encode(const C& c, int* st, float* obs) {
     if (c.kind != DA_ADVERTISER || st[8] == 0) return false;  // :292-311: None before an impression
     obs[0] = (float)__ddiv_rn(dbl(st, 0), dbl(st, 2));  // budget_left
     obs[1] = (float)dbl(st, 2);                         // type.budget
@@ -198,19 +228,23 @@ struct DigitalAdsProgram {
     return true;
   }
   // (1 - 0.0) * step_clicks + (0.0 * left) / budget == float(step_clicks)  (:329-337)
-  __device__ static float reward(const Ctx&, int* st) { return (float)st[6]; }
-  __device__ static bool terminated(const Ctx& c, const int* st) {
+  template <class C>
+  __device__ static float reward(const C&, int* st) { return (float)st[6]; }
+  template <class C>
+  __device__ static bool terminated(const C& c, const int* st) {
     return c.kind == DA_ADVERTISER && dbl(st, 0) <= 0.0;  // :339-343
   }
-  __device__ static bool truncated(const Ctx&, const int*) { return false; }
+  template <class C>
+  __device__ static bool truncated(const C&, const int*) { return false; }
 
-  __device__ static void reset_agent(const Ctx& c, int* st) {
+  template <class C>
+  __device__ static void reset_agent(const C& c, int* st) {
 #pragma unroll
     for (int w = 0; w < NWORDS; ++w) st[w] = 0;
     if (c.kind != DA_ADVERTISER) return;
     // Agent.reset: type = supertype.sample() -> the env-managed sampler's value of this episode
     // (env.py:212-216; samplers.py:142-147: np.random.uniform, then np.clip)
-    const EngineSpec& sp = *c.spec;
+    const auto& sp = *c.spec;
     const int idx = sp.agent_iparam[c.slot][0];
     double budget = sp.agent_fparam[c.slot][0];
     if (idx >= 0) {
@@ -227,7 +261,7 @@ struct DigitalAdsProgram {
 }  // namespace
 
 #ifndef PHX_JIT_TU
-Family* make_digital_ads_family(const phx_spec&) { return new EngineFamily<DigitalAdsProgram>(); }
+Family* make_digital_ads_family(const phx_spec& s) { return make_engine_family<DigitalAdsProgram>(s); }
 #endif
 
 }  // namespace phx

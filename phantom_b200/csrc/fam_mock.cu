@@ -21,6 +21,9 @@
 //                3 messages handled, 4 sum of handled payload values
 // agent_iparam[slot] = {agent.num_steps or -1, echo seed value, echo mode (0 halve/1 req-resp)}
 #include "phx_engine_host.cuh"
+#ifndef PHX_JIT_TU
+#include "phx_engine_wide_host.cuh"
+#endif
 
 namespace phx {
 namespace {
@@ -51,9 +54,12 @@ struct MockProgram {
     return PHX_OK;
   }
 
-  template <class E>
-  __device__ static void act(const Ctx& c, int* st, bool has_action, const float*, E& out) {
-    const EngineSpec& sp = *c.spec;
+  // (every callback is a template over the context type: the same text runs on the warp-tile
+  // engines (Ctx) and on the 128-lane block engine (WCtx, phx_engine_wide.cuh))
+  static constexpr bool WIDE_OK = true;
+  template <class C, class E>
+  __device__ static void act(const C& c, int* st, bool has_action, const float*, E& out) {
+    const auto& sp = *c.spec;
     if (c.kind == MK_STRATEGIC || c.kind == MK_CODEC) {
       if (has_action) st[1] += 1;  // decode_action_count; EmptyDecoder compositions return []
       return;
@@ -62,16 +68,19 @@ struct MockProgram {
       const int seed = sp.agent_iparam[c.slot][1];
       if (seed <= 0) return;
       const int type = sp.agent_iparam[c.slot][2] ? MK_REQUEST : MK_TEST_MESSAGE;
-      for (uint32_t m = c.out_mask & ~((2u << c.slot) - 1u); m; m &= m - 1)
-        out.send(__ffs(m) - 1, type, seed);
+      for (int r = c.next_neighbour(c.slot); r >= 0; r = c.next_neighbour(r))
+        out.send(r, type, seed);
     }
   }
-  __device__ static void view(const Ctx&, const int*, int*) {}
-  __device__ static void pre(const Ctx&, int*) {}
-  __device__ static void post(const Ctx&, int*) {}
+  template <class C>
+  __device__ static void view(const C&, const int*, int*) {}
+  template <class C>
+  __device__ static void pre(const C&, int*) {}
+  template <class C>
+  __device__ static void post(const C&, int*) {}
 
-  template <class E>
-  __device__ static bool handle(const Ctx& c, int* st, const Msg& m, E& out) {
+  template <class C, class E>
+  __device__ static bool handle(const C& c, int* st, const Msg& m, E& out) {
     if (c.kind != MK_ECHO) return false;  // no handler registered: ValueError (agents.py:140)
     st[3] += 1;
     st[4] += m.p[0];
@@ -86,7 +95,8 @@ struct MockProgram {
     return m.type == MK_RESPONSE;  // test_resolver.py:39-45: returns []
   }
 
-  __device__ static bool encode(const Ctx& c, int* st, float* obs) {
+  template <class C>
+  __device__ static bool encode(const C& c, int* st, float* obs) {
     if (c.kind == MK_STRATEGIC) {
       st[0] += 1;
       obs[0] = c.proportion_time_elapsed();
@@ -106,23 +116,27 @@ struct MockProgram {
     }
     return true;
   }
-  __device__ static float reward(const Ctx& c, int* st) {
+  template <class C>
+  __device__ static float reward(const C& c, int* st) {
     st[2] += 1;
     return c.kind == MK_CODEC ? (float)c.spec->agent_fparam[c.slot][0] : 0.0f;  // Constant(value)
   }
-  __device__ static bool terminated(const Ctx& c, const int*) {
+  template <class C>
+  __device__ static bool terminated(const C& c, const int*) {
     return c.step == c.spec->agent_iparam[c.slot][0];
   }
-  __device__ static bool truncated(const Ctx& c, const int*) {
+  template <class C>
+  __device__ static bool truncated(const C& c, const int*) {
     return c.step == c.spec->agent_iparam[c.slot][0];
   }
-  __device__ static void reset_agent(const Ctx&, int*) {}  // call counters survive resets
+  template <class C>
+  __device__ static void reset_agent(const C&, int*) {}  // call counters survive resets
 };
 
 }  // namespace
 
 #ifndef PHX_JIT_TU  // a specialised translation unit only needs the program above
-Family* make_mock_family(const phx_spec&) { return new EngineFamily<MockProgram>(); }
+Family* make_mock_family(const phx_spec& s) { return make_engine_family<MockProgram>(s); }
 #endif
 
 }  // namespace phx

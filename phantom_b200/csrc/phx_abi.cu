@@ -293,8 +293,8 @@ static int32_t check_spec(const phx_spec* s) {
                 "initial_stage out of range");
   }
   if (s->flags & PHX_FLAG_STOCHASTIC_NETWORK) {
-    PHX_REQUIRE(s->n_agents <= 32, PHX_ERR_UNSUPPORTED,
-                "StochasticNetwork is implemented by the queue engine: at most 32 agents per env");
+    // (33..128 agents: the block engine, for the families that run on it -- the tile engine
+    // refuses wider specs itself)
     PHX_REQUIRE(s->n_base_connections >= 0 && s->n_base_connections <= PHX_MAX_BASE_CONNECTIONS,
                 PHX_ERR_INVALID, "n_base_connections out of range");
   }

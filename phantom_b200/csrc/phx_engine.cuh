@@ -59,33 +59,41 @@ struct EnvWords<P, std::void_t<decltype(P::ENVW)>> {
 constexpr int ENGINE_BLOCK = 128;
 constexpr int ENGINE_MAX_AGENTS = 32;
 
-// Generic part of phx_spec in kernel-parameter (constant bank) form.
-struct EngineSpec {
+// Generic part of phx_spec in device form.  One definition for both widths of an env tile:
+//   EngineSpec  <= 32 agents, a mask over slots is ONE word; passed as a kernel parameter
+//               (constant bank) or, in a specialised build, a compile-time constant
+//   WideSpec    <= 128 agents, masks of PHX_MASK_WORDS words; lives in global memory
+//               (phx_engine_wide.cuh)
+struct WMask {
+  uint32_t w[PHX_MASK_WORDS];
+};
+template <int MAXA, class M>
+struct EngineSpecT {
   int32_t E, n_agents, n_strategic, num_steps, round_limit, env_kind;
   uint32_t flags;
   int32_t obs_dim, act_dim;
-  int8_t kind[ENGINE_MAX_AGENTS];
-  int8_t sidx[ENGINE_MAX_AGENTS];      // strategic index or -1
-  uint32_t adj[ENGINE_MAX_AGENTS];     // bit r of adj[s]: edge s -> r
-  uint32_t sender_ok[PHX_MAX_TYPES];   // bit s: slot s may send this payload type
-  uint32_t receiver_ok[PHX_MAX_TYPES];
-  uint32_t strategic_mask;             // over slots
-  uint32_t kind_mask[8];               // slots of each agent kind
+  int8_t kind[MAXA];
+  int8_t sidx[MAXA];            // strategic index or -1
+  M adj[MAXA];                  // bit r of adj[s]: edge s -> r
+  M sender_ok[PHX_MAX_TYPES];   // bit s: slot s may send this payload type
+  M receiver_ok[PHX_MAX_TYPES];
+  M strategic_mask;             // over slots
+  M kind_mask[8];               // slots of each agent kind
   int32_t n_stages, initial_stage;
-  uint32_t stage_acting[PHX_MAX_STAGES];
-  uint32_t stage_rewarded[PHX_MAX_STAGES];
+  M stage_acting[PHX_MAX_STAGES];
+  M stage_rewarded[PHX_MAX_STAGES];
   uint8_t stage_rewarded_none[PHX_MAX_STAGES];
   int8_t stage_next[PHX_MAX_STAGES];
-  uint32_t leaders, followers;         // over slots
+  M leaders, followers;         // over slots
   uint64_t seed;
   uint32_t env_offset;
   int32_t iparams[PHX_MAX_PARAMS];
   float fparams[PHX_MAX_PARAMS];
   double dparams[4];                   // family parameters that must stay float64
-  int32_t agent_iparam[ENGINE_MAX_AGENTS][4];
-  double agent_fparam[ENGINE_MAX_AGENTS][4];
-  int32_t codec_op[ENGINE_MAX_AGENTS][PHX_MAX_CODEC_OPS];  // opcode | length << 8
-  float codec_val[ENGINE_MAX_AGENTS][PHX_MAX_CODEC_OPS];
+  int32_t agent_iparam[MAXA][4];
+  double agent_fparam[MAXA][4];
+  int32_t codec_op[MAXA][PHX_MAX_CODEC_OPS];  // opcode | length << 8
+  float codec_val[MAXA][PHX_MAX_CODEC_OPS];
   // device form of the stages' env handlers (fsm.py:294-307; include/phx.h phx_stage.rule_*):
   // an if / elif / else chain, each branch a conjunction of comparisons between two operands
   int8_t stage_rule[PHX_MAX_STAGES][4];  // {handler, resolves, n_branches, else}
@@ -94,6 +102,8 @@ struct EngineSpec {
   int32_t rule_rhs[PHX_MAX_STAGES][PHX_RULE_BRANCHES][PHX_RULE_TERMS];         // PHX_RULE_CONST
   uint8_t stage_allowed[PHX_MAX_STAGES];  // FSMStage.next_stages as a stage bitmask
 };
+using EngineSpec = EngineSpecT<ENGINE_MAX_AGENTS, uint32_t>;
+using WideSpec = EngineSpecT<PHX_MAX_AGENTS, WMask>;
 
 enum { SR_HANDLER = 0, SR_RESOLVES, SR_BRANCHES, SR_ELSE };
 enum { RT_LHS = 0, RT_SLOT, RT_WORD, RT_CMP, RT_RHS, RT_RHS_SLOT, RT_RHS_WORD };
@@ -118,8 +128,8 @@ __device__ __forceinline__ bool rule_compare(int cmp, int lhs, int rhs) {
 #else
 #define PHX_RULE_UNROLL _Pragma("unroll 1")
 #endif
-template <class Operand>
-__device__ __forceinline__ int stage_rule_pick(const EngineSpec& sp, int stage, Operand&& operand) {
+template <class Spec, class Operand>
+__device__ __forceinline__ int stage_rule_pick(const Spec& sp, int stage, Operand&& operand) {
   const int nb = sp.stage_rule[stage][SR_BRANCHES];
   PHX_RULE_UNROLL
   for (int b = 0; b < PHX_RULE_BRANCHES; ++b) {
@@ -245,6 +255,22 @@ struct Ctx {
   __device__ __forceinline__ int iparam0_of(int other_slot) const { return ip0_tab[other_slot]; }
   __device__ __forceinline__ uint32_t rand24_hi(uint32_t stream, uint32_t idx) const {
     return rng_d24_hi(spec->seed, env_id, episode, (uint32_t)step, stream, idx);
+  }
+  // Width-independent iteration (the same program text runs on the 128-lane block engine, whose
+  // masks are PHX_MASK_WORDS words -- phx_engine_wide.cuh WCtx):
+  //     for (int r = c.next_neighbour(-1); r >= 0; r = c.next_neighbour(r)) ...
+  static constexpr int MASK_WORDS = 1;
+  __device__ __forceinline__ static int next_bit(uint32_t m, int after) {
+    m = after >= 31 ? 0u : (m & ~((2u << after) - 1u));  // after == -1: (2u << -1) is avoided below
+    return m ? __ffs(m) - 1 : -1;
+  }
+  __device__ __forceinline__ int next_neighbour(int after) const {
+    return after < 0 ? (out_mask ? __ffs(out_mask) - 1 : -1) : next_bit(out_mask, after);
+  }
+  // agents of a kind in the env class (whether connected or not), in slot order
+  __device__ __forceinline__ int next_of_kind(int k, int after) const {
+    const uint32_t m = spec->kind_mask[k];
+    return after < 0 ? (m ? __ffs(m) - 1 : -1) : next_bit(m, after);
   }
 };
 

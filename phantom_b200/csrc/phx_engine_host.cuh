@@ -17,12 +17,23 @@ namespace phx {
 
 inline uint32_t low_mask(const uint32_t* words) { return words[0]; }
 
-// Lowers the generic part of phx_spec into the engine's kernel-parameter form.
+inline void mask_from(uint32_t& d, const uint32_t* src) { d = src[0]; }
+inline void mask_from(WMask& d, const uint32_t* src) {
+  for (int k = 0; k < PHX_MASK_WORDS; ++k) d.w[k] = src[k];
+}
+inline void mask_set(uint32_t& d, int i) { d |= 1u << i; }
+inline void mask_set(WMask& d, int i) { d.w[i >> 5] |= 1u << (i & 31); }
+
+// Lowers the generic part of phx_spec into the engines' device form (EngineSpec / WideSpec).
+template <class Spec>
 inline int32_t make_engine_spec(const phx_spec& s, int32_t E, uint64_t seed, int64_t env_offset,
-                                EngineSpec* out, int nwords, int envwords) {
-  PHX_REQUIRE(s.n_agents <= ENGINE_MAX_AGENTS, PHX_ERR_UNSUPPORTED,
-              "queue engine (tile variant) supports up to 32 agents per env");
-  EngineSpec& d = *out;
+                                Spec* out, int nwords, int envwords) {
+  constexpr int MAXA = (int)(sizeof(out->kind) / sizeof(out->kind[0]));
+  PHX_REQUIRE(s.n_agents <= MAXA, PHX_ERR_UNSUPPORTED,
+              MAXA <= ENGINE_MAX_AGENTS
+                  ? "queue engine (tile variant) supports up to 32 agents per env"
+                  : "queue engine (block variant) supports up to 128 agents per env");
+  Spec& d = *out;
   std::memset(&d, 0, sizeof(d));
   d.E = E;
   d.n_agents = s.n_agents;
@@ -36,9 +47,9 @@ inline int32_t make_engine_spec(const phx_spec& s, int32_t E, uint64_t seed, int
   for (int i = 0; i < s.n_agents; ++i) {
     d.kind[i] = (int8_t)s.agent_kind[i];
     d.sidx[i] = (int8_t)s.strategic_index[i];
-    d.adj[i] = s.adjacency[i][0];
-    if (s.strategic_index[i] >= 0) d.strategic_mask |= 1u << i;
-    if (s.agent_kind[i] >= 0 && s.agent_kind[i] < 8) d.kind_mask[s.agent_kind[i]] |= 1u << i;
+    mask_from(d.adj[i], s.adjacency[i]);
+    if (s.strategic_index[i] >= 0) mask_set(d.strategic_mask, i);
+    if (s.agent_kind[i] >= 0 && s.agent_kind[i] < 8) mask_set(d.kind_mask[s.agent_kind[i]], i);
     for (int k = 0; k < 4; ++k) d.agent_iparam[i][k] = s.agent_iparam[i][k];
     for (int k = 0; k < 4; ++k) d.agent_fparam[i][k] = s.agent_fparam[i][k];
     for (int k = 0; k < PHX_MAX_CODEC_OPS; ++k) {
@@ -47,14 +58,14 @@ inline int32_t make_engine_spec(const phx_spec& s, int32_t E, uint64_t seed, int
     }
   }
   for (int t = 0; t < s.n_payload_types; ++t) {
-    d.sender_ok[t] = s.type_sender_ok[t][0];
-    d.receiver_ok[t] = s.type_receiver_ok[t][0];
+    mask_from(d.sender_ok[t], s.type_sender_ok[t]);
+    mask_from(d.receiver_ok[t], s.type_receiver_ok[t]);
   }
   d.n_stages = s.n_stages;
   d.initial_stage = s.env_kind == PHX_ENV_FSM ? s.initial_stage : 0;
   for (int k = 0; k < s.n_stages && k < PHX_MAX_STAGES; ++k) {
-    d.stage_acting[k] = s.stages[k].acting[0];
-    d.stage_rewarded[k] = s.stages[k].rewarded[0];
+    mask_from(d.stage_acting[k], s.stages[k].acting);
+    mask_from(d.stage_rewarded[k], s.stages[k].rewarded);
     d.stage_rewarded_none[k] = (uint8_t)(s.stages[k].rewarded_is_none != 0);
     const phx_stage& g = s.stages[k];
     d.stage_allowed[k] = (uint8_t)(g.next_allowed & 0xFFu);
@@ -132,8 +143,8 @@ inline int32_t make_engine_spec(const phx_spec& s, int32_t E, uint64_t seed, int
       }
     }
   }
-  d.leaders = s.leaders[0];
-  d.followers = s.followers[0];
+  mask_from(d.leaders, s.leaders);
+  mask_from(d.followers, s.followers);
   d.seed = seed;
   d.env_offset = (uint32_t)env_offset;
   for (int k = 0; k < PHX_MAX_PARAMS; ++k) {

@@ -378,8 +378,14 @@ class PhantomEnv:
     def adjacency(self) -> np.ndarray:
         """Per-env graphs of a StochasticNetwork: uint8 [E, n_agents, n_agents], entry [e, s, r]
         = 1 iff env e currently has the edge s -> r (network.py:439-448 run per env)."""
-        rows = self.field(L.FIELD_ADJACENCY, np.uint32, width=self.tile_width)
         n = self.spec.n_agents
+        if self.exec_name.startswith("wide"):  # block engine: rows of PHX_MASK_WORDS words
+            W = L.PHX_MASK_WORDS
+            rows = self.field(L.FIELD_ADJACENCY, np.uint32, width=self.tile_width * W)
+            rows = rows.reshape(rows.shape[0], self.tile_width, W)[:, :n]
+            r = np.arange(n)
+            return ((rows[:, :, r >> 5] >> (r & 31).astype(np.uint32)[None, None, :]) & 1).astype(np.uint8)
+        rows = self.field(L.FIELD_ADJACENCY, np.uint32, width=self.tile_width)
         return ((rows[:, :n, None] >> np.arange(n, dtype=np.uint32)[None, None, :]) & 1).astype(np.uint8)
 
     def agent_column(self, agent: Agent, word: int, dtype=np.int32) -> np.ndarray:
@@ -523,11 +529,17 @@ class PhantomEnv:
 
     def is_terminated(self) -> bool:
         self._require_single("is_terminated")
-        term = self.field(L.FIELD_TERMINATED, np.uint32, width=1)
-        return bin(int(term[0])).count("1") == len(self.strategic_agents)
+        term = self.field(L.FIELD_TERMINATED, np.uint32, width=self._done_words)
+        return sum(bin(int(w)).count("1") for w in np.atleast_1d(term[0])) == len(self.strategic_agents)
 
     def is_truncated(self) -> bool:
         self._require_single("is_truncated")
-        trunc = self.field(L.FIELD_TRUNCATED, np.uint32, width=1)
+        trunc = self.field(L.FIELD_TRUNCATED, np.uint32, width=self._done_words)
         at_max = self.num_steps is not None and self.current_step == self.num_steps
-        return at_max or bin(int(trunc[0])).count("1") == len(self.strategic_agents)
+        return at_max or sum(bin(int(w)).count("1") for w in np.atleast_1d(trunc[0])) == len(self.strategic_agents)
+
+    @property
+    def _done_words(self) -> int:
+        """Words per env of the done sets: one (bitmask over <= 32 slots), PHX_MASK_WORDS on the
+        128-lane block engine."""
+        return L.PHX_MASK_WORDS if self.exec_name.startswith("wide") else 1

@@ -214,8 +214,8 @@ def lower(env, exec_mode: str = "auto", auto_reset: bool = False) -> L.PhxSpec:
         if len(base) > L.PHX_MAX_BASE_CONNECTIONS:
             raise NotLowerableError(
                 f"more than {L.PHX_MAX_BASE_CONNECTIONS} StochasticNetwork base connections")
-        if len(agents) > 32:
-            raise NotLowerableError("StochasticNetwork lowers to the queue engine: <= 32 agents")
+        if len(agents) > L.PHX_MAX_AGENTS:
+            raise NotLowerableError(f"StochasticNetwork: at most {L.PHX_MAX_AGENTS} agents per env")
         flags |= L.FLAG_STOCHASTIC_NETWORK
         spec.n_base_connections = len(base)
         for c, (u, v, rate) in enumerate(base):

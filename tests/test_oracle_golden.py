@@ -369,7 +369,8 @@ def test_object_oracle_matches_simple_market_handler_golden(golden_dir):
     assert (sellers_next[:, :, :-1] & sellers_next[:, :, 1:]).any()
 
 
-@pytest.mark.parametrize("name", ["digital_ads_reference.npz", "digital_ads_wide_reference.npz"])
+@pytest.mark.parametrize("name", ["digital_ads_reference.npz", "digital_ads_wide_reference.npz",
+                                  "digital_ads_full_reference.npz"])
 def test_oracle_port_runs_the_digital_ads_example(golden_dir, name):
     """The UNMODIFIED example file executed on the oracle port (its `import phantom` bound to
     oracle.phantom_oracle) reproduces the fixture the same file produced on the reference: pins
