@@ -263,17 +263,27 @@ def gen_shuffle_and_stochastic_reference() -> None:
 SIMPLE_MARKET_WIDE_BUYERS = ((0.3, 0.1, 0.9), (0.8, 0.5, 1.0), (0.6, 0.0, 1.0), (0.5, 0.25, 0.25))
 
 
-def gen_simple_market_reference() -> None:
+def gen_simple_market_reference(only=slice(None)) -> None:
     """The reference's own examples/environments/simple_market modules, UNMODIFIED (imported by
     oracle/workloads/simple_market.py:build_reference), under the contract RNG:
       simple_market_reference.npz       the example script's cast: 3 buyers + 2 sellers, 10 steps
       simple_market_wide_reference.npz  4 buyers with non-degenerate type samplers + 3 sellers
-                                        (np.mean over three prices), 12 steps"""
+                                        (np.mean over three prices), 12 steps
+      simple_market_9s_reference.npz    3 buyers + 9 sellers: np.mean enters numpy's pairwise
+                                        summation (8 accumulators) -- 12 agents, 16-lane tiles
+      simple_market_block_reference.npz 28 buyers + 12 sellers = 40 agents: the 128-lane block
+                                        engine; pairwise sum of 8 + 3 leftover prices"""
     from .workloads import simple_market as wl
 
+    rb = np.random.RandomState(20261029)
+    block_buyers = tuple((float(np.round(p, 3)), float(np.round(lo, 3)), float(np.round(lo + w, 3)))
+                         for p, lo, w in zip(rb.uniform(0.2, 0.9, 28), rb.uniform(0.0, 0.6, 28),
+                                             rb.uniform(0.0, 0.4, 28)))
     for name, buyers, n_sellers, T, n_env, n_ep, seed in (
             ("simple_market_reference.npz", wl.EXAMPLE_BUYERS, wl.EXAMPLE_SELLERS, 10, 8, 3, 20261024),
-            ("simple_market_wide_reference.npz", SIMPLE_MARKET_WIDE_BUYERS, 3, 12, 6, 2, 20261025)):
+            ("simple_market_wide_reference.npz", SIMPLE_MARKET_WIDE_BUYERS, 3, 12, 6, 2, 20261025),
+            ("simple_market_9s_reference.npz", SIMPLE_MARKET_WIDE_BUYERS[:3], 9, 10, 4, 2, 20261030),
+            ("simple_market_block_reference.npz", block_buyers, 12, 8, 3, 2, 20261031))[only]:
         actions, mask = wl.actions_for(n_env, n_ep, T, len(buyers), n_sellers, seed % 1000)
         per_env = []
         for e in range(n_env):

@@ -17,8 +17,10 @@
 // A program takes part by being a template over its context type (fam_mock.cu,
 // fam_digital_ads.cu: `template <class C> ... const C& c`) and never touching a raw mask:
 // WCtx offers has_neighbour / next_neighbour / next_of_kind like Ctx does.
-// Not carried over (loud PHX_ERR_UNSUPPORTED at create): env-level words (ENVW), the collective
-// resolve hook, shuffle_batches, run-time specialisation.
+// Env-level words (ENVW / env_post, see phx_engine.cuh) are kept by every lane; env_post reads
+// other agents' state through a copy of all state words in shared memory.
+// Not carried over (loud PHX_ERR_UNSUPPORTED at create): the collective resolve hook,
+// shuffle_batches, run-time specialisation.
 #pragma once
 #include "phx_engine.cuh"
 
@@ -180,6 +182,7 @@ struct WideArgs {
   uint32_t* reward_none; // [E][4]
   float* obs_cache;      // [E][G][O]
   uint32_t* obs_cached;  // [E][4]
+  int32_t* env_state;    // [ENVW][E] env-level words of the program (nullptr if ENVW == 0)
   uint32_t* adj_env;     // [E][G][4] StochasticNetwork: per-env adjacency rows (else nullptr)
   const uint2* base_conn;
   int32_t n_base;
@@ -203,6 +206,8 @@ struct WideSmem {
   int32_t red[WIDE_MW];
   uint32_t redu[WIDE_MW];
   int32_t bcast;
+  // programs with env-level words: every agent's state, published before env_post
+  int32_t pub[EnvWords<P>::value > 0 ? (P::NWORDS > 0 ? P::NWORDS : 1) : 1][EnvWords<P>::value > 0 ? WIDE_G : 1];
 };
 
 __device__ __forceinline__ int wide_sum(int v, int32_t* red) {
@@ -414,13 +419,19 @@ __global__ void __launch_bounds__(WIDE_G) wide_step_kernel(const WideArgs<P> a) 
   for (int w = 0; w < P::NWORDS; ++w) st[w] = a.state[((size_t)w * sp.E + e) * WIDE_G + slot];
   float rcache = cached_env ? a.reward_cache[(size_t)e * WIDE_G + slot] : 0.f;
   uint32_t fault_key = 0xFFFFFFFFu;  // (phase << 16 | slot << 8 | code), smallest wins
-  int envdummy[1] = {0};
+  // env-level words: every lane keeps the same copy
+  constexpr int EW = EnvWords<P>::value;
+  int envw[EW > 0 ? EW : 1] = {0}, envsnap[EW > 0 ? EW : 1] = {0};
+  if constexpr (EW > 0) {
+#pragma unroll
+    for (int w = 0; w < EW; ++w) envw[w] = a.env_state[(size_t)w * sp.E + e];
+  }
 
   WCtx ctx;
   ctx.spec = &sp;
   ctx.slot = slot;
   ctx.kind = kind;
-  ctx.env = envdummy;
+  ctx.env = envsnap;
   ctx.env_id = sp.env_offset + (uint32_t)e;
   ctx.views = &sm.views[0][0];
   ctx.view_stride = P::VW > 0 ? P::VW : 1;
@@ -445,6 +456,10 @@ __global__ void __launch_bounds__(WIDE_G) wide_step_kernel(const WideArgs<P> a) 
     ctx.stage = h.z;
     const bool was_done = is_agent && (wbit(sm.term, slot) || wbit(sm.trunc, slot));
     const bool has_ctx = is_agent && !was_done;  // env.py:344-348: no context for done agents
+    if constexpr (EW > 0) {  // the EnvView of this step (env.py:340)
+#pragma unroll
+      for (int w = 0; w < EW; ++w) envsnap[w] = envw[w];
+    }
 
     if (P::VW > 0) {  // start-of-step snapshot of every agent's public state
       if (is_agent) P::view(ctx, st, &sm.views[slot][0]);
@@ -515,12 +530,30 @@ __global__ void __launch_bounds__(WIDE_G) wide_step_kernel(const WideArgs<P> a) 
     if (trace_lane) a.trace.cnt[row] = traced;
 
     if (has_ctx && resolves) P::post(ctx, st);  // env.py:175-178
+    if constexpr (EW > 0) {  // the env class's own post_message_resolution override
+      if (resolves) {        // (uniform over the block: the stage is an env-level word)
+#pragma unroll
+        for (int w = 0; w < P::NWORDS; ++w) sm.pub[w][slot] = st[w];
+        __syncthreads();
+        P::env_post(ctx, envw, [&](int s_, auto w_) { return sm.pub[decltype(w_)::value][s_]; });
+        __syncthreads();
+      }
+    }
 
     // ---- the stage's env handler picks the next stage (fsm.py:294-307)
     if (handled) {
       next_stage = stage_rule_pick(sp, h.z, [&](int okind, int rs, int rw, int constant) {
         if (okind == PHX_RULE_STEP) return (int)h.x;
-        if (okind != PHX_RULE_AGENT_WORD) return constant;  // (no env-level words on this engine)
+        if (okind == PHX_RULE_ENV_WORD) {
+          int v = constant;
+          if constexpr (EW > 0) {
+#pragma unroll
+            for (int w = 0; w < EW; ++w)
+              if (w == rw) v = envw[w];
+          }
+          return v;
+        }
+        if (okind != PHX_RULE_AGENT_WORD) return constant;
         if (slot == rs) {
           int mine = 0;
 #pragma unroll
@@ -657,6 +690,10 @@ __global__ void __launch_bounds__(WIDE_G) wide_step_kernel(const WideArgs<P> a) 
       }
       if (is_agent) P::reset_agent(ctx, st);
       __syncthreads();
+      if constexpr (EW > 0) {  // reset() builds a fresh EnvView (fsm.py:232-236)
+#pragma unroll
+        for (int w = 0; w < EW; ++w) envsnap[w] = envw[w];
+      }
       if (P::VW > 0) {
         if (is_agent) P::view(ctx, st, &sm.views[slot][0]);
         __syncthreads();
@@ -680,7 +717,13 @@ __global__ void __launch_bounds__(WIDE_G) wide_step_kernel(const WideArgs<P> a) 
 
   // ---- write back
   __syncthreads();
-  if (slot == 0) a.hdr[e] = h;
+  if (slot == 0) {
+    a.hdr[e] = h;
+    if constexpr (EW > 0) {
+#pragma unroll
+      for (int w = 0; w < EW; ++w) a.env_state[(size_t)w * sp.E + e] = envw[w];
+    }
+  }
   if (slot < WIDE_MW) {
     a.term[(size_t)e * WIDE_MW + slot] = sm.term[slot];
     a.trunc[(size_t)e * WIDE_MW + slot] = sm.trunc[slot];
@@ -723,12 +766,17 @@ wide_reset_kernel(const WideArgs<P> a, const uint8_t* env_mask, float* obs, uint
   h.x = 0;
   h.y += 1;
   h.z = sp.env_kind == PHX_ENV_FSM ? sp.initial_stage : 0;
-  int envdummy[1] = {0};
+  constexpr int EW = EnvWords<P>::value;
+  int envw[EW > 0 ? EW : 1] = {0};  // env-level words survive a reset unless the program says otherwise
+  if constexpr (EW > 0) {
+#pragma unroll
+    for (int w = 0; w < EW; ++w) envw[w] = a.env_state[(size_t)w * sp.E + e];
+  }
   WCtx ctx;
   ctx.spec = &sp;
   ctx.slot = slot;
   ctx.kind = is_agent ? sp.kind[slot] : -1;
-  ctx.env = envdummy;
+  ctx.env = envw;
   ctx.step = 0;
   ctx.stage = h.z;
   ctx.env_id = sp.env_offset + (uint32_t)e;

@@ -18,7 +18,6 @@ static __global__ void wide_init_kernel(int E, int4* hdr) {
 template <class P>
 class WideFamily : public Family {
  public:
-  static_assert(EnvWords<P>::value == 0, "the block engine has no env-level words yet");
   ~WideFamily() override {
     cudaFree(d_spec);
     cudaFree(d_state);
@@ -28,12 +27,13 @@ class WideFamily : public Family {
     cudaFree(d_ocached);
     cudaFree(d_adj);
     cudaFree(d_base);
+    cudaFree(d_env);
   }
 
   int32_t init(const phx_spec& s) override {
     PHX_REQUIRE(!(s.flags & PHX_FLAG_SHUFFLE_BATCHES), PHX_ERR_UNSUPPORTED,
                 "shuffle_batches is not available on the 128-lane block engine");
-    int32_t rc = make_engine_spec(s, E, seed, env_offset, &wspec, P::NWORDS, 0);
+    int32_t rc = make_engine_spec(s, E, seed, env_offset, &wspec, P::NWORDS, EnvWords<P>::value);
     if (rc != PHX_OK) return rc;
     rc = P::validate(s);
     if (rc != PHX_OK) return rc;
@@ -83,6 +83,10 @@ class WideFamily : public Family {
         PHX_CUDA(cudaMemset(d_ocached, 0, mw));
       }
     }
+    if (EnvWords<P>::value > 0) {  // env-level words start at zero (e.g. avg_price = 0.0)
+      PHX_CUDA(cudaMalloc(&d_env, sizeof(int32_t) * (size_t)E * EnvWords<P>::value));
+      PHX_CUDA(cudaMemset(d_env, 0, sizeof(int32_t) * (size_t)E * EnvWords<P>::value));
+    }
     if (s.flags & PHX_FLAG_STOCHASTIC_NETWORK) {
       PHX_REQUIRE(s.n_base_connections >= 0 && s.n_base_connections <= PHX_MAX_BASE_CONNECTIONS,
                   PHX_ERR_INVALID, "n_base_connections out of range");
@@ -131,6 +135,7 @@ class WideFamily : public Family {
     a.reward_none = d_rnone;
     a.obs_cache = d_ocache;
     a.obs_cached = d_ocached;
+    a.env_state = d_env;
     a.adj_env = d_adj;
     a.base_conn = d_base;
     a.n_base = n_base;
@@ -169,7 +174,13 @@ class WideFamily : public Family {
   }
 
   int32_t family_field(int32_t field, int32_t index, void** p, size_t* bytes) override {
-    (void)index;
+    if (field == PHX_FIELD_ENV_STATE) {  // int32 [E]: env-level word `index`
+      PHX_REQUIRE(index >= 0 && index < EnvWords<P>::value, PHX_ERR_INVALID,
+                  "PHX_FIELD_ENV_STATE: this env class has no such env-level word");
+      *p = d_env + (size_t)index * E;
+      *bytes = sizeof(int32_t) * (size_t)E;
+      return PHX_OK;
+    }
     if (field == PHX_FIELD_ADJACENCY) {  // uint32 [E, 128, 4]
       PHX_REQUIRE(d_adj != nullptr, PHX_ERR_INVALID,
                   "PHX_FIELD_ADJACENCY needs PHX_FLAG_STOCHASTIC_NETWORK");
@@ -200,6 +211,7 @@ class WideFamily : public Family {
   uint32_t* d_ocached = nullptr;
   uint32_t* d_adj = nullptr;
   uint2* d_base = nullptr;
+  int32_t* d_env = nullptr;  // [ENVW][E]
   int32_t n_base = 0;
   std::string name = "wide(G=128)";
 };

@@ -21,7 +21,16 @@ from phantom_b200.spaces import Box, Discrete
 from phantom_b200.utils.samplers import KIND_UNIFORM_FLOAT, Sampler
 
 KIND_BUYER, KIND_SELLER = 0, 1
-MAX_SELLERS = 7
+MAX_SELLERS = 15
+
+
+def buyer_layout(n_sellers: int):
+    """State-word layout of a buyer (csrc/fam_simple_market.cu SimpleMarketProgramT<MAXS>): the
+    device program is built for MAXS = 7 remembered sellers (19 words) or 15 (36 words).
+    -> (word of the dict order, words it takes, word of current_reward, word of type.value)"""
+    maxs = 7 if n_sellers <= 7 else 15
+    w_ord, ow = 2 * maxs, (1 if maxs == 7 else 2)
+    return w_ord, ow, w_ord + ow, w_ord + ow + 2
 
 
 @ph.msg_payload()
@@ -68,13 +77,22 @@ class BuyerAgent(ph.StrategicAgent):
         self.action_space = Discrete(2)
         self.observation_space = Box(low=0, high=1, shape=(3,))
 
+    def _layout(self):
+        return buyer_layout(int(self._phx_env.spec.iparams[0]))
+
     @property
     def current_reward(self):
-        return _f64_column(self._phx_env, self, 15)
+        return _f64_column(self._phx_env, self, self._layout()[2])
 
     @property
     def type(self):
-        return BuyerSupertype(value=_f64_column(self._phx_env, self, 17))
+        return BuyerSupertype(value=_f64_column(self._phx_env, self, self._layout()[3]))
+
+    @property
+    def n_sellers_heard(self):
+        """len(self.seller_prices): the top nibble of the dict-order words."""
+        w_ord, ow, _, _ = self._layout()
+        return (self._phx_env.agent_column(self, w_ord + ow - 1).astype(np.uint32) >> 28).astype(np.int64)
 
 
 class SellerAgent(ph.StrategicAgent):
@@ -107,7 +125,7 @@ def _collect(env, agents, spec) -> None:
     buyers = [a for a in agents if isinstance(a, BuyerAgent)]
     sellers = [a for a in agents if isinstance(a, SellerAgent)]
     if not buyers or not 1 <= len(sellers) <= MAX_SELLERS:
-        raise NotLowerableError("simple-market device program: >= 1 buyer and 1..7 sellers")
+        raise NotLowerableError("simple-market device program: >= 1 buyer and 1..15 sellers")
     if not isinstance(env, SimpleMarketEnv):
         raise NotLowerableError("simple-market agents run under SimpleMarketEnv")
     first = env._stages[env.initial_stage].acting_agents

@@ -306,7 +306,9 @@ def test_object_oracle_matches_stochastic_network_golden(golden_dir):
             assert np.array_equal(want, g["adjacency"][e, ep]), (e, ep)
 
 
-@pytest.mark.parametrize("name", ["simple_market_reference.npz", "simple_market_wide_reference.npz"])
+@pytest.mark.parametrize("name", ["simple_market_reference.npz", "simple_market_wide_reference.npz",
+                                  "simple_market_9s_reference.npz",
+                                  "simple_market_block_reference.npz"])
 def test_object_oracle_matches_simple_market_golden(golden_dir, name):
     """The reference's own simple_market example (env-level post_message_resolution + custom
     EnvView field, two-stage FSM, three RNG call sites): oracle restatement == the unmodified
