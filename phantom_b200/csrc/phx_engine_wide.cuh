@@ -22,6 +22,8 @@
 // Not carried over (loud PHX_ERR_UNSUPPORTED at create): the collective resolve hook,
 // shuffle_batches, run-time specialisation.
 #pragma once
+#include <cstddef>
+
 #include "phx_engine.cuh"
 
 namespace phx {
@@ -80,25 +82,41 @@ struct WCtx {
   }
 };
 
-// Segmented queue of the env in shared memory; storage and capacities are set at launch.
+// The block's dynamic shared memory (WideSmem<P>, then the queue storage).  Declared at namespace
+// scope so that every queue access is derived from a __shared__ symbol and compiles to LDS / STS
+// (pointers kept in a struct that is indexed at run time decay to generic loads).
+extern __shared__ __align__(16) unsigned char wide_raw[];
+
+// Segmented queue of the env in shared memory; storage and capacities are set at launch.  The
+// members are BYTE OFFSETS into wide_raw.
 struct WQueue {
-  uint16_t* head;  // [total]  recv | type << 8
-  int32_t* pay;    // [PW][total]
-  uint16_t* base;  // [G + 1]
-  uint8_t* cnt;    // [G]
-  uint8_t* order;  // [G]
-  int32_t* nseg;
+  uint32_t head;   // uint16 [total]  recv | type << 8
+  uint32_t pay;    // int32  [PW][total]
+  uint32_t base;   // uint16 [G + 1]
+  uint32_t cnt;    // uint8  [G]
+  uint32_t order;  // uint8  [G]
+  uint32_t nseg;   // int32
   int total;
-  __device__ __forceinline__ uint16_t& hd(int k, int seg) { return head[base[seg] + k]; }
-  __device__ __forceinline__ int32_t& py(int w, int k, int seg) {
-    return pay[w * total + base[seg] + k];
+  __device__ __forceinline__ int base_of(int seg) const {
+    return reinterpret_cast<const uint16_t*>(wide_raw + base)[seg];
   }
-  __device__ __forceinline__ int cap_of(int seg) const { return base[seg + 1] - base[seg]; }
+  __device__ __forceinline__ uint16_t& hd(int k, int seg) const {
+    return reinterpret_cast<uint16_t*>(wide_raw + head)[base_of(seg) + k];
+  }
+  __device__ __forceinline__ int32_t& py(int w, int k, int seg) const {
+    return reinterpret_cast<int32_t*>(wide_raw + pay)[w * total + base_of(seg) + k];
+  }
+  __device__ __forceinline__ int cap_of(int seg) const { return base_of(seg + 1) - base_of(seg); }
+  __device__ __forceinline__ uint8_t& cnt_of(int seg) const { return (wide_raw + cnt)[seg]; }
+  __device__ __forceinline__ uint8_t& order_at(int i) const { return (wide_raw + order)[i]; }
+  __device__ __forceinline__ int32_t& nseg_ref() const {
+    return *reinterpret_cast<int32_t*>(wide_raw + nseg);
+  }
 };
 
 template <int PW>
 struct WEmit {
-  WQueue* q;
+  const WQueue* q;
   const WideSpec* spec;
   int slot;
   const uint32_t* out_mask;
@@ -256,7 +274,7 @@ __device__ inline void wide_resample_row(uint64_t seed, const uint2* base, int n
 // order = the receivers by the position of their first message.  Returns the responses pushed.
 template <class P, bool TRACK>
 __device__ __forceinline__ int wide_round(const WideArgs<P>& a, const WCtx& ctx, int* st,
-                                          bool has_ctx, WQueue& qc, WQueue& qn, WideSmem<P>& sm,
+                                          bool has_ctx, const WQueue& qc, const WQueue& qn, WideSmem<P>& sm,
                                           int round, uint32_t& fault_key, int& traced, size_t row,
                                           bool trace_lane) {
   constexpr int INF = 0x7FFFFFFF;
@@ -264,13 +282,13 @@ __device__ __forceinline__ int wide_round(const WideArgs<P>& a, const WCtx& ctx,
   WEmit<P::PW> resp{&qn, ctx.spec, slot, ctx.out_mask, 0, 0u};
   int first = INF, pos = 0;
   bool bad_type = false;
-  const int nseg = *qc.nseg;
+  const int nseg = qc.nseg_ref();
   if constexpr (P::BATCHED) {
     if (has_ctx) P::batch_begin(ctx, st);
   }
   for (int si = 0; si < nseg; ++si) {
-    const int seg = qc.order[si];
-    const int c = qc.cnt[seg];
+    const int seg = qc.order_at(si);
+    const int c = qc.cnt_of(seg);
     for (int k = 0; k < c; ++k, ++pos) {
       const uint32_t hd = qc.hd(k, seg);  // recv | type << 8
       if ((int)(hd & 0xFFu) != slot) continue;
@@ -294,7 +312,7 @@ __device__ __forceinline__ int wide_round(const WideArgs<P>& a, const WCtx& ctx,
                                    PHX_FAULT_UNKNOWN_MSG_TYPE);
   if (resp.fault)
     fault_key = min(fault_key, ((uint32_t)(round + 1) << 16) | ((uint32_t)slot << 8) | resp.fault);
-  qn.cnt[slot] = (uint8_t)resp.n;
+  qn.cnt_of(slot) = (uint8_t)resp.n;
   const int total_next = wide_sum(resp.n, sm.red);  // (barrier: first_idx and qn are visible)
 
   int rank = 0, nrecv = 0;
@@ -303,13 +321,13 @@ __device__ __forceinline__ int wide_round(const WideArgs<P>& a, const WCtx& ctx,
     nrecv += fj != INF;
     rank += fj < first;
   }
-  if (first != INF) qn.order[rank] = (uint8_t)slot;
-  if (slot == 0) *qn.nseg = nrecv;
+  if (first != INF) qn.order_at(rank) = (uint8_t)slot;
+  if (slot == 0) qn.nseg_ref() = nrecv;
   __syncthreads();
   if (TRACK && trace_lane) {
     for (int si = 0; si < nrecv; ++si) {
-      const int seg = qn.order[si];
-      for (int k = 0; k < qn.cnt[seg]; ++k) {
+      const int seg = qn.order_at(si);
+      for (int k = 0; k < qn.cnt_of(seg); ++k) {
         if (traced < a.trace.cap)
           a.trace.rows[row * a.trace.cap + traced] =
               make_int4((int)(((uint32_t)qn.hd(k, seg) << 8) | (uint32_t)seg), qn.py(0, k, seg),
@@ -329,19 +347,19 @@ struct WideBlock {
 };
 
 template <class P>
-__device__ __forceinline__ void wide_setup(const WideArgs<P>& a, unsigned char* raw, int slot, int e,
-                                           WideBlock<P>& wb) {
+__device__ __forceinline__ void wide_setup(const WideArgs<P>& a, int slot, int e, WideBlock<P>& wb) {
   const WideSpec& sp = *a.spec;
-  WideSmem<P>& sm = *reinterpret_cast<WideSmem<P>*>(raw);
-  unsigned char* dyn = raw + ((sizeof(WideSmem<P>) + 15) & ~(size_t)15);
+  WideSmem<P>& sm = *reinterpret_cast<WideSmem<P>*>(wide_raw);
+  const uint32_t dyn = (uint32_t)((sizeof(WideSmem<P>) + 15) & ~(size_t)15);
   wb.sm = &sm;
+#pragma unroll
   for (int q = 0; q < 3; ++q) {
-    wb.q[q].pay = reinterpret_cast<int32_t*>(dyn + a.lay.off_pay[q]);
-    wb.q[q].head = reinterpret_cast<uint16_t*>(dyn + a.lay.off_head[q]);
-    wb.q[q].base = sm.qbase[q];
-    wb.q[q].cnt = sm.qcnt[q];
-    wb.q[q].order = sm.qorder[q];
-    wb.q[q].nseg = &sm.qnseg[q];
+    wb.q[q].pay = dyn + (uint32_t)a.lay.off_pay[q];
+    wb.q[q].head = dyn + (uint32_t)a.lay.off_head[q];
+    wb.q[q].base = (uint32_t)(offsetof(WideSmem<P>, qbase) + sizeof(sm.qbase[0]) * q);
+    wb.q[q].cnt = (uint32_t)(offsetof(WideSmem<P>, qcnt) + sizeof(sm.qcnt[0]) * q);
+    wb.q[q].order = (uint32_t)(offsetof(WideSmem<P>, qorder) + sizeof(sm.qorder[0]) * q);
+    wb.q[q].nseg = (uint32_t)(offsetof(WideSmem<P>, qnseg) + sizeof(int32_t) * q);
     wb.q[q].total = q == 0 ? a.lay.act_total : a.lay.resp_total;
   }
   const bool is_agent = slot < sp.n_agents;
@@ -389,13 +407,12 @@ __device__ __forceinline__ void wide_in_row(WideSmem<P>& sm, int n_agents, int s
 
 template <class P, bool TRACK>
 __global__ void __launch_bounds__(WIDE_G) wide_step_kernel(const WideArgs<P> a) {
-  extern __shared__ __align__(16) unsigned char wide_raw[];
   const WideSpec& sp = *a.spec;
   const int slot = threadIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int e = blockIdx.x;
   const bool is_agent = slot < sp.n_agents;
   WideBlock<P> wb;
-  wide_setup<P>(a, wide_raw, slot, e, wb);
+  wide_setup<P>(a, slot, e, wb);
   WideSmem<P>& sm = *wb.sm;
   __syncthreads();
   wide_in_row<P>(sm, sp.n_agents, slot);
@@ -491,9 +508,9 @@ __global__ void __launch_bounds__(WIDE_G) wide_step_kernel(const WideArgs<P> a) 
     // ---- acting phase
     WEmit<P::PW> out{&wb.q[0], &sp, slot, ctx.out_mask, 0, 0u};
     if (has_ctx && acting) P::act(ctx, st, strategic && has_action_now, act, out);
-    wb.q[0].cnt[slot] = (uint8_t)out.n;
-    wb.q[0].order[slot] = (uint8_t)slot;
-    if (slot == 0) *wb.q[0].nseg = sp.n_agents;
+    wb.q[0].cnt_of(slot) = (uint8_t)out.n;
+    wb.q[0].order_at(slot) = (uint8_t)slot;
+    if (slot == 0) wb.q[0].nseg_ref() = sp.n_agents;
     if (out.fault) fault_key = min(fault_key, (0u << 16) | ((uint32_t)slot << 8) | out.fault);
     int pending = wide_sum(out.n, sm.red);
 
@@ -501,7 +518,7 @@ __global__ void __launch_bounds__(WIDE_G) wide_step_kernel(const WideArgs<P> a) 
     const bool trace_lane = TRACK && slot == 0;
     if (trace_lane) {  // pushes of the acting phase, in global push order
       for (int si = 0; si < sp.n_agents; ++si)
-        for (int k = 0; k < wb.q[0].cnt[si]; ++k) {
+        for (int k = 0; k < wb.q[0].cnt_of(si); ++k) {
           if (traced < a.trace.cap)
             a.trace.rows[row * a.trace.cap + traced] =
                 make_int4((int)(((uint32_t)wb.q[0].hd(k, si) << 8) | (uint32_t)si),
@@ -522,8 +539,9 @@ __global__ void __launch_bounds__(WIDE_G) wide_step_kernel(const WideArgs<P> a) 
         fault_key = min(fault_key, ((uint32_t)(round + 1) << 16) | (0xFFu << 8) | PHX_FAULT_ROUND_LIMIT);
         break;
       }
-      WQueue& qc = round == 0 ? wb.q[0] : wb.q[1 + ((round - 1) & 1)];
-      WQueue& qn = wb.q[1 + (round & 1)];
+      // (selected by value: a run-time index into wb.q[] would put the queues in local memory)
+      const WQueue qc = round == 0 ? wb.q[0] : ((round - 1) & 1) ? wb.q[2] : wb.q[1];
+      const WQueue qn = (round & 1) ? wb.q[2] : wb.q[1];
       pending = wide_round<P, TRACK>(a, ctx, st, has_ctx, qc, qn, sm, round, fault_key, traced, row,
                                      trace_lane);
     }
@@ -750,14 +768,13 @@ template <class P>
 __global__ void __launch_bounds__(WIDE_G)
 wide_reset_kernel(const WideArgs<P> a, const uint8_t* env_mask, float* obs, uint8_t* obs_mask,
                   bool agents_only) {
-  extern __shared__ __align__(16) unsigned char wide_raw[];
   const WideSpec& sp = *a.spec;
   const int slot = threadIdx.x;
   const int e = blockIdx.x;
   if (env_mask != nullptr && env_mask[e] == 0) return;  // (block-uniform)
   const bool is_agent = slot < sp.n_agents;
   WideBlock<P> wb;
-  wide_setup<P>(a, wide_raw, slot, e, wb);
+  wide_setup<P>(a, slot, e, wb);
   WideSmem<P>& sm = *wb.sm;
   int4 h = a.hdr[e];
   int st[P::NWORDS > 0 ? P::NWORDS : 1];
