@@ -3,12 +3,14 @@
 // -- "an experiment brings its own agent classes" (phantom/agents.py:48-60) -- without a rebuild
 // of the library: libphx owns the HBM state, the ABI and the launch logic, the user's unit owns
 // the callbacks.  The kernels in the cubin are the thread-per-env engine (phx_engine1.cuh: at
-// most 8 agents per env) instantiated for the user's program; `phx_user_desc` says how many
-// state words / view words / payload words it uses.
+// most 8 agents per env) and -- for width-independent programs (WIDE_OK, phx_user.cuh) -- the
+// 128-lane block engine (phx_engine_wide.cuh: 9..128 agents) instantiated for the user's
+// program; `phx_user_desc` says how many state words / view words / payload words it uses.
 #include <cstring>
 #include <string>
 
 #include "phx_engine_host.cuh"
+#include "phx_engine_wide_host.cuh"
 
 namespace phx {
 namespace {
@@ -184,8 +186,61 @@ class UserFamily final : public Family {
   int32_t* d_env = nullptr;
 };
 
+// A user's program on the block engine: WideFamilyCore with the kernels of the cubin.
+class UserWideFamily final : public WideFamilyCore {
+ public:
+  explicit UserWideFamily(const char* cubin) : cubin_path(cubin ? cubin : "") {}
+  ~UserWideFamily() override {
+    if (lib) cudaLibraryUnload(lib);
+  }
+
+  int32_t init(const phx_spec& s) override {
+    PHX_REQUIRE(!cubin_path.empty(), PHX_ERR_INVALID, "phx_create_user: cubin path is NULL");
+    PHX_CUDA(cudaLibraryLoadFromFile(&lib, cubin_path.c_str(), nullptr, nullptr, 0, nullptr, nullptr, 0));
+    cudaKernel_t ks = nullptr, kt = nullptr, kr = nullptr;
+    PHX_CUDA(cudaLibraryGetKernel(&ks, lib, "phx_user_wide_step"));
+    PHX_CUDA(cudaLibraryGetKernel(&kt, lib, "phx_user_wide_step_tracked"));
+    PHX_CUDA(cudaLibraryGetKernel(&kr, lib, "phx_user_wide_reset"));
+    void* dptr = nullptr;
+    size_t dbytes = 0;
+    int32_t desc[12] = {};
+    PHX_CUDA(cudaLibraryGetGlobal(&dptr, &dbytes, lib, "phx_user_desc"));
+    PHX_REQUIRE(dbytes >= sizeof(desc), PHX_ERR_INVALID, "phx_user_desc has the wrong size");
+    PHX_CUDA(cudaMemcpy(desc, dptr, sizeof(desc), cudaMemcpyDeviceToHost));
+    PHX_REQUIRE(desc[0] == 0x50485855, PHX_ERR_INVALID,
+                "the cubin does not end with PHX_USER_PROGRAM(...) of this library version");
+    PHX_REQUIRE(desc[10] > 0, PHX_ERR_UNSUPPORTED,
+                "env classes of more than 8 agents run on the 128-lane block engine: the user "
+                "program must be width independent and declare WIDE_OK (csrc/phx_user.cuh)");
+    PHX_REQUIRE(s.obs_dim <= desc[5] && s.act_dim == desc[4], PHX_ERR_INVALID,
+                "spec obs_dim / act_dim do not match the device program");
+    info.nwords = desc[1];
+    info.pw = desc[3];
+    info.obs_dim = desc[5];
+    info.envw = desc[7];
+    info.smem_fixed = (size_t)desc[10];
+    const int actcap = desc[11] & 0xFFFF, respcap = (desc[11] >> 16) & 0xFFFF;
+    info.cap = [actcap, respcap](bool acting, int, int deg, int) {
+      const int cap = acting ? actcap : respcap, want = deg > 0 ? deg : 1;
+      return want < cap ? want : cap;  // wide_cap's default: one message per neighbour and round
+    };
+    info.k_step = (const void*)ks;
+    info.k_step_tracked = (const void*)kt;
+    info.k_reset = (const void*)kr;
+    name = "wide(G=128, user program)";
+    return core_init(s);
+  }
+
+ private:
+  std::string cubin_path;
+  cudaLibrary_t lib = nullptr;
+};
+
 }  // namespace
 
-Family* make_user_family(const char* cubin_path) { return new UserFamily(cubin_path); }
+Family* make_user_family(const char* cubin_path, const phx_spec& s) {
+  if (s.n_agents > ENGINE1_SLOTS || s.exec_mode == PHX_EXEC_WIDE) return new UserWideFamily(cubin_path);
+  return new UserFamily(cubin_path);
+}
 
 }  // namespace phx

@@ -366,7 +366,7 @@ static int32_t create_common(const phx_spec* spec, const char* cubin_path, int32
   PHX_REQUIRE(ndev > 0, PHX_ERR_NO_DEVICE,
               "no CUDA device visible: libphx has no CPU fallback by design");
   PHX_REQUIRE(device >= 0 && device < ndev, PHX_ERR_INVALID, "device index out of range");
-  Family* fam = spec->family == PHX_FAMILY_USER ? phx::make_user_family(cubin_path) : make_family(spec);
+  Family* fam = spec->family == PHX_FAMILY_USER ? phx::make_user_family(cubin_path, *spec) : make_family(spec);
   if (fam == nullptr) {
     set_error("no device program for family " + std::to_string(spec->family));
     return PHX_ERR_UNSUPPORTED;

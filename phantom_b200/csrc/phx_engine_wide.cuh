@@ -151,13 +151,23 @@ struct HasWideCaps : std::false_type {};
 template <class P>
 struct HasWideCaps<P, std::void_t<decltype(&P::wide_act_cap), decltype(&P::wide_resp_cap)>>
     : std::true_type {};
+// ... or just the bounds, when they differ from the narrow engines' ACTCAP / RESPCAP (a hub that
+// answers every neighbour): static constexpr int WIDE_ACTCAP, WIDE_RESPCAP.
+template <class P, class = void>
+struct WideCapConst {
+  static constexpr int act = P::ACTCAP, resp = P::RESPCAP;
+};
+template <class P>
+struct WideCapConst<P, std::void_t<decltype(P::WIDE_ACTCAP), decltype(P::WIDE_RESPCAP)>> {
+  static constexpr int act = P::WIDE_ACTCAP, resp = P::WIDE_RESPCAP;
+};
 template <class P>
 __host__ __device__ inline int wide_cap(bool acting, int kind, int degree, int n_agents) {
   if constexpr (HasWideCaps<P>::value) {
     return acting ? P::wide_act_cap(kind, degree, n_agents) : P::wide_resp_cap(kind, degree, n_agents);
   } else {
-    // one message per neighbour and round unless the program says otherwise
-    const int cap = acting ? P::ACTCAP : P::RESPCAP;
+    // one message per neighbour and round, up to the program's bound
+    const int cap = acting ? WideCapConst<P>::act : WideCapConst<P>::resp;
     const int want = degree > 0 ? degree : 1;
     return want < cap ? want : cap;
   }
@@ -168,15 +178,14 @@ struct WideLayout {  // byte offsets into the dynamic shared memory of a block
   int off_pay[3], off_head[3];
   int bytes;
 };
-template <class P>
-__host__ __device__ inline WideLayout wide_layout(int act_total, int resp_total) {
+__host__ __device__ inline WideLayout wide_layout_rt(int pw, int act_total, int resp_total) {
   WideLayout l;
   l.act_total = act_total;
   l.resp_total = resp_total;
   int at = 0;
   for (int q = 0; q < 3; ++q) {
     l.off_pay[q] = at;
-    at += 4 * P::PW * (q == 0 ? act_total : resp_total);
+    at += 4 * pw * (q == 0 ? act_total : resp_total);
   }
   for (int q = 0; q < 3; ++q) {
     l.off_head[q] = at;
@@ -406,7 +415,7 @@ __device__ __forceinline__ void wide_in_row(WideSmem<P>& sm, int n_agents, int s
 }
 
 template <class P, bool TRACK>
-__global__ void __launch_bounds__(WIDE_G) wide_step_kernel(const WideArgs<P> a) {
+__device__ __forceinline__ void wide_step_body(const WideArgs<P>& a) {
   const WideSpec& sp = *a.spec;
   const int slot = threadIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int e = blockIdx.x;
@@ -763,11 +772,15 @@ __global__ void __launch_bounds__(WIDE_G) wide_step_kernel(const WideArgs<P> a) 
   if (slot == 0 && fk != 0xFFFFFFFFu) raise_fault(a.faults, e, fk & 0xFFu);
 }
 
+template <class P, bool TRACK>
+__global__ void __launch_bounds__(WIDE_G) wide_step_kernel(const WideArgs<P> a) {
+  wide_step_body<P, TRACK>(a);
+}
+
 // PhantomEnv.reset / FiniteStateMachineEnv.reset / StackelbergEnv.reset for masked envs.
 template <class P>
-__global__ void __launch_bounds__(WIDE_G)
-wide_reset_kernel(const WideArgs<P> a, const uint8_t* env_mask, float* obs, uint8_t* obs_mask,
-                  bool agents_only) {
+__device__ __forceinline__ void wide_reset_body(const WideArgs<P>& a, const uint8_t* env_mask,
+                                                float* obs, uint8_t* obs_mask, bool agents_only) {
   const WideSpec& sp = *a.spec;
   const int slot = threadIdx.x;
   const int e = blockIdx.x;
@@ -851,5 +864,18 @@ wide_reset_kernel(const WideArgs<P> a, const uint8_t* env_mask, float* obs, uint
 #pragma unroll
   for (int w = 0; w < P::NWORDS; ++w) a.state[((size_t)w * sp.E + e) * WIDE_G + slot] = st[w];
 }
+
+template <class P>
+__global__ void __launch_bounds__(WIDE_G)
+wide_reset_kernel(const WideArgs<P> a, const uint8_t* env_mask, float* obs, uint8_t* obs_mask,
+                  bool agents_only) {
+  wide_reset_body<P>(a, env_mask, obs, obs_mask, agents_only);
+}
+
+// A program says that its callbacks are width independent with `static constexpr bool WIDE_OK`.
+template <class P, class = void>
+struct IsWideOk : std::false_type {};
+template <class P>
+struct IsWideOk<P, std::void_t<decltype(P::WIDE_OK)>> : std::bool_constant<P::WIDE_OK> {};
 
 }  // namespace phx

@@ -1,10 +1,17 @@
 // phx_engine_wide_host.cuh -- host side of the 128-lane block engine (phx_engine_wide.cuh): a
-// Family that owns the state of E envs of a device program P with 33..128 agents (or fewer, when
-// PHX_EXEC_WIDE is forced) and launches wide_step_kernel<P>, one block per env.
+// Family that owns the state of E envs of a device program with 33..128 agents (or fewer, when
+// PHX_EXEC_WIDE is forced) and launches wide_step_kernel, one block per env.
+//   WideFamilyCore  everything that does not depend on the program type: buffers, launches,
+//                   fields.  What it needs to know about the program is a WideProgramInfo
+//                   (sizes, queue capacities, kernel handles) -- so the same class serves the
+//                   families compiled into libphx (WideFamily<P>) and a user's program that
+//                   arrives as a cubin (fam_user.cu).
 // Field mapping: PHX_FIELD_FAMILY + w = state word w, int32 [E, 128] (slot-major inside an env);
 // PHX_FIELD_TERMINATED / _TRUNCATED = uint32 [E, 4] bitmasks over agent slots;
-// PHX_FIELD_ADJACENCY = uint32 [E, 128, 4] rows.
+// PHX_FIELD_ADJACENCY = uint32 [E, 128, 4] rows; PHX_FIELD_ENV_STATE = int32 [E] per word.
 #pragma once
+#include <functional>
+
 #include "phx_engine_host.cuh"
 #include "phx_engine_wide.cuh"
 
@@ -15,10 +22,21 @@ static __global__ void wide_init_kernel(int E, int4* hdr) {
   if (i < E) hdr[i] = make_int4(0, -1, 0, 0);  // episode becomes 0 on the first reset
 }
 
-template <class P>
-class WideFamily : public Family {
+struct WideTag {};  // WideArgs<P> has the same layout for every P
+
+struct WideProgramInfo {
+  int nwords = 0, envw = 0, pw = 1, obs_dim = 1;
+  size_t smem_fixed = 0;  // sizeof(WideSmem<P>)
+  // segment capacity of one agent: (acting phase?, kind, degree in the full graph, n_agents)
+  std::function<int(bool, int, int, int)> cap;
+  const void* k_step = nullptr;          // wide_step_kernel<P, false> (or a cudaKernel_t)
+  const void* k_step_tracked = nullptr;  // wide_step_kernel<P, true>
+  const void* k_reset = nullptr;         // wide_reset_kernel<P>
+};
+
+class WideFamilyCore : public Family {
  public:
-  ~WideFamily() override {
+  ~WideFamilyCore() override {
     cudaFree(d_spec);
     cudaFree(d_state);
     cudaFree(d_rcache);
@@ -30,27 +48,26 @@ class WideFamily : public Family {
     cudaFree(d_env);
   }
 
-  int32_t init(const phx_spec& s) override {
+  // `info` is filled by the subclass before this runs.
+  int32_t core_init(const phx_spec& s) {
     PHX_REQUIRE(!(s.flags & PHX_FLAG_SHUFFLE_BATCHES), PHX_ERR_UNSUPPORTED,
                 "shuffle_batches is not available on the 128-lane block engine");
-    int32_t rc = make_engine_spec(s, E, seed, env_offset, &wspec, P::NWORDS, EnvWords<P>::value);
+    int32_t rc = make_engine_spec(s, E, seed, env_offset, &wspec, info.nwords, info.envw);
     if (rc != PHX_OK) return rc;
-    rc = P::validate(s);
-    if (rc != PHX_OK) return rc;
-    PHX_REQUIRE(s.obs_dim <= P::OBS_DIM, PHX_ERR_INVALID, "obs_dim exceeds the family's OBS_DIM");
+    PHX_REQUIRE(s.obs_dim <= info.obs_dim, PHX_ERR_INVALID, "obs_dim exceeds the family's OBS_DIM");
     int act_total = 0, resp_total = 0;
     for (int i = 0; i < s.n_agents; ++i) {
       int deg = 0;
       for (int r = 0; r < s.n_agents; ++r) deg += mask_bit(s.adjacency[i], r);
-      const int ca = wide_cap<P>(true, s.agent_kind[i], deg, s.n_agents);
-      const int cr = wide_cap<P>(false, s.agent_kind[i], deg, s.n_agents);
+      const int ca = info.cap(true, s.agent_kind[i], deg, s.n_agents);
+      const int cr = info.cap(false, s.agent_kind[i], deg, s.n_agents);
       PHX_REQUIRE(ca >= 0 && ca <= 255 && cr >= 0 && cr <= 255, PHX_ERR_UNSUPPORTED,
                   "an agent's per-round fan-out exceeds 255 messages");
       act_total += ca;
       resp_total += cr;
     }
-    lay = wide_layout<P>(act_total, resp_total);
-    smem = ((sizeof(WideSmem<P>) + 15) & ~(size_t)15) + (size_t)lay.bytes;
+    lay = wide_layout_rt(info.pw, act_total, resp_total);
+    smem = ((info.smem_fixed + 15) & ~(size_t)15) + (size_t)lay.bytes;
     PHX_REQUIRE(smem <= 200 * 1024, PHX_ERR_UNSUPPORTED,
                 "message queues of this env class exceed the shared memory of a block");
 
@@ -68,7 +85,7 @@ class WideFamily : public Family {
     PHX_CUDA(cudaMalloc(&d_spec, sizeof(WideSpec)));
     PHX_CUDA(cudaMemcpy(d_spec, &wspec, sizeof(WideSpec), cudaMemcpyHostToDevice));
     const size_t n = (size_t)E * WIDE_G;
-    const size_t nw = P::NWORDS > 0 ? P::NWORDS : 1;
+    const size_t nw = info.nwords > 0 ? info.nwords : 1;
     PHX_CUDA(cudaMalloc(&d_state, sizeof(int32_t) * n * nw));
     PHX_CUDA(cudaMemset(d_state, 0, sizeof(int32_t) * n * nw));
     if (s.env_kind != PHX_ENV_BASE) {
@@ -83,9 +100,9 @@ class WideFamily : public Family {
         PHX_CUDA(cudaMemset(d_ocached, 0, mw));
       }
     }
-    if (EnvWords<P>::value > 0) {  // env-level words start at zero (e.g. avg_price = 0.0)
-      PHX_CUDA(cudaMalloc(&d_env, sizeof(int32_t) * (size_t)E * EnvWords<P>::value));
-      PHX_CUDA(cudaMemset(d_env, 0, sizeof(int32_t) * (size_t)E * EnvWords<P>::value));
+    if (info.envw > 0) {  // env-level words start at zero (e.g. avg_price = 0.0)
+      PHX_CUDA(cudaMalloc(&d_env, sizeof(int32_t) * (size_t)E * info.envw));
+      PHX_CUDA(cudaMemset(d_env, 0, sizeof(int32_t) * (size_t)E * info.envw));
     }
     if (s.flags & PHX_FLAG_STOCHASTIC_NETWORK) {
       PHX_REQUIRE(s.n_base_connections >= 0 && s.n_base_connections <= PHX_MAX_BASE_CONNECTIONS,
@@ -106,24 +123,19 @@ class WideFamily : public Family {
       PHX_CUDA(cudaMalloc(&d_adj, sizeof(uint32_t) * n * WIDE_MW));
       PHX_CUDA(cudaMemset(d_adj, 0, sizeof(uint32_t) * n * WIDE_MW));
     }
-    PHX_CUDA(cudaFuncSetAttribute(wide_step_kernel<P, false>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    PHX_CUDA(cudaFuncSetAttribute(wide_step_kernel<P, true>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    PHX_CUDA(cudaFuncSetAttribute(wide_reset_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)smem));
+    for (const void* k : {info.k_step, info.k_step_tracked, info.k_reset})
+      PHX_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     wide_init_kernel<<<(E + 255) / 256, 256>>>(E, d_hdr);
     PHX_CUDA(cudaGetLastError());
     // constructor-time agent state (PhantomEnv.__init__ ends with agent.reset(), env.py:122-124)
     rc = launch_reset(nullptr, nullptr, nullptr, 0, /*agents_only=*/true);
     if (rc != PHX_OK) return rc;
     PHX_CUDA(cudaDeviceSynchronize());
-    name = "wide(G=128)";
     return PHX_OK;
   }
 
-  WideArgs<P> make_args(int32_t T, const StepIO& io) const {
-    WideArgs<P> a;
+  WideArgs<WideTag> make_args(int32_t T, const StepIO& io) const {
+    WideArgs<WideTag> a;
     a.spec = d_spec;
     a.T = T;
     a.lay = lay;
@@ -148,9 +160,9 @@ class WideFamily : public Family {
   int32_t launch_reset(const uint8_t* env_mask, float* obs, uint8_t* obs_mask, cudaStream_t stream,
                        bool agents_only) {
     StepIO io{};
-    const WideArgs<P> a = make_args(1, io);
-    wide_reset_kernel<P><<<E, WIDE_G, smem, stream>>>(a, env_mask, obs, obs_mask, agents_only);
-    PHX_CUDA(cudaGetLastError());
+    WideArgs<WideTag> a = make_args(1, io);
+    void* args[] = {(void*)&a, (void*)&env_mask, (void*)&obs, (void*)&obs_mask, (void*)&agents_only};
+    PHX_CUDA(cudaLaunchKernel(info.k_reset, dim3(E), dim3(WIDE_G), args, smem, stream));
     return PHX_OK;
   }
 
@@ -164,18 +176,16 @@ class WideFamily : public Family {
       const int32_t rc = ensure_trace(T);
       if (rc != PHX_OK) return rc;
     }
-    const WideArgs<P> a = make_args(T, io);
-    if (tracking())
-      wide_step_kernel<P, true><<<E, WIDE_G, smem, stream>>>(a);
-    else
-      wide_step_kernel<P, false><<<E, WIDE_G, smem, stream>>>(a);
-    PHX_CUDA(cudaGetLastError());
+    WideArgs<WideTag> a = make_args(T, io);
+    void* args[] = {(void*)&a};
+    PHX_CUDA(cudaLaunchKernel(tracking() ? info.k_step_tracked : info.k_step, dim3(E), dim3(WIDE_G),
+                              args, smem, stream));
     return PHX_OK;
   }
 
   int32_t family_field(int32_t field, int32_t index, void** p, size_t* bytes) override {
     if (field == PHX_FIELD_ENV_STATE) {  // int32 [E]: env-level word `index`
-      PHX_REQUIRE(index >= 0 && index < EnvWords<P>::value, PHX_ERR_INVALID,
+      PHX_REQUIRE(index >= 0 && index < info.envw, PHX_ERR_INVALID,
                   "PHX_FIELD_ENV_STATE: this env class has no such env-level word");
       *p = d_env + (size_t)index * E;
       *bytes = sizeof(int32_t) * (size_t)E;
@@ -189,7 +199,7 @@ class WideFamily : public Family {
       return PHX_OK;
     }
     const int w = field - PHX_FIELD_FAMILY;
-    if (w >= 0 && w < P::NWORDS) {
+    if (w >= 0 && w < info.nwords) {
       *p = d_state + (size_t)w * E * WIDE_G;
       *bytes = sizeof(int32_t) * (size_t)E * WIDE_G;
       return PHX_OK;
@@ -200,6 +210,7 @@ class WideFamily : public Family {
 
   const char* exec_name() const override { return name.c_str(); }
 
+  WideProgramInfo info;
   WideSpec wspec{};
   WideSpec* d_spec = nullptr;
   WideLayout lay{};
@@ -214,6 +225,26 @@ class WideFamily : public Family {
   int32_t* d_env = nullptr;  // [ENVW][E]
   int32_t n_base = 0;
   std::string name = "wide(G=128)";
+};
+
+// The block engine for a program compiled into libphx.
+template <class P>
+class WideFamily : public WideFamilyCore {
+ public:
+  int32_t init(const phx_spec& s) override {
+    const int32_t rc = P::validate(s);
+    if (rc != PHX_OK) return rc;
+    info.nwords = P::NWORDS;
+    info.envw = EnvWords<P>::value;
+    info.pw = P::PW;
+    info.obs_dim = P::OBS_DIM;
+    info.smem_fixed = sizeof(WideSmem<P>);
+    info.cap = [](bool acting, int kind, int deg, int n) { return wide_cap<P>(acting, kind, deg, n); };
+    info.k_step = (const void*)wide_step_kernel<P, false>;
+    info.k_step_tracked = (const void*)wide_step_kernel<P, true>;
+    info.k_reset = (const void*)wide_reset_kernel<P>;
+    return core_init(s);
+  }
 };
 
 // The family object of an engine-backed program: the block engine for env classes wider than a

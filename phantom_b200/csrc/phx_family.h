@@ -95,7 +95,7 @@ Family* make_dense_family(const phx_spec& spec);
 Family* make_supply_chain2_family(const phx_spec& spec);
 Family* make_simple_market_family(const phx_spec& spec);
 Family* make_digital_ads_family(const phx_spec& spec);
-Family* make_user_family(const char* cubin_path);
+Family* make_user_family(const char* cubin_path, const phx_spec& spec);
 int32_t selftest_ratio(int32_t device, int32_t den, int32_t lo, int32_t count, float* host_out);
 
 }  // namespace phx

@@ -21,13 +21,38 @@
 // cubin through the runtime's library API (`phx_create_user`): the kernels below are the
 // thread-per-env engine (env classes of at most 8 agents) instantiated for the user's program,
 // and `phx_user_desc` tells the library how much state and shared memory the program needs.
+//
+// Env classes of 9..128 agents run on the 128-lane block engine (phx_engine_wide.cuh).  A program
+// opts in by being WIDTH INDEPENDENT: every callback a template over the context type
+// (`template <class C> ... const C& c`; Ctx on the thread engine, WCtx on the block engine),
+// neighbours iterated with c.next_neighbour() / c.next_of_kind(), never a raw mask word, and
+//     static constexpr bool WIDE_OK = true;
+// Its queue segments are sized per agent as min(cap, degree in the graph), cap = ACTCAP / RESPCAP
+// or, if declared, WIDE_ACTCAP / WIDE_RESPCAP (<= 255).
 #pragma once
 #define PHX_JIT_TU 1  // (a program unit, not libphx: the families' host classes stay out)
 #include "phx_engine1.cuh"
+#include "phx_engine_wide.cuh"
 
 namespace phx {
 constexpr int32_t PHX_USER_MAGIC = 0x50485855;  // "PHXU"
+
+// block-engine bodies of a user program: empty unless the program declares WIDE_OK
+template <class P, bool TRACK>
+__device__ __forceinline__ void user_wide_step(const WideArgs<P>& a) {
+  if constexpr (IsWideOk<P>::value) wide_step_body<P, TRACK>(a);
 }
+template <class P>
+__device__ __forceinline__ void user_wide_reset(const WideArgs<P>& a, const uint8_t* env_mask,
+                                                float* obs, uint8_t* obs_mask, bool agents_only) {
+  if constexpr (IsWideOk<P>::value) wide_reset_body<P>(a, env_mask, obs, obs_mask, agents_only);
+}
+template <class P>
+constexpr int32_t user_wide_smem() {
+  if constexpr (IsWideOk<P>::value) return (int32_t)sizeof(WideSmem<P>);
+  return 0;
+}
+}  // namespace phx
 
 #define PHX_USER_PROGRAM(Prog)                                                                  \
   extern "C" __global__ void __launch_bounds__(::phx::ENGINE1_BLOCK)                            \
@@ -43,7 +68,22 @@ constexpr int32_t PHX_USER_MAGIC = 0x50485855;  // "PHXU"
                  uint8_t* obs_mask, bool agents_only) {                                         \
     ::phx::engine_reset_body<Prog, 8>(a, env_mask, obs, obs_mask, agents_only);                 \
   }                                                                                             \
+  extern "C" __global__ void __launch_bounds__(::phx::WIDE_G)                                   \
+  phx_user_wide_step(const ::phx::WideArgs<Prog> a) {                                           \
+    ::phx::user_wide_step<Prog, false>(a);                                                      \
+  }                                                                                             \
+  extern "C" __global__ void __launch_bounds__(::phx::WIDE_G)                                   \
+  phx_user_wide_step_tracked(const ::phx::WideArgs<Prog> a) {                                   \
+    ::phx::user_wide_step<Prog, true>(a);                                                       \
+  }                                                                                             \
+  extern "C" __global__ void __launch_bounds__(::phx::WIDE_G)                                   \
+  phx_user_wide_reset(const ::phx::WideArgs<Prog> a, const uint8_t* env_mask, float* obs,       \
+                      uint8_t* obs_mask, bool agents_only) {                                    \
+    ::phx::user_wide_reset<Prog>(a, env_mask, obs, obs_mask, agents_only);                      \
+  }                                                                                             \
   extern "C" __device__ const int32_t phx_user_desc[12] = {                                     \
       ::phx::PHX_USER_MAGIC, Prog::NWORDS,     Prog::VW,      Prog::PW,                         \
       Prog::ACT_DIM,         Prog::OBS_DIM,    Prog::Q1CAP,   ::phx::EnvWords<Prog>::value,     \
-      (int32_t)sizeof(::phx::BlockSmem<Prog, 8>), Prog::BATCHED ? 1 : 0, 0, 0};
+      (int32_t)sizeof(::phx::BlockSmem<Prog, 8>), Prog::BATCHED ? 1 : 0,                        \
+      ::phx::user_wide_smem<Prog>(),                                                            \
+      ::phx::WideCapConst<Prog>::act | (::phx::WideCapConst<Prog>::resp << 16)};

@@ -9,21 +9,24 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def test_user_program_matches_python_handlers():
+@pytest.mark.parametrize("n_bidders,E,exec_name", [
+    (3, 24, "thread-per-env(G=8, user program)"),
+    (40, 6, "wide(G=128, user program)")])  # 41 agents: the 128-lane block engine
+def test_user_program_matches_python_handlers(n_bidders, E, exec_name):
     import oracle.phantom_oracle as po
     from oracle import harness
 
     from .user_program import auction_env as ae
 
-    E, T, n_ep = 24, 40, 2
+    T, n_ep, S = 40, 2, n_bidders
     r = np.random.RandomState(4)
-    A = r.uniform(0, 1, size=(E, n_ep, T, 3, 1)).astype(np.float32)
-    M = (r.uniform(size=(E, n_ep, T, 3)) > 0.15).astype(np.uint8)
-    env = ae.build_device(num_envs=E, seed=1, num_steps=T)
-    assert env.exec_name == "thread-per-env(G=8, user program)"
+    A = r.uniform(0, 1, size=(E, n_ep, T, S, 1)).astype(np.float32)
+    M = (r.uniform(size=(E, n_ep, T, S)) > 0.15).astype(np.uint8)
+    env = ae.build_device(n_bidders, num_envs=E, seed=1, num_steps=T)
+    assert env.exec_name == exec_name
     traces = []
     for e in range(E):
-        ref = ae.build_reference(po, T)
+        ref = ae.build_reference(po, T, n_bidders)
         traces.append(harness.run_generic(ref, harness.EpisodeClock([]), A[e], M[e], 3))
     for ep in range(n_ep):
         obs, mask = env.reset_batch()

@@ -11,7 +11,7 @@ N_BIDDERS = 3
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def build_device(**batch_kwargs):
+def build_device(n_bidders=N_BIDDERS, **batch_kwargs):
     import phantom_b200 as ph
     from phantom_b200.agents import device_column
     from phantom_b200.families import REGISTRY, register_user_family
@@ -59,7 +59,7 @@ def build_device(**batch_kwargs):
                                     (Bid, Ack), obs_dim=3, act_dim=1, collect=collect)
         info.classes = (Bidder, Book)
     Bidder, Book = REGISTRY["auction_game"].classes
-    ids = [f"B{i + 1}" for i in range(N_BIDDERS)]
+    ids = [f"B{i + 1}" for i in range(n_bidders)]
     agents = [Bidder(b, "BOOK") for b in ids] + [Book("BOOK")]
     net = ph.Network(agents, ph.resolvers.BatchResolver(
         enable_tracking=batch_kwargs.pop("enable_tracking", False)))
@@ -67,7 +67,7 @@ def build_device(**batch_kwargs):
     return ph.PhantomEnv(num_steps=batch_kwargs.pop("num_steps", 40), network=net, **batch_kwargs)
 
 
-def build_reference(ph, num_steps=40):
+def build_reference(ph, num_steps=40, n_bidders=N_BIDDERS):
     """The same env with Python handlers (reference plugin API)."""
     from oracle.phantom_oracle.spaces import Box
 
@@ -128,7 +128,7 @@ def build_reference(ph, num_steps=40):
             self.best = max(self.best, message.payload.price)
             return [(message.sender_id, Ack(self.count, self.best))]
 
-    ids = [f"B{i + 1}" for i in range(N_BIDDERS)]
+    ids = [f"B{i + 1}" for i in range(n_bidders)]
     agents = [Bidder(b, "BOOK") for b in ids] + [Book("BOOK")]
     net = ph.Network(agents, ph.resolvers.BatchResolver())
     net.add_connections_between(["BOOK"], ids)
