@@ -713,7 +713,7 @@ def run_ours(args):
                 "parallelism": f"env-sharded x{world}, no data-path collective",
             },
             "roofline": dict(c2["roofline"], traffic=traffic, traffic_source=traffic_src,
-                             kernel="sc_fast_kernel"),
+                             kernel="sc_fast2_kernel<0,1,0> (lean I/O, vectorised action ring; programmatic dependent launch)"),
             "e2e": dict(c2["e2e"], bound="pcie / host expansion",
                         d2h_GBps_per_gpu=c2["e2e"]["d2h_bytes_per_step"] * c2["e2e"]["value"] /
                         (world * E * T) / 1e9,

@@ -412,6 +412,10 @@ struct Sc2Args {
   // [T, E]; *wire_overflow is set if a value of the launch does not fit its field
   uint32_t* wire;
   uint32_t* wire_overflow;
+  // programmatic dependent launch: let the NEXT launch on the stream start its blocks once this
+  // one has `pdl_lead` steps left (its launch latency, block scheduling and table fill then
+  // overlap this grid's tail); T + 1 = never (the implicit trigger at grid completion)
+  int32_t pdl_lead;
 };
 
 template <bool FULL_IO, bool VEC, bool WIRE, int RING = SC2_RING, bool AR = false>
@@ -421,10 +425,9 @@ __global__ void __launch_bounds__(SC_BLOCK) sc_fast2_kernel(const Sc2Args args) 
   extern __shared__ __align__(16) unsigned char sc2_smem[];
   float (*act_ring)[SC_BLOCK] = reinterpret_cast<float (*)[SC_BLOCK]>(sc2_smem);
   const uint8_t* dsum = sc2_smem + sizeof(float) * RING * SC_BLOCK;
-  // Programmatic dependent launch: the next launch on the stream may start its blocks and run
-  // its prologue (the table fill below) while this grid is still stepping; it waits at
-  // griddep_wait() before it touches anything a previous kernel may have written.
-  griddep_launch_dependents();
+  // Programmatic dependent launch (PHX_PDL=1): this grid may have been started while the previous
+  // launch on the stream was still stepping; it runs its prologue (the table fill below) and
+  // waits at griddep_wait() before it touches anything a previous kernel may have written.
   {  // digit-sum table -> shared memory (4-byte words; the host pads the table to 16 bytes)
     const uint32_t* src = reinterpret_cast<const uint32_t*>(args.dsum);
     uint32_t* dst = reinterpret_cast<uint32_t*>(sc2_smem + sizeof(float) * RING * SC_BLOCK);
@@ -554,7 +557,12 @@ __global__ void __launch_bounds__(SC_BLOCK) sc_fast2_kernel(const Sc2Args args) 
       fetch_group();
     }
   };
+  bool triggered = false;
   while (t < T) {
+    if (!triggered && t + args.pdl_lead >= T) {  // (warp-uniform: t is)
+      griddep_launch_dependents();
+      triggered = true;
+    }
     // How many aligned 4-step groups can EVERY env of the warp run from here?  (aligned: the
     // next step's word is the first of a Philox block; no auto-reset wrap inside a group)
     const int g = h.x + 1;
@@ -1250,6 +1258,7 @@ class SupplyChainFast final : public Family {
       b.a = a;
       b.dsum = d_dsum;
       b.pow5 = pow5;
+      b.pdl_lead = use_pdl ? pdl_lead : -(1 << 30);
       if (sc_variant == 4 && a.vec_actions && env_count % 32 == 0 && !wire) {  // two lanes per env
         const int grid4 = env_count / (SC4_THREADS / 2);
         const bool ar = (plan.flags & PHX_FLAG_AUTO_RESET) != 0;
@@ -1474,11 +1483,15 @@ class SupplyChainFast final : public Family {
   // where more than one is valid: A/B measurements and the cross-kernel parity tests
   const int sc_variant = std::getenv("PHX_SC_KERNEL") ? std::atoi(std::getenv("PHX_SC_KERNEL")) : 2;
   const bool use_v1 = sc_variant == 1;
-  // PHX_PDL=1 launches sc_fast2_kernel with programmatic stream serialization (the next launch's
-  // blocks start while this grid runs and wait at griddepcontrol.wait).  Measured and rejected as
-  // a default: 55.9 us per launch against 30.3 -- the waiting blocks of the next launches take
-  // the schedulers' warp slots from the running one (profiles/r02_ab_sc_kernels.txt).
-  const bool use_pdl = std::getenv("PHX_PDL") != nullptr && std::getenv("PHX_PDL")[0] == '1';
+  // sc_fast2_kernel is launched with programmatic stream serialization (PHX_PDL=0 turns it off):
+  // a launch lets the NEXT launch on the stream start its blocks when it has PHX_PDL_LEAD (8)
+  // steps left, so that the successor's launch latency, block scheduling and table fill overlap
+  // this grid's tail; the successor waits at griddepcontrol.wait before it reads the env state.
+  // Measured per 65 536 x 100 launch (profiles/r02_ab_sc_kernels.txt): 30.74 us without, 29.54
+  // with a lead of 8 steps (4: 29.82, 12: 29.60, 20: 30.21).  A trigger at the very START of the
+  // kernel was rejected earlier in the round (every queued launch becomes resident and spins).
+  const bool use_pdl = !(std::getenv("PHX_PDL") != nullptr && std::getenv("PHX_PDL")[0] == '0');
+  const int pdl_lead = std::getenv("PHX_PDL_LEAD") ? std::atoi(std::getenv("PHX_PDL_LEAD")) : 8;
   // PHX_NO_WIRE=1 (read when the handle is created) keeps phx_rollout_host on the float planes
   const bool no_wire = std::getenv("PHX_NO_WIRE") != nullptr && std::getenv("PHX_NO_WIRE")[0] == '1';
   const int sc_warps = std::getenv("PHX_SC_WARPS") ? std::atoi(std::getenv("PHX_SC_WARPS")) : 4;

@@ -176,6 +176,7 @@ __host__ __device__ inline int wide_cap(bool acting, int kind, int degree, int n
 struct WideLayout {  // byte offsets into the dynamic shared memory of a block
   int act_total, resp_total;
   int off_pay[3], off_head[3];
+  int off_flat;  // uint32 [max(act_total, resp_total)]: the round's queue in push order
   int bytes;
 };
 __host__ __device__ inline WideLayout wide_layout_rt(int pw, int act_total, int resp_total) {
@@ -192,6 +193,8 @@ __host__ __device__ inline WideLayout wide_layout_rt(int pw, int act_total, int 
     at += 2 * (q == 0 ? act_total : resp_total);
     at = (at + 3) & ~3;
   }
+  l.off_flat = at;
+  at += 4 * (act_total > resp_total ? act_total : resp_total);
   l.bytes = at;
   return l;
 }
@@ -233,6 +236,8 @@ struct WideSmem {
   int32_t red[WIDE_MW];
   uint32_t redu[WIDE_MW];
   int32_t bcast;
+  int16_t pbase[WIDE_G];  // flattening a round's queue: first position of the i-th segment visited
+  uint8_t pseg[WIDE_G];   // ... and its producer
   // programs with env-level words: every agent's state, published before env_post
   int32_t pub[EnvWords<P>::value > 0 ? (P::NWORDS > 0 ? P::NWORDS : 1) : 1][EnvWords<P>::value > 0 ? WIDE_G : 1];
 };
@@ -277,40 +282,81 @@ __device__ inline void wide_resample_row(uint64_t seed, const uint2* base, int n
   for (int w = 0; w < WIDE_MW; ++w) row[w] = r[w];
 }
 
-// One resolver round (resolvers.py:137-158): every receiver lane scans the current queue in
-// global push order (segments in first-arrival order of their producers), handles the
-// messages addressed to it and appends its responses to its segment of `qn`; `qn`'s segment
-// order = the receivers by the position of their first message.  Returns the responses pushed.
+// One resolver round (resolvers.py:137-158): the block flattens the current queue into global
+// push order (segments in first-arrival order of their producers); every receiver lane scans
+// that copy, handles the messages addressed to it and appends its responses to its segment of
+// `qn`; `qn`'s segment order = the receivers by the position of their first message.  Returns
+// the responses pushed.
 template <class P, bool TRACK>
 __device__ __forceinline__ int wide_round(const WideArgs<P>& a, const WCtx& ctx, int* st,
                                           bool has_ctx, const WQueue& qc, const WQueue& qn, WideSmem<P>& sm,
                                           int round, uint32_t& fault_key, int& traced, size_t row,
-                                          bool trace_lane) {
+                                          bool trace_lane, uint32_t flat_off) {
   constexpr int INF = 0x7FFFFFFF;
-  const int slot = ctx.slot;
+  const int slot = ctx.slot, lane = slot & 31, warp = slot >> 5;
   WEmit<P::PW> resp{&qn, ctx.spec, slot, ctx.out_mask, 0, 0u};
-  int first = INF, pos = 0;
+  int first = INF;
   bool bad_type = false;
   const int nseg = qc.nseg_ref();
+
+  // ---- 1. flatten the queue into push order: flat[p] = recv | type << 8 | producer << 16 |
+  // index in the producer's segment << 24.  (Walking the segments per receiver costs four
+  // DEPENDENT shared-memory loads per segment -- order, count, base, head -- in every lane; the
+  // flat copy is one broadcast load per message.)  Lane i takes the i-th segment visited; a block
+  // exclusive scan of the segment lengths gives its first position.
+  int c_i = 0, seg_i = 0;
+  if (slot < nseg) {
+    seg_i = qc.order_at(slot);
+    c_i = qc.cnt_of(seg_i);
+  }
+  int incl = c_i;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const int v = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+    if (lane >= off) incl += v;
+  }
+  if (lane == 31) sm.red[warp] = incl;
+  __syncthreads();
+  int woff = 0;
+#pragma unroll
+  for (int w = 0; w < WIDE_MW; ++w)
+    if (w < warp) woff += sm.red[w];
+  const int tot = sm.red[0] + sm.red[1] + sm.red[2] + sm.red[3];
+  sm.pbase[slot] = (int16_t)(slot < nseg ? woff + incl - c_i : 0x7FFF);
+  sm.pseg[slot] = (uint8_t)seg_i;
+  __syncthreads();
+  uint32_t* flat = reinterpret_cast<uint32_t*>(wide_raw + flat_off);
+  for (int p = slot; p < tot; p += WIDE_G) {
+    // the segment that holds position p: the LAST i with pbase[i] <= p (empty segments share
+    // their successor's first position)
+    int lo = 0, hi = nseg - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (sm.pbase[mid] <= p) lo = mid;
+      else hi = mid - 1;
+    }
+    const int seg = sm.pseg[lo], k = p - sm.pbase[lo];
+    flat[p] = (uint32_t)qc.hd(k, seg) | ((uint32_t)seg << 16) | ((uint32_t)k << 24);
+  }
+  __syncthreads();
+
+  // ---- 2. every receiver handles its batch, in push order
   if constexpr (P::BATCHED) {
     if (has_ctx) P::batch_begin(ctx, st);
   }
-  for (int si = 0; si < nseg; ++si) {
-    const int seg = qc.order_at(si);
-    const int c = qc.cnt_of(seg);
-    for (int k = 0; k < c; ++k, ++pos) {
-      const uint32_t hd = qc.hd(k, seg);  // recv | type << 8
-      if ((int)(hd & 0xFFu) != slot) continue;
-      if (first == INF) first = pos;  // first-arrival position of this receiver
-      if (!has_ctx) continue;         // done agent: mail dropped (resolvers.py:143-144)
-      if (!wbit(ctx.in_mask, seg)) continue;  // delivery-time edge filter (:146-148)
-      Msg m;
-      m.sender = seg;
-      m.type = (int)(hd >> 8);
-      m.p[0] = qc.py(0, k, seg);
-      m.p[1] = P::PW > 1 ? qc.py(P::PW > 1 ? 1 : 0, k, seg) : 0;
-      if (!P::handle(ctx, st, m, resp)) bad_type = true;  // agents.py:140-143
-    }
+  for (int pos = 0; pos < tot; ++pos) {
+    const uint32_t f = flat[pos];
+    if ((int)(f & 0xFFu) != slot) continue;
+    if (first == INF) first = pos;  // first-arrival position of this receiver
+    if (!has_ctx) continue;         // done agent: mail dropped (resolvers.py:143-144)
+    const int seg = (int)((f >> 16) & 0xFFu), k = (int)(f >> 24);
+    if (!wbit(ctx.in_mask, seg)) continue;  // delivery-time edge filter (:146-148)
+    Msg m;
+    m.sender = seg;
+    m.type = (int)((f >> 8) & 0xFFu);
+    m.p[0] = qc.py(0, k, seg);
+    m.p[1] = P::PW > 1 ? qc.py(P::PW > 1 ? 1 : 0, k, seg) : 0;
+    if (!P::handle(ctx, st, m, resp)) bad_type = true;  // agents.py:140-143
   }
   if constexpr (P::BATCHED) {
     if (has_ctx && first != INF) P::batch_end(ctx, st, resp);
@@ -353,6 +399,7 @@ template <class P>
 struct WideBlock {
   WideSmem<P>* sm;
   WQueue q[3];  // 0 acting phase, 1 / 2 response rounds
+  uint32_t flat_off;
 };
 
 template <class P>
@@ -361,6 +408,7 @@ __device__ __forceinline__ void wide_setup(const WideArgs<P>& a, int slot, int e
   WideSmem<P>& sm = *reinterpret_cast<WideSmem<P>*>(wide_raw);
   const uint32_t dyn = (uint32_t)((sizeof(WideSmem<P>) + 15) & ~(size_t)15);
   wb.sm = &sm;
+  wb.flat_off = dyn + (uint32_t)a.lay.off_flat;
 #pragma unroll
   for (int q = 0; q < 3; ++q) {
     wb.q[q].pay = dyn + (uint32_t)a.lay.off_pay[q];
@@ -552,7 +600,7 @@ __device__ __forceinline__ void wide_step_body(const WideArgs<P>& a) {
       const WQueue qc = round == 0 ? wb.q[0] : ((round - 1) & 1) ? wb.q[2] : wb.q[1];
       const WQueue qn = (round & 1) ? wb.q[2] : wb.q[1];
       pending = wide_round<P, TRACK>(a, ctx, st, has_ctx, qc, qn, sm, round, fault_key, traced, row,
-                                     trace_lane);
+                                     trace_lane, wb.flat_off);
     }
     if (trace_lane) a.trace.cnt[row] = traced;
 
