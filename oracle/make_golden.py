@@ -345,6 +345,7 @@ def gen_simple_market_handler_reference() -> None:
 
 
 FSM_HANDLER_FUZZ_CASES = 40
+FSM_WIDE_FUZZ_CASES = 16
 
 
 def gen_fsm_handler_fuzz_reference() -> None:
@@ -372,6 +373,13 @@ def gen_fsm_handler_fuzz_reference() -> None:
         json.dump(out, f, separators=(",", ":"))
     raised = sorted(int(s) for s, t in out.items() if t[-1][0] == "raise")
     print("fsm_compound_fuzz_reference.json", len(out), "cases; raising:", raised)
+    # ... and on env classes wider than a warp (33..120 agents): the block engine's fixture
+    out = {str(s): kats.run_random_handler_fsm(K, s, wide=True) for s in range(FSM_WIDE_FUZZ_CASES)}
+    with open(os.path.join(GOLDEN, "fsm_wide_fuzz_reference.json"), "w") as f:
+        json.dump(out, f, separators=(",", ":"))
+    raised = sorted(int(s) for s, t in out.items() if t[-1][0] == "raise")
+    print("fsm_wide_fuzz_reference.json", len(out), "cases; raising:", raised,
+          "bytes:", os.path.getsize(os.path.join(GOLDEN, "fsm_wide_fuzz_reference.json")))
 
 
 def gen_digital_ads_reference(only=slice(None)) -> None:

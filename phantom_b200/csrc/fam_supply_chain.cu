@@ -1568,10 +1568,9 @@ struct ScProgram {
       const int ask = min(__float2int_rn(a0), sp.iparams[1] - st[0]);  // supply_chain.py:136-142
       out.send(sp.agent_iparam[c.slot][0], SC_STOCK_REQUEST, ask);
     } else if (c.kind == SC_CUSTOMER) {  // supply_chain.py:61-67
-      const int want = rng_packed_randint(sp.seed, c.env_id, c.episode, (uint32_t)c.step,
-                                          SC_STREAM_ORDER, (uint32_t)sp.iparams[0],
-                                          (uint32_t)sp.iparams[2], (uint32_t)sp.iparams[3],
-                                          (uint32_t)sp.agent_iparam[c.slot][1]);
+      const int want = c.packed_randint(SC_STREAM_ORDER, (uint32_t)sp.iparams[0],
+                                        (uint32_t)sp.iparams[2], (uint32_t)sp.iparams[3],
+                                        (uint32_t)sp.agent_iparam[c.slot][1]);
       out.send(sp.agent_iparam[c.slot][0], SC_ORDER_REQUEST, want);
     }
   }

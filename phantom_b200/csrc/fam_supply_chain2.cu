@@ -20,6 +20,9 @@
 // RNG: stream 0 order size, stream 4 shop choice (idx = customer ordinal); stream 3 samplers
 // (step 0, idx = position in the env's sampler list).
 #include "phx_engine_host.cuh"
+#ifndef PHX_JIT_TU
+#include "phx_engine_wide_host.cuh"
+#endif
 
 namespace phx {
 namespace {
@@ -36,6 +39,7 @@ struct Sc2Program {
                        ACT_DIM = 1, Q1CAP = 8;
   static constexpr int RECVCAP = 8;  // max messages one agent receives in a round
   static constexpr bool BATCHED = false, HAS_PRE = true, HAS_POST = false;
+  static constexpr bool WIDE_OK = true;  // every callback is a template over the context type
 
   static int q1_cap(const phx_spec& s) { return s.n_agents; }
 
@@ -56,9 +60,9 @@ struct Sc2Program {
     return __hiloint2double(st[5], st[4]);
   }
 
-  template <class E>
-  __device__ static void act(const Ctx& c, int* st, bool has_action, const float* action, E& out) {
-    const EngineSpec& sp = *c.spec;
+  template <class C, class E>
+  __device__ static void act(const C& c, int* st, bool has_action, const float* action, E& out) {
+    const auto& sp = *c.spec;
     if (c.kind == S2_SHOP) {
       if (!has_action) return;
       const float a0 = action[0];
@@ -74,14 +78,17 @@ struct Sc2Program {
       out.send(sp.iparams[3 + pick], S2_ORDER_REQUEST, size);
     }
   }
-  __device__ static void view(const Ctx&, const int*, int*) {}
-  __device__ static void pre(const Ctx& c, int* st) {
+  template <class C>
+  __device__ static void view(const C&, const int*, int*) {}
+  template <class C>
+  __device__ static void pre(const C& c, int* st) {
     if (c.kind == S2_SHOP) st[1] = st[2] = 0;
   }
-  __device__ static void post(const Ctx&, int*) {}
+  template <class C>
+  __device__ static void post(const C&, int*) {}
 
-  template <class E>
-  __device__ static bool handle(const Ctx& c, int* st, const Msg& m, E& out) {
+  template <class C, class E>
+  __device__ static bool handle(const C& c, int* st, const Msg& m, E& out) {
     if (c.kind == S2_SHOP) {
       if (m.type == S2_STOCK_RESPONSE) {
         st[3] = m.p[0];
@@ -106,8 +113,9 @@ struct Sc2Program {
     return m.type == S2_ORDER_RESPONSE;
   }
 
-  __device__ static bool encode(const Ctx& c, int* st, float* obs) {
-    const EngineSpec& sp = *c.spec;
+  template <class C>
+  __device__ static bool encode(const C& c, int* st, float* obs) {
+    const auto& sp = *c.spec;
     const float cap = (float)(sp.iparams[9] * sp.iparams[0]);  // n_customers * max_order
     obs[0] = __fdiv_rn((float)st[0], (float)sp.iparams[1]);
     obs[1] = __fdiv_rn((float)st[1], cap);
@@ -115,17 +123,21 @@ struct Sc2Program {
     obs[3] = (float)__ddiv_rn(weight(st), sp.dparams[0]);  // float32(type.w / MAX_W), float64 division
     return true;
   }
-  __device__ static float reward(const Ctx&, int* st) {
+  template <class C>
+  __device__ static float reward(const C&, int* st) {
     // sales - type.excess_stock_weight * stock in float64, two roundings (no contraction)
     return (float)__dsub_rn((double)st[1], __dmul_rn(weight(st), (double)st[0]));
   }
-  __device__ static bool terminated(const Ctx&, const int*) { return false; }
-  __device__ static bool truncated(const Ctx&, const int*) { return false; }
+  template <class C>
+  __device__ static bool terminated(const C&, const int*) { return false; }
+  template <class C>
+  __device__ static bool truncated(const C&, const int*) { return false; }
 
-  __device__ static void reset_agent(const Ctx& c, int* st) {
+  template <class C>
+  __device__ static void reset_agent(const C& c, int* st) {
     if (c.kind != S2_SHOP) return;
     // Agent.reset(): self.type = self.supertype.sample() -- the env-managed sampler's value
-    const EngineSpec& sp = *c.spec;
+    const auto& sp = *c.spec;
     const int idx = sp.agent_iparam[c.slot][2];
     double w = sp.agent_fparam[c.slot][0];
     if (idx >= 0) {  // UniformFloatSampler: low + (high - low) * u, u = d24 / 2^24, all float64
@@ -142,7 +154,7 @@ struct Sc2Program {
 }  // namespace
 
 #ifndef PHX_JIT_TU  // a specialised translation unit only needs the program above
-Family* make_supply_chain2_family(const phx_spec&) { return new EngineFamily<Sc2Program>(); }
+Family* make_supply_chain2_family(const phx_spec& s) { return make_engine_family<Sc2Program>(s); }
 #endif
 
 }  // namespace phx

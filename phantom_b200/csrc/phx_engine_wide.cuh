@@ -19,8 +19,7 @@
 // WCtx offers has_neighbour / next_neighbour / next_of_kind like Ctx does.
 // Env-level words (ENVW / env_post, see phx_engine.cuh) are kept by every lane; env_post reads
 // other agents' state through a copy of all state words in shared memory.
-// Not carried over (loud PHX_ERR_UNSUPPORTED at create): the collective resolve hook,
-// shuffle_batches, run-time specialisation.
+// Not carried over: the collective resolve hook and run-time specialisation.
 #pragma once
 #include <cstddef>
 
@@ -177,6 +176,7 @@ struct WideLayout {  // byte offsets into the dynamic shared memory of a block
   int act_total, resp_total;
   int off_pay[3], off_head[3];
   int off_flat;  // uint32 [max(act_total, resp_total)]: the round's queue in push order
+  int off_list;  // uint16 [max(act_total, resp_total)]: shuffle_batches: the receivers' batch lists
   int bytes;
 };
 __host__ __device__ inline WideLayout wide_layout_rt(int pw, int act_total, int resp_total) {
@@ -195,6 +195,8 @@ __host__ __device__ inline WideLayout wide_layout_rt(int pw, int act_total, int 
   }
   l.off_flat = at;
   at += 4 * (act_total > resp_total ? act_total : resp_total);
+  l.off_list = at;
+  at += (2 * (act_total > resp_total ? act_total : resp_total) + 3) & ~3;
   l.bytes = at;
   return l;
 }
@@ -258,6 +260,25 @@ __device__ __forceinline__ uint32_t wide_min(uint32_t v, uint32_t* red) {
   __syncthreads();
   return s;
 }
+// exclusive prefix sum of v over the block's lanes (slot order) and the block total
+__device__ __forceinline__ int wide_excl_scan(int v, int32_t* red, int& total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int incl = v;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const int u = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+    if (lane >= off) incl += u;
+  }
+  if (lane == 31) red[warp] = incl;
+  __syncthreads();
+  int woff = 0;
+#pragma unroll
+  for (int w = 0; w < WIDE_MW; ++w)
+    if (w < warp) woff += red[w];
+  total = red[0] + red[1] + red[2] + red[3];
+  __syncthreads();  // `red` may be rewritten right away
+  return woff + incl - v;
+}
 __device__ __forceinline__ int wide_popc(const uint32_t* m) {
   return __popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]);
 }
@@ -291,9 +312,10 @@ template <class P, bool TRACK>
 __device__ __forceinline__ int wide_round(const WideArgs<P>& a, const WCtx& ctx, int* st,
                                           bool has_ctx, const WQueue& qc, const WQueue& qn, WideSmem<P>& sm,
                                           int round, uint32_t& fault_key, int& traced, size_t row,
-                                          bool trace_lane, uint32_t flat_off) {
+                                          bool trace_lane, uint32_t flat_off, uint32_t list_off,
+                                          int& k_batch) {
   constexpr int INF = 0x7FFFFFFF;
-  const int slot = ctx.slot, lane = slot & 31, warp = slot >> 5;
+  const int slot = ctx.slot;
   WEmit<P::PW> resp{&qn, ctx.spec, slot, ctx.out_mask, 0, 0u};
   int first = INF;
   bool bad_type = false;
@@ -309,20 +331,9 @@ __device__ __forceinline__ int wide_round(const WideArgs<P>& a, const WCtx& ctx,
     seg_i = qc.order_at(slot);
     c_i = qc.cnt_of(seg_i);
   }
-  int incl = c_i;
-#pragma unroll
-  for (int off = 1; off < 32; off <<= 1) {
-    const int v = __shfl_up_sync(0xFFFFFFFFu, incl, off);
-    if (lane >= off) incl += v;
-  }
-  if (lane == 31) sm.red[warp] = incl;
-  __syncthreads();
-  int woff = 0;
-#pragma unroll
-  for (int w = 0; w < WIDE_MW; ++w)
-    if (w < warp) woff += sm.red[w];
-  const int tot = sm.red[0] + sm.red[1] + sm.red[2] + sm.red[3];
-  sm.pbase[slot] = (int16_t)(slot < nseg ? woff + incl - c_i : 0x7FFF);
+  int tot = 0;
+  const int pb = wide_excl_scan(c_i, sm.red, tot);
+  sm.pbase[slot] = (int16_t)(slot < nseg ? pb : 0x7FFF);
   sm.pseg[slot] = (uint8_t)seg_i;
   __syncthreads();
   uint32_t* flat = reinterpret_cast<uint32_t*>(wide_raw + flat_off);
@@ -344,19 +355,52 @@ __device__ __forceinline__ int wide_round(const WideArgs<P>& a, const WCtx& ctx,
   if constexpr (P::BATCHED) {
     if (has_ctx) P::batch_begin(ctx, st);
   }
-  for (int pos = 0; pos < tot; ++pos) {
-    const uint32_t f = flat[pos];
-    if ((int)(f & 0xFFu) != slot) continue;
-    if (first == INF) first = pos;  // first-arrival position of this receiver
-    if (!has_ctx) continue;         // done agent: mail dropped (resolvers.py:143-144)
+  auto deliver = [&](const uint32_t f) {
     const int seg = (int)((f >> 16) & 0xFFu), k = (int)(f >> 24);
-    if (!wbit(ctx.in_mask, seg)) continue;  // delivery-time edge filter (:146-148)
     Msg m;
     m.sender = seg;
     m.type = (int)((f >> 8) & 0xFFu);
     m.p[0] = qc.py(0, k, seg);
     m.p[1] = P::PW > 1 ? qc.py(P::PW > 1 ? 1 : 0, k, seg) : 0;
     if (!P::handle(ctx, st, m, resp)) bad_type = true;  // agents.py:140-143
+  };
+  // (TRACK = the FULL build of the kernel: message tracking and / or shuffle_batches; the lean
+  // build carries neither -- the shuffle path inlines the program's handlers a second time and
+  // cost the 122-agent market 33 % when it sat in the same kernel)
+  if (!TRACK || !(ctx.spec->flags & PHX_FLAG_SHUFFLE_BATCHES)) {
+    for (int pos = 0; pos < tot; ++pos) {
+      const uint32_t f = flat[pos];
+      if ((int)(f & 0xFFu) != slot) continue;
+      if (first == INF) first = pos;  // first-arrival position of this receiver
+      if (!has_ctx) continue;         // done agent: mail dropped (resolvers.py:143-144)
+      if (!wbit(ctx.in_mask, (int)((f >> 16) & 0xFFu))) continue;  // delivery-time edge filter (:146-148)
+      deliver(f);
+    }
+  } else {
+    // BatchResolver(shuffle_batches=True), resolvers.py:146-151: the batch is first reduced to the
+    // messages whose edge still exists, then shuffled (the contract's Fisher-Yates, see
+    // shuffle_batch in phx_engine.cuh), then handled.  The receivers' lists share one array of
+    // `tot` entries: count, block scan for the offsets, fill, shuffle in place.
+    int n_mine = 0;
+    for (int pos = 0; pos < tot; ++pos) {
+      const uint32_t f = flat[pos];
+      if ((int)(f & 0xFFu) != slot) continue;
+      if (first == INF) first = pos;
+      n_mine += has_ctx && wbit(ctx.in_mask, (int)((f >> 16) & 0xFFu));
+    }
+    int all = 0;
+    const int off = wide_excl_scan(n_mine, sm.red, all);
+    uint16_t* list = reinterpret_cast<uint16_t*>(wide_raw + list_off) + off;
+    if (n_mine > 0) {
+      int j = 0;
+      for (int pos = first; j < n_mine; ++pos) {
+        const uint32_t f = flat[pos];
+        if ((int)(f & 0xFFu) == slot && wbit(ctx.in_mask, (int)((f >> 16) & 0xFFu)))
+          list[j++] = (uint16_t)pos;
+      }
+      shuffle_list(ctx.spec->seed, ctx.env_id, ctx.episode, ctx.step, slot, list, n_mine, k_batch);
+      for (j = 0; j < n_mine; ++j) deliver(flat[list[j]]);
+    }
   }
   if constexpr (P::BATCHED) {
     if (has_ctx && first != INF) P::batch_end(ctx, st, resp);
@@ -399,7 +443,7 @@ template <class P>
 struct WideBlock {
   WideSmem<P>* sm;
   WQueue q[3];  // 0 acting phase, 1 / 2 response rounds
-  uint32_t flat_off;
+  uint32_t flat_off, list_off;
 };
 
 template <class P>
@@ -409,6 +453,7 @@ __device__ __forceinline__ void wide_setup(const WideArgs<P>& a, int slot, int e
   const uint32_t dyn = (uint32_t)((sizeof(WideSmem<P>) + 15) & ~(size_t)15);
   wb.sm = &sm;
   wb.flat_off = dyn + (uint32_t)a.lay.off_flat;
+  wb.list_off = dyn + (uint32_t)a.lay.off_list;
 #pragma unroll
   for (int q = 0; q < 3; ++q) {
     wb.q[q].pay = dyn + (uint32_t)a.lay.off_pay[q];
@@ -572,7 +617,7 @@ __device__ __forceinline__ void wide_step_body(const WideArgs<P>& a) {
     int pending = wide_sum(out.n, sm.red);
 
     int traced = 0;
-    const bool trace_lane = TRACK && slot == 0;
+    const bool trace_lane = TRACK && slot == 0 && a.trace.rows != nullptr;
     if (trace_lane) {  // pushes of the acting phase, in global push order
       for (int si = 0; si < sp.n_agents; ++si)
         for (int k = 0; k < wb.q[0].cnt_of(si); ++k) {
@@ -591,6 +636,7 @@ __device__ __forceinline__ void wide_step_body(const WideArgs<P>& a) {
     if (has_ctx && resolves) P::pre(ctx, st);  // env.py:170-173
 
     // ---- BatchResolver.resolve (resolvers.py:128-163)
+    int k_batch = 0;  // batches this receiver has shuffled in this step (shuffle_batches only)
     for (int round = 0; pending > 0; ++round) {
       if (sp.round_limit >= 0 && round >= sp.round_limit) {  // resolvers.py:160-163
         fault_key = min(fault_key, ((uint32_t)(round + 1) << 16) | (0xFFu << 8) | PHX_FAULT_ROUND_LIMIT);
@@ -600,7 +646,7 @@ __device__ __forceinline__ void wide_step_body(const WideArgs<P>& a) {
       const WQueue qc = round == 0 ? wb.q[0] : ((round - 1) & 1) ? wb.q[2] : wb.q[1];
       const WQueue qn = (round & 1) ? wb.q[2] : wb.q[1];
       pending = wide_round<P, TRACK>(a, ctx, st, has_ctx, qc, qn, sm, round, fault_key, traced, row,
-                                     trace_lane, wb.flat_off);
+                                     trace_lane, wb.flat_off, wb.list_off, k_batch);
     }
     if (trace_lane) a.trace.cnt[row] = traced;
 

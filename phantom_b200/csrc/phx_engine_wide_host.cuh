@@ -30,7 +30,7 @@ struct WideProgramInfo {
   // segment capacity of one agent: (acting phase?, kind, degree in the full graph, n_agents)
   std::function<int(bool, int, int, int)> cap;
   const void* k_step = nullptr;          // wide_step_kernel<P, false> (or a cudaKernel_t)
-  const void* k_step_tracked = nullptr;  // wide_step_kernel<P, true>
+  const void* k_step_tracked = nullptr;  // wide_step_kernel<P, true>: tracking and / or shuffle_batches
   const void* k_reset = nullptr;         // wide_reset_kernel<P>
 };
 
@@ -50,8 +50,6 @@ class WideFamilyCore : public Family {
 
   // `info` is filled by the subclass before this runs.
   int32_t core_init(const phx_spec& s) {
-    PHX_REQUIRE(!(s.flags & PHX_FLAG_SHUFFLE_BATCHES), PHX_ERR_UNSUPPORTED,
-                "shuffle_batches is not available on the 128-lane block engine");
     int32_t rc = make_engine_spec(s, E, seed, env_offset, &wspec, info.nwords, info.envw);
     if (rc != PHX_OK) return rc;
     PHX_REQUIRE(s.obs_dim <= info.obs_dim, PHX_ERR_INVALID, "obs_dim exceeds the family's OBS_DIM");
@@ -178,8 +176,9 @@ class WideFamilyCore : public Family {
     }
     WideArgs<WideTag> a = make_args(T, io);
     void* args[] = {(void*)&a};
-    PHX_CUDA(cudaLaunchKernel(tracking() ? info.k_step_tracked : info.k_step, dim3(E), dim3(WIDE_G),
-                              args, smem, stream));
+    const bool full = tracking() || (spec.flags & PHX_FLAG_SHUFFLE_BATCHES) != 0;
+    PHX_CUDA(cudaLaunchKernel(full ? info.k_step_tracked : info.k_step, dim3(E), dim3(WIDE_G), args,
+                              smem, stream));
     return PHX_OK;
   }
 

@@ -552,7 +552,7 @@ ALL = [
 
 
 # ---------------------------------------------------------------- random handler-driven FSMs
-def random_handler_fsm(K, case_seed, compound=False, **kw):
+def random_handler_fsm(K, case_seed, compound=False, wide=False, **kw):
     """A random FiniteStateMachineEnv over the mock agents: 1-4 stages with random acting /
     rewarded sets, handler-less stages and stages with env handlers (`K.stage_handler`: always /
     clock / echo-agent counters after the handler's own resolve_network()), next_stages that
@@ -561,11 +561,14 @@ def random_handler_fsm(K, case_seed, compound=False, **kw):
     `case_seed`; used as a differential fuzz oracle-vs-reference (CPU) and device-vs-oracle (GPU).
     compound=True: most handlers are if / elif / else chains of up to four branches, each one or
     two comparisons between the clock, echo-agent counters and constants (a different draw
-    sequence, its own golden)."""
-    r = np.random.RandomState(case_seed + (1000 if compound else 0))
+    sequence, its own golden).
+    wide=True: 33..120 agents (12-49 strategic, 21-70 echo agents on a sparse random graph) -- env
+    classes wider than a warp, which run on the 128-lane block engine; compound handlers."""
+    r = np.random.RandomState(case_seed + (2000 if wide else 1000 if compound else 0))
     ph = K.ph
-    strat = [f"s{i}" for i in range(int(r.randint(1, 4)))]
-    echo = [f"e{i}" for i in range(int(r.randint(0, 4)))]
+    strat = [f"s{i}" for i in range(int(r.randint(12, 50) if wide else r.randint(1, 4)))]
+    echo = [f"e{i}" for i in range(int(r.randint(21, 71) if wide else r.randint(0, 4)))]
+    compound = compound or wide
     seeds = {e: int(r.choice([0, 0, 3, 4, 9])) for e in echo}
     agents = [K.MockStrategicAgent(a, num_steps=(int(r.randint(1, 7)) if r.uniform() < 0.3 else None))
               for a in strat]
@@ -574,7 +577,7 @@ def random_handler_fsm(K, case_seed, compound=False, **kw):
     network = ph.Network(agents)
     for i in range(len(echo)):
         for j in range(i + 1, len(echo)):
-            if r.uniform() < 0.6:
+            if r.uniform() < (0.05 if wide else 0.6):
                 network.add_connection(echo[i], echo[j])
     sids = [f"S{k}" for k in range(int(r.randint(1, 5)))]
     stages = []
@@ -638,10 +641,10 @@ def random_handler_fsm(K, case_seed, compound=False, **kw):
     return env, strat, echo
 
 
-def run_random_handler_fsm(K, case_seed, compound=False, prepare=None):
+def run_random_handler_fsm(K, case_seed, compound=False, prepare=None, wide=False):
     """Steps the random FSM to the end of its episode (or its first exception) and returns a
     plain-Python trace that is comparable across implementations."""
-    env, strat, echo = random_handler_fsm(K, case_seed, compound=compound)
+    env, strat, echo = random_handler_fsm(K, case_seed, compound=compound, wide=wide)
     if prepare is not None:
         prepare(env)
 

@@ -32,12 +32,7 @@ def test_kat_on_device(K, scenario, exec_mode, monkeypatch):
     lanes per env, and a 128-lane block per env (csrc/phx_engine_wide.cuh, forced here: it is
     what env classes of 33..128 agents run on)."""
     monkeypatch.setattr(K.ph.PhantomEnv, "default_exec_mode", exec_mode)
-    try:
-        env = scenario(K)
-    except Exception as exc:
-        if exec_mode == "wide" and "128-lane block engine" in str(exc):
-            pytest.skip(str(exc))  # shuffle_batches: stated limit of the block engine
-        raise
+    env = scenario(K)
     if env is not None:
         assert env.exec_name.startswith({"thread": "thread-per-env", "queue": "queue(G=",
                                          "wide": "wide(G=128)"}[exec_mode])
@@ -196,3 +191,26 @@ def test_compound_stage_rules_specialised(K, monkeypatch):
     for s in (0, 3, 4, 7, 11, 19, 34):
         got = json.loads(json.dumps(kats.run_random_handler_fsm(K, s, compound=True, prepare=prepare)))
         assert got == want[str(s)], f"compound case seed {s}"
+
+
+def test_wide_random_fsms_match_the_reference(K):
+    """16 random FSM env classes of 33..120 agents (12-49 strategic agents, 21-70 echo agents on a
+    sparse graph, compound stage handlers, invalid transitions, agents terminating mid-episode)
+    on the 128-lane block engine == the traces of the UNMODIFIED reference
+    (tests/golden/fsm_wide_fuzz_reference.json)."""
+    import json
+    import os
+
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden",
+                        "fsm_wide_fuzz_reference.json")
+    want = json.load(open(path))
+    seen = []
+
+    def prepare(env):
+        env._ensure_handle()
+        seen.append(env.exec_name)
+
+    for s in range(len(want)):
+        got = json.loads(json.dumps(kats.run_random_handler_fsm(K, s, wide=True, prepare=prepare)))
+        assert got == want[str(s)], f"wide case seed {s}"
+    assert seen and all(n == "wide(G=128)" for n in seen)

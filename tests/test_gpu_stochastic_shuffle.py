@@ -32,7 +32,8 @@ def test_market_with_shuffled_batches_matches_reference(golden_dir):
 
 
 @pytest.mark.parametrize("variant,exec_mode", [("shuffle", "queue"), ("plain", "queue"),
-                                               ("plain", "thread")])
+                                               ("plain", "thread"), ("shuffle", "wide"),
+                                               ("plain", "wide")])
 def test_stochastic_network_matches_reference(golden_dir, variant, exec_mode):
     """Every episode's graph, every step's outputs and state, and the message trace (which shows
     both the dropped deliveries and the shuffled batch order)."""
@@ -48,6 +49,7 @@ def test_stochastic_network_matches_reference(golden_dir, variant, exec_mode):
     seed, A, M = int(g["seed"]), g["actions"], g["action_mask"]
     env = make(num_envs=A.shape[0], seed=seed)
     assert ("thread" in env.exec_name) == (exec_mode == "thread")
+    assert ("wide" in env.exec_name) == (exec_mode == "wide")  # the 128-lane block engine, forced
     from .generic_parity import assert_device_step_equal
 
     for ep in range(A.shape[1]):
@@ -64,7 +66,7 @@ def test_stochastic_network_matches_reference(golden_dir, variant, exec_mode):
     run_device_trace_vs_golden(make, g, 4)
 
 
-@pytest.mark.parametrize("exec_mode", ["thread", "queue"])
+@pytest.mark.parametrize("exec_mode", ["thread", "queue", "wide"])
 def test_stochastic_network_auto_reset_and_sharding(exec_mode):
     """Auto-reset inside a rollout resamples the graphs exactly like explicit resets; results do
     not depend on how envs are split over handles; edge frequencies follow the rates."""

@@ -68,3 +68,9 @@ def test_random_handler_fsms_match_the_reference(K):
     for s in range(len(want)):
         got = json.loads(json.dumps(kats.run_random_handler_fsm(K, s, compound=True)))
         assert got == want[str(s)], f"compound case seed {s}"
+    # env classes wider than a warp: 33..120 agents
+    want = json.load(open(path.replace("fsm_handler_fuzz", "fsm_wide_fuzz")))
+    assert len(want) == 16
+    for s in range(len(want)):
+        got = json.loads(json.dumps(kats.run_random_handler_fsm(K, s, wide=True)))
+        assert got == want[str(s)], f"wide case seed {s}"
