@@ -132,6 +132,9 @@ typedef enum phx_rule_lhs {
   PHX_RULE_CONST = 4       /* right-hand sides only: the int32 constant `rhs`              */
 } phx_rule_lhs;
 typedef enum phx_cmp { PHX_CMP_LT = 0, PHX_CMP_LE, PHX_CMP_EQ, PHX_CMP_NE, PHX_CMP_GE, PHX_CMP_GT } phx_cmp;
+/* OR-ed into phx_rule_term.cmp: both operands are float32 values (a float32 state word, or the
+ * bits of a float32 constant in `rhs`) and are compared as such */
+#define PHX_CMP_F32 8
 
 /* handler == 2: the handler is an if / elif / ... / else chain.  Branch b holds when ALL of its
  * n_terms comparisons `<lhs operand> <cmp> <rhs operand>` hold (an operand is a phx_rule_lhs kind

@@ -346,6 +346,7 @@ def gen_simple_market_handler_reference() -> None:
 
 FSM_HANDLER_FUZZ_CASES = 40
 FSM_WIDE_FUZZ_CASES = 16
+FSM_FLOAT_FUZZ_CASES = 32
 
 
 def gen_fsm_handler_fuzz_reference() -> None:
@@ -373,6 +374,12 @@ def gen_fsm_handler_fuzz_reference() -> None:
         json.dump(out, f, separators=(",", ":"))
     raised = sorted(int(s) for s, t in out.items() if t[-1][0] == "raise")
     print("fsm_compound_fuzz_reference.json", len(out), "cases; raising:", raised)
+    # ... with float32 comparisons in the chains (an echo agent's float32 `level`)
+    out = {str(s): kats.run_random_handler_fsm(K, s, floats=True) for s in range(FSM_FLOAT_FUZZ_CASES)}
+    with open(os.path.join(GOLDEN, "fsm_float_fuzz_reference.json"), "w") as f:
+        json.dump(out, f, separators=(",", ":"))
+    raised = sorted(int(s) for s, t in out.items() if t[-1][0] == "raise")
+    print("fsm_float_fuzz_reference.json", len(out), "cases; raising:", raised)
     # ... and on env classes wider than a warp (33..120 agents): the block engine's fixture
     out = {str(s): kats.run_random_handler_fsm(K, s, wide=True) for s in range(FSM_WIDE_FUZZ_CASES)}
     with open(os.path.join(GOLDEN, "fsm_wide_fuzz_reference.json"), "w") as f:

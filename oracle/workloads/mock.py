@@ -68,7 +68,13 @@ def build_classes(ph):
             self.request_response = request_response
             self.handled_count = 0
             self.handled_total = 0
+            self.level = np.float32(0.0)  # float32 state: level * 0.5 + value per handled message
             self._slots = None  # filled by the env builder: agent id -> slot
+
+        def _bump(self, value):
+            self.handled_count += 1
+            self.handled_total += value
+            self.level = np.float32(self.level * np.float32(0.5) + np.float32(value))
 
         def generate_messages(self, ctx):
             if self.seed_value <= 0:
@@ -80,21 +86,18 @@ def build_classes(ph):
 
         @ph.agents.msg_handler(TestMessage)
         def on_test_message(self, ctx, message):
-            self.handled_count += 1
-            self.handled_total += message.payload.value
+            self._bump(message.payload.value)
             if message.payload.value > 1:
                 return [(message.sender_id, TestMessage(message.payload.value // 2))]
 
         @ph.agents.msg_handler(Request)
         def on_request(self, ctx, message):
-            self.handled_count += 1
-            self.handled_total += message.payload.cash
+            self._bump(message.payload.cash)
             return [(message.sender_id, Response(message.payload.cash // 2))]
 
         @ph.agents.msg_handler(Response)
         def on_response(self, ctx, message):
-            self.handled_count += 1
-            self.handled_total += message.payload.cash
+            self._bump(message.payload.cash)
             return []
 
     Box = __import__("oracle.phantom_oracle.spaces", fromlist=["Box"]).Box

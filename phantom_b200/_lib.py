@@ -33,6 +33,7 @@ PHX_OK, PHX_ERR_INVALID, PHX_ERR_CUDA, PHX_ERR_UNSUPPORTED, PHX_ERR_NO_DEVICE = 
 RULE_ALWAYS, RULE_STEP, RULE_AGENT_WORD, RULE_ENV_WORD, RULE_CONST = range(5)
 PHX_RULE_BRANCHES, PHX_RULE_TERMS = 4, 2
 CMP_LT, CMP_LE, CMP_EQ, CMP_NE, CMP_GE, CMP_GT = range(6)
+CMP_F32 = 8  # flag: the term compares float32 values
 # phx_env_kind
 ENV_BASE, ENV_FSM, ENV_STACKELBERG = 0, 1, 2
 # phx_family

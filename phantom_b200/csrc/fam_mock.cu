@@ -18,7 +18,9 @@
 //             reward = reward_functions.Constant (reward_functions.py:26-38)
 // Payload types: 0 = TestMessage(value), 1 = Request(cash), 2 = Response(cash) (int payloads).
 // State words:   0 encode_obs_count, 1 decode_action_count, 2 compute_reward_count,
-//                3 messages handled, 4 sum of handled payload values
+//                3 messages handled, 4 sum of handled payload values,
+//                5 echo agents: `level` (float32) = level * 0.5 + value per handled message,
+//                  float32 arithmetic with one rounding per operation (numpy float32 scalars)
 // agent_iparam[slot] = {agent.num_steps or -1, echo seed value, echo mode (0 halve/1 req-resp)}
 #include "phx_engine_host.cuh"
 #ifndef PHX_JIT_TU
@@ -35,7 +37,7 @@ struct MockProgram {
   // run-time specialisation (phx_jit.cuh): where this program lives and what it is called
   static constexpr const char* JIT_SOURCE = "fam_mock.cu";
   static constexpr const char* JIT_NAME = "MockProgram";
-  static constexpr int PW = 1, NWORDS = 5, VW = 0, ACTCAP = 32, RESPCAP = 32, OBS_DIM = 8,
+  static constexpr int PW = 1, NWORDS = 6, VW = 0, ACTCAP = 32, RESPCAP = 32, OBS_DIM = 8,
                        ACT_DIM = 1, Q1CAP = 32;
   static constexpr int RECVCAP = 32;  // max messages one agent receives in a round
   static constexpr bool BATCHED = false, HAS_PRE = false, HAS_POST = false;
@@ -84,6 +86,7 @@ struct MockProgram {
     if (c.kind != MK_ECHO) return false;  // no handler registered: ValueError (agents.py:140)
     st[3] += 1;
     st[4] += m.p[0];
+    st[5] = __float_as_int(__fadd_rn(__fmul_rn(__int_as_float(st[5]), 0.5f), (float)m.p[0]));
     if (m.type == MK_TEST_MESSAGE) {  // test_tracking.py:21-26
       if (m.p[0] > 1) out.send(m.sender, MK_TEST_MESSAGE, m.p[0] / 2);
       return true;

@@ -109,6 +109,17 @@ enum { SR_HANDLER = 0, SR_RESOLVES, SR_BRANCHES, SR_ELSE };
 enum { RT_LHS = 0, RT_SLOT, RT_WORD, RT_CMP, RT_RHS, RT_RHS_SLOT, RT_RHS_WORD };
 
 __device__ __forceinline__ bool rule_compare(int cmp, int lhs, int rhs) {
+  if (cmp & PHX_CMP_F32) {  // float32 operands (IEEE comparisons, as numpy's float32 scalars)
+    const float a = __int_as_float(lhs), b = __int_as_float(rhs);
+    switch (cmp & 7) {
+      case PHX_CMP_LT: return a < b;
+      case PHX_CMP_LE: return a <= b;
+      case PHX_CMP_EQ: return a == b;
+      case PHX_CMP_NE: return a != b;
+      case PHX_CMP_GE: return a >= b;
+      default: return a > b;
+    }
+  }
   switch (cmp) {
     case PHX_CMP_LT: return lhs < rhs;
     case PHX_CMP_LE: return lhs <= rhs;

@@ -120,7 +120,7 @@ inline int32_t make_engine_spec(const phx_spec& s, int32_t E, uint64_t seed, int
       d.rule_branch[k][b][1] = (int8_t)br[b].then;
       for (int j = 0; j < br[b].n_terms; ++j) {
         const phx_rule_term& t = br[b].term[j];
-        PHX_REQUIRE(t.cmp >= PHX_CMP_LT && t.cmp <= PHX_CMP_GT, PHX_ERR_INVALID,
+        PHX_REQUIRE((t.cmp & ~PHX_CMP_F32) >= PHX_CMP_LT && (t.cmp & ~PHX_CMP_F32) <= PHX_CMP_GT, PHX_ERR_INVALID,
                     "FSM stage rule: bad lhs / cmp");
         // `always` only as the single unconditional rule
         const bool always = t.lhs == PHX_RULE_ALWAYS && br[b].n_terms == 1;

@@ -90,6 +90,7 @@ class EchoAgent(ph.Agent):
 
     handled_count = device_column(3)
     handled_total = device_column(4)
+    level = device_column(5, dtype="float32")  # level * 0.5 + value per handled message (float32)
 
     def __init__(self, agent_id, seed_value: int = 0, request_response: bool = False):
         super().__init__(agent_id)

@@ -52,7 +52,10 @@ class StageRule:
           device_column attribute name of that agent's class or a state word index |
           ("env", word) for families with env-level words.
     cmp:  one of "<", "<=", "==", "!=", ">=", ">".
-    rhs:  an int32 constant, or another operand ("step" / ("agent", ...) / ("env", word)).
+    rhs:  an int32 constant, or another operand ("step" / ("agent", ...) / ("env", word)); for a
+          float32 device column: a float constant that is exactly representable in float32, or
+          another float32 column (the comparison is then made in float32, as between numpy
+          float32 scalars).
     also: a second comparison `(lhs, cmp, rhs)` that must hold as well (AND).
     elifs: further branches `(terms, stage)` tried in order when the first does not hold, `terms`
           one comparison `(lhs, cmp, rhs)` or a list of up to TERMS of them (AND).  OR is two

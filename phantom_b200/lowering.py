@@ -96,26 +96,36 @@ def _lower_stage_rule(out, sid, st, stage_ids, agents, slot) -> None:
             raise NotLowerableError("StageRule returns an unknown stage and no spare stage index is left")
 
     def operand(x, rhs):
-        """-> (kind, slot, word, constant) of one side of a comparison."""
+        """-> (kind, slot, word, constant, is_float32) of one side of a comparison."""
         if rhs and isinstance(x, (int, np.integer)) and not isinstance(x, bool):
             if not -2 ** 31 <= int(x) < 2 ** 31:
                 raise NotLowerableError(f"StageRule of stage '{sid}': rhs {x} is not an int32")
-            return L.RULE_CONST, 0, 0, int(x)
+            return L.RULE_CONST, 0, 0, int(x), False
+        if rhs and isinstance(x, (float, np.floating)):
+            # compared as float32 on the device: the constant must BE a float32, or `<=` / `==`
+            # against the Python handler's float64 comparison could differ at that very value
+            if not np.isfinite(x) or float(np.float32(x)) != float(x):
+                raise NotLowerableError(
+                    f"StageRule of stage '{sid}': rhs {x!r} is not exactly representable in float32")
+            return L.RULE_CONST, 0, 0, int(np.float32(x).view(np.int32)), True
         if x == "step":
-            return L.RULE_STEP, 0, 0, 0
+            return L.RULE_STEP, 0, 0, 0, False
         if isinstance(x, tuple) and len(x) == 3 and x[0] == "agent":
             _, aid, column = x
             if aid not in slot:
                 raise NotLowerableError(f"StageRule of stage '{sid}': unknown agent '{aid}'")
+            is_f32 = False
             if isinstance(column, str):
                 desc = getattr(type(agents[slot[aid]]), column, None)
-                if not hasattr(desc, "word") or getattr(desc, "dtype", "int32") != "int32":
+                dname = np.dtype(getattr(desc, "dtype", "int32")).name if hasattr(desc, "word") else ""
+                if dname not in ("int32", "float32"):
                     raise NotLowerableError(
-                        f"StageRule of stage '{sid}': '{column}' is not an int32 device column of '{aid}'")
-                column = desc.word
-            return L.RULE_AGENT_WORD, slot[aid], int(column), 0
+                        f"StageRule of stage '{sid}': '{column}' is not an int32 / float32 device "
+                        f"column of '{aid}'")
+                column, is_f32 = desc.word, dname == "float32"
+            return L.RULE_AGENT_WORD, slot[aid], int(column), 0, is_f32
         if isinstance(x, tuple) and len(x) == 2 and x[0] == "env":
-            return L.RULE_ENV_WORD, 0, int(x[1]), 0
+            return L.RULE_ENV_WORD, 0, int(x[1]), 0, False
         side = "rhs" if rhs else "lhs"
         raise NotLowerableError(f"StageRule of stage '{sid}': unknown {side} {x!r}")
 
@@ -132,8 +142,13 @@ def _lower_stage_rule(out, sid, st, stage_ids, agents, slot) -> None:
             if lhs == "always":
                 t.lhs = L.RULE_ALWAYS
                 continue
-            t.lhs, t.slot, t.word, _ = operand(lhs, False)
-            t.rhs_kind, t.rhs_slot, t.rhs_word, t.rhs = operand(rhs, True)
+            t.lhs, t.slot, t.word, _, lf = operand(lhs, False)
+            t.rhs_kind, t.rhs_slot, t.rhs_word, t.rhs, rf = operand(rhs, True)
+            if lf != rf:  # an int32 word against a float (or the reverse): bits are not comparable
+                raise NotLowerableError(
+                    f"StageRule of stage '{sid}': {lhs!r} {cmp} {rhs!r} mixes int32 and float32 operands")
+            if lf:
+                t.cmp |= L.CMP_F32
 
 
 def lower(env, exec_mode: str = "auto", auto_reset: bool = False) -> L.PhxSpec:

@@ -552,7 +552,7 @@ ALL = [
 
 
 # ---------------------------------------------------------------- random handler-driven FSMs
-def random_handler_fsm(K, case_seed, compound=False, wide=False, **kw):
+def random_handler_fsm(K, case_seed, compound=False, wide=False, floats=False, **kw):
     """A random FiniteStateMachineEnv over the mock agents: 1-4 stages with random acting /
     rewarded sets, handler-less stages and stages with env handlers (`K.stage_handler`: always /
     clock / echo-agent counters after the handler's own resolve_network()), next_stages that
@@ -563,12 +563,17 @@ def random_handler_fsm(K, case_seed, compound=False, wide=False, **kw):
     two comparisons between the clock, echo-agent counters and constants (a different draw
     sequence, its own golden).
     wide=True: 33..120 agents (12-49 strategic, 21-70 echo agents on a sparse random graph) -- env
-    classes wider than a warp, which run on the 128-lane block engine; compound handlers."""
-    r = np.random.RandomState(case_seed + (2000 if wide else 1000 if compound else 0))
+    classes wider than a warp, which run on the 128-lane block engine; compound handlers.
+    floats=True: compound handlers whose comparisons may also be FLOAT32 ones -- an echo agent's
+    `level` (a float32 recurrence over the handled values) against a float constant or another
+    agent's level."""
+    r = np.random.RandomState(case_seed + (3000 if floats else 2000 if wide else 1000 if compound else 0))
     ph = K.ph
     strat = [f"s{i}" for i in range(int(r.randint(12, 50) if wide else r.randint(1, 4)))]
     echo = [f"e{i}" for i in range(int(r.randint(21, 71) if wide else r.randint(0, 4)))]
-    compound = compound or wide
+    compound = compound or wide or floats
+    if floats and not echo:
+        echo = ["e0"]
     seeds = {e: int(r.choice([0, 0, 3, 4, 9])) for e in echo}
     agents = [K.MockStrategicAgent(a, num_steps=(int(r.randint(1, 7)) if r.uniform() < 0.3 else None))
               for a in strat]
@@ -606,6 +611,11 @@ def random_handler_fsm(K, case_seed, compound=False, wide=False, **kw):
                         ["handled_count", "handled_total"][int(r.randint(2))])
 
             def term():
+                if floats and echo and r.uniform() < 0.5:  # a float32 comparison
+                    lvl = lambda: ("agent", echo[int(r.randint(len(echo)))], "level")
+                    consts = [0.5, 1.0, 1.5, 2.25, 3.0, 4.5, 6.75, 9.0]
+                    rhs = lvl() if r.uniform() < 0.3 else consts[int(r.randint(len(consts)))]
+                    return (lvl(), ["<", "<=", "==", "!=", ">=", ">"][int(r.randint(6))], rhs)
                 return (operand(False), ["<", "<=", "==", "!=", ">=", ">"][int(r.randint(6))],
                         operand(True))
 
@@ -641,10 +651,10 @@ def random_handler_fsm(K, case_seed, compound=False, wide=False, **kw):
     return env, strat, echo
 
 
-def run_random_handler_fsm(K, case_seed, compound=False, prepare=None, wide=False):
+def run_random_handler_fsm(K, case_seed, compound=False, prepare=None, wide=False, floats=False):
     """Steps the random FSM to the end of its episode (or its first exception) and returns a
     plain-Python trace that is comparable across implementations."""
-    env, strat, echo = random_handler_fsm(K, case_seed, compound=compound, wide=wide)
+    env, strat, echo = random_handler_fsm(K, case_seed, compound=compound, wide=wide, floats=floats)
     if prepare is not None:
         prepare(env)
 
@@ -666,7 +676,8 @@ def run_random_handler_fsm(K, case_seed, compound=False, prepare=None, wide=Fals
             {k: bool(v) for k, v in step.terminations.items()},
             {k: bool(v) for k, v in step.truncations.items()},
             [list(map(int, counts(env.agents[a]))) for a in strat],
-            [[int(env.agents[e].handled_count), int(env.agents[e].handled_total)] for e in echo]))
+            [[int(env.agents[e].handled_count), int(env.agents[e].handled_total)] +
+             ([float(env.agents[e].level)] if floats else []) for e in echo]))
         if step.terminations["__all__"] or step.truncations["__all__"]:
             break
     if hasattr(env, "close"):

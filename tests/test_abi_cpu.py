@@ -135,6 +135,27 @@ def test_lowering_fsm_stage_handlers():
         ph.StageRule("A", "step", "<", 1, otherwise="A", elifs=[(("step", "<", k), "A") for k in range(4)])
     with pytest.raises(ph.NotLowerableError):
         one_stage(ph.StageRule("A", "step", "<", ("agent", "nobody", 0), otherwise="A")).spec
+    # float32 comparisons: a float32 device column against a float32-exact constant / column
+    def echo_stage(handler):
+        agents = [mock.MockStrategicAgent("agent"), mock.EchoAgent("e")]
+        return ph.FiniteStateMachineEnv(
+            num_steps=1, network=ph.Network(agents), initial_stage="A",
+            stages=[ph.FSMStage(stage_id="A", acting_agents=["agent"], next_stages=["A"],
+                                handler=handler)])
+
+    t = echo_stage(ph.StageRule("A", ("agent", "e", "level"), "<=", 2.25, otherwise="A")
+                   ).spec.stages[0].rule_branch[0].term[0]
+    assert t.cmp == (L.CMP_LE | L.CMP_F32) and t.rhs_kind == L.RULE_CONST
+    assert np.array([t.rhs], np.int32).view(np.float32)[0] == np.float32(2.25)
+    t = echo_stage(ph.StageRule("A", ("agent", "e", "level"), ">", ("agent", "e", "level"),
+                                otherwise="A")).spec.stages[0].rule_branch[0].term[0]
+    assert t.cmp == (L.CMP_GT | L.CMP_F32) and t.rhs_kind == L.RULE_AGENT_WORD and t.rhs_word == 5
+    for bad in (ph.StageRule("A", ("agent", "e", "level"), "<", 0.1, otherwise="A"),      # not a float32
+                ph.StageRule("A", ("agent", "e", "level"), "<", 3, otherwise="A"),        # float vs int
+                ph.StageRule("A", ("agent", "e", "handled_count"), "<", 1.5, otherwise="A"),
+                ph.StageRule("A", "step", "<", 1.5, otherwise="A")):
+        with pytest.raises(ph.NotLowerableError):
+            echo_stage(bad).spec
     with pytest.raises(ph.NotLowerableError):
         one_stage(lambda env: "A").spec
     with pytest.raises(ph.NotLowerableError):

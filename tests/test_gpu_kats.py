@@ -171,6 +171,12 @@ def test_random_handler_fsms_match_the_reference(K, exec_mode, monkeypatch):
     for s in range(len(want)):
         got = json.loads(json.dumps(kats.run_random_handler_fsm(K, s, compound=True)))
         assert got == want[str(s)], f"compound case seed {s}"
+    # ... with FLOAT32 comparisons in the chains: an echo agent's float32 `level` (a recurrence
+    # over the handled values, one rounding per operation) against float constants / other levels
+    want = json.load(open(path.replace("fsm_handler_fuzz", "fsm_float_fuzz")))
+    for s in range(len(want)):
+        got = json.loads(json.dumps(kats.run_random_handler_fsm(K, s, floats=True)))
+        assert got == want[str(s)], f"float case seed {s}"
 
 
 def test_compound_stage_rules_specialised(K, monkeypatch):
@@ -191,6 +197,10 @@ def test_compound_stage_rules_specialised(K, monkeypatch):
     for s in (0, 3, 4, 7, 11, 19, 34):
         got = json.loads(json.dumps(kats.run_random_handler_fsm(K, s, compound=True, prepare=prepare)))
         assert got == want[str(s)], f"compound case seed {s}"
+    want = json.load(open(path.replace("fsm_compound_fuzz", "fsm_float_fuzz")))
+    for s in (1, 2, 5, 9, 17):
+        got = json.loads(json.dumps(kats.run_random_handler_fsm(K, s, floats=True, prepare=prepare)))
+        assert got == want[str(s)], f"float case seed {s}"
 
 
 def test_wide_random_fsms_match_the_reference(K):

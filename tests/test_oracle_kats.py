@@ -68,6 +68,12 @@ def test_random_handler_fsms_match_the_reference(K):
     for s in range(len(want)):
         got = json.loads(json.dumps(kats.run_random_handler_fsm(K, s, compound=True)))
         assert got == want[str(s)], f"compound case seed {s}"
+    # float32 comparisons (an echo agent's float32 `level`) next to the integer ones
+    want = json.load(open(path.replace("fsm_handler_fuzz", "fsm_float_fuzz")))
+    assert len(want) == 32
+    for s in range(len(want)):
+        got = json.loads(json.dumps(kats.run_random_handler_fsm(K, s, floats=True)))
+        assert got == want[str(s)], f"float case seed {s}"
     # env classes wider than a warp: 33..120 agents
     want = json.load(open(path.replace("fsm_handler_fuzz", "fsm_wide_fuzz")))
     assert len(want) == 16
