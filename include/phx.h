@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PHX_ABI_VERSION 6
+#define PHX_ABI_VERSION 7
 
 #define PHX_MAX_AGENTS 128  /* agent slots per env                                   */
 #define PHX_MAX_TYPES 16    /* payload types per env class                           */
@@ -173,6 +173,14 @@ typedef struct phx_stage {
   int32_t rule_then, rule_else;      /* stage indices                                    */
   int32_t rule_n_branches;           /* handler == 2: 1 .. PHX_RULE_BRANCHES             */
   phx_rule_branch rule_branch[PHX_RULE_BRANCHES];
+  /* The ORDER in which the stage's acting agents act.  The reference hands the user's list to
+   * _handle_acting_agents (FSMStage.acting_agents, phantom/fsm.py:276-277; StackelbergEnv's
+   * leader_agents / follower_agents, phantom/stackelberg.py:133-140), so the push order of a
+   * step's messages follows that list, not the network's agent order.  0 = slot order (the
+   * list is ascending in slot); else the n_act_order slots of `acting` in list order.
+   * PHX_ENV_STACKELBERG: stages[0] / stages[1] carry the leaders' / followers' order. */
+  int32_t n_act_order;
+  uint8_t act_order[PHX_MAX_AGENTS];
 } phx_stage;
 
 /* Flat description of one env class, lowered from the Python objects

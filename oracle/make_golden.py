@@ -347,6 +347,7 @@ def gen_simple_market_handler_reference() -> None:
 FSM_HANDLER_FUZZ_CASES = 40
 FSM_WIDE_FUZZ_CASES = 16
 FSM_FLOAT_FUZZ_CASES = 32
+FSM_ORDER_FUZZ_SEEDS = (1103, 1308, 1334, 1732, 1734, 2051, 2484, 2509, 2614, 2937, 2948, 3054, 3380)
 
 
 def gen_fsm_handler_fuzz_reference() -> None:
@@ -380,6 +381,14 @@ def gen_fsm_handler_fuzz_reference() -> None:
         json.dump(out, f, separators=(",", ":"))
     raised = sorted(int(s) for s, t in out.items() if t[-1][0] == "raise")
     print("fsm_float_fuzz_reference.json", len(out), "cases; raising:", raised)
+    # ... the float32 cases of a 2 500-seed device-vs-oracle campaign (tools/fuzz_campaign.py) whose
+    # outcome depends on the ORDER in which a stage's agents act: the reference walks
+    # FSMStage.acting_agents in list order (fsm.py:276-277), not in network order, and the echo
+    # agents' float32 `level` recurrence is sensitive to the order of a receiver's batch
+    out = {str(s): kats.run_random_handler_fsm(K, s, floats=True) for s in FSM_ORDER_FUZZ_SEEDS}
+    with open(os.path.join(GOLDEN, "fsm_order_fuzz_reference.json"), "w") as f:
+        json.dump(out, f, separators=(",", ":"))
+    print("fsm_order_fuzz_reference.json", len(out), "cases")
     # ... and on env classes wider than a warp (33..120 agents): the block engine's fixture
     out = {str(s): kats.run_random_handler_fsm(K, s, wide=True) for s in range(FSM_WIDE_FUZZ_CASES)}
     with open(os.path.join(GOLDEN, "fsm_wide_fuzz_reference.json"), "w") as f:

@@ -21,7 +21,7 @@ PHX_MAX_PARAMS = 16
 PHX_TRACE_WORDS = 4
 PHX_MAX_CODEC_OPS = 6
 PHX_MAX_BASE_CONNECTIONS = 528
-PHX_ABI_VERSION = 6
+PHX_ABI_VERSION = 7
 
 # phx_status
 PHX_OK, PHX_ERR_INVALID, PHX_ERR_CUDA, PHX_ERR_UNSUPPORTED, PHX_ERR_NO_DEVICE = 0, -1, -2, -3, -4
@@ -85,6 +85,8 @@ class PhxStage(C.Structure):
         ("rule_else", C.c_int32),
         ("rule_n_branches", C.c_int32),
         ("rule_branch", PhxRuleBranch * 4),
+        ("n_act_order", C.c_int32),
+        ("act_order", C.c_uint8 * PHX_MAX_AGENTS),
     ]
 
 

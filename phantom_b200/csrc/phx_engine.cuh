@@ -101,6 +101,13 @@ struct EngineSpecT {
   int8_t rule_term[PHX_MAX_STAGES][PHX_RULE_BRANCHES][PHX_RULE_TERMS][8];      // RT_*
   int32_t rule_rhs[PHX_MAX_STAGES][PHX_RULE_BRANCHES][PHX_RULE_TERMS];         // PHX_RULE_CONST
   uint8_t stage_allowed[PHX_MAX_STAGES];  // FSMStage.next_stages as a stage bitmask
+  // Acting ORDER per phase (FSM: stage; Stackelberg: 0 leaders' / 1 followers' turn; else 0): the
+  // reference walks the user's list (fsm.py:276-277, stackelberg.py:133-140), the push order of
+  // a step's mail follows it.  any_act_order == 0: every list is ascending in slot (the engines
+  // keep their slot-order loops); else the first n_act[ph] entries of act_order[ph].
+  uint8_t any_act_order;
+  uint8_t n_act[PHX_MAX_STAGES];
+  int8_t act_order[PHX_MAX_STAGES][MAXA];
 };
 using EngineSpec = EngineSpecT<ENGINE_MAX_AGENTS, uint32_t>;
 using WideSpec = EngineSpecT<PHX_MAX_AGENTS, WMask>;
@@ -946,9 +953,23 @@ __device__ __forceinline__ void engine_step_body(const EngineArgs<P>& a) {
       if (a.io.action_mask) has_next = a.io.action_mask[arow];
     }
     ts.qa.cnt[slot] = (uint8_t)out.n;
-    ts.qa.order[slot] = (uint8_t)slot;
-    ts.qa.ordcnt[slot] = (uint16_t)(slot | (out.n << 8));
-    if (slot == 0) ts.qa.nseg = sp.n_agents;
+    int n_acting_segs = sp.n_agents;
+    if (!sp.any_act_order) {  // agents act in slot order: segment i is the i-th visited
+      ts.qa.order[slot] = (uint8_t)slot;
+      ts.qa.ordcnt[slot] = (uint16_t)(slot | (out.n << 8));
+      if (slot == 0) ts.qa.nseg = sp.n_agents;
+    } else {  // the stage's own acting order: the segments are visited in list order
+      const int phase = sp.env_kind == PHX_ENV_FSM ? ctx.stage
+                        : sp.env_kind == PHX_ENV_STACKELBERG ? ((h.x & 1) == 1 ? 0 : 1) : 0;
+      n_acting_segs = sp.n_act[phase];
+      __syncwarp(tmask);  // the segment lengths of the other lanes
+      if (slot < n_acting_segs) {
+        const int o = sp.act_order[phase][slot];
+        ts.qa.order[slot] = (uint8_t)o;
+        ts.qa.ordcnt[slot] = (uint16_t)(o | (ts.qa.cnt[o] << 8));
+      }
+      if (slot == 0) ts.qa.nseg = n_acting_segs;
+    }
     if (out.fault) fault_key = min(fault_key, (0u << 16) | ((uint32_t)slot << 8) | out.fault);
     int pending = __reduce_add_sync(tmask, out.n);
     __syncwarp(tmask);
@@ -956,8 +977,8 @@ __device__ __forceinline__ void engine_step_body(const EngineArgs<P>& a) {
     int traced = 0;
     const bool trace_lane = TRACK && env_live && slot == 0;
     if (trace_lane) {  // pushes of the acting phase, in global push order
-      for (int si = 0; si < sp.n_agents; ++si)
-        for (int k = 0; k < ts.qa.cnt[si]; ++k) {
+      for (int oi = 0; oi < n_acting_segs; ++oi)
+        for (int si = ts.qa.order[oi], k = 0; k < ts.qa.cnt[si]; ++k) {
           if (traced < a.trace.cap)
             a.trace.rows[row * a.trace.cap + traced] =
                 make_int4((int)(((uint32_t)ts.qa.hd(k, si) << 8) | (uint32_t)si), ts.qa.py(0, k, si),

@@ -417,9 +417,8 @@ __device__ __forceinline__ void engine1_step_body(const EngineArgs<P>& a) {
     } else {
     int cur = 0;
     Emit1<P> out{sm, &sp, L, cur, tid, 0, 0u, 0, 0u};
-    PHX_AGENT_UNROLL
-    for (int s = 0; s < n; ++s) {
-      if (!((acting >> s) & 1u) || ((done >> s) & 1u)) continue;
+    auto act_one = [&](const int s) {
+      if (!((acting >> s) & 1u) || ((done >> s) & 1u)) return;
       bind(s);
       out.slot = s;
       out.out_mask = ctx.out_mask;
@@ -437,6 +436,15 @@ __device__ __forceinline__ void engine1_step_body(const EngineArgs<P>& a) {
       }
       P::act(ctx, st, has_action, act, out);
       store_state(s, st);
+    };
+    if (!sp.any_act_order) {  // slot order (the base env; stage lists that ascend in slot)
+      PHX_AGENT_UNROLL
+      for (int s = 0; s < n; ++s) act_one(s);
+    } else {  // the stage's own acting order (fsm.py:276-277, stackelberg.py:133-140)
+      const int phase = sp.env_kind == PHX_ENV_FSM ? h.z
+                        : sp.env_kind == PHX_ENV_STACKELBERG ? ((h.x & 1) == 1 ? 0 : 1) : 0;
+      const int n_act = sp.n_act[phase];
+      for (int i = 0; i < n_act; ++i) act_one(sp.act_order[phase][i]);
     }
     if (out.fault && !fault) fault = out.fault;
     int n_cur = out.n;

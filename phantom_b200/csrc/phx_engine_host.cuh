@@ -145,6 +145,32 @@ inline int32_t make_engine_spec(const phx_spec& s, int32_t E, uint64_t seed, int
   }
   mask_from(d.leaders, s.leaders);
   mask_from(d.followers, s.followers);
+  // acting order per phase (include/phx.h phx_stage.n_act_order)
+  const int n_phases = s.env_kind == PHX_ENV_FSM ? s.n_stages : s.env_kind == PHX_ENV_STACKELBERG ? 2 : 1;
+  for (int ph = 0; ph < n_phases && ph < PHX_MAX_STAGES; ++ph) {
+    const phx_stage& g = s.stages[ph];
+    const int na = s.env_kind == PHX_ENV_BASE ? 0 : g.n_act_order;
+    PHX_REQUIRE(na >= 0 && na <= s.n_agents, PHX_ERR_INVALID, "n_act_order out of range");
+    if (na == 0) {  // slot order
+      d.n_act[ph] = (uint8_t)s.n_agents;
+      for (int i = 0; i < s.n_agents; ++i) d.act_order[ph][i] = (int8_t)i;
+      continue;
+    }
+    const uint32_t* acting = s.env_kind == PHX_ENV_FSM ? g.acting : (ph == 0 ? s.leaders : s.followers);
+    uint32_t seen[PHX_MASK_WORDS] = {0, 0, 0, 0};
+    for (int i = 0; i < na; ++i) {
+      const int o = g.act_order[i];
+      PHX_REQUIRE(o < s.n_agents && mask_bit(acting, o) && !mask_bit(seen, o), PHX_ERR_INVALID,
+                  "act_order: every entry must be a distinct acting agent of the stage");
+      seen[o >> 5] |= 1u << (o & 31);
+      d.act_order[ph][i] = (int8_t)o;
+    }
+    int n_acting = 0;
+    for (int i = 0; i < s.n_agents; ++i) n_acting += mask_bit(acting, i);
+    PHX_REQUIRE(n_acting == na, PHX_ERR_INVALID, "act_order must list every acting agent of the stage");
+    d.n_act[ph] = (uint8_t)na;
+    d.any_act_order = 1;
+  }
   d.seed = seed;
   d.env_offset = (uint32_t)env_offset;
   for (int k = 0; k < PHX_MAX_PARAMS; ++k) {
@@ -211,6 +237,7 @@ inline std::string jit_spec_literal(const EngineSpec& d) {
   f(d.leaders); f(d.followers); f(d.seed); f(d.env_offset); f(d.iparams); f(d.fparams);
   f(d.dparams); f(d.agent_iparam); f(d.agent_fparam); f(d.codec_op); f(d.codec_val);
   f(d.stage_rule); f(d.rule_branch); f(d.rule_term); f(d.rule_rhs); f(d.stage_allowed);
+  f(d.any_act_order); f(d.n_act); f(d.act_order);
   o += "}";
   return o;
 }
@@ -254,6 +281,9 @@ bool build_static_plan(const phx_spec& s, StaticPlan* out, std::string* why) {
   if (s.n_agents > SPL_AGENTS) return fail("more than 8 agents");
   if (s.flags & (PHX_FLAG_STOCHASTIC_NETWORK | PHX_FLAG_SHUFFLE_BATCHES))
     return fail("per-env graphs / shuffled batches are data dependent");
+  if (s.env_kind != PHX_ENV_BASE)
+    for (int ph = 0; ph < PHX_MAX_STAGES; ++ph)
+      if (s.stages[ph].n_act_order > 0) return fail("a stage's acting order differs from slot order");
   StaticPlan& pl = *out;
   std::memset(&pl, 0, sizeof(pl));
   pl.n_phases = s.env_kind == PHX_ENV_FSM ? s.n_stages : s.env_kind == PHX_ENV_STACKELBERG ? 2 : 1;
@@ -418,6 +448,9 @@ class EngineFamily : public Family {
     if constexpr (HasCollective<P>::value) {  // the program's collective resolve (tile engine)
       const char* off = std::getenv("PHX_COLLECTIVE");
       collective_ok_ = !(off && off[0] == '0') && P::collective_ok(s);
+      if (s.env_kind != PHX_ENV_BASE)  // (the collective forms assume agents act in slot order)
+        for (int ph = 0; ph < PHX_MAX_STAGES; ++ph)
+          if (s.stages[ph].n_act_order > 0) collective_ok_ = false;
     }
     PHX_REQUIRE(s.obs_dim <= P::OBS_DIM, PHX_ERR_INVALID, "obs_dim exceeds the family's OBS_DIM");
     return PHX_OK;

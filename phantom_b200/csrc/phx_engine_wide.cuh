@@ -611,16 +611,26 @@ __device__ __forceinline__ void wide_step_body(const WideArgs<P>& a) {
     WEmit<P::PW> out{&wb.q[0], &sp, slot, ctx.out_mask, 0, 0u};
     if (has_ctx && acting) P::act(ctx, st, strategic && has_action_now, act, out);
     wb.q[0].cnt_of(slot) = (uint8_t)out.n;
-    wb.q[0].order_at(slot) = (uint8_t)slot;
-    if (slot == 0) wb.q[0].nseg_ref() = sp.n_agents;
+    // the segments are visited in the order the agents acted: slot order, or the stage's own
+    // list (fsm.py:276-277, stackelberg.py:133-140)
+    int n_acting_segs = sp.n_agents;
+    if (!sp.any_act_order) {
+      wb.q[0].order_at(slot) = (uint8_t)slot;
+    } else {
+      const int phase = sp.env_kind == PHX_ENV_FSM ? ctx.stage
+                        : sp.env_kind == PHX_ENV_STACKELBERG ? ((h.x & 1) == 1 ? 0 : 1) : 0;
+      n_acting_segs = sp.n_act[phase];
+      if (slot < n_acting_segs) wb.q[0].order_at(slot) = (uint8_t)sp.act_order[phase][slot];
+    }
+    if (slot == 0) wb.q[0].nseg_ref() = n_acting_segs;
     if (out.fault) fault_key = min(fault_key, (0u << 16) | ((uint32_t)slot << 8) | out.fault);
     int pending = wide_sum(out.n, sm.red);
 
     int traced = 0;
     const bool trace_lane = TRACK && slot == 0 && a.trace.rows != nullptr;
     if (trace_lane) {  // pushes of the acting phase, in global push order
-      for (int si = 0; si < sp.n_agents; ++si)
-        for (int k = 0; k < wb.q[0].cnt_of(si); ++k) {
+      for (int oi = 0; oi < n_acting_segs; ++oi)
+        for (int si = wb.q[0].order_at(oi), k = 0; k < wb.q[0].cnt_of(si); ++k) {
           if (traced < a.trace.cap)
             a.trace.rows[row * a.trace.cap + traced] =
                 make_int4((int)(((uint32_t)wb.q[0].hd(k, si) << 8) | (uint32_t)si),

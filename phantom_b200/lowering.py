@@ -151,6 +151,19 @@ def _lower_stage_rule(out, sid, st, stage_ids, agents, slot) -> None:
                 t.cmp |= L.CMP_F32
 
 
+def _lower_act_order(stage, ids, slot, what) -> None:
+    """The order in which a stage's agents act = the order of the user's list (the reference
+    hands it to _handle_acting_agents: fsm.py:276-277, stackelberg.py:133-140).  Stored only when
+    it differs from slot order (include/phx.h phx_stage.n_act_order)."""
+    slots = [slot[a] for a in ids]
+    if len(set(slots)) != len(slots):
+        raise NotLowerableError(f"{what}: an agent is listed twice")
+    if slots != sorted(slots):
+        stage.n_act_order = len(slots)
+        for i, v in enumerate(slots):
+            stage.act_order[i] = v
+
+
 def lower(env, exec_mode: str = "auto", auto_reset: bool = False) -> L.PhxSpec:
     from .fsm import FiniteStateMachineEnv
     from .stackelberg import StackelbergEnv
@@ -251,6 +264,7 @@ def lower(env, exec_mode: str = "auto", auto_reset: bool = False) -> L.PhxSpec:
                 _lower_stage_rule(spec.stages[k], sid, st, stage_ids, agents, slot)
             for aid in st.acting_agents:
                 L.set_mask(spec.stages[k].acting, slot[aid])
+            _lower_act_order(spec.stages[k], st.acting_agents, slot, f"acting_agents of stage '{sid}'")
             if st.rewarded_agents is None:
                 spec.stages[k].rewarded_is_none = 1
             else:
@@ -266,6 +280,8 @@ def lower(env, exec_mode: str = "auto", auto_reset: bool = False) -> L.PhxSpec:
             L.set_mask(spec.leaders, slot[aid])
         for aid in env.follower_agents:
             L.set_mask(spec.followers, slot[aid])
+        _lower_act_order(spec.stages[0], env.leader_agents, slot, "leader_agents")
+        _lower_act_order(spec.stages[1], env.follower_agents, slot, "follower_agents")
     else:
         spec.env_kind = L.ENV_BASE
     if spec.env_kind not in info.env_kinds:

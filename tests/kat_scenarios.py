@@ -531,6 +531,27 @@ def scenario_codec_composition(K):
     return env
 
 
+def scenario_stackelberg_acting_order(K):
+    """StackelbergEnv hands `leader_agents` to _handle_acting_agents as the user wrote it
+    (/root/reference/phantom/stackelberg.py:133-140, env.py:320-336): the leaders act in LIST
+    order, not in network order, and that is the push order of their messages.  e1 (listed
+    first) and e0 both message e2; e2's float32 `level` (level * 0.5 + value per handled message)
+    tells the two orders apart: [9, 3] then the reply 2 -> 5.75; network order would give 7.25."""
+    ph = K.ph
+    agents = [K.EchoAgent("e0", seed_value=3), K.EchoAgent("e1", seed_value=9), K.EchoAgent("e2"),
+              K.MockStrategicAgent("lead"), K.MockStrategicAgent("follow")]
+    network = ph.Network(agents)
+    network.add_connection("e0", "e2")
+    network.add_connection("e1", "e2")
+    env = ph.StackelbergEnv(4, K.finish_network(network), ["e1", "lead", "e0"], ["follow"])
+    env.reset()
+    env.step({"lead": np.array([0])})
+    levels = [float(np.asarray(env.agents[e].level).reshape(-1)[0]) for e in ("e0", "e1", "e2")]
+    assert levels == [1.0, 3.0, 5.75], levels
+    assert [int(np.asarray(env.agents[e].handled_count).reshape(-1)[0]) for e in ("e0", "e1", "e2")] == [1, 2, 3]
+    return env
+
+
 ALL = [
     scenario_env_step_with_done_dropout,
     scenario_is_terminated_truncated,
@@ -542,6 +563,7 @@ ALL = [
     scenario_fsm_invalid_transition_runtime,
     scenario_fsm_handler_state_driven,
     scenario_stackelberg,
+    scenario_stackelberg_acting_order,
     scenario_tracking_golden_vector,
     scenario_resolver_round_ordering,
     scenario_round_limit,

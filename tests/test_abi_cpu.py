@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_spec_layout_matches_compiled_struct():
     assert L.lib.phx_sizeof_spec() == C.sizeof(L.PhxSpec)
-    assert L.lib.phx_abi_version() == L.PHX_ABI_VERSION == 6
+    assert L.lib.phx_abi_version() == L.PHX_ABI_VERSION == 7
 
 
 def test_no_cpu_fallback():

@@ -177,6 +177,13 @@ def test_random_handler_fsms_match_the_reference(K, exec_mode, monkeypatch):
     for s in range(len(want)):
         got = json.loads(json.dumps(kats.run_random_handler_fsm(K, s, floats=True)))
         assert got == want[str(s)], f"float case seed {s}"
+    # ... and the cases of a 2 500-seed campaign whose outcome depends on the ORDER of
+    # FSMStage.acting_agents: the agents act in the user's list order (fsm.py:276-277), which
+    # decides the order of a receiver's batch and with it an order-sensitive float32 recurrence
+    want = json.load(open(path.replace("fsm_handler_fuzz", "fsm_order_fuzz")))
+    for s in want:
+        got = json.loads(json.dumps(kats.run_random_handler_fsm(K, int(s), floats=True)))
+        assert got == want[s], f"order case seed {s}"
 
 
 def test_compound_stage_rules_specialised(K, monkeypatch):

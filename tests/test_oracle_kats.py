@@ -39,7 +39,7 @@ def test_handler_kats_on_the_unmodified_reference():
         "K = mock.build_classes(ref_shim.import_reference())\n"
         "for f in (k.scenario_fsm_one_state_with_handler, k.scenario_fsm_invalid_transition_runtime,\n"
         "          k.scenario_fsm_handler_state_driven, k.scenario_fsm_one_state,\n"
-        "          k.scenario_fsm_odd_even_two_agents):\n"
+        "          k.scenario_fsm_odd_even_two_agents, k.scenario_stackelberg_acting_order):\n"
         "    f(K)\n"
         "print('reference ok')\n")
     out = subprocess.run([sys.executable, "-c", code], cwd=repo, capture_output=True, text=True,
@@ -74,6 +74,12 @@ def test_random_handler_fsms_match_the_reference(K):
     for s in range(len(want)):
         got = json.loads(json.dumps(kats.run_random_handler_fsm(K, s, floats=True)))
         assert got == want[str(s)], f"float case seed {s}"
+    # cases whose outcome depends on the order of FSMStage.acting_agents (fsm.py:276-277)
+    want = json.load(open(path.replace("fsm_handler_fuzz", "fsm_order_fuzz")))
+    assert len(want) == 13
+    for s in want:
+        got = json.loads(json.dumps(kats.run_random_handler_fsm(K, int(s), floats=True)))
+        assert got == want[s], f"order case seed {s}"
     # env classes wider than a warp: 33..120 agents
     want = json.load(open(path.replace("fsm_handler_fuzz", "fsm_wide_fuzz")))
     assert len(want) == 16
