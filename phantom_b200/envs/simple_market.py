@@ -133,6 +133,17 @@ def _collect(env, agents, spec) -> None:
         raise NotLowerableError(
             "simple-market device program: the sellers must act in the initial stage (a buyer "
             "that observes before any price was heard raises ValueError in the reference)")
+    # SellerAgent.decode_action prices `ctx.neighbour_ids` in the graph's own (insertion) order
+    # (market_agents.py:108-112), which is the push order of the Price messages; the device program
+    # walks a seller's neighbours in slot order, so the two must agree
+    for a in sellers:
+        order = [env.agents[n]._phx_slot for n in env.network.neighbours(a.id)]
+        if order != sorted(order):
+            raise NotLowerableError(
+                f"simple-market device program: the neighbours of seller '{a.id}' were connected in "
+                "an order that differs from the network's agent order; the reference would price "
+                "them in connection order.  Add the connections in agent order (e.g. "
+                "add_connections_between(buyer_ids, seller_ids) with buyer_ids in network order)")
     spec.iparams[0] = len(sellers)
     draw = 0
     for group in (buyers, sellers):

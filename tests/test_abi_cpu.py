@@ -369,3 +369,24 @@ def test_compound_stage_rule_unit_compiles(tmp_path):
                           capture_output=True, text=True)
     assert proc.returncode == 0, proc.stderr[-2000:]
     assert " 0 bytes stack frame" in proc.stderr, proc.stderr[-1500:]
+
+
+def test_simple_market_refuses_a_neighbour_order_the_device_would_not_reproduce():
+    """SellerAgent.decode_action walks ctx.neighbour_ids in the graph's insertion order
+    (market_agents.py:108-112); the device program walks slots.  A network whose connection
+    order differs from its agent order is refused at lowering, not mis-ordered silently."""
+    import phantom_b200 as ph
+    from phantom_b200.envs import simple_market as sm
+    from phantom_b200.utils.samplers import UniformFloatSampler
+
+    def build(first, second):
+        agents = [sm.BuyerAgent(b, 0.5, supertype=sm.BuyerSupertype(UniformFloatSampler(0.2, 0.2)))
+                  for b in ("b1", "b2")] + [sm.SellerAgent("s1")]
+        net = ph.Network(agents)
+        net.add_connection(first, "s1")
+        net.add_connection(second, "s1")
+        return sm.SimpleMarketEnv(num_steps=3, network=net)
+
+    assert build("b1", "b2").spec.n_agents == 3
+    with pytest.raises(ph.NotLowerableError, match="connected in an order"):
+        build("b2", "b1").spec
