@@ -34,7 +34,9 @@ def random_mock_env(K, case_seed, **kw):
                            request_response=bool(r.uniform() < 0.3)) for e in echo]
     agents = [agents[i] for i in r.permutation(len(agents))]
     round_limit = None if r.uniform() < 0.6 else int(r.randint(1, 5))
-    network = ph.Network(agents, ph.resolvers.BatchResolver(enable_tracking=True, round_limit=round_limit),
+    shuffle = bool(r.uniform() < 0.35)  # BatchResolver(shuffle_batches=True): the contract's Fisher-Yates
+    network = ph.Network(agents, ph.resolvers.BatchResolver(enable_tracking=True, round_limit=round_limit,
+                                                            shuffle_batches=shuffle),
                          ignore_connection_errors=bool(r.uniform() < 0.3))
     for i in range(len(echo)):
         for j in range(i + 1, len(echo)):
@@ -50,11 +52,22 @@ def random_mock_env(K, case_seed, **kw):
         everyone = list(r.permutation(strat + echo))
         cut = int(r.randint(1, len(everyone)))
         env = ph.StackelbergEnv(8, net, [str(x) for x in everyone[:cut]], [str(x) for x in everyone[cut:]], **kw)
-    return env, strat, echo
+    return env, strat, echo, shuffle
 
 
 def run_mock_env(K, case_seed):
-    env, strat, echo = random_mock_env(K, case_seed)
+    import contextlib
+
+    seed = 77 + case_seed
+    is_device = hasattr(K.ph.PhantomEnv, "default_exec_mode")
+    env, strat, echo, shuffle = random_mock_env(K, case_seed, **({"seed": seed} if is_device else {}))
+    clock, patch = None, contextlib.nullcontext()
+    if not is_device:  # the oracle / reference: np.random.shuffle -> the contract's shuffle
+        from oracle import harness
+
+        clock = harness.EpisodeClock([])
+        slot_of = {aid: i for i, aid in enumerate(env.agent_ids)}
+        patch = harness.patched_np_shuffle(seed, 0, clock, env, slot_of)
 
     def plain(d):
         return {k: (None if v is None else
@@ -69,12 +82,17 @@ def run_mock_env(K, case_seed):
                         int(getattr(p, "value", getattr(p, "cash", 0)))])
         return out
 
-    trace = []
+    trace = [("shuffle", shuffle)]
     try:
+      with patch:
+        if clock is not None:
+            clock.on_reset()
         obs, _ = env.reset()
         trace.append(("reset", plain(obs)))
         for t in range(8):
             env.network.resolver.clear_tracked_messages()
+            if clock is not None:
+                clock.on_step(env)
             step = env.step({a: np.array([0]) for a in strat})
             trace.append((
                 "step", plain(step.observations), plain(step.rewards),
@@ -106,7 +124,8 @@ def main():
     bad = []
     for s in range(a.first, a.first + a.count):
         want = json.loads(json.dumps(run_mock_env(KO, s)))
-        for mode in ("thread", "queue", "wide"):
+        # (shuffled batches need the per-receiver lists of the tile / block engines)
+        for mode in (("queue", "wide") if want[0][1] else ("thread", "queue", "wide")):
             KD.ph.PhantomEnv.default_exec_mode = mode
             try:
                 got = json.loads(json.dumps(run_mock_env(KD, s)))
