@@ -347,6 +347,7 @@ def gen_simple_market_handler_reference() -> None:
 FSM_HANDLER_FUZZ_CASES = 40
 FSM_WIDE_FUZZ_CASES = 16
 FSM_FLOAT_FUZZ_CASES = 32
+FSM_WAITING_FUZZ_CASES = 40
 FSM_ORDER_FUZZ_SEEDS = (1103, 1308, 1334, 1732, 1734, 2051, 2484, 2509, 2614, 2937, 2948, 3054, 3380)
 
 
@@ -389,6 +390,13 @@ def gen_fsm_handler_fuzz_reference() -> None:
     with open(os.path.join(GOLDEN, "fsm_order_fuzz_reference.json"), "w") as f:
         json.dump(out, f, separators=(",", ":"))
     print("fsm_order_fuzz_reference.json", len(out), "cases")
+    # ... handlers that do NOT resolve although mail was sent: the mail waits in the resolver for a
+    # later step's resolve_network() (fsm.py:280-283)
+    out = {str(s): kats.run_random_handler_fsm(K, s, waiting=True) for s in range(FSM_WAITING_FUZZ_CASES)}
+    with open(os.path.join(GOLDEN, "fsm_waiting_fuzz_reference.json"), "w") as f:
+        json.dump(out, f, separators=(",", ":"))
+    raised = sorted(int(s) for s, t in out.items() if t[-1][0] == "raise")
+    print("fsm_waiting_fuzz_reference.json", len(out), "cases; raising:", raised)
     # ... and on env classes wider than a warp (33..120 agents): the block engine's fixture
     out = {str(s): kats.run_random_handler_fsm(K, s, wide=True) for s in range(FSM_WIDE_FUZZ_CASES)}
     with open(os.path.join(GOLDEN, "fsm_wide_fuzz_reference.json"), "w") as f:

@@ -27,6 +27,8 @@ class UserFamily final : public Family {
     cudaFree(d_ocache);
     cudaFree(d_ocached);
     cudaFree(d_env);
+    cudaFree(d_carry);
+    cudaFree(d_carry_n);
     if (lib) cudaLibraryUnload(lib);
   }
 
@@ -78,6 +80,11 @@ class UserFamily final : public Family {
       PHX_CUDA(cudaMalloc(&d_env, sizeof(int32_t) * (size_t)E * envw));
       PHX_CUDA(cudaMemset(d_env, 0, sizeof(int32_t) * (size_t)E * envw));
     }
+    if (waiting_mail_possible(s)) {  // mail that waits across steps (see EngineFamily::init)
+      PHX_CUDA(cudaMalloc(&d_carry_n, sizeof(int32_t) * (size_t)E));
+      PHX_CUDA(cudaMemset(d_carry_n, 0, sizeof(int32_t) * (size_t)E));
+      PHX_CUDA(cudaMalloc(&d_carry, sizeof(int32_t) * (size_t)E * q1cap * (1 + pw)));
+    }
     {  // env header: episode becomes 0 on the first reset
       std::vector<int4> h((size_t)E, make_int4(0, -1, 0, 0));
       PHX_CUDA(cudaMemcpy(d_hdr, h.data(), sizeof(int4) * (size_t)E, cudaMemcpyHostToDevice));
@@ -120,6 +127,8 @@ class UserFamily final : public Family {
     a.io = io;
     a.faults = fault_sink();
     a.trace = trace_sink();
+    a.carry_n = d_carry_n;
+    a.carry = d_carry;
     return a;
   }
 
@@ -184,6 +193,8 @@ class UserFamily final : public Family {
   float* d_ocache = nullptr;
   uint32_t* d_ocached = nullptr;
   int32_t* d_env = nullptr;
+  int32_t* d_carry_n = nullptr;
+  int32_t* d_carry = nullptr;
 };
 
 // A user's program on the block engine: WideFamilyCore with the kernels of the cubin.

@@ -466,6 +466,11 @@ struct EngineArgs {
   StepIO io;
   FaultSink faults;
   TraceSink trace;
+  // thread-per-env engine, FSM env classes with a stage handler that does not resolve: the mail
+  // that WAITS for a later step's resolve_network() (fsm.py:280-283 -- the resolver's queue
+  // outlives the step), between launches.  nullptr = no such stage.
+  int32_t* carry_n;  // [E]
+  int32_t* carry;    // [E][qcap][1 + PW]  head (sender | recv << 8 | type << 16), payload words
 };
 
 // StochasticNetwork.resample_connectivity (network.py:439-448): base connection c of an env
@@ -1318,6 +1323,7 @@ __device__ __forceinline__ void engine_reset_body(const EngineArgs<P>& a, const 
       a.hdr[e] = h;
       a.term[e] = 0;
       a.trunc[e] = 0;
+      if (a.carry_n != nullptr) a.carry_n[e] = 0;  // Network.reset -> resolver.reset()
       if (sp.env_kind != PHX_ENV_BASE) a.reward_none[e] = sp.strategic_mask;  // _rewards = None
     }
 #pragma unroll

@@ -268,6 +268,20 @@ __device__ __forceinline__ void engine1_step_body(const EngineArgs<P>& a) {
     for (int w = 0; w < P::NWORDS; ++w) ST(w, slot) = st[w];
   };
 
+  // Mail that waits for a later step's resolve (a stage handler that does not call
+  // resolve_network(), fsm.py:280-283): the resolver's queue outlives the step in the reference.
+  // Here it stays in this thread's queue between steps and in HBM between launches.
+  int carry_cnt = 0, carry_q = 0;
+  if (a.carry != nullptr) {
+    carry_cnt = min(a.carry_n[e], a.qcap);
+    for (int i = 0; i < carry_cnt; ++i) {
+      const int32_t* src = a.carry + ((size_t)e * a.qcap + i) * (1 + P::PW);
+      QH(0, i) = src[0];
+#pragma unroll
+      for (int k = 0; k < P::PW; ++k) QP(0, i, k) = src[1 + k];
+    }
+  }
+
   for (int t = 0; t < a.T; ++t) {
     const size_t row = (size_t)t * sp.E + e;
     h.x += 1;  // env.py:252
@@ -415,8 +429,8 @@ __device__ __forceinline__ void engine1_step_body(const EngineArgs<P>& a) {
         default: route(std::integral_constant<int, 7>{}); break;
       }
     } else {
-    int cur = 0;
-    Emit1<P> out{sm, &sp, L, cur, tid, 0, 0u, 0, 0u};
+    int cur = carry_q;  // (0 unless mail is waiting: this step's sends go behind it)
+    Emit1<P> out{sm, &sp, L, cur, tid, 0, 0u, carry_cnt, 0u};
     auto act_one = [&](const int s) {
       if (!((acting >> s) & 1u) || ((done >> s) & 1u)) return;
       bind(s);
@@ -449,16 +463,24 @@ __device__ __forceinline__ void engine1_step_body(const EngineArgs<P>& a) {
     if (out.fault && !fault) fault = out.fault;
     int n_cur = out.n;
     int traced = 0;
-    if (TRACK && env_live) {
-      for (int i = 0; i < n_cur; ++i, ++traced)
+    if (TRACK && env_live) {  // this step's pushes (waiting mail was traced when it was pushed)
+      for (int i = carry_cnt; i < n_cur; ++i, ++traced)
         if (traced < a.trace.cap)
           a.trace.rows[row * a.trace.cap + traced] =
               make_int4(QH(cur, i), QP(cur, i, 0), P::PW > 1 ? QP(cur, i, P::PW > 1 ? 1 : 0) : 0, 0);
     }
 
-    if (!resolves && n_cur > 0) {  // the mail would wait for a later step's resolve
-      if (!fault) fault = PHX_FAULT_UNRESOLVED_MAIL;
+    if (!resolves && n_cur > 0) {  // the mail waits for a later step's resolve
+      if (a.carry != nullptr) {
+        carry_cnt = n_cur;
+        carry_q = cur;
+      } else if (!fault) {
+        fault = PHX_FAULT_UNRESOLVED_MAIL;
+      }
       n_cur = 0;
+    } else {
+      carry_cnt = 0;  // resolved below (or there was nothing)
+      carry_q = 0;
     }
 
     // ---- pre_message_resolution (env.py:170-173)
@@ -665,6 +687,7 @@ __device__ __forceinline__ void engine1_step_body(const EngineArgs<P>& a) {
       h.y += 1;
       h.z = sp.initial_stage;
       term = trunc = 0;
+      carry_cnt = carry_q = 0;  // Network.reset -> resolver.reset() drops waiting mail
       ctx.step = 0;
       ctx.episode = (uint32_t)h.y;
       ctx.stage = h.z;
@@ -744,6 +767,15 @@ __device__ __forceinline__ void engine1_step_body(const EngineArgs<P>& a) {
 
   // ---- write back
   if (env_live) {
+    if (a.carry != nullptr) {
+      a.carry_n[e] = carry_cnt;
+      for (int i = 0; i < carry_cnt; ++i) {
+        int32_t* dst = a.carry + ((size_t)e * a.qcap + i) * (1 + P::PW);
+        dst[0] = QH(carry_q, i);
+#pragma unroll
+        for (int k = 0; k < P::PW; ++k) dst[1 + k] = QP(carry_q, i, k);
+      }
+    }
     a.hdr[e] = h;
     a.term[e] = term;
     a.trunc[e] = trunc;

@@ -284,6 +284,10 @@ bool build_static_plan(const phx_spec& s, StaticPlan* out, std::string* why) {
   if (s.env_kind != PHX_ENV_BASE)
     for (int ph = 0; ph < PHX_MAX_STAGES; ++ph)
       if (s.stages[ph].n_act_order > 0) return fail("a stage's acting order differs from slot order");
+  if (s.env_kind == PHX_ENV_FSM)
+    for (int ph = 0; ph < s.n_stages; ++ph)
+      if (s.stages[ph].handler != 0 && s.stages[ph].rule_resolves == 0)
+        return fail("a stage handler does not resolve: mail may wait across steps");
   StaticPlan& pl = *out;
   std::memset(&pl, 0, sizeof(pl));
   pl.n_phases = s.env_kind == PHX_ENV_FSM ? s.n_stages : s.env_kind == PHX_ENV_STACKELBERG ? 2 : 1;
@@ -389,6 +393,15 @@ __global__ void engine_init_kernel(int E, int G, int4* hdr, int32_t* state, int 
   (void)state; (void)nwords; (void)G;
 }
 
+// Can mail wait for a later step's resolve?  Only under the FSM env, in a stage whose handler
+// does not call resolve_network() (fsm.py:280-283).
+inline bool waiting_mail_possible(const phx_spec& s) {
+  if (s.env_kind != PHX_ENV_FSM) return false;
+  for (int k = 0; k < s.n_stages && k < PHX_MAX_STAGES; ++k)
+    if (s.stages[k].handler != 0 && s.stages[k].rule_resolves == 0) return true;
+  return false;
+}
+
 // Family backed by the queue engine.  `Field` mapping: PHX_FIELD_FAMILY + w = state word w,
 // int32 [E, G] (slot-major inside an env).
 template <class P>
@@ -403,6 +416,8 @@ class EngineFamily : public Family {
     cudaFree(d_adj);
     cudaFree(d_base);
     cudaFree(d_env);
+    cudaFree(d_carry);
+    cudaFree(d_carry_n);
     if (jit_lib) cudaLibraryUnload(jit_lib);
   }
 
@@ -503,6 +518,13 @@ class EngineFamily : public Family {
       PHX_CUDA(cudaMalloc(&d_adj, sizeof(uint32_t) * n));
       PHX_CUDA(cudaMemset(d_adj, 0, sizeof(uint32_t) * n));
     }
+    // mail that waits across steps (a stage handler that does not resolve, fsm.py:280-283): kept
+    // by the thread-per-env engine; the tile engines fault with PHX_FAULT_UNRESOLVED_MAIL
+    if (thread_per_env && waiting_mail_possible(s)) {
+      PHX_CUDA(cudaMalloc(&d_carry_n, sizeof(int32_t) * (size_t)E));
+      PHX_CUDA(cudaMemset(d_carry_n, 0, sizeof(int32_t) * (size_t)E));
+      PHX_CUDA(cudaMalloc(&d_carry, sizeof(int32_t) * (size_t)E * qcap1 * (1 + P::PW)));
+    }
     engine_init_kernel<P><<<(E + 255) / 256, 256>>>(E, G, d_hdr, d_state, P::NWORDS);
     PHX_CUDA(cudaGetLastError());
     // constructor-time agent state (PhantomEnv.__init__ ends with agent.reset(), env.py:122-124)
@@ -549,6 +571,8 @@ class EngineFamily : public Family {
     a.io = io;
     a.faults = fault_sink();
     a.trace = trace_sink();
+    a.carry_n = d_carry_n;
+    a.carry = d_carry;
     return a;
   }
 
@@ -798,6 +822,8 @@ class EngineFamily : public Family {
   cudaLibrary_t jit_lib = nullptr;   // specialised build of the step kernel (load_specialised)
   cudaKernel_t jit_kernel = nullptr;
   int32_t* d_env = nullptr;   // [ENVW][E] env-level words (programs with ENVW > 0)
+  int32_t* d_carry_n = nullptr;  // waiting mail (thread-per-env engine, see init)
+  int32_t* d_carry = nullptr;
   uint32_t* d_adj = nullptr;  // StochasticNetwork only
   uint2* d_base = nullptr;
   int32_t n_base = 0;

@@ -574,7 +574,7 @@ ALL = [
 
 
 # ---------------------------------------------------------------- random handler-driven FSMs
-def random_handler_fsm(K, case_seed, compound=False, wide=False, floats=False, **kw):
+def random_handler_fsm(K, case_seed, compound=False, wide=False, floats=False, waiting=False, **kw):
     """A random FiniteStateMachineEnv over the mock agents: 1-4 stages with random acting /
     rewarded sets, handler-less stages and stages with env handlers (`K.stage_handler`: always /
     clock / echo-agent counters after the handler's own resolve_network()), next_stages that
@@ -588,8 +588,13 @@ def random_handler_fsm(K, case_seed, compound=False, wide=False, floats=False, *
     classes wider than a warp, which run on the 128-lane block engine; compound handlers.
     floats=True: compound handlers whose comparisons may also be FLOAT32 ones -- an echo agent's
     `level` (a float32 recurrence over the handled values) against a float constant or another
-    agent's level."""
-    r = np.random.RandomState(case_seed + (3000 if floats else 2000 if wide else 1000 if compound else 0))
+    agent's level.
+    waiting=True: float32 cases whose handlers may NOT call resolve_network() although the acting
+    agents sent mail -- the mail waits in the resolver for a later step's resolve
+    (fsm.py:280-283), together with whatever is pushed in between."""
+    r = np.random.RandomState(case_seed + (4000 if waiting else 3000 if floats else 2000 if wide
+                                           else 1000 if compound else 0))
+    floats = floats or waiting
     ph = K.ph
     strat = [f"s{i}" for i in range(int(r.randint(12, 50) if wide else r.randint(1, 4)))]
     echo = [f"e{i}" for i in range(int(r.randint(21, 71) if wide else r.randint(0, 4)))]
@@ -619,7 +624,7 @@ def random_handler_fsm(K, case_seed, compound=False, wide=False, floats=False, *
                                       next_stages=[then]))
             continue
         sends = any(seeds.get(a, 0) > 0 for a in acting)
-        resolve = True if sends else bool(r.uniform() < 0.5)
+        resolve = True if (sends and not waiting) else bool(r.uniform() < 0.5)
         cmp = ["<", "<=", "==", "!=", ">=", ">"][int(r.randint(6))]
         if compound and kind != "always" and r.uniform() < 0.75:
             def operand(rhs):
@@ -673,10 +678,13 @@ def random_handler_fsm(K, case_seed, compound=False, wide=False, floats=False, *
     return env, strat, echo
 
 
-def run_random_handler_fsm(K, case_seed, compound=False, prepare=None, wide=False, floats=False):
+def run_random_handler_fsm(K, case_seed, compound=False, prepare=None, wide=False, floats=False,
+                           waiting=False):
     """Steps the random FSM to the end of its episode (or its first exception) and returns a
     plain-Python trace that is comparable across implementations."""
-    env, strat, echo = random_handler_fsm(K, case_seed, compound=compound, wide=wide, floats=floats)
+    env, strat, echo = random_handler_fsm(K, case_seed, compound=compound, wide=wide, floats=floats,
+                                          waiting=waiting)
+    floats = floats or waiting
     if prepare is not None:
         prepare(env)
 

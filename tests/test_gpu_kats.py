@@ -120,17 +120,30 @@ def test_handler_driven_fsm_envs_diverge(K, exec_mode, monkeypatch):
 
 def test_handler_without_resolve_leaves_mail(K):
     """A stage handler that never calls resolve_network() while agents sent messages: the
-    reference keeps that mail queued for some later resolve; the device refuses (sticky fault,
-    RuntimeError) instead of silently dropping it."""
+    reference keeps that mail queued for some later resolve.  The thread-per-env engine (the
+    default for env classes of <= 8 agents) does too -- nothing is delivered, nothing is lost,
+    the queue grows until it overflows loudly; the tile engine refuses at the first such step
+    (sticky fault, RuntimeError) instead of silently dropping the mail."""
     import numpy as np
 
     ph = K.ph
-    network = ph.Network([K.MockStrategicAgent("s"), K.EchoAgent("a", seed_value=4), K.EchoAgent("b")])
-    network.add_connection("a", "b")
-    env = ph.FiniteStateMachineEnv(
-        num_steps=3, network=network, initial_stage="X",
-        stages=[ph.FSMStage(stage_id="X", acting_agents=["s", "a"], next_stages=["X"],
-                            handler=ph.StageRule("X", resolve_network=False))])
+
+    def build(**kw):
+        network = ph.Network([K.MockStrategicAgent("s"), K.EchoAgent("a", seed_value=4), K.EchoAgent("b")])
+        network.add_connection("a", "b")
+        return ph.FiniteStateMachineEnv(
+            num_steps=3, network=network, initial_stage="X",
+            stages=[ph.FSMStage(stage_id="X", acting_agents=["s", "a"], next_stages=["X"],
+                                handler=ph.StageRule("X", resolve_network=False))], **kw)
+
+    env = build()
+    assert env.exec_name.startswith("thread-per-env")
+    env.reset()
+    for _ in range(3):
+        env.step({"s": np.array([0])})
+    assert int(env.agents["b"].handled_count) == 0  # three messages wait, none was delivered
+    env.close()
+    env = build(exec_mode="queue")
     env.reset()
     with pytest.raises(RuntimeError, match="unresolved"):
         env.step({"s": np.array([0])})
@@ -231,3 +244,37 @@ def test_wide_random_fsms_match_the_reference(K):
         got = json.loads(json.dumps(kats.run_random_handler_fsm(K, s, wide=True, prepare=prepare)))
         assert got == want[str(s)], f"wide case seed {s}"
     assert seen and all(n == "wide(G=128)" for n in seen)
+
+
+def test_mail_that_waits_across_steps(K, monkeypatch):
+    """A stage handler that does not call resolve_network() leaves the step's mail in the
+    resolver; it is delivered -- behind it whatever was pushed in between -- by the next resolve
+    (fsm.py:280-283).  The thread-per-env engine keeps that queue between steps and launches
+    (EngineArgs.carry): 40 random FSMs == the traces of the UNMODIFIED reference
+    (tests/golden/fsm_waiting_fuzz_reference.json), generic and specialised builds.  The tile and
+    block engines still refuse loudly (PHX_FAULT_UNRESOLVED_MAIL)."""
+    import json
+    import os
+
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden",
+                        "fsm_waiting_fuzz_reference.json")
+    want = json.load(open(path))
+    monkeypatch.setattr(K.ph.PhantomEnv, "default_exec_mode", "thread")
+    for s in range(len(want)):
+        got = json.loads(json.dumps(kats.run_random_handler_fsm(K, s, waiting=True)))
+        assert got == want[str(s)], f"waiting case seed {s}"
+
+    def prepare(env):
+        env.specialise()
+
+    for s in (0, 1, 2, 3, 5, 8, 13, 21):
+        got = json.loads(json.dumps(kats.run_random_handler_fsm(K, s, waiting=True, prepare=prepare)))
+        assert got == want[str(s)], f"waiting case seed {s} (specialised)"
+    # a case in which mail really waits, on the tile engine: refused, not mis-delivered
+    monkeypatch.setattr(K.ph.PhantomEnv, "default_exec_mode", "queue")
+    differ = [s for s in range(len(want))
+              if json.loads(json.dumps(kats.run_random_handler_fsm(K, s, waiting=True))) != want[str(s)]]
+    assert differ, "no case exercised waiting mail"
+    for s in differ:
+        got = kats.run_random_handler_fsm(K, s, waiting=True)
+        assert got[-1][0] == "raise", (s, got[-1])

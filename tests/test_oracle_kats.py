@@ -80,6 +80,12 @@ def test_random_handler_fsms_match_the_reference(K):
     for s in want:
         got = json.loads(json.dumps(kats.run_random_handler_fsm(K, int(s), floats=True)))
         assert got == want[s], f"order case seed {s}"
+    # mail that waits across steps (handlers that do not resolve)
+    want = json.load(open(path.replace("fsm_handler_fuzz", "fsm_waiting_fuzz")))
+    assert len(want) == 40
+    for s in range(len(want)):
+        got = json.loads(json.dumps(kats.run_random_handler_fsm(K, s, waiting=True)))
+        assert got == want[str(s)], f"waiting case seed {s}"
     # env classes wider than a warp: 33..120 agents
     want = json.load(open(path.replace("fsm_handler_fuzz", "fsm_wide_fuzz")))
     assert len(want) == 16

@@ -45,6 +45,7 @@ def main():
     for variant, kw, modes, count in (("plain", {}, ("thread", "queue", "wide"), a.count),
                                       ("compound", {"compound": True}, ("thread", "queue", "wide"), a.count),
                                       ("float32", {"floats": True}, ("thread", "queue", "wide"), a.count),
+                                      ("waiting-mail", {"waiting": True}, ("thread",), a.count),
                                       ("wide", {"wide": True}, ("auto",), max(a.count // 5, 1))):
         bad = []
         for s in range(a.first, a.first + count):
