@@ -278,3 +278,29 @@ def test_mail_that_waits_across_steps(K, monkeypatch):
     for s in differ:
         got = kats.run_random_handler_fsm(K, s, waiting=True)
         assert got[-1][0] == "raise", (s, got[-1])
+    # inside ONE launch the waiting mail stays in shared memory between the steps, between
+    # launches it goes through HBM: a T-step rollout == T single-step launches (auto-reset on)
+    import numpy as np
+
+    from .generic_parity import assert_batchsteps_equal
+
+    monkeypatch.setattr(K.ph.PhantomEnv, "default_exec_mode", "thread")
+    checked = 0
+    for s in differ[:6]:
+        if want[str(s)][-1][0] == "raise":
+            continue
+        envs = [kats.random_handler_fsm(K, s, waiting=True, num_envs=64, seed=3, auto_reset=True)[0]
+                for _ in range(2)]
+        S = len(envs[0].strategic_agents)
+        A = np.zeros((20, 64, S, 1), np.float32)
+        for e in envs:
+            e.reset_batch()
+        ro = envs[0].rollout_batch(A)
+        for t in range(20):
+            out = envs[1].step_batch(A[t])
+            assert_batchsteps_equal(type(out)(*[x[t] for x in ro]), out, f"case {s} step {t}")
+        for e in envs:
+            e.check_errors()
+            e.close()
+        checked += 1
+    assert checked >= 2
