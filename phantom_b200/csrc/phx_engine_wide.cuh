@@ -177,6 +177,7 @@ struct WideLayout {  // byte offsets into the dynamic shared memory of a block
   int off_pay[3], off_head[3];
   int off_flat;  // uint32 [max(act_total, resp_total)]: the round's queue in push order
   int off_list;  // uint16 [max(act_total, resp_total)]: shuffle_batches: the receivers' batch lists
+  int off_mark;  // uint8  [max(act_total, resp_total)]: first-arrival marks of a round
   int bytes;
 };
 __host__ __device__ inline WideLayout wide_layout_rt(int pw, int act_total, int resp_total) {
@@ -197,6 +198,8 @@ __host__ __device__ inline WideLayout wide_layout_rt(int pw, int act_total, int 
   at += 4 * (act_total > resp_total ? act_total : resp_total);
   l.off_list = at;
   at += (2 * (act_total > resp_total ? act_total : resp_total) + 3) & ~3;
+  l.off_mark = at;
+  at += ((act_total > resp_total ? act_total : resp_total) + 3) & ~3;
   l.bytes = at;
   return l;
 }
@@ -238,6 +241,7 @@ struct WideSmem {
   int32_t red[WIDE_MW];
   uint32_t redu[WIDE_MW];
   int32_t bcast;
+  int32_t mark_part[2][WIDE_MW];  // compaction of the first-arrival marks (wide_round)
   int16_t pbase[WIDE_G];  // flattening a round's queue: first position of the i-th segment visited
   uint8_t pseg[WIDE_G];   // ... and its producer
   // programs with env-level words: every agent's state, published before env_post
@@ -313,7 +317,7 @@ __device__ __forceinline__ int wide_round(const WideArgs<P>& a, const WCtx& ctx,
                                           bool has_ctx, const WQueue& qc, const WQueue& qn, WideSmem<P>& sm,
                                           int round, uint32_t& fault_key, int& traced, size_t row,
                                           bool trace_lane, uint32_t flat_off, uint32_t list_off,
-                                          int& k_batch) {
+                                          uint32_t mark_off, int& k_batch) {
   constexpr int INF = 0x7FFFFFFF;
   const int slot = ctx.slot;
   WEmit<P::PW> resp{&qn, ctx.spec, slot, ctx.out_mask, 0, 0u};
@@ -348,6 +352,7 @@ __device__ __forceinline__ int wide_round(const WideArgs<P>& a, const WCtx& ctx,
     }
     const int seg = sm.pseg[lo], k = p - sm.pbase[lo];
     flat[p] = (uint32_t)qc.hd(k, seg) | ((uint32_t)seg << 16) | ((uint32_t)k << 24);
+    (wide_raw + mark_off)[p] = 0;  // first-arrival marks of this round (step 3)
   }
   __syncthreads();
 
@@ -405,22 +410,41 @@ __device__ __forceinline__ int wide_round(const WideArgs<P>& a, const WCtx& ctx,
   if constexpr (P::BATCHED) {
     if (has_ctx && first != INF) P::batch_end(ctx, st, resp);
   }
-  sm.first_idx[slot] = first;
+  // mark the position of this receiver's first message (a byte per position, cleared by the
+  // flattening pass; this lane is its only writer): the marked positions, compacted, are the
+  // next queue's segment order
+  uint8_t* marks = wide_raw + mark_off;
+  if (first != INF) marks[first] = 1;
   if (bad_type)
     fault_key = min(fault_key, ((uint32_t)(round + 1) << 16) | ((uint32_t)slot << 8) |
                                    PHX_FAULT_UNKNOWN_MSG_TYPE);
   if (resp.fault)
     fault_key = min(fault_key, ((uint32_t)(round + 1) << 16) | ((uint32_t)slot << 8) | resp.fault);
   qn.cnt_of(slot) = (uint8_t)resp.n;
-  const int total_next = wide_sum(resp.n, sm.red);  // (barrier: first_idx and qn are visible)
+  const int total_next = wide_sum(resp.n, sm.red);  // (barrier: the marks and qn are visible)
 
-  int rank = 0, nrecv = 0;
-  for (int j = 0; j < WIDE_G; ++j) {
-    const int fj = sm.first_idx[j];
-    nrecv += fj != INF;
-    rank += fj < first;
+  // next queue's segment order = the receivers by the position of their first message
+  // (resolvers.py:126,142: dict insertion order): compact the marked positions -- a ballot per
+  // warp, the four warp totals through shared memory (two buffers, one barrier per 128 positions)
+  int nrecv = 0;
+  {
+    const int lane = slot & 31, warp = slot >> 5;
+    for (int c0 = 0; c0 < tot; c0 += WIDE_G) {
+      const int p = c0 + slot;
+      const uint32_t f = p < tot ? flat[p] : 0u;
+      const bool mark = p < tot && marks[p] != 0;
+      const uint32_t b = __ballot_sync(0xFFFFFFFFu, mark);
+      int32_t* part = sm.mark_part[(c0 / WIDE_G) & 1];
+      if (lane == 0) part[warp] = __popc(b);
+      __syncthreads();
+      int woff = 0;
+#pragma unroll
+      for (int w = 0; w < WIDE_MW; ++w)
+        if (w < warp) woff += part[w];
+      if (mark) qn.order_at(nrecv + woff + __popc(b & ((1u << lane) - 1u))) = (uint8_t)(f & 0xFFu);
+      nrecv += part[0] + part[1] + part[2] + part[3];
+    }
   }
-  if (first != INF) qn.order_at(rank) = (uint8_t)slot;
   if (slot == 0) qn.nseg_ref() = nrecv;
   __syncthreads();
   if (TRACK && trace_lane) {
@@ -443,7 +467,7 @@ template <class P>
 struct WideBlock {
   WideSmem<P>* sm;
   WQueue q[3];  // 0 acting phase, 1 / 2 response rounds
-  uint32_t flat_off, list_off;
+  uint32_t flat_off, list_off, mark_off;
 };
 
 template <class P>
@@ -454,6 +478,7 @@ __device__ __forceinline__ void wide_setup(const WideArgs<P>& a, int slot, int e
   wb.sm = &sm;
   wb.flat_off = dyn + (uint32_t)a.lay.off_flat;
   wb.list_off = dyn + (uint32_t)a.lay.off_list;
+  wb.mark_off = dyn + (uint32_t)a.lay.off_mark;
 #pragma unroll
   for (int q = 0; q < 3; ++q) {
     wb.q[q].pay = dyn + (uint32_t)a.lay.off_pay[q];
@@ -656,7 +681,7 @@ __device__ __forceinline__ void wide_step_body(const WideArgs<P>& a) {
       const WQueue qc = round == 0 ? wb.q[0] : ((round - 1) & 1) ? wb.q[2] : wb.q[1];
       const WQueue qn = (round & 1) ? wb.q[2] : wb.q[1];
       pending = wide_round<P, TRACK>(a, ctx, st, has_ctx, qc, qn, sm, round, fault_key, traced, row,
-                                     trace_lane, wb.flat_off, wb.list_off, k_batch);
+                                     trace_lane, wb.flat_off, wb.list_off, wb.mark_off, k_batch);
     }
     if (trace_lane) a.trace.cnt[row] = traced;
 
