@@ -390,3 +390,28 @@ def test_simple_market_refuses_a_neighbour_order_the_device_would_not_reproduce(
     assert build("b1", "b2").spec.n_agents == 3
     with pytest.raises(ph.NotLowerableError, match="connected in an order"):
         build("b2", "b1").spec
+
+
+def test_lowering_keeps_the_acting_order_of_the_users_lists():
+    """FSMStage.acting_agents / leader_agents / follower_agents are walked in LIST order by the
+    reference (fsm.py:276-277, stackelberg.py:133-140): phx_stage.act_order carries a list that
+    is not ascending in slot, an ascending one is left at 0 (= slot order), a duplicate is refused."""
+    import phantom_b200 as ph
+    from phantom_b200.envs import mock
+
+    def agents():
+        return [mock.EchoAgent("e0"), mock.EchoAgent("e1"), mock.MockStrategicAgent("s")]
+
+    def fsm(order):
+        return ph.FiniteStateMachineEnv(
+            num_steps=2, network=ph.Network(agents()), initial_stage="A",
+            stages=[ph.FSMStage(stage_id="A", acting_agents=order, next_stages=["A"])])
+
+    st = fsm(["e1", "s", "e0"]).spec.stages[0]
+    assert st.n_act_order == 3 and list(st.act_order[:3]) == [1, 2, 0] and st.acting[0] == 0b111
+    assert fsm(["e0", "s"]).spec.stages[0].n_act_order == 0
+    with pytest.raises(ph.NotLowerableError, match="listed twice"):
+        fsm(["e0", "e0"]).spec
+    env = ph.StackelbergEnv(4, ph.Network(agents()), ["s", "e0"], ["e1"])
+    assert env.spec.stages[0].n_act_order == 2 and list(env.spec.stages[0].act_order[:2]) == [2, 0]
+    assert env.spec.stages[1].n_act_order == 0
