@@ -22,6 +22,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--dir", default=os.path.join(REPO, "tests", "_campaign"))
     ap.add_argument("--market", type=int, default=60)
+    ap.add_argument("--chain2", type=int, default=60)
     a = ap.parse_args()
     from tests.generic_parity import run_device_vs_golden
     from tests.test_gpu_digital_ads import ads_state
@@ -30,7 +31,7 @@ def main():
     from phantom_b200.envs import simple_market as sm
     from phantom_b200.utils.samplers import UniformFloatSampler
 
-    report = {"ads": [], "market": []}
+    report = {"ads": [], "market": [], "chain2": []}
     for path in sorted(glob.glob(os.path.join(a.dir, "ads_*.npz"))):
         g = np.load(path)
         counts = [int(x) for x in g["counts"]]
@@ -84,8 +85,49 @@ def main():
                 ok = False
                 print("MISMATCH market", c, n_buyers, n_sellers, mode, type(exc).__name__, str(exc)[:200], flush=True)
             report["market"].append((c, n_buyers, n_sellers, mode, ok))
+    # (c) the tutorial's multi-shop supply chain on a StochasticNetwork: random shop / customer
+    # counts (<= 8 agents: the family's domain), connection rates, shuffled batches or not
+    from oracle import rng
+    from oracle.workloads import supply_chain2 as w2
+    from phantom_b200.envs.supply_chain2 import SupplyChain2Env
+    from tests.test_gpu_supply_chain2 import shop_state
+
+    for c in range(a.chain2):
+        r = np.random.RandomState(11000 + c)
+        n_shops = int(r.randint(1, 4))
+        n_cust = int(r.randint(1, 8 - n_shops))
+        rates = (float(np.round(r.uniform(0.3, 1.0), 3)), float(np.round(r.uniform(0.2, 1.0), 3)))
+        shuffle = bool(r.uniform() < 0.5)
+        T, n_env, n_ep, seed = int(r.randint(5, 21)), 4, 2, 50000 + c
+        A = r.uniform(0, 100, size=(n_env, n_ep, T, n_shops, 1)).astype(np.float32)
+        M = (r.uniform(size=(n_env, n_ep, T, n_shops)) > 0.1).astype(np.uint8)
+        per_env = []
+        for e in range(n_env):
+            streams = {s: rng.StepStream(seed, e, s)
+                       for s in (w2.STREAM_ORDER, w2.STREAM_SAMPLER, w2.STREAM_SHOP_CHOICE, w2.STREAM_CONNECTIVITY)}
+            with harness.patched_np_uniform(streams[w2.STREAM_SAMPLER]), \
+                    harness.patched_np_random(streams[w2.STREAM_CONNECTIVITY]):
+                env = w2.build(po, streams, po.utils.samplers.UniformFloatSampler, n_shops=n_shops,
+                               n_customers=n_cust, num_steps=T, rates=rates, shuffle_batches=shuffle)
+                clock = harness.EpisodeClock(list(streams.values()))
+                slot_of = {aid: i for i, aid in enumerate(env.agent_ids)}
+                with harness.patched_np_shuffle(seed, e, clock, env, slot_of):
+                    per_env.append(harness.run_generic(env, clock, A[e], M[e], 4, state_fn=w2.state))
+        g = {k: np.stack([t[k] for t in per_env]) for k in per_env[0] if k != "messages"}
+        g.update(actions=A, action_mask=M, seed=np.int64(seed))
+        for mode in (["queue", "wide"] if shuffle else ["thread", "queue", "wide"]):
+            try:
+                run_device_vs_golden(lambda **kw: SupplyChain2Env(n_shops, n_cust, num_steps=T, rates=rates,
+                                                                  shuffle_batches=shuffle, exec_mode=mode, **kw),
+                                     g, state_fn=shop_state).close()
+                ok = True
+            except Exception as exc:
+                ok = False
+                print("MISMATCH chain2", c, n_shops, n_cust, rates, shuffle, mode, type(exc).__name__, str(exc)[:200], flush=True)
+            report["chain2"].append((c, n_shops, n_cust, mode, ok))
     bad = {k: [x for x in v if not x[-1]] for k, v in report.items()}
-    print(json.dumps({"ads_runs": len(report["ads"]), "market_runs": len(report["market"]), "mismatches": bad}))
+    print(json.dumps({"ads_runs": len(report["ads"]), "market_runs": len(report["market"]),
+                      "chain2_runs": len(report["chain2"]), "mismatches": bad}))
 
 
 if __name__ == "__main__":

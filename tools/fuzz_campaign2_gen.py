@@ -21,6 +21,8 @@ def main():
     ap.add_argument("--out", default=os.path.join(REPO, "tests", "_campaign"))
     ap.add_argument("--count", type=int, default=30)
     ap.add_argument("--first", type=int, default=0)
+    ap.add_argument("--small-budgets", action="store_true",
+                    help="budgets of 0.3 .. 2.5: most advertisers run out of money and terminate mid-episode")
     a = ap.parse_args()
     from oracle import harness
     from oracle.make_golden import pack_generic
@@ -32,13 +34,13 @@ def main():
         big = r.uniform() < 0.4
         counts = [int(r.randint(1, 41 if big else 11)) for _ in range(3)]
         strategy = "first" if r.uniform() < 0.5 else "second"
-        T = int(r.randint(4, 15))
+        T = int(r.randint(8, 21) if a.small_budgets else r.randint(4, 15))
         n_env, n_ep, seed = 2, 2, 30000 + c
         theme = {"travel": counts[0], "tech": counts[1], "sport": counts[2]}
         budgets = []
         for n in counts:
-            lo = float(np.round(r.uniform(1.0, 12.0), 2))
-            hi = float(np.round(lo + r.uniform(0.5, 10.0), 2))
+            lo = float(np.round(r.uniform(0.3, 1.5) if a.small_budgets else r.uniform(1.0, 12.0), 2))
+            hi = float(np.round(lo + (r.uniform(0.1, 1.0) if a.small_budgets else r.uniform(0.5, 10.0)), 2))
             budgets += [(lo, hi, lo, float(np.round(hi - r.uniform(0.0, 0.4), 2)))] * n
         S = sum(counts)
         actions, mask = wl.actions_for(n_env, n_ep, T, S, seed % 1000)
