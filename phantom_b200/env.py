@@ -263,8 +263,11 @@ class PhantomEnv:
         self._ensure_handle()
         if self._out is None:
             self._out = self._alloc_outputs(())
-        if env_mask is not None:
-            env_mask = env_mask.to(device=self._out.observations.device, dtype=torch.uint8).contiguous()
+        if env_mask is not None:  # (a tensor or anything array-like)
+            env_mask = torch.as_tensor(env_mask).to(device=self._out.observations.device,
+                                                    dtype=torch.uint8).contiguous()
+            if env_mask.numel() != self.num_envs:
+                raise ValueError(f"env_mask must have {self.num_envs} entries")
         self._out.obs_mask.zero_()
         L.check(L.lib.phx_reset(self._handle, self._ptr(env_mask),
                                 self._out.observations.data_ptr(),
