@@ -291,6 +291,11 @@ __device__ __forceinline__ void engine1_step_body(const EngineArgs<P>& a) {
     const uint32_t done = term | trunc;  // agents without a context this step (env.py:344-348)
     int st[P::NWORDS > 0 ? P::NWORDS : 1];
     prefetch_actions(t + 1);
+    // This step's actions (issued one step ago) have landed.  The wait is unconditional: a step
+    // in which no strategic agent acts (a stage of other agents, everybody done) used to skip it,
+    // which left two copies into the same ring slot formally in flight (racecheck: "invalid
+    // memcpy_async synchronization").
+    cp_async_wait<1>();
     if constexpr (EW > 0) {  // the EnvView of this step (env.py:340)
 #pragma unroll
       for (int w = 0; w < EW; ++w) envsnap[w] = envw[w];
@@ -356,7 +361,6 @@ __device__ __forceinline__ void engine1_step_body(const EngineArgs<P>& a) {
           for (int j = 0; j < P::ACT_DIM; ++j) act[j] = 0.f;
           if (sidx >= 0) {
             has_action = a.io.action_mask ? a.io.action_mask[row * S + sidx] != 0 : true;
-            cp_async_wait<1>();  // this step's actions (issued one step ago) have landed
 #pragma unroll
             for (int j = 0; j < P::ACT_DIM; ++j) act[j] = ACT(t & 1, sidx, j);
           }
@@ -444,7 +448,6 @@ __device__ __forceinline__ void engine1_step_body(const EngineArgs<P>& a) {
       for (int j = 0; j < P::ACT_DIM; ++j) act[j] = 0.f;
       if (sidx >= 0) {
         has_action = a.io.action_mask ? a.io.action_mask[row * S + sidx] != 0 : true;
-        cp_async_wait<1>();  // this step's actions (issued one step ago) have landed
 #pragma unroll
         for (int j = 0; j < P::ACT_DIM; ++j) act[j] = ACT(t & 1, sidx, j);
       }
