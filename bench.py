@@ -92,12 +92,15 @@ def make_env(name, **kw):
 
 
 # ------------------------------------------------------------------------------ helpers
-def ncu_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the bench kernel, from the
-    committed ncu --set full capture (profiles/traffic.json names the source file)."""
+def ncu_traffic(config=None):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the bench kernel (or of the
+    kernel of sub-config `config`), from the committed ncu --set full capture
+    (profiles/traffic.json names the source file).  (None, None) if there is no capture."""
     try:
         with open(os.path.join(REPO, "profiles", "traffic.json")) as f:
             t = json.load(f)
+        if config is not None:
+            t = t["configs"][config]
         return int(t["dram_bytes_read"]) + int(t["dram_bytes_write"]), t["source"]
     except Exception:
         return None, None
@@ -473,6 +476,8 @@ def config_record(name, rec, world, peak, peak_src, with_cpu, args):
                      "algorithmic_bytes_per_env_step": c["b_io"] + c["b_state"] / T,
                      "peak_source": peak_src},
     }
+    if name != "C2" and world == 1 and E == c["E"]:  # (a capture of the full-size one-GPU launch)
+        out["roofline"]["traffic"], out["roofline"]["traffic_source"] = ncu_traffic(name)
     if "e2e_s" in rec:
         e2e_value = world * E * T * rec["e2e_steps"] / rec["e2e_s"]
         out["e2e"] = {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": rec["h2d"],
