@@ -348,6 +348,7 @@ FSM_HANDLER_FUZZ_CASES = 40
 FSM_WIDE_FUZZ_CASES = 16
 FSM_FLOAT_FUZZ_CASES = 32
 FSM_WAITING_FUZZ_CASES = 40
+MOCK_ENV_FUZZ_CASES = 60
 FSM_ORDER_FUZZ_SEEDS = (1103, 1308, 1334, 1732, 1734, 2051, 2484, 2509, 2614, 2937, 2948, 3054, 3380)
 
 
@@ -397,6 +398,14 @@ def gen_fsm_handler_fuzz_reference() -> None:
         json.dump(out, f, separators=(",", ":"))
     raised = sorted(int(s) for s, t in out.items() if t[-1][0] == "raise")
     print("fsm_waiting_fuzz_reference.json", len(out), "cases; raising:", raised)
+    # random PhantomEnv / StackelbergEnv env classes (message traces, round limits, bad edges,
+    # shuffled batches under the contract shuffle): tests/kat_scenarios.py:run_mock_env
+    out = {str(s): kats.run_mock_env(K, s) for s in range(MOCK_ENV_FUZZ_CASES)}
+    with open(os.path.join(GOLDEN, "mock_env_fuzz_reference.json"), "w") as f:
+        json.dump(out, f, separators=(",", ":"))
+    raised = sorted(int(s) for s, t in out.items() if t[-1][0] == "raise")
+    print("mock_env_fuzz_reference.json", len(out), "cases; raising:", raised,
+          "shuffled:", sum(bool(t[0][1]) for t in out.values()))
     # ... and on env classes wider than a warp (33..120 agents): the block engine's fixture
     out = {str(s): kats.run_random_handler_fsm(K, s, wide=True) for s in range(FSM_WIDE_FUZZ_CASES)}
     with open(os.path.join(GOLDEN, "fsm_wide_fuzz_reference.json"), "w") as f:

@@ -713,3 +713,100 @@ def run_random_handler_fsm(K, case_seed, compound=False, prepare=None, wide=Fals
     if hasattr(env, "close"):
         env.close()
     return trace
+
+
+# ---- random PhantomEnv / StackelbergEnv env classes over the mock agents (differential fuzz of the
+# base and Stackelberg step loops incl. message tracking, round limits, bad edges and shuffled
+# batches; tools/fuzz_campaign3.py ran thousands of them, a fixture of the unmodified reference
+# pins 60: tests/golden/mock_env_fuzz_reference.json)
+def random_mock_env(K, case_seed, **kw):
+    r = np.random.RandomState(50000 + case_seed)
+    ph = K.ph
+    strat = [f"s{i}" for i in range(int(r.randint(1, 4)))]
+    echo = [f"e{i}" for i in range(int(r.randint(1, 5)))]
+    agents = [K.MockStrategicAgent(a, num_steps=(int(r.randint(1, 7)) if r.uniform() < 0.3 else None))
+              for a in strat]
+    agents += [K.EchoAgent(e, seed_value=int(r.choice([0, 0, 3, 4, 9, 17])),
+                           request_response=bool(r.uniform() < 0.3)) for e in echo]
+    agents = [agents[i] for i in r.permutation(len(agents))]
+    round_limit = None if r.uniform() < 0.6 else int(r.randint(1, 5))
+    shuffle = bool(r.uniform() < 0.35)  # BatchResolver(shuffle_batches=True): the contract's Fisher-Yates
+    network = ph.Network(agents, ph.resolvers.BatchResolver(enable_tracking=True, round_limit=round_limit,
+                                                            shuffle_batches=shuffle),
+                         ignore_connection_errors=bool(r.uniform() < 0.3))
+    for i in range(len(echo)):
+        for j in range(i + 1, len(echo)):
+            if r.uniform() < 0.6:
+                network.add_connection(echo[i], echo[j])
+    if r.uniform() < 0.15:  # an echo agent next to a strategic one: no handler there (ValueError)
+        network.add_connection(echo[0], strat[0])
+    kind = "stackelberg" if r.uniform() < 0.5 else "base"
+    net = K.finish_network(network)
+    if kind == "base":
+        env = ph.PhantomEnv(num_steps=8, network=net, **kw)
+    else:
+        everyone = list(r.permutation(strat + echo))
+        cut = int(r.randint(1, len(everyone)))
+        env = ph.StackelbergEnv(8, net, [str(x) for x in everyone[:cut]], [str(x) for x in everyone[cut:]], **kw)
+    return env, strat, echo, shuffle
+
+
+def run_mock_env(K, case_seed):
+    """Steps one random env class to the end of its episode (or its first exception) and returns a
+    plain-Python trace: observations, rewards, done flags, call counters, float32 levels and the
+    tracked message list of every step.  The oracle / reference side shuffles batches with the
+    contract's Fisher-Yates (oracle/harness.py patched_np_shuffle)."""
+    import contextlib
+
+    seed = 77 + case_seed
+    is_device = hasattr(K.ph.PhantomEnv, "default_exec_mode")
+    env, strat, echo, shuffle = random_mock_env(K, case_seed, **({"seed": seed} if is_device else {}))
+    clock, patch = None, contextlib.nullcontext()
+    if not is_device:  # the oracle / reference: np.random.shuffle -> the contract's shuffle
+        from oracle import harness
+
+        clock = harness.EpisodeClock([])
+        slot_of = {aid: i for i, aid in enumerate(env.agent_ids)}
+        patch = harness.patched_np_shuffle(seed, 0, clock, env, slot_of)
+
+    def plain(d):
+        return {k: (None if v is None else
+                    [round(float(x), 6) for x in np.asarray(v, np.float64).reshape(-1)])
+                for k, v in d.items()}
+
+    def msgs():
+        out = []
+        for m in env.network.resolver.tracked_messages:
+            p = m.payload
+            out.append([str(m.sender_id), str(m.receiver_id), type(p).__name__,
+                        int(getattr(p, "value", getattr(p, "cash", 0)))])
+        return out
+
+    trace = [("shuffle", shuffle)]
+    try:
+      with patch:
+        if clock is not None:
+            clock.on_reset()
+        obs, _ = env.reset()
+        trace.append(("reset", plain(obs)))
+        for t in range(8):
+            env.network.resolver.clear_tracked_messages()
+            if clock is not None:
+                clock.on_step(env)
+            step = env.step({a: np.array([0]) for a in strat})
+            trace.append((
+                "step", plain(step.observations), plain(step.rewards),
+                {k: bool(v) for k, v in step.terminations.items()},
+                {k: bool(v) for k, v in step.truncations.items()},
+                [list(map(int, counts(env.agents[a]))) for a in strat],
+                [[int(env.agents[e].handled_count), int(env.agents[e].handled_total),
+                  float(env.agents[e].level)] for e in echo], msgs()))
+            if step.terminations["__all__"] or step.truncations["__all__"]:
+                break
+    except Exception as exc:
+        trace.append(("raise", type(exc).__name__))
+    if hasattr(env, "close"):
+        env.close()
+    return trace
+
+

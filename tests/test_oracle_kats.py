@@ -92,3 +92,22 @@ def test_random_handler_fsms_match_the_reference(K):
     for s in range(len(want)):
         got = json.loads(json.dumps(kats.run_random_handler_fsm(K, s, wide=True)))
         assert got == want[str(s)], f"wide case seed {s}"
+
+
+def test_random_base_and_stackelberg_envs_match_the_reference(K):
+    """60 random PhantomEnv / StackelbergEnv env classes over the mock agents (halving and
+    request / response echoes, random graphs, ignore_connection_errors, round limits, receivers
+    without a handler, agents terminating mid-episode, leader / follower lists in random order,
+    shuffled batches) on the oracle port == the traces of the UNMODIFIED reference, message lists
+    and exception types included (tests/golden/mock_env_fuzz_reference.json)."""
+    import json
+    import os
+
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden",
+                        "mock_env_fuzz_reference.json")
+    want = json.load(open(path))
+    assert len(want) == 60 and sum(t[-1][0] == "raise" for t in want.values()) >= 3
+    assert sum(bool(t[0][1]) for t in want.values()) >= 10  # shuffled cases
+    for s in range(len(want)):
+        got = json.loads(json.dumps(kats.run_mock_env(K, s)))
+        assert got == want[str(s)], f"case seed {s}"
