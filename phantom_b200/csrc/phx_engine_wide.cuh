@@ -9,17 +9,23 @@
 //     per-env sets (done agents, cached rewards / observations) in shared memory, one word per
 //     warp: warp w's ballot IS word w, so a set is updated without atomics.
 //   * tile collectives become block collectives: a ballot / REDUX per warp, four partial
-//     results in shared memory, one __syncthreads.  A resolver round costs three barriers.
+//     results in shared memory, one __syncthreads.
 // The queue is the segmented queue of the tile engine (a segment per producing agent, read in
 // first-arrival order, see phx_engine.cuh), with segment capacities taken from the lowered env
 // class at launch (P::wide_act_cap / wide_resp_cap, or the agent's degree), so that an exchange
-// that answers 120 bidders sits next to 120 agents that send one message.
+// that answers 120 bidders sits next to 120 agents that send one message.  A resolver round
+// (wide_round): (1) the block flattens the queue into push order (a block scan of the segment
+// lengths, a cooperative copy), (2) every receiver lane scans that copy and handles its batch
+// (shuffle_batches: per-receiver lists from a second block scan, Fisher-Yates in place), (3) the
+// next queue's segment order = the marked first-arrival positions, compacted by ballots.  Seven
+// to nine block barriers per round; what dominates is a hub agent's serial batch (barrier stall).
 // A program takes part by being a template over its context type (fam_mock.cu,
 // fam_digital_ads.cu: `template <class C> ... const C& c`) and never touching a raw mask:
 // WCtx offers has_neighbour / next_neighbour / next_of_kind like Ctx does.
 // Env-level words (ENVW / env_post, see phx_engine.cuh) are kept by every lane; env_post reads
 // other agents' state through a copy of all state words in shared memory.
-// Not carried over: the collective resolve hook and run-time specialisation.
+// Not carried over: the collective resolve hook, run-time specialisation, waiting mail (a stage
+// handler that does not resolve faults with PHX_FAULT_UNRESOLVED_MAIL, as on the tile engine).
 #pragma once
 #include <cstddef>
 
