@@ -62,8 +62,10 @@ typedef enum phx_fault {
   PHX_FAULT_INVALID_ACTION = 7,   /* non-finite / out-of-contract action value
                                      (ValueError/OverflowError from int(round(a)))     */
   PHX_FAULT_UNRESOLVED_MAIL = 8,  /* a stage handler that does not call resolve_network()
-                                     left messages queued: the reference would carry them
-                                     into a later step's resolve; the device does not     */
+                                     left messages queued: the reference carries them into
+                                     a later step's resolve; so does the thread-per-env
+                                     engine (<= 8 agents), the tile and block engines
+                                     refuse with this fault                              */
   PHX_FAULT_PLAN_MISMATCH = 9     /* a step kernel specialised with a STATIC message schedule
                                      (phx_jit_source) saw a send its device program did not
                                      declare: the program's act_sends / handle_sends signature

@@ -58,8 +58,8 @@ def _fault_exception(code: int, env_index: int) -> Exception:
         L.FAULT_QUEUE_OVERFLOW: RuntimeError("device message queue capacity exceeded." + where),
         L.FAULT_INVALID_ACTION: ValueError("action is non-finite or outside the contract." + where),
         L.FAULT_UNRESOLVED_MAIL: RuntimeError(
-            "an FSM stage handler left messages unresolved; the device does not carry mail "
-            "into a later step." + where),
+            "an FSM stage handler left messages unresolved; only the thread-per-env engine "
+            "(env classes of <= 8 agents) carries mail into a later step." + where),
         L.FAULT_PLAN_MISMATCH: RuntimeError(
             "a statically scheduled step kernel saw a send its device program did not declare "
             "(act_sends / handle_sends); re-create the env without specialise()." + where),
