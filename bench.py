@@ -106,6 +106,20 @@ def ncu_traffic(config=None):
         return None, None
 
 
+def pcie_ceiling(n_gpus, e2e_value):
+    """The measured N-rank host-copy ceiling of the e2e path (profiles/pcie_nrank.json: every rank
+    moves a launch's 118 MB out / 26 MB in, all ranks at once) and the e2e figure as a fraction
+    of it.  {} if no measurement for this N is committed."""
+    try:
+        with open(os.path.join(REPO, "profiles", "pcie_nrank.json")) as f:
+            t = json.load(f)
+        ceil = float(t["per_n"][str(int(n_gpus))]["e2e_ceiling_env_steps_per_s"])
+        return {"ceiling": ceil, "frac_of_ceiling": float(e2e_value) / ceil,
+                "ceiling_source": t["source"]}
+    except Exception:
+        return {}
+
+
 def port_calibration():
     """port speed / unmodified-reference speed, measured where both can run (the build
     container; tools/calibrate_port.py)."""
@@ -722,7 +736,8 @@ def run_ours(args):
             "e2e": dict(c2["e2e"], bound="pcie / host expansion",
                         d2h_GBps_per_gpu=c2["e2e"]["d2h_bytes_per_step"] * c2["e2e"]["value"] /
                         (world * E * T) / 1e9,
-                        host_threads=int(os.environ.get("PHX_HOST_THREADS", "1"))),
+                        host_threads=int(os.environ.get("PHX_HOST_THREADS", "1")),
+                        **pcie_ceiling(world, c2["e2e"]["value"])),
             "single_step": single,
             "full_io": None if full_io is None else dict(
                 full_io, frac=full_io["achieved_GBps"] / peak, peak=peak),
